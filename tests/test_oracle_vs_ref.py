@@ -1,0 +1,45 @@
+"""CPU: live comparison of the oracle restatement with the UNMODIFIED reference compiled as oracle/_ref/*.so
+(built by oracle/Makefile where /root/reference exists; the prebuilt .so files travel to the GPU box)."""
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+
+pytestmark = pytest.mark.skipif(not O.have_ref(), reason="oracle/_ref not built (needs /root/reference)")
+
+
+def _clouds(rng, n):
+    yield "uniform", rng.random((n, 3), dtype=np.float32)
+    yield "quantised", (np.round(rng.random((n, 3)) * [300, 300, 2]) / 100).astype(np.float32)
+    yield "duplicates", rng.random((n // 8, 3), dtype=np.float32)[rng.integers(0, n // 8, n)]
+    yield "collinear", np.stack([rng.random(n), np.zeros(n), np.zeros(n)], 1).astype(np.float32)
+    yield "identical", np.ones((n, 3), np.float32)
+
+
+@pytest.mark.parametrize("K", [1, 16])
+def test_knn_live(K):
+    rng = np.random.default_rng(5)
+    for name, p in _clouds(rng, 6000):
+        assert np.array_equal(O.knn(p, p, K, threads=4), O.ref_knn(p, p, K, omp=True)), name
+
+
+def test_knn_batch_live():
+    rng = np.random.default_rng(6)
+    P = rng.random((4, 3000, 3), dtype=np.float32)
+    assert np.array_equal(O.knn_batch(P, P, 16, threads=4), O.ref_knn_batch(P, P, 16, omp=True))
+    Q = np.ascontiguousarray(P[:, :750])
+    assert np.array_equal(O.knn_batch(Q, P, 1, threads=4), O.ref_knn_batch(Q, P, 1, omp=False))
+
+
+@pytest.mark.parametrize("dl", [0.04, 0.11])
+def test_grid_live(dl):
+    rng = np.random.default_rng(7)
+    n = 60000
+    p = (rng.random((n, 3)) * [7, 5, 3]).astype(np.float32)
+    p[: n // 2, 2] = 0  # a dense floor
+    rgb = rng.integers(0, 256, (n, 3)).astype(np.uint8)
+    lab = rng.integers(0, 13, n).astype(np.uint8)
+    a = O.grid_subsample(p, rgb, lab, dl)
+    b = O.ref_grid_subsample(p, rgb, lab, dl)
+    for x, y in zip(a, b):
+        assert x.tobytes() == y.tobytes()
