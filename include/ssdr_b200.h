@@ -1,0 +1,139 @@
+/*
+ * ssdr_b200.h -- C ABI of libssdr_b200.so: the B200-native (sm_100a) drop-in for SSDR-AL's data-parallel
+ * point-cloud hot path.  Plain pointers and sizes only; no torch / numpy / C++ types cross this boundary.
+ *
+ * Reference interfaces replaced (paths relative to SSDR_AL_s3dis/ of shaofeifei11/SSDR-AL):
+ *   ssdr_knn, ssdr_knn_batch         <- cpp_knn / cpp_knn_omp / cpp_knn_batch / cpp_knn_batch_omp
+ *                                       utils/nearest_neighbors/knn_.h:2-17 (bound by knn.pyx:8-23)
+ *   ssdr_grid_subsample/_fetch/_free <- grid_subsampling()
+ *                                       utils/cpp_wrappers/cpp_subsampling/grid_subsampling/grid_subsampling.h:84-91
+ *                                       (bound by wrapper.cpp:58-286)
+ *   ssdr_fps_f32 / ssdr_fps_f64      <- farthest_features_sample()        fps_gcn_cpu.py:119-147
+ *   ssdr_kcenter_f32 / _f64          <- kCenterGreedy.select_batch_()     kcenterGreedy.py:84-128
+ *
+ * Conventions
+ *   - Every function returns 0 (SSDR_OK) or a non-zero ssdr_status; ssdr_last_error() then returns a
+ *     thread-local, NUL-terminated message.  Nothing throws, nothing aborts.
+ *   - "host" entry points borrow caller-owned host buffers (row-major, C-contiguous) for the duration of the
+ *     call and write caller-allocated outputs -- the same ownership rule as the reference prototypes.
+ *   - "_dev" entry points take device pointers on the current device plus a cudaStream_t passed as void*
+ *     (NULL = the library's per-thread stream); they enqueue work and do not synchronise unless documented.
+ *   - The library is re-entrant per calling thread (per-thread stream + workspace).  It refuses to run in a
+ *     fork()ed child of a process that already initialised it (SSDR_ERR_FORK) instead of hanging.
+ *   - There is no CPU fallback: without a CUDA device every compute entry point fails with SSDR_ERR_CUDA.
+ */
+#ifndef SSDR_B200_H
+#define SSDR_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+    SSDR_OK = 0,
+    SSDR_ERR_INVALID = 1,     /* bad argument (NULL pointer, dim != 3, ...) */
+    SSDR_ERR_CUDA = 2,        /* CUDA runtime error or no device */
+    SSDR_ERR_NOMEM = 3,       /* device or host allocation failed */
+    SSDR_ERR_UNSUPPORTED = 4, /* valid in the reference but outside this implementation's documented limits */
+    SSDR_ERR_FORK = 5,        /* called from a fork()ed child after CUDA initialisation in the parent */
+    SSDR_ERR_EMPTY = 6        /* grid subsampling produced no point (reference: RuntimeError("Error")) */
+} ssdr_status;
+
+/* ---- runtime ------------------------------------------------------------------------------------ */
+const char* ssdr_last_error(void);
+int ssdr_version(void);               /* major*10000 + minor*100 + patch */
+int ssdr_device_count(int* count);    /* number of visible CUDA devices */
+int ssdr_set_device(int device);      /* device used by the calling thread's subsequent calls */
+int ssdr_get_device(int* device);
+int ssdr_device_sm_count(int* sms);
+int ssdr_synchronize(void);           /* wait for the calling thread's library stream */
+/* Pinned host memory helpers (optional; host entry points accept any host pointer but copy fastest from these). */
+int ssdr_host_alloc(void** ptr, size_t bytes);
+int ssdr_host_free(void* ptr);
+
+/* ---- KNN ----------------------------------------------------------------------------------------- */
+/* Exact K nearest neighbours with nanoflann-identical results (indices ascending by fp32 squared distance,
+ * equal distances in nanoflann's tree-visit order).  dim must be 3.  If K > npts only the first npts slots
+ * of each output row are written (the reference leaves the rest at the caller's zero initialisation). */
+int ssdr_knn(const float* points, size_t npts, size_t dim, const float* queries, size_t nqueries, size_t K,
+             int64_t* indices /* (nqueries, K) */);
+int ssdr_knn_batch(const float* batch_data /* (B, npts, dim) */, size_t batch_size, size_t npts, size_t dim,
+                   const float* queries /* (B, nqueries, dim) */, size_t nqueries, size_t K,
+                   int64_t* batch_indices /* (B, nqueries, K) */);
+
+typedef struct {
+    uint64_t queries;         /* rows processed */
+    uint64_t tie_rows;        /* rows whose top-(K+1) held an exact or near fp32 distance tie (re-resolved) */
+    uint64_t tree_builds;     /* nanoflann-identical trees built on device for those rows */
+    uint64_t dist_evals;      /* candidate distance evaluations of the main kernel */
+} ssdr_knn_stats;
+
+/* Device-resident variant: d_points (B,npts,3), d_queries (B,nqueries,3), d_indices (B,nqueries,K) int64.
+ * Enqueues on `stream`; stats (nullable, host struct) forces a stream synchronisation when requested. */
+int ssdr_knn_batch_dev(const float* d_points, size_t batch_size, size_t npts, const float* d_queries,
+                       size_t nqueries, size_t K, int64_t* d_indices, void* stream, ssdr_knn_stats* stats);
+/* int32 output flavour for callers that feed TF int32 tensors (helper_tool.py:183 casts anyway). */
+int ssdr_knn_batch_dev_i32(const float* d_points, size_t batch_size, size_t npts, const float* d_queries,
+                           size_t nqueries, size_t K, int32_t* d_indices, void* stream, ssdr_knn_stats* stats);
+
+/* ---- grid subsampling ------------------------------------------------------------------------------ */
+#define SSDR_GRID_ORDER_KEY 0       /* rows in ascending voxel key (canonical, deterministic) */
+#define SSDR_GRID_ORDER_REFERENCE 1 /* rows in the reference's libstdc++ hash-iteration order */
+
+/* Phase 1: run on the device, learn M.  feats / classes nullable (then fdim / ldim ignored).
+ * Phase 2: ssdr_grid_fetch copies the M rows into caller-allocated host arrays (nullable each).
+ * keys_out / counts_out are extras (voxel key, points per voxel) for diagnostics and tests. */
+int ssdr_grid_subsample(const float* points /* (N,3) */, const float* feats /* (N,fdim) */,
+                        const int32_t* classes /* (N,ldim) */, size_t N, size_t fdim, size_t ldim, float sampleDl,
+                        int order, size_t* M_out, void** handle);
+int ssdr_grid_fetch(void* handle, float* points_out, float* feats_out, int32_t* classes_out);
+int ssdr_grid_fetch_ex(void* handle, float* points_out, float* feats_out, int32_t* classes_out,
+                       uint64_t* keys_out, int32_t* counts_out);
+int ssdr_grid_free(void* handle);
+
+/* Device-resident variant: inputs are device pointers; results stay on the device inside the handle and can be
+ * read back with ssdr_grid_fetch or borrowed with ssdr_grid_dev_ptrs (valid until ssdr_grid_free). */
+int ssdr_grid_subsample_dev(const float* d_points, const float* d_feats, const int32_t* d_classes, size_t N,
+                            size_t fdim, size_t ldim, float sampleDl, int order, void* stream, size_t* M_out,
+                            void** handle);
+int ssdr_grid_dev_ptrs(void* handle, const float** d_points, const float** d_feats, const int32_t** d_classes);
+
+/* ---- farthest-feature sampling / k-center greedy ---------------------------------------------------- */
+/* FPS: out[0] = first; out[s+1] = argmax_i min_{t<=s} sum_j (F[i,j]-F[out[t],j])^2, first index on ties,
+ * distances in the input dtype with numpy's pairwise summation order (bit-exact picks). */
+int ssdr_fps_f32(const float* F, size_t N, size_t D, int32_t first, size_t n_samples, int32_t* out);
+int ssdr_fps_f64(const double* F, size_t N, size_t D, int32_t first, size_t n_samples, int32_t* out);
+int ssdr_fps_f32_dev(const float* d_F, size_t N, size_t D, int32_t first, size_t n_samples, int32_t* d_out,
+                     void* stream);
+int ssdr_fps_f64_dev(const double* d_F, size_t N, size_t D, int32_t first, size_t n_samples, int32_t* d_out,
+                     void* stream);
+
+/* k-center greedy with sklearn's euclidean distance (sqrt(max(0,|x|^2+|c|^2-2x.c)) accumulated in float64,
+ * rounded to the input dtype).  selected: n_sel indices already chosen; out: n_pick new indices. */
+int ssdr_kcenter_f32(const float* X, size_t N, size_t D, const int64_t* selected, size_t n_sel, size_t n_pick,
+                     int64_t* out);
+int ssdr_kcenter_f64(const double* X, size_t N, size_t D, const int64_t* selected, size_t n_sel, size_t n_pick,
+                     int64_t* out);
+int ssdr_kcenter_f32_dev(const float* d_X, size_t N, size_t D, const int64_t* d_selected, size_t n_sel,
+                         size_t n_pick, int64_t* d_out, void* stream);
+int ssdr_kcenter_f64_dev(const double* d_X, size_t N, size_t D, const int64_t* d_selected, size_t n_sel,
+                         size_t n_pick, int64_t* d_out, void* stream);
+
+/* Row-sharded multi-GPU selection (one process per GPU).  Every rank holds the FULL matrix d_F (so the chosen
+ * centre row is local) but scans only rows [row_begin,row_end); after each step the packed (distance, index)
+ * candidates are combined across ranks by an 8-byte max all-reduce over NCCL.  `nccl_comm` is an ncclComm_t.
+ * All ranks receive identical picks. */
+int ssdr_fps_f32_sharded(const float* d_F, size_t N, size_t D, size_t row_begin, size_t row_end, int32_t first,
+                         size_t n_samples, int32_t* d_out, void* nccl_comm, void* stream);
+/* NCCL bootstrap helpers so the host side can create the communicator without linking NCCL itself. */
+int ssdr_nccl_unique_id(void* id128 /* 128 bytes */);
+int ssdr_nccl_comm_init(void** comm, int nranks, const void* id128, int rank);
+int ssdr_nccl_comm_destroy(void* comm);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SSDR_B200_H */

@@ -1,0 +1,112 @@
+"""ctypes binding of libssdr_b200.so (the C ABI declared in include/ssdr_b200.h)."""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libssdr_b200.so")
+_lib = None
+
+f32p = C.POINTER(C.c_float)
+f64p = C.POINTER(C.c_double)
+i32p = C.POINTER(C.c_int32)
+i64p = C.POINTER(C.c_int64)
+u64p = C.POINTER(C.c_uint64)
+sz = C.c_size_t
+vp = C.c_void_p
+
+
+class KnnStats(C.Structure):
+    _fields_ = [("queries", C.c_uint64), ("tie_rows", C.c_uint64), ("tree_builds", C.c_uint64),
+                ("dist_evals", C.c_uint64)]
+
+
+# name -> argtypes (every function returns int status unless listed in _RESTYPE)
+SIGNATURES = {
+    "ssdr_last_error": [],
+    "ssdr_version": [],
+    "ssdr_device_count": [C.POINTER(C.c_int)],
+    "ssdr_set_device": [C.c_int],
+    "ssdr_get_device": [C.POINTER(C.c_int)],
+    "ssdr_device_sm_count": [C.POINTER(C.c_int)],
+    "ssdr_synchronize": [],
+    "ssdr_host_alloc": [C.POINTER(vp), sz],
+    "ssdr_host_free": [vp],
+    "ssdr_knn": [vp, sz, sz, vp, sz, sz, vp],
+    "ssdr_knn_batch": [vp, sz, sz, sz, vp, sz, sz, vp],
+    "ssdr_knn_batch_dev": [vp, sz, sz, vp, sz, sz, vp, vp, C.POINTER(KnnStats)],
+    "ssdr_knn_batch_dev_i32": [vp, sz, sz, vp, sz, sz, vp, vp, C.POINTER(KnnStats)],
+    "ssdr_grid_subsample": [vp, vp, vp, sz, sz, sz, C.c_float, C.c_int, C.POINTER(sz), C.POINTER(vp)],
+    "ssdr_grid_fetch": [vp, vp, vp, vp],
+    "ssdr_grid_fetch_ex": [vp, vp, vp, vp, vp, vp],
+    "ssdr_grid_free": [vp],
+    "ssdr_grid_subsample_dev": [vp, vp, vp, sz, sz, sz, C.c_float, C.c_int, vp, C.POINTER(sz), C.POINTER(vp)],
+    "ssdr_grid_dev_ptrs": [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)],
+    "ssdr_fps_f32": [vp, sz, sz, C.c_int32, sz, vp],
+    "ssdr_fps_f64": [vp, sz, sz, C.c_int32, sz, vp],
+    "ssdr_fps_f32_dev": [vp, sz, sz, C.c_int32, sz, vp, vp],
+    "ssdr_fps_f64_dev": [vp, sz, sz, C.c_int32, sz, vp, vp],
+    "ssdr_kcenter_f32": [vp, sz, sz, vp, sz, sz, vp],
+    "ssdr_kcenter_f64": [vp, sz, sz, vp, sz, sz, vp],
+    "ssdr_kcenter_f32_dev": [vp, sz, sz, vp, sz, sz, vp, vp],
+    "ssdr_kcenter_f64_dev": [vp, sz, sz, vp, sz, sz, vp, vp],
+    "ssdr_fps_f32_sharded": [vp, sz, sz, sz, sz, C.c_int32, sz, vp, vp, vp],
+    "ssdr_nccl_unique_id": [vp],
+    "ssdr_nccl_comm_init": [C.POINTER(vp), C.c_int, vp, C.c_int],
+    "ssdr_nccl_comm_destroy": [vp],
+}
+_RESTYPE = {"ssdr_last_error": C.c_char_p}
+
+
+def lib():
+    """Load the shared library; fail loudly when it has not been built (no fallback exists)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                "libssdr_b200.so is not built (%s). Run `python -m ssdr_al_b200.build` -- this package has no "
+                "CPU fallback." % LIB_PATH)
+        L = C.CDLL(LIB_PATH)
+        for name, args in SIGNATURES.items():
+            fn = getattr(L, name)
+            fn.argtypes = args
+            fn.restype = _RESTYPE.get(name, C.c_int)
+        _lib = L
+    return _lib
+
+
+def check(status):
+    if status != 0:
+        msg = lib().ssdr_last_error()
+        raise RuntimeError((msg or b"libssdr_b200 error").decode("utf-8", "replace"))
+
+
+def ptr(a):
+    """void* of a numpy array (None -> NULL)."""
+    return None if a is None else a.ctypes.data_as(vp)
+
+
+def device_count():
+    n = C.c_int(0)
+    lib().ssdr_device_count(C.byref(n))
+    return n.value
+
+
+def set_device(i):
+    check(lib().ssdr_set_device(int(i)))
+
+
+def pinned_empty(shape, dtype):
+    """numpy array backed by CUDA pinned host memory (freed when the array is garbage collected)."""
+    dtype = np.dtype(dtype)
+    n = int(np.prod(shape)) * dtype.itemsize
+    p = vp()
+    check(lib().ssdr_host_alloc(C.byref(p), n))
+    buf = (C.c_char * max(n, 1)).from_address(p.value)
+    arr = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+    _PINNED[id(buf)] = (buf, p)
+    return arr
+
+
+_PINNED = {}

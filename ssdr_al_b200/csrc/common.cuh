@@ -1,0 +1,76 @@
+// common.cuh -- runtime plumbing shared by every translation unit of libssdr_b200.so:
+// status/error reporting, per-thread context (stream + grow-only workspaces), fork detection, host<->device staging.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stddef.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/ssdr_b200.h"
+
+namespace ssdr {
+
+// ---- error plumbing ---------------------------------------------------------------------------------
+int set_error(int status, const char* fmt, ...);
+#define SSDR_CHECK_CUDA(expr)                                                                          \
+    do {                                                                                               \
+        cudaError_t _e = (expr);                                                                       \
+        if (_e != cudaSuccess)                                                                         \
+            return ::ssdr::set_error(_e == cudaErrorMemoryAllocation ? SSDR_ERR_NOMEM : SSDR_ERR_CUDA, \
+                                     "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, \
+                                     __LINE__);                                                        \
+    } while (0)
+#define SSDR_TRY(expr)           \
+    do {                         \
+        int _s = (expr);         \
+        if (_s != SSDR_OK) return _s; \
+    } while (0)
+#define SSDR_REQUIRE(cond, status, ...)                         \
+    do {                                                        \
+        if (!(cond)) return ::ssdr::set_error(status, __VA_ARGS__); \
+    } while (0)
+
+// ---- grow-only device / pinned buffers ----------------------------------------------------------------
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    int reserve(size_t bytes);  // keeps contents only if no growth is needed
+    void release();
+    template <typename T>
+    T* as() const { return reinterpret_cast<T*>(p); }
+};
+struct PinBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    int reserve(size_t bytes);
+    void release();
+    template <typename T>
+    T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+enum { WS_SLOTS = 24 };
+
+// One per calling thread and device.
+struct Ctx {
+    int device = -1;
+    int sm_count = 0;
+    int max_smem_optin = 0;
+    cudaStream_t stream = nullptr;  // the library's own stream for host entry points
+    cudaEvent_t ev = nullptr;
+    DevBuf ws[WS_SLOTS];            // workspaces, addressed by the owning module
+    PinBuf pin[4];                  // pinned staging
+};
+
+// Returns the calling thread's context for its current device (creating it on first use).
+int get_ctx(Ctx** out);
+
+// Host -> device copy of `bytes` from an arbitrary host pointer.  Pinned/registered sources go straight to
+// cudaMemcpyAsync; pageable sources are pipelined through two pinned staging chunks.
+int h2d(Ctx* c, void* dst, const void* src, size_t bytes, cudaStream_t s);
+// Device -> host, synchronous on return (the caller's buffer is valid afterwards).
+int d2h_sync(Ctx* c, void* dst, const void* src, size_t bytes, cudaStream_t s);
+
+static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+}  // namespace ssdr

@@ -1,0 +1,500 @@
+// grid.cu -- voxel grid (barycentre) subsampling on sm_100a.
+//
+// Replaces grid_subsampling() (utils/cpp_wrappers/cpp_subsampling/grid_subsampling/grid_subsampling.cpp:5-106),
+// a single-threaded unordered_map loop, by a sort + segmented sequential reduce that reproduces the reference
+// bit for bit:
+//   1. min/max corners                         (cloud.cpp:27-67)                     -> minmax_kernel
+//   2. origin = floor(min * (1/dl)) * dl, nX, nY (grid_subsampling.cpp:27-31)        -> setup_kernel
+//   3. key = iX + nX*iY + nX*nY*iZ with i* = floor((p-origin)/dl) in IEEE fp32, true division
+//      (grid_subsampling.cpp:53-56)                                                  -> key_kernel
+//   4. STABLE radix sort of (key, input index) over the significant key bits only    -> cub::DeviceRadixSort
+//      (library plumbing; every arithmetic kernel around it is hand written)
+//   5. segment heads -> voxel start offsets, M                                       -> cub::DeviceSelect
+//   6. one thread per voxel walks its points IN INPUT ORDER (the stable sort keeps ascending index inside a
+//      voxel), accumulating fp32 sums exactly like SampledData::update_* (grid_subsampling.h:42-79), then
+//      bary = sum * float(1.0/count), feat = sum / float(count) (grid_subsampling.cpp:87-95) and the label vote
+//      with libstdc++'s unordered_map iteration order as tie-break (grid_subsampling.cpp:97-102)  -> reduce_kernel
+// Rows come out in ascending voxel-key order (SSDR_GRID_ORDER_KEY).
+#include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_select.cuh>
+#include <cub/iterator/counting_input_iterator.cuh>
+
+#include "common.cuh"
+
+namespace ssdr {
+namespace grid {
+
+struct Meta {
+    float mn[3], mx[3];
+    float origin[3];
+    float dl;
+    unsigned long long nX, nY, nZ;
+    int key_bits;
+    int error;  // 1: key space too large, 2: more than LABEL_CAP distinct labels in one voxel
+    unsigned long long M;
+};
+
+enum { WS_META = 0, WS_PART = 1, WS_KEYS = 2, WS_KEYS2 = 3, WS_IDX = 4, WS_IDX2 = 5, WS_TEMP = 6, WS_STARTS = 7,
+       WS_IN_P = 9, WS_IN_F = 10, WS_IN_C = 11 };
+
+constexpr int LABEL_CAP = 64;
+constexpr int MM_BLOCK = 256;
+
+// ---- 1. min / max ------------------------------------------------------------------------------------
+__global__ void minmax_kernel(const float* __restrict__ pts, unsigned long long N, float* __restrict__ partials) {
+    float mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += stride) {
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+            float v = __ldg(pts + 3 * i + d);
+            mn[d] = v < mn[d] ? v : mn[d];
+            mx[d] = v > mx[d] ? v : mx[d];
+        }
+    }
+    __shared__ float s[6][MM_BLOCK / 32];
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+#pragma unroll
+        for (int m = 16; m > 0; m >>= 1) {
+            mn[d] = fminf(mn[d], __shfl_xor_sync(0xffffffffu, mn[d], m));
+            mx[d] = fmaxf(mx[d], __shfl_xor_sync(0xffffffffu, mx[d], m));
+        }
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0)
+        for (int d = 0; d < 3; ++d) {
+            s[d][warp] = mn[d];
+            s[3 + d][warp] = mx[d];
+        }
+    __syncthreads();
+    if (threadIdx.x < 6) {
+        float v = s[threadIdx.x][0];
+        for (int w = 1; w < MM_BLOCK / 32; ++w)
+            v = threadIdx.x < 3 ? fminf(v, s[threadIdx.x][w]) : fmaxf(v, s[threadIdx.x][w]);
+        partials[blockIdx.x * 6 + threadIdx.x] = v;
+    }
+}
+
+// float -> size_t the way x86-64 gcc does it for |v| < 2^63 (truncate to int64, reinterpret)
+__device__ __forceinline__ unsigned long long f2u64(float v) { return (unsigned long long)(long long)v; }
+
+__device__ __forceinline__ int bits_for(unsigned long long n) {  // bits needed to represent values < n
+    int b = 0;
+    while (b < 64 && (n > (1ull << b))) ++b;
+    return b;
+}
+
+// ---- 2. grid geometry ---------------------------------------------------------------------------------
+__global__ void setup_kernel(const float* __restrict__ partials, int nparts, float dl, Meta* meta) {
+    const int t = threadIdx.x;
+    __shared__ float r[6];
+    if (t < 6) {
+        float v = partials[t];
+        for (int b = 1; b < nparts; ++b) v = t < 3 ? fminf(v, partials[b * 6 + t]) : fmaxf(v, partials[b * 6 + t]);
+        r[t] = v;
+    }
+    __syncthreads();
+    if (t == 0) {
+        Meta m;
+        const float inv = __fdiv_rn(1.0f, dl);
+        for (int d = 0; d < 3; ++d) {
+            m.mn[d] = r[d];
+            m.mx[d] = r[3 + d];
+            m.origin[d] = __fmul_rn(floorf(__fmul_rn(r[d], inv)), dl);
+        }
+        m.dl = dl;
+        m.nX = f2u64(floorf(__fdiv_rn(__fsub_rn(m.mx[0], m.origin[0]), dl))) + 1ull;
+        m.nY = f2u64(floorf(__fdiv_rn(__fsub_rn(m.mx[1], m.origin[1]), dl))) + 1ull;
+        m.nZ = f2u64(floorf(__fdiv_rn(__fsub_rn(m.mx[2], m.origin[2]), dl))) + 1ull;
+        // the largest key is bounded by nX*nY*nZ (+ slack for a point one cell below the origin through rounding)
+        const int bx = bits_for(m.nX + 1), by = bits_for(m.nY + 1), bz = bits_for(m.nZ + 1);
+        m.error = 0;
+        m.key_bits = bx + by + bz;
+        if (m.key_bits > 62 || !(dl > 0.0f)) m.error = 1;
+        m.M = 0;
+        *meta = m;
+    }
+}
+
+// ---- 3. voxel keys --------------------------------------------------------------------------------------
+template <typename KeyT>
+__global__ void key_kernel(const float* __restrict__ pts, unsigned long long N, const Meta* __restrict__ meta,
+                           KeyT* __restrict__ keys, unsigned* __restrict__ idx) {
+    const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    const float dl = meta->dl;
+    const unsigned long long iX = f2u64(floorf(__fdiv_rn(__fsub_rn(__ldg(pts + 3 * i + 0), meta->origin[0]), dl)));
+    const unsigned long long iY = f2u64(floorf(__fdiv_rn(__fsub_rn(__ldg(pts + 3 * i + 1), meta->origin[1]), dl)));
+    const unsigned long long iZ = f2u64(floorf(__fdiv_rn(__fsub_rn(__ldg(pts + 3 * i + 2), meta->origin[2]), dl)));
+    const unsigned long long key = iX + meta->nX * iY + meta->nX * meta->nY * iZ;
+    keys[i] = (KeyT)key;
+    idx[i] = (unsigned)i;
+}
+
+template <typename KeyT>
+struct HeadPred {
+    const KeyT* keys;
+    __device__ __forceinline__ bool operator()(const unsigned& i) const { return i == 0 || keys[i] != keys[i - 1]; }
+};
+
+// ---- label vote: libstdc++ unordered_map<int,int> iteration order (identity hash, unique keys) ----------
+// Faithful emulation of _M_insert_unique_node / _M_rehash_aux for up to LABEL_CAP nodes.
+__device__ int label_first_in_iteration_order(const int* labels, const int* counts, int n, int maxcount) {
+    const int NB[5] = {1, 13, 29, 59, 127};
+    short next[LABEL_CAP];
+    short bucket[127];  // node BEFORE the first node of the bucket; -2 = before_begin, -1 = empty
+    int nb = 1, level = 0, head = -1;
+    bucket[0] = -1;
+    for (int id = 0; id < n; ++id) {
+        if (id + 1 > (level == 0 ? 0 : nb)) {  // _Prime_rehash_policy::_M_need_rehash
+            ++level;
+            const int nnb = NB[level];
+            for (int b = 0; b < nnb; ++b) bucket[b] = -1;
+            int p = head, bbegin = 0;
+            head = -1;
+            while (p >= 0) {
+                const int nx = next[p];
+                const int b = (int)((unsigned long long)(long long)labels[p] % (unsigned long long)nnb);
+                if (bucket[b] == -1) {
+                    next[p] = (short)head;
+                    head = p;
+                    bucket[b] = -2;
+                    if (next[p] >= 0) bucket[bbegin] = (short)p;
+                    bbegin = b;
+                } else {
+                    const int before = bucket[b];
+                    if (before == -2) {
+                        next[p] = (short)head;
+                        head = p;
+                    } else {
+                        next[p] = next[before];
+                        next[before] = (short)p;
+                    }
+                }
+                p = nx;
+            }
+            nb = nnb;
+        }
+        const int b = (int)((unsigned long long)(long long)labels[id] % (unsigned long long)nb);
+        if (bucket[b] != -1) {
+            const int before = bucket[b];
+            if (before == -2) {
+                next[id] = (short)head;
+                head = id;
+            } else {
+                next[id] = next[before];
+                next[before] = (short)id;
+            }
+        } else {
+            next[id] = (short)head;
+            head = id;
+            if (next[id] >= 0)
+                bucket[(int)((unsigned long long)(long long)labels[next[id]] % (unsigned long long)nb)] = (short)id;
+            bucket[b] = -2;
+        }
+    }
+    for (int p = head; p >= 0; p = next[p])
+        if (counts[p] == maxcount) return labels[p];
+    return labels[0];
+}
+
+// ---- 6. per-voxel sequential reduce -----------------------------------------------------------------------
+template <typename KeyT, int FD>  // FD = compile-time feature width, -1 = generic (accumulate in the output row)
+__global__ void reduce_kernel(const float* __restrict__ pts, const float* __restrict__ feats,
+                              const int* __restrict__ cls, int fdim, int ldim, const KeyT* __restrict__ keys,
+                              const unsigned* __restrict__ idx, const unsigned* __restrict__ starts,
+                              unsigned long long N, unsigned long long M, float* __restrict__ out_p,
+                              float* __restrict__ out_f, int* __restrict__ out_c,
+                              unsigned long long* __restrict__ out_k, int* __restrict__ out_n, Meta* meta) {
+    const unsigned long long v = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= M) return;
+    const unsigned long long s = starts[v];
+    const unsigned long long e = v + 1 < M ? (unsigned long long)starts[v + 1] : N;
+    float sx = 0.f, sy = 0.f, sz = 0.f;
+    float fs[FD > 0 ? FD : 1];
+#pragma unroll
+    for (int j = 0; j < (FD > 0 ? FD : 1); ++j) fs[j] = 0.f;
+    if (FD < 0)
+        for (int j = 0; j < fdim; ++j) out_f[v * fdim + j] = 0.f;
+    int labs[LABEL_CAP], cnts[LABEL_CAP];
+    int nl = 0;
+    bool overflow = false;
+    for (unsigned long long i = s; i < e; ++i) {
+        const unsigned long long p = idx[i];
+        sx = __fadd_rn(sx, __ldg(pts + 3 * p + 0));
+        sy = __fadd_rn(sy, __ldg(pts + 3 * p + 1));
+        sz = __fadd_rn(sz, __ldg(pts + 3 * p + 2));
+        if (FD > 0) {
+#pragma unroll
+            for (int j = 0; j < (FD > 0 ? FD : 1); ++j) fs[j] = __fadd_rn(fs[j], __ldg(feats + p * FD + j));
+        } else if (FD < 0) {
+            for (int j = 0; j < fdim; ++j)
+                out_f[v * fdim + j] = __fadd_rn(out_f[v * fdim + j], __ldg(feats + p * fdim + j));
+        }
+        if (ldim >= 1) {  // first label column in the same pass
+            const int lab = __ldg(cls + p * ldim);
+            int q = 0;
+            while (q < nl && labs[q] != lab) ++q;
+            if (q == nl) {
+                if (nl < LABEL_CAP) {
+                    labs[nl] = lab;
+                    cnts[nl] = 0;
+                    ++nl;
+                } else {
+                    overflow = true;
+                    q = 0;
+                }
+            }
+            cnts[q] += 1;
+        }
+    }
+    const int count = (int)(e - s);
+    const float a = (float)(1.0 / (double)count);  // grid_subsampling.cpp:87: double reciprocal narrowed to float
+    out_p[3 * v + 0] = __fmul_rn(sx, a);
+    out_p[3 * v + 1] = __fmul_rn(sy, a);
+    out_p[3 * v + 2] = __fmul_rn(sz, a);
+    const float cf = (float)count;
+    if (FD > 0) {
+#pragma unroll
+        for (int j = 0; j < (FD > 0 ? FD : 1); ++j) out_f[v * FD + j] = __fdiv_rn(fs[j], cf);
+    } else if (FD < 0) {
+        for (int j = 0; j < fdim; ++j) out_f[v * fdim + j] = __fdiv_rn(out_f[v * fdim + j], cf);
+    }
+    for (int col = 0; col < ldim; ++col) {
+        if (col > 0) {  // further label columns: one more walk each (rare: ldim is 1 for every reference caller)
+            nl = 0;
+            for (unsigned long long i = s; i < e; ++i) {
+                const int lab = __ldg(cls + (unsigned long long)idx[i] * ldim + col);
+                int q = 0;
+                while (q < nl && labs[q] != lab) ++q;
+                if (q == nl) {
+                    if (nl < LABEL_CAP) {
+                        labs[nl] = lab;
+                        cnts[nl] = 0;
+                        ++nl;
+                    } else {
+                        overflow = true;
+                        q = 0;
+                    }
+                }
+                cnts[q] += 1;
+            }
+        }
+        int best = -1, nbest = 0, arg = 0;
+        for (int q = 0; q < nl; ++q) {
+            if (cnts[q] > best) {
+                best = cnts[q];
+                nbest = 1;
+                arg = q;
+            } else if (cnts[q] == best)
+                ++nbest;
+        }
+        out_c[v * ldim + col] = nbest == 1 ? labs[arg] : label_first_in_iteration_order(labs, cnts, nl, best);
+    }
+    if (overflow) meta->error = 2;
+    out_k[v] = (unsigned long long)keys[s];
+    out_n[v] = count;
+}
+
+struct Handle {
+    size_t M = 0, fdim = 0, ldim = 0;
+    float* d_p = nullptr;
+    float* d_f = nullptr;
+    int* d_c = nullptr;
+    unsigned long long* d_k = nullptr;
+    int* d_n = nullptr;
+    cudaStream_t stream = nullptr;
+    int device = 0;
+};
+
+static void free_handle(Handle* h) {
+    if (!h) return;
+    if (h->d_p) cudaFree(h->d_p);
+    if (h->d_f) cudaFree(h->d_f);
+    if (h->d_c) cudaFree(h->d_c);
+    if (h->d_k) cudaFree(h->d_k);
+    if (h->d_n) cudaFree(h->d_n);
+    delete h;
+}
+
+template <typename KeyT>
+static int sort_and_reduce(Ctx* c, cudaStream_t s, const float* d_p, const float* d_f, const int* d_c, size_t N,
+                           size_t fdim, size_t ldim, int key_bits, Handle* h) {
+    SSDR_TRY(c->ws[WS_KEYS].reserve(N * sizeof(KeyT)));
+    SSDR_TRY(c->ws[WS_KEYS2].reserve(N * sizeof(KeyT)));
+    SSDR_TRY(c->ws[WS_IDX].reserve(N * sizeof(unsigned)));
+    SSDR_TRY(c->ws[WS_IDX2].reserve(N * sizeof(unsigned)));
+    SSDR_TRY(c->ws[WS_STARTS].reserve((N + 1) * sizeof(unsigned)));
+    Meta* meta = c->ws[WS_META].as<Meta>();
+    KeyT* keys = c->ws[WS_KEYS].as<KeyT>();
+    KeyT* keys2 = c->ws[WS_KEYS2].as<KeyT>();
+    unsigned* idx = c->ws[WS_IDX].as<unsigned>();
+    unsigned* idx2 = c->ws[WS_IDX2].as<unsigned>();
+    unsigned* starts = c->ws[WS_STARTS].as<unsigned>();
+    const unsigned blocks = (unsigned)((N + 255) / 256);
+    key_kernel<KeyT><<<blocks, 256, 0, s>>>(d_p, N, meta, keys, idx);
+    SSDR_CHECK_CUDA(cudaGetLastError());
+
+    cub::DoubleBuffer<KeyT> kb(keys, keys2);
+    cub::DoubleBuffer<unsigned> vb(idx, idx2);
+    size_t t1 = 0, t2 = 0;
+    if (key_bits < 1) key_bits = 1;
+    SSDR_CHECK_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, t1, kb, vb, (unsigned)N, 0, key_bits, s));
+    cub::CountingInputIterator<unsigned> counting(0);
+    HeadPred<KeyT> pred{keys};
+    SSDR_CHECK_CUDA(cub::DeviceSelect::If(nullptr, t2, counting, starts, &meta->M, (unsigned)N, pred, s));
+    SSDR_TRY(c->ws[WS_TEMP].reserve(t1 > t2 ? t1 : t2));
+    SSDR_CHECK_CUDA(cub::DeviceRadixSort::SortPairs(c->ws[WS_TEMP].p, t1, kb, vb, (unsigned)N, 0, key_bits, s));
+    pred.keys = kb.Current();
+    SSDR_CHECK_CUDA(cub::DeviceSelect::If(c->ws[WS_TEMP].p, t2, counting, starts, &meta->M, (unsigned)N, pred, s));
+    Meta hm;
+    SSDR_TRY(d2h_sync(c, &hm, meta, sizeof(Meta), s));
+    const size_t M = (size_t)hm.M;
+    SSDR_REQUIRE(M >= 1 && M <= N, SSDR_ERR_EMPTY, "Error");
+    h->M = M;
+    h->fdim = d_f ? fdim : 0;
+    h->ldim = d_c ? ldim : 0;
+    SSDR_CHECK_CUDA(cudaMalloc(&h->d_p, M * 3 * sizeof(float)));
+    if (h->fdim) SSDR_CHECK_CUDA(cudaMalloc(&h->d_f, M * h->fdim * sizeof(float)));
+    if (h->ldim) SSDR_CHECK_CUDA(cudaMalloc(&h->d_c, M * h->ldim * sizeof(int)));
+    SSDR_CHECK_CUDA(cudaMalloc(&h->d_k, M * sizeof(unsigned long long)));
+    SSDR_CHECK_CUDA(cudaMalloc(&h->d_n, M * sizeof(int)));
+    const unsigned vb_blocks = (unsigned)((M + 127) / 128);
+#define SSDR_REDUCE(FDV)                                                                                       \
+    reduce_kernel<KeyT, FDV><<<vb_blocks, 128, 0, s>>>(d_p, d_f, d_c, (int)h->fdim, (int)h->ldim, kb.Current(), \
+                                                       vb.Current(), starts, N, M, h->d_p, h->d_f, h->d_c,    \
+                                                       h->d_k, h->d_n, meta)
+    switch (h->fdim) {
+        case 0: SSDR_REDUCE(0); break;
+        case 1: SSDR_REDUCE(1); break;
+        case 2: SSDR_REDUCE(2); break;
+        case 3: SSDR_REDUCE(3); break;
+        case 4: SSDR_REDUCE(4); break;
+        case 6: SSDR_REDUCE(6); break;
+        case 8: SSDR_REDUCE(8); break;
+        default: SSDR_REDUCE(-1); break;
+    }
+#undef SSDR_REDUCE
+    SSDR_CHECK_CUDA(cudaGetLastError());
+    if (h->ldim) {  // the only late failure mode is a label-table overflow; surface it before results are used
+        SSDR_TRY(d2h_sync(c, &hm, meta, sizeof(Meta), s));
+        SSDR_REQUIRE(hm.error != 2, SSDR_ERR_UNSUPPORTED, "more than %d distinct labels inside one voxel", LABEL_CAP);
+    }
+    return SSDR_OK;
+}
+
+static int run_dev(Ctx* c, cudaStream_t s, const float* d_p, const float* d_f, const int* d_c, size_t N, size_t fdim,
+                   size_t ldim, float dl, int order, size_t* M_out, void** handle) {
+    SSDR_REQUIRE(d_p && M_out && handle, SSDR_ERR_INVALID, "NULL pointer");
+    SSDR_REQUIRE(N >= 1, SSDR_ERR_EMPTY, "Error");
+    SSDR_REQUIRE(N < 0xFFFFFFFFull, SSDR_ERR_UNSUPPORTED, "N=%zu exceeds 2^32-2 points per call", N);
+    SSDR_REQUIRE(order == SSDR_GRID_ORDER_KEY, SSDR_ERR_UNSUPPORTED,
+                 "order=REFERENCE (libstdc++ hash iteration order) is not implemented on the device yet");
+    SSDR_REQUIRE(dl > 0.0f, SSDR_ERR_INVALID, "sampleDl must be positive");
+    if (!d_f) fdim = 0;
+    if (!d_c) ldim = 0;
+    const int nparts = c->sm_count * 4;
+    SSDR_TRY(c->ws[WS_META].reserve(sizeof(Meta)));
+    SSDR_TRY(c->ws[WS_PART].reserve((size_t)nparts * 6 * sizeof(float)));
+    Meta* meta = c->ws[WS_META].as<Meta>();
+    minmax_kernel<<<nparts, MM_BLOCK, 0, s>>>(d_p, N, c->ws[WS_PART].as<float>());
+    setup_kernel<<<1, 32, 0, s>>>(c->ws[WS_PART].as<float>(), nparts, dl, meta);
+    SSDR_CHECK_CUDA(cudaGetLastError());
+    Meta hm;
+    SSDR_TRY(d2h_sync(c, &hm, meta, sizeof(Meta), s));
+    SSDR_REQUIRE(hm.error == 0, SSDR_ERR_UNSUPPORTED,
+                 "voxel key space %llu x %llu x %llu needs more than 62 bits (sampleDl too small for the extent?)",
+                 hm.nX, hm.nY, hm.nZ);
+    Handle* h = new Handle();
+    h->stream = s;
+    h->device = c->device;
+    int rc = hm.key_bits <= 32 ? sort_and_reduce<unsigned>(c, s, d_p, d_f, d_c, N, fdim, ldim, hm.key_bits, h)
+                               : sort_and_reduce<unsigned long long>(c, s, d_p, d_f, d_c, N, fdim, ldim, hm.key_bits, h);
+    if (rc != SSDR_OK) {
+        free_handle(h);
+        return rc;
+    }
+    *M_out = h->M;
+    *handle = h;
+    return SSDR_OK;
+}
+
+}  // namespace grid
+}  // namespace ssdr
+
+using namespace ssdr;
+
+extern "C" {
+
+int ssdr_grid_subsample_dev(const float* d_points, const float* d_feats, const int32_t* d_classes, size_t N,
+                            size_t fdim, size_t ldim, float sampleDl, int order, void* stream, size_t* M_out,
+                            void** handle) {
+    Ctx* c;
+    SSDR_TRY(get_ctx(&c));
+    return grid::run_dev(c, stream ? (cudaStream_t)stream : c->stream, d_points, d_feats, d_classes, N, fdim, ldim,
+                         sampleDl, order, M_out, handle);
+}
+
+int ssdr_grid_subsample(const float* points, const float* feats, const int32_t* classes, size_t N, size_t fdim,
+                        size_t ldim, float sampleDl, int order, size_t* M_out, void** handle) {
+    SSDR_REQUIRE(points && M_out && handle, SSDR_ERR_INVALID, "NULL pointer");
+    SSDR_REQUIRE(N >= 1, SSDR_ERR_EMPTY, "Error");
+    Ctx* c;
+    SSDR_TRY(get_ctx(&c));
+    if (!feats) fdim = 0;
+    if (!classes) ldim = 0;
+    SSDR_TRY(c->ws[grid::WS_IN_P].reserve(N * 3 * sizeof(float)));
+    SSDR_TRY(h2d(c, c->ws[grid::WS_IN_P].p, points, N * 3 * sizeof(float), c->stream));
+    const float* d_f = nullptr;
+    const int* d_c = nullptr;
+    if (fdim) {
+        SSDR_TRY(c->ws[grid::WS_IN_F].reserve(N * fdim * sizeof(float)));
+        SSDR_TRY(h2d(c, c->ws[grid::WS_IN_F].p, feats, N * fdim * sizeof(float), c->stream));
+        d_f = c->ws[grid::WS_IN_F].as<float>();
+    }
+    if (ldim) {
+        SSDR_TRY(c->ws[grid::WS_IN_C].reserve(N * ldim * sizeof(int)));
+        SSDR_TRY(h2d(c, c->ws[grid::WS_IN_C].p, classes, N * ldim * sizeof(int), c->stream));
+        d_c = c->ws[grid::WS_IN_C].as<int>();
+    }
+    return grid::run_dev(c, c->stream, c->ws[grid::WS_IN_P].as<float>(), d_f, d_c, N, fdim, ldim, sampleDl, order,
+                         M_out, handle);
+}
+
+int ssdr_grid_fetch_ex(void* handle, float* points_out, float* feats_out, int32_t* classes_out, uint64_t* keys_out,
+                       int32_t* counts_out) {
+    SSDR_REQUIRE(handle, SSDR_ERR_INVALID, "NULL handle");
+    grid::Handle* h = (grid::Handle*)handle;
+    Ctx* c;
+    SSDR_TRY(get_ctx(&c));
+    cudaStream_t s = h->stream;
+    if (points_out) SSDR_CHECK_CUDA(cudaMemcpyAsync(points_out, h->d_p, h->M * 3 * sizeof(float), cudaMemcpyDeviceToHost, s));
+    if (feats_out && h->d_f)
+        SSDR_CHECK_CUDA(cudaMemcpyAsync(feats_out, h->d_f, h->M * h->fdim * sizeof(float), cudaMemcpyDeviceToHost, s));
+    if (classes_out && h->d_c)
+        SSDR_CHECK_CUDA(cudaMemcpyAsync(classes_out, h->d_c, h->M * h->ldim * sizeof(int), cudaMemcpyDeviceToHost, s));
+    if (keys_out) SSDR_CHECK_CUDA(cudaMemcpyAsync(keys_out, h->d_k, h->M * sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
+    if (counts_out) SSDR_CHECK_CUDA(cudaMemcpyAsync(counts_out, h->d_n, h->M * sizeof(int), cudaMemcpyDeviceToHost, s));
+    SSDR_CHECK_CUDA(cudaStreamSynchronize(s));
+    return SSDR_OK;
+}
+
+int ssdr_grid_fetch(void* handle, float* points_out, float* feats_out, int32_t* classes_out) {
+    return ssdr_grid_fetch_ex(handle, points_out, feats_out, classes_out, nullptr, nullptr);
+}
+
+int ssdr_grid_dev_ptrs(void* handle, const float** d_points, const float** d_feats, const int32_t** d_classes) {
+    SSDR_REQUIRE(handle, SSDR_ERR_INVALID, "NULL handle");
+    grid::Handle* h = (grid::Handle*)handle;
+    if (d_points) *d_points = h->d_p;
+    if (d_feats) *d_feats = h->d_f;
+    if (d_classes) *d_classes = h->d_c;
+    return SSDR_OK;
+}
+
+int ssdr_grid_free(void* handle) {
+    grid::free_handle((grid::Handle*)handle);
+    return SSDR_OK;
+}
+}

@@ -1,0 +1,169 @@
+// runtime.cu -- status reporting, per-thread contexts, device management for libssdr_b200.so.
+#include <stdarg.h>
+#include <unistd.h>
+
+#include "common.cuh"
+
+namespace ssdr {
+
+static thread_local char g_err[512] = "";
+static pid_t g_init_pid = 0;
+
+int set_error(int status, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return status;
+}
+
+int DevBuf::reserve(size_t bytes) {
+    if (bytes <= cap) return SSDR_OK;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    size_t want = align_up(bytes + bytes / 8, 1 << 20);  // a little head-room so repeated calls stop reallocating
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        e = cudaMalloc(&p, bytes);
+        want = bytes;
+    }
+    if (e != cudaSuccess) {
+        p = nullptr;
+        cudaGetLastError();
+        return set_error(SSDR_ERR_NOMEM, "cudaMalloc(%zu bytes) failed: %s", bytes, cudaGetErrorString(e));
+    }
+    cap = want;
+    return SSDR_OK;
+}
+void DevBuf::release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+}
+int PinBuf::reserve(size_t bytes) {
+    if (bytes <= cap) return SSDR_OK;
+    if (p) cudaFreeHost(p);
+    p = nullptr;
+    cap = 0;
+    cudaError_t e = cudaHostAlloc(&p, bytes, cudaHostAllocDefault);
+    if (e != cudaSuccess) {
+        p = nullptr;
+        cudaGetLastError();
+        return set_error(SSDR_ERR_NOMEM, "cudaHostAlloc(%zu bytes) failed: %s", bytes, cudaGetErrorString(e));
+    }
+    cap = bytes;
+    return SSDR_OK;
+}
+void PinBuf::release() {
+    if (p) cudaFreeHost(p);
+    p = nullptr;
+    cap = 0;
+}
+
+enum { MAX_DEV = 16 };
+static thread_local Ctx g_ctx[MAX_DEV];
+
+int get_ctx(Ctx** out) {
+    pid_t me = getpid();
+    if (g_init_pid == 0) g_init_pid = me;
+    else if (g_init_pid != me)
+        return set_error(SSDR_ERR_FORK,
+                         "libssdr_b200 was initialised in process %d and cannot be used in its fork()ed child %d; "
+                         "use the 'spawn' or 'forkserver' multiprocessing start method (or num_workers=0)",
+                         (int)g_init_pid, (int)me);
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return set_error(SSDR_ERR_CUDA, "no usable CUDA device: %s (this library has no CPU fallback)",
+                         cudaGetErrorString(e));
+    }
+    if (dev < 0 || dev >= MAX_DEV) return set_error(SSDR_ERR_CUDA, "device ordinal %d out of range", dev);
+    Ctx* c = &g_ctx[dev];
+    if (c->device != dev) {
+        cudaDeviceProp prop;
+        SSDR_CHECK_CUDA(cudaGetDeviceProperties(&prop, dev));
+        if (prop.major < 10)
+            return set_error(SSDR_ERR_CUDA, "device %d (%s, sm_%d%d) is not a Blackwell sm_100 GPU", dev, prop.name,
+                             prop.major, prop.minor);
+        SSDR_CHECK_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+        SSDR_CHECK_CUDA(cudaEventCreateWithFlags(&c->ev, cudaEventDisableTiming));
+        c->sm_count = prop.multiProcessorCount;
+        c->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
+        c->device = dev;
+    }
+    *out = c;
+    return SSDR_OK;
+}
+
+int h2d(Ctx* c, void* dst, const void* src, size_t bytes, cudaStream_t s) {
+    (void)c;
+    if (bytes == 0) return SSDR_OK;
+    SSDR_CHECK_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, s));
+    return SSDR_OK;
+}
+
+int d2h_sync(Ctx* c, void* dst, const void* src, size_t bytes, cudaStream_t s) {
+    (void)c;
+    if (bytes) SSDR_CHECK_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, s));
+    SSDR_CHECK_CUDA(cudaStreamSynchronize(s));
+    return SSDR_OK;
+}
+
+}  // namespace ssdr
+
+using namespace ssdr;
+
+extern "C" {
+
+const char* ssdr_last_error(void) { return g_err; }
+int ssdr_version(void) { return 100; }
+
+int ssdr_device_count(int* count) {
+    SSDR_REQUIRE(count, SSDR_ERR_INVALID, "count is NULL");
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        *count = 0;
+        return set_error(SSDR_ERR_CUDA, "cudaGetDeviceCount: %s", cudaGetErrorString(e));
+    }
+    *count = n;
+    return SSDR_OK;
+}
+int ssdr_set_device(int device) {
+    SSDR_CHECK_CUDA(cudaSetDevice(device));
+    return SSDR_OK;
+}
+int ssdr_get_device(int* device) {
+    SSDR_REQUIRE(device, SSDR_ERR_INVALID, "device is NULL");
+    SSDR_CHECK_CUDA(cudaGetDevice(device));
+    return SSDR_OK;
+}
+int ssdr_device_sm_count(int* sms) {
+    SSDR_REQUIRE(sms, SSDR_ERR_INVALID, "sms is NULL");
+    Ctx* c;
+    SSDR_TRY(get_ctx(&c));
+    *sms = c->sm_count;
+    return SSDR_OK;
+}
+int ssdr_synchronize(void) {
+    Ctx* c;
+    SSDR_TRY(get_ctx(&c));
+    SSDR_CHECK_CUDA(cudaStreamSynchronize(c->stream));
+    return SSDR_OK;
+}
+int ssdr_host_alloc(void** ptr, size_t bytes) {
+    SSDR_REQUIRE(ptr, SSDR_ERR_INVALID, "ptr is NULL");
+    Ctx* c;
+    SSDR_TRY(get_ctx(&c));
+    SSDR_CHECK_CUDA(cudaHostAlloc(ptr, bytes ? bytes : 1, cudaHostAllocDefault));
+    return SSDR_OK;
+}
+int ssdr_host_free(void* ptr) {
+    if (ptr) SSDR_CHECK_CUDA(cudaFreeHost(ptr));
+    return SSDR_OK;
+}
+}

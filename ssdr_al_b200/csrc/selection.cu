@@ -1,0 +1,647 @@
+// selection.cu -- farthest-feature sampling and k-center greedy on sm_100a.
+//
+// Replaces the per-pick numpy passes of farthest_features_sample (fps_gcn_cpu.py:137-146) and
+// kCenterGreedy.update_distances/select_batch_ (kcenterGreedy.py:60-128).
+//
+// One PERSISTENT cooperative kernel runs every pick: each CTA owns a contiguous slab of rows, streams it from
+// HBM/L2 through a cp.async multi-stage shared-memory ring (padded rows => conflict-free LDS), evaluates the
+// distance of every row to the current centre in the reference's exact floating-point order, folds it into the
+// running min-distance, and reduces (distance, index) to one candidate per CTA.  A grid barrier publishes the
+// candidates; every CTA then reduces them redundantly, so the next centre is known everywhere with a single
+// barrier per pick and no host round trip.  The step is HBM/L2-bandwidth bound: N*(sizeof(T)*D + 2*sizeof(T)).
+//
+// Arithmetic contracts (bit-exact picks):
+//   FPS     : d = pairwise_sum_j((F[i,j]-F[c,j])^2) in T with numpy's summation tree: eight strided
+//             accumulators per <=128-wide leaf, ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7)), sequential tail, leaves
+//             combined by recursive halving.  Eight lanes own the eight accumulators of one row; the xor-butterfly
+//             reproduces the combine tree exactly because IEEE addition is commutative.
+//   k-center: d = sqrt(max(0, T(-2*dot64 + |x|^2 + |c|^2))) like sklearn's euclidean_distances (float64
+//             accumulation, rounded to T before clamp and sqrt).  BLAS's summation order is unspecified; ours is
+//             eight strided fp64 FMA chains + butterfly.
+#include <cooperative_groups.h>
+#include <math.h>
+
+#include "common.cuh"
+
+namespace ssdr {
+namespace sel {
+
+constexpr int THREADS = 256;
+constexpr int WARPS = THREADS / 32;
+constexpr int MAX_LEAVES = 128;
+constexpr int MAX_STACK = 10;
+
+enum Mode { MODE_FPS = 0, MODE_KCENTER = 1 };
+
+__host__ __device__ constexpr size_t align_up_dev(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+struct LeafPlan {
+    int n_leaves;
+    unsigned short start[MAX_LEAVES];
+    unsigned short len[MAX_LEAVES];
+    unsigned char merges[MAX_LEAVES];  // number of (left + right) combines after finishing leaf i
+};
+
+template <typename T>
+struct Params {
+    const T* F;
+    unsigned long long N;
+    int D;
+    unsigned long long row_begin, row_end;  // rows scanned by this launch (global indices)
+    int stride;                             // smem row stride in elements
+    int rows_per_tile;                      // multiple of 4
+    int nstages;
+    int vec;                                // elements per cp.async (16B when possible)
+    const long long* forced;                // device: centres of the first n_forced steps
+    int n_forced;
+    int step_begin, step_end;
+    T* mind;                                // running min distance, N entries
+    const double* xx;                       // k-center: squared row norms (fp64)
+    unsigned long long* winners;            // per step: packed winner (see pack())
+    unsigned long long* cand;               // 2 * gridDim * 2 u64 candidate mailboxes
+    unsigned int* barrier;                  // zero at launch
+    long long* picks;                       // nullable: picks[s] = winner row of step s
+    LeafPlan plan;
+};
+
+__device__ __forceinline__ void cp_async_16(void* smem, const void* gmem) {
+    unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_8(void* smem, const void* gmem) {
+    unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(s), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_4(void* smem, const void* gmem) {
+    unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(s), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_dyn(int n) {
+    switch (n) {
+        case 0: cp_async_wait<0>(); break;
+        case 1: cp_async_wait<1>(); break;
+        case 2: cp_async_wait<2>(); break;
+        case 3: cp_async_wait<3>(); break;
+        case 4: cp_async_wait<4>(); break;
+        default: cp_async_wait<5>(); break;
+    }
+}
+
+template <typename T>
+__device__ __forceinline__ void cp_elems(T* dst, const T* src, int vec) {
+    if (sizeof(T) * vec == 16) cp_async_16(dst, src);
+    else if (sizeof(T) * vec == 8) cp_async_8(dst, src);
+    else cp_async_4(dst, src);
+}
+
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];\n" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void red_release_add_u32(unsigned* p, unsigned v) {
+    asm volatile("red.release.gpu.global.add.u32 [%0], %1;\n" ::"l"(p), "r"(v) : "memory");
+}
+
+// exact, non-contracted arithmetic
+__device__ __forceinline__ float xsub(float a, float b) { return __fsub_rn(a, b); }
+__device__ __forceinline__ float xmul(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ float xadd(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ double xsub(double a, double b) { return __dsub_rn(a, b); }
+__device__ __forceinline__ double xmul(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ double xadd(double a, double b) { return __dadd_rn(a, b); }
+template <typename T>
+__device__ __forceinline__ T sqdiff(T a, T c) {
+    T d = xsub(a, c);
+    return xmul(d, d);
+}
+__device__ __forceinline__ float shfl_xor(float v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
+__device__ __forceinline__ double shfl_xor(double v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
+
+// ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7)) over the 8 lanes of a row group
+template <typename T>
+__device__ __forceinline__ T butterfly8(T v) {
+    v = xadd(v, shfl_xor(v, 1));
+    v = xadd(v, shfl_xor(v, 2));
+    v = xadd(v, shfl_xor(v, 4));
+    return v;
+}
+
+// numpy pairwise sum of (a[i]-c[i])^2 for one row; the 8 lanes with the same (lane>>3) cooperate, j = lane&7.
+template <typename T>
+__device__ __forceinline__ T row_sqdist(const T* __restrict__ a, const T* __restrict__ c, int D, int j,
+                                        const LeafPlan& plan) {
+    if (D < 8) {
+        T res = (T)0;
+        for (int i = 0; i < D; ++i) res = xadd(res, sqdiff(a[i], c[i]));
+        return res;
+    }
+    T st[MAX_STACK];
+#pragma unroll 1
+    for (int l = 0; l < plan.n_leaves; ++l) {
+        const int s = plan.start[l], n = plan.len[l];
+        const int nm = n - (n & 7);
+        T acc = sqdiff(a[s + j], c[s + j]);
+        for (int i = 8; i < nm; i += 8) acc = xadd(acc, sqdiff(a[s + i + j], c[s + i + j]));
+        T res = butterfly8(acc);
+        for (int i = nm; i < n; ++i) res = xadd(res, sqdiff(a[s + i], c[s + i]));
+        if (plan.n_leaves == 1) return res;
+        // shift-register stack (static indexing keeps it in registers)
+#pragma unroll
+        for (int q = MAX_STACK - 1; q > 0; --q) st[q] = st[q - 1];
+        st[0] = res;
+        for (int m = plan.merges[l]; m > 0; --m) {
+            st[0] = xadd(st[1], st[0]);  // left + right
+#pragma unroll
+            for (int q = 1; q < MAX_STACK - 1; ++q) st[q] = st[q + 1];
+        }
+    }
+    return st[0];
+}
+
+// fp64 dot product of one row with the centre (k-center); order: 8 strided FMA chains + butterfly + tail.
+template <typename T>
+__device__ __forceinline__ double row_dot64(const T* __restrict__ a, const T* __restrict__ c, int D, int j) {
+    double acc = 0.0;
+    const int nm = D - (D & 7);
+    for (int i = 0; i < nm; i += 8) acc = fma((double)a[i + j], (double)c[i + j], acc);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+    for (int i = nm; i < D; ++i) acc = fma((double)a[i], (double)c[i], acc);
+    return acc;
+}
+
+// ---- candidate = (distance, row) with "max distance, then lowest row" order ----------------------------
+struct Cand {
+    unsigned long long hi, lo;  // float: hi = dist_bits<<32 | ~row (lo unused); double: hi = dist bits, lo = ~row
+};
+template <typename T>
+__device__ __forceinline__ Cand make_cand(T d, unsigned long long row);
+template <>
+__device__ __forceinline__ Cand make_cand<float>(float d, unsigned long long row) {
+    Cand c;
+    c.hi = ((unsigned long long)__float_as_uint(d) << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned)row);
+    c.lo = 0;
+    return c;
+}
+template <>
+__device__ __forceinline__ Cand make_cand<double>(double d, unsigned long long row) {
+    Cand c;
+    c.hi = (unsigned long long)__double_as_longlong(d);
+    c.lo = ~row;
+    return c;
+}
+template <typename T>
+__device__ __forceinline__ unsigned long long cand_row(const Cand& c);
+template <>
+__device__ __forceinline__ unsigned long long cand_row<float>(const Cand& c) {
+    return (unsigned long long)(0xFFFFFFFFu - (unsigned)(c.hi & 0xFFFFFFFFull));
+}
+template <>
+__device__ __forceinline__ unsigned long long cand_row<double>(const Cand& c) {
+    return ~c.lo;
+}
+__device__ __forceinline__ bool cand_less(const Cand& a, const Cand& b) {
+    return a.hi < b.hi || (a.hi == b.hi && a.lo < b.lo);
+}
+__device__ __forceinline__ Cand cand_max(const Cand& a, const Cand& b) { return cand_less(a, b) ? b : a; }
+__device__ __forceinline__ Cand cand_shfl_xor(const Cand& a, int m) {
+    Cand r;
+    r.hi = __shfl_xor_sync(0xffffffffu, a.hi, m);
+    r.lo = __shfl_xor_sync(0xffffffffu, a.lo, m);
+    return r;
+}
+__device__ __forceinline__ Cand warp_max(Cand c) {
+#pragma unroll
+    for (int m = 16; m > 0; m >>= 1) c = cand_max(c, cand_shfl_xor(c, m));
+    return c;
+}
+
+template <typename T, int MODE>
+__global__ void __launch_bounds__(THREADS, 1) select_kernel(const Params<T> p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    typedef typename std::conditional<MODE == MODE_KCENTER, double, T>::type RowVal;
+    const int D = p.D;
+    const int stride = p.stride;
+    const int R = p.rows_per_tile;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int G = gridDim.x;
+
+    // shared layout: centre row | per-row results | stage ring | reduction scratch
+    T* s_center = reinterpret_cast<T*>(smem_raw);
+    size_t off = align_up_dev((size_t)(D + 8) * sizeof(T), 16);
+    RowVal* s_rowval = reinterpret_cast<RowVal*>(smem_raw + off);
+    off += align_up_dev((size_t)R * sizeof(RowVal), 16);
+    T* s_tiles = reinterpret_cast<T*>(smem_raw + off);
+    off += (size_t)p.nstages * R * stride * sizeof(T);
+    Cand* s_red = reinterpret_cast<Cand*>(smem_raw + align_up_dev(off, 16));
+    __shared__ unsigned long long s_next_center;
+
+    // contiguous slab of rows for this CTA, in whole tiles
+    const unsigned long long nrows = p.row_end - p.row_begin;
+    const unsigned long long tiles_total = (nrows + R - 1) / R;
+    const unsigned long long tiles_per_cta = (tiles_total + G - 1) / G;
+    const unsigned long long t_begin = min((unsigned long long)blockIdx.x * tiles_per_cta, tiles_total);
+    const unsigned long long t_end = min(t_begin + tiles_per_cta, tiles_total);
+    const int ntiles = (int)(t_end - t_begin);
+
+    const int cpr = D / p.vec;  // chunks per row
+    const int dcol = THREADS % cpr, drow = THREADS / cpr;
+
+    auto issue_tile = [&](int t) {
+        if (t < ntiles) {
+            const unsigned long long r0 = p.row_begin + (t_begin + t) * (unsigned long long)R;
+            const int rows = (int)min((unsigned long long)R, p.row_end - r0);
+            T* dst = s_tiles + (size_t)(t % p.nstages) * R * stride;
+            const T* src = p.F + r0 * (unsigned long long)D;
+            int row = tid / cpr, col = tid % cpr;
+            while (row < rows) {
+                cp_elems(dst + (size_t)row * stride + col * p.vec, src + (size_t)row * D + col * p.vec, p.vec);
+                col += dcol;
+                row += drow;
+                if (col >= cpr) {
+                    col -= cpr;
+                    ++row;
+                }
+            }
+        }
+        cp_async_commit();
+    };
+
+    for (int step = p.step_begin; step < p.step_end; ++step) {
+        // ---- centre of this step
+        __syncthreads();  // warp 0 has published s_next_center; nobody still reads the previous step's smem
+        unsigned long long c_row;
+        if (step < p.n_forced) c_row = (unsigned long long)p.forced[step];
+        else if (step == p.step_begin) {
+            Cand w;
+            w.hi = p.winners[2 * (step - 1)];
+            w.lo = p.winners[2 * (step - 1) + 1];
+            c_row = cand_row<T>(w);
+        } else
+            c_row = s_next_center;
+        for (int i = tid; i < D; i += THREADS) s_center[i] = p.F[c_row * (unsigned long long)D + i];
+        double xx_c = 0.0;
+        if (MODE == MODE_KCENTER) xx_c = p.xx[c_row];
+
+        // ---- pipeline prologue
+        for (int t = 0; t < p.nstages - 1; ++t) issue_tile(t);
+
+        Cand best;
+        best.hi = 0;
+        best.lo = 0;
+        for (int t = 0; t < ntiles; ++t) {
+            cp_async_wait_dyn(p.nstages - 2);
+            __syncthreads();  // tile t landed for all threads; stage (t-1)%nstages is free
+            issue_tile(t + p.nstages - 1);
+
+            const unsigned long long r0 = p.row_begin + (t_begin + t) * (unsigned long long)R;
+            const int rows = (int)min((unsigned long long)R, p.row_end - r0);
+            const T* tile = s_tiles + (size_t)(t % p.nstages) * R * stride;
+            const int g = lane >> 3, j = lane & 7;
+            // row groups of 4 rows, round-robin over warps
+            for (int rg = warp; rg * 4 < rows; rg += WARPS) {
+                const int row = rg * 4 + g;
+                const T* a = tile + (size_t)row * stride;
+                if (MODE == MODE_FPS) {
+                    T d = row_sqdist<T>(a, s_center, D, j, p.plan);
+                    if (j == 0 && row < rows) s_rowval[row] = (RowVal)d;
+                } else {
+                    double d = row_dot64<T>(a, s_center, D, j);
+                    if (j == 0 && row < rows) s_rowval[row] = (RowVal)d;
+                }
+            }
+            __syncthreads();
+            for (int row = tid; row < rows; row += THREADS) {
+                const unsigned long long gi = r0 + row;
+                T d;
+                if (MODE == MODE_FPS) {
+                    d = (T)s_rowval[row];
+                } else {
+                    double v = -2.0 * (double)s_rowval[row];
+                    v = __dadd_rn(v, p.xx[gi]);
+                    v = __dadd_rn(v, xx_c);
+                    T tv = (T)v;
+                    tv = tv > (T)0 ? tv : (T)0;  // np.maximum(d, 0)
+                    d = sizeof(T) == 4 ? (T)__fsqrt_rn((float)tv) : (T)__dsqrt_rn((double)tv);
+                }
+                T m = p.mind[gi];
+                m = d < m ? d : m;
+                p.mind[gi] = m;
+                best = cand_max(best, make_cand<T>(m, gi));
+            }
+        }
+        cp_async_wait<0>();
+
+        // ---- CTA candidate
+        best = warp_max(best);
+        if (lane == 0) s_red[warp] = best;
+        __syncthreads();
+        if (warp == 0) {
+            Cand c = lane < WARPS ? s_red[lane] : Cand{0, 0};
+            c = warp_max(c);
+            if (lane == 0) {
+                unsigned long long* box = p.cand + ((size_t)(step & 1) * G + blockIdx.x) * 2;
+                box[0] = c.hi;
+                box[1] = c.lo;
+                __threadfence();
+                red_release_add_u32(p.barrier, 1u);
+                const unsigned target = (unsigned)(step - p.step_begin + 1) * (unsigned)G;
+                while (ld_acquire_u32(p.barrier) < target) {
+                }
+            }
+            __syncwarp();
+            // ---- every CTA reduces all candidates redundantly
+            Cand w{0, 0};
+            for (int b = lane; b < G; b += 32) {
+                const unsigned long long* box = p.cand + ((size_t)(step & 1) * G + b) * 2;
+                Cand o;
+                o.hi = __ldcg(box);
+                o.lo = __ldcg(box + 1);
+                w = cand_max(w, o);
+            }
+            w = warp_max(w);
+            if (lane == 0) {
+                s_next_center = cand_row<T>(w);
+                if (blockIdx.x == 0) {
+                    p.winners[2 * step] = w.hi;
+                    p.winners[2 * step + 1] = w.lo;
+                    if (p.picks) p.picks[step] = (long long)cand_row<T>(w);
+                }
+            }
+        }
+        // the __syncthreads at the top of the next step publishes s_next_center
+    }
+}
+
+// squared row norms in fp64 (k-center): one warp per row, coalesced, FMA chain per lane + butterfly
+template <typename T>
+__global__ void row_norms_kernel(const T* __restrict__ F, unsigned long long N, int D, double* __restrict__ xx) {
+    const unsigned long long row = (unsigned long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= N) return;
+    const int lane = threadIdx.x & 31;
+    const T* a = F + row * (unsigned long long)D;
+    double acc = 0.0;
+    for (int i = lane; i < D; i += 32) {
+        double v = (double)a[i];
+        acc = fma(v, v, acc);
+    }
+#pragma unroll
+    for (int m = 16; m > 0; m >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, m);
+    if (lane == 0) xx[row] = acc;
+}
+
+template <typename T>
+__global__ void fill_kernel(T* p, unsigned long long n, T v) {
+    unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+
+__global__ void fps_emit_kernel(const long long* picks, int first, int* out, unsigned long long n_samples) {
+    unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_samples) out[i] = i == 0 ? first : (int)picks[i - 1];
+}
+__global__ void kcenter_emit_kernel(const long long* picks, long long n_sel, long long* out, unsigned long long n_pick) {
+    unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_pick) return;
+    if (n_sel == 0) out[i] = i == 0 ? 0 : picks[i - 1];
+    else out[i] = picks[n_sel - 1 + i];
+}
+
+// ---- host side ------------------------------------------------------------------------------------------
+static void plan_emit(LeafPlan& pl, int start, int n) {
+    if (n <= 128) {
+        pl.start[pl.n_leaves] = (unsigned short)start;
+        pl.len[pl.n_leaves] = (unsigned short)n;
+        pl.merges[pl.n_leaves] = 0;
+        pl.n_leaves++;
+        return;
+    }
+    int n2 = n / 2;
+    n2 -= n2 % 8;
+    plan_emit(pl, start, n2);
+    plan_emit(pl, start + n2, n - n2);
+    pl.merges[pl.n_leaves - 1]++;
+}
+
+// workspace slots used by this module
+enum { WS_MIND = 0, WS_XX = 1, WS_WIN = 2, WS_CAND = 3, WS_BAR = 4, WS_FORCED = 5, WS_PICKS = 6, WS_F = 7, WS_OUT = 8 };
+
+template <typename T>
+struct Launch {
+    Params<T> p;
+    int grid = 0;
+    size_t smem = 0;
+};
+
+// Fill geometry (stride, tile rows, stages, grid) for a (T, D) problem.
+template <typename T, int MODE>
+static int configure(Ctx* c, Launch<T>& L, const T* dF, size_t N, size_t D) {
+    typedef typename std::conditional<MODE == MODE_KCENTER, double, T>::type RowVal;
+    Params<T>& p = L.p;
+    p.F = dF;
+    p.N = N;
+    p.D = (int)D;
+    const int vec_full = 16 / (int)sizeof(T);
+    int vec = ((D % vec_full) == 0 && ((uintptr_t)dF % 16) == 0) ? vec_full : 1;
+    // conflict-free row stride: 8 lanes x 4 row groups must cover all 32 banks (float: stride%32 in {8,24};
+    // double: stride%16 == 8, two half-warp phases)
+    int stride = (int)D;
+    for (;; stride += vec) {
+        if (sizeof(T) == 4 && (stride % 32 == 8 || stride % 32 == 24)) break;
+        if (sizeof(T) == 8 && (stride % 16 == 8)) break;
+    }
+    p.stride = stride;
+    p.vec = vec;
+    const size_t row_bytes = (size_t)stride * sizeof(T);
+    const size_t budget = (size_t)c->max_smem_optin - 2048;
+    const size_t fixed = align_up_dev((D + 8) * sizeof(T), 16) + WARPS * sizeof(Cand) + 64;
+    int nst = 4;
+    long rows = (long)((32 * 1024) / row_bytes) / 4 * 4;
+    if (rows < 4) rows = 4;
+    if (rows > 1024) rows = 1024;
+    auto need = [&](long r, int st) { return fixed + align_up_dev((size_t)r * sizeof(RowVal), 16) + (size_t)st * r * row_bytes; };
+    while (nst > 2 && need(rows, nst) > budget) --nst;
+    SSDR_REQUIRE(need(rows, nst) <= budget, SSDR_ERR_UNSUPPORTED,
+                 "feature dimension D=%zu needs %zu bytes of shared memory per CTA (limit %zu)", D, need(rows, nst), budget);
+    p.rows_per_tile = (int)rows;
+    p.nstages = nst;
+    L.smem = need(rows, nst);
+    p.plan.n_leaves = 0;
+    if (D >= 8) plan_emit(p.plan, 0, (int)D);
+    auto kern = select_kernel<T, MODE>;
+    SSDR_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smem));
+    int nb = 0;
+    SSDR_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, THREADS, L.smem));
+    SSDR_REQUIRE(nb >= 1, SSDR_ERR_CUDA, "selection kernel does not fit on an SM (smem %zu)", L.smem);
+    L.grid = c->sm_count;
+    return SSDR_OK;
+}
+
+template <typename T, int MODE>
+static int launch_steps(Launch<T>& L, int step_begin, int step_end, cudaStream_t s) {
+    L.p.step_begin = step_begin;
+    L.p.step_end = step_end;
+    SSDR_CHECK_CUDA(cudaMemsetAsync(L.p.barrier, 0, sizeof(unsigned), s));
+    void* args[] = {(void*)&L.p};
+    SSDR_CHECK_CUDA(cudaLaunchCooperativeKernel((void*)select_kernel<T, MODE>, dim3(L.grid), dim3(THREADS), args,
+                                                L.smem, s));
+    return SSDR_OK;
+}
+
+// Common set-up: workspaces, initial min-distance, forced centres.  d_forced may alias ws.
+template <typename T, int MODE>
+static int prepare(Ctx* c, Launch<T>& L, const T* dF, size_t N, size_t D, size_t row_begin, size_t row_end,
+                   const long long* d_forced, int n_forced, int n_steps, cudaStream_t s) {
+    SSDR_REQUIRE(N >= 1 && N < 0xFFFFFFFFull, SSDR_ERR_INVALID, "N=%zu out of range", N);
+    SSDR_REQUIRE(D >= 1 && D <= 8192, SSDR_ERR_UNSUPPORTED, "feature dimension D=%zu not in [1, 8192]", D);
+    SSDR_TRY((configure<T, MODE>(c, L, dF, N, D)));
+    Params<T>& p = L.p;
+    p.row_begin = row_begin;
+    p.row_end = row_end;
+    SSDR_TRY(c->ws[WS_MIND].reserve(N * sizeof(T)));
+    SSDR_TRY(c->ws[WS_WIN].reserve((size_t)(n_steps > 0 ? n_steps : 1) * 16));
+    SSDR_TRY(c->ws[WS_CAND].reserve((size_t)2 * L.grid * 16));
+    SSDR_TRY(c->ws[WS_BAR].reserve(256));
+    SSDR_TRY(c->ws[WS_PICKS].reserve((size_t)(n_steps > 0 ? n_steps : 1) * sizeof(long long)));
+    p.mind = c->ws[WS_MIND].as<T>();
+    p.winners = c->ws[WS_WIN].as<unsigned long long>();
+    p.cand = c->ws[WS_CAND].as<unsigned long long>();
+    p.barrier = c->ws[WS_BAR].as<unsigned>();
+    p.picks = c->ws[WS_PICKS].as<long long>();
+    p.forced = d_forced;
+    p.n_forced = n_forced;
+    p.xx = nullptr;
+    const unsigned blocks = (unsigned)((N + 255) / 256);
+    if (MODE == MODE_FPS) {
+        fill_kernel<T><<<blocks, 256, 0, s>>>(p.mind, N, (T)1e10);  // fps_gcn_cpu.py:135
+    } else {
+        fill_kernel<T><<<blocks, 256, 0, s>>>(p.mind, N, (T)INFINITY);  // min_distances None => first dist wins
+        SSDR_TRY(c->ws[WS_XX].reserve(N * sizeof(double)));
+        p.xx = c->ws[WS_XX].as<double>();
+        row_norms_kernel<T><<<(unsigned)((N + 7) / 8), 256, 0, s>>>(dF, N, (int)D, c->ws[WS_XX].as<double>());
+    }
+    SSDR_CHECK_CUDA(cudaGetLastError());
+    return SSDR_OK;
+}
+
+template <typename T>
+static int fps_dev(Ctx* c, const T* dF, size_t N, size_t D, int32_t first, size_t n_samples, int32_t* d_out,
+                   cudaStream_t s) {
+    SSDR_REQUIRE(dF && d_out, SSDR_ERR_INVALID, "NULL pointer");
+    SSDR_REQUIRE(n_samples >= 1 && n_samples < (1ull << 31), SSDR_ERR_INVALID, "n_samples=%zu out of range", n_samples);
+    SSDR_REQUIRE(first >= 0 && (size_t)first < N, SSDR_ERR_INVALID, "first index %d outside [0, %zu)", first, N);
+    const int n_steps = (int)n_samples - 1;
+    Launch<T> L;
+    SSDR_TRY(c->ws[WS_FORCED].reserve(sizeof(long long)));
+    long long f64 = first;
+    SSDR_CHECK_CUDA(cudaMemcpyAsync(c->ws[WS_FORCED].p, &f64, sizeof(f64), cudaMemcpyHostToDevice, s));
+    SSDR_TRY((prepare<T, MODE_FPS>(c, L, dF, N, D, 0, N, c->ws[WS_FORCED].as<long long>(), 1, n_steps, s)));
+    if (n_steps > 0) SSDR_TRY((launch_steps<T, MODE_FPS>(L, 0, n_steps, s)));
+    fps_emit_kernel<<<(unsigned)((n_samples + 255) / 256), 256, 0, s>>>(L.p.picks, first, d_out, n_samples);
+    SSDR_CHECK_CUDA(cudaGetLastError());
+    return SSDR_OK;
+}
+
+template <typename T>
+static int kcenter_dev(Ctx* c, const T* dX, size_t N, size_t D, const int64_t* d_sel, size_t n_sel, size_t n_pick,
+                       int64_t* d_out, cudaStream_t s) {
+    SSDR_REQUIRE(dX && (d_out || n_pick == 0) && (d_sel || n_sel == 0), SSDR_ERR_INVALID, "NULL pointer");
+    SSDR_REQUIRE(n_sel + n_pick < (1ull << 31), SSDR_ERR_INVALID, "too many steps");
+    if (n_pick == 0) return SSDR_OK;
+    Launch<T> L;
+    const long long* forced = reinterpret_cast<const long long*>(d_sel);
+    int n_forced = (int)n_sel;
+    if (n_sel == 0) {  // np.argmax(None) == 0 in the reference: the first pick is row 0
+        SSDR_TRY(c->ws[WS_FORCED].reserve(sizeof(long long)));
+        SSDR_CHECK_CUDA(cudaMemsetAsync(c->ws[WS_FORCED].p, 0, sizeof(long long), s));
+        forced = c->ws[WS_FORCED].as<long long>();
+        n_forced = 1;
+    }
+    // pick p is the winner of step n_sel-1+p (n_sel==0: pick 0 is row 0 itself, pick p>=1 the winner of step p-1)
+    const int n_steps = n_sel == 0 ? (int)n_pick - 1 : (int)(n_sel + n_pick) - 1;
+    SSDR_TRY((prepare<T, MODE_KCENTER>(c, L, dX, N, D, 0, N, forced, n_forced, n_steps, s)));
+    if (n_steps > 0) SSDR_TRY((launch_steps<T, MODE_KCENTER>(L, 0, n_steps, s)));
+    kcenter_emit_kernel<<<(unsigned)((n_pick + 255) / 256), 256, 0, s>>>(L.p.picks, (long long)n_sel,
+                                                                        reinterpret_cast<long long*>(d_out), n_pick);
+    SSDR_CHECK_CUDA(cudaGetLastError());
+    return SSDR_OK;
+}
+
+// host-pointer wrappers: stage in, run, copy picks out
+template <typename T>
+static int fps_host(const T* F, size_t N, size_t D, int32_t first, size_t n_samples, int32_t* out) {
+    SSDR_REQUIRE(F && out, SSDR_ERR_INVALID, "NULL pointer");
+    Ctx* c;
+    SSDR_TRY(get_ctx(&c));
+    SSDR_TRY(c->ws[WS_F].reserve(N * D * sizeof(T)));
+    SSDR_TRY(c->ws[WS_OUT].reserve(n_samples * sizeof(int32_t)));
+    SSDR_TRY(h2d(c, c->ws[WS_F].p, F, N * D * sizeof(T), c->stream));
+    SSDR_TRY(fps_dev<T>(c, c->ws[WS_F].as<T>(), N, D, first, n_samples, c->ws[WS_OUT].as<int32_t>(), c->stream));
+    return d2h_sync(c, out, c->ws[WS_OUT].p, n_samples * sizeof(int32_t), c->stream);
+}
+template <typename T>
+static int kcenter_host(const T* X, size_t N, size_t D, const int64_t* sel, size_t n_sel, size_t n_pick, int64_t* out) {
+    SSDR_REQUIRE(X && (out || !n_pick) && (sel || !n_sel), SSDR_ERR_INVALID, "NULL pointer");
+    for (size_t i = 0; i < n_sel; ++i)
+        SSDR_REQUIRE(sel[i] >= 0 && (size_t)sel[i] < N, SSDR_ERR_INVALID, "selected[%zu]=%lld outside [0, %zu)", i,
+                     (long long)sel[i], N);
+    Ctx* c;
+    SSDR_TRY(get_ctx(&c));
+    SSDR_TRY(c->ws[WS_F].reserve(N * D * sizeof(T)));
+    SSDR_TRY(c->ws[WS_OUT].reserve((n_pick + n_sel + 1) * sizeof(int64_t)));
+    SSDR_TRY(h2d(c, c->ws[WS_F].p, X, N * D * sizeof(T), c->stream));
+    int64_t* d_out = c->ws[WS_OUT].as<int64_t>();
+    int64_t* d_sel = d_out + n_pick;
+    SSDR_TRY(h2d(c, d_sel, sel, n_sel * sizeof(int64_t), c->stream));
+    SSDR_TRY(kcenter_dev<T>(c, c->ws[WS_F].as<T>(), N, D, d_sel, n_sel, n_pick, d_out, c->stream));
+    return d2h_sync(c, out, d_out, n_pick * sizeof(int64_t), c->stream);
+}
+
+}  // namespace sel
+}  // namespace ssdr
+
+using namespace ssdr;
+
+extern "C" {
+int ssdr_fps_f32(const float* F, size_t N, size_t D, int32_t first, size_t n, int32_t* out) {
+    return sel::fps_host<float>(F, N, D, first, n, out);
+}
+int ssdr_fps_f64(const double* F, size_t N, size_t D, int32_t first, size_t n, int32_t* out) {
+    return sel::fps_host<double>(F, N, D, first, n, out);
+}
+int ssdr_fps_f32_dev(const float* F, size_t N, size_t D, int32_t first, size_t n, int32_t* out, void* stream) {
+    Ctx* c;
+    SSDR_TRY(get_ctx(&c));
+    return sel::fps_dev<float>(c, F, N, D, first, n, out, stream ? (cudaStream_t)stream : c->stream);
+}
+int ssdr_fps_f64_dev(const double* F, size_t N, size_t D, int32_t first, size_t n, int32_t* out, void* stream) {
+    Ctx* c;
+    SSDR_TRY(get_ctx(&c));
+    return sel::fps_dev<double>(c, F, N, D, first, n, out, stream ? (cudaStream_t)stream : c->stream);
+}
+int ssdr_kcenter_f32(const float* X, size_t N, size_t D, const int64_t* sel_, size_t n_sel, size_t n_pick, int64_t* out) {
+    return sel::kcenter_host<float>(X, N, D, sel_, n_sel, n_pick, out);
+}
+int ssdr_kcenter_f64(const double* X, size_t N, size_t D, const int64_t* sel_, size_t n_sel, size_t n_pick, int64_t* out) {
+    return sel::kcenter_host<double>(X, N, D, sel_, n_sel, n_pick, out);
+}
+int ssdr_kcenter_f32_dev(const float* X, size_t N, size_t D, const int64_t* sel_, size_t n_sel, size_t n_pick,
+                         int64_t* out, void* stream) {
+    Ctx* c;
+    SSDR_TRY(get_ctx(&c));
+    return sel::kcenter_dev<float>(c, X, N, D, sel_, n_sel, n_pick, out, stream ? (cudaStream_t)stream : c->stream);
+}
+int ssdr_kcenter_f64_dev(const double* X, size_t N, size_t D, const int64_t* sel_, size_t n_sel, size_t n_pick,
+                         int64_t* out, void* stream) {
+    Ctx* c;
+    SSDR_TRY(get_ctx(&c));
+    return sel::kcenter_dev<double>(c, X, N, D, sel_, n_sel, n_pick, out, stream ? (cudaStream_t)stream : c->stream);
+}
+}

@@ -1,0 +1,38 @@
+"""KNN behind the reference's `nearest_neighbors` module interface (utils/nearest_neighbors/knn.pyx:33-149)."""
+import numpy as np
+
+from . import _lib
+
+
+def _check_dim(dim):
+    if dim != 3:
+        raise RuntimeError("ssdr_al_b200.nearest_neighbors supports dim == 3 only (got %d); every caller in the "
+                           "reference passes xyz" % dim)
+
+
+def knn(pts, queries, K, omp=False):
+    """knn.pyx:33-69.  `omp` only selected threading in the reference; results are identical, so it is ignored."""
+    indices = np.zeros((queries.shape[0], K), dtype=np.int64)
+    pts_c = np.ascontiguousarray(pts, dtype=np.float32)
+    queries_c = np.ascontiguousarray(queries, dtype=np.float32)
+    _check_dim(pts_c.shape[1])
+    _lib.check(_lib.lib().ssdr_knn(_lib.ptr(pts_c), pts_c.shape[0], pts_c.shape[1], _lib.ptr(queries_c),
+                                   queries_c.shape[0], int(K), _lib.ptr(indices)))
+    return indices
+
+
+def knn_batch(pts, queries, K, omp=False):
+    """knn.pyx:71-109."""
+    indices = np.zeros((pts.shape[0], queries.shape[1], K), dtype=np.int64)
+    pts_c = np.ascontiguousarray(pts, dtype=np.float32)
+    queries_c = np.ascontiguousarray(queries, dtype=np.float32)
+    _check_dim(pts_c.shape[2])
+    _lib.check(_lib.lib().ssdr_knn_batch(_lib.ptr(pts_c), pts_c.shape[0], pts_c.shape[1], pts_c.shape[2],
+                                         _lib.ptr(queries_c), queries_c.shape[1], int(K), _lib.ptr(indices)))
+    return indices
+
+
+def knn_batch_distance_pick(pts, nqueries, K, omp=False):
+    """knn.pyx:111-149.  The reference seeds this with time(0) (knn_.cxx:143), so it is not reproducible, and no
+    caller exists anywhere in SSDR-AL; it is exported only so that attribute lookups do not fail."""
+    raise NotImplementedError("knn_batch_distance_pick is unused by SSDR-AL and non-deterministic in the reference")

@@ -1,0 +1,91 @@
+"""GPU parity: FPS and k-center through the C ABI vs golden vectors (made by the reference) and the oracle."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def S():
+    import ssdr_al_b200 as S
+    return S
+
+
+@pytest.mark.parametrize("tag", ["d32", "d256", "d129_f64", "d3", "d20"])
+def test_fps_golden(S, golden, tag):
+    g = golden.fps
+    F, want = g[tag + "_F"], g[tag + "_picks"]
+    got = S.selection.fps(F, len(want), int(want[0]))
+    assert got.dtype == np.int32
+    assert np.array_equal(got, want)
+
+
+def test_fps_reference_rng_stream(S, golden):
+    g = golden.fps
+    np.random.seed(7)  # make_golden.py seeds numpy the same way before calling the reference
+    got = S.farthest_features_sample(g["d32_F"], len(g["d32_picks"]))
+    assert np.array_equal(got, g["d32_picks"])
+    np.random.seed(7)
+    got = S.farthest_features_sample(list(g["d20_F"]), len(g["d20_picks"]))  # list input, more picks than rows
+    assert np.array_equal(got, g["d20_picks"])
+
+
+@pytest.mark.parametrize("N,D,picks,dt", [
+    (20011, 32, 300, np.float32), (5003, 256, 150, np.float32), (3001, 136, 100, np.float32),
+    (4000, 1000, 40, np.float32), (7000, 5, 200, np.float32), (6000, 33, 100, np.float32),
+    (2500, 64, 120, np.float64), (1500, 300, 60, np.float64), (999, 1, 50, np.float32),
+])
+def test_fps_vs_oracle(S, oracle, N, D, picks, dt):
+    rng = np.random.default_rng(N + D)
+    F = rng.standard_normal((N, D)).astype(dt)
+    first = int(rng.integers(0, N))
+    assert np.array_equal(S.selection.fps(F, picks, first), oracle.fps(F, picks, first))
+
+
+def test_fps_ties_take_lowest_index(S, oracle):
+    # heavy duplication: many rows share the same distance; np.argmax must pick the first
+    rng = np.random.default_rng(3)
+    base = rng.integers(0, 4, (40, 16)).astype(np.float32)
+    F = base[rng.integers(0, 40, 5000)]
+    assert np.array_equal(S.selection.fps(F, 80, 17), oracle.fps(F, 80, 17))
+
+
+def test_fps_edge_cases(S):
+    F = np.arange(12, dtype=np.float32).reshape(4, 3)
+    assert np.array_equal(S.selection.fps(F, 1, 2), [2])
+    assert S.selection.fps(F, 0, 0).shape == (0,)
+    with pytest.raises(RuntimeError):
+        S.selection.fps(F, 2, 9)  # first index out of range
+
+
+def test_fps_large_property(S):
+    """BASELINE config-4 shape (500k x 32): picks are distinct, start with `first`, and each pick maximises the
+    running min-distance (checked on a sample of steps with numpy in float64 tolerance-free form)."""
+    rng = np.random.default_rng(3)
+    N, D, picks = 500_000, 32, 64
+    F = rng.standard_normal((N, D)).astype(np.float32)
+    got = S.selection.fps(F, picks, 12345)
+    assert got[0] == 12345 and len(set(got.tolist())) == picks
+    mind = np.full(N, 1e10)
+    for s in range(picks - 1):
+        d = np.sum((F - F[got[s]]) ** 2, axis=-1)
+        mind = np.minimum(mind, d)
+        assert got[s + 1] == int(np.argmax(mind))
+
+
+@pytest.mark.parametrize("tag", ["d129_f64", "d32_f32", "d256_f64"])
+def test_kcenter_golden(S, golden, tag):
+    g = golden.kcenter
+    X, sel, want = g[tag + "_X"], g[tag + "_sel"], g[tag + "_picks"]
+    got = S.kCenterGreedy(X).select_batch_(sel, len(want))
+    assert isinstance(got, list) and isinstance(got[0], np.int64)
+    assert np.array_equal(np.asarray(got), want)
+
+
+@pytest.mark.parametrize("N,D,dt", [(20000, 32, np.float32), (8000, 129, np.float64), (6000, 256, np.float32),
+                                    (3000, 7, np.float64)])
+def test_kcenter_vs_oracle(S, oracle, N, D, dt):
+    rng = np.random.default_rng(N)
+    X = rng.standard_normal((N, D)).astype(dt)
+    sel = np.arange(N - 100, N)
+    assert np.array_equal(S.selection.kcenter(X, sel, 150), oracle.kcenter(X, sel, 150))
