@@ -30,7 +30,8 @@ struct Meta {
     float dl;
     unsigned long long nX, nY, nZ;
     int key_bits;
-    int error;  // 1: key space too large, 2: more than LABEL_CAP distinct labels in one voxel
+    int error;  // 2: more than LABEL_CAP distinct labels in one voxel
+    unsigned long long max_key;  // largest key seen (key_kernel) -> number of radix bits worth sorting
     unsigned long long M;
 };
 
@@ -79,9 +80,9 @@ __global__ void minmax_kernel(const float* __restrict__ pts, unsigned long long 
 // float -> size_t the way x86-64 gcc does it for |v| < 2^63 (truncate to int64, reinterpret)
 __device__ __forceinline__ unsigned long long f2u64(float v) { return (unsigned long long)(long long)v; }
 
-__device__ __forceinline__ int bits_for(unsigned long long n) {  // bits needed to represent values < n
-    int b = 0;
-    while (b < 64 && (n > (1ull << b))) ++b;
+static int bits_for_value(unsigned long long v) {  // radix bits needed to order values <= v
+    int b = 1;
+    while (b < 64 && (v >> b)) ++b;
     return b;
 }
 
@@ -107,34 +108,47 @@ __global__ void setup_kernel(const float* __restrict__ partials, int nparts, flo
         m.nX = f2u64(floorf(__fdiv_rn(__fsub_rn(m.mx[0], m.origin[0]), dl))) + 1ull;
         m.nY = f2u64(floorf(__fdiv_rn(__fsub_rn(m.mx[1], m.origin[1]), dl))) + 1ull;
         m.nZ = f2u64(floorf(__fdiv_rn(__fsub_rn(m.mx[2], m.origin[2]), dl))) + 1ull;
-        // the largest key is bounded by nX*nY*nZ (+ slack for a point one cell below the origin through rounding)
-        const int bx = bits_for(m.nX + 1), by = bits_for(m.nY + 1), bz = bits_for(m.nZ + 1);
         m.error = 0;
-        m.key_bits = bx + by + bz;
-        if (m.key_bits > 62 || !(dl > 0.0f)) m.error = 1;
+        m.key_bits = 64;
+        m.max_key = 0;
         m.M = 0;
         *meta = m;
     }
 }
 
 // ---- 3. voxel keys --------------------------------------------------------------------------------------
-template <typename KeyT>
-__global__ void key_kernel(const float* __restrict__ pts, unsigned long long N, const Meta* __restrict__ meta,
-                           KeyT* __restrict__ keys, unsigned* __restrict__ idx) {
+// Keys are computed in wrapping 64-bit arithmetic exactly like the reference's size_t expression, so even
+// degenerate inputs (a point rounding to one cell below the origin, overflowing nX*nY*nZ) group identically.
+__global__ void key_kernel(const float* __restrict__ pts, unsigned long long N, Meta* __restrict__ meta,
+                           unsigned long long* __restrict__ keys, unsigned* __restrict__ idx) {
     const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= N) return;
-    const float dl = meta->dl;
-    const unsigned long long iX = f2u64(floorf(__fdiv_rn(__fsub_rn(__ldg(pts + 3 * i + 0), meta->origin[0]), dl)));
-    const unsigned long long iY = f2u64(floorf(__fdiv_rn(__fsub_rn(__ldg(pts + 3 * i + 1), meta->origin[1]), dl)));
-    const unsigned long long iZ = f2u64(floorf(__fdiv_rn(__fsub_rn(__ldg(pts + 3 * i + 2), meta->origin[2]), dl)));
-    const unsigned long long key = iX + meta->nX * iY + meta->nX * meta->nY * iZ;
-    keys[i] = (KeyT)key;
-    idx[i] = (unsigned)i;
+    unsigned long long key = 0;
+    if (i < N) {
+        const float dl = meta->dl;
+        const unsigned long long iX = f2u64(floorf(__fdiv_rn(__fsub_rn(__ldg(pts + 3 * i + 0), meta->origin[0]), dl)));
+        const unsigned long long iY = f2u64(floorf(__fdiv_rn(__fsub_rn(__ldg(pts + 3 * i + 1), meta->origin[1]), dl)));
+        const unsigned long long iZ = f2u64(floorf(__fdiv_rn(__fsub_rn(__ldg(pts + 3 * i + 2), meta->origin[2]), dl)));
+        key = iX + meta->nX * iY + meta->nX * meta->nY * iZ;
+        keys[i] = key;
+        idx[i] = (unsigned)i;
+    }
+    unsigned long long mk = key;
+#pragma unroll
+    for (int m = 16; m > 0; m >>= 1) {
+        unsigned long long o = __shfl_xor_sync(0xffffffffu, mk, m);
+        mk = o > mk ? o : mk;
+    }
+    __shared__ unsigned long long smax[8];
+    if ((threadIdx.x & 31) == 0) smax[threadIdx.x >> 5] = mk;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < (int)(blockDim.x >> 5); ++w) mk = smax[w] > mk ? smax[w] : mk;
+        atomicMax(&meta->max_key, mk);
+    }
 }
 
-template <typename KeyT>
 struct HeadPred {
-    const KeyT* keys;
+    const unsigned long long* keys;
     __device__ __forceinline__ bool operator()(const unsigned& i) const { return i == 0 || keys[i] != keys[i - 1]; }
 };
 
@@ -200,9 +214,9 @@ __device__ int label_first_in_iteration_order(const int* labels, const int* coun
 }
 
 // ---- 6. per-voxel sequential reduce -----------------------------------------------------------------------
-template <typename KeyT, int FD>  // FD = compile-time feature width, -1 = generic (accumulate in the output row)
+template <int FD>  // FD = compile-time feature width, -1 = generic (accumulate in the output row)
 __global__ void reduce_kernel(const float* __restrict__ pts, const float* __restrict__ feats,
-                              const int* __restrict__ cls, int fdim, int ldim, const KeyT* __restrict__ keys,
+                              const int* __restrict__ cls, int fdim, int ldim, const unsigned long long* __restrict__ keys,
                               const unsigned* __restrict__ idx, const unsigned* __restrict__ starts,
                               unsigned long long N, unsigned long long M, float* __restrict__ out_p,
                               float* __restrict__ out_f, int* __restrict__ out_c,
@@ -293,7 +307,7 @@ __global__ void reduce_kernel(const float* __restrict__ pts, const float* __rest
         out_c[v * ldim + col] = nbest == 1 ? labs[arg] : label_first_in_iteration_order(labs, cnts, nl, best);
     }
     if (overflow) meta->error = 2;
-    out_k[v] = (unsigned long long)keys[s];
+    out_k[v] = keys[s];
     out_n[v] = count;
 }
 
@@ -318,9 +332,20 @@ static void free_handle(Handle* h) {
     delete h;
 }
 
-template <typename KeyT>
-static int sort_and_reduce(Ctx* c, cudaStream_t s, const float* d_p, const float* d_f, const int* d_c, size_t N,
-                           size_t fdim, size_t ldim, int key_bits, Handle* h) {
+static int run_dev(Ctx* c, cudaStream_t s, const float* d_p, const float* d_f, const int* d_c, size_t N, size_t fdim,
+                   size_t ldim, float dl, int order, size_t* M_out, void** handle) {
+    typedef unsigned long long KeyT;
+    SSDR_REQUIRE(d_p && M_out && handle, SSDR_ERR_INVALID, "NULL pointer");
+    SSDR_REQUIRE(N >= 1, SSDR_ERR_EMPTY, "Error");
+    SSDR_REQUIRE(N < 0x7FFFFFFFull, SSDR_ERR_UNSUPPORTED, "N=%zu exceeds 2^31-2 points per call", N);
+    SSDR_REQUIRE(order == SSDR_GRID_ORDER_KEY, SSDR_ERR_UNSUPPORTED,
+                 "order=REFERENCE (libstdc++ hash iteration order) is not implemented on the device yet");
+    SSDR_REQUIRE(dl > 0.0f, SSDR_ERR_INVALID, "sampleDl must be positive");
+    if (!d_f) fdim = 0;
+    if (!d_c) ldim = 0;
+    const int nparts = c->sm_count * 4;
+    SSDR_TRY(c->ws[WS_META].reserve(sizeof(Meta)));
+    SSDR_TRY(c->ws[WS_PART].reserve((size_t)nparts * 6 * sizeof(float)));
     SSDR_TRY(c->ws[WS_KEYS].reserve(N * sizeof(KeyT)));
     SSDR_TRY(c->ws[WS_KEYS2].reserve(N * sizeof(KeyT)));
     SSDR_TRY(c->ws[WS_IDX].reserve(N * sizeof(unsigned)));
@@ -332,40 +357,59 @@ static int sort_and_reduce(Ctx* c, cudaStream_t s, const float* d_p, const float
     unsigned* idx = c->ws[WS_IDX].as<unsigned>();
     unsigned* idx2 = c->ws[WS_IDX2].as<unsigned>();
     unsigned* starts = c->ws[WS_STARTS].as<unsigned>();
-    const unsigned blocks = (unsigned)((N + 255) / 256);
-    key_kernel<KeyT><<<blocks, 256, 0, s>>>(d_p, N, meta, keys, idx);
+
+    minmax_kernel<<<nparts, MM_BLOCK, 0, s>>>(d_p, N, c->ws[WS_PART].as<float>());
+    setup_kernel<<<1, 32, 0, s>>>(c->ws[WS_PART].as<float>(), nparts, dl, meta);
+    key_kernel<<<(unsigned)((N + 255) / 256), 256, 0, s>>>(d_p, N, meta, keys, idx);
     SSDR_CHECK_CUDA(cudaGetLastError());
+    Meta hm;
+    SSDR_TRY(d2h_sync(c, &hm, meta, sizeof(Meta), s));  // sync 1: how many key bits are worth sorting
+    const int key_bits = bits_for_value(hm.max_key);
 
     cub::DoubleBuffer<KeyT> kb(keys, keys2);
     cub::DoubleBuffer<unsigned> vb(idx, idx2);
     size_t t1 = 0, t2 = 0;
-    if (key_bits < 1) key_bits = 1;
-    SSDR_CHECK_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, t1, kb, vb, (unsigned)N, 0, key_bits, s));
+    SSDR_CHECK_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, t1, kb, vb, (int)N, 0, key_bits, s));
     cub::CountingInputIterator<unsigned> counting(0);
-    HeadPred<KeyT> pred{keys};
-    SSDR_CHECK_CUDA(cub::DeviceSelect::If(nullptr, t2, counting, starts, &meta->M, (unsigned)N, pred, s));
+    HeadPred pred{keys};
+    SSDR_CHECK_CUDA(cub::DeviceSelect::If(nullptr, t2, counting, starts, &meta->M, (int)N, pred, s));
     SSDR_TRY(c->ws[WS_TEMP].reserve(t1 > t2 ? t1 : t2));
-    SSDR_CHECK_CUDA(cub::DeviceRadixSort::SortPairs(c->ws[WS_TEMP].p, t1, kb, vb, (unsigned)N, 0, key_bits, s));
+    SSDR_CHECK_CUDA(cub::DeviceRadixSort::SortPairs(c->ws[WS_TEMP].p, t1, kb, vb, (int)N, 0, key_bits, s));
     pred.keys = kb.Current();
-    SSDR_CHECK_CUDA(cub::DeviceSelect::If(c->ws[WS_TEMP].p, t2, counting, starts, &meta->M, (unsigned)N, pred, s));
-    Meta hm;
-    SSDR_TRY(d2h_sync(c, &hm, meta, sizeof(Meta), s));
+    SSDR_CHECK_CUDA(cub::DeviceSelect::If(c->ws[WS_TEMP].p, t2, counting, starts, &meta->M, (int)N, pred, s));
+    SSDR_TRY(d2h_sync(c, &hm, meta, sizeof(Meta), s));  // sync 2: M, to size the outputs
     const size_t M = (size_t)hm.M;
     SSDR_REQUIRE(M >= 1 && M <= N, SSDR_ERR_EMPTY, "Error");
+
+    Handle* h = new Handle();
+    h->stream = s;
+    h->device = c->device;
     h->M = M;
-    h->fdim = d_f ? fdim : 0;
-    h->ldim = d_c ? ldim : 0;
-    SSDR_CHECK_CUDA(cudaMalloc(&h->d_p, M * 3 * sizeof(float)));
-    if (h->fdim) SSDR_CHECK_CUDA(cudaMalloc(&h->d_f, M * h->fdim * sizeof(float)));
-    if (h->ldim) SSDR_CHECK_CUDA(cudaMalloc(&h->d_c, M * h->ldim * sizeof(int)));
-    SSDR_CHECK_CUDA(cudaMalloc(&h->d_k, M * sizeof(unsigned long long)));
-    SSDR_CHECK_CUDA(cudaMalloc(&h->d_n, M * sizeof(int)));
-    const unsigned vb_blocks = (unsigned)((M + 127) / 128);
-#define SSDR_REDUCE(FDV)                                                                                       \
-    reduce_kernel<KeyT, FDV><<<vb_blocks, 128, 0, s>>>(d_p, d_f, d_c, (int)h->fdim, (int)h->ldim, kb.Current(), \
-                                                       vb.Current(), starts, N, M, h->d_p, h->d_f, h->d_c,    \
-                                                       h->d_k, h->d_n, meta)
-    switch (h->fdim) {
+    h->fdim = fdim;
+    h->ldim = ldim;
+    auto fail = [&](int rc) {
+        free_handle(h);
+        return rc;
+    };
+#define SSDR_ALLOC(ptr, bytes)                                                                            \
+    do {                                                                                                  \
+        cudaError_t _e = cudaMalloc((void**)&(ptr), (bytes));                                             \
+        if (_e != cudaSuccess) {                                                                          \
+            cudaGetLastError();                                                                           \
+            return fail(set_error(SSDR_ERR_NOMEM, "cudaMalloc(%zu) failed: %s", (size_t)(bytes), cudaGetErrorString(_e))); \
+        }                                                                                                 \
+    } while (0)
+    SSDR_ALLOC(h->d_p, M * 3 * sizeof(float));
+    if (fdim) SSDR_ALLOC(h->d_f, M * fdim * sizeof(float));
+    if (ldim) SSDR_ALLOC(h->d_c, M * ldim * sizeof(int));
+    SSDR_ALLOC(h->d_k, M * sizeof(unsigned long long));
+    SSDR_ALLOC(h->d_n, M * sizeof(int));
+#undef SSDR_ALLOC
+    const unsigned vblocks = (unsigned)((M + 127) / 128);
+#define SSDR_REDUCE(FDV)                                                                                         \
+    reduce_kernel<FDV><<<vblocks, 128, 0, s>>>(d_p, d_f, d_c, (int)fdim, (int)ldim, kb.Current(), vb.Current(), \
+                                               starts, N, M, h->d_p, h->d_f, h->d_c, h->d_k, h->d_n, meta)
+    switch (fdim) {
         case 0: SSDR_REDUCE(0); break;
         case 1: SSDR_REDUCE(1); break;
         case 2: SSDR_REDUCE(2); break;
@@ -376,44 +420,15 @@ static int sort_and_reduce(Ctx* c, cudaStream_t s, const float* d_p, const float
         default: SSDR_REDUCE(-1); break;
     }
 #undef SSDR_REDUCE
-    SSDR_CHECK_CUDA(cudaGetLastError());
-    if (h->ldim) {  // the only late failure mode is a label-table overflow; surface it before results are used
-        SSDR_TRY(d2h_sync(c, &hm, meta, sizeof(Meta), s));
-        SSDR_REQUIRE(hm.error != 2, SSDR_ERR_UNSUPPORTED, "more than %d distinct labels inside one voxel", LABEL_CAP);
+    {
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return fail(set_error(SSDR_ERR_CUDA, "reduce_kernel launch failed: %s", cudaGetErrorString(e)));
     }
-    return SSDR_OK;
-}
-
-static int run_dev(Ctx* c, cudaStream_t s, const float* d_p, const float* d_f, const int* d_c, size_t N, size_t fdim,
-                   size_t ldim, float dl, int order, size_t* M_out, void** handle) {
-    SSDR_REQUIRE(d_p && M_out && handle, SSDR_ERR_INVALID, "NULL pointer");
-    SSDR_REQUIRE(N >= 1, SSDR_ERR_EMPTY, "Error");
-    SSDR_REQUIRE(N < 0xFFFFFFFFull, SSDR_ERR_UNSUPPORTED, "N=%zu exceeds 2^32-2 points per call", N);
-    SSDR_REQUIRE(order == SSDR_GRID_ORDER_KEY, SSDR_ERR_UNSUPPORTED,
-                 "order=REFERENCE (libstdc++ hash iteration order) is not implemented on the device yet");
-    SSDR_REQUIRE(dl > 0.0f, SSDR_ERR_INVALID, "sampleDl must be positive");
-    if (!d_f) fdim = 0;
-    if (!d_c) ldim = 0;
-    const int nparts = c->sm_count * 4;
-    SSDR_TRY(c->ws[WS_META].reserve(sizeof(Meta)));
-    SSDR_TRY(c->ws[WS_PART].reserve((size_t)nparts * 6 * sizeof(float)));
-    Meta* meta = c->ws[WS_META].as<Meta>();
-    minmax_kernel<<<nparts, MM_BLOCK, 0, s>>>(d_p, N, c->ws[WS_PART].as<float>());
-    setup_kernel<<<1, 32, 0, s>>>(c->ws[WS_PART].as<float>(), nparts, dl, meta);
-    SSDR_CHECK_CUDA(cudaGetLastError());
-    Meta hm;
-    SSDR_TRY(d2h_sync(c, &hm, meta, sizeof(Meta), s));
-    SSDR_REQUIRE(hm.error == 0, SSDR_ERR_UNSUPPORTED,
-                 "voxel key space %llu x %llu x %llu needs more than 62 bits (sampleDl too small for the extent?)",
-                 hm.nX, hm.nY, hm.nZ);
-    Handle* h = new Handle();
-    h->stream = s;
-    h->device = c->device;
-    int rc = hm.key_bits <= 32 ? sort_and_reduce<unsigned>(c, s, d_p, d_f, d_c, N, fdim, ldim, hm.key_bits, h)
-                               : sort_and_reduce<unsigned long long>(c, s, d_p, d_f, d_c, N, fdim, ldim, hm.key_bits, h);
-    if (rc != SSDR_OK) {
-        free_handle(h);
-        return rc;
+    if (ldim) {  // the only late failure mode is a label-table overflow; surface it before results are used
+        int rc = d2h_sync(c, &hm, meta, sizeof(Meta), s);
+        if (rc != SSDR_OK) return fail(rc);
+        if (hm.error == 2)
+            return fail(set_error(SSDR_ERR_UNSUPPORTED, "more than %d distinct labels inside one voxel", LABEL_CAP));
     }
     *M_out = h->M;
     *handle = h;
