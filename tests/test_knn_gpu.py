@@ -1,0 +1,170 @@
+"""GPU parity: KNN through the C ABI vs golden vectors (made by the reference nanoflann build) and the oracle.
+Indices must be BIT-EXACT, including rows where equal fp32 distances make nanoflann's tree-visit order decide."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+CLOUDS = ["uniform", "room", "quant", "dups", "tiny"]
+
+
+@pytest.fixture(scope="module")
+def NN():
+    import ssdr_al_b200 as S
+    return S.nearest_neighbors
+
+
+def _room(rng, n, quant=None):
+    face = rng.integers(0, 3, n)
+    p = rng.random((n, 3)) * np.array([7.0, 5.0, 3.0])
+    p[face == 0, 2] = 0.0
+    p[face == 1, 1] = 0.0
+    p[face == 2, 0] = 0.0
+    p += rng.normal(0, 0.005, p.shape)
+    if quant:
+        p = np.round(p / quant) * quant
+    return p.astype(np.float32)
+
+
+def _device_tree(pts):
+    from ssdr_al_b200 import _lib
+    pts = np.ascontiguousarray(pts, np.float32)
+    n = len(pts)
+    cap = 2 * n + 2
+    vind = np.zeros(n, np.uint32)
+    nn = np.zeros(1, np.uint32)
+    a = dict(left=np.zeros(cap, np.uint32), right=np.zeros(cap, np.uint32), child1=np.zeros(cap, np.int32),
+             child2=np.zeros(cap, np.int32), divfeat=np.zeros(cap, np.int32), divlow=np.zeros(cap, np.float32),
+             divhigh=np.zeros(cap, np.float32))
+    _lib.check(_lib.lib().ssdr_knn_debug_tree(_lib.ptr(pts), n, _lib.ptr(vind), _lib.ptr(nn), _lib.ptr(a["left"]),
+                                              _lib.ptr(a["right"]), _lib.ptr(a["child1"]), _lib.ptr(a["child2"]),
+                                              _lib.ptr(a["divfeat"]), _lib.ptr(a["divlow"]), _lib.ptr(a["divhigh"])))
+    return vind, {k: v[:nn[0]] for k, v in a.items()}
+
+
+def _node_table(nodes):
+    out = {}
+    for i in range(len(nodes["left"])):
+        key = (int(nodes["left"][i]), int(nodes["right"][i]))
+        out[key] = None if nodes["child1"][i] < 0 else (int(nodes["divfeat"][i]), float(nodes["divlow"][i]),
+                                                       float(nodes["divhigh"][i]))
+    return out
+
+
+@pytest.mark.parametrize("name", CLOUDS)
+def test_device_tree_equals_oracle_tree(oracle, golden, name):
+    p = golden.knn[name + "_pts"]
+    vind, nodes = _device_tree(p)
+    ovind, onodes = oracle.kdtree_export(p)
+    assert np.array_equal(vind.astype(np.int64), ovind)
+    assert _node_table(nodes) == _node_table(onodes)
+
+
+def test_device_tree_degenerate_clouds(oracle):
+    rng = np.random.default_rng(9)
+    for p in (np.ones((700, 3), np.float32),
+              np.stack([rng.random(900), np.zeros(900), np.zeros(900)], 1).astype(np.float32),
+              rng.random((11, 3), dtype=np.float32), rng.random((1, 3), dtype=np.float32),
+              rng.random((50_000, 3), dtype=np.float32)):
+        vind, nodes = _device_tree(p)
+        ovind, onodes = oracle.kdtree_export(p)
+        assert np.array_equal(vind.astype(np.int64), ovind)
+        assert _node_table(nodes) == _node_table(onodes)
+
+
+@pytest.mark.parametrize("name", CLOUDS)
+def test_knn_golden_self_k16(NN, golden, name):
+    g = golden.knn
+    p, want = g[name + "_pts"], g[name + "_k16"]
+    got = NN.knn(p, p, want.shape[1], omp=True)
+    assert got.dtype == np.int64 and got.shape == want.shape
+    assert np.array_equal(got, want)
+
+
+@pytest.mark.parametrize("name", CLOUDS)
+def test_knn_golden_external_queries(NN, golden, name):
+    g = golden.knn
+    p, q = g[name + "_pts"], g[name + "_q"]
+    assert np.array_equal(NN.knn(p, q, 1), g[name + "_q_k1"])
+    assert np.array_equal(NN.knn(p, q, 5), g[name + "_q_k5"])
+
+
+def test_knn_golden_batch_and_upsampling(NN, golden):
+    g = golden.knn
+    bp = g["batch_pts"]
+    assert np.array_equal(NN.knn_batch(bp, bp, 16, omp=True), g["batch_k16"])
+    sub = bp[:, :300, :]  # non-contiguous slice, exactly like s3dis_dataset.py:166
+    assert not sub.flags["C_CONTIGUOUS"]
+    assert np.array_equal(NN.knn_batch(sub, bp, 1, omp=True), g["batch_sub_k1"])
+
+
+def test_knn_k_larger_than_npts(NN, golden):
+    g = golden.knn
+    p = g["small_pts"]
+    got = NN.knn(p, p[:1], 10)
+    assert np.array_equal(got, g["small_k10"])
+
+
+@pytest.mark.parametrize("K", [1, 3, 16, 20, 40])
+def test_knn_vs_oracle_tie_free_and_tied(NN, oracle, K):
+    rng = np.random.default_rng(K)
+    clouds = {
+        "uniform": rng.random((60_000, 3), dtype=np.float32) * np.float32(4.0) - np.float32(2.0),
+        "room": _room(rng, 60_000),
+        "quant": _room(rng, 30_000, quant=0.01),
+        "dups": rng.random((4000, 3), dtype=np.float32)[rng.integers(0, 4000, 30_000)],
+        "plane": np.concatenate([rng.random((20_000, 2), dtype=np.float32), np.zeros((20_000, 1), np.float32)], 1),
+    }
+    for name, p in clouds.items():
+        want = oracle.knn(p, p, K, threads=8)
+        got = NN.knn(p, p, K)
+        bad = np.flatnonzero((got != want).any(axis=1))
+        assert bad.size == 0, "%s: %d rows differ, first %d: %s vs %s" % (name, bad.size, bad[0], got[bad[0]], want[bad[0]])
+
+
+def test_knn_external_queries_outside_bbox(NN, oracle):
+    rng = np.random.default_rng(77)
+    p = _room(rng, 40_000)
+    q = (rng.random((20_000, 3)) * np.array([12.0, 9.0, 6.0]) - 2.5).astype(np.float32)
+    for K in (1, 16):
+        assert np.array_equal(NN.knn(p, q, K), oracle.knn(p, q, K, threads=8))
+
+
+def test_knn_batch_randla_pyramid_config2_shapes(NN, oracle):
+    """BASELINE config 2 (scaled to 2 x 40960 so the oracle finishes in seconds): the loop of s3dis_dataset.py:164-177."""
+    rng = np.random.default_rng(1)
+    B, N = 2, 40960
+    xyz = (rng.uniform(-1, 1, (B, N, 3)) * np.array([2.0, 2.0, 1.5])).astype(np.float32)
+    for ratio in (4, 4, 4, 4, 2):
+        neigh = NN.knn_batch(xyz, xyz, 16, omp=True)
+        assert np.array_equal(neigh, oracle.knn_batch(xyz, xyz, 16, threads=8))
+        sub = xyz[:, : xyz.shape[1] // ratio, :]
+        up = NN.knn_batch(sub, xyz, 1, omp=True)
+        assert np.array_equal(up, oracle.knn_batch(sub, xyz, 1, threads=8))
+        xyz = sub
+
+
+def test_knn_config1_full_size_properties(NN):
+    """Config-1-sized cloud (~107k barycentres): self is the first neighbour, rows ascend in distance, and a random
+    sample of rows equals brute force."""
+    rng = np.random.default_rng(0)
+    p = np.unique(np.round(_room(rng, 400_000) / 0.04).astype(np.int32), axis=0).astype(np.float32) * np.float32(0.04)
+    p += rng.normal(0, 0.003, p.shape).astype(np.float32)
+    idx = NN.knn(p, p, 16)
+    assert (idx[:, 0] == np.arange(len(p))).all()
+    d = ((p[idx] - p[:, None, :]) ** 2).sum(-1)
+    assert (np.diff(d, axis=1) >= -1e-7).all()
+    for r in rng.integers(0, len(p), 50):
+        bd = ((p - p[r]) ** 2).sum(-1)
+        assert set(np.argsort(bd, kind="stable")[:16].tolist()) == set(idx[r].tolist())
+
+
+def test_knn_interface_contract(NN):
+    p = np.random.default_rng(0).random((100, 3))
+    assert NN.knn(p.astype(np.float64), p[:7], 4).shape == (7, 4)  # float64 is coerced like np.ascontiguousarray(., f32)
+    with pytest.raises(RuntimeError, match="dim"):
+        NN.knn(np.zeros((10, 2), np.float32), np.zeros((3, 2), np.float32), 2)
+    with pytest.raises(NotImplementedError):
+        NN.knn_batch_distance_pick(p[None], 10, 4)
