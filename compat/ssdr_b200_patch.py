@@ -1,0 +1,31 @@
+"""One-line activation of the GPU selection loop inside an unmodified SSDR-AL checkout:
+
+    import ssdr_b200_patch; ssdr_b200_patch.install()
+
+farthest_features_sample is defined inside fps_gcn_cpu.py / fps_gcn_cuda.py themselves (fps_gcn_cpu.py:119,
+fps_gcn_cuda.py:123) and looked up as a module global by GCN_FPS_sampling (fps_gcn_cpu.py:170), so rebinding the
+module attribute is enough; kCenterGreedy is rebound in gcn.py's namespace (gcn.py:10 star-import)."""
+import importlib
+import os
+import sys
+
+_REPO = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
+if _REPO not in sys.path:
+    sys.path.insert(0, _REPO)
+
+
+def install(modules=("fps_gcn_cpu", "fps_gcn_cuda", "gcn", "kcenterGreedy")):
+    from ssdr_al_b200.selection import farthest_features_sample, kCenterGreedy
+    patched = []
+    for name in modules:
+        try:
+            mod = sys.modules.get(name) or importlib.import_module(name)
+        except Exception:
+            continue
+        if hasattr(mod, "farthest_features_sample"):
+            mod.farthest_features_sample = farthest_features_sample
+            patched.append(name + ".farthest_features_sample")
+        if hasattr(mod, "kCenterGreedy"):
+            mod.kCenterGreedy = kCenterGreedy
+            patched.append(name + ".kCenterGreedy")
+    return patched

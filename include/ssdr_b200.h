@@ -17,7 +17,8 @@
  *   - "host" entry points borrow caller-owned host buffers (row-major, C-contiguous) for the duration of the
  *     call and write caller-allocated outputs -- the same ownership rule as the reference prototypes.
  *   - "_dev" entry points take device pointers on the current device plus a cudaStream_t passed as void*
- *     (NULL = the library's per-thread stream); they enqueue work and do not synchronise unless documented.
+ *     (NULL = the CUDA default stream, exactly as in a kernel launch), so the work is ordered with the caller's own
+ *     work on that stream.  Use one stream per calling thread: the per-thread workspaces are reused across calls.
  *   - The library is re-entrant per calling thread (per-thread stream + workspace).  It refuses to run in a
  *     fork()ed child of a process that already initialised it (SSDR_ERR_FORK) instead of hanging.
  *   - There is no CPU fallback: without a CUDA device every compute entry point fails with SSDR_ERR_CUDA.
@@ -69,6 +70,9 @@ typedef struct {
     uint64_t tie_rows;        /* rows whose top-(K+1) held an exact or near fp32 distance tie (re-resolved) */
     uint64_t tree_builds;     /* nanoflann-identical trees built on device for those rows */
     uint64_t dist_evals;      /* candidate distance evaluations of the main kernel */
+    double grid_build_ms;     /* device time of stage A (bbox, cell counting sort of points and queries) */
+    double main_kernel_ms;    /* device time of the main query kernel alone (CUDA events on the launch stream) */
+    double tie_path_ms;       /* device time of the tie path (tree build + exact replay), 0 when unused */
 } ssdr_knn_stats;
 
 /* Device-resident variant: d_points (B,npts,3), d_queries (B,nqueries,3), d_indices (B,nqueries,K) int64.

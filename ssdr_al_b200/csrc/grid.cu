@@ -322,13 +322,13 @@ struct Handle {
     int device = 0;
 };
 
-static void free_handle(Handle* h) {
+static void free_handle(Handle* h) {  // stream-ordered pool: no device-wide synchronisation, memory is recycled
     if (!h) return;
-    if (h->d_p) cudaFree(h->d_p);
-    if (h->d_f) cudaFree(h->d_f);
-    if (h->d_c) cudaFree(h->d_c);
-    if (h->d_k) cudaFree(h->d_k);
-    if (h->d_n) cudaFree(h->d_n);
+    if (h->d_p) cudaFreeAsync(h->d_p, h->stream);
+    if (h->d_f) cudaFreeAsync(h->d_f, h->stream);
+    if (h->d_c) cudaFreeAsync(h->d_c, h->stream);
+    if (h->d_k) cudaFreeAsync(h->d_k, h->stream);
+    if (h->d_n) cudaFreeAsync(h->d_n, h->stream);
     delete h;
 }
 
@@ -393,10 +393,10 @@ static int run_dev(Ctx* c, cudaStream_t s, const float* d_p, const float* d_f, c
     };
 #define SSDR_ALLOC(ptr, bytes)                                                                            \
     do {                                                                                                  \
-        cudaError_t _e = cudaMalloc((void**)&(ptr), (bytes));                                             \
+        cudaError_t _e = cudaMallocAsync((void**)&(ptr), (bytes), s);                                             \
         if (_e != cudaSuccess) {                                                                          \
             cudaGetLastError();                                                                           \
-            return fail(set_error(SSDR_ERR_NOMEM, "cudaMalloc(%zu) failed: %s", (size_t)(bytes), cudaGetErrorString(_e))); \
+            return fail(set_error(SSDR_ERR_NOMEM, "cudaMallocAsync(%zu) failed: %s", (size_t)(bytes), cudaGetErrorString(_e))); \
         }                                                                                                 \
     } while (0)
     SSDR_ALLOC(h->d_p, M * 3 * sizeof(float));
@@ -447,7 +447,7 @@ int ssdr_grid_subsample_dev(const float* d_points, const float* d_feats, const i
                             void** handle) {
     Ctx* c;
     SSDR_TRY(get_ctx(&c));
-    return grid::run_dev(c, stream ? (cudaStream_t)stream : c->stream, d_points, d_feats, d_classes, N, fdim, ldim,
+    return grid::run_dev(c, (cudaStream_t)stream, d_points, d_feats, d_classes, N, fdim, ldim,
                          sampleDl, order, M_out, handle);
 }
 

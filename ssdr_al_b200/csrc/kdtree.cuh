@@ -3,14 +3,17 @@
 //
 // build_kernel reproduces KDTreeSingleIndexAdaptor::buildIndex (utils/nearest_neighbors/nanoflann.hpp:1136-1147,
 // divideTree :848-896, middleSplit_ :898-937, planeSplit :948-975) bit for bit -- same vind permutation, same
-// divfeat/divlow/divhigh -- but level-synchronously and data-parallel:
-//   * one CTA per batch item walks the tree one LEVEL at a time over flat position arrays;
-//   * a node's tight bbox (computeMinMax) is a segmented atomic min/max over its positions;
-//   * each of planeSplit's two Hoare sweeps is a prefix count: the k-th misplaced element from the left swaps with
-//     the k-th misplaced element from the right (validated against the sequential code in
-//     tools/proto_kdtree.py and tests/test_knn_gpu.py::test_device_tree_equals_oracle_tree).
+// divfeat/divlow/divhigh -- as ONE persistent cooperative launch for all batch items:
+//   * the tree is grown level by level; a grid barrier separates levels, work lists carry the nodes to split;
+//   * a node with more than SMALL_MAX points is split by a whole CTA (block-wide prefix counts over global memory),
+//     a smaller node by ONE WARP entirely in shared memory (ballot/popc prefix counts), so deep levels with
+//     thousands of nodes use every warp of the GPU;
+//   * computeMinMax is a warp/block min-max reduction; each of planeSplit's two Hoare sweeps is a prefix count: the
+//     k-th misplaced element from the left swaps with the k-th misplaced element from the right (SURVEY.md A.5;
+//     checked against the sequential code in tools/proto_kdtree.py and
+//     tests/test_knn_gpu.py::test_device_tree_equals_sequential_tree).
 // exact_query_kernel replays findNeighbors/searchLevel (:1163-1178, :1270-1328) and KNNResultSet::addPoint
-// (:72-96) with one thread per flagged query and an explicit stack.
+// (:72-96) with one thread per flagged query, an explicit stack and one 32-byte node record per visit.
 #pragma once
 #include "common.cuh"
 
@@ -18,46 +21,67 @@ namespace ssdr {
 namespace kdtree {
 
 constexpr int BT = 1024;
+constexpr int NW = BT / 32;
 constexpr int IPT = 4;
 constexpr int LEAF = 10;
+constexpr int SMALL_MAX = 512;
+constexpr int MAX_LEVELS = 512;
 constexpr int MAX_DEPTH = 96;
 constexpr int MAX_K = 64;
+constexpr int WARP_SMEM = SMALL_MAX * 4 + SMALL_MAX * 4 + SMALL_MAX + SMALL_MAX;  // sv, sval, sL(u16), sR(u16)
 
-__device__ __forceinline__ unsigned f2ord(float f) {
-    unsigned u = __float_as_uint(f);
-    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
-}
-__device__ __forceinline__ float ord2f(unsigned u) {
-    return __uint_as_float((u & 0x80000000u) ? (u & 0x7FFFFFFFu) : ~u);
-}
-
-struct Tree {             // all pointers are per-item base pointers; item b uses offset b*N (positions) / b*cap (nodes)
-    unsigned N, cap;      // points per item, node capacity per item (2N+2)
-    unsigned* vind;       // [B*N]   position -> point index (nanoflann's vind)
-    unsigned* node_of;    // [B*N]   position -> node currently owning it
-    unsigned* lpos;       // [B*N]   scratch: k-th misplaced position from the left, per node at [l+k]
-    unsigned* rpos;       // [B*N]   scratch: k-th misplaced position from the right
-    unsigned* psat;       // [B*N]   inclusive prefix count of predicate-true positions
-    unsigned* pfail;      // [B*N]   inclusive prefix count of predicate-false positions
-    unsigned* nl;         // [B*cap] node range [nl, nr)
-    unsigned* nr;
-    float* lo;            // [B*cap*3] loose bbox (root bbox cut by the ancestors' planes) -- drives middleSplit_
-    float* hi;
-    unsigned* tlo;        // [B*cap*3] tight bbox, order-preserving uint encoding
-    unsigned* thi;
-    int* c1;              // [B*cap] children (-1 = leaf)
-    int* c2;
-    int* feat;            // [B*cap] split dimension
-    float* cutval;        // [B*cap]
-    unsigned* start;      // [B*cap] first position of the current Hoare sweep
-    unsigned* totsat;     // [B*cap] predicate-true count of the current sweep
-    unsigned* lim1;       // [B*cap]
-    unsigned char* active;  // [B*cap]
-    unsigned* n_nodes;    // [B]
-    const unsigned char* item_needed;  // [B] build only where a flagged row lives
+struct __align__(16) NodeRec {
+    int c1, c2;            // children (per-item node ids), -1 = leaf          nanoflann.hpp:853-856
+    int feat;              // split dimension                                   :877
+    unsigned pad;
+    float divlow, divhigh; // tight max of left child / min of right child      :886-887
+    unsigned l, r;         // vind range [l, r)
 };
 
-// block-wide inclusive scan of one u64 per thread (low word / high word carry two independent counters)
+struct Tree {
+    unsigned N, cap, B;    // points per item, node capacity per item (2N+2), items
+    unsigned lcap;         // capacity of one work list
+    unsigned* vind;        // [B*N]   position -> point index (nanoflann's vind)
+    unsigned* lpos;        // [B*N]   big-node scratch: k-th misplaced position from the left, at [l+k]
+    unsigned* rpos;        // [B*N]   ... from the right
+    unsigned* psat;        // [B*N]   inclusive prefix count of predicate-true positions (from the sweep start)
+    unsigned* pfail;       // [B*N]   inclusive prefix count of predicate-false positions
+    NodeRec* nodes;        // [B*cap]
+    float* nlo;            // [B*cap*3] loose bbox (root bbox cut by the ancestors' planes) -- drives middleSplit_
+    float* nhi;
+    float* root_lo;        // [B*3] tight root bbox (computeBoundingBox :1241-1263)
+    float* root_hi;
+    unsigned* node_count;  // [B]
+    unsigned* list;        // [2 parities][2 classes][lcap] global node ids (item*cap + node)
+    unsigned* list_cnt;    // [(MAX_LEVELS+1)*2]
+    unsigned* barrier;     // grid barrier counter
+    unsigned* error;       // bit 0: node capacity, bit 1: level cap, bit 2: DFS stack
+    const unsigned char* item_needed;  // [B] build only where a flagged row lives (nullptr = all)
+};
+
+__device__ __forceinline__ unsigned ld_acq(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];\n" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void red_rel_add(unsigned* p, unsigned v) {
+    asm volatile("red.release.gpu.global.add.u32 [%0], %1;\n" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void grid_sync(unsigned* counter, unsigned& phase) {
+    __syncthreads();
+    ++phase;
+    if (threadIdx.x == 0) {
+        __threadfence();
+        red_rel_add(counter, 1u);
+        const unsigned target = phase * gridDim.x;
+        while (ld_acq(counter) < target) {
+        }
+        __threadfence();
+    }
+    __syncthreads();
+}
+
+// block-wide inclusive scan of one u64 per thread (low / high word carry two independent counters)
 __device__ __forceinline__ unsigned long long block_scan_incl(unsigned long long v, unsigned long long* s_warp,
                                                               unsigned long long* total) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -69,313 +93,469 @@ __device__ __forceinline__ unsigned long long block_scan_incl(unsigned long long
     if (lane == 31) s_warp[warp] = v;
     __syncthreads();
     if (warp == 0) {
-        unsigned long long w = lane < (BT / 32) ? s_warp[lane] : 0ull;
+        unsigned long long w = lane < NW ? s_warp[lane] : 0ull;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
             unsigned long long n = __shfl_up_sync(0xffffffffu, w, o);
             if (lane >= o) w += n;
         }
-        s_warp[lane] = w;  // inclusive warp totals
+        s_warp[lane] = w;
     }
     __syncthreads();
     const unsigned long long base = warp ? s_warp[warp - 1] : 0ull;
-    *total = s_warp[BT / 32 - 1];
+    *total = s_warp[NW - 1];
     v += base;
-    __syncthreads();  // s_warp is reused by the next call
+    __syncthreads();
     return v;
 }
 
-__global__ void __launch_bounds__(BT, 1) build_kernel(const float* __restrict__ pts_all, Tree t) {
-    const unsigned b = blockIdx.x;
-    if (t.item_needed && !t.item_needed[b]) return;
-    const unsigned N = t.N, cap = t.cap;
-    const float* pts = pts_all + (size_t)b * N * 3;
-    unsigned* vind = t.vind + (size_t)b * N;
-    unsigned* node_of = t.node_of + (size_t)b * N;
-    unsigned* lpos = t.lpos + (size_t)b * N;
-    unsigned* rpos = t.rpos + (size_t)b * N;
-    unsigned* psat = t.psat + (size_t)b * N;
-    unsigned* pfail = t.pfail + (size_t)b * N;
-    unsigned* nl = t.nl + (size_t)b * cap;
-    unsigned* nr = t.nr + (size_t)b * cap;
-    float* lo = t.lo + (size_t)b * cap * 3;
-    float* hi = t.hi + (size_t)b * cap * 3;
-    unsigned* tlo = t.tlo + (size_t)b * cap * 3;
-    unsigned* thi = t.thi + (size_t)b * cap * 3;
-    int* c1 = t.c1 + (size_t)b * cap;
-    int* c2 = t.c2 + (size_t)b * cap;
-    int* feat = t.feat + (size_t)b * cap;
-    float* cutval = t.cutval + (size_t)b * cap;
-    unsigned* start = t.start + (size_t)b * cap;
-    unsigned* totsat = t.totsat + (size_t)b * cap;
-    unsigned* lim1 = t.lim1 + (size_t)b * cap;
-    unsigned char* active = t.active + (size_t)b * cap;
-
-    __shared__ unsigned long long s_warp[32];
-    __shared__ unsigned s_level_begin, s_level_end, s_next, s_nactive;
-    const unsigned tid = threadIdx.x;
-
-    for (unsigned i = tid; i < N; i += BT) {
-        vind[i] = i;
-        node_of[i] = 0;
+// middleSplit_ (:898-929): split dimension and cut value from the loose bbox and the node's tight min/max
+__device__ __forceinline__ void decide_split(const float lo[3], const float hi[3], const float mn[3], const float mx[3],
+                                             int* cf_out, float* cv_out) {
+    const float EPS = 0.00001f;
+    float span[3];
+#pragma unroll
+    for (int d = 0; d < 3; ++d) span[d] = __fsub_rn(hi[d], lo[d]);
+    float max_span = span[0];
+    if (span[1] > max_span) max_span = span[1];
+    if (span[2] > max_span) max_span = span[2];
+    const float thr = __fmul_rn(__fsub_rn(1.0f, EPS), max_span);
+    float max_spread = -1.f;
+    int cf = 0;
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+        if (span[d] > thr) {
+            const float spread = __fsub_rn(mx[d], mn[d]);
+            if (spread > max_spread) {
+                cf = d;
+                max_spread = spread;
+            }
+        }
     }
-    if (tid == 0) {
-        nl[0] = 0;
-        nr[0] = N;
-        c1[0] = c2[0] = -1;
-        s_level_begin = 0;
-        s_level_end = 1;
-    }
-    __syncthreads();
+    const float lo_c = cf == 0 ? lo[0] : (cf == 1 ? lo[1] : lo[2]);
+    const float hi_c = cf == 0 ? hi[0] : (cf == 1 ? hi[1] : hi[2]);
+    const float mn_c = cf == 0 ? mn[0] : (cf == 1 ? mn[1] : mn[2]);
+    const float mx_c = cf == 0 ? mx[0] : (cf == 1 ? mx[1] : mx[2]);
+    const float split_val = __fdiv_rn(__fadd_rn(lo_c, hi_c), 2.0f);
+    float cv;
+    if (split_val < mn_c) cv = mn_c;
+    else if (split_val > mx_c) cv = mx_c;
+    else cv = split_val;
+    *cf_out = cf;
+    *cv_out = cv;
+}
 
-    for (int level = 0;; ++level) {
-        const unsigned lb = s_level_begin, le = s_level_end;
-        // ---- P1: tight bbox (computeMinMax) of every node of this level
-        for (unsigned n = lb + tid; n < le; n += BT) {
+// divideTree's bookkeeping for one split node (:877-892): children records, loose bboxes, next-level work lists
+__device__ __forceinline__ void emit_children(const Tree& t, unsigned g, unsigned b, unsigned l, unsigned r,
+                                              unsigned idx, int cf, float cv, float divlow, float divhigh,
+                                              const float lo[3], const float hi[3], int level) {
+    const unsigned a = atomicAdd(&t.node_count[b], 2u);
+    if (a + 1 >= t.cap) {
+        atomicOr(t.error, 1u);
+        return;
+    }
+    const unsigned ga = b * t.cap + a, gb = ga + 1;
+    NodeRec ra, rb;
+    ra.c1 = ra.c2 = rb.c1 = rb.c2 = -1;
+    ra.feat = rb.feat = 0;
+    ra.pad = rb.pad = 0;
+    ra.divlow = ra.divhigh = rb.divlow = rb.divhigh = 0.f;
+    ra.l = l;
+    ra.r = l + idx;
+    rb.l = l + idx;
+    rb.r = r;
+    t.nodes[ga] = ra;
+    t.nodes[gb] = rb;
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+        t.nlo[(size_t)ga * 3 + d] = lo[d];
+        t.nhi[(size_t)ga * 3 + d] = (d == cf) ? cv : hi[d];
+        t.nlo[(size_t)gb * 3 + d] = (d == cf) ? cv : lo[d];
+        t.nhi[(size_t)gb * 3 + d] = hi[d];
+    }
+    NodeRec me;
+    me.c1 = (int)a;
+    me.c2 = (int)(a + 1);
+    me.feat = cf;
+    me.pad = 0;
+    me.divlow = divlow;
+    me.divhigh = divhigh;
+    me.l = l;
+    me.r = r;
+    t.nodes[g] = me;
+    if (level + 1 >= MAX_LEVELS) {
+        atomicOr(t.error, 2u);
+        return;
+    }
+    unsigned* next = t.list + (size_t)(((level + 1) & 1) * 2) * t.lcap;
+    const unsigned cl = idx, cr = (r - l) - idx;
+    if (cl > (unsigned)LEAF) {
+        const int cls = cl > (unsigned)SMALL_MAX ? 0 : 1;
+        const unsigned pos = atomicAdd(&t.list_cnt[(level + 1) * 2 + cls], 1u);
+        next[(size_t)cls * t.lcap + pos] = ga;
+    }
+    if (cr > (unsigned)LEAF) {
+        const int cls = cr > (unsigned)SMALL_MAX ? 0 : 1;
+        const unsigned pos = atomicAdd(&t.list_cnt[(level + 1) * 2 + cls], 1u);
+        next[(size_t)cls * t.lcap + pos] = gb;
+    }
+}
+
+// ---- one warp splits one node of <= SMALL_MAX points in shared memory --------------------------------------
+__device__ __forceinline__ void split_small(const float* __restrict__ pts_all, const Tree& t, unsigned g, int level,
+                                            unsigned char* wsm) {
+    const int lane = threadIdx.x & 31;
+    const unsigned ltmask = (1u << lane) - 1u;
+    unsigned* sv = reinterpret_cast<unsigned*>(wsm);
+    float* sval = reinterpret_cast<float*>(wsm + SMALL_MAX * 4);
+    unsigned short* sL = reinterpret_cast<unsigned short*>(wsm + SMALL_MAX * 8);
+    unsigned short* sR = sL + SMALL_MAX / 2;
+    const unsigned b = g / t.cap;
+    const float* pts = pts_all + (size_t)b * t.N * 3;
+    unsigned* vind = t.vind + (size_t)b * t.N;
+    const unsigned l = __ldcg(&t.nodes[g].l), r = __ldcg(&t.nodes[g].r);
+    const unsigned count = r - l;
+    float lo[3], hi[3];
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+        lo[d] = __ldcg(&t.nlo[(size_t)g * 3 + d]);
+        hi[d] = __ldcg(&t.nhi[(size_t)g * 3 + d]);
+    }
+    const int nslot = (int)((count + 31) / 32);
+    // computeMinMax over the node (:827-836)
+    float mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
+    for (int s = 0; s < nslot; ++s) {
+        const unsigned p = (unsigned)s * 32 + lane;
+        if (p < count) {
+            const unsigned v = __ldcg(vind + l + p);
+            sv[p] = v;
 #pragma unroll
             for (int d = 0; d < 3; ++d) {
-                tlo[n * 3 + d] = 0xFFFFFFFFu;
-                thi[n * 3 + d] = 0u;
-            }
-            active[n] = 0;
-        }
-        if (tid == 0) {
-            s_next = 0;
-            s_nactive = 0;
-        }
-        __syncthreads();
-        for (unsigned base = 0; base < N; base += BT) {
-            const unsigned i = base + tid;
-            const bool in = i < N;
-            unsigned n = in ? node_of[i] : 0xFFFFFFFFu;
-            const bool mine = in && n >= lb;
-            unsigned e[3] = {0, 0, 0};
-            if (mine) {
-                const unsigned p = vind[i];
-#pragma unroll
-                for (int d = 0; d < 3; ++d) e[d] = f2ord(__ldg(pts + 3 * (size_t)p + d));
-            }
-            if (!mine) n = 0xFFFFFFFFu;
-            // warp aggregation when the whole warp sits in one node (the common case near the root)
-            const unsigned n0 = __shfl_sync(0xffffffffu, n, 0);
-            if (__all_sync(0xffffffffu, n == n0)) {
-                if (n0 != 0xFFFFFFFFu) {
-                    unsigned mn[3] = {e[0], e[1], e[2]}, mx[3] = {e[0], e[1], e[2]};
-#pragma unroll
-                    for (int d = 0; d < 3; ++d)
-#pragma unroll
-                        for (int m = 16; m > 0; m >>= 1) {
-                            mn[d] = min(mn[d], __shfl_xor_sync(0xffffffffu, mn[d], m));
-                            mx[d] = max(mx[d], __shfl_xor_sync(0xffffffffu, mx[d], m));
-                        }
-                    if ((tid & 31) == 0) {
-#pragma unroll
-                        for (int d = 0; d < 3; ++d) {
-                            atomicMin(&tlo[n0 * 3 + d], mn[d]);
-                            atomicMax(&thi[n0 * 3 + d], mx[d]);
-                        }
-                    }
-                }
-            } else if (mine) {
-#pragma unroll
-                for (int d = 0; d < 3; ++d) {
-                    atomicMin(&tlo[n * 3 + d], e[d]);
-                    atomicMax(&thi[n * 3 + d], e[d]);
-                }
+                const float x = __ldg(pts + 3 * (size_t)v + d);
+                mn[d] = fminf(mn[d], x);
+                mx[d] = fmaxf(mx[d], x);
             }
         }
-        __syncthreads();
-        // ---- P2: middleSplit_ decisions (nanoflann.hpp:898-929)
-        for (unsigned n = lb + tid; n < le; n += BT) {
-            const unsigned l = nl[n], r = nr[n];
-            if (level == 0) {  // root: loose bbox = data bbox (computeBoundingBox :1241-1263)
+    }
 #pragma unroll
-                for (int d = 0; d < 3; ++d) {
-                    lo[n * 3 + d] = ord2f(tlo[n * 3 + d]);
-                    hi[n * 3 + d] = ord2f(thi[n * 3 + d]);
-                }
-            }
-            if (r - l > (unsigned)LEAF) {
-                const float EPS = 0.00001f;
-                float span[3], max_span;
+    for (int d = 0; d < 3; ++d)
 #pragma unroll
-                for (int d = 0; d < 3; ++d) span[d] = __fsub_rn(hi[n * 3 + d], lo[n * 3 + d]);
-                max_span = span[0];
-                if (span[1] > max_span) max_span = span[1];
-                if (span[2] > max_span) max_span = span[2];
-                const float thr = __fmul_rn(__fsub_rn(1.0f, EPS), max_span);
-                float max_spread = -1.f;
-                int cf = 0;
-#pragma unroll
-                for (int d = 0; d < 3; ++d) {
-                    if (span[d] > thr) {
-                        const float spread = __fsub_rn(ord2f(thi[n * 3 + d]), ord2f(tlo[n * 3 + d]));
-                        if (spread > max_spread) {
-                            cf = d;
-                            max_spread = spread;
-                        }
-                    }
-                }
-                const float split_val = __fdiv_rn(__fadd_rn(lo[n * 3 + cf], hi[n * 3 + cf]), 2.0f);
-                const float mn = ord2f(tlo[n * 3 + cf]), mx = ord2f(thi[n * 3 + cf]);
-                float cv;
-                if (split_val < mn) cv = mn;
-                else if (split_val > mx) cv = mx;
-                else cv = split_val;
-                feat[n] = cf;
-                cutval[n] = cv;
-                start[n] = l;
-                active[n] = 1;
-                atomicAdd(&s_nactive, 1u);
-            }
+        for (int m = 16; m > 0; m >>= 1) {
+            mn[d] = fminf(mn[d], __shfl_xor_sync(0xffffffffu, mn[d], m));
+            mx[d] = fmaxf(mx[d], __shfl_xor_sync(0xffffffffu, mx[d], m));
         }
-        __syncthreads();
-        if (s_nactive == 0) break;
+    int cf;
+    float cv;
+    decide_split(lo, hi, mn, mx, &cf, &cv);
+    __syncwarp();
+    for (int s = 0; s < nslot; ++s) {
+        const unsigned p = (unsigned)s * 32 + lane;
+        if (p < count) sval[p] = __ldg(pts + 3 * (size_t)sv[p] + cf);
+    }
+    __syncwarp();
+    // planeSplit (:948-975): sweep 0 uses "< cutval" from position 0, sweep 1 "<= cutval" from lim1
+    unsigned start = 0, lim1 = 0, lim2 = 0;
+    for (int sweep = 0; sweep < 2; ++sweep) {
+        unsigned tot = 0;
+        for (int s = 0; s < nslot; ++s) {
+            const unsigned p = (unsigned)s * 32 + lane;
+            const bool in = p < count && p >= start;
+            const float v = in ? sval[p] : 0.f;
+            const bool sat = in && (sweep == 0 ? (v < cv) : (v <= cv));
+            tot += __popc(__ballot_sync(0xffffffffu, sat));
+        }
+        const unsigned lim = start + tot;
+        unsigned sb = 0, fb = 0, m = 0;
+        for (int s = 0; s < nslot; ++s) {
+            const unsigned p = (unsigned)s * 32 + lane;
+            const bool in = p < count && p >= start;
+            const float v = in ? sval[p] : 0.f;
+            const bool sat = in && (sweep == 0 ? (v < cv) : (v <= cv));
+            const bool fail = in && !sat;
+            const unsigned bs = __ballot_sync(0xffffffffu, sat), bf = __ballot_sync(0xffffffffu, fail);
+            const bool left_misplaced = fail && p < lim;
+            if (left_misplaced) sL[fb + __popc(bf & ltmask)] = (unsigned short)p;
+            if (sat && p >= lim) sR[tot - (sb + __popc(bs & ltmask) + 1)] = (unsigned short)p;
+            m += __popc(__ballot_sync(0xffffffffu, left_misplaced));
+            sb += __popc(bs);
+            fb += __popc(bf);
+        }
+        __syncwarp();
+        for (unsigned k = lane; k < m; k += 32) {
+            const unsigned a = sL[k], c = sR[k];
+            const unsigned va = sv[a], vc = sv[c];
+            sv[a] = vc;
+            sv[c] = va;
+            const float fa = sval[a], fc = sval[c];
+            sval[a] = fc;
+            sval[c] = fa;
+        }
+        __syncwarp();
+        if (sweep == 0) {
+            lim1 = lim;
+            start = lim;
+        } else {
+            lim2 = lim;
+        }
+    }
+    unsigned idx;  // :934-936
+    if (lim1 > count / 2) idx = lim1;
+    else if (lim2 < count / 2) idx = lim2;
+    else idx = count / 2;
+    float dlow = -INFINITY, dhigh = INFINITY;
+    for (int s = 0; s < nslot; ++s) {
+        const unsigned p = (unsigned)s * 32 + lane;
+        if (p < count) {
+            const float v = sval[p];
+            if (p < idx) dlow = fmaxf(dlow, v);
+            else dhigh = fminf(dhigh, v);
+            vind[l + p] = sv[p];
+        }
+    }
+#pragma unroll
+    for (int m = 16; m > 0; m >>= 1) {
+        dlow = fmaxf(dlow, __shfl_xor_sync(0xffffffffu, dlow, m));
+        dhigh = fminf(dhigh, __shfl_xor_sync(0xffffffffu, dhigh, m));
+    }
+    if (lane == 0) emit_children(t, g, b, l, r, idx, cf, cv, dlow, dhigh, lo, hi, level);
+    __syncwarp();
+}
 
-        // ---- planeSplit: two Hoare sweeps as prefix counts (nanoflann.hpp:948-975)
-        for (int sweep = 0; sweep < 2; ++sweep) {
-            unsigned long long carry = 0;
-            for (unsigned base = 0; base < N; base += BT * IPT) {
-                const unsigned i0 = base + tid * IPT;
-                unsigned long long f[IPT];
-                unsigned long long local = 0;
+// ---- one CTA splits one node of > SMALL_MAX points over global memory -----------------------------------------
+__device__ __forceinline__ void split_big(const float* __restrict__ pts_all, const Tree& t, unsigned g, int level,
+                                          unsigned long long* s_warp, float* s_red, float* s_bc) {
+    const unsigned tid = threadIdx.x;
+    const int lane = tid & 31, warp = tid >> 5;
+    const unsigned b = g / t.cap;
+    const float* pts = pts_all + (size_t)b * t.N * 3;
+    unsigned* vind = t.vind + (size_t)b * t.N;
+    unsigned* lpos = t.lpos + (size_t)b * t.N;
+    unsigned* rpos = t.rpos + (size_t)b * t.N;
+    unsigned* psat = t.psat + (size_t)b * t.N;
+    unsigned* pfail = t.pfail + (size_t)b * t.N;
+    __syncthreads();  // smem broadcast slots may still be read by a previous node's stragglers
+    const unsigned l = __ldcg(&t.nodes[g].l), r = __ldcg(&t.nodes[g].r);
+    const unsigned count = r - l;
+    float lo[3], hi[3];
 #pragma unroll
-                for (int k = 0; k < IPT; ++k) {
-                    const unsigned i = i0 + k;
-                    unsigned long long fl = 0;
-                    if (i < N) {
-                        const unsigned n = node_of[i];
-                        if (n >= lb && active[n] && i >= start[n]) {
-                            const float v = __ldg(pts + 3 * (size_t)vind[i] + feat[n]);
-                            const float cv = cutval[n];
-                            const bool sat = sweep == 0 ? (v < cv) : (v <= cv);
-                            fl = sat ? 1ull : (1ull << 32);
-                        }
-                    }
-                    local += fl;
-                    f[k] = local;  // inclusive inside the thread
-                }
-                unsigned long long tot;
-                const unsigned long long incl = block_scan_incl(local, s_warp, &tot);
-                const unsigned long long excl = incl - local + carry;
+    for (int d = 0; d < 3; ++d) {
+        lo[d] = __ldcg(&t.nlo[(size_t)g * 3 + d]);
+        hi[d] = __ldcg(&t.nhi[(size_t)g * 3 + d]);
+    }
+    float mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
+    for (unsigned i = l + tid; i < r; i += BT) {
+        const unsigned v = __ldcg(vind + i);
 #pragma unroll
-                for (int k = 0; k < IPT; ++k) {
-                    const unsigned i = i0 + k;
-                    if (i < N) {
-                        const unsigned long long v = excl + f[k];
-                        psat[i] = (unsigned)(v & 0xFFFFFFFFull);
-                        pfail[i] = (unsigned)(v >> 32);
-                    }
-                }
-                carry += tot;
-            }
-            __syncthreads();
-            for (unsigned n = lb + tid; n < le; n += BT) {
-                if (active[n]) {
-                    const unsigned s0 = start[n], r = nr[n];
-                    unsigned ts = 0;
-                    if (r > s0) ts = psat[r - 1] - (s0 > 0 ? psat[s0 - 1] : 0u);
-                    totsat[n] = ts;
-                }
-            }
-            __syncthreads();
-            for (unsigned base = 0; base < N; base += BT) {
-                const unsigned i = base + tid;
-                if (i < N) {
-                    const unsigned n = node_of[i];
-                    if (n >= lb && active[n]) {
-                        const unsigned s0 = start[n];
-                        if (i >= s0) {
-                            const unsigned ts = totsat[n], lim = s0 + ts, l = nl[n];
-                            const unsigned bs = s0 > 0 ? psat[s0 - 1] : 0u, bf = s0 > 0 ? pfail[s0 - 1] : 0u;
-                            const unsigned cs = psat[i] - bs, cfl = pfail[i] - bf;  // inclusive counts from s0
-                            const bool sat = (i == 0 ? psat[0] : psat[i] - psat[i - 1]) != 0;
-                            if (!sat) {
-                                if (i < lim) lpos[l + (cfl - 1)] = i;
-                            } else {
-                                if (i >= lim) rpos[l + (ts - cs)] = i;
-                            }
-                        }
-                    }
-                }
-            }
-            __syncthreads();
-            for (unsigned base = 0; base < N; base += BT) {
-                const unsigned i = base + tid;
-                if (i < N) {
-                    const unsigned n = node_of[i];
-                    if (n >= lb && active[n]) {
-                        const unsigned s0 = start[n], ts = totsat[n], lim = s0 + ts, l = nl[n];
-                        unsigned m = 0;  // misplaced pairs = predicate-false positions in [s0, lim)
-                        if (lim > s0) m = pfail[lim - 1] - (s0 > 0 ? pfail[s0 - 1] : 0u);
-                        const unsigned k = i - l;
-                        if (k < m) {
-                            const unsigned a = lpos[l + k], bb = rpos[l + k];
-                            const unsigned va = vind[a], vb = vind[bb];
-                            vind[a] = vb;
-                            vind[bb] = va;
-                        }
-                    }
-                }
-            }
-            __syncthreads();
-            for (unsigned n = lb + tid; n < le; n += BT) {
-                if (active[n]) {
-                    const unsigned lim = start[n] + totsat[n];
-                    if (sweep == 0) {
-                        lim1[n] = lim;
-                        start[n] = lim;
-                    } else {
-                        // ---- split index (middleSplit_ :934-936) and children (divideTree :877-892)
-                        const unsigned l = nl[n], r = nr[n], count = r - l;
-                        const unsigned l1 = lim1[n] - l, l2 = lim - l;
-                        unsigned idx;
-                        if (l1 > count / 2) idx = l1;
-                        else if (l2 < count / 2) idx = l2;
-                        else idx = count / 2;
-                        const unsigned off = atomicAdd(&s_next, 2u);
-                        const unsigned a = le + off, bb = a + 1;
-                        const int cf = feat[n];
-                        const float cv = cutval[n];
-                        nl[a] = l;
-                        nr[a] = l + idx;
-                        nl[bb] = l + idx;
-                        nr[bb] = r;
-#pragma unroll
-                        for (int d = 0; d < 3; ++d) {
-                            const float lv = lo[n * 3 + d], hv = hi[n * 3 + d];
-                            lo[a * 3 + d] = lv;
-                            hi[a * 3 + d] = (d == cf) ? cv : hv;
-                            lo[bb * 3 + d] = (d == cf) ? cv : lv;
-                            hi[bb * 3 + d] = hv;
-                        }
-                        c1[a] = c2[a] = c1[bb] = c2[bb] = -1;
-                        c1[n] = (int)a;
-                        c2[n] = (int)bb;
-                    }
-                }
-            }
-            __syncthreads();
+        for (int d = 0; d < 3; ++d) {
+            const float x = __ldg(pts + 3 * (size_t)v + d);
+            mn[d] = fminf(mn[d], x);
+            mx[d] = fmaxf(mx[d], x);
         }
-        // ---- positions move to their child node
-        for (unsigned base = 0; base < N; base += BT) {
-            const unsigned i = base + tid;
-            if (i < N) {
-                const unsigned n = node_of[i];
-                if (n >= lb && active[n]) {
-                    const unsigned a = (unsigned)c1[n];
-                    node_of[i] = i < nr[a] ? a : (unsigned)c2[n];
+    }
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+#pragma unroll
+        for (int m = 16; m > 0; m >>= 1) {
+            mn[d] = fminf(mn[d], __shfl_xor_sync(0xffffffffu, mn[d], m));
+            mx[d] = fmaxf(mx[d], __shfl_xor_sync(0xffffffffu, mx[d], m));
+        }
+        if (lane == 0) {
+            s_red[d * NW + warp] = mn[d];
+            s_red[(3 + d) * NW + warp] = mx[d];
+        }
+    }
+    __syncthreads();
+    if (tid == 0) {
+        float amn[3], amx[3];
+        for (int d = 0; d < 3; ++d) {
+            amn[d] = s_red[d * NW];
+            amx[d] = s_red[(3 + d) * NW];
+            for (int w = 1; w < NW; ++w) {
+                amn[d] = fminf(amn[d], s_red[d * NW + w]);
+                amx[d] = fmaxf(amx[d], s_red[(3 + d) * NW + w]);
+            }
+        }
+        int cf;
+        float cv;
+        decide_split(lo, hi, amn, amx, &cf, &cv);
+        s_bc[0] = __int_as_float(cf);
+        s_bc[1] = cv;
+    }
+    __syncthreads();
+    const int cf = __float_as_int(s_bc[0]);
+    const float cv = s_bc[1];
+
+    unsigned start = l, lim1 = l, lim2 = l;
+    for (int sweep = 0; sweep < 2; ++sweep) {
+        unsigned long long carry = 0;
+        for (unsigned base = start; base < r; base += BT * IPT) {
+            const unsigned i0 = base + tid * IPT;
+            unsigned long long f[IPT];
+            unsigned long long local = 0;
+#pragma unroll
+            for (int k = 0; k < IPT; ++k) {
+                const unsigned i = i0 + k;
+                unsigned long long fl = 0;
+                if (i < r) {
+                    const float v = __ldg(pts + 3 * (size_t)__ldcg(vind + i) + cf);
+                    const bool sat = sweep == 0 ? (v < cv) : (v <= cv);
+                    fl = sat ? 1ull : (1ull << 32);
                 }
+                local += fl;
+                f[k] = local;
+            }
+            unsigned long long tot;
+            const unsigned long long incl = block_scan_incl(local, s_warp, &tot);
+            const unsigned long long excl = incl - local + carry;
+#pragma unroll
+            for (int k = 0; k < IPT; ++k) {
+                const unsigned i = i0 + k;
+                if (i < r) {
+                    const unsigned long long v = excl + f[k];
+                    psat[i] = (unsigned)(v & 0xFFFFFFFFull);
+                    pfail[i] = (unsigned)(v >> 32);
+                }
+            }
+            carry += tot;
+        }
+        __syncthreads();
+        const unsigned tot_sat = r > start ? psat[r - 1] : 0u;
+        const unsigned lim = start + tot_sat;
+        const unsigned m = lim > start ? pfail[lim - 1] : 0u;  // misplaced pairs
+        for (unsigned i = start + tid; i < r; i += BT) {
+            const unsigned cs = psat[i], cfl = pfail[i];
+            const bool sat = (i == start ? cs : cs - psat[i - 1]) != 0;
+            if (!sat) {
+                if (i < lim) lpos[l + (cfl - 1)] = i;
+            } else {
+                if (i >= lim) rpos[l + (tot_sat - cs)] = i;
+            }
+        }
+        __syncthreads();
+        for (unsigned k = tid; k < m; k += BT) {
+            const unsigned a = lpos[l + k], c = rpos[l + k];
+            const unsigned va = __ldcg(vind + a), vc = __ldcg(vind + c);
+            vind[a] = vc;
+            vind[c] = va;
+        }
+        __syncthreads();
+        if (sweep == 0) {
+            lim1 = lim;
+            start = lim;
+        } else {
+            lim2 = lim;
+        }
+    }
+    const unsigned l1 = lim1 - l, l2 = lim2 - l;
+    unsigned idx;
+    if (l1 > count / 2) idx = l1;
+    else if (l2 < count / 2) idx = l2;
+    else idx = count / 2;
+    float dlow = -INFINITY, dhigh = INFINITY;
+    for (unsigned i = l + tid; i < r; i += BT) {
+        const float v = __ldg(pts + 3 * (size_t)__ldcg(vind + i) + cf);
+        if (i - l < idx) dlow = fmaxf(dlow, v);
+        else dhigh = fminf(dhigh, v);
+    }
+#pragma unroll
+    for (int m = 16; m > 0; m >>= 1) {
+        dlow = fmaxf(dlow, __shfl_xor_sync(0xffffffffu, dlow, m));
+        dhigh = fminf(dhigh, __shfl_xor_sync(0xffffffffu, dhigh, m));
+    }
+    if (lane == 0) {
+        s_red[warp] = dlow;
+        s_red[NW + warp] = dhigh;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        for (int w = 1; w < NW; ++w) {
+            dlow = fmaxf(dlow, s_red[w]);
+            dhigh = fminf(dhigh, s_red[NW + w]);
+        }
+        emit_children(t, g, b, l, r, idx, cf, cv, dlow, dhigh, lo, hi, level);
+    }
+}
+
+__global__ void __launch_bounds__(BT, 1) build_kernel(const float* __restrict__ pts_all, const Tree t) {
+    extern __shared__ __align__(16) unsigned char dyn_smem[];
+    __shared__ unsigned long long s_warp[32];
+    __shared__ float s_red[6 * NW];
+    __shared__ float s_bc[4];
+    const unsigned tid = threadIdx.x;
+    const int lane = tid & 31, warp = tid >> 5;
+    unsigned phase = 0;
+
+    // ---- roots: vind = identity (init_vind :1232-1238), data bbox (computeBoundingBox :1241-1263)
+    for (unsigned b = blockIdx.x; b < t.B; b += gridDim.x) {
+        if (t.item_needed && !t.item_needed[b]) continue;
+        const float* pts = pts_all + (size_t)b * t.N * 3;
+        unsigned* vind = t.vind + (size_t)b * t.N;
+        float mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
+        for (unsigned i = tid; i < t.N; i += BT) {
+            vind[i] = i;
+#pragma unroll
+            for (int d = 0; d < 3; ++d) {
+                const float x = __ldg(pts + 3 * (size_t)i + d);
+                mn[d] = fminf(mn[d], x);
+                mx[d] = fmaxf(mx[d], x);
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+#pragma unroll
+            for (int m = 16; m > 0; m >>= 1) {
+                mn[d] = fminf(mn[d], __shfl_xor_sync(0xffffffffu, mn[d], m));
+                mx[d] = fmaxf(mx[d], __shfl_xor_sync(0xffffffffu, mx[d], m));
+            }
+            if (lane == 0) {
+                s_red[d * NW + warp] = mn[d];
+                s_red[(3 + d) * NW + warp] = mx[d];
             }
         }
         __syncthreads();
         if (tid == 0) {
-            s_level_begin = le;
-            s_level_end = le + s_next;
+            const unsigned g = b * t.cap;
+            for (int d = 0; d < 3; ++d) {
+                float a = s_red[d * NW], c = s_red[(3 + d) * NW];
+                for (int w = 1; w < NW; ++w) {
+                    a = fminf(a, s_red[d * NW + w]);
+                    c = fmaxf(c, s_red[(3 + d) * NW + w]);
+                }
+                t.nlo[(size_t)g * 3 + d] = a;
+                t.nhi[(size_t)g * 3 + d] = c;
+                t.root_lo[b * 3 + d] = a;
+                t.root_hi[b * 3 + d] = c;
+            }
+            NodeRec root;
+            root.c1 = root.c2 = -1;
+            root.feat = 0;
+            root.pad = 0;
+            root.divlow = root.divhigh = 0.f;
+            root.l = 0;
+            root.r = t.N;
+            t.nodes[g] = root;
+            t.node_count[b] = 1;
+            if (t.N > (unsigned)LEAF) {
+                const int cls = t.N > (unsigned)SMALL_MAX ? 0 : 1;
+                const unsigned pos = atomicAdd(&t.list_cnt[cls], 1u);
+                t.list[(size_t)cls * t.lcap + pos] = g;
+            }
         }
         __syncthreads();
     }
-    if (tid == 0) t.n_nodes[b] = s_level_end;
+    grid_sync(t.barrier, phase);
+
+    for (int level = 0; level < MAX_LEVELS; ++level) {
+        const unsigned nbig = __ldcg(&t.list_cnt[level * 2]), nsmall = __ldcg(&t.list_cnt[level * 2 + 1]);
+        if (nbig == 0 && nsmall == 0) break;
+        const unsigned* cur = t.list + (size_t)((level & 1) * 2) * t.lcap;
+        for (unsigned i = blockIdx.x; i < nbig; i += gridDim.x)
+            split_big(pts_all, t, __ldcg(cur + i), level, s_warp, s_red, s_bc);
+        for (unsigned w = blockIdx.x * NW + warp; w < nsmall; w += gridDim.x * NW)
+            split_small(pts_all, t, __ldcg(cur + t.lcap + w), level, dyn_smem + (size_t)warp * WARP_SMEM);
+        grid_sync(t.barrier, phase);
+    }
 }
 
 __global__ void mark_items_kernel(const unsigned* __restrict__ flag_list, unsigned n_flag, unsigned Q,
@@ -384,26 +564,35 @@ __global__ void mark_items_kernel(const unsigned* __restrict__ flag_list, unsign
     if (i < n_flag) item_needed[flag_list[i] / Q] = 1;
 }
 
+__device__ __forceinline__ NodeRec load_node(const NodeRec* p) {
+    const uint4 a = __ldg(reinterpret_cast<const uint4*>(p));
+    const uint4 c = __ldg(reinterpret_cast<const uint4*>(p) + 1);
+    NodeRec n;
+    n.c1 = (int)a.x;
+    n.c2 = (int)a.y;
+    n.feat = (int)a.z;
+    n.pad = a.w;
+    n.divlow = __uint_as_float(c.x);
+    n.divhigh = __uint_as_float(c.y);
+    n.l = c.z;
+    n.r = c.w;
+    return n;
+}
+
 // ---- exact replay of nanoflann's search for the flagged rows -------------------------------------------------
 template <typename OutT>
-__global__ void __launch_bounds__(64) exact_query_kernel(const float* __restrict__ pts_all,
-                                                         const float* __restrict__ q_all, Tree t, unsigned Q, int K,
-                                                         const unsigned* __restrict__ flag_list, unsigned n_flag,
-                                                         OutT* __restrict__ out, unsigned* __restrict__ overflow) {
+__global__ void __launch_bounds__(32) exact_query_kernel(const float* __restrict__ pts_all,
+                                                         const float* __restrict__ q_all, const Tree t, unsigned Q,
+                                                         int K, const unsigned* __restrict__ flag_list,
+                                                         unsigned n_flag, OutT* __restrict__ out) {
     const unsigned f = blockIdx.x * blockDim.x + threadIdx.x;
     if (f >= n_flag) return;
     const unsigned row = flag_list[f];
     const unsigned b = row / Q;
-    const unsigned N = t.N, cap = t.cap;
+    const unsigned N = t.N;
     const float* pts = pts_all + (size_t)b * N * 3;
     const unsigned* vind = t.vind + (size_t)b * N;
-    const unsigned* nl = t.nl + (size_t)b * cap;
-    const unsigned* nr = t.nr + (size_t)b * cap;
-    const unsigned* tlo = t.tlo + (size_t)b * cap * 3;
-    const unsigned* thi = t.thi + (size_t)b * cap * 3;
-    const int* c1 = t.c1 + (size_t)b * cap;
-    const int* c2 = t.c2 + (size_t)b * cap;
-    const int* feat = t.feat + (size_t)b * cap;
+    const NodeRec* nodes = t.nodes + (size_t)b * t.cap;
     const float q[3] = {q_all[3 * (size_t)row], q_all[3 * (size_t)row + 1], q_all[3 * (size_t)row + 2]};
 
     float rd[MAX_K];
@@ -415,7 +604,7 @@ __global__ void __launch_bounds__(64) exact_query_kernel(const float* __restrict
     float d0[3] = {0.f, 0.f, 0.f};
     float distsq = 0.f;
     for (int d = 0; d < 3; ++d) {
-        const float blo = ord2f(tlo[d]), bhi = ord2f(thi[d]);
+        const float blo = t.root_lo[b * 3 + d], bhi = t.root_hi[b * 3 + d];
         if (q[d] < blo) {
             const float df = __fsub_rn(q[d], blo);
             d0[d] = __fmul_rn(df, df);
@@ -429,53 +618,51 @@ __global__ void __launch_bounds__(64) exact_query_kernel(const float* __restrict
     }
     int st_node[MAX_DEPTH];
     float st_min[MAX_DEPTH], st_d[MAX_DEPTH][3];
-    int sp = 0;
     st_node[0] = 0;
     st_min[0] = distsq;
     st_d[0][0] = d0[0];
     st_d[0][1] = d0[1];
     st_d[0][2] = d0[2];
-    sp = 1;
+    int sp = 1;
     bool first = true;
     while (sp > 0) {
         --sp;
-        int node = st_node[sp];
+        const int node = st_node[sp];
         const float mind = st_min[sp];
         float dd[3] = {st_d[sp][0], st_d[sp][1], st_d[sp][2]};
         if (!first && !(mind <= rd[K - 1])) continue;  // mindistsq*epsError <= worstDist()  (:1319)
         first = false;
-        while (c1[node] >= 0) {
-            const int idx = feat[node];
-            const float val = q[idx];
-            const int a = c1[node], bb = c2[node];
-            const float divlow = ord2f(thi[a * 3 + idx]);
-            const float divhigh = ord2f(tlo[bb * 3 + idx]);
-            const float diff1 = __fsub_rn(val, divlow), diff2 = __fsub_rn(val, divhigh);
+        NodeRec nd = load_node(nodes + node);
+        while (nd.c1 >= 0) {
+            const int idx = nd.feat;
+            const float val = idx == 0 ? q[0] : (idx == 1 ? q[1] : q[2]);
+            const float ddi = idx == 0 ? dd[0] : (idx == 1 ? dd[1] : dd[2]);
+            const float diff1 = __fsub_rn(val, nd.divlow), diff2 = __fsub_rn(val, nd.divhigh);
             int best, other;
             float cut;
             if (__fadd_rn(diff1, diff2) < 0.f) {
-                best = a;
-                other = bb;
+                best = nd.c1;
+                other = nd.c2;
                 cut = __fmul_rn(diff2, diff2);
             } else {
-                best = bb;
-                other = a;
+                best = nd.c2;
+                other = nd.c1;
                 cut = __fmul_rn(diff1, diff1);
             }
             if (sp < MAX_DEPTH) {
                 st_node[sp] = other;
-                st_min[sp] = __fsub_rn(__fadd_rn(mind, cut), dd[idx]);
+                st_min[sp] = __fsub_rn(__fadd_rn(mind, cut), ddi);
                 st_d[sp][0] = idx == 0 ? cut : dd[0];
                 st_d[sp][1] = idx == 1 ? cut : dd[1];
                 st_d[sp][2] = idx == 2 ? cut : dd[2];
                 ++sp;
             } else {
-                *overflow = 1u;  // tree deeper than MAX_DEPTH: reported to the host, never silently wrong
+                atomicOr(t.error, 4u);  // deeper than MAX_DEPTH: reported to the host, never silently wrong
             }
-            node = best;
+            nd = load_node(nodes + best);
         }
         const float worst = rd[K - 1];  // snapshot once per leaf (:1277)
-        for (unsigned i = nl[node]; i < nr[node]; ++i) {
+        for (unsigned i = nd.l; i < nd.r; ++i) {
             const unsigned index = vind[i];
             float dist = 0.f;
 #pragma unroll
@@ -508,42 +695,63 @@ __global__ void __launch_bounds__(64) exact_query_kernel(const float* __restrict
 
 enum { TW_BASE = 16 };  // workspace slots TW_BASE.. are owned by this header
 
-// Carve the tree arrays out of three workspace slabs.
-static int alloc_tree(Ctx* c, size_t B, size_t N, Tree* out) {
+// Carve the tree arrays out of workspace slabs and zero the small control block.
+static int alloc_tree(Ctx* c, cudaStream_t s, size_t B, size_t N, Tree* out) {
     const size_t cap = 2 * N + 2;
-    const size_t posb = B * N * sizeof(unsigned), nodeb = B * cap * sizeof(unsigned);
-    SSDR_TRY(c->ws[TW_BASE + 0].reserve(6 * posb));
-    SSDR_TRY(c->ws[TW_BASE + 1].reserve(nodeb * 21 + B * cap + 64));
-    SSDR_TRY(c->ws[TW_BASE + 2].reserve(B * sizeof(unsigned) + B + 72));
+    const size_t lcap = B * (N / 5 + 2) + 16;  // a level never holds more split-able nodes than that
+    SSDR_TRY(c->ws[TW_BASE + 0].reserve(5 * B * N * sizeof(unsigned)));
+    SSDR_TRY(c->ws[TW_BASE + 1].reserve(B * cap * (sizeof(NodeRec) + 6 * sizeof(float))));
+    SSDR_TRY(c->ws[TW_BASE + 2].reserve(4 * lcap * sizeof(unsigned)));
+    const size_t ctl_words = 6 * B + B + (size_t)(MAX_LEVELS + 1) * 2 + 8 + (B + 3) / 4 + 4;
+    SSDR_TRY(c->ws[TW_BASE + 3].reserve(ctl_words * sizeof(unsigned)));
     Tree t;
     t.N = (unsigned)N;
     t.cap = (unsigned)cap;
+    t.B = (unsigned)B;
+    t.lcap = (unsigned)lcap;
     unsigned* pb = c->ws[TW_BASE + 0].as<unsigned>();
     t.vind = pb;
-    t.node_of = pb + B * N;
-    t.lpos = pb + 2 * B * N;
-    t.rpos = pb + 3 * B * N;
-    t.psat = pb + 4 * B * N;
-    t.pfail = pb + 5 * B * N;
-    unsigned* nb = c->ws[TW_BASE + 1].as<unsigned>();
-    const size_t u = B * cap;
-    t.nl = nb;
-    t.nr = nb + u;
-    t.lo = reinterpret_cast<float*>(nb + 2 * u);
-    t.hi = reinterpret_cast<float*>(nb + 5 * u);
-    t.tlo = nb + 8 * u;
-    t.thi = nb + 11 * u;
-    t.c1 = reinterpret_cast<int*>(nb + 14 * u);
-    t.c2 = reinterpret_cast<int*>(nb + 15 * u);
-    t.feat = reinterpret_cast<int*>(nb + 16 * u);
-    t.cutval = reinterpret_cast<float*>(nb + 17 * u);
-    t.start = nb + 18 * u;
-    t.totsat = nb + 19 * u;
-    t.lim1 = nb + 20 * u;
-    t.active = reinterpret_cast<unsigned char*>(nb + 21 * u);
-    t.n_nodes = c->ws[TW_BASE + 2].as<unsigned>();
+    t.lpos = pb + B * N;
+    t.rpos = pb + 2 * B * N;
+    t.psat = pb + 3 * B * N;
+    t.pfail = pb + 4 * B * N;
+    t.nodes = c->ws[TW_BASE + 1].as<NodeRec>();
+    t.nlo = reinterpret_cast<float*>(t.nodes + B * cap);
+    t.nhi = t.nlo + B * cap * 3;
+    t.list = c->ws[TW_BASE + 2].as<unsigned>();
+    unsigned* ctl = c->ws[TW_BASE + 3].as<unsigned>();
+    SSDR_CHECK_CUDA(cudaMemsetAsync(ctl, 0, ctl_words * sizeof(unsigned), s));
+    t.root_lo = reinterpret_cast<float*>(ctl);
+    t.root_hi = reinterpret_cast<float*>(ctl + 3 * B);
+    t.node_count = ctl + 6 * B;
+    t.list_cnt = ctl + 7 * B;
+    t.barrier = t.list_cnt + (size_t)(MAX_LEVELS + 1) * 2;
+    t.error = t.barrier + 4;
     t.item_needed = nullptr;
     *out = t;
+    return SSDR_OK;
+}
+static unsigned char* tree_needed_flags(const Tree& t) { return reinterpret_cast<unsigned char*>(t.error + 4); }
+
+static int launch_build(Ctx* c, cudaStream_t s, const float* d_pts, const Tree& t) {
+    const size_t smem = (size_t)NW * WARP_SMEM;
+    SSDR_CHECK_CUDA(cudaFuncSetAttribute(build_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int nb = 0;
+    SSDR_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, build_kernel, BT, smem));
+    SSDR_REQUIRE(nb >= 1, SSDR_ERR_CUDA, "tree build kernel does not fit on an SM");
+    const float* pts = d_pts;
+    Tree tt = t;
+    void* args[] = {(void*)&pts, (void*)&tt};
+    SSDR_CHECK_CUDA(cudaLaunchCooperativeKernel((void*)build_kernel, dim3(c->sm_count), dim3(BT), args, smem, s));
+    return SSDR_OK;
+}
+
+static int check_tree_error(Ctx* c, cudaStream_t s, const Tree& t) {
+    unsigned h_err = 0;
+    SSDR_TRY(d2h_sync(c, &h_err, t.error, sizeof(unsigned), s));
+    SSDR_REQUIRE(h_err == 0, SSDR_ERR_UNSUPPORTED,
+                 "exact tie path gave up (flags %u: 1 node capacity, 2 more than %d tree levels, 4 search stack deeper "
+                 "than %d)", h_err, MAX_LEVELS, MAX_DEPTH);
     return SSDR_OK;
 }
 
@@ -554,20 +762,16 @@ static int resolve_flagged(Ctx* c, cudaStream_t s, const float* d_pts, size_t B,
                            unsigned long long* builds) {
     SSDR_REQUIRE(K <= (size_t)MAX_K, SSDR_ERR_UNSUPPORTED, "K=%zu > %d in the exact tie path", K, MAX_K);
     Tree t;
-    SSDR_TRY(alloc_tree(c, B, N, &t));
-    unsigned char* needed = reinterpret_cast<unsigned char*>(t.n_nodes + B);
+    SSDR_TRY(alloc_tree(c, s, B, N, &t));
+    unsigned char* needed = tree_needed_flags(t);
     t.item_needed = needed;
-    unsigned* overflow = reinterpret_cast<unsigned*>(needed + ((B + 3) / 4) * 4);
-    SSDR_CHECK_CUDA(cudaMemsetAsync(needed, 0, ((B + 3) / 4) * 4 + 4, s));
     mark_items_kernel<<<(n_flag + 255) / 256, 256, 0, s>>>(flag_list, n_flag, (unsigned)Q, needed);
-    build_kernel<<<(unsigned)B, BT, 0, s>>>(d_pts, t);
-    exact_query_kernel<OutT><<<(n_flag + 63) / 64, 64, 0, s>>>(d_pts, d_q, t, (unsigned)Q, (int)K, flag_list, n_flag,
-                                                              d_out, overflow);
+    SSDR_TRY(launch_build(c, s, d_pts, t));
+    exact_query_kernel<OutT><<<(n_flag + 31) / 32, 32, 0, s>>>(d_pts, d_q, t, (unsigned)Q, (int)K, flag_list, n_flag,
+                                                              d_out);
     SSDR_CHECK_CUDA(cudaGetLastError());
-    unsigned h_over = 0;
-    SSDR_TRY(d2h_sync(c, &h_over, overflow, sizeof(unsigned), s));
-    SSDR_REQUIRE(h_over == 0, SSDR_ERR_UNSUPPORTED, "KD-tree deeper than %d levels in the exact tie path", MAX_DEPTH);
-    if (builds) *builds = B;  // upper bound; items without flagged rows exit immediately
+    SSDR_TRY(check_tree_error(c, s, t));
+    if (builds) *builds = B;  // upper bound; items without flagged rows are skipped inside the kernel
     return SSDR_OK;
 }
 

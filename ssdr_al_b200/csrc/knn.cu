@@ -309,6 +309,7 @@ static int run_dev(Ctx* c, cudaStream_t s, const float* d_pts, size_t B, size_t 
     DevStats* dstats = c->ws[WS_STATS].as<DevStats>();
     unsigned* flag_list = c->ws[WS_FLAGS].as<unsigned>();
 
+    if (stats) SSDR_CHECK_CUDA(cudaEventRecord(c->tev[0], s));
     SSDR_CHECK_CUDA(cudaMemsetAsync(cnt_p, 0, ncell * 4 * 2, s));
     SSDR_CHECK_CUDA(cudaMemsetAsync(dstats, 0, sizeof(DevStats), s));
     bbox_init_kernel<<<(unsigned)((B * 6 + 63) / 64), 64, 0, s>>>(enc, (int)B);
@@ -343,6 +344,7 @@ static int run_dev(Ctx* c, cudaStream_t s, const float* d_pts, size_t B, size_t 
     if (K > N) SSDR_CHECK_CUDA(cudaMemsetAsync(d_out, 0, (size_t)totalQ * K * sizeof(OutT), s));
 
     const unsigned qblocks = (totalQ + 127) / 128;
+    if (stats) SSDR_CHECK_CUDA(cudaEventRecord(c->tev[1], s));
 #define SSDR_QUERY(KC)                                                                                            \
     query_kernel<KC, OutT><<<qblocks, 128, 0, s>>>(sort_p, sort_q, start_p, items, (unsigned)N, (unsigned)Q, totalQ, \
                                                    (int)K, d_out, &dstats->flag_count, flag_list, &dstats->evals)
@@ -354,6 +356,7 @@ static int run_dev(Ctx* c, cudaStream_t s, const float* d_pts, size_t B, size_t 
     else SSDR_QUERY(65);
 #undef SSDR_QUERY
     SSDR_CHECK_CUDA(cudaGetLastError());
+    if (stats) SSDR_CHECK_CUDA(cudaEventRecord(c->tev[2], s));
 
     // ---- C: exact nanoflann replay of the flagged rows
     DevStats hs;
@@ -363,7 +366,15 @@ static int run_dev(Ctx* c, cudaStream_t s, const float* d_pts, size_t B, size_t 
         SSDR_TRY((kdtree::resolve_flagged<OutT>(c, s, d_pts, B, N, d_q, Q, K, d_out, flag_list, hs.flag_count, &builds)));
     }
     if (stats) {
+        SSDR_CHECK_CUDA(cudaEventRecord(c->tev[3], s));
         SSDR_CHECK_CUDA(cudaStreamSynchronize(s));
+        float ms = 0.f;
+        SSDR_CHECK_CUDA(cudaEventElapsedTime(&ms, c->tev[0], c->tev[1]));
+        stats->grid_build_ms = ms;
+        SSDR_CHECK_CUDA(cudaEventElapsedTime(&ms, c->tev[1], c->tev[2]));
+        stats->main_kernel_ms = ms;
+        SSDR_CHECK_CUDA(cudaEventElapsedTime(&ms, c->tev[2], c->tev[3]));
+        stats->tie_path_ms = hs.flag_count ? ms : 0.0;
         stats->queries = totalQ;
         stats->tie_rows = hs.flag_count;
         stats->tree_builds = builds;
@@ -419,7 +430,7 @@ int ssdr_knn_batch_dev(const float* d_points, size_t batch_size, size_t npts, co
                        size_t K, int64_t* d_indices, void* stream, ssdr_knn_stats* stats) {
     Ctx* c;
     SSDR_TRY(get_ctx(&c));
-    return knn::run_dev<long long>(c, stream ? (cudaStream_t)stream : c->stream, d_points, batch_size, npts, d_queries,
+    return knn::run_dev<long long>(c, (cudaStream_t)stream, d_points, batch_size, npts, d_queries,
                                    nqueries, K, reinterpret_cast<long long*>(d_indices), stats);
 }
 // Diagnostic: build the nanoflann-identical tree of one cloud on the device and copy it back (tests compare it with
@@ -434,48 +445,33 @@ int ssdr_knn_debug_tree(const float* points, size_t npts, uint32_t* vind_out, ui
     SSDR_TRY(c->ws[knn::WS_IN_P].reserve(npts * 3 * sizeof(float)));
     SSDR_TRY(h2d(c, c->ws[knn::WS_IN_P].p, points, npts * 3 * sizeof(float), s));
     kdtree::Tree t;
-    SSDR_TRY(kdtree::alloc_tree(c, 1, npts, &t));
-    t.item_needed = nullptr;
-    kdtree::build_kernel<<<1, kdtree::BT, 0, s>>>(c->ws[knn::WS_IN_P].as<float>(), t);
-    SSDR_CHECK_CUDA(cudaGetLastError());
-    SSDR_TRY(d2h_sync(c, n_nodes_out, t.n_nodes, sizeof(unsigned), s));
+    SSDR_TRY(kdtree::alloc_tree(c, s, 1, npts, &t));
+    SSDR_TRY(kdtree::launch_build(c, s, c->ws[knn::WS_IN_P].as<float>(), t));
+    SSDR_TRY(kdtree::check_tree_error(c, s, t));
+    SSDR_TRY(d2h_sync(c, n_nodes_out, t.node_count, sizeof(unsigned), s));
     const size_t nn = *n_nodes_out;
     SSDR_REQUIRE(nn <= t.cap, SSDR_ERR_CUDA, "node count %zu exceeds capacity", nn);
     SSDR_TRY(d2h_sync(c, vind_out, t.vind, npts * sizeof(unsigned), s));
-    if (left) SSDR_TRY(d2h_sync(c, left, t.nl, nn * sizeof(unsigned), s));
-    if (right) SSDR_TRY(d2h_sync(c, right, t.nr, nn * sizeof(unsigned), s));
-    if (child1) SSDR_TRY(d2h_sync(c, child1, t.c1, nn * sizeof(int), s));
-    if (child2) SSDR_TRY(d2h_sync(c, child2, t.c2, nn * sizeof(int), s));
-    if (divfeat) SSDR_TRY(d2h_sync(c, divfeat, t.feat, nn * sizeof(int), s));
-    if (divlow && divhigh && child1 && child2 && divfeat) {
-        unsigned* tl = (unsigned*)malloc(nn * 3 * sizeof(unsigned));
-        unsigned* th = (unsigned*)malloc(nn * 3 * sizeof(unsigned));
-        int rc = d2h_sync(c, tl, t.tlo, nn * 3 * sizeof(unsigned), s);
-        if (rc == SSDR_OK) rc = d2h_sync(c, th, t.thi, nn * 3 * sizeof(unsigned), s);
-        auto dec = [](unsigned u) {
-            unsigned v = (u & 0x80000000u) ? (u & 0x7FFFFFFFu) : ~u;
-            float f;
-            memcpy(&f, &v, 4);
-            return f;
-        };
-        for (size_t n = 0; rc == SSDR_OK && n < nn; ++n) {
-            divlow[n] = divhigh[n] = 0.f;
-            if (child1[n] >= 0) {
-                divlow[n] = dec(th[(size_t)child1[n] * 3 + divfeat[n]]);
-                divhigh[n] = dec(tl[(size_t)child2[n] * 3 + divfeat[n]]);
-            }
-        }
-        free(tl);
-        free(th);
-        SSDR_TRY(rc);
+    kdtree::NodeRec* h = (kdtree::NodeRec*)malloc(nn * sizeof(kdtree::NodeRec));
+    SSDR_REQUIRE(h, SSDR_ERR_NOMEM, "host allocation failed");
+    int rc = d2h_sync(c, h, t.nodes, nn * sizeof(kdtree::NodeRec), s);
+    for (size_t n = 0; rc == SSDR_OK && n < nn; ++n) {
+        if (left) left[n] = h[n].l;
+        if (right) right[n] = h[n].r;
+        if (child1) child1[n] = h[n].c1;
+        if (child2) child2[n] = h[n].c2;
+        if (divfeat) divfeat[n] = h[n].feat;
+        if (divlow) divlow[n] = h[n].divlow;
+        if (divhigh) divhigh[n] = h[n].divhigh;
     }
-    return SSDR_OK;
+    free(h);
+    return rc;
 }
 int ssdr_knn_batch_dev_i32(const float* d_points, size_t batch_size, size_t npts, const float* d_queries,
                            size_t nqueries, size_t K, int32_t* d_indices, void* stream, ssdr_knn_stats* stats) {
     Ctx* c;
     SSDR_TRY(get_ctx(&c));
-    return knn::run_dev<int>(c, stream ? (cudaStream_t)stream : c->stream, d_points, batch_size, npts, d_queries,
+    return knn::run_dev<int>(c, (cudaStream_t)stream, d_points, batch_size, npts, d_queries,
                              nqueries, K, d_indices, stats);
 }
 }

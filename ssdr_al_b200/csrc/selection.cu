@@ -3,12 +3,15 @@
 // Replaces the per-pick numpy passes of farthest_features_sample (fps_gcn_cpu.py:137-146) and
 // kCenterGreedy.update_distances/select_batch_ (kcenterGreedy.py:60-128).
 //
-// One PERSISTENT cooperative kernel runs every pick: each CTA owns a contiguous slab of rows, streams it from
-// HBM/L2 through a cp.async multi-stage shared-memory ring (padded rows => conflict-free LDS), evaluates the
-// distance of every row to the current centre in the reference's exact floating-point order, folds it into the
-// running min-distance, and reduces (distance, index) to one candidate per CTA.  A grid barrier publishes the
-// candidates; every CTA then reduces them redundantly, so the next centre is known everywhere with a single
-// barrier per pick and no host round trip.  The step is HBM/L2-bandwidth bound: N*(sizeof(T)*D + 2*sizeof(T)).
+// One PERSISTENT cooperative kernel runs every pick.  Every WARP owns a contiguous run of rows and streams it from
+// HBM/L2 through its own cp.async multi-stage shared-memory ring (padded rows => conflict-free LDS; no block-wide
+// barrier inside a pick; the ring keeps running across picks, so the next pick's first rows are already in flight
+// while the grid agrees on the next centre).  The warp evaluates the distance of its rows to the current centre in
+// the reference's exact floating-point order, folds it into the running min-distance with coalesced 128-byte
+// accesses and keeps a (distance, index) candidate per lane.  A grid barrier publishes one candidate per CTA; every
+// CTA then reduces them redundantly, so the next centre is known everywhere with a single barrier per pick and no
+// host round trip.  The step is HBM/L2-bandwidth bound: N*(sizeof(T)*D + 2*sizeof(T)).  D in {32,64,128,256} is
+// compiled in (fully unrolled, centre row in registers); any other D takes the generic leaf-plan path.
 //
 // Arithmetic contracts (bit-exact picks):
 //   FPS     : d = pairwise_sum_j((F[i,j]-F[c,j])^2) in T with numpy's summation tree: eight strided
@@ -24,6 +27,7 @@
 #include "common.cuh"
 
 namespace ssdr {
+int nccl_allreduce_max_u64(void* comm, unsigned long long* buf, size_t count, cudaStream_t stream);  // nccl_shim.cu
 namespace sel {
 
 constexpr int THREADS = 256;
@@ -49,7 +53,8 @@ struct Params {
     int D;
     unsigned long long row_begin, row_end;  // rows scanned by this launch (global indices)
     int stride;                             // smem row stride in elements
-    int rows_per_tile;                      // multiple of 4
+    int groups_per_unit;                    // a warp iteration ("unit") covers 4*groups_per_unit rows (<= 32)
+    int nwarps;                             // warps per CTA (8 unless a very wide row forces fewer)
     int nstages;
     int vec;                                // elements per cp.async (16B when possible)
     const long long* forced;                // device: centres of the first n_forced steps
@@ -223,44 +228,77 @@ __device__ __forceinline__ Cand warp_max(Cand c) {
     return c;
 }
 
-template <typename T, int MODE>
+// compile-time pairwise tree for D % 8 == 0 (numpy: leaves <= 128 wide, recursive halving above); creg[k] = c[8k+j]
+template <typename T, int N, int OFF>
+__device__ __forceinline__ T pw_fixed(const T* __restrict__ a, const T* creg, int j) {
+    if constexpr (N <= 128) {
+        T acc = sqdiff(a[OFF + j], creg[OFF / 8]);
+#pragma unroll
+        for (int i = 8; i < N; i += 8) acc = xadd(acc, sqdiff(a[OFF + i + j], creg[(OFF + i) / 8]));
+        return butterfly8(acc);
+    } else {
+        constexpr int N2 = (N / 2) - ((N / 2) % 8);
+        const T l = pw_fixed<T, N2, OFF>(a, creg, j);
+        const T r = pw_fixed<T, N - N2, OFF + N2>(a, creg, j);
+        return xadd(l, r);
+    }
+}
+template <typename T, int N>
+__device__ __forceinline__ double dot64_fixed(const T* __restrict__ a, const T* creg, int j) {
+    double acc = 0.0;
+#pragma unroll
+    for (int i = 0; i < N; i += 8) acc = fma((double)a[i + j], (double)creg[i / 8], acc);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+    return acc;
+}
+
+template <typename T, int MODE, int DT>
 __global__ void __launch_bounds__(THREADS, 1) select_kernel(const Params<T> p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     typedef typename std::conditional<MODE == MODE_KCENTER, double, T>::type RowVal;
-    const int D = p.D;
+    const int D = DT > 0 ? DT : p.D;
     const int stride = p.stride;
-    const int R = p.rows_per_tile;
+    const int GPU_ = p.groups_per_unit;
+    const int RW = 4 * GPU_;  // rows per unit
+    const int S = p.nstages;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int G = gridDim.x;
+    const int NWARP = p.nwarps;
+    const int g = lane >> 3, j = lane & 7;
 
-    // shared layout: centre row | per-row results | stage ring | reduction scratch
+    // shared layout: centre row (generic path) | reduction scratch | per-warp stage rings
     T* s_center = reinterpret_cast<T*>(smem_raw);
-    size_t off = align_up_dev((size_t)(D + 8) * sizeof(T), 16);
-    RowVal* s_rowval = reinterpret_cast<RowVal*>(smem_raw + off);
-    off += align_up_dev((size_t)R * sizeof(RowVal), 16);
-    T* s_tiles = reinterpret_cast<T*>(smem_raw + off);
-    off += (size_t)p.nstages * R * stride * sizeof(T);
-    Cand* s_red = reinterpret_cast<Cand*>(smem_raw + align_up_dev(off, 16));
+    size_t off = align_up_dev((size_t)(p.D + 8) * sizeof(T), 16);
+    Cand* s_red = reinterpret_cast<Cand*>(smem_raw + off);
+    off += align_up_dev(WARPS * sizeof(Cand), 16);
+    const size_t unit_elems = (size_t)RW * stride;
+    T* ring = reinterpret_cast<T*>(smem_raw + off) + (size_t)warp * S * unit_elems;
     __shared__ unsigned long long s_next_center;
 
-    // contiguous slab of rows for this CTA, in whole tiles
+    // contiguous run of units for this warp
     const unsigned long long nrows = p.row_end - p.row_begin;
-    const unsigned long long tiles_total = (nrows + R - 1) / R;
-    const unsigned long long tiles_per_cta = (tiles_total + G - 1) / G;
-    const unsigned long long t_begin = min((unsigned long long)blockIdx.x * tiles_per_cta, tiles_total);
-    const unsigned long long t_end = min(t_begin + tiles_per_cta, tiles_total);
-    const int ntiles = (int)(t_end - t_begin);
+    const unsigned long long units_total = (nrows + RW - 1) / RW;
+    const unsigned long long TW = (unsigned long long)G * NWARP;
+    const unsigned long long upw = (units_total + TW - 1) / TW;
+    const unsigned long long gw = (unsigned long long)blockIdx.x * NWARP + warp;
+    const unsigned long long u_begin = min(gw * upw, units_total);
+    const unsigned long long u_end = min(u_begin + upw, units_total);
+    const int n_it = (int)(u_end - u_begin);
+    const long long total_it = (long long)n_it * (p.step_end - p.step_begin);
 
-    const int cpr = D / p.vec;  // chunks per row
-    const int dcol = THREADS % cpr, drow = THREADS / cpr;
+    const int cpr = D / p.vec;  // cp.async chunks per row
+    const int dcol = 32 % cpr, drow = 32 / cpr;
 
-    auto issue_tile = [&](int t) {
-        if (t < ntiles) {
-            const unsigned long long r0 = p.row_begin + (t_begin + t) * (unsigned long long)R;
-            const int rows = (int)min((unsigned long long)R, p.row_end - r0);
-            T* dst = s_tiles + (size_t)(t % p.nstages) * R * stride;
+    auto issue = [&](long long gi) {  // unit (gi % n_it) of this warp into stage (gi % S)
+        if (gi < total_it) {
+            const int it = (int)(gi % n_it);
+            const unsigned long long r0 = p.row_begin + (u_begin + it) * (unsigned long long)RW;
+            const int rows = (int)min((unsigned long long)RW, p.row_end - r0);
+            T* dst = ring + (size_t)(gi % S) * unit_elems;
             const T* src = p.F + r0 * (unsigned long long)D;
-            int row = tid / cpr, col = tid % cpr;
+            int row = lane / cpr, col = lane % cpr;
             while (row < rows) {
                 cp_elems(dst + (size_t)row * stride + col * p.vec, src + (size_t)row * D + col * p.vec, p.vec);
                 col += dcol;
@@ -274,9 +312,11 @@ __global__ void __launch_bounds__(THREADS, 1) select_kernel(const Params<T> p) {
         cp_async_commit();
     };
 
+    for (int q = 0; q < S - 1; ++q) issue(q);  // the ring never drains between picks
+
+    long long gi = 0;
     for (int step = p.step_begin; step < p.step_end; ++step) {
-        // ---- centre of this step
-        __syncthreads();  // warp 0 has published s_next_center; nobody still reads the previous step's smem
+        __syncthreads();  // warp 0 has published s_next_center; the generic centre row is no longer read
         unsigned long long c_row;
         if (step < p.n_forced) c_row = (unsigned long long)p.forced[step];
         else if (step == p.step_begin) {
@@ -286,65 +326,76 @@ __global__ void __launch_bounds__(THREADS, 1) select_kernel(const Params<T> p) {
             c_row = cand_row<T>(w);
         } else
             c_row = s_next_center;
-        for (int i = tid; i < D; i += THREADS) s_center[i] = p.F[c_row * (unsigned long long)D + i];
+        T creg[DT > 0 ? DT / 8 : 1];
+        if (DT > 0) {
+#pragma unroll
+            for (int k = 0; k < (DT > 0 ? DT / 8 : 1); ++k) creg[k] = __ldcg(p.F + c_row * (unsigned long long)D + 8 * k + j);
+        } else {
+            for (int i = tid; i < D; i += NWARP * 32) s_center[i] = p.F[c_row * (unsigned long long)D + i];
+            __syncthreads();
+        }
         double xx_c = 0.0;
         if (MODE == MODE_KCENTER) xx_c = p.xx[c_row];
-
-        // ---- pipeline prologue
-        for (int t = 0; t < p.nstages - 1; ++t) issue_tile(t);
 
         Cand best;
         best.hi = 0;
         best.lo = 0;
-        for (int t = 0; t < ntiles; ++t) {
-            cp_async_wait_dyn(p.nstages - 2);
-            __syncthreads();  // tile t landed for all threads; stage (t-1)%nstages is free
-            issue_tile(t + p.nstages - 1);
-
-            const unsigned long long r0 = p.row_begin + (t_begin + t) * (unsigned long long)R;
-            const int rows = (int)min((unsigned long long)R, p.row_end - r0);
-            const T* tile = s_tiles + (size_t)(t % p.nstages) * R * stride;
-            const int g = lane >> 3, j = lane & 7;
-            // row groups of 4 rows, round-robin over warps
-            for (int rg = warp; rg * 4 < rows; rg += WARPS) {
-                const int row = rg * 4 + g;
-                const T* a = tile + (size_t)row * stride;
-                if (MODE == MODE_FPS) {
-                    T d = row_sqdist<T>(a, s_center, D, j, p.plan);
-                    if (j == 0 && row < rows) s_rowval[row] = (RowVal)d;
-                } else {
-                    double d = row_dot64<T>(a, s_center, D, j);
-                    if (j == 0 && row < rows) s_rowval[row] = (RowVal)d;
-                }
+        for (int it = 0; it < n_it; ++it, ++gi) {
+            issue(gi + S - 1);
+            cp_async_wait_dyn(S - 1);
+            __syncwarp();
+            const unsigned long long r0 = p.row_begin + (u_begin + it) * (unsigned long long)RW;
+            const int rows = (int)min((unsigned long long)RW, p.row_end - r0);
+            const T* tile = ring + (size_t)(gi % S) * unit_elems;
+            // running min-distance (and row norm) of "my" row: issued now, consumed after the distance loop
+            T m_old = (T)0;
+            double xx_r = 0.0;
+            if (lane < rows) {
+                m_old = __ldcg(p.mind + r0 + lane);
+                if (MODE == MODE_KCENTER) xx_r = __ldg(p.xx + r0 + lane);
             }
-            __syncthreads();
-            for (int row = tid; row < rows; row += THREADS) {
-                const unsigned long long gi = r0 + row;
+            RowVal mine = (RowVal)0;
+#pragma unroll 4
+            for (int i = 0; i < GPU_; ++i) {
+                const T* a = tile + (size_t)(4 * i + g) * stride;
+                RowVal d;
+                if (MODE == MODE_FPS) {
+                    if (DT > 0) d = (RowVal)pw_fixed<T, (DT > 0 ? DT : 8), 0>(a, creg, j);
+                    else d = (RowVal)row_sqdist<T>(a, s_center, D, j, p.plan);
+                } else {
+                    if (DT > 0) d = (RowVal)dot64_fixed<T, (DT > 0 ? DT : 8)>(a, creg, j);
+                    else d = (RowVal)row_dot64<T>(a, s_center, D, j);
+                }
+                // lane L owns row L of the unit: it lives in group L/4, row-in-group L%4 (lanes (L%4)*8.. hold it)
+                const RowVal v = __shfl_sync(0xffffffffu, d, (lane & 3) * 8);
+                if ((lane >> 2) == i) mine = v;
+            }
+            if (lane < rows) {
+                const unsigned long long gr = r0 + lane;
                 T d;
                 if (MODE == MODE_FPS) {
-                    d = (T)s_rowval[row];
+                    d = (T)mine;
                 } else {
-                    double v = -2.0 * (double)s_rowval[row];
-                    v = __dadd_rn(v, p.xx[gi]);
+                    double v = -2.0 * (double)mine;
+                    v = __dadd_rn(v, xx_r);
                     v = __dadd_rn(v, xx_c);
                     T tv = (T)v;
                     tv = tv > (T)0 ? tv : (T)0;  // np.maximum(d, 0)
                     d = sizeof(T) == 4 ? (T)__fsqrt_rn((float)tv) : (T)__dsqrt_rn((double)tv);
                 }
-                T m = p.mind[gi];
-                m = d < m ? d : m;
-                p.mind[gi] = m;
-                best = cand_max(best, make_cand<T>(m, gi));
+                const T m = d < m_old ? d : m_old;
+                if (d < m_old) __stcg(p.mind + gr, m);
+                best = cand_max(best, make_cand<T>(m, gr));
             }
+            __syncwarp();  // every lane is done with this stage before a later issue() overwrites it
         }
-        cp_async_wait<0>();
 
         // ---- CTA candidate
         best = warp_max(best);
         if (lane == 0) s_red[warp] = best;
         __syncthreads();
         if (warp == 0) {
-            Cand c = lane < WARPS ? s_red[lane] : Cand{0, 0};
+            Cand c = lane < NWARP ? s_red[lane] : Cand{0, 0};
             c = warp_max(c);
             if (lane == 0) {
                 unsigned long long* box = p.cand + ((size_t)(step & 1) * G + blockIdx.x) * 2;
@@ -378,6 +429,7 @@ __global__ void __launch_bounds__(THREADS, 1) select_kernel(const Params<T> p) {
         }
         // the __syncthreads at the top of the next step publishes s_next_center
     }
+    cp_async_wait<0>();
 }
 
 // squared row norms in fp64 (k-center): one warp per row, coalesced, FMA chain per lane + butterfly
@@ -406,6 +458,11 @@ __global__ void fill_kernel(T* p, unsigned long long n, T v) {
 __global__ void fps_emit_kernel(const long long* picks, int first, int* out, unsigned long long n_samples) {
     unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n_samples) out[i] = i == 0 ? first : (int)picks[i - 1];
+}
+__global__ void fps_emit_winners_kernel(const unsigned long long* winners, int first, int* out,
+                                        unsigned long long n_samples) {
+    unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_samples) out[i] = i == 0 ? first : (int)(0xFFFFFFFFu - (unsigned)(winners[2 * (i - 1)] & 0xFFFFFFFFull));
 }
 __global__ void kcenter_emit_kernel(const long long* picks, long long n_sel, long long* out, unsigned long long n_pick) {
     unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -438,12 +495,25 @@ struct Launch {
     Params<T> p;
     int grid = 0;
     size_t smem = 0;
+    void* fn = nullptr;
 };
 
-// Fill geometry (stride, tile rows, stages, grid) for a (T, D) problem.
+typedef cudaError_t (*AttrFn)(int);
+
+template <typename T, int MODE, int DT>
+static int setup_variant(size_t smem, void** fn_out) {
+    auto kern = select_kernel<T, MODE, DT>;
+    SSDR_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int nb = 0;
+    SSDR_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, THREADS, smem));
+    SSDR_REQUIRE(nb >= 1, SSDR_ERR_CUDA, "selection kernel does not fit on an SM (smem %zu)", smem);
+    *fn_out = (void*)kern;
+    return SSDR_OK;
+}
+
+// Fill geometry (stride, unit rows, stages, grid) for a (T, D) problem and pick the kernel variant.
 template <typename T, int MODE>
 static int configure(Ctx* c, Launch<T>& L, const T* dF, size_t N, size_t D) {
-    typedef typename std::conditional<MODE == MODE_KCENTER, double, T>::type RowVal;
     Params<T>& p = L.p;
     p.F = dF;
     p.N = N;
@@ -461,25 +531,30 @@ static int configure(Ctx* c, Launch<T>& L, const T* dF, size_t N, size_t D) {
     p.vec = vec;
     const size_t row_bytes = (size_t)stride * sizeof(T);
     const size_t budget = (size_t)c->max_smem_optin - 2048;
-    const size_t fixed = align_up_dev((D + 8) * sizeof(T), 16) + WARPS * sizeof(Cand) + 64;
-    int nst = 4;
-    long rows = (long)((32 * 1024) / row_bytes) / 4 * 4;
-    if (rows < 4) rows = 4;
-    if (rows > 1024) rows = 1024;
-    auto need = [&](long r, int st) { return fixed + align_up_dev((size_t)r * sizeof(RowVal), 16) + (size_t)st * r * row_bytes; };
-    while (nst > 2 && need(rows, nst) > budget) --nst;
-    SSDR_REQUIRE(need(rows, nst) <= budget, SSDR_ERR_UNSUPPORTED,
-                 "feature dimension D=%zu needs %zu bytes of shared memory per CTA (limit %zu)", D, need(rows, nst), budget);
-    p.rows_per_tile = (int)rows;
+    const size_t fixed = align_up_dev((D + 8) * sizeof(T), 16) + align_up_dev(WARPS * sizeof(Cand), 16) + 64;
+    // unit = 4*groups rows per warp iteration, ~6 KB per stage, 4 stages if they fit
+    int groups = (int)(6144 / (4 * row_bytes));
+    groups = groups < 1 ? 1 : (groups > 8 ? 8 : groups);
+    int nst = 4, nw = WARPS;
+    auto need = [&](int gr, int st, int w) { return fixed + (size_t)w * st * 4 * gr * row_bytes; };
+    while (nst > 2 && need(groups, nst, nw) > budget) --nst;
+    while (groups > 1 && need(groups, nst, nw) > budget) --groups;
+    while (nw > 1 && need(groups, nst, nw) > budget) nw /= 2;
+    SSDR_REQUIRE(need(groups, nst, nw) <= budget, SSDR_ERR_UNSUPPORTED,
+                 "feature dimension D=%zu needs %zu bytes of shared memory per CTA (limit %zu)", D,
+                 need(groups, nst, nw), budget);
+    p.groups_per_unit = groups;
     p.nstages = nst;
-    L.smem = need(rows, nst);
+    p.nwarps = nw;
+    L.smem = need(groups, nst, nw);
     p.plan.n_leaves = 0;
     if (D >= 8) plan_emit(p.plan, 0, (int)D);
-    auto kern = select_kernel<T, MODE>;
-    SSDR_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smem));
-    int nb = 0;
-    SSDR_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, THREADS, L.smem));
-    SSDR_REQUIRE(nb >= 1, SSDR_ERR_CUDA, "selection kernel does not fit on an SM (smem %zu)", L.smem);
+    const bool fixed_ok = vec == vec_full;  // the unrolled variants assume 16-byte rows
+    if (fixed_ok && D == 32) SSDR_TRY((setup_variant<T, MODE, 32>(L.smem, &L.fn)));
+    else if (fixed_ok && D == 64) SSDR_TRY((setup_variant<T, MODE, 64>(L.smem, &L.fn)));
+    else if (fixed_ok && D == 128) SSDR_TRY((setup_variant<T, MODE, 128>(L.smem, &L.fn)));
+    else if (fixed_ok && D == 256) SSDR_TRY((setup_variant<T, MODE, 256>(L.smem, &L.fn)));
+    else SSDR_TRY((setup_variant<T, MODE, 0>(L.smem, &L.fn)));
     L.grid = c->sm_count;
     return SSDR_OK;
 }
@@ -490,8 +565,7 @@ static int launch_steps(Launch<T>& L, int step_begin, int step_end, cudaStream_t
     L.p.step_end = step_end;
     SSDR_CHECK_CUDA(cudaMemsetAsync(L.p.barrier, 0, sizeof(unsigned), s));
     void* args[] = {(void*)&L.p};
-    SSDR_CHECK_CUDA(cudaLaunchCooperativeKernel((void*)select_kernel<T, MODE>, dim3(L.grid), dim3(THREADS), args,
-                                                L.smem, s));
+    SSDR_CHECK_CUDA(cudaLaunchCooperativeKernel(L.fn, dim3(L.grid), dim3(L.p.nwarps * 32), args, L.smem, s));
     return SSDR_OK;
 }
 
@@ -574,6 +648,31 @@ static int kcenter_dev(Ctx* c, const T* dX, size_t N, size_t D, const int64_t* d
     return SSDR_OK;
 }
 
+// Row-sharded FPS (one process per GPU): every rank scans rows [row_begin,row_end) of its full copy of F; after each
+// pick the packed (distance bits << 32 | ~row) winners are max-all-reduced (8 bytes) so all ranks continue from the
+// same centre.  One cooperative launch per pick: the collective is host-enqueued, latency bound by design.
+static int fps_sharded_dev(Ctx* c, const float* dF, size_t N, size_t D, size_t row_begin, size_t row_end,
+                           int32_t first, size_t n_samples, int32_t* d_out, void* comm, cudaStream_t s) {
+    SSDR_REQUIRE(dF && d_out && comm, SSDR_ERR_INVALID, "NULL pointer");
+    SSDR_REQUIRE(row_begin <= row_end && row_end <= N, SSDR_ERR_INVALID, "bad row shard [%zu,%zu) of %zu", row_begin,
+                 row_end, N);
+    SSDR_REQUIRE(n_samples >= 1 && n_samples < (1ull << 31), SSDR_ERR_INVALID, "n_samples=%zu out of range", n_samples);
+    SSDR_REQUIRE(first >= 0 && (size_t)first < N, SSDR_ERR_INVALID, "first index %d outside [0, %zu)", first, N);
+    const int n_steps = (int)n_samples - 1;
+    Launch<float> L;
+    SSDR_TRY(c->ws[WS_FORCED].reserve(sizeof(long long)));
+    long long f64 = first;
+    SSDR_CHECK_CUDA(cudaMemcpyAsync(c->ws[WS_FORCED].p, &f64, sizeof(f64), cudaMemcpyHostToDevice, s));
+    SSDR_TRY((prepare<float, MODE_FPS>(c, L, dF, N, D, row_begin, row_end, c->ws[WS_FORCED].as<long long>(), 1, n_steps, s)));
+    for (int step = 0; step < n_steps; ++step) {
+        SSDR_TRY((launch_steps<float, MODE_FPS>(L, step, step + 1, s)));
+        SSDR_TRY(nccl_allreduce_max_u64(comm, L.p.winners + 2 * (size_t)step, 1, s));
+    }
+    fps_emit_winners_kernel<<<(unsigned)((n_samples + 255) / 256), 256, 0, s>>>(L.p.winners, first, d_out, n_samples);
+    SSDR_CHECK_CUDA(cudaGetLastError());
+    return SSDR_OK;
+}
+
 // host-pointer wrappers: stage in, run, copy picks out
 template <typename T>
 static int fps_host(const T* F, size_t N, size_t D, int32_t first, size_t n_samples, int32_t* out) {
@@ -619,12 +718,19 @@ int ssdr_fps_f64(const double* F, size_t N, size_t D, int32_t first, size_t n, i
 int ssdr_fps_f32_dev(const float* F, size_t N, size_t D, int32_t first, size_t n, int32_t* out, void* stream) {
     Ctx* c;
     SSDR_TRY(get_ctx(&c));
-    return sel::fps_dev<float>(c, F, N, D, first, n, out, stream ? (cudaStream_t)stream : c->stream);
+    return sel::fps_dev<float>(c, F, N, D, first, n, out, (cudaStream_t)stream);
 }
 int ssdr_fps_f64_dev(const double* F, size_t N, size_t D, int32_t first, size_t n, int32_t* out, void* stream) {
     Ctx* c;
     SSDR_TRY(get_ctx(&c));
-    return sel::fps_dev<double>(c, F, N, D, first, n, out, stream ? (cudaStream_t)stream : c->stream);
+    return sel::fps_dev<double>(c, F, N, D, first, n, out, (cudaStream_t)stream);
+}
+int ssdr_fps_f32_sharded(const float* d_F, size_t N, size_t D, size_t row_begin, size_t row_end, int32_t first,
+                         size_t n_samples, int32_t* d_out, void* nccl_comm, void* stream) {
+    Ctx* c;
+    SSDR_TRY(get_ctx(&c));
+    return sel::fps_sharded_dev(c, d_F, N, D, row_begin, row_end, first, n_samples, d_out, nccl_comm,
+                                (cudaStream_t)stream);
 }
 int ssdr_kcenter_f32(const float* X, size_t N, size_t D, const int64_t* sel_, size_t n_sel, size_t n_pick, int64_t* out) {
     return sel::kcenter_host<float>(X, N, D, sel_, n_sel, n_pick, out);
@@ -636,12 +742,12 @@ int ssdr_kcenter_f32_dev(const float* X, size_t N, size_t D, const int64_t* sel_
                          int64_t* out, void* stream) {
     Ctx* c;
     SSDR_TRY(get_ctx(&c));
-    return sel::kcenter_dev<float>(c, X, N, D, sel_, n_sel, n_pick, out, stream ? (cudaStream_t)stream : c->stream);
+    return sel::kcenter_dev<float>(c, X, N, D, sel_, n_sel, n_pick, out, (cudaStream_t)stream);
 }
 int ssdr_kcenter_f64_dev(const double* X, size_t N, size_t D, const int64_t* sel_, size_t n_sel, size_t n_pick,
                          int64_t* out, void* stream) {
     Ctx* c;
     SSDR_TRY(get_ctx(&c));
-    return sel::kcenter_dev<double>(c, X, N, D, sel_, n_sel, n_pick, out, stream ? (cudaStream_t)stream : c->stream);
+    return sel::kcenter_dev<double>(c, X, N, D, sel_, n_sel, n_pick, out, (cudaStream_t)stream);
 }
 }

@@ -1,0 +1,93 @@
+"""Device-resident entry points: the same C ABI, fed with CUDA tensors (torch is used only for device memory and
+streams).  Work is enqueued on torch's current stream."""
+import ctypes as C
+
+import torch
+
+from . import _lib
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _p(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def knn_batch(pts, queries, K, out=None, want_stats=False, int32=False):
+    """pts (B,N,3) f32 cuda, queries (B,Q,3) f32 cuda -> (B,Q,K) int64 (or int32) cuda tensor [, stats dict]."""
+    assert pts.is_cuda and queries.is_cuda and pts.dtype == torch.float32 and queries.dtype == torch.float32
+    pts = pts.contiguous()
+    queries = pts if queries is pts else queries.contiguous()
+    B, N, _ = pts.shape
+    Q = queries.shape[1]
+    if out is None:
+        out = torch.zeros((B, Q, K), dtype=torch.int32 if int32 else torch.int64, device=pts.device)
+    st = _lib.KnnStats() if want_stats else None
+    fn = _lib.lib().ssdr_knn_batch_dev_i32 if out.dtype == torch.int32 else _lib.lib().ssdr_knn_batch_dev
+    _lib.check(fn(_p(pts), B, N, _p(queries), Q, int(K), _p(out), _stream(), C.byref(st) if st else None))
+    if want_stats:
+        return out, {f: getattr(st, f) for f, _ in _lib.KnnStats._fields_}
+    return out
+
+
+def grid_subsample(points, features=None, classes=None, sampleDl=0.1):
+    """points (N,3) f32, features (N,fdim) f32, classes (N,ldim) i32 cuda tensors -> tuple of cuda tensors."""
+    N = points.shape[0]
+    fdim = features.shape[1] if features is not None else 0
+    ldim = (1 if classes.dim() == 1 else classes.shape[1]) if classes is not None else 0
+    M = C.c_size_t(0)
+    h = C.c_void_p()
+    L = _lib.lib()
+    _lib.check(L.ssdr_grid_subsample_dev(_p(points), _p(features), _p(classes), N, fdim, ldim, float(sampleDl), 0,
+                                         _stream(), C.byref(M), C.byref(h)))
+    try:
+        m = M.value
+        dp, df, dc = C.c_void_p(), C.c_void_p(), C.c_void_p()
+        _lib.check(L.ssdr_grid_dev_ptrs(h, C.byref(dp), C.byref(df), C.byref(dc)))
+        out_p = torch.empty((m, 3), dtype=torch.float32, device=points.device)
+        _copy_d2d(out_p, dp, m * 12)
+        out_f = out_c = None
+        if fdim:
+            out_f = torch.empty((m, fdim), dtype=torch.float32, device=points.device)
+            _copy_d2d(out_f, df, m * fdim * 4)
+        if ldim:
+            out_c = torch.empty((m, ldim), dtype=torch.int32, device=points.device)
+            _copy_d2d(out_c, dc, m * ldim * 4)
+        torch.cuda.current_stream().synchronize()
+    finally:
+        L.ssdr_grid_free(h)
+    return out_p, out_f, out_c
+
+
+_cudart = None
+
+
+def _copy_d2d(dst, src_ptr, nbytes):
+    global _cudart
+    if _cudart is None:
+        _cudart = C.CDLL("libcudart.so.12")
+    rc = _cudart.cudaMemcpyAsync(C.c_void_p(dst.data_ptr()), src_ptr, C.c_size_t(nbytes), C.c_int(3), _stream())
+    if rc != 0:
+        raise RuntimeError("cudaMemcpyAsync failed: %d" % rc)
+
+
+def fps(F, n_samples, first, out=None):
+    """F (N,D) f32/f64 cuda -> (n_samples,) int32 cuda."""
+    F = F.contiguous()
+    if out is None:
+        out = torch.zeros(n_samples, dtype=torch.int32, device=F.device)
+    fn = _lib.lib().ssdr_fps_f32_dev if F.dtype == torch.float32 else _lib.lib().ssdr_fps_f64_dev
+    _lib.check(fn(_p(F), F.shape[0], F.shape[1], int(first), int(n_samples), _p(out), _stream()))
+    return out
+
+
+def kcenter(X, selected, n_pick, out=None):
+    """X (N,D) f32/f64 cuda, selected int64 cuda -> (n_pick,) int64 cuda."""
+    X = X.contiguous()
+    if out is None:
+        out = torch.zeros(n_pick, dtype=torch.int64, device=X.device)
+    fn = _lib.lib().ssdr_kcenter_f32_dev if X.dtype == torch.float32 else _lib.lib().ssdr_kcenter_f64_dev
+    _lib.check(fn(_p(X), X.shape[0], X.shape[1], _p(selected), selected.numel(), int(n_pick), _p(out), _stream()))
+    return out

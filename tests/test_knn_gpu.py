@@ -54,7 +54,7 @@ def _node_table(nodes):
 
 
 @pytest.mark.parametrize("name", CLOUDS)
-def test_device_tree_equals_oracle_tree(oracle, golden, name):
+def test_device_tree_equals_sequential_tree(oracle, golden, name):
     p = golden.knn[name + "_pts"]
     vind, nodes = _device_tree(p)
     ovind, onodes = oracle.kdtree_export(p)
