@@ -83,7 +83,7 @@ int ssdr_knn_batch_dev(const float* d_points, size_t batch_size, size_t npts, co
 int ssdr_knn_batch_dev_i32(const float* d_points, size_t batch_size, size_t npts, const float* d_queries,
                            size_t nqueries, size_t K, int32_t* d_indices, void* stream, ssdr_knn_stats* stats);
 
-/* Diagnostic only: the nanoflann-identical tree built on the device for one cloud (node arrays: 2*npts+2 entries). */
+/* Diagnostic only: the nanoflann-identical tree built on the device for one cloud (node arrays: 3*npts+64 entries). */
 int ssdr_knn_debug_tree(const float* points, size_t npts, uint32_t* vind_out, uint32_t* n_nodes_out, uint32_t* left,
                         uint32_t* right, int32_t* child1, int32_t* child2, int32_t* divfeat, float* divlow,
                         float* divhigh);

@@ -3,11 +3,14 @@
 //
 // build_kernel reproduces KDTreeSingleIndexAdaptor::buildIndex (utils/nearest_neighbors/nanoflann.hpp:1136-1147,
 // divideTree :848-896, middleSplit_ :898-937, planeSplit :948-975) bit for bit -- same vind permutation, same
-// divfeat/divlow/divhigh -- as ONE persistent cooperative launch for all batch items:
-//   * the tree is grown level by level; a grid barrier separates levels, work lists carry the nodes to split;
-//   * a node with more than SMALL_MAX points is split by a whole CTA (block-wide prefix counts over global memory),
-//     a smaller node by ONE WARP entirely in shared memory (ballot/popc prefix counts), so deep levels with
-//     thousands of nodes use every warp of the GPU;
+// divfeat/divlow/divhigh -- as ONE persistent cooperative launch for all batch items.  The working array is
+// position-ordered float4 (x, y, z, point index), i.e. nanoflann's vind with the coordinates carried along, so
+// every pass is a coalesced stream and the later search reads a leaf with one load per point:
+//   * TOP: nodes with more than MED_MAX points are split level by level from global memory, one CTA per node
+//     (block-wide prefix counts), a grid barrier between levels;
+//   * SUBTREES: every node of <= MED_MAX points is handed to one CTA that loads it into shared memory ONCE and grows
+//     its whole subtree there -- CTA-wide splits for nodes > SMALL_MAX, one warp per node below (ballot/popc prefix
+//     counts) -- with block barriers only, then writes the permuted points back;
 //   * computeMinMax is a warp/block min-max reduction; each of planeSplit's two Hoare sweeps is a prefix count: the
 //     k-th misplaced element from the left swaps with the k-th misplaced element from the right (SURVEY.md A.5;
 //     checked against the sequential code in tools/proto_kdtree.py and
@@ -24,38 +27,57 @@ constexpr int BT = 1024;
 constexpr int NW = BT / 32;
 constexpr int IPT = 4;
 constexpr int LEAF = 10;
-constexpr int SMALL_MAX = 512;
+constexpr int SMALL_MAX = 512;    // split by one warp
+constexpr int MED_MAX = 4096;     // whole subtree grown in the shared memory of one CTA
+constexpr int LIST_MED = 8;       // > SMALL_MAX nodes inside one subtree level (<= MED_MAX / (SMALL_MAX+1))
+constexpr int LIST_SMALL = 384;   // split-able nodes inside one subtree level (<= MED_MAX / (LEAF+1))
 constexpr int MAX_LEVELS = 512;
 constexpr int MAX_DEPTH = 96;
 constexpr int MAX_K = 64;
-constexpr int WARP_SMEM = SMALL_MAX * 4 + SMALL_MAX * 4 + SMALL_MAX + SMALL_MAX;  // sv, sval, sL(u16), sR(u16)
 
 struct __align__(16) NodeRec {
     int c1, c2;            // children (per-item node ids), -1 = leaf          nanoflann.hpp:853-856
     int feat;              // split dimension                                   :877
     unsigned pad;
     float divlow, divhigh; // tight max of left child / min of right child      :886-887
-    unsigned l, r;         // vind range [l, r)
+    unsigned l, r;         // position range [l, r) in pp
 };
 
+struct __align__(16) Entry {  // a node waiting to be split inside a subtree (positions relative to the subtree)
+    unsigned gid;
+    unsigned short l, r;
+    float lo[3], hi[3];        // loose bbox (drives middleSplit_)
+};
+
+// dynamic shared memory of build_kernel (subtree phase)
+constexpr size_t SM_PP = 0;
+constexpr size_t SM_PSAT = SM_PP + (size_t)MED_MAX * 16;
+constexpr size_t SM_PFAIL = SM_PSAT + (size_t)MED_MAX * 2;
+constexpr size_t SM_LPOS = SM_PFAIL + (size_t)MED_MAX * 2;
+constexpr size_t SM_RPOS = SM_LPOS + (size_t)MED_MAX;
+constexpr size_t SM_WSCR = SM_RPOS + (size_t)MED_MAX;
+constexpr size_t SM_LISTS = SM_WSCR + (size_t)NW * 1024;
+constexpr size_t SM_TOTAL = SM_LISTS + 2 * (size_t)(LIST_MED + LIST_SMALL) * sizeof(Entry);
+
 struct Tree {
-    unsigned N, cap, B;    // points per item, node capacity per item (2N+2), items
-    unsigned lcap;         // capacity of one work list
-    unsigned* vind;        // [B*N]   position -> point index (nanoflann's vind)
-    unsigned* lpos;        // [B*N]   big-node scratch: k-th misplaced position from the left, at [l+k]
+    unsigned N, cap, B;    // points per item, node capacity per item, items
+    unsigned lcap;         // capacity of one top-level work list / of the subtree list
+    float4* pp;            // [B*N]   position-ordered points: (x, y, z, index) -- nanoflann's vind + coordinates
+    unsigned* lpos;        // [B*N]   top-level scratch: k-th misplaced position from the left, at [l+k]
     unsigned* rpos;        // [B*N]   ... from the right
     unsigned* psat;        // [B*N]   inclusive prefix count of predicate-true positions (from the sweep start)
     unsigned* pfail;       // [B*N]   inclusive prefix count of predicate-false positions
     NodeRec* nodes;        // [B*cap]
-    float* nlo;            // [B*cap*3] loose bbox (root bbox cut by the ancestors' planes) -- drives middleSplit_
+    float* nlo;            // [B*cap*3] loose bbox of top-level nodes and subtree roots
     float* nhi;
     float* root_lo;        // [B*3] tight root bbox (computeBoundingBox :1241-1263)
     float* root_hi;
     unsigned* node_count;  // [B]
-    unsigned* list;        // [2 parities][2 classes][lcap] global node ids (item*cap + node)
-    unsigned* list_cnt;    // [(MAX_LEVELS+1)*2]
+    unsigned* list;        // [2 parities][lcap] top-level nodes (global ids: item*cap + node)
+    unsigned* sublist;     // [lcap] subtree roots
+    unsigned* list_cnt;    // [MAX_LEVELS+1] top-level counts; [MAX_LEVELS+1] = subtree count
     unsigned* barrier;     // grid barrier counter
-    unsigned* error;       // bit 0: node capacity, bit 1: level cap, bit 2: DFS stack
+    unsigned* error;       // bit 0: node capacity, bit 1: level cap, bit 2: DFS stack, bit 3: list capacity
     const unsigned char* item_needed;  // [B] build only where a flagged row lives (nullptr = all)
 };
 
@@ -145,27 +167,43 @@ __device__ __forceinline__ void decide_split(const float lo[3], const float hi[3
     *cv_out = cv;
 }
 
-// divideTree's bookkeeping for one split node (:877-892): children records, loose bboxes, next-level work lists
-__device__ __forceinline__ void emit_children(const Tree& t, unsigned g, unsigned b, unsigned l, unsigned r,
-                                              unsigned idx, int cf, float cv, float divlow, float divhigh,
-                                              const float lo[3], const float hi[3], int level) {
-    const unsigned a = atomicAdd(&t.node_count[b], 2u);
-    if (a + 1 >= t.cap) {
-        atomicOr(t.error, 1u);
-        return;
-    }
-    const unsigned ga = b * t.cap + a, gb = ga + 1;
-    NodeRec ra, rb;
+__device__ __forceinline__ float comp(const float4& v, int d) { return d == 0 ? v.x : (d == 1 ? v.y : v.z); }
+
+__device__ __forceinline__ void store_split(const Tree& t, unsigned g, unsigned ga, unsigned b, unsigned l, unsigned r,
+                                            unsigned idx, int cf, float divlow, float divhigh) {
+    // ga = global id of the left child (right child = ga + 1); per-item ids go into the parent's record
+    NodeRec ra, rb, me;
     ra.c1 = ra.c2 = rb.c1 = rb.c2 = -1;
     ra.feat = rb.feat = 0;
-    ra.pad = rb.pad = 0;
+    ra.pad = rb.pad = me.pad = 0;
     ra.divlow = ra.divhigh = rb.divlow = rb.divhigh = 0.f;
     ra.l = l;
     ra.r = l + idx;
     rb.l = l + idx;
     rb.r = r;
     t.nodes[ga] = ra;
-    t.nodes[gb] = rb;
+    t.nodes[ga + 1] = rb;
+    me.c1 = (int)(ga - b * t.cap);
+    me.c2 = me.c1 + 1;
+    me.feat = cf;
+    me.divlow = divlow;
+    me.divhigh = divhigh;
+    me.l = l;
+    me.r = r;
+    t.nodes[g] = me;
+}
+
+// divideTree's bookkeeping for one TOP-LEVEL split (:877-892): children records, loose bboxes, work lists
+__device__ __forceinline__ void emit_children_top(const Tree& t, unsigned g, unsigned b, unsigned l, unsigned r,
+                                                  unsigned idx, int cf, float cv, float divlow, float divhigh,
+                                                  const float lo[3], const float hi[3], int level) {
+    const unsigned a = atomicAdd(&t.node_count[b], 2u);
+    if (a + 1 >= t.cap) {
+        atomicOr(t.error, 1u);
+        return;
+    }
+    const unsigned ga = b * t.cap + a, gb = ga + 1;
+    store_split(t, g, ga, b, l, r, idx, cf, divlow, divhigh);
 #pragma unroll
     for (int d = 0; d < 3; ++d) {
         t.nlo[(size_t)ga * 3 + d] = lo[d];
@@ -173,162 +211,34 @@ __device__ __forceinline__ void emit_children(const Tree& t, unsigned g, unsigne
         t.nlo[(size_t)gb * 3 + d] = (d == cf) ? cv : lo[d];
         t.nhi[(size_t)gb * 3 + d] = hi[d];
     }
-    NodeRec me;
-    me.c1 = (int)a;
-    me.c2 = (int)(a + 1);
-    me.feat = cf;
-    me.pad = 0;
-    me.divlow = divlow;
-    me.divhigh = divhigh;
-    me.l = l;
-    me.r = r;
-    t.nodes[g] = me;
     if (level + 1 >= MAX_LEVELS) {
         atomicOr(t.error, 2u);
         return;
     }
-    unsigned* next = t.list + (size_t)(((level + 1) & 1) * 2) * t.lcap;
-    const unsigned cl = idx, cr = (r - l) - idx;
-    if (cl > (unsigned)LEAF) {
-        const int cls = cl > (unsigned)SMALL_MAX ? 0 : 1;
-        const unsigned pos = atomicAdd(&t.list_cnt[(level + 1) * 2 + cls], 1u);
-        next[(size_t)cls * t.lcap + pos] = ga;
-    }
-    if (cr > (unsigned)LEAF) {
-        const int cls = cr > (unsigned)SMALL_MAX ? 0 : 1;
-        const unsigned pos = atomicAdd(&t.list_cnt[(level + 1) * 2 + cls], 1u);
-        next[(size_t)cls * t.lcap + pos] = gb;
+    unsigned* next = t.list + (size_t)((level + 1) & 1) * t.lcap;
+    const unsigned cnt[2] = {idx, (r - l) - idx};
+    const unsigned gid[2] = {ga, gb};
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+        if (cnt[k] > (unsigned)MED_MAX) {
+            const unsigned pos = atomicAdd(&t.list_cnt[level + 1], 1u);
+            if (pos < t.lcap) next[pos] = gid[k];
+            else atomicOr(t.error, 8u);
+        } else if (cnt[k] > (unsigned)LEAF) {
+            const unsigned pos = atomicAdd(&t.list_cnt[MAX_LEVELS + 1], 1u);
+            if (pos < t.lcap) t.sublist[pos] = gid[k];
+            else atomicOr(t.error, 8u);
+        }
     }
 }
 
-// ---- one warp splits one node of <= SMALL_MAX points in shared memory --------------------------------------
-__device__ __forceinline__ void split_small(const float* __restrict__ pts_all, const Tree& t, unsigned g, int level,
-                                            unsigned char* wsm) {
-    const int lane = threadIdx.x & 31;
-    const unsigned ltmask = (1u << lane) - 1u;
-    unsigned* sv = reinterpret_cast<unsigned*>(wsm);
-    float* sval = reinterpret_cast<float*>(wsm + SMALL_MAX * 4);
-    unsigned short* sL = reinterpret_cast<unsigned short*>(wsm + SMALL_MAX * 8);
-    unsigned short* sR = sL + SMALL_MAX / 2;
-    const unsigned b = g / t.cap;
-    const float* pts = pts_all + (size_t)b * t.N * 3;
-    unsigned* vind = t.vind + (size_t)b * t.N;
-    const unsigned l = __ldcg(&t.nodes[g].l), r = __ldcg(&t.nodes[g].r);
-    const unsigned count = r - l;
-    float lo[3], hi[3];
-#pragma unroll
-    for (int d = 0; d < 3; ++d) {
-        lo[d] = __ldcg(&t.nlo[(size_t)g * 3 + d]);
-        hi[d] = __ldcg(&t.nhi[(size_t)g * 3 + d]);
-    }
-    const int nslot = (int)((count + 31) / 32);
-    // computeMinMax over the node (:827-836)
-    float mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
-    for (int s = 0; s < nslot; ++s) {
-        const unsigned p = (unsigned)s * 32 + lane;
-        if (p < count) {
-            const unsigned v = __ldcg(vind + l + p);
-            sv[p] = v;
-#pragma unroll
-            for (int d = 0; d < 3; ++d) {
-                const float x = __ldg(pts + 3 * (size_t)v + d);
-                mn[d] = fminf(mn[d], x);
-                mx[d] = fmaxf(mx[d], x);
-            }
-        }
-    }
-#pragma unroll
-    for (int d = 0; d < 3; ++d)
-#pragma unroll
-        for (int m = 16; m > 0; m >>= 1) {
-            mn[d] = fminf(mn[d], __shfl_xor_sync(0xffffffffu, mn[d], m));
-            mx[d] = fmaxf(mx[d], __shfl_xor_sync(0xffffffffu, mx[d], m));
-        }
-    int cf;
-    float cv;
-    decide_split(lo, hi, mn, mx, &cf, &cv);
-    __syncwarp();
-    for (int s = 0; s < nslot; ++s) {
-        const unsigned p = (unsigned)s * 32 + lane;
-        if (p < count) sval[p] = __ldg(pts + 3 * (size_t)sv[p] + cf);
-    }
-    __syncwarp();
-    // planeSplit (:948-975): sweep 0 uses "< cutval" from position 0, sweep 1 "<= cutval" from lim1
-    unsigned start = 0, lim1 = 0, lim2 = 0;
-    for (int sweep = 0; sweep < 2; ++sweep) {
-        unsigned tot = 0;
-        for (int s = 0; s < nslot; ++s) {
-            const unsigned p = (unsigned)s * 32 + lane;
-            const bool in = p < count && p >= start;
-            const float v = in ? sval[p] : 0.f;
-            const bool sat = in && (sweep == 0 ? (v < cv) : (v <= cv));
-            tot += __popc(__ballot_sync(0xffffffffu, sat));
-        }
-        const unsigned lim = start + tot;
-        unsigned sb = 0, fb = 0, m = 0;
-        for (int s = 0; s < nslot; ++s) {
-            const unsigned p = (unsigned)s * 32 + lane;
-            const bool in = p < count && p >= start;
-            const float v = in ? sval[p] : 0.f;
-            const bool sat = in && (sweep == 0 ? (v < cv) : (v <= cv));
-            const bool fail = in && !sat;
-            const unsigned bs = __ballot_sync(0xffffffffu, sat), bf = __ballot_sync(0xffffffffu, fail);
-            const bool left_misplaced = fail && p < lim;
-            if (left_misplaced) sL[fb + __popc(bf & ltmask)] = (unsigned short)p;
-            if (sat && p >= lim) sR[tot - (sb + __popc(bs & ltmask) + 1)] = (unsigned short)p;
-            m += __popc(__ballot_sync(0xffffffffu, left_misplaced));
-            sb += __popc(bs);
-            fb += __popc(bf);
-        }
-        __syncwarp();
-        for (unsigned k = lane; k < m; k += 32) {
-            const unsigned a = sL[k], c = sR[k];
-            const unsigned va = sv[a], vc = sv[c];
-            sv[a] = vc;
-            sv[c] = va;
-            const float fa = sval[a], fc = sval[c];
-            sval[a] = fc;
-            sval[c] = fa;
-        }
-        __syncwarp();
-        if (sweep == 0) {
-            lim1 = lim;
-            start = lim;
-        } else {
-            lim2 = lim;
-        }
-    }
-    unsigned idx;  // :934-936
-    if (lim1 > count / 2) idx = lim1;
-    else if (lim2 < count / 2) idx = lim2;
-    else idx = count / 2;
-    float dlow = -INFINITY, dhigh = INFINITY;
-    for (int s = 0; s < nslot; ++s) {
-        const unsigned p = (unsigned)s * 32 + lane;
-        if (p < count) {
-            const float v = sval[p];
-            if (p < idx) dlow = fmaxf(dlow, v);
-            else dhigh = fminf(dhigh, v);
-            vind[l + p] = sv[p];
-        }
-    }
-#pragma unroll
-    for (int m = 16; m > 0; m >>= 1) {
-        dlow = fmaxf(dlow, __shfl_xor_sync(0xffffffffu, dlow, m));
-        dhigh = fminf(dhigh, __shfl_xor_sync(0xffffffffu, dhigh, m));
-    }
-    if (lane == 0) emit_children(t, g, b, l, r, idx, cf, cv, dlow, dhigh, lo, hi, level);
-    __syncwarp();
-}
-
-// ---- one CTA splits one node of > SMALL_MAX points over global memory -----------------------------------------
-__device__ __forceinline__ void split_big(const float* __restrict__ pts_all, const Tree& t, unsigned g, int level,
-                                          unsigned long long* s_warp, float* s_red, float* s_bc) {
+// ---- TOP: one CTA splits one node of > MED_MAX points over global memory ----------------------------------------
+__device__ __forceinline__ void split_big(const Tree& t, unsigned g, int level, unsigned long long* s_warp,
+                                          float* s_red, float* s_bc) {
     const unsigned tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
     const unsigned b = g / t.cap;
-    const float* pts = pts_all + (size_t)b * t.N * 3;
-    unsigned* vind = t.vind + (size_t)b * t.N;
+    float4* pp = t.pp + (size_t)b * t.N;
     unsigned* lpos = t.lpos + (size_t)b * t.N;
     unsigned* rpos = t.rpos + (size_t)b * t.N;
     unsigned* psat = t.psat + (size_t)b * t.N;
@@ -342,15 +252,16 @@ __device__ __forceinline__ void split_big(const float* __restrict__ pts_all, con
         lo[d] = __ldcg(&t.nlo[(size_t)g * 3 + d]);
         hi[d] = __ldcg(&t.nhi[(size_t)g * 3 + d]);
     }
+    // computeMinMax (:827-836)
     float mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
     for (unsigned i = l + tid; i < r; i += BT) {
-        const unsigned v = __ldcg(vind + i);
-#pragma unroll
-        for (int d = 0; d < 3; ++d) {
-            const float x = __ldg(pts + 3 * (size_t)v + d);
-            mn[d] = fminf(mn[d], x);
-            mx[d] = fmaxf(mx[d], x);
-        }
+        const float4 v = __ldcg(pp + i);
+        mn[0] = fminf(mn[0], v.x);
+        mx[0] = fmaxf(mx[0], v.x);
+        mn[1] = fminf(mn[1], v.y);
+        mx[1] = fmaxf(mx[1], v.y);
+        mn[2] = fminf(mn[2], v.z);
+        mx[2] = fmaxf(mx[2], v.z);
     }
 #pragma unroll
     for (int d = 0; d < 3; ++d) {
@@ -385,6 +296,7 @@ __device__ __forceinline__ void split_big(const float* __restrict__ pts_all, con
     const int cf = __float_as_int(s_bc[0]);
     const float cv = s_bc[1];
 
+    // planeSplit (:948-975)
     unsigned start = l, lim1 = l, lim2 = l;
     for (int sweep = 0; sweep < 2; ++sweep) {
         unsigned long long carry = 0;
@@ -397,7 +309,7 @@ __device__ __forceinline__ void split_big(const float* __restrict__ pts_all, con
                 const unsigned i = i0 + k;
                 unsigned long long fl = 0;
                 if (i < r) {
-                    const float v = __ldg(pts + 3 * (size_t)__ldcg(vind + i) + cf);
+                    const float v = comp(__ldcg(pp + i), cf);
                     const bool sat = sweep == 0 ? (v < cv) : (v <= cv);
                     fl = sat ? 1ull : (1ull << 32);
                 }
@@ -434,9 +346,9 @@ __device__ __forceinline__ void split_big(const float* __restrict__ pts_all, con
         __syncthreads();
         for (unsigned k = tid; k < m; k += BT) {
             const unsigned a = lpos[l + k], c = rpos[l + k];
-            const unsigned va = __ldcg(vind + a), vc = __ldcg(vind + c);
-            vind[a] = vc;
-            vind[c] = va;
+            const float4 va = __ldcg(pp + a), vc = __ldcg(pp + c);
+            pp[a] = vc;
+            pp[c] = va;
         }
         __syncthreads();
         if (sweep == 0) {
@@ -447,13 +359,13 @@ __device__ __forceinline__ void split_big(const float* __restrict__ pts_all, con
         }
     }
     const unsigned l1 = lim1 - l, l2 = lim2 - l;
-    unsigned idx;
+    unsigned idx;  // :934-936
     if (l1 > count / 2) idx = l1;
     else if (l2 < count / 2) idx = l2;
     else idx = count / 2;
     float dlow = -INFINITY, dhigh = INFINITY;
     for (unsigned i = l + tid; i < r; i += BT) {
-        const float v = __ldg(pts + 3 * (size_t)__ldcg(vind + i) + cf);
+        const float v = comp(__ldcg(pp + i), cf);
         if (i - l < idx) dlow = fmaxf(dlow, v);
         else dhigh = fminf(dhigh, v);
     }
@@ -472,8 +384,355 @@ __device__ __forceinline__ void split_big(const float* __restrict__ pts_all, con
             dlow = fmaxf(dlow, s_red[w]);
             dhigh = fminf(dhigh, s_red[NW + w]);
         }
-        emit_children(t, g, b, l, r, idx, cf, cv, dlow, dhigh, lo, hi, level);
+        emit_children_top(t, g, b, l, r, idx, cf, cv, dlow, dhigh, lo, hi, level);
     }
+}
+
+// ---- SUBTREES: everything below lives in the shared memory of one CTA ------------------------------------------
+struct SubCtx {
+    float4* spp;            // [count] the subtree's points, position-ordered
+    unsigned short* psat;   // CTA-wide split scratch
+    unsigned short* pfail;
+    unsigned short* lpos;
+    unsigned short* rpos;
+    Entry* next;            // next level's lists: [0, LIST_MED) medium, [LIST_MED, ..) small
+    unsigned* cnt_next;     // [2] medium, small
+    unsigned* nalloc;       // node ids handed out inside the reserved block
+    unsigned base_gid;      // global id of the first reserved node
+    unsigned nreserved;
+    unsigned b, l0;         // item, absolute position of the subtree's first point
+};
+
+__device__ __forceinline__ void emit_children_sub(const Tree& t, const SubCtx& sc, const Entry& e, unsigned idx, int cf,
+                                                  float cv, float divlow, float divhigh) {
+    const unsigned a = atomicAdd(sc.nalloc, 2u);
+    if (a + 1 >= sc.nreserved) {
+        atomicOr(t.error, 1u);
+        return;
+    }
+    const unsigned ga = sc.base_gid + a;
+    store_split(t, e.gid, ga, sc.b, sc.l0 + e.l, sc.l0 + e.r, idx, cf, divlow, divhigh);
+    const unsigned cnt[2] = {idx, (unsigned)(e.r - e.l) - idx};
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+        if (cnt[k] <= (unsigned)LEAF) continue;
+        Entry ce;
+        ce.gid = ga + k;
+        ce.l = (unsigned short)(k == 0 ? e.l : e.l + idx);
+        ce.r = (unsigned short)(k == 0 ? e.l + idx : e.r);
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+            ce.lo[d] = (k == 1 && d == cf) ? cv : e.lo[d];
+            ce.hi[d] = (k == 0 && d == cf) ? cv : e.hi[d];
+        }
+        if (cnt[k] > (unsigned)SMALL_MAX) {
+            const unsigned pos = atomicAdd(&sc.cnt_next[0], 1u);
+            if (pos < (unsigned)LIST_MED) sc.next[pos] = ce;
+            else atomicOr(t.error, 8u);
+        } else {
+            const unsigned pos = atomicAdd(&sc.cnt_next[1], 1u);
+            if (pos < (unsigned)LIST_SMALL) sc.next[LIST_MED + pos] = ce;
+            else atomicOr(t.error, 8u);
+        }
+    }
+}
+
+// one warp splits one node of <= SMALL_MAX points in place
+__device__ __forceinline__ void split_small_sm(const Tree& t, const SubCtx& sc, const Entry& e, unsigned short* wscr) {
+    const int lane = threadIdx.x & 31;
+    const unsigned ltmask = (1u << lane) - 1u;
+    float4* sp = sc.spp + e.l;
+    unsigned short* sL = wscr;
+    unsigned short* sR = wscr + SMALL_MAX / 2;
+    const unsigned count = (unsigned)(e.r - e.l);
+    const int nslot = (int)((count + 31) / 32);
+    float mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
+    for (int s = 0; s < nslot; ++s) {
+        const unsigned p = (unsigned)s * 32 + lane;
+        if (p < count) {
+            const float4 v = sp[p];
+            mn[0] = fminf(mn[0], v.x);
+            mx[0] = fmaxf(mx[0], v.x);
+            mn[1] = fminf(mn[1], v.y);
+            mx[1] = fmaxf(mx[1], v.y);
+            mn[2] = fminf(mn[2], v.z);
+            mx[2] = fmaxf(mx[2], v.z);
+        }
+    }
+#pragma unroll
+    for (int d = 0; d < 3; ++d)
+#pragma unroll
+        for (int m = 16; m > 0; m >>= 1) {
+            mn[d] = fminf(mn[d], __shfl_xor_sync(0xffffffffu, mn[d], m));
+            mx[d] = fmaxf(mx[d], __shfl_xor_sync(0xffffffffu, mx[d], m));
+        }
+    int cf;
+    float cv;
+    decide_split(e.lo, e.hi, mn, mx, &cf, &cv);
+    const float* sval = reinterpret_cast<const float*>(sp) + cf;  // component cf of point p = sval[4*p]
+    unsigned start = 0, lim1 = 0, lim2 = 0;
+    for (int sweep = 0; sweep < 2; ++sweep) {
+        unsigned tot = 0;
+        for (int s = 0; s < nslot; ++s) {
+            const unsigned p = (unsigned)s * 32 + lane;
+            const bool in = p < count && p >= start;
+            const float v = in ? sval[4 * p] : 0.f;
+            const bool sat = in && (sweep == 0 ? (v < cv) : (v <= cv));
+            tot += __popc(__ballot_sync(0xffffffffu, sat));
+        }
+        const unsigned lim = start + tot;
+        unsigned sb = 0, fb = 0, m = 0;
+        for (int s = 0; s < nslot; ++s) {
+            const unsigned p = (unsigned)s * 32 + lane;
+            const bool in = p < count && p >= start;
+            const float v = in ? sval[4 * p] : 0.f;
+            const bool sat = in && (sweep == 0 ? (v < cv) : (v <= cv));
+            const bool fail = in && !sat;
+            const unsigned bs = __ballot_sync(0xffffffffu, sat), bf = __ballot_sync(0xffffffffu, fail);
+            const bool left_misplaced = fail && p < lim;
+            if (left_misplaced) sL[fb + __popc(bf & ltmask)] = (unsigned short)p;
+            if (sat && p >= lim) sR[tot - (sb + __popc(bs & ltmask) + 1)] = (unsigned short)p;
+            m += __popc(__ballot_sync(0xffffffffu, left_misplaced));
+            sb += __popc(bs);
+            fb += __popc(bf);
+        }
+        __syncwarp();
+        for (unsigned k = lane; k < m; k += 32) {
+            const unsigned a = sL[k], c = sR[k];
+            const float4 va = sp[a], vc = sp[c];
+            sp[a] = vc;
+            sp[c] = va;
+        }
+        __syncwarp();
+        if (sweep == 0) {
+            lim1 = lim;
+            start = lim;
+        } else {
+            lim2 = lim;
+        }
+    }
+    unsigned idx;  // :934-936
+    if (lim1 > count / 2) idx = lim1;
+    else if (lim2 < count / 2) idx = lim2;
+    else idx = count / 2;
+    float dlow = -INFINITY, dhigh = INFINITY;
+    for (int s = 0; s < nslot; ++s) {
+        const unsigned p = (unsigned)s * 32 + lane;
+        if (p < count) {
+            const float v = sval[4 * p];
+            if (p < idx) dlow = fmaxf(dlow, v);
+            else dhigh = fminf(dhigh, v);
+        }
+    }
+#pragma unroll
+    for (int m = 16; m > 0; m >>= 1) {
+        dlow = fmaxf(dlow, __shfl_xor_sync(0xffffffffu, dlow, m));
+        dhigh = fminf(dhigh, __shfl_xor_sync(0xffffffffu, dhigh, m));
+    }
+    if (lane == 0) emit_children_sub(t, sc, e, idx, cf, cv, dlow, dhigh);
+    __syncwarp();
+}
+
+// the whole CTA splits one node of SMALL_MAX < count <= MED_MAX points in place (count <= BT*IPT: one scan per sweep)
+__device__ __forceinline__ void split_med_sm(const Tree& t, const SubCtx& sc, const Entry& e, unsigned long long* s_warp,
+                                             float* s_red, float* s_bc) {
+    const unsigned tid = threadIdx.x;
+    const int lane = tid & 31, warp = tid >> 5;
+    float4* sp = sc.spp + e.l;
+    const unsigned count = (unsigned)(e.r - e.l);
+    __syncthreads();
+    float mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
+    for (unsigned i = tid; i < count; i += BT) {
+        const float4 v = sp[i];
+        mn[0] = fminf(mn[0], v.x);
+        mx[0] = fmaxf(mx[0], v.x);
+        mn[1] = fminf(mn[1], v.y);
+        mx[1] = fmaxf(mx[1], v.y);
+        mn[2] = fminf(mn[2], v.z);
+        mx[2] = fmaxf(mx[2], v.z);
+    }
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+#pragma unroll
+        for (int m = 16; m > 0; m >>= 1) {
+            mn[d] = fminf(mn[d], __shfl_xor_sync(0xffffffffu, mn[d], m));
+            mx[d] = fmaxf(mx[d], __shfl_xor_sync(0xffffffffu, mx[d], m));
+        }
+        if (lane == 0) {
+            s_red[d * NW + warp] = mn[d];
+            s_red[(3 + d) * NW + warp] = mx[d];
+        }
+    }
+    __syncthreads();
+    if (tid == 0) {
+        float amn[3], amx[3];
+        for (int d = 0; d < 3; ++d) {
+            amn[d] = s_red[d * NW];
+            amx[d] = s_red[(3 + d) * NW];
+            for (int w = 1; w < NW; ++w) {
+                amn[d] = fminf(amn[d], s_red[d * NW + w]);
+                amx[d] = fmaxf(amx[d], s_red[(3 + d) * NW + w]);
+            }
+        }
+        int cf;
+        float cv;
+        decide_split(e.lo, e.hi, amn, amx, &cf, &cv);
+        s_bc[0] = __int_as_float(cf);
+        s_bc[1] = cv;
+    }
+    __syncthreads();
+    const int cf = __float_as_int(s_bc[0]);
+    const float cv = s_bc[1];
+    const float* sval = reinterpret_cast<const float*>(sp) + cf;
+
+    unsigned start = 0, lim1 = 0, lim2 = 0;
+    for (int sweep = 0; sweep < 2; ++sweep) {
+        const unsigned i0 = start + tid * IPT;
+        unsigned long long f[IPT];
+        unsigned long long local = 0;
+#pragma unroll
+        for (int k = 0; k < IPT; ++k) {
+            const unsigned i = i0 + k;
+            unsigned long long fl = 0;
+            if (i < count) {
+                const float v = sval[4 * i];
+                const bool sat = sweep == 0 ? (v < cv) : (v <= cv);
+                fl = sat ? 1ull : (1ull << 32);
+            }
+            local += fl;
+            f[k] = local;
+        }
+        unsigned long long tot;
+        const unsigned long long incl = block_scan_incl(local, s_warp, &tot);
+        const unsigned long long excl = incl - local;
+#pragma unroll
+        for (int k = 0; k < IPT; ++k) {
+            const unsigned i = i0 + k;
+            if (i < count) {
+                const unsigned long long v = excl + f[k];
+                sc.psat[i] = (unsigned short)(v & 0xFFFFull);
+                sc.pfail[i] = (unsigned short)((v >> 32) & 0xFFFFull);
+            }
+        }
+        __syncthreads();
+        const unsigned tot_sat = (unsigned)(tot & 0xFFFFFFFFull);
+        const unsigned lim = start + tot_sat;
+        const unsigned m = lim > start ? sc.pfail[lim - 1] : 0u;
+        for (unsigned i = start + tid; i < count; i += BT) {
+            const unsigned cs = sc.psat[i], cfl = sc.pfail[i];
+            const bool sat = (i == start ? cs : cs - sc.psat[i - 1]) != 0;
+            if (!sat) {
+                if (i < lim) sc.lpos[cfl - 1] = (unsigned short)i;
+            } else {
+                if (i >= lim) sc.rpos[tot_sat - cs] = (unsigned short)i;
+            }
+        }
+        __syncthreads();
+        for (unsigned k = tid; k < m; k += BT) {
+            const unsigned a = sc.lpos[k], c = sc.rpos[k];
+            const float4 va = sp[a], vc = sp[c];
+            sp[a] = vc;
+            sp[c] = va;
+        }
+        __syncthreads();
+        if (sweep == 0) {
+            lim1 = lim;
+            start = lim;
+        } else {
+            lim2 = lim;
+        }
+    }
+    unsigned idx;
+    if (lim1 > count / 2) idx = lim1;
+    else if (lim2 < count / 2) idx = lim2;
+    else idx = count / 2;
+    float dlow = -INFINITY, dhigh = INFINITY;
+    for (unsigned i = tid; i < count; i += BT) {
+        const float v = sval[4 * i];
+        if (i < idx) dlow = fmaxf(dlow, v);
+        else dhigh = fminf(dhigh, v);
+    }
+#pragma unroll
+    for (int m = 16; m > 0; m >>= 1) {
+        dlow = fmaxf(dlow, __shfl_xor_sync(0xffffffffu, dlow, m));
+        dhigh = fminf(dhigh, __shfl_xor_sync(0xffffffffu, dhigh, m));
+    }
+    if (lane == 0) {
+        s_red[warp] = dlow;
+        s_red[NW + warp] = dhigh;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        for (int w = 1; w < NW; ++w) {
+            dlow = fmaxf(dlow, s_red[w]);
+            dhigh = fminf(dhigh, s_red[NW + w]);
+        }
+        emit_children_sub(t, sc, e, idx, cf, cv, dlow, dhigh);
+    }
+    __syncthreads();
+}
+
+__device__ __forceinline__ void build_subtree(const Tree& t, unsigned groot, unsigned char* dsm,
+                                              unsigned long long* s_warp, float* s_red, float* s_bc, unsigned* s_ctl) {
+    // s_ctl: [0..1] counts of list 0 (medium, small), [2..3] counts of list 1, [4] nalloc, [5] base node id
+    const unsigned tid = threadIdx.x;
+    const int warp = tid >> 5;
+    float4* spp = reinterpret_cast<float4*>(dsm + SM_PP);
+    Entry* lists = reinterpret_cast<Entry*>(dsm + SM_LISTS);
+    __syncthreads();  // the previous subtree of this CTA is completely done with shared memory
+    const unsigned b = groot / t.cap;
+    const unsigned l0 = __ldcg(&t.nodes[groot].l), r0 = __ldcg(&t.nodes[groot].r);
+    const unsigned count = r0 - l0;
+    float4* pp = t.pp + (size_t)b * t.N + l0;
+    for (unsigned i = tid; i < count; i += BT) spp[i] = __ldcg(pp + i);
+    if (tid == 0) {
+        const unsigned base = atomicAdd(&t.node_count[b], 2u * count);
+        if (base + 2u * count > t.cap) atomicOr(t.error, 1u);
+        s_ctl[0] = count > (unsigned)SMALL_MAX ? 1u : 0u;
+        s_ctl[1] = count > (unsigned)SMALL_MAX ? 0u : 1u;
+        s_ctl[2] = s_ctl[3] = 0u;
+        s_ctl[4] = 0u;
+        s_ctl[5] = base;
+        Entry e;
+        e.gid = groot;
+        e.l = 0;
+        e.r = (unsigned short)count;
+        for (int d = 0; d < 3; ++d) {
+            e.lo[d] = __ldcg(&t.nlo[(size_t)groot * 3 + d]);
+            e.hi[d] = __ldcg(&t.nhi[(size_t)groot * 3 + d]);
+        }
+        lists[count > (unsigned)SMALL_MAX ? 0 : LIST_MED] = e;
+    }
+    __syncthreads();
+    SubCtx sc;
+    sc.spp = spp;
+    sc.psat = reinterpret_cast<unsigned short*>(dsm + SM_PSAT);
+    sc.pfail = reinterpret_cast<unsigned short*>(dsm + SM_PFAIL);
+    sc.lpos = reinterpret_cast<unsigned short*>(dsm + SM_LPOS);
+    sc.rpos = reinterpret_cast<unsigned short*>(dsm + SM_RPOS);
+    sc.nalloc = &s_ctl[4];
+    sc.base_gid = b * t.cap + s_ctl[5];
+    sc.nreserved = 2u * count;
+    sc.b = b;
+    sc.l0 = l0;
+    const bool ok = s_ctl[5] + 2u * count <= t.cap;
+    for (int lvl = 0; ok; ++lvl) {
+        const int cur = lvl & 1;
+        Entry* cl = lists + (size_t)cur * (LIST_MED + LIST_SMALL);
+        sc.next = lists + (size_t)(cur ^ 1) * (LIST_MED + LIST_SMALL);
+        sc.cnt_next = &s_ctl[(cur ^ 1) * 2];
+        const unsigned nmed = min(s_ctl[cur * 2], (unsigned)LIST_MED);
+        const unsigned nsmall = min(s_ctl[cur * 2 + 1], (unsigned)LIST_SMALL);
+        if (nmed == 0 && nsmall == 0) break;
+        for (unsigned m = 0; m < nmed; ++m) split_med_sm(t, sc, cl[m], s_warp, s_red, s_bc);
+        __syncthreads();
+        for (unsigned w = warp; w < nsmall; w += NW)
+            split_small_sm(t, sc, cl[LIST_MED + w], reinterpret_cast<unsigned short*>(dsm + SM_WSCR) + (size_t)warp * 512);
+        __syncthreads();
+        if (tid == 0) s_ctl[cur * 2] = s_ctl[cur * 2 + 1] = 0u;
+        __syncthreads();
+    }
+    for (unsigned i = tid; i < count; i += BT) pp[i] = spp[i];
 }
 
 __global__ void __launch_bounds__(BT, 1) build_kernel(const float* __restrict__ pts_all, const Tree t) {
@@ -481,24 +740,30 @@ __global__ void __launch_bounds__(BT, 1) build_kernel(const float* __restrict__ 
     __shared__ unsigned long long s_warp[32];
     __shared__ float s_red[6 * NW];
     __shared__ float s_bc[4];
+    __shared__ unsigned s_ctl[8];
     const unsigned tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
     unsigned phase = 0;
 
-    // ---- roots: vind = identity (init_vind :1232-1238), data bbox (computeBoundingBox :1241-1263)
+    // ---- roots: pp = (point, identity index) (init_vind :1232-1238), data bbox (computeBoundingBox :1241-1263)
     for (unsigned b = blockIdx.x; b < t.B; b += gridDim.x) {
         if (t.item_needed && !t.item_needed[b]) continue;
         const float* pts = pts_all + (size_t)b * t.N * 3;
-        unsigned* vind = t.vind + (size_t)b * t.N;
+        float4* pp = t.pp + (size_t)b * t.N;
         float mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
         for (unsigned i = tid; i < t.N; i += BT) {
-            vind[i] = i;
-#pragma unroll
-            for (int d = 0; d < 3; ++d) {
-                const float x = __ldg(pts + 3 * (size_t)i + d);
-                mn[d] = fminf(mn[d], x);
-                mx[d] = fmaxf(mx[d], x);
-            }
+            float4 v;
+            v.x = __ldg(pts + 3 * (size_t)i);
+            v.y = __ldg(pts + 3 * (size_t)i + 1);
+            v.z = __ldg(pts + 3 * (size_t)i + 2);
+            v.w = __uint_as_float(i);
+            pp[i] = v;
+            mn[0] = fminf(mn[0], v.x);
+            mx[0] = fmaxf(mx[0], v.x);
+            mn[1] = fminf(mn[1], v.y);
+            mx[1] = fmaxf(mx[1], v.y);
+            mn[2] = fminf(mn[2], v.z);
+            mx[2] = fmaxf(mx[2], v.z);
         }
         __syncthreads();
 #pragma unroll
@@ -536,26 +801,30 @@ __global__ void __launch_bounds__(BT, 1) build_kernel(const float* __restrict__ 
             root.r = t.N;
             t.nodes[g] = root;
             t.node_count[b] = 1;
-            if (t.N > (unsigned)LEAF) {
-                const int cls = t.N > (unsigned)SMALL_MAX ? 0 : 1;
-                const unsigned pos = atomicAdd(&t.list_cnt[cls], 1u);
-                t.list[(size_t)cls * t.lcap + pos] = g;
+            if (t.N > (unsigned)MED_MAX) {
+                const unsigned pos = atomicAdd(&t.list_cnt[0], 1u);
+                t.list[pos] = g;
+            } else if (t.N > (unsigned)LEAF) {
+                const unsigned pos = atomicAdd(&t.list_cnt[MAX_LEVELS + 1], 1u);
+                t.sublist[pos] = g;
             }
         }
         __syncthreads();
     }
     grid_sync(t.barrier, phase);
 
+    // ---- TOP levels
     for (int level = 0; level < MAX_LEVELS; ++level) {
-        const unsigned nbig = __ldcg(&t.list_cnt[level * 2]), nsmall = __ldcg(&t.list_cnt[level * 2 + 1]);
-        if (nbig == 0 && nsmall == 0) break;
-        const unsigned* cur = t.list + (size_t)((level & 1) * 2) * t.lcap;
-        for (unsigned i = blockIdx.x; i < nbig; i += gridDim.x)
-            split_big(pts_all, t, __ldcg(cur + i), level, s_warp, s_red, s_bc);
-        for (unsigned w = blockIdx.x * NW + warp; w < nsmall; w += gridDim.x * NW)
-            split_small(pts_all, t, __ldcg(cur + t.lcap + w), level, dyn_smem + (size_t)warp * WARP_SMEM);
+        const unsigned nbig = __ldcg(&t.list_cnt[level]);
+        if (nbig == 0) break;
+        const unsigned* cur = t.list + (size_t)(level & 1) * t.lcap;
+        for (unsigned i = blockIdx.x; i < nbig; i += gridDim.x) split_big(t, __ldcg(cur + i), level, s_warp, s_red, s_bc);
         grid_sync(t.barrier, phase);
     }
+    // ---- SUBTREES (independent; no further grid barrier)
+    const unsigned nsub = min(__ldcg(&t.list_cnt[MAX_LEVELS + 1]), t.lcap);
+    for (unsigned i = blockIdx.x; i < nsub; i += gridDim.x)
+        build_subtree(t, __ldcg(t.sublist + i), dyn_smem, s_warp, s_red, s_bc, s_ctl);
 }
 
 __global__ void mark_items_kernel(const unsigned* __restrict__ flag_list, unsigned n_flag, unsigned Q,
@@ -581,17 +850,14 @@ __device__ __forceinline__ NodeRec load_node(const NodeRec* p) {
 
 // ---- exact replay of nanoflann's search for the flagged rows -------------------------------------------------
 template <typename OutT>
-__global__ void __launch_bounds__(32) exact_query_kernel(const float* __restrict__ pts_all,
-                                                         const float* __restrict__ q_all, const Tree t, unsigned Q,
+__global__ void __launch_bounds__(32) exact_query_kernel(const float* __restrict__ q_all, const Tree t, unsigned Q,
                                                          int K, const unsigned* __restrict__ flag_list,
                                                          unsigned n_flag, OutT* __restrict__ out) {
     const unsigned f = blockIdx.x * blockDim.x + threadIdx.x;
     if (f >= n_flag) return;
     const unsigned row = flag_list[f];
     const unsigned b = row / Q;
-    const unsigned N = t.N;
-    const float* pts = pts_all + (size_t)b * N * 3;
-    const unsigned* vind = t.vind + (size_t)b * N;
+    const float4* pp = t.pp + (size_t)b * t.N;
     const NodeRec* nodes = t.nodes + (size_t)b * t.cap;
     const float q[3] = {q_all[3 * (size_t)row], q_all[3 * (size_t)row + 1], q_all[3 * (size_t)row + 2]};
 
@@ -661,71 +927,77 @@ __global__ void __launch_bounds__(32) exact_query_kernel(const float* __restrict
             }
             nd = load_node(nodes + best);
         }
-        const float worst = rd[K - 1];  // snapshot once per leaf (:1277)
-        for (unsigned i = nd.l; i < nd.r; ++i) {
-            const unsigned index = vind[i];
-            float dist = 0.f;
+        // leaf (:1277-1287): fetch its <= LEAF points with independent loads, then insert in vind order
+        const int n = (int)(nd.r - nd.l);
+        float4 buf[LEAF];
 #pragma unroll
-            for (int d = 0; d < 3; ++d) {
-                const float df = __fsub_rn(q[d], __ldg(pts + 3 * (size_t)index + d));
-                dist = __fadd_rn(dist, __fmul_rn(df, df));
-            }
-            if (dist < worst) {  // KNNResultSet::addPoint (:72-96), strict '>' shifting
-                int j;
-                for (j = count; j > 0; --j) {
-                    if (rd[j - 1] > dist) {
-                        if (j < K) {
-                            rd[j] = rd[j - 1];
-                            ri[j] = ri[j - 1];
-                        }
-                    } else
-                        break;
+        for (int k = 0; k < LEAF; ++k)
+            if (k < n) buf[k] = __ldg(pp + nd.l + k);
+        const float worst = rd[K - 1];  // snapshot once per leaf (:1277)
+#pragma unroll
+        for (int k = 0; k < LEAF; ++k) {
+            if (k < n) {
+                const float dx = __fsub_rn(q[0], buf[k].x), dy = __fsub_rn(q[1], buf[k].y), dz = __fsub_rn(q[2], buf[k].z);
+                const float dist = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+                if (dist < worst) {  // KNNResultSet::addPoint (:72-96), strict '>' shifting
+                    const unsigned index = __float_as_uint(buf[k].w);
+                    int jj;
+                    for (jj = count; jj > 0; --jj) {
+                        if (rd[jj - 1] > dist) {
+                            if (jj < K) {
+                                rd[jj] = rd[jj - 1];
+                                ri[jj] = ri[jj - 1];
+                            }
+                        } else
+                            break;
+                    }
+                    if (jj < K) {
+                        rd[jj] = dist;
+                        ri[jj] = index;
+                    }
+                    if (count < K) ++count;
                 }
-                if (j < K) {
-                    rd[j] = dist;
-                    ri[j] = index;
-                }
-                if (count < K) ++count;
             }
         }
     }
     OutT* o = out + (size_t)row * K;
-    for (int j = 0; j < count; ++j) o[j] = (OutT)ri[j];
+    for (int jj = 0; jj < count; ++jj) o[jj] = (OutT)ri[jj];
 }
 
 enum { TW_BASE = 16 };  // workspace slots TW_BASE.. are owned by this header
 
 // Carve the tree arrays out of workspace slabs and zero the small control block.
 static int alloc_tree(Ctx* c, cudaStream_t s, size_t B, size_t N, Tree* out) {
-    const size_t cap = 2 * N + 2;
-    const size_t lcap = B * (N / 5 + 2) + 16;  // a level never holds more split-able nodes than that
-    SSDR_TRY(c->ws[TW_BASE + 0].reserve(5 * B * N * sizeof(unsigned)));
+    const size_t cap = 3 * N + 64;
+    const size_t lcap = B * (N / (LEAF + 1) + 2) + 16;
+    SSDR_TRY(c->ws[TW_BASE + 0].reserve(B * N * (sizeof(float4) + 4 * sizeof(unsigned))));
     SSDR_TRY(c->ws[TW_BASE + 1].reserve(B * cap * (sizeof(NodeRec) + 6 * sizeof(float))));
-    SSDR_TRY(c->ws[TW_BASE + 2].reserve(4 * lcap * sizeof(unsigned)));
-    const size_t ctl_words = 6 * B + B + (size_t)(MAX_LEVELS + 1) * 2 + 8 + (B + 3) / 4 + 4;
+    SSDR_TRY(c->ws[TW_BASE + 2].reserve(3 * lcap * sizeof(unsigned)));
+    const size_t ctl_words = 6 * B + B + (size_t)(MAX_LEVELS + 2) + 8 + (B + 3) / 4 + 4;
     SSDR_TRY(c->ws[TW_BASE + 3].reserve(ctl_words * sizeof(unsigned)));
     Tree t;
     t.N = (unsigned)N;
     t.cap = (unsigned)cap;
     t.B = (unsigned)B;
     t.lcap = (unsigned)lcap;
-    unsigned* pb = c->ws[TW_BASE + 0].as<unsigned>();
-    t.vind = pb;
-    t.lpos = pb + B * N;
-    t.rpos = pb + 2 * B * N;
-    t.psat = pb + 3 * B * N;
-    t.pfail = pb + 4 * B * N;
+    t.pp = c->ws[TW_BASE + 0].as<float4>();
+    unsigned* pb = reinterpret_cast<unsigned*>(t.pp + B * N);
+    t.lpos = pb;
+    t.rpos = pb + B * N;
+    t.psat = pb + 2 * B * N;
+    t.pfail = pb + 3 * B * N;
     t.nodes = c->ws[TW_BASE + 1].as<NodeRec>();
     t.nlo = reinterpret_cast<float*>(t.nodes + B * cap);
     t.nhi = t.nlo + B * cap * 3;
     t.list = c->ws[TW_BASE + 2].as<unsigned>();
+    t.sublist = t.list + 2 * lcap;
     unsigned* ctl = c->ws[TW_BASE + 3].as<unsigned>();
     SSDR_CHECK_CUDA(cudaMemsetAsync(ctl, 0, ctl_words * sizeof(unsigned), s));
     t.root_lo = reinterpret_cast<float*>(ctl);
     t.root_hi = reinterpret_cast<float*>(ctl + 3 * B);
     t.node_count = ctl + 6 * B;
     t.list_cnt = ctl + 7 * B;
-    t.barrier = t.list_cnt + (size_t)(MAX_LEVELS + 1) * 2;
+    t.barrier = t.list_cnt + (size_t)(MAX_LEVELS + 2);
     t.error = t.barrier + 4;
     t.item_needed = nullptr;
     *out = t;
@@ -734,7 +1006,7 @@ static int alloc_tree(Ctx* c, cudaStream_t s, size_t B, size_t N, Tree* out) {
 static unsigned char* tree_needed_flags(const Tree& t) { return reinterpret_cast<unsigned char*>(t.error + 4); }
 
 static int launch_build(Ctx* c, cudaStream_t s, const float* d_pts, const Tree& t) {
-    const size_t smem = (size_t)NW * WARP_SMEM;
+    const size_t smem = SM_TOTAL;
     SSDR_CHECK_CUDA(cudaFuncSetAttribute(build_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int nb = 0;
     SSDR_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, build_kernel, BT, smem));
@@ -751,7 +1023,7 @@ static int check_tree_error(Ctx* c, cudaStream_t s, const Tree& t) {
     SSDR_TRY(d2h_sync(c, &h_err, t.error, sizeof(unsigned), s));
     SSDR_REQUIRE(h_err == 0, SSDR_ERR_UNSUPPORTED,
                  "exact tie path gave up (flags %u: 1 node capacity, 2 more than %d tree levels, 4 search stack deeper "
-                 "than %d)", h_err, MAX_LEVELS, MAX_DEPTH);
+                 "than %d, 8 work list capacity)", h_err, MAX_LEVELS, MAX_DEPTH);
     return SSDR_OK;
 }
 
@@ -767,8 +1039,7 @@ static int resolve_flagged(Ctx* c, cudaStream_t s, const float* d_pts, size_t B,
     t.item_needed = needed;
     mark_items_kernel<<<(n_flag + 255) / 256, 256, 0, s>>>(flag_list, n_flag, (unsigned)Q, needed);
     SSDR_TRY(launch_build(c, s, d_pts, t));
-    exact_query_kernel<OutT><<<(n_flag + 31) / 32, 32, 0, s>>>(d_pts, d_q, t, (unsigned)Q, (int)K, flag_list, n_flag,
-                                                              d_out);
+    exact_query_kernel<OutT><<<(n_flag + 31) / 32, 32, 0, s>>>(d_q, t, (unsigned)Q, (int)K, flag_list, n_flag, d_out);
     SSDR_CHECK_CUDA(cudaGetLastError());
     SSDR_TRY(check_tree_error(c, s, t));
     if (builds) *builds = B;  // upper bound; items without flagged rows are skipped inside the kernel

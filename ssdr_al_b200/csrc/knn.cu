@@ -434,7 +434,7 @@ int ssdr_knn_batch_dev(const float* d_points, size_t batch_size, size_t npts, co
                                    nqueries, K, reinterpret_cast<long long*>(d_indices), stats);
 }
 // Diagnostic: build the nanoflann-identical tree of one cloud on the device and copy it back (tests compare it with
-// a sequential CPU build).  Node arrays must hold 2*npts+2 entries.
+// a sequential CPU build).  Node arrays must hold 3*npts+64 entries.
 int ssdr_knn_debug_tree(const float* points, size_t npts, uint32_t* vind_out, uint32_t* n_nodes_out, uint32_t* left,
                         uint32_t* right, int32_t* child1, int32_t* child2, int32_t* divfeat, float* divlow,
                         float* divhigh) {
@@ -451,7 +451,14 @@ int ssdr_knn_debug_tree(const float* points, size_t npts, uint32_t* vind_out, ui
     SSDR_TRY(d2h_sync(c, n_nodes_out, t.node_count, sizeof(unsigned), s));
     const size_t nn = *n_nodes_out;
     SSDR_REQUIRE(nn <= t.cap, SSDR_ERR_CUDA, "node count %zu exceeds capacity", nn);
-    SSDR_TRY(d2h_sync(c, vind_out, t.vind, npts * sizeof(unsigned), s));
+    {
+        float4* hp = (float4*)malloc(npts * sizeof(float4));
+        SSDR_REQUIRE(hp, SSDR_ERR_NOMEM, "host allocation failed");
+        int rc0 = d2h_sync(c, hp, t.pp, npts * sizeof(float4), s);
+        for (size_t i = 0; rc0 == SSDR_OK && i < npts; ++i) memcpy(&vind_out[i], &hp[i].w, 4);
+        free(hp);
+        SSDR_TRY(rc0);
+    }
     kdtree::NodeRec* h = (kdtree::NodeRec*)malloc(nn * sizeof(kdtree::NodeRec));
     SSDR_REQUIRE(h, SSDR_ERR_NOMEM, "host allocation failed");
     int rc = d2h_sync(c, h, t.nodes, nn * sizeof(kdtree::NodeRec), s);

@@ -30,7 +30,7 @@ namespace ssdr {
 int nccl_allreduce_max_u64(void* comm, unsigned long long* buf, size_t count, cudaStream_t stream);  // nccl_shim.cu
 namespace sel {
 
-constexpr int THREADS = 256;
+constexpr int THREADS = 512;          // upper bound; the host launches p.nwarps*32 threads
 constexpr int WARPS = THREADS / 32;
 constexpr int MAX_LEAVES = 128;
 constexpr int MAX_STACK = 10;
@@ -212,19 +212,26 @@ template <>
 __device__ __forceinline__ unsigned long long cand_row<double>(const Cand& c) {
     return ~c.lo;
 }
-__device__ __forceinline__ bool cand_less(const Cand& a, const Cand& b) {
-    return a.hi < b.hi || (a.hi == b.hi && a.lo < b.lo);
+template <typename T>
+__device__ __forceinline__ Cand cand_max(const Cand& a, const Cand& b) {
+    if (sizeof(T) == 4) {  // packed in hi alone
+        Cand r;
+        r.hi = a.hi < b.hi ? b.hi : a.hi;
+        r.lo = 0;
+        return r;
+    }
+    const bool less = a.hi < b.hi || (a.hi == b.hi && a.lo < b.lo);
+    return less ? b : a;
 }
-__device__ __forceinline__ Cand cand_max(const Cand& a, const Cand& b) { return cand_less(a, b) ? b : a; }
-__device__ __forceinline__ Cand cand_shfl_xor(const Cand& a, int m) {
-    Cand r;
-    r.hi = __shfl_xor_sync(0xffffffffu, a.hi, m);
-    r.lo = __shfl_xor_sync(0xffffffffu, a.lo, m);
-    return r;
-}
+template <typename T>
 __device__ __forceinline__ Cand warp_max(Cand c) {
 #pragma unroll
-    for (int m = 16; m > 0; m >>= 1) c = cand_max(c, cand_shfl_xor(c, m));
+    for (int m = 16; m > 0; m >>= 1) {
+        Cand o;
+        o.hi = __shfl_xor_sync(0xffffffffu, c.hi, m);
+        o.lo = sizeof(T) == 4 ? 0ull : __shfl_xor_sync(0xffffffffu, c.lo, m);
+        c = cand_max<T>(c, o);
+    }
     return c;
 }
 
@@ -254,14 +261,30 @@ __device__ __forceinline__ double dot64_fixed(const T* __restrict__ a, const T* 
     return acc;
 }
 
-template <typename T, int MODE, int DT>
+// Mailbox of one CTA for one step parity: candidate + tag (= step + 1).  Readers poll the tags directly, so a pick
+// costs one release store and one acquire poll instead of an atomic counter plus a second read.
+struct __align__(32) Mailbox {
+    unsigned long long hi, lo;
+    unsigned long long tag;
+    unsigned long long pad;
+};
+__device__ __forceinline__ void st_release_u64(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.release.gpu.global.u64 [%0], %1;\n" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];\n" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+
+template <typename T, int MODE, int DT, int GT>  // DT: compile-time D (0 = generic), GT: row groups per unit (0 = runtime)
 __global__ void __launch_bounds__(THREADS, 1) select_kernel(const Params<T> p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     typedef typename std::conditional<MODE == MODE_KCENTER, double, T>::type RowVal;
     const int D = DT > 0 ? DT : p.D;
     const int stride = p.stride;
-    const int GPU_ = p.groups_per_unit;
-    const int RW = 4 * GPU_;  // rows per unit
+    const int NG = GT > 0 ? GT : p.groups_per_unit;
+    const int RW = 4 * NG;  // rows per unit
     const int S = p.nstages;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int G = gridDim.x;
@@ -270,10 +293,10 @@ __global__ void __launch_bounds__(THREADS, 1) select_kernel(const Params<T> p) {
 
     // shared layout: centre row (generic path) | reduction scratch | per-warp stage rings
     T* s_center = reinterpret_cast<T*>(smem_raw);
-    size_t off = align_up_dev((size_t)(p.D + 8) * sizeof(T), 16);
+    unsigned off = (unsigned)align_up_dev((size_t)(p.D + 8) * sizeof(T), 16);
     Cand* s_red = reinterpret_cast<Cand*>(smem_raw + off);
-    off += align_up_dev(WARPS * sizeof(Cand), 16);
-    const size_t unit_elems = (size_t)RW * stride;
+    off += (unsigned)align_up_dev(WARPS * sizeof(Cand), 16);
+    const unsigned unit_elems = (unsigned)RW * (unsigned)stride;
     T* ring = reinterpret_cast<T*>(smem_raw + off) + (size_t)warp * S * unit_elems;
     __shared__ unsigned long long s_next_center;
 
@@ -286,35 +309,39 @@ __global__ void __launch_bounds__(THREADS, 1) select_kernel(const Params<T> p) {
     const unsigned long long u_begin = min(gw * upw, units_total);
     const unsigned long long u_end = min(u_begin + upw, units_total);
     const int n_it = (int)(u_end - u_begin);
-    const long long total_it = (long long)n_it * (p.step_end - p.step_begin);
+    const unsigned long long w_row0 = p.row_begin + u_begin * (unsigned long long)RW;  // first row of this warp
+    const unsigned long long w_rows = min((unsigned long long)n_it * RW, p.row_end - min(w_row0, p.row_end));
+    long long loads_left = (long long)n_it * (p.step_end - p.step_begin);
 
     const int cpr = D / p.vec;  // cp.async chunks per row
-    const int dcol = 32 % cpr, drow = 32 / cpr;
-
-    auto issue = [&](long long gi) {  // unit (gi % n_it) of this warp into stage (gi % S)
-        if (gi < total_it) {
-            const int it = (int)(gi % n_it);
-            const unsigned long long r0 = p.row_begin + (u_begin + it) * (unsigned long long)RW;
-            const int rows = (int)min((unsigned long long)RW, p.row_end - r0);
-            T* dst = ring + (size_t)(gi % S) * unit_elems;
-            const T* src = p.F + r0 * (unsigned long long)D;
-            int row = lane / cpr, col = lane % cpr;
-            while (row < rows) {
-                cp_elems(dst + (size_t)row * stride + col * p.vec, src + (size_t)row * D + col * p.vec, p.vec);
-                col += dcol;
-                row += drow;
-                if (col >= cpr) {
-                    col -= cpr;
-                    ++row;
-                }
+    // ring feeder state (no divisions in the loop): next unit to load and the stage it goes to
+    int ld_it = 0, ld_stage = 0;
+    auto issue = [&]() {
+        if (loads_left > 0) {
+            --loads_left;
+            const unsigned r_in = (unsigned)ld_it * (unsigned)RW;
+            const int rows = (int)min((unsigned long long)RW, w_rows - r_in);
+            T* dst = ring + (unsigned)ld_stage * unit_elems;
+            const T* src = p.F + (w_row0 + r_in) * (unsigned long long)D;
+            if (cpr <= 32 && (32 % cpr) == 0) {  // a warp pass covers 32/cpr whole rows
+                const int rpp = 32 / cpr, col = (lane % cpr) * p.vec;
+                for (int row = lane / cpr; row < rows; row += rpp)
+                    cp_elems(dst + (unsigned)row * stride + col, src + (unsigned)row * D + col, p.vec);
+            } else {
+                for (int row = 0; row < rows; ++row)
+                    for (int c = lane; c < cpr; c += 32)
+                        cp_elems(dst + (unsigned)row * stride + c * p.vec, src + (unsigned)row * D + c * p.vec, p.vec);
             }
+            if (++ld_it == n_it) ld_it = 0;
+            if (++ld_stage == S) ld_stage = 0;
         }
         cp_async_commit();
     };
 
-    for (int q = 0; q < S - 1; ++q) issue(q);  // the ring never drains between picks
+    for (int q = 0; q < S - 1; ++q) issue();  // the ring never drains between picks
+    int cur_stage = 0;
 
-    long long gi = 0;
+    Mailbox* boxes = reinterpret_cast<Mailbox*>(p.cand);
     for (int step = p.step_begin; step < p.step_end; ++step) {
         __syncthreads();  // warp 0 has published s_next_center; the generic centre row is no longer read
         unsigned long long c_row;
@@ -340,13 +367,15 @@ __global__ void __launch_bounds__(THREADS, 1) select_kernel(const Params<T> p) {
         Cand best;
         best.hi = 0;
         best.lo = 0;
-        for (int it = 0; it < n_it; ++it, ++gi) {
-            issue(gi + S - 1);
+        unsigned r_in = 0;
+        for (int it = 0; it < n_it; ++it, r_in += RW) {
+            issue();
             cp_async_wait_dyn(S - 1);
             __syncwarp();
-            const unsigned long long r0 = p.row_begin + (u_begin + it) * (unsigned long long)RW;
-            const int rows = (int)min((unsigned long long)RW, p.row_end - r0);
-            const T* tile = ring + (size_t)(gi % S) * unit_elems;
+            const int rows = (int)min((unsigned long long)RW, w_rows - r_in);
+            const unsigned long long r0 = w_row0 + r_in;
+            const T* tile = ring + (unsigned)cur_stage * unit_elems;
+            if (++cur_stage == S) cur_stage = 0;
             // running min-distance (and row norm) of "my" row: issued now, consumed after the distance loop
             T m_old = (T)0;
             double xx_r = 0.0;
@@ -355,9 +384,10 @@ __global__ void __launch_bounds__(THREADS, 1) select_kernel(const Params<T> p) {
                 if (MODE == MODE_KCENTER) xx_r = __ldg(p.xx + r0 + lane);
             }
             RowVal mine = (RowVal)0;
-#pragma unroll 4
-            for (int i = 0; i < GPU_; ++i) {
-                const T* a = tile + (size_t)(4 * i + g) * stride;
+#pragma unroll
+            for (int i = 0; i < (GT > 0 ? GT : 8); ++i) {
+                if (GT == 0 && i >= NG) break;
+                const T* a = tile + (unsigned)(4 * i + g) * (unsigned)stride;
                 RowVal d;
                 if (MODE == MODE_FPS) {
                     if (DT > 0) d = (RowVal)pw_fixed<T, (DT > 0 ? DT : 8), 0>(a, creg, j);
@@ -385,39 +415,37 @@ __global__ void __launch_bounds__(THREADS, 1) select_kernel(const Params<T> p) {
                 }
                 const T m = d < m_old ? d : m_old;
                 if (d < m_old) __stcg(p.mind + gr, m);
-                best = cand_max(best, make_cand<T>(m, gr));
+                best = cand_max<T>(best, make_cand<T>(m, gr));
             }
             __syncwarp();  // every lane is done with this stage before a later issue() overwrites it
         }
 
-        // ---- CTA candidate
-        best = warp_max(best);
+        // ---- CTA candidate -> mailbox; every CTA polls all mailboxes and reduces them redundantly
+        best = warp_max<T>(best);
         if (lane == 0) s_red[warp] = best;
         __syncthreads();
         if (warp == 0) {
             Cand c = lane < NWARP ? s_red[lane] : Cand{0, 0};
-            c = warp_max(c);
+            c = warp_max<T>(c);
+            const unsigned long long tag = (unsigned long long)(step + 1);
+            Mailbox* mine_box = boxes + (size_t)(step & 1) * G + blockIdx.x;
             if (lane == 0) {
-                unsigned long long* box = p.cand + ((size_t)(step & 1) * G + blockIdx.x) * 2;
-                box[0] = c.hi;
-                box[1] = c.lo;
+                mine_box->hi = c.hi;
+                mine_box->lo = c.lo;
                 __threadfence();
-                red_release_add_u32(p.barrier, 1u);
-                const unsigned target = (unsigned)(step - p.step_begin + 1) * (unsigned)G;
-                while (ld_acquire_u32(p.barrier) < target) {
-                }
+                st_release_u64(&mine_box->tag, tag);
             }
-            __syncwarp();
-            // ---- every CTA reduces all candidates redundantly
             Cand w{0, 0};
             for (int b = lane; b < G; b += 32) {
-                const unsigned long long* box = p.cand + ((size_t)(step & 1) * G + b) * 2;
+                const Mailbox* mb = boxes + (size_t)(step & 1) * G + b;
+                while (ld_acquire_u64(&mb->tag) != tag) {
+                }
                 Cand o;
-                o.hi = __ldcg(box);
-                o.lo = __ldcg(box + 1);
-                w = cand_max(w, o);
+                o.hi = __ldcg(&mb->hi);
+                o.lo = __ldcg(&mb->lo);
+                w = cand_max<T>(w, o);
             }
-            w = warp_max(w);
+            w = warp_max<T>(w);
             if (lane == 0) {
                 s_next_center = cand_row<T>(w);
                 if (blockIdx.x == 0) {
@@ -500,18 +528,18 @@ struct Launch {
 
 typedef cudaError_t (*AttrFn)(int);
 
-template <typename T, int MODE, int DT>
-static int setup_variant(size_t smem, void** fn_out) {
-    auto kern = select_kernel<T, MODE, DT>;
+template <typename T, int MODE, int DT, int GT>
+static int setup_variant(size_t smem, int threads, void** fn_out) {
+    auto kern = select_kernel<T, MODE, DT, GT>;
     SSDR_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int nb = 0;
-    SSDR_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, THREADS, smem));
-    SSDR_REQUIRE(nb >= 1, SSDR_ERR_CUDA, "selection kernel does not fit on an SM (smem %zu)", smem);
+    SSDR_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, threads, smem));
+    SSDR_REQUIRE(nb >= 1, SSDR_ERR_CUDA, "selection kernel does not fit on an SM (smem %zu, %d threads)", smem, threads);
     *fn_out = (void*)kern;
     return SSDR_OK;
 }
 
-// Fill geometry (stride, unit rows, stages, grid) for a (T, D) problem and pick the kernel variant.
+// Fill geometry (stride, unit rows, stages, warps, grid) for a (T, D) problem and pick the kernel variant.
 template <typename T, int MODE>
 static int configure(Ctx* c, Launch<T>& L, const T* dF, size_t N, size_t D) {
     Params<T>& p = L.p;
@@ -532,14 +560,18 @@ static int configure(Ctx* c, Launch<T>& L, const T* dF, size_t N, size_t D) {
     const size_t row_bytes = (size_t)stride * sizeof(T);
     const size_t budget = (size_t)c->max_smem_optin - 2048;
     const size_t fixed = align_up_dev((D + 8) * sizeof(T), 16) + align_up_dev(WARPS * sizeof(Cand), 16) + 64;
-    // unit = 4*groups rows per warp iteration, ~6 KB per stage, 4 stages if they fit
-    int groups = (int)(6144 / (4 * row_bytes));
-    groups = groups < 1 ? 1 : (groups > 8 ? 8 : groups);
-    int nst = 4, nw = WARPS;
     auto need = [&](int gr, int st, int w) { return fixed + (size_t)w * st * 4 * gr * row_bytes; };
-    while (nst > 2 && need(groups, nst, nw) > budget) --nst;
-    while (groups > 1 && need(groups, nst, nw) > budget) --groups;
+    // fixed variants: (D, groups per unit) compiled in; units of 2-4 KB, 3 stages, 16 warps
+    const bool fixed_ok = vec == vec_full && (D == 32 || D == 64 || D == 128 || D == 256);
+    int groups, nst = 3, nw = WARPS;
+    if (fixed_ok) groups = D == 32 ? 4 : (D == 64 ? 2 : 1);
+    else {
+        groups = (int)(3072 / (4 * row_bytes));
+        groups = groups < 1 ? 1 : (groups > 8 ? 8 : groups);
+    }
     while (nw > 1 && need(groups, nst, nw) > budget) nw /= 2;
+    while (nst > 2 && need(groups, nst, nw) > budget) --nst;
+    while (!fixed_ok && groups > 1 && need(groups, nst, nw) > budget) --groups;
     SSDR_REQUIRE(need(groups, nst, nw) <= budget, SSDR_ERR_UNSUPPORTED,
                  "feature dimension D=%zu needs %zu bytes of shared memory per CTA (limit %zu)", D,
                  need(groups, nst, nw), budget);
@@ -549,12 +581,12 @@ static int configure(Ctx* c, Launch<T>& L, const T* dF, size_t N, size_t D) {
     L.smem = need(groups, nst, nw);
     p.plan.n_leaves = 0;
     if (D >= 8) plan_emit(p.plan, 0, (int)D);
-    const bool fixed_ok = vec == vec_full;  // the unrolled variants assume 16-byte rows
-    if (fixed_ok && D == 32) SSDR_TRY((setup_variant<T, MODE, 32>(L.smem, &L.fn)));
-    else if (fixed_ok && D == 64) SSDR_TRY((setup_variant<T, MODE, 64>(L.smem, &L.fn)));
-    else if (fixed_ok && D == 128) SSDR_TRY((setup_variant<T, MODE, 128>(L.smem, &L.fn)));
-    else if (fixed_ok && D == 256) SSDR_TRY((setup_variant<T, MODE, 256>(L.smem, &L.fn)));
-    else SSDR_TRY((setup_variant<T, MODE, 0>(L.smem, &L.fn)));
+    const int threads = nw * 32;
+    if (fixed_ok && D == 32) SSDR_TRY((setup_variant<T, MODE, 32, 4>(L.smem, threads, &L.fn)));
+    else if (fixed_ok && D == 64) SSDR_TRY((setup_variant<T, MODE, 64, 2>(L.smem, threads, &L.fn)));
+    else if (fixed_ok && D == 128) SSDR_TRY((setup_variant<T, MODE, 128, 1>(L.smem, threads, &L.fn)));
+    else if (fixed_ok && D == 256) SSDR_TRY((setup_variant<T, MODE, 256, 1>(L.smem, threads, &L.fn)));
+    else SSDR_TRY((setup_variant<T, MODE, 0, 0>(L.smem, threads, &L.fn)));
     L.grid = c->sm_count;
     return SSDR_OK;
 }
@@ -563,7 +595,8 @@ template <typename T, int MODE>
 static int launch_steps(Launch<T>& L, int step_begin, int step_end, cudaStream_t s) {
     L.p.step_begin = step_begin;
     L.p.step_end = step_end;
-    SSDR_CHECK_CUDA(cudaMemsetAsync(L.p.barrier, 0, sizeof(unsigned), s));
+    // mailbox tags are step+1 and unique per launch range, but a previous call may have left equal tags behind
+    SSDR_CHECK_CUDA(cudaMemsetAsync(L.p.cand, 0, (size_t)2 * L.grid * sizeof(Mailbox), s));
     void* args[] = {(void*)&L.p};
     SSDR_CHECK_CUDA(cudaLaunchCooperativeKernel(L.fn, dim3(L.grid), dim3(L.p.nwarps * 32), args, L.smem, s));
     return SSDR_OK;
@@ -581,7 +614,7 @@ static int prepare(Ctx* c, Launch<T>& L, const T* dF, size_t N, size_t D, size_t
     p.row_end = row_end;
     SSDR_TRY(c->ws[WS_MIND].reserve(N * sizeof(T)));
     SSDR_TRY(c->ws[WS_WIN].reserve((size_t)(n_steps > 0 ? n_steps : 1) * 16));
-    SSDR_TRY(c->ws[WS_CAND].reserve((size_t)2 * L.grid * 16));
+    SSDR_TRY(c->ws[WS_CAND].reserve((size_t)2 * L.grid * sizeof(Mailbox)));
     SSDR_TRY(c->ws[WS_BAR].reserve(256));
     SSDR_TRY(c->ws[WS_PICKS].reserve((size_t)(n_steps > 0 ? n_steps : 1) * sizeof(long long)));
     p.mind = c->ws[WS_MIND].as<T>();

@@ -32,7 +32,7 @@ def _device_tree(pts):
     from ssdr_al_b200 import _lib
     pts = np.ascontiguousarray(pts, np.float32)
     n = len(pts)
-    cap = 2 * n + 2
+    cap = 3 * n + 64
     vind = np.zeros(n, np.uint32)
     nn = np.zeros(1, np.uint32)
     a = dict(left=np.zeros(cap, np.uint32), right=np.zeros(cap, np.uint32), child1=np.zeros(cap, np.int32),
