@@ -15,6 +15,8 @@
 //      sums).  Such rows are flagged by B and re-resolved by an exact replay of the nanoflann tree (kdtree.cuh).
 #include <cub/device/device_scan.cuh>
 
+#include <vector>
+
 #include "common.cuh"
 #include "kdtree.cuh"
 
@@ -462,16 +464,40 @@ int ssdr_knn_debug_tree(const float* points, size_t npts, uint32_t* vind_out, ui
     kdtree::NodeRec* h = (kdtree::NodeRec*)malloc(nn * sizeof(kdtree::NodeRec));
     SSDR_REQUIRE(h, SSDR_ERR_NOMEM, "host allocation failed");
     int rc = d2h_sync(c, h, t.nodes, nn * sizeof(kdtree::NodeRec), s);
-    for (size_t n = 0; rc == SSDR_OK && n < nn; ++n) {
-        if (left) left[n] = h[n].l;
-        if (right) right[n] = h[n].r;
-        if (child1) child1[n] = h[n].c1;
-        if (child2) child2[n] = h[n].c2;
-        if (divfeat) divfeat[n] = h[n].feat;
-        if (divlow) divlow[n] = h[n].divlow;
-        if (divhigh) divhigh[n] = h[n].divhigh;
+    // node ids are handed out in blocks (gaps are never written): export the reachable nodes in pre-order
+    size_t n_out = 0;
+    if (rc == SSDR_OK) {
+        std::vector<unsigned> stack, order;
+        std::vector<int> remap(nn, -1);
+        stack.push_back(0);
+        while (!stack.empty()) {
+            const unsigned n = stack.back();
+            stack.pop_back();
+            remap[n] = (int)order.size();
+            order.push_back(n);
+            if (h[n].c1 >= 0) {
+                if ((size_t)h[n].c1 >= nn || (size_t)h[n].c2 >= nn) {
+                    rc = set_error(SSDR_ERR_CUDA, "corrupt tree: child id out of range");
+                    break;
+                }
+                stack.push_back((unsigned)h[n].c2);
+                stack.push_back((unsigned)h[n].c1);
+            }
+        }
+        n_out = order.size();
+        for (size_t k = 0; rc == SSDR_OK && k < n_out; ++k) {
+            const kdtree::NodeRec& r = h[order[k]];
+            if (left) left[k] = r.l;
+            if (right) right[k] = r.r;
+            if (child1) child1[k] = r.c1 >= 0 ? remap[r.c1] : -1;
+            if (child2) child2[k] = r.c2 >= 0 ? remap[r.c2] : -1;
+            if (divfeat) divfeat[k] = r.feat;
+            if (divlow) divlow[k] = r.divlow;
+            if (divhigh) divhigh[k] = r.divhigh;
+        }
     }
     free(h);
+    *n_nodes_out = (uint32_t)n_out;
     return rc;
 }
 int ssdr_knn_batch_dev_i32(const float* d_points, size_t batch_size, size_t npts, const float* d_queries,
