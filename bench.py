@@ -300,7 +300,8 @@ def run_ours(args):
         "clocks": clocks,
         "knn_detail": {"tie_rows_per_step": int(tie_rows), "stage_ms": [
             {"call": kind, "level_points": LEVELS[li], "grid_build_ms": st["grid_build_ms"],
-             "main_kernel_ms": st["main_kernel_ms"], "tie_path_ms": st["tie_path_ms"], "tie_rows": st["tie_rows"]}
+             "main_kernel_ms": st["main_kernel_ms"], "tie_path_ms": st["tie_path_ms"], "tree_build_ms": st["tree_build_ms"],
+             "tie_rows": st["tie_rows"]}
             for kind, li, st in stats]},
         "extra": extra,
     }

@@ -20,7 +20,7 @@ vp = C.c_void_p
 class KnnStats(C.Structure):
     _fields_ = [("queries", C.c_uint64), ("tie_rows", C.c_uint64), ("tree_builds", C.c_uint64),
                 ("dist_evals", C.c_uint64), ("grid_build_ms", C.c_double), ("main_kernel_ms", C.c_double),
-                ("tie_path_ms", C.c_double)]
+                ("tie_path_ms", C.c_double), ("tree_build_ms", C.c_double)]
 
 
 # name -> argtypes (every function returns int status unless listed in _RESTYPE)
@@ -99,16 +99,48 @@ def set_device(i):
     check(lib().ssdr_set_device(int(i)))
 
 
+class _PinnedBlock(object):
+    """A CUDA pinned host allocation that returns itself to the pool when the last numpy view dies."""
+    __slots__ = ("ptr", "nbytes", "__array_interface__", "__weakref__")
+
+    def __init__(self, ptr, nbytes):
+        self.ptr = ptr
+        self.nbytes = nbytes
+        self.__array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 3}
+
+    def __del__(self):
+        try:
+            _POOL.setdefault(self.nbytes, []).append(self.ptr)
+        except Exception:  # interpreter shutdown
+            pass
+
+
+_POOL = {}          # size class -> free pinned pointers
+_POOL_LIMIT = 1 << 30
+
+
 def pinned_empty(shape, dtype):
-    """numpy array backed by CUDA pinned host memory (freed when the array is garbage collected)."""
+    """Fresh numpy array in CUDA pinned host memory (device<->host copies run at full PCIe speed, no page faults).
+    The memory goes back to a pool when the array is garbage collected, so every call still returns an independent
+    array like np.empty does."""
     dtype = np.dtype(dtype)
-    n = int(np.prod(shape)) * dtype.itemsize
-    p = vp()
-    check(lib().ssdr_host_alloc(C.byref(p), n))
-    buf = (C.c_char * max(n, 1)).from_address(p.value)
-    arr = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
-    _PINNED[id(buf)] = (buf, p)
-    return arr
+    count = int(np.prod(shape))
+    nbytes = count * dtype.itemsize
+    if nbytes == 0:
+        return np.empty(shape, dtype)
+    cls = 1 << max(12, (nbytes - 1).bit_length())  # power-of-two size classes
+    free = _POOL.get(cls)
+    if free:
+        ptr = free.pop()
+    else:
+        p = vp()
+        check(lib().ssdr_host_alloc(C.byref(p), cls))
+        ptr = p.value
+    block = _PinnedBlock(ptr, cls)
+    return np.asarray(block)[:nbytes].view(dtype).reshape(shape)
 
 
-_PINNED = {}
+def pinned_zeros(shape, dtype):
+    a = pinned_empty(shape, dtype)
+    a[...] = 0
+    return a

@@ -58,7 +58,7 @@ struct Ctx {
     int max_smem_optin = 0;
     cudaStream_t stream = nullptr;  // the library's own stream for host entry points
     cudaEvent_t ev = nullptr;
-    cudaEvent_t tev[4] = {nullptr, nullptr, nullptr, nullptr};  // timing events (stats paths)
+    cudaEvent_t tev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};  // timing events (stats paths)
     DevBuf ws[WS_SLOTS];            // workspaces, addressed by the owning module
     PinBuf pin[4];                  // pinned staging
 };

@@ -849,11 +849,15 @@ __device__ __forceinline__ NodeRec load_node(const NodeRec* p) {
 }
 
 // ---- exact replay of nanoflann's search for the flagged rows -------------------------------------------------
+// per_warp != 0: one query per 32-thread CTA, walked by lane 0 alone -- a pointer-chasing DFS gains nothing from SIMT
+// and loses to divergence, so with few flagged rows every query gets its own warp scheduler slot; per_warp == 0
+// (duplicate-heavy clouds, most rows flagged): one query per thread.
 template <typename OutT>
 __global__ void __launch_bounds__(32) exact_query_kernel(const float* __restrict__ q_all, const Tree t, unsigned Q,
                                                          int K, const unsigned* __restrict__ flag_list,
-                                                         unsigned n_flag, OutT* __restrict__ out) {
-    const unsigned f = blockIdx.x * blockDim.x + threadIdx.x;
+                                                         unsigned n_flag, OutT* __restrict__ out, int per_warp) {
+    if (per_warp && threadIdx.x != 0) return;
+    const unsigned f = per_warp ? blockIdx.x : blockIdx.x * blockDim.x + threadIdx.x;
     if (f >= n_flag) return;
     const unsigned row = flag_list[f];
     const unsigned b = row / Q;
@@ -1031,7 +1035,7 @@ static int check_tree_error(Ctx* c, cudaStream_t s, const Tree& t) {
 template <typename OutT>
 static int resolve_flagged(Ctx* c, cudaStream_t s, const float* d_pts, size_t B, size_t N, const float* d_q, size_t Q,
                            size_t K, OutT* d_out, const unsigned* flag_list, unsigned n_flag,
-                           unsigned long long* builds) {
+                           unsigned long long* builds, cudaEvent_t ev_mid = nullptr) {
     SSDR_REQUIRE(K <= (size_t)MAX_K, SSDR_ERR_UNSUPPORTED, "K=%zu > %d in the exact tie path", K, MAX_K);
     Tree t;
     SSDR_TRY(alloc_tree(c, s, B, N, &t));
@@ -1039,7 +1043,10 @@ static int resolve_flagged(Ctx* c, cudaStream_t s, const float* d_pts, size_t B,
     t.item_needed = needed;
     mark_items_kernel<<<(n_flag + 255) / 256, 256, 0, s>>>(flag_list, n_flag, (unsigned)Q, needed);
     SSDR_TRY(launch_build(c, s, d_pts, t));
-    exact_query_kernel<OutT><<<(n_flag + 31) / 32, 32, 0, s>>>(d_q, t, (unsigned)Q, (int)K, flag_list, n_flag, d_out);
+    if (ev_mid) SSDR_CHECK_CUDA(cudaEventRecord(ev_mid, s));
+    const int per_warp = n_flag <= 8192u;
+    exact_query_kernel<OutT><<<per_warp ? n_flag : (n_flag + 31) / 32, 32, 0, s>>>(d_q, t, (unsigned)Q, (int)K,
+                                                                                  flag_list, n_flag, d_out, per_warp);
     SSDR_CHECK_CUDA(cudaGetLastError());
     SSDR_TRY(check_tree_error(c, s, t));
     if (builds) *builds = B;  // upper bound; items without flagged rows are skipped inside the kernel

@@ -365,7 +365,8 @@ static int run_dev(Ctx* c, cudaStream_t s, const float* d_pts, size_t B, size_t 
     SSDR_TRY(d2h_sync(c, &hs, dstats, sizeof(DevStats), s));
     unsigned long long builds = 0;
     if (hs.flag_count > 0) {
-        SSDR_TRY((kdtree::resolve_flagged<OutT>(c, s, d_pts, B, N, d_q, Q, K, d_out, flag_list, hs.flag_count, &builds)));
+        SSDR_TRY((kdtree::resolve_flagged<OutT>(c, s, d_pts, B, N, d_q, Q, K, d_out, flag_list, hs.flag_count, &builds,
+                                                stats ? c->tev[4] : nullptr)));
     }
     if (stats) {
         SSDR_CHECK_CUDA(cudaEventRecord(c->tev[3], s));
@@ -377,6 +378,11 @@ static int run_dev(Ctx* c, cudaStream_t s, const float* d_pts, size_t B, size_t 
         stats->main_kernel_ms = ms;
         SSDR_CHECK_CUDA(cudaEventElapsedTime(&ms, c->tev[2], c->tev[3]));
         stats->tie_path_ms = hs.flag_count ? ms : 0.0;
+        stats->tree_build_ms = 0.0;
+        if (hs.flag_count) {
+            SSDR_CHECK_CUDA(cudaEventElapsedTime(&ms, c->tev[2], c->tev[4]));
+            stats->tree_build_ms = ms;  // includes the flag-count read-back that precedes the build
+        }
         stats->queries = totalQ;
         stats->tie_rows = hs.flag_count;
         stats->tree_builds = builds;

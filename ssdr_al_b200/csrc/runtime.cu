@@ -90,7 +90,7 @@ int get_ctx(Ctx** out) {
                              prop.major, prop.minor);
         SSDR_CHECK_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
         SSDR_CHECK_CUDA(cudaEventCreateWithFlags(&c->ev, cudaEventDisableTiming));
-        for (int i = 0; i < 4; ++i) SSDR_CHECK_CUDA(cudaEventCreate(&c->tev[i]));
+        for (int i = 0; i < 5; ++i) SSDR_CHECK_CUDA(cudaEventCreate(&c->tev[i]));
         cudaMemPool_t pool;  // keep freed stream-ordered blocks cached instead of returning them to the driver
         if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
             unsigned long long keep = ~0ull;

@@ -323,7 +323,19 @@ __global__ void __launch_bounds__(THREADS, 1) select_kernel(const Params<T> p) {
             const int rows = (int)min((unsigned long long)RW, w_rows - r_in);
             T* dst = ring + (unsigned)ld_stage * unit_elems;
             const T* src = p.F + (w_row0 + r_in) * (unsigned long long)D;
-            if (cpr <= 32 && (32 % cpr) == 0) {  // a warp pass covers 32/cpr whole rows
+            if constexpr (DT > 0 && GT > 0) {
+                // compile-time geometry: 16-byte chunks, chunk q of the unit = lane + 32k; the source is contiguous
+                constexpr int VEC = 16 / (int)sizeof(T);
+                constexpr int CPR = DT / VEC;                // chunks per row (power of two)
+                constexpr int CH = 4 * GT * CPR / 32;        // chunks per lane per unit
+                const int nchunks = rows * CPR;
+#pragma unroll
+                for (int k = 0; k < CH; ++k) {
+                    const int q = lane + 32 * k;
+                    const int row = q / CPR, col = (q % CPR) * VEC;
+                    if (q < nchunks) cp_async_16(dst + (unsigned)row * (unsigned)stride + col, src + (unsigned)q * VEC);
+                }
+            } else if (cpr <= 32 && (32 % cpr) == 0) {  // a warp pass covers 32/cpr whole rows
                 const int rpp = 32 / cpr, col = (lane % cpr) * p.vec;
                 for (int row = lane / cpr; row < rows; row += rpp)
                     cp_elems(dst + (unsigned)row * stride + col, src + (unsigned)row * D + col, p.vec);

@@ -12,7 +12,8 @@ def _check_dim(dim):
 
 def knn(pts, queries, K, omp=False):
     """knn.pyx:33-69.  `omp` only selected threading in the reference; results are identical, so it is ignored."""
-    indices = np.zeros((queries.shape[0], K), dtype=np.int64)
+    # knn.pyx:53 allocates np.zeros; every slot is overwritten unless K > npts, so pinned memory is only zeroed then
+    indices = (_lib.pinned_zeros if K > pts.shape[0] else _lib.pinned_empty)((queries.shape[0], K), np.int64)
     pts_c = np.ascontiguousarray(pts, dtype=np.float32)
     queries_c = np.ascontiguousarray(queries, dtype=np.float32)
     _check_dim(pts_c.shape[1])
@@ -23,7 +24,8 @@ def knn(pts, queries, K, omp=False):
 
 def knn_batch(pts, queries, K, omp=False):
     """knn.pyx:71-109."""
-    indices = np.zeros((pts.shape[0], queries.shape[1], K), dtype=np.int64)
+    indices = (_lib.pinned_zeros if K > pts.shape[1] else _lib.pinned_empty)((pts.shape[0], queries.shape[1], K),
+                                                                             np.int64)
     pts_c = np.ascontiguousarray(pts, dtype=np.float32)
     queries_c = np.ascontiguousarray(queries, dtype=np.float32)
     _check_dim(pts_c.shape[2])
