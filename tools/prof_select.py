@@ -8,19 +8,20 @@ from ssdr_al_b200 import device as D
 dev = torch.device("cuda", 0)
 which = sys.argv[1] if len(sys.argv) > 1 else "fps32"
 picks = int(sys.argv[2]) if len(sys.argv) > 2 else 200
+nrows = int(sys.argv[3]) if len(sys.argv) > 3 else 500_000
 g = torch.Generator(device=dev); g.manual_seed(3)
 if which.startswith("fps") or which.startswith("kc"):
     d = int(which[3:]) if which.startswith("fps") else int(which[2:])
-    F = torch.randn((500_000, d), generator=g, device=dev, dtype=torch.float32)
+    F = torch.randn((nrows, d), generator=g, device=dev, dtype=torch.float32)
     for rep in range(2):
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
         if which.startswith("fps"):
             out = D.fps(F, picks, 12345)
         else:
-            out = D.kcenter(F, torch.arange(499_984, 500_000, device=dev), picks)
+            out = D.kcenter(F, torch.arange(nrows - 16, nrows, device=dev), picks)
         b.record(); torch.cuda.synchronize()
-        print(which, "picks", picks, "ms", a.elapsed_time(b), "ms/pick", a.elapsed_time(b) / picks, flush=True)
+        print(which, "rows", nrows, "picks", picks, "ms", a.elapsed_time(b), "us/pick", 1e3 * a.elapsed_time(b) / picks, flush=True)
 elif which == "grid":
     rng = np.random.default_rng(0)
     n = 1_000_000
