@@ -151,28 +151,44 @@ __global__ void cell_scatter_kernel(const float* __restrict__ xyz, unsigned n_pe
 }
 
 // ---- B: main query kernel -------------------------------------------------------------------------------------
-__device__ __forceinline__ unsigned long long u64min(unsigned long long a, unsigned long long b) { return a < b ? a : b; }
-__device__ __forceinline__ unsigned long long u64max(unsigned long long a, unsigned long long b) { return a > b ? a : b; }
-__device__ __forceinline__ float key_dist(unsigned long long k) { return __uint_as_float((unsigned)(k >> 32)); }
-
+// Top list: distances and indices in separate register arrays, ordered by DISTANCE ONLY (equal distances keep
+// arrival order).  That is enough: a row whose top-(K+1) holds two equal distances is flagged and re-resolved by the
+// exact nanoflann replay anyway, and without such a tie the order by distance is the order by (distance, index).
+// The branch-free insertion costs 2 FMNMX + 1 FSETP + 2 SEL per slot.
 template <int KCAP>
-__device__ __forceinline__ void list_insert(unsigned long long (&list)[KCAP], unsigned long long key) {
+__device__ __forceinline__ void list_insert(float (&dist)[KCAP], unsigned (&idx)[KCAP], float d, unsigned id) {
+    bool p_prev = true;  // d < dist[j] for the slot above (the caller checked d < dist[KCAP-1])
 #pragma unroll
-    for (int j = KCAP - 1; j > 0; --j) list[j] = u64max(list[j - 1], u64min(list[j], key));
-    list[0] = u64min(list[0], key);
+    for (int j = KCAP - 1; j > 0; --j) {
+        const bool p = d < dist[j - 1];
+        const float nd = fmaxf(dist[j - 1], fminf(dist[j], d));
+        idx[j] = p ? idx[j - 1] : (p_prev ? id : idx[j]);
+        dist[j] = nd;
+        p_prev = p;
+    }
+    dist[0] = fminf(dist[0], d);
+    idx[0] = p_prev ? id : idx[0];
 }
 
 template <int KCAP>
-__device__ __forceinline__ unsigned scan_range(unsigned long long (&list)[KCAP], const float4* __restrict__ spts,
-                                               unsigned s, unsigned e, float qx, float qy, float qz) {
+__device__ __forceinline__ unsigned scan_range(float (&dist)[KCAP], unsigned (&idx)[KCAP],
+                                               const float4* __restrict__ spts, unsigned s, unsigned e, float qx,
+                                               float qy, float qz) {
     for (unsigned i = s; i < e; ++i) {
         const float4 p = __ldg(spts + i);
         const float dx = __fsub_rn(qx, p.x), dy = __fsub_rn(qy, p.y), dz = __fsub_rn(qz, p.z);
         const float d = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
-        const unsigned long long key = ((unsigned long long)__float_as_uint(d) << 32) | (unsigned)__float_as_int(p.w);
-        if (key < list[KCAP - 1]) list_insert<KCAP>(list, key);
+        if (d < dist[KCAP - 1]) list_insert<KCAP>(dist, idx, d, (unsigned)__float_as_int(p.w));
     }
     return e - s;
+}
+
+// conservative squared distance from coordinate v to the slab of cell c along one axis (0 inside, minus the slack
+// that covers fp32 rounding in the cell assignment)
+__device__ __forceinline__ float slab_gap(float v, float lo, float h, int c, float eps) {
+    const float a = lo + (float)c * h, b = lo + (float)(c + 1) * h;
+    float g = fmaxf(fmaxf(a - v, v - b), 0.f) - eps;
+    return g > 0.f ? g : 0.f;
 }
 
 template <int KCAP, typename OutT>
@@ -194,27 +210,54 @@ __global__ void __launch_bounds__(128) query_kernel(const float4* __restrict__ s
         const int cy = cell_coord(q.y, m.lo[1], m.inv_h, gy);
         const int cz = cell_coord(q.z, m.lo[2], m.inv_h, gz);
         const unsigned* cs = cell_start + m.cell_base;
-        unsigned long long list[KCAP];
+        float dist[KCAP];
+        unsigned idx[KCAP];
 #pragma unroll
-        for (int j = 0; j < KCAP; ++j) list[j] = ~0ull;
+        for (int j = 0; j < KCAP; ++j) {
+            dist[j] = INFINITY;
+            idx[j] = 0xFFFFFFFFu;
+        }
+        // one row of cells (fixed y, z; x in [xa, xb]) is contiguous in the cell-sorted array; skip it when even its
+        // nearest possible point cannot enter the list
+        auto scan_row = [&](int z, int y, int xa, int xb) {
+            if (z < 0 || z >= gz || y < 0 || y >= gy) return;
+            xa = max(xa, 0);
+            xb = min(xb, gx - 1);
+            if (xa > xb) return;
+            const float gy_ = slab_gap(q.y, m.lo[1], m.h, y, m.eps_abs), gz_ = slab_gap(q.z, m.lo[2], m.h, z, m.eps_abs);
+            float gx_ = 0.f;
+            if (cx < xa) gx_ = slab_gap(q.x, m.lo[0], m.h, xa, m.eps_abs);
+            else if (cx > xb) gx_ = slab_gap(q.x, m.lo[0], m.h, xb, m.eps_abs);
+            const float lower = (gx_ * gx_ + gy_ * gy_ + gz_ * gz_) * 0.99999f;
+            if (!(lower < dist[KCAP - 1])) return;
+            const unsigned row = (unsigned)((z * gy + y) * gx);
+            my_evals += scan_range<KCAP>(dist, idx, spts, cs[row + xa], cs[row + xb + 1], q.x, q.y, q.z);
+        };
 
         for (int r = 1;; ++r) {
+            // rows of the shell at Chebyshev radius r (for r == 1: the whole 3x3 block, nearest rows first: own row,
+            // the 4 face rows, the 4 diagonal rows).  One call site keeps a single copy of the insertion network.
+            const int w = 2 * r + 1, nrow = w * w;
+            for (int k = 0; k < nrow; ++k) {
+                int dz, dy;
+                if (r == 1) {
+                    dz = (int)((0x2402049u >> (3 * k)) & 7u) - 1;  // packed (offset + 1), 3 bits per entry, order:
+                    dy = (int)((0x2081281u >> (3 * k)) & 7u) - 1;  // (0,0)(0,-1)(0,1)(-1,0)(1,0)(-1,-1)(-1,1)(1,-1)(1,1)
+                } else {
+                    dz = k / w - r;
+                    dy = k % w - r;
+                }
+                const bool whole = (r == 1) || dz == -r || dz == r || dy == -r || dy == r;
+                const int nseg = whole ? 1 : 2;
+                for (int sg = 0; sg < nseg; ++sg) {
+                    const int xa = whole ? cx - r : (sg == 0 ? cx - r : cx + r);
+                    const int xb = whole ? cx + r : xa;
+                    scan_row(cz + dz, cy + dy, xa, xb);
+                }
+            }
             const int x0 = max(cx - r, 0), x1 = min(cx + r, gx - 1);
             const int y0 = max(cy - r, 0), y1 = min(cy + r, gy - 1);
             const int z0 = max(cz - r, 0), z1 = min(cz + r, gz - 1);
-            for (int z = z0; z <= z1; ++z)
-                for (int y = y0; y <= y1; ++y) {
-                    const unsigned row = (unsigned)((z * gy + y) * gx);
-                    const bool whole = (r == 1) || z == cz - r || z == cz + r || y == cy - r || y == cy + r;
-                    if (whole) {
-                        my_evals += scan_range<KCAP>(list, spts, cs[row + x0], cs[row + x1 + 1], q.x, q.y, q.z);
-                    } else {
-                        if (cx - r >= 0)
-                            my_evals += scan_range<KCAP>(list, spts, cs[row + cx - r], cs[row + cx - r + 1], q.x, q.y, q.z);
-                        if (cx + r < gx)
-                            my_evals += scan_range<KCAP>(list, spts, cs[row + cx + r], cs[row + cx + r + 1], q.x, q.y, q.z);
-                    }
-                }
             if (x0 == 0 && x1 == gx - 1 && y0 == 0 && y1 == gy - 1 && z0 == 0 && z1 == gz - 1) break;  // whole grid
             // every unscanned point lies beyond a face of the block: lower-bound its distance
             float R = INFINITY;
@@ -225,13 +268,9 @@ __global__ void __launch_bounds__(128) query_kernel(const float4* __restrict__ s
             if (cz - r >= 0) R = fminf(R, q.z - (m.lo[2] + (float)(cz - r) * m.h));
             if (cz + r <= gz - 1) R = fminf(R, (m.lo[2] + (float)(cz + r + 1) * m.h) - q.z);
             R -= m.eps_abs;
-            if (R > 0.f) {
-                // the last kept entry (rank KCAP >= K+1) must be strictly inside the guaranteed radius; an empty slot
-                // decodes to NaN, so the test fails until KCAP candidates were seen.  Static index: the list stays
-                // in registers.
-                const float worst = key_dist(list[KCAP - 1]);
-                if (worst < R * R * 0.99999f) break;
-            }
+            // the last kept entry (rank KCAP >= K+1) must be strictly inside the guaranteed radius (+inf while fewer
+            // than KCAP candidates were seen)
+            if (R > 0.f && dist[KCAP - 1] < R * R * 0.99999f) break;
         }
 
         // ---- emit + tie flags
@@ -240,15 +279,12 @@ __global__ void __launch_bounds__(128) query_kernel(const float4* __restrict__ s
         bool flag = false;
 #pragma unroll
         for (int j = 0; j < KCAP - 1; ++j) {
-            if (j < valid) o[j] = (OutT)(unsigned)(list[j] & 0xFFFFFFFFull);
-            if (j + 1 < valid && (unsigned)(list[j] >> 32) == (unsigned)(list[j + 1] >> 32)) flag = true;
+            if (j < valid) o[j] = (OutT)idx[j];
+            if (j + 1 < valid && dist[j] == dist[j + 1]) flag = true;
+            // boundary tie or near tie between rank K and K+1 (pruning-rounding hazard)
+            if (j + 1 == K && N > (unsigned)K && dist[j + 1] <= dist[j] * 1.00001f) flag = true;
         }
-        if (KCAP - 1 < valid) o[KCAP - 1] = (OutT)(unsigned)(list[KCAP - 1] & 0xFFFFFFFFull);
-        if (N > (unsigned)K) {  // boundary tie or near tie between rank K and K+1 (pruning-rounding hazard)
-#pragma unroll
-            for (int j = 0; j < KCAP - 1; ++j)
-                if (j + 1 == K && key_dist(list[j + 1]) <= key_dist(list[j]) * 1.00001f) flag = true;
-        }
+        if (KCAP - 1 < valid) o[KCAP - 1] = (OutT)idx[KCAP - 1];
         if (flag) flag_list[atomicAdd(flag_count, 1u)] = b * Q + qid;
     }
 #pragma unroll

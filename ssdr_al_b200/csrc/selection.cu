@@ -261,20 +261,53 @@ __device__ __forceinline__ double dot64_fixed(const T* __restrict__ a, const T* 
     return acc;
 }
 
-// Mailbox of one CTA for one step parity: candidate + tag (= step + 1).  Readers poll the tags directly, so a pick
-// costs one release store and one acquire poll instead of an atomic counter plus a second read.
+// Mailbox of one CTA for one step parity, low-latency style: the candidate travels as 32-bit chunks, each chunk
+// paired with the 32-bit step tag inside ONE naturally atomic 8-byte word.  A reader that sees the tag in a word has
+// the chunk too, so a pick costs one plain store burst and one (parallel) poll -- no fence, no counter, no second read.
 struct __align__(32) Mailbox {
-    unsigned long long hi, lo;
-    unsigned long long tag;
-    unsigned long long pad;
+    unsigned long long w[4];  // float: w[0] = {dist bits, tag}, w[1] = {~row, tag}; double: four chunks
 };
-__device__ __forceinline__ void st_release_u64(unsigned long long* p, unsigned long long v) {
-    asm volatile("st.release.gpu.global.u64 [%0], %1;\n" ::"l"(p), "l"(v) : "memory");
+__device__ __forceinline__ void st_relaxed_u64(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;\n" ::"l"(p), "l"(v) : "memory");
 }
-__device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long long* p) {
+__device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long long* p) {
     unsigned long long v;
-    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];\n" : "=l"(v) : "l"(p) : "memory");
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];\n" : "=l"(v) : "l"(p) : "memory");
     return v;
+}
+template <typename T>
+__device__ __forceinline__ void mailbox_post(Mailbox* mb, const Cand& c, unsigned tag) {
+    const unsigned long long t = (unsigned long long)tag;
+    st_relaxed_u64(&mb->w[0], ((c.hi >> 32) << 32) | t);
+    st_relaxed_u64(&mb->w[1], ((c.hi & 0xFFFFFFFFull) << 32) | t);
+    if (sizeof(T) == 8) {
+        st_relaxed_u64(&mb->w[2], ((c.lo >> 32) << 32) | t);
+        st_relaxed_u64(&mb->w[3], ((c.lo & 0xFFFFFFFFull) << 32) | t);
+    }
+}
+// raw chunk words of one mailbox (all loads independent, so several mailboxes can be in flight per lane)
+template <typename T>
+__device__ __forceinline__ void mailbox_load(const Mailbox* mb, unsigned long long (&v)[4]) {
+    v[0] = ld_relaxed_u64(&mb->w[0]);
+    v[1] = ld_relaxed_u64(&mb->w[1]);
+    if (sizeof(T) == 8) {
+        v[2] = ld_relaxed_u64(&mb->w[2]);
+        v[3] = ld_relaxed_u64(&mb->w[3]);
+    } else {
+        v[2] = v[3] = 0;
+    }
+}
+// true when every chunk carries `tag`; then `out` holds the candidate
+template <typename T>
+__device__ __forceinline__ bool mailbox_decode(const unsigned long long (&v)[4], unsigned tag, Cand* out) {
+    bool ok = (unsigned)v[0] == tag && (unsigned)v[1] == tag;
+    out->hi = ((v[0] >> 32) << 32) | (v[1] >> 32);
+    out->lo = 0;
+    if (sizeof(T) == 8) {
+        ok = ok && (unsigned)v[2] == tag && (unsigned)v[3] == tag;
+        out->lo = ((v[2] >> 32) << 32) | (v[3] >> 32);
+    }
+    return ok;
 }
 
 template <typename T, int MODE, int DT, int GT>  // DT: compile-time D (0 = generic), GT: row groups per unit (0 = runtime)
@@ -439,24 +472,41 @@ __global__ void __launch_bounds__(THREADS, 1) select_kernel(const Params<T> p) {
         if (warp == 0) {
             Cand c = lane < NWARP ? s_red[lane] : Cand{0, 0};
             c = warp_max<T>(c);
-            const unsigned long long tag = (unsigned long long)(step + 1);
-            Mailbox* mine_box = boxes + (size_t)(step & 1) * G + blockIdx.x;
-            if (lane == 0) {
-                mine_box->hi = c.hi;
-                mine_box->lo = c.lo;
-                __threadfence();
-                st_release_u64(&mine_box->tag, tag);
-            }
+            const unsigned tag = (unsigned)(step + 1);
+            Mailbox* row_boxes = boxes + (size_t)(step & 1) * G;
+            if (lane == 0) mailbox_post<T>(row_boxes + blockIdx.x, c, tag);
+            // poll all mailboxes: every lane keeps its loads in flight together and retries only the missing ones
             Cand w{0, 0};
-            for (int b = lane; b < G; b += 32) {
-                const Mailbox* mb = boxes + (size_t)(step & 1) * G + b;
-                while (ld_acquire_u64(&mb->tag) != tag) {
+            constexpr int KM = 5;  // 5 x 32 = 160 >= 148 CTAs
+            unsigned pending = 0;
+#pragma unroll
+            for (int k = 0; k < KM; ++k)
+                if (lane + 32 * k < G) pending |= 1u << k;
+            while (pending) {
+                unsigned long long v[KM][4];
+#pragma unroll
+                for (int k = 0; k < KM; ++k)
+                    if (pending & (1u << k)) mailbox_load<T>(row_boxes + lane + 32 * k, v[k]);
+#pragma unroll
+                for (int k = 0; k < KM; ++k) {
+                    if (pending & (1u << k)) {
+                        Cand o;
+                        if (mailbox_decode<T>(v[k], tag, &o)) {
+                            w = cand_max<T>(w, o);
+                            pending &= ~(1u << k);
+                        }
+                    }
                 }
+            }
+            for (int bb = lane + 32 * KM; bb < G; bb += 32) {  // larger grids (not on B200): simple spin
                 Cand o;
-                o.hi = __ldcg(&mb->hi);
-                o.lo = __ldcg(&mb->lo);
+                unsigned long long v[4];
+                do {
+                    mailbox_load<T>(row_boxes + bb, v);
+                } while (!mailbox_decode<T>(v, tag, &o));
                 w = cand_max<T>(w, o);
             }
+            __syncwarp();
             w = warp_max<T>(w);
             if (lane == 0) {
                 s_next_center = cand_row<T>(w);
