@@ -89,6 +89,9 @@ int ssdr_knn_debug_tree(const float* points, size_t npts, uint32_t* vind_out, ui
                         uint32_t* right, int32_t* child1, int32_t* child2, int32_t* divfeat, float* divlow,
                         float* divhigh);
 
+/* Diagnostic only: %globaltimer marks (ns) of the tree build for B clouds of npts points; see knn.cu. */
+int ssdr_knn_debug_build_timing(const float* points, size_t B, size_t npts, uint64_t* marks16);
+
 /* ---- grid subsampling ------------------------------------------------------------------------------ */
 #define SSDR_GRID_ORDER_KEY 0       /* rows in ascending voxel key (canonical, deterministic) */
 #define SSDR_GRID_ORDER_REFERENCE 1 /* rows in the reference's libstdc++ hash-iteration order */

@@ -39,6 +39,7 @@ SIGNATURES = {
     "ssdr_knn_batch_dev": [vp, sz, sz, vp, sz, sz, vp, vp, C.POINTER(KnnStats)],
     "ssdr_knn_batch_dev_i32": [vp, sz, sz, vp, sz, sz, vp, vp, C.POINTER(KnnStats)],
     "ssdr_knn_debug_tree": [vp, sz, vp, vp, vp, vp, vp, vp, vp, vp, vp],
+    "ssdr_knn_debug_build_timing": [vp, sz, sz, vp],
     "ssdr_grid_subsample": [vp, vp, vp, sz, sz, sz, C.c_float, C.c_int, C.POINTER(sz), C.POINTER(vp)],
     "ssdr_grid_fetch": [vp, vp, vp, vp],
     "ssdr_grid_fetch_ex": [vp, vp, vp, vp, vp, vp],

@@ -25,11 +25,12 @@ namespace kdtree {
 
 constexpr int BT = 1024;
 constexpr int NW = BT / 32;
-constexpr int IPT = 4;
+constexpr int IPT = 4;          // subtree CTA-wide scan: MED_MAX == BT * IPT
+constexpr int IPT_BIG = 4;      // top-level scan chunk per thread (8 and loop unrolling measured slower: spills)
 constexpr int LEAF = 10;
-constexpr int SMALL_MAX = 512;    // split by one warp
+constexpr int SMALL_MAX = 1024;   // split by one warp (32 slots per lane)
 constexpr int MED_MAX = 4096;     // whole subtree grown in the shared memory of one CTA
-constexpr int LIST_MED = 8;       // > SMALL_MAX nodes inside one subtree level (<= MED_MAX / (SMALL_MAX+1))
+constexpr int LIST_MED = 4;       // > SMALL_MAX nodes inside one subtree level (<= MED_MAX / (SMALL_MAX+1))
 constexpr int LIST_SMALL = 384;   // split-able nodes inside one subtree level (<= MED_MAX / (LEAF+1))
 constexpr int MAX_LEVELS = 512;
 constexpr int MAX_DEPTH = 96;
@@ -56,7 +57,7 @@ constexpr size_t SM_PFAIL = SM_PSAT + (size_t)MED_MAX * 2;
 constexpr size_t SM_LPOS = SM_PFAIL + (size_t)MED_MAX * 2;
 constexpr size_t SM_RPOS = SM_LPOS + (size_t)MED_MAX;
 constexpr size_t SM_WSCR = SM_RPOS + (size_t)MED_MAX;
-constexpr size_t SM_LISTS = SM_WSCR + (size_t)NW * 1024;
+constexpr size_t SM_LISTS = SM_WSCR + (size_t)NW * SMALL_MAX * 2;  // per warp: sL, sR (u16 x SMALL_MAX/2 each)
 constexpr size_t SM_TOTAL = SM_LISTS + 2 * (size_t)(LIST_MED + LIST_SMALL) * sizeof(Entry);
 
 struct Tree {
@@ -79,8 +80,18 @@ struct Tree {
     unsigned* barrier;     // grid barrier counter
     unsigned* error;       // bit 0: node capacity, bit 1: level cap, bit 2: DFS stack, bit 3: list capacity
     const unsigned char* item_needed;  // [B] build only where a flagged row lives (nullptr = all)
+    unsigned long long* tstamps;       // [16] optional %globaltimer marks (diagnostics; nullptr = off)
 };
 
+__device__ __forceinline__ unsigned long long gtimer() {
+    unsigned long long v;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(v));
+    return v;
+}
+__device__ __forceinline__ void mark(const unsigned long long* dummy, unsigned long long* ts, int slot) {
+    (void)dummy;
+    if (ts && blockIdx.x == 0 && threadIdx.x == 0) ts[slot] = gtimer();
+}
 __device__ __forceinline__ unsigned ld_acq(const unsigned* p) {
     unsigned v;
     asm volatile("ld.acquire.gpu.global.u32 %0, [%1];\n" : "=r"(v) : "l"(p) : "memory");
@@ -300,16 +311,19 @@ __device__ __forceinline__ void split_big(const Tree& t, unsigned g, int level, 
     unsigned start = l, lim1 = l, lim2 = l;
     for (int sweep = 0; sweep < 2; ++sweep) {
         unsigned long long carry = 0;
-        for (unsigned base = start; base < r; base += BT * IPT) {
-            const unsigned i0 = base + tid * IPT;
-            unsigned long long f[IPT];
+        for (unsigned base = start; base < r; base += BT * IPT_BIG) {
+            const unsigned i0 = base + tid * IPT_BIG;
+            unsigned long long f[IPT_BIG];
+            float vals[IPT_BIG];
+#pragma unroll
+            for (int k = 0; k < IPT_BIG; ++k) vals[k] = (i0 + k < r) ? comp(__ldcg(pp + i0 + k), cf) : 0.f;
             unsigned long long local = 0;
 #pragma unroll
-            for (int k = 0; k < IPT; ++k) {
+            for (int k = 0; k < IPT_BIG; ++k) {
                 const unsigned i = i0 + k;
                 unsigned long long fl = 0;
                 if (i < r) {
-                    const float v = comp(__ldcg(pp + i), cf);
+                    const float v = vals[k];
                     const bool sat = sweep == 0 ? (v < cv) : (v <= cv);
                     fl = sat ? 1ull : (1ull << 32);
                 }
@@ -320,7 +334,7 @@ __device__ __forceinline__ void split_big(const Tree& t, unsigned g, int level, 
             const unsigned long long incl = block_scan_incl(local, s_warp, &tot);
             const unsigned long long excl = incl - local + carry;
 #pragma unroll
-            for (int k = 0; k < IPT; ++k) {
+            for (int k = 0; k < IPT_BIG; ++k) {
                 const unsigned i = i0 + k;
                 if (i < r) {
                     const unsigned long long v = excl + f[k];
@@ -727,7 +741,7 @@ __device__ __forceinline__ void build_subtree(const Tree& t, unsigned groot, uns
         for (unsigned m = 0; m < nmed; ++m) split_med_sm(t, sc, cl[m], s_warp, s_red, s_bc);
         __syncthreads();
         for (unsigned w = warp; w < nsmall; w += NW)
-            split_small_sm(t, sc, cl[LIST_MED + w], reinterpret_cast<unsigned short*>(dsm + SM_WSCR) + (size_t)warp * 512);
+            split_small_sm(t, sc, cl[LIST_MED + w], reinterpret_cast<unsigned short*>(dsm + SM_WSCR) + (size_t)warp * SMALL_MAX);
         __syncthreads();
         if (tid == 0) s_ctl[cur * 2] = s_ctl[cur * 2 + 1] = 0u;
         __syncthreads();
@@ -744,6 +758,7 @@ __global__ void __launch_bounds__(BT, 1) build_kernel(const float* __restrict__ 
     const unsigned tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
     unsigned phase = 0;
+    mark(nullptr, t.tstamps, 0);
 
     // ---- roots: pp = (point, identity index) (init_vind :1232-1238), data bbox (computeBoundingBox :1241-1263)
     for (unsigned b = blockIdx.x; b < t.B; b += gridDim.x) {
@@ -812,6 +827,7 @@ __global__ void __launch_bounds__(BT, 1) build_kernel(const float* __restrict__ 
         __syncthreads();
     }
     grid_sync(t.barrier, phase);
+    mark(nullptr, t.tstamps, 1);
 
     // ---- TOP levels
     for (int level = 0; level < MAX_LEVELS; ++level) {
@@ -820,11 +836,15 @@ __global__ void __launch_bounds__(BT, 1) build_kernel(const float* __restrict__ 
         const unsigned* cur = t.list + (size_t)(level & 1) * t.lcap;
         for (unsigned i = blockIdx.x; i < nbig; i += gridDim.x) split_big(t, __ldcg(cur + i), level, s_warp, s_red, s_bc);
         grid_sync(t.barrier, phase);
+        if (level < 8) mark(nullptr, t.tstamps, 2 + level);
     }
+    mark(nullptr, t.tstamps, 10);
     // ---- SUBTREES (independent; no further grid barrier)
     const unsigned nsub = min(__ldcg(&t.list_cnt[MAX_LEVELS + 1]), t.lcap);
     for (unsigned i = blockIdx.x; i < nsub; i += gridDim.x)
         build_subtree(t, __ldcg(t.sublist + i), dyn_smem, s_warp, s_red, s_bc, s_ctl);
+    mark(nullptr, t.tstamps, 11);  // CTA 0's own end
+    if (t.tstamps && threadIdx.x == 0) atomicMax(&t.tstamps[12], gtimer());  // last CTA's end
 }
 
 __global__ void mark_items_kernel(const unsigned* __restrict__ flag_list, unsigned n_flag, unsigned Q,
@@ -1004,6 +1024,7 @@ static int alloc_tree(Ctx* c, cudaStream_t s, size_t B, size_t N, Tree* out) {
     t.barrier = t.list_cnt + (size_t)(MAX_LEVELS + 2);
     t.error = t.barrier + 4;
     t.item_needed = nullptr;
+    t.tstamps = nullptr;
     *out = t;
     return SSDR_OK;
 }

@@ -479,6 +479,28 @@ int ssdr_knn_batch_dev(const float* d_points, size_t batch_size, size_t npts, co
 }
 // Diagnostic: build the nanoflann-identical tree of one cloud on the device and copy it back (tests compare it with
 // a sequential CPU build).  Node arrays must hold 3*npts+64 entries.
+// Diagnostic: build B trees of npts points each (device timing only) and return %globaltimer marks in ns:
+// [0] start, [1] roots done, [2..9] top level k done, [10] top done, [11] CTA 0 done, [12] last CTA done.
+int ssdr_knn_debug_build_timing(const float* points, size_t B, size_t npts, uint64_t* marks16) {
+    SSDR_REQUIRE(points && npts >= 1 && B >= 1 && marks16, SSDR_ERR_INVALID, "bad argument");
+    Ctx* c;
+    SSDR_TRY(get_ctx(&c));
+    cudaStream_t s = c->stream;
+    SSDR_TRY(c->ws[knn::WS_IN_P].reserve(B * npts * 3 * sizeof(float)));
+    SSDR_TRY(h2d(c, c->ws[knn::WS_IN_P].p, points, B * npts * 3 * sizeof(float), s));
+    SSDR_TRY(c->ws[knn::WS_STATS].reserve(16 * sizeof(unsigned long long) + 64));
+    unsigned long long* d_marks = reinterpret_cast<unsigned long long*>(c->ws[knn::WS_STATS].as<char>() + 64);
+    for (int rep = 0; rep < 3; ++rep) {  // the last repetition is the warm one
+        kdtree::Tree t;
+        SSDR_TRY(kdtree::alloc_tree(c, s, B, npts, &t));
+        SSDR_CHECK_CUDA(cudaMemsetAsync(d_marks, 0, 16 * sizeof(unsigned long long), s));
+        t.tstamps = d_marks;
+        SSDR_TRY(kdtree::launch_build(c, s, c->ws[knn::WS_IN_P].as<float>(), t));
+        SSDR_TRY(kdtree::check_tree_error(c, s, t));
+    }
+    return d2h_sync(c, marks16, d_marks, 16 * sizeof(unsigned long long), s);
+}
+
 int ssdr_knn_debug_tree(const float* points, size_t npts, uint32_t* vind_out, uint32_t* n_nodes_out, uint32_t* left,
                         uint32_t* right, int32_t* child1, int32_t* child2, int32_t* divfeat, float* divlow,
                         float* divhigh) {
