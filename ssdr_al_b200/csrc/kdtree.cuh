@@ -33,6 +33,7 @@ constexpr int MED_MAX = 4096;     // whole subtree grown in the shared memory of
 constexpr int LIST_MED = 4;       // > SMALL_MAX nodes inside one subtree level (<= MED_MAX / (SMALL_MAX+1))
 constexpr int LIST_SMALL = 384;   // split-able nodes inside one subtree level (<= MED_MAX / (LEAF+1))
 constexpr int MAX_LEVELS = 512;
+constexpr int MAX_GROUP_LEVELS = 64;  // levels that may use several CTAs per node (node size halves per level)
 constexpr int MAX_DEPTH = 96;
 constexpr int MAX_K = 64;
 
@@ -78,6 +79,9 @@ struct Tree {
     unsigned* sublist;     // [lcap] subtree roots
     unsigned* list_cnt;    // [MAX_LEVELS+1] top-level counts; [MAX_LEVELS+1] = subtree count
     unsigned* barrier;     // grid barrier counter
+    unsigned* gbar;        // [MAX_GROUP_LEVELS*G] group barrier counters (one per level and node slot), zeroed per build
+    unsigned* gred;        // [MAX_GROUP_LEVELS*G*8] group reductions: ~min xyz, max xyz, max(left cut coord), ~min(right)
+    unsigned* gpart;       // [G*2*G*2] per node slot, per sweep, per member CTA: (true count, false count)
     unsigned* error;       // bit 0: node capacity, bit 1: level cap, bit 2: DFS stack, bit 3: list capacity
     const unsigned char* item_needed;  // [B] build only where a flagged row lives (nullptr = all)
     unsigned long long* tstamps;       // [16] optional %globaltimer marks (diagnostics; nullptr = off)
@@ -398,6 +402,245 @@ __device__ __forceinline__ void split_big(const Tree& t, unsigned g, int level, 
             dlow = fmaxf(dlow, s_red[w]);
             dhigh = fminf(dhigh, s_red[NW + w]);
         }
+        emit_children_top(t, g, b, l, r, idx, cf, cv, dlow, dhigh, lo, hi, level);
+    }
+}
+
+// ---- TOP, group mode: when a level has fewer big nodes than CTAs, k = gridDim / nodes CTAs share one node -----------
+// Each member owns a contiguous slice of the node's positions; cross-CTA prefix counts go through per-member totals,
+// and the members meet at a group barrier (a counter private to this node and level) between the phases.
+__device__ __forceinline__ void group_sync(unsigned* counter, unsigned k, unsigned& phase) {
+    __syncthreads();
+    ++phase;
+    if (threadIdx.x == 0) {
+        // release/acquire on the counter order every member's writes: the release is cumulative over what the
+        // bar.sync above made visible to this thread, the acquire is published to the CTA by the bar.sync below
+        red_rel_add(counter, 1u);
+        const unsigned target = phase * k;
+        while (ld_acq(counter) < target) {
+        }
+    }
+    __syncthreads();
+}
+__device__ __forceinline__ unsigned f2ord_u(float f) {
+    unsigned u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float ord2f_u(unsigned u) {
+    return __uint_as_float((u & 0x80000000u) ? (u & 0x7FFFFFFFu) : ~u);
+}
+
+__device__ __forceinline__ void split_big_group(const Tree& t, unsigned g, int level, unsigned slot, unsigned k,
+                                                unsigned s, unsigned long long* s_warp, float* s_red) {
+    const unsigned tid = threadIdx.x;
+    const int lane = tid & 31, warp = tid >> 5;
+    const unsigned G = gridDim.x;
+    const unsigned b = g / t.cap;
+    float4* pp = t.pp + (size_t)b * t.N;
+    unsigned* lpos = t.lpos + (size_t)b * t.N;
+    unsigned* rpos = t.rpos + (size_t)b * t.N;
+    unsigned* psat = t.psat + (size_t)b * t.N;
+    unsigned* pfail = t.pfail + (size_t)b * t.N;
+    unsigned* bar = t.gbar + (size_t)level * G + slot;
+    unsigned* red = t.gred + ((size_t)level * G + slot) * 8;
+    unsigned phase = 0;
+    const unsigned l = __ldcg(&t.nodes[g].l), r = __ldcg(&t.nodes[g].r);
+    const unsigned count = r - l;
+    float lo[3], hi[3];
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+        lo[d] = __ldcg(&t.nlo[(size_t)g * 3 + d]);
+        hi[d] = __ldcg(&t.nhi[(size_t)g * 3 + d]);
+    }
+    // ---- M: computeMinMax over the member's slice, combined with order-preserving atomics (identity 0)
+    {
+        const unsigned len = (count + k - 1) / k;
+        const unsigned a = min(l + s * len, r), e = min(a + len, r);
+        float mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
+        for (unsigned i = a + tid; i < e; i += BT) {
+            const float4 v = __ldcg(pp + i);
+            mn[0] = fminf(mn[0], v.x);
+            mx[0] = fmaxf(mx[0], v.x);
+            mn[1] = fminf(mn[1], v.y);
+            mx[1] = fmaxf(mx[1], v.y);
+            mn[2] = fminf(mn[2], v.z);
+            mx[2] = fmaxf(mx[2], v.z);
+        }
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+#pragma unroll
+            for (int m = 16; m > 0; m >>= 1) {
+                mn[d] = fminf(mn[d], __shfl_xor_sync(0xffffffffu, mn[d], m));
+                mx[d] = fmaxf(mx[d], __shfl_xor_sync(0xffffffffu, mx[d], m));
+            }
+            if (lane == 0) {
+                s_red[d * NW + warp] = mn[d];
+                s_red[(3 + d) * NW + warp] = mx[d];
+            }
+        }
+        __syncthreads();
+        if (tid < 6) {  // one atomic per CTA and quantity; +-inf (empty slice) never reaches the atomics
+            float v = s_red[tid * NW];
+            for (int w = 1; w < NW; ++w) v = tid < 3 ? fminf(v, s_red[tid * NW + w]) : fmaxf(v, s_red[tid * NW + w]);
+            if (tid < 3 && v != INFINITY) atomicMax(&red[tid], ~f2ord_u(v));
+            if (tid >= 3 && v != -INFINITY) atomicMax(&red[tid], f2ord_u(v));
+        }
+    }
+    group_sync(bar, k, phase);
+    float tmn[3], tmx[3];
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+        tmn[d] = ord2f_u(~__ldcg(&red[d]));
+        tmx[d] = ord2f_u(__ldcg(&red[3 + d]));
+    }
+    int cf;
+    float cv;
+    decide_split(lo, hi, tmn, tmx, &cf, &cv);
+
+    // ---- planeSplit (:948-975), two sweeps
+    unsigned start = l, lim1 = l, lim2 = l;
+    for (int sweep = 0; sweep < 2; ++sweep) {
+        unsigned* part = t.gpart + (((size_t)slot * 2 + sweep) * G) * 2;
+        const unsigned cnt = r - start;
+        const unsigned len = (cnt + k - 1) / k;
+        const unsigned a = min(start + s * len, r), e = min(a + len, r);
+        // A1: local inclusive prefix counts over [a, e)
+        unsigned long long carry = 0;
+        for (unsigned base = a; base < e; base += BT * IPT_BIG) {
+            const unsigned i0 = base + tid * IPT_BIG;
+            unsigned long long f[IPT_BIG];
+            unsigned long long local = 0;
+#pragma unroll
+            for (int q = 0; q < IPT_BIG; ++q) {
+                const unsigned i = i0 + q;
+                unsigned long long fl = 0;
+                if (i < e) {
+                    const float v = comp(__ldcg(pp + i), cf);
+                    const bool sat = sweep == 0 ? (v < cv) : (v <= cv);
+                    fl = sat ? 1ull : (1ull << 32);
+                }
+                local += fl;
+                f[q] = local;
+            }
+            unsigned long long tot;
+            const unsigned long long incl = block_scan_incl(local, s_warp, &tot);
+            const unsigned long long excl = incl - local + carry;
+#pragma unroll
+            for (int q = 0; q < IPT_BIG; ++q) {
+                const unsigned i = i0 + q;
+                if (i < e) {
+                    const unsigned long long v = excl + f[q];
+                    psat[i] = (unsigned)(v & 0xFFFFFFFFull);
+                    pfail[i] = (unsigned)(v >> 32);
+                }
+            }
+            carry += tot;
+        }
+        if (tid == 0) {
+            part[2 * s] = (unsigned)(carry & 0xFFFFFFFFull);
+            part[2 * s + 1] = (unsigned)(carry >> 32);
+        }
+        group_sync(bar, k, phase);
+        // A2: global ranks = member base + local counts (warp 0 sums the member totals, smem broadcasts them)
+        if (warp == 0) {
+            unsigned bs = 0, bf = 0, ts = 0, mm = 0;
+            const unsigned lim_guess_len = len;
+            for (unsigned q = lane; q < k; q += 32) {
+                const unsigned ps = __ldcg(&part[2 * q]), pf = __ldcg(&part[2 * q + 1]);
+                if (q < s) {
+                    bs += ps;
+                    bf += pf;
+                }
+                ts += ps;
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                bs += __shfl_xor_sync(0xffffffffu, bs, o);
+                bf += __shfl_xor_sync(0xffffffffu, bf, o);
+                ts += __shfl_xor_sync(0xffffffffu, ts, o);
+            }
+            const unsigned lim_w = start + ts;
+            if (lim_w > start) {  // misplaced pairs = predicate-false positions in [start, lim)
+                const unsigned sq = (lim_w - 1 - start) / lim_guess_len;  // member that owns position lim-1
+                for (unsigned q = lane; q < sq; q += 32) mm += __ldcg(&part[2 * q + 1]);
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) mm += __shfl_xor_sync(0xffffffffu, mm, o);
+                mm += __ldcg(&pfail[lim_w - 1]);
+            }
+            if (lane == 0) {
+                s_red[0] = __uint_as_float(bs);
+                s_red[1] = __uint_as_float(bf);
+                s_red[2] = __uint_as_float(ts);
+                s_red[3] = __uint_as_float(mm);
+            }
+        }
+        __syncthreads();
+        const unsigned base_sat = __float_as_uint(s_red[0]), base_fail = __float_as_uint(s_red[1]);
+        const unsigned tot_sat = __float_as_uint(s_red[2]), m = __float_as_uint(s_red[3]);
+        const unsigned lim = start + tot_sat;
+        for (unsigned i = a + tid; i < e; i += BT) {
+            const unsigned ls = psat[i], lf = pfail[i];
+            const bool sat = (i == a ? ls : ls - psat[i - 1]) != 0;
+            if (!sat) {
+                if (i < lim) lpos[l + (base_fail + lf - 1)] = i;
+            } else {
+                if (i >= lim) rpos[l + (tot_sat - (base_sat + ls))] = i;
+            }
+        }
+        group_sync(bar, k, phase);
+        // A3: swaps, pairs dealt round-robin to the members
+        for (unsigned q = s * BT + tid; q < m; q += k * BT) {
+            const unsigned pa = __ldcg(&lpos[l + q]), pc = __ldcg(&rpos[l + q]);
+            const float4 va = __ldcg(pp + pa), vc = __ldcg(pp + pc);
+            pp[pa] = vc;
+            pp[pc] = va;
+        }
+        group_sync(bar, k, phase);
+        if (sweep == 0) {
+            lim1 = lim;
+            start = lim;
+        } else {
+            lim2 = lim;
+        }
+    }
+    const unsigned l1 = lim1 - l, l2 = lim2 - l;
+    unsigned idx;  // :934-936
+    if (l1 > count / 2) idx = l1;
+    else if (l2 < count / 2) idx = l2;
+    else idx = count / 2;
+    // ---- F: divlow / divhigh over the member's slice
+    {
+        const unsigned len = (count + k - 1) / k;
+        const unsigned a = min(l + s * len, r), e = min(a + len, r);
+        float dlow = -INFINITY, dhigh = INFINITY;
+        for (unsigned i = a + tid; i < e; i += BT) {
+            const float v = comp(__ldcg(pp + i), cf);
+            if (i - l < idx) dlow = fmaxf(dlow, v);
+            else dhigh = fminf(dhigh, v);
+        }
+#pragma unroll
+        for (int m = 16; m > 0; m >>= 1) {
+            dlow = fmaxf(dlow, __shfl_xor_sync(0xffffffffu, dlow, m));
+            dhigh = fminf(dhigh, __shfl_xor_sync(0xffffffffu, dhigh, m));
+        }
+        __syncthreads();  // s_red still holds the A2 broadcast of the last sweep
+        if (lane == 0) {
+            s_red[warp] = dlow;
+            s_red[NW + warp] = dhigh;
+        }
+        __syncthreads();
+        if (tid == 0) {
+            for (int w = 1; w < NW; ++w) {
+                dlow = fmaxf(dlow, s_red[w]);
+                dhigh = fminf(dhigh, s_red[NW + w]);
+            }
+            if (dlow != -INFINITY) atomicMax(&red[6], f2ord_u(dlow));
+            if (dhigh != INFINITY) atomicMax(&red[7], ~f2ord_u(dhigh));
+        }
+    }
+    group_sync(bar, k, phase);
+    if (s == 0 && tid == 0) {
+        const float dlow = ord2f_u(__ldcg(&red[6])), dhigh = ord2f_u(~__ldcg(&red[7]));
         emit_children_top(t, g, b, l, r, idx, cf, cv, dlow, dhigh, lo, hi, level);
     }
 }
@@ -834,7 +1077,14 @@ __global__ void __launch_bounds__(BT, 1) build_kernel(const float* __restrict__ 
         const unsigned nbig = __ldcg(&t.list_cnt[level]);
         if (nbig == 0) break;
         const unsigned* cur = t.list + (size_t)(level & 1) * t.lcap;
-        for (unsigned i = blockIdx.x; i < nbig; i += gridDim.x) split_big(t, __ldcg(cur + i), level, s_warp, s_red, s_bc);
+        const unsigned kgrp = gridDim.x / nbig;  // CTAs per node when the level has fewer nodes than CTAs
+        if (kgrp >= 2 && level < MAX_GROUP_LEVELS) {
+            const unsigned slot = blockIdx.x / kgrp;
+            if (slot < nbig) split_big_group(t, __ldcg(cur + slot), level, slot, kgrp, blockIdx.x % kgrp, s_warp, s_red);
+        } else {
+            for (unsigned i = blockIdx.x; i < nbig; i += gridDim.x)
+                split_big(t, __ldcg(cur + i), level, s_warp, s_red, s_bc);
+        }
         grid_sync(t.barrier, phase);
         if (level < 8) mark(nullptr, t.tstamps, 2 + level);
     }
@@ -999,6 +1249,9 @@ static int alloc_tree(Ctx* c, cudaStream_t s, size_t B, size_t N, Tree* out) {
     SSDR_TRY(c->ws[TW_BASE + 2].reserve(3 * lcap * sizeof(unsigned)));
     const size_t ctl_words = 6 * B + B + (size_t)(MAX_LEVELS + 2) + 8 + (B + 3) / 4 + 4;
     SSDR_TRY(c->ws[TW_BASE + 3].reserve(ctl_words * sizeof(unsigned)));
+    const size_t G = (size_t)c->sm_count;
+    const size_t grp_words = (size_t)MAX_GROUP_LEVELS * G * 9 + G * 2 * G * 2;
+    SSDR_TRY(c->ws[TW_BASE + 4].reserve(grp_words * sizeof(unsigned)));
     Tree t;
     t.N = (unsigned)N;
     t.cap = (unsigned)cap;
@@ -1023,6 +1276,10 @@ static int alloc_tree(Ctx* c, cudaStream_t s, size_t B, size_t N, Tree* out) {
     t.list_cnt = ctl + 7 * B;
     t.barrier = t.list_cnt + (size_t)(MAX_LEVELS + 2);
     t.error = t.barrier + 4;
+    t.gbar = c->ws[TW_BASE + 4].as<unsigned>();
+    t.gred = t.gbar + (size_t)MAX_GROUP_LEVELS * G;
+    t.gpart = t.gred + (size_t)MAX_GROUP_LEVELS * G * 8;
+    SSDR_CHECK_CUDA(cudaMemsetAsync(t.gbar, 0, (size_t)MAX_GROUP_LEVELS * G * 9 * sizeof(unsigned), s));
     t.item_needed = nullptr;
     t.tstamps = nullptr;
     *out = t;

@@ -42,49 +42,16 @@ __device__ __forceinline__ float ord2f(unsigned u) {
     return __uint_as_float((u & 0x80000000u) ? (u & 0x7FFFFFFFu) : ~u);
 }
 
-// ---- A1: bounding box per item ---------------------------------------------------------------------------
-__global__ void bbox_init_kernel(unsigned* enc, int B) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < B * 6) enc[i] = (i % 6) < 3 ? 0xFFFFFFFFu : 0u;
-}
-__global__ void bbox_kernel(const float* __restrict__ pts, unsigned N, unsigned* __restrict__ enc) {
-    const unsigned b = blockIdx.y;
-    const float* p = pts + (size_t)b * N * 3;
-    float mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
-    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < N; i += gridDim.x * blockDim.x) {
-#pragma unroll
-        for (int d = 0; d < 3; ++d) {
-            float v = __ldg(p + 3 * (size_t)i + d);
-            mn[d] = fminf(mn[d], v);
-            mx[d] = fmaxf(mx[d], v);
-        }
-    }
-#pragma unroll
-    for (int d = 0; d < 3; ++d)
-#pragma unroll
-        for (int m = 16; m > 0; m >>= 1) {
-            mn[d] = fminf(mn[d], __shfl_xor_sync(0xffffffffu, mn[d], m));
-            mx[d] = fmaxf(mx[d], __shfl_xor_sync(0xffffffffu, mx[d], m));
-        }
-    if ((threadIdx.x & 31) == 0) {
-#pragma unroll
-        for (int d = 0; d < 3; ++d) {
-            atomicMin(&enc[b * 6 + d], f2ord(mn[d]));
-            atomicMax(&enc[b * 6 + 3 + d], f2ord(mx[d]));
-        }
-    }
-}
-
-// ---- A2: cell grid geometry per item ----------------------------------------------------------------------
-__global__ void setup_items_kernel(const unsigned* __restrict__ enc, ItemMeta* __restrict__ items, int B, unsigned N,
-                                   float occupancy, unsigned cell_cap, unsigned cstride) {
-    const int b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= B) return;
+// ---- A1+A2: bounding box per item, then (last block) the cell grid geometry --------------------------------------
+// enc holds order-preserving encodings combined with atomicMax and identity 0: [0..2] = ~ord(min), [3..5] = ord(max),
+// so one memset prepares it together with the counters.
+__device__ void setup_item(const unsigned* __restrict__ enc, ItemMeta* __restrict__ items, int b, unsigned N,
+                           float occupancy, unsigned cell_cap, unsigned cstride) {
     ItemMeta m;
     float ext[3], E = 0.f, amax = 0.f;
     for (int d = 0; d < 3; ++d) {
-        m.lo[d] = ord2f(enc[b * 6 + d]);
-        m.hi[d] = ord2f(enc[b * 6 + 3 + d]);
+        m.lo[d] = ord2f(~__ldcg(&enc[b * 6 + d]));
+        m.hi[d] = ord2f(__ldcg(&enc[b * 6 + 3 + d]));
         ext[d] = m.hi[d] - m.lo[d];
         E = fmaxf(E, ext[d]);
         amax = fmaxf(amax, fmaxf(fabsf(m.lo[d]), fabsf(m.hi[d])));
@@ -115,39 +82,93 @@ __global__ void setup_items_kernel(const unsigned* __restrict__ enc, ItemMeta* _
     items[b] = m;
 }
 
+__global__ void bbox_setup_kernel(const float* __restrict__ pts, unsigned N, unsigned* __restrict__ enc,
+                                  unsigned* __restrict__ ticket, ItemMeta* __restrict__ items, int B, float occupancy,
+                                  unsigned cell_cap, unsigned cstride) {
+    const unsigned b = blockIdx.y;
+    const float* p = pts + (size_t)b * N * 3;
+    float mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < N; i += gridDim.x * blockDim.x) {
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+            float v = __ldg(p + 3 * (size_t)i + d);
+            mn[d] = fminf(mn[d], v);
+            mx[d] = fmaxf(mx[d], v);
+        }
+    }
+#pragma unroll
+    for (int d = 0; d < 3; ++d)
+#pragma unroll
+        for (int m = 16; m > 0; m >>= 1) {
+            mn[d] = fminf(mn[d], __shfl_xor_sync(0xffffffffu, mn[d], m));
+            mx[d] = fmaxf(mx[d], __shfl_xor_sync(0xffffffffu, mx[d], m));
+        }
+    if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+            if (mn[d] != INFINITY) atomicMax(&enc[b * 6 + d], ~f2ord(mn[d]));
+            if (mx[d] != -INFINITY) atomicMax(&enc[b * 6 + 3 + d], f2ord(mx[d]));
+        }
+    }
+    // last block done -> geometry of every item
+    __shared__ bool s_last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = atomicAdd(ticket, 1u) == gridDim.x * gridDim.y - 1;
+    __syncthreads();
+    if (s_last) {
+        __threadfence();
+        for (int it = threadIdx.x; it < B; it += blockDim.x)
+            setup_item(enc, items, it, N, occupancy, cell_cap, cstride);
+    }
+}
+
 __device__ __forceinline__ int cell_coord(float x, float lo, float inv_h, int g) {
     int c = (int)floorf((x - lo) * inv_h);
     return c < 0 ? 0 : (c >= g ? g - 1 : c);
 }
 
-// ---- A3: counting sort into cells ---------------------------------------------------------------------------
-__global__ void cell_count_kernel(const float* __restrict__ xyz, unsigned n_per_item, unsigned total,
-                                  const ItemMeta* __restrict__ items, unsigned* __restrict__ cell_of,
-                                  unsigned* __restrict__ counts) {
-    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= total) return;
-    const ItemMeta& m = items[i / n_per_item];
-    const float x = __ldg(xyz + 3 * (size_t)i), y = __ldg(xyz + 3 * (size_t)i + 1), z = __ldg(xyz + 3 * (size_t)i + 2);
+// ---- A3: counting sort into cells; points and (when they differ) queries in the same launches ---------------------
+struct SortJob {
+    const float* xyz;     // (B, n, 3)
+    unsigned n, total;    // per item, all items
+    unsigned* cell_of;    // [total]
+    unsigned* counts;     // [ncell]
+    const unsigned* starts;  // [ncell] exclusive scan of counts (this job's block of the concatenated scan)
+    unsigned* cursor;     // [ncell]
+    float4* sorted;       // [total]
+    unsigned start_bias;  // subtracted from starts (the queries' counts are scanned behind the points')
+};
+
+__global__ void cell_count_kernel(SortJob jp, SortJob jq, const ItemMeta* __restrict__ items) {
+    unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool isq = i >= jp.total;
+    const SortJob& j = isq ? jq : jp;
+    if (isq) i -= jp.total;
+    if (i >= j.total) return;
+    const ItemMeta& m = items[i / j.n];
+    const float x = __ldg(j.xyz + 3 * (size_t)i), y = __ldg(j.xyz + 3 * (size_t)i + 1), z = __ldg(j.xyz + 3 * (size_t)i + 2);
     const int cx = cell_coord(x, m.lo[0], m.inv_h, m.g[0]);
     const int cy = cell_coord(y, m.lo[1], m.inv_h, m.g[1]);
     const int cz = cell_coord(z, m.lo[2], m.inv_h, m.g[2]);
     const unsigned cell = m.cell_base + (unsigned)((cz * m.g[1] + cy) * m.g[0] + cx);
-    cell_of[i] = cell;
-    atomicAdd(&counts[cell], 1u);
+    j.cell_of[i] = cell;
+    atomicAdd(&j.counts[cell], 1u);
 }
-__global__ void cell_scatter_kernel(const float* __restrict__ xyz, unsigned n_per_item, unsigned total,
-                                    const unsigned* __restrict__ cell_of, const unsigned* __restrict__ starts,
-                                    unsigned* __restrict__ cursor, float4* __restrict__ sorted) {
-    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= total) return;
-    const unsigned cell = cell_of[i];
-    const unsigned pos = starts[cell] + atomicAdd(&cursor[cell], 1u);
+__global__ void cell_scatter_kernel(SortJob jp, SortJob jq) {
+    unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool isq = i >= jp.total;
+    const SortJob& j = isq ? jq : jp;
+    if (isq) i -= jp.total;
+    if (i >= j.total) return;
+    const unsigned cell = j.cell_of[i];
+    const unsigned pos = j.starts[cell] - j.start_bias + atomicAdd(&j.cursor[cell], 1u);
     float4 v;
-    v.x = __ldg(xyz + 3 * (size_t)i);
-    v.y = __ldg(xyz + 3 * (size_t)i + 1);
-    v.z = __ldg(xyz + 3 * (size_t)i + 2);
-    v.w = __int_as_float((int)(i % n_per_item));  // index inside the item
-    sorted[pos] = v;
+    v.x = __ldg(j.xyz + 3 * (size_t)i);
+    v.y = __ldg(j.xyz + 3 * (size_t)i + 1);
+    v.z = __ldg(j.xyz + 3 * (size_t)i + 2);
+    v.w = __int_as_float((int)(i % j.n));  // index inside the item
+    j.sorted[pos] = v;
 }
 
 // ---- B: main query kernel -------------------------------------------------------------------------------------
@@ -317,67 +338,76 @@ static int run_dev(Ctx* c, cudaStream_t s, const float* d_pts, size_t B, size_t 
     }
     float occupancy = g_occupancy_scale * (float)K;
     occupancy = occupancy < 0.6f ? 0.6f : (occupancy > 24.f ? 24.f : occupancy);
-    size_t cap = 4 * N + 64;
+    // cells per item: h is chosen so that cells ~= N / occupancy; 3x head-room for the +1 per axis and flat clouds
+    // (setup_item grows h until the grid fits, so the bound costs speed at worst, never correctness)
+    size_t cap = (size_t)(3.0 * (double)N / occupancy) + 64;
     if (cap > (1u << 24)) cap = (1u << 24);
     const unsigned cstride = (unsigned)cap + 1;
     const size_t ncell = B * (size_t)cstride + 1;
     const bool self = (d_q == d_pts && Q == N);
     const unsigned totalP = (unsigned)(B * N), totalQ = (unsigned)(B * Q);
+    const int njobs = self ? 1 : 2;
 
-    SSDR_TRY(c->ws[WS_ENC].reserve(B * 6 * sizeof(unsigned)));
+    // one zero-initialised control slab: stats | ticket | bbox encodings | counts (P,Q) | cursors (P,Q)
+    const size_t hdr_words = 16 + B * 6;
+    const size_t ctl_words = hdr_words + 2 * (size_t)njobs * ncell;
+    SSDR_TRY(c->ws[WS_CNT_P].reserve(ctl_words * 4));
     SSDR_TRY(c->ws[WS_ITEMS].reserve(B * sizeof(ItemMeta)));
-    SSDR_TRY(c->ws[WS_CELL_P].reserve((size_t)totalP * 4));
-    SSDR_TRY(c->ws[WS_CNT_P].reserve(ncell * 4 * 2));  // counts | cursor
-    SSDR_TRY(c->ws[WS_START_P].reserve(ncell * 4));
+    SSDR_TRY(c->ws[WS_CELL_P].reserve(((size_t)totalP + (self ? 0 : totalQ)) * 4));
+    SSDR_TRY(c->ws[WS_START_P].reserve((size_t)njobs * ncell * 4));
     SSDR_TRY(c->ws[WS_SORT_P].reserve((size_t)totalP * sizeof(float4)));
     SSDR_TRY(c->ws[WS_FLAGS].reserve((size_t)totalQ * 4 + 16));
-    SSDR_TRY(c->ws[WS_STATS].reserve(sizeof(DevStats)));
-    if (!self) {
-        SSDR_TRY(c->ws[WS_CELL_Q].reserve((size_t)totalQ * 4));
-        SSDR_TRY(c->ws[WS_CNT_Q].reserve(ncell * 4 * 2));
-        SSDR_TRY(c->ws[WS_START_Q].reserve(ncell * 4));
-        SSDR_TRY(c->ws[WS_SORT_Q].reserve((size_t)totalQ * sizeof(float4)));
-    }
-    unsigned* enc = c->ws[WS_ENC].as<unsigned>();
+    if (!self) SSDR_TRY(c->ws[WS_SORT_Q].reserve((size_t)totalQ * sizeof(float4)));
+    unsigned* ctl = c->ws[WS_CNT_P].as<unsigned>();
+    DevStats* dstats = reinterpret_cast<DevStats*>(ctl);
+    unsigned* ticket = ctl + 8;
+    unsigned* enc = ctl + 16;
+    unsigned* counts = ctl + hdr_words;                       // [njobs][ncell]
+    unsigned* cursors = counts + (size_t)njobs * ncell;       // [njobs][ncell]
+    unsigned* starts = c->ws[WS_START_P].as<unsigned>();      // [njobs][ncell], one concatenated exclusive scan
     ItemMeta* items = c->ws[WS_ITEMS].as<ItemMeta>();
-    unsigned* cnt_p = c->ws[WS_CNT_P].as<unsigned>();
-    unsigned* cur_p = cnt_p + ncell;
-    unsigned* start_p = c->ws[WS_START_P].as<unsigned>();
+    unsigned* start_p = starts;
     float4* sort_p = c->ws[WS_SORT_P].as<float4>();
-    DevStats* dstats = c->ws[WS_STATS].as<DevStats>();
     unsigned* flag_list = c->ws[WS_FLAGS].as<unsigned>();
 
     if (stats) SSDR_CHECK_CUDA(cudaEventRecord(c->tev[0], s));
-    SSDR_CHECK_CUDA(cudaMemsetAsync(cnt_p, 0, ncell * 4 * 2, s));
-    SSDR_CHECK_CUDA(cudaMemsetAsync(dstats, 0, sizeof(DevStats), s));
-    bbox_init_kernel<<<(unsigned)((B * 6 + 63) / 64), 64, 0, s>>>(enc, (int)B);
+    SSDR_CHECK_CUDA(cudaMemsetAsync(ctl, 0, ctl_words * 4, s));
     unsigned bx = (unsigned)((N + 1023) / 1024);
     if (bx > 256) bx = 256;
-    bbox_kernel<<<dim3(bx, (unsigned)B), 256, 0, s>>>(d_pts, (unsigned)N, enc);
-    setup_items_kernel<<<(unsigned)((B + 63) / 64), 64, 0, s>>>(enc, items, (int)B, (unsigned)N, occupancy,
-                                                               (unsigned)cap, cstride);
-    cell_count_kernel<<<(totalP + 255) / 256, 256, 0, s>>>(d_pts, (unsigned)N, totalP, items,
-                                                          c->ws[WS_CELL_P].as<unsigned>(), cnt_p);
-    size_t tbytes = 0;
-    SSDR_CHECK_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tbytes, cnt_p, start_p, (int)ncell, s));
-    SSDR_TRY(c->ws[WS_TEMP].reserve(tbytes));
-    SSDR_CHECK_CUDA(cub::DeviceScan::ExclusiveSum(c->ws[WS_TEMP].p, tbytes, cnt_p, start_p, (int)ncell, s));
-    cell_scatter_kernel<<<(totalP + 255) / 256, 256, 0, s>>>(d_pts, (unsigned)N, totalP, c->ws[WS_CELL_P].as<unsigned>(),
-                                                            start_p, cur_p, sort_p);
-    const float4* sort_q = sort_p;
+    bbox_setup_kernel<<<dim3(bx, (unsigned)B), 256, 0, s>>>(d_pts, (unsigned)N, enc, ticket, items, (int)B, occupancy,
+                                                           (unsigned)cap, cstride);
+    SortJob jp, jq;
+    jp.xyz = d_pts;
+    jp.n = (unsigned)N;
+    jp.total = totalP;
+    jp.cell_of = c->ws[WS_CELL_P].as<unsigned>();
+    jp.counts = counts;
+    jp.starts = starts;
+    jp.cursor = cursors;
+    jp.sorted = sort_p;
+    jp.start_bias = 0;
+    jq = jp;
+    jq.total = 0;
     if (!self) {
-        unsigned* cnt_q = c->ws[WS_CNT_Q].as<unsigned>();
-        unsigned* cur_q = cnt_q + ncell;
-        unsigned* start_q = c->ws[WS_START_Q].as<unsigned>();
-        SSDR_CHECK_CUDA(cudaMemsetAsync(cnt_q, 0, ncell * 4 * 2, s));
-        cell_count_kernel<<<(totalQ + 255) / 256, 256, 0, s>>>(d_q, (unsigned)Q, totalQ, items,
-                                                              c->ws[WS_CELL_Q].as<unsigned>(), cnt_q);
-        SSDR_CHECK_CUDA(cub::DeviceScan::ExclusiveSum(c->ws[WS_TEMP].p, tbytes, cnt_q, start_q, (int)ncell, s));
-        cell_scatter_kernel<<<(totalQ + 255) / 256, 256, 0, s>>>(d_q, (unsigned)Q, totalQ,
-                                                                c->ws[WS_CELL_Q].as<unsigned>(), start_q, cur_q,
-                                                                c->ws[WS_SORT_Q].as<float4>());
-        sort_q = c->ws[WS_SORT_Q].as<float4>();
+        jq.xyz = d_q;
+        jq.n = (unsigned)Q;
+        jq.total = totalQ;
+        jq.cell_of = jp.cell_of + totalP;
+        jq.counts = counts + ncell;
+        jq.starts = starts + ncell;
+        jq.cursor = cursors + ncell;
+        jq.sorted = c->ws[WS_SORT_Q].as<float4>();
+        jq.start_bias = totalP;  // the concatenated scan continues behind the points' total
     }
+    const unsigned tot = totalP + jq.total;
+    cell_count_kernel<<<(tot + 255) / 256, 256, 0, s>>>(jp, jq, items);
+    size_t tbytes = 0;
+    const int nscan = (int)((size_t)njobs * ncell);
+    SSDR_CHECK_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tbytes, counts, starts, nscan, s));
+    SSDR_TRY(c->ws[WS_TEMP].reserve(tbytes));
+    SSDR_CHECK_CUDA(cub::DeviceScan::ExclusiveSum(c->ws[WS_TEMP].p, tbytes, counts, starts, nscan, s));
+    cell_scatter_kernel<<<(tot + 255) / 256, 256, 0, s>>>(jp, jq);
+    const float4* sort_q = self ? sort_p : jq.sorted;
     SSDR_CHECK_CUDA(cudaGetLastError());
     if (K > N) SSDR_CHECK_CUDA(cudaMemsetAsync(d_out, 0, (size_t)totalQ * K * sizeof(OutT), s));
 
