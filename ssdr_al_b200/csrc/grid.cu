@@ -7,19 +7,15 @@
 //   2. origin = floor(min * (1/dl)) * dl, nX, nY (grid_subsampling.cpp:27-31)        -> setup_kernel
 //   3. key = iX + nX*iY + nX*nY*iZ with i* = floor((p-origin)/dl) in IEEE fp32, true division
 //      (grid_subsampling.cpp:53-56)                                                  -> key_kernel
-//   4. STABLE radix sort of (key, input index) over the significant key bits only    -> cub::DeviceRadixSort
-//      (library plumbing; every arithmetic kernel around it is hand written)
-//   5. segment heads -> voxel start offsets, M                                       -> cub::DeviceSelect
+//   4. STABLE LSD radix sort of (key, input index) over the significant key bits only -> prim::radix_sort_pairs
+//   5. segment heads -> exclusive scan -> voxel start offsets, M                     -> head_flag/voxel_start kernels
 //   6. one thread per voxel walks its points IN INPUT ORDER (the stable sort keeps ascending index inside a
 //      voxel), accumulating fp32 sums exactly like SampledData::update_* (grid_subsampling.h:42-79), then
 //      bary = sum * float(1.0/count), feat = sum / float(count) (grid_subsampling.cpp:87-95) and the label vote
 //      with libstdc++'s unordered_map iteration order as tie-break (grid_subsampling.cpp:97-102)  -> reduce_kernel
 // Rows come out in ascending voxel-key order (SSDR_GRID_ORDER_KEY).
-#include <cub/device/device_radix_sort.cuh>
-#include <cub/device/device_select.cuh>
-#include <cub/iterator/counting_input_iterator.cuh>
-
 #include "common.cuh"
+#include "primitives.cuh"
 
 namespace ssdr {
 namespace grid {
@@ -147,10 +143,17 @@ __global__ void key_kernel(const float* __restrict__ pts, unsigned long long N, 
     }
 }
 
-struct HeadPred {
-    const unsigned long long* keys;
-    __device__ __forceinline__ bool operator()(const unsigned& i) const { return i == 0 || keys[i] != keys[i - 1]; }
-};
+// ---- 5. voxel segments of the sorted keys ---------------------------------------------------------------------
+__global__ void head_flag_kernel(const unsigned long long* __restrict__ keys, unsigned long long N,
+                                 unsigned* __restrict__ flags) {
+    const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < N) flags[i] = (i == 0 || keys[i] != keys[i - 1]) ? 1u : 0u;
+}
+__global__ void voxel_start_kernel(const unsigned* __restrict__ flags, const unsigned* __restrict__ vid,
+                                   unsigned long long N, unsigned* __restrict__ starts) {
+    const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < N && flags[i]) starts[vid[i]] = (unsigned)i;
+}
 
 // ---- label vote: libstdc++ unordered_map<int,int> iteration order (identity hash, unique keys) ----------
 // Faithful emulation of _M_insert_unique_node / _M_rehash_aux for up to LABEL_CAP nodes.
@@ -366,17 +369,22 @@ static int run_dev(Ctx* c, cudaStream_t s, const float* d_p, const float* d_f, c
     SSDR_TRY(d2h_sync(c, &hm, meta, sizeof(Meta), s));  // sync 1: how many key bits are worth sorting
     const int key_bits = bits_for_value(hm.max_key);
 
-    cub::DoubleBuffer<KeyT> kb(keys, keys2);
-    cub::DoubleBuffer<unsigned> vb(idx, idx2);
-    size_t t1 = 0, t2 = 0;
-    SSDR_CHECK_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, t1, kb, vb, (int)N, 0, key_bits, s));
-    cub::CountingInputIterator<unsigned> counting(0);
-    HeadPred pred{keys};
-    SSDR_CHECK_CUDA(cub::DeviceSelect::If(nullptr, t2, counting, starts, &meta->M, (int)N, pred, s));
-    SSDR_TRY(c->ws[WS_TEMP].reserve(t1 > t2 ? t1 : t2));
-    SSDR_CHECK_CUDA(cub::DeviceRadixSort::SortPairs(c->ws[WS_TEMP].p, t1, kb, vb, (int)N, 0, key_bits, s));
-    pred.keys = kb.Current();
-    SSDR_CHECK_CUDA(cub::DeviceSelect::If(c->ws[WS_TEMP].p, t2, counting, starts, &meta->M, (int)N, pred, s));
+    // 4. stable radix sort over the significant bits; 5. heads -> voxel ids -> starts (M lands in meta->M)
+    SSDR_TRY(c->ws[WS_TEMP].reserve((prim::rs_scratch_words(N) + prim::scan_scratch_words(N) + 8) * sizeof(unsigned)));
+    unsigned* scratch = c->ws[WS_TEMP].as<unsigned>();
+    SSDR_CHECK_CUDA(cudaMemsetAsync(scratch, 0, (prim::rs_scratch_words(N) + prim::scan_scratch_words(N) + 8) * sizeof(unsigned), s));
+    int cur = 0;
+    SSDR_TRY(prim::radix_sort_pairs(keys, idx, keys2, idx2, N, key_bits, scratch, &cur, s));
+    const KeyT* keys_sorted = cur ? keys2 : keys;
+    const unsigned* idx_sorted = cur ? idx2 : idx;
+    unsigned* flags = reinterpret_cast<unsigned*>(cur ? keys : keys2);  // the other key buffer is free now: 8 B/pt
+    unsigned* vid = flags + N;
+    const unsigned nb = (unsigned)((N + 255) / 256);
+    head_flag_kernel<<<nb, 256, 0, s>>>(keys_sorted, N, flags);
+    SSDR_TRY(prim::exclusive_scan_u32(flags, vid, N, scratch + prim::rs_scratch_words(N),
+                                      reinterpret_cast<unsigned*>(&meta->M), s));
+    voxel_start_kernel<<<nb, 256, 0, s>>>(flags, vid, N, starts);
+    SSDR_CHECK_CUDA(cudaGetLastError());
     SSDR_TRY(d2h_sync(c, &hm, meta, sizeof(Meta), s));  // sync 2: M, to size the outputs
     const size_t M = (size_t)hm.M;
     SSDR_REQUIRE(M >= 1 && M <= N, SSDR_ERR_EMPTY, "Error");
@@ -407,7 +415,7 @@ static int run_dev(Ctx* c, cudaStream_t s, const float* d_p, const float* d_f, c
 #undef SSDR_ALLOC
     const unsigned vblocks = (unsigned)((M + 127) / 128);
 #define SSDR_REDUCE(FDV)                                                                                         \
-    reduce_kernel<FDV><<<vblocks, 128, 0, s>>>(d_p, d_f, d_c, (int)fdim, (int)ldim, kb.Current(), vb.Current(), \
+    reduce_kernel<FDV><<<vblocks, 128, 0, s>>>(d_p, d_f, d_c, (int)fdim, (int)ldim, keys_sorted, idx_sorted, \
                                                starts, N, M, h->d_p, h->d_f, h->d_c, h->d_k, h->d_n, meta)
     switch (fdim) {
         case 0: SSDR_REDUCE(0); break;

@@ -5,7 +5,7 @@
 //
 // Device pipeline (all batch items in the same launches):
 //   A. uniform cell grid per item: bbox -> cell edge from the expected K-NN radius -> counting sort of the points
-//      (and of the queries, for warp coherence) into cells.
+//      (and of the queries, for warp coherence) into cells (hand-written scan, primitives.cuh).
 //   B. main kernel, one thread per (cell-sorted) query: scan the 3x3x3 block, then Chebyshev shells, keeping the
 //      exact top-(K+1) under the order (fp32 squared distance, index) in registers as packed 64-bit keys; stop when
 //      the (K+1)-th distance is provably inside the scanned block.  Distances use the reference's operation order
@@ -13,12 +13,11 @@
 //   C. nanoflann's own order differs from (distance, index) ONLY when the top-(K+1) holds equal or almost equal
 //      distances (tree-visit order decides ties, nanoflann.hpp:72-96,1317; pruning compares differently rounded
 //      sums).  Such rows are flagged by B and re-resolved by an exact replay of the nanoflann tree (kdtree.cuh).
-#include <cub/device/device_scan.cuh>
-
 #include <vector>
 
 #include "common.cuh"
 #include "kdtree.cuh"
+#include "primitives.cuh"
 
 namespace ssdr {
 namespace knn {
@@ -349,7 +348,8 @@ static int run_dev(Ctx* c, cudaStream_t s, const float* d_pts, size_t B, size_t 
     const int njobs = self ? 1 : 2;
 
     // one zero-initialised control slab: stats | ticket | bbox encodings | counts (P,Q) | cursors (P,Q)
-    const size_t hdr_words = 16 + B * 6;
+    const size_t nscan_words = prim::scan_scratch_words((size_t)njobs * ncell);
+    const size_t hdr_words = 16 + B * 6 + nscan_words;  // stats, ticket, bbox encodings, scan scratch (zeroed)
     const size_t ctl_words = hdr_words + 2 * (size_t)njobs * ncell;
     SSDR_TRY(c->ws[WS_CNT_P].reserve(ctl_words * 4));
     SSDR_TRY(c->ws[WS_ITEMS].reserve(B * sizeof(ItemMeta)));
@@ -401,11 +401,7 @@ static int run_dev(Ctx* c, cudaStream_t s, const float* d_pts, size_t B, size_t 
     }
     const unsigned tot = totalP + jq.total;
     cell_count_kernel<<<(tot + 255) / 256, 256, 0, s>>>(jp, jq, items);
-    size_t tbytes = 0;
-    const int nscan = (int)((size_t)njobs * ncell);
-    SSDR_CHECK_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tbytes, counts, starts, nscan, s));
-    SSDR_TRY(c->ws[WS_TEMP].reserve(tbytes));
-    SSDR_CHECK_CUDA(cub::DeviceScan::ExclusiveSum(c->ws[WS_TEMP].p, tbytes, counts, starts, nscan, s));
+    SSDR_TRY(prim::exclusive_scan_u32(counts, starts, (size_t)njobs * ncell, ctl + 16 + B * 6, nullptr, s));
     cell_scatter_kernel<<<(tot + 255) / 256, 256, 0, s>>>(jp, jq);
     const float4* sort_q = self ? sort_p : jq.sorted;
     SSDR_CHECK_CUDA(cudaGetLastError());

@@ -41,7 +41,7 @@ __device__ __forceinline__ unsigned block_scan_u32(unsigned v, unsigned* s_warp,
 }
 
 // phase 1: per-tile sums; the last block to finish turns them into exclusive tile offsets (and the grand total)
-__global__ void __launch_bounds__(SCAN_THREADS) scan_sums_kernel(const unsigned* __restrict__ in, size_t n,
+static __global__ void __launch_bounds__(SCAN_THREADS) scan_sums_kernel(const unsigned* __restrict__ in, size_t n,
                                                                  unsigned* __restrict__ tile_off, unsigned ntiles,
                                                                  unsigned* __restrict__ ticket,
                                                                  unsigned* __restrict__ total_out) {
@@ -79,7 +79,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_sums_kernel(const unsigned*
 }
 
 // phase 2: exclusive scan inside each tile + tile offset
-__global__ void __launch_bounds__(SCAN_THREADS) scan_apply_kernel(const unsigned* __restrict__ in,
+static __global__ void __launch_bounds__(SCAN_THREADS) scan_apply_kernel(const unsigned* __restrict__ in,
                                                                   unsigned* __restrict__ out, size_t n,
                                                                   const unsigned* __restrict__ tile_off) {
     __shared__ unsigned s_warp[32];
@@ -124,7 +124,7 @@ constexpr int RS_BITS = 8;
 constexpr int RS_BINS = 1 << RS_BITS;
 
 // histogram of the current digit per block, stored digit-major: hist[digit * nblocks + block]
-__global__ void __launch_bounds__(RS_THREADS) rs_hist_kernel(const unsigned long long* __restrict__ keys, size_t n,
+static __global__ void __launch_bounds__(RS_THREADS) rs_hist_kernel(const unsigned long long* __restrict__ keys, size_t n,
                                                              int shift, unsigned* __restrict__ hist, unsigned nblocks) {
     __shared__ unsigned s_h[RS_BINS];
     for (int i = threadIdx.x; i < RS_BINS; i += RS_THREADS) s_h[i] = 0;
@@ -141,7 +141,7 @@ __global__ void __launch_bounds__(RS_THREADS) rs_hist_kernel(const unsigned long
 
 // stable scatter: element e of the block (blocked order: thread t owns e = t*ITEMS + k) goes to
 // offs[digit][block] + (number of earlier elements of the block with the same digit)
-__global__ void __launch_bounds__(RS_THREADS) rs_scatter_kernel(const unsigned long long* __restrict__ keys_in,
+static __global__ void __launch_bounds__(RS_THREADS) rs_scatter_kernel(const unsigned long long* __restrict__ keys_in,
                                                                 const unsigned* __restrict__ vals_in,
                                                                 unsigned long long* __restrict__ keys_out,
                                                                 unsigned* __restrict__ vals_out, size_t n, int shift,
