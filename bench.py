@@ -185,12 +185,9 @@ def run_ours(args):
         return launches
 
     def count_launches(stats):
-        # our kernels per call: bbox_init, bbox, setup_items, cell_count, cell_scatter, query (+3 for the query sort
-        # when queries != support) (+ mark_items, build, exact_query when a tie row exists); CUB scans not counted
-        n = 0
-        for kind, _, st in stats:
-            n += 6 + (3 if kind == "k1" else 0) + (3 if st["tie_rows"] else 0)
-        return n
+        # our kernels per call: bbox_setup, cell_count, scan_sums, scan_apply, cell_scatter, query
+        # (+ mark_items, build, exact_query when a tie row exists); memsets and torch's slicing copies not counted
+        return sum(6 + (3 if st["tie_rows"] else 0) for _, _, st in stats)
 
     for _ in range(max(args.warmup, 3)):
         gpu_pyramid()
