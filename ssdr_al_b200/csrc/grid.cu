@@ -13,7 +13,8 @@
 //      voxel), accumulating fp32 sums exactly like SampledData::update_* (grid_subsampling.h:42-79), then
 //      bary = sum * float(1.0/count), feat = sum / float(count) (grid_subsampling.cpp:87-95) and the label vote
 //      with libstdc++'s unordered_map iteration order as tie-break (grid_subsampling.cpp:97-102)  -> reduce_kernel
-// Rows come out in ascending voxel-key order (SSDR_GRID_ORDER_KEY).
+//   7. optional (SSDR_GRID_ORDER_REFERENCE): rows permuted into the reference's libstdc++ hash-iteration order.
+// Rows come out in ascending voxel-key order by default (SSDR_GRID_ORDER_KEY).
 #include "common.cuh"
 #include "primitives.cuh"
 
@@ -32,7 +33,7 @@ struct Meta {
 };
 
 enum { WS_META = 0, WS_PART = 1, WS_KEYS = 2, WS_KEYS2 = 3, WS_IDX = 4, WS_IDX2 = 5, WS_TEMP = 6, WS_STARTS = 7,
-       WS_IN_P = 9, WS_IN_F = 10, WS_IN_C = 11 };
+       WS_IN_P = 9, WS_IN_F = 10, WS_IN_C = 11, WS_HASH = 12, WS_CMIN = 13 };
 
 constexpr int LABEL_CAP = 64;
 constexpr int MM_BLOCK = 256;
@@ -84,12 +85,21 @@ static int bits_for_value(unsigned long long v) {  // radix bits needed to order
 
 // ---- 2. grid geometry ---------------------------------------------------------------------------------
 __global__ void setup_kernel(const float* __restrict__ partials, int nparts, float dl, Meta* meta) {
-    const int t = threadIdx.x;
+    // one warp per quantity (3 mins, 3 maxes): strided loads + shuffle reduction
+    const int t = threadIdx.x, q = t >> 5, lane = t & 31;
     __shared__ float r[6];
-    if (t < 6) {
-        float v = partials[t];
-        for (int b = 1; b < nparts; ++b) v = t < 3 ? fminf(v, partials[b * 6 + t]) : fmaxf(v, partials[b * 6 + t]);
-        r[t] = v;
+    if (q < 6) {
+        float v = q < 3 ? INFINITY : -INFINITY;
+        for (int b = lane; b < nparts; b += 32) {
+            const float x = partials[b * 6 + q];
+            v = q < 3 ? fminf(v, x) : fmaxf(v, x);
+        }
+#pragma unroll
+        for (int m = 16; m > 0; m >>= 1) {
+            const float o = __shfl_xor_sync(0xffffffffu, v, m);
+            v = q < 3 ? fminf(v, o) : fmaxf(v, o);
+        }
+        if (lane == 0) r[q] = v;
     }
     __syncthreads();
     if (t == 0) {
@@ -314,6 +324,62 @@ __global__ void reduce_kernel(const float* __restrict__ pts, const float* __rest
     out_n[v] = count;
 }
 
+// ---- 7. reference row order: libstdc++ unordered_map<size_t,...> iteration order, epoch by epoch ----------------
+// The map is rehashed through a fixed prime sequence; within one bucket count ("epoch") the list is the sequence of
+// bucket runs in REVERSE order of bucket creation, each run in REVERSE insertion order, where the epoch's insertion
+// sequence is: the previous list (a rehash re-inserts it in list order), then the new nodes (SURVEY.md A.3;
+// tools/proto_hash_order.py checks this closed form against the sequential emulation).  Each epoch is therefore an
+// atomicMin (bucket creation time) plus one stable radix sort.
+__global__ void first_index_kernel(const unsigned* __restrict__ idx_sorted, const unsigned* __restrict__ starts,
+                                   unsigned long long M, unsigned long long* __restrict__ fkey,
+                                   unsigned* __restrict__ vox) {
+    const unsigned long long v = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= M) return;
+    fkey[v] = idx_sorted[starts[v]];  // a voxel is inserted when its first point (smallest input index) arrives
+    vox[v] = (unsigned)v;
+}
+__global__ void node_key_kernel(const unsigned long long* __restrict__ vkeys, const unsigned* __restrict__ ins,
+                                unsigned long long M, unsigned long long* __restrict__ nkey) {
+    const unsigned long long r = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r < M) nkey[r] = vkeys[ins[r]];
+}
+__global__ void epoch_bucket_kernel(const unsigned long long* __restrict__ nkey, const unsigned* __restrict__ cur,
+                                    unsigned prev, unsigned hi, unsigned long long nb, unsigned* __restrict__ node,
+                                    unsigned* __restrict__ bkt, unsigned* __restrict__ cmin) {
+    const unsigned j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= hi) return;
+    const unsigned n = j < prev ? cur[j] : j;
+    const unsigned b = (unsigned)(nkey[n] % nb);
+    node[j] = n;
+    bkt[j] = b;
+    atomicMin(&cmin[b], j);
+}
+__global__ void epoch_key_kernel(const unsigned* __restrict__ bkt, const unsigned* __restrict__ cmin, unsigned hi,
+                                 int sh, unsigned long long* __restrict__ comp) {
+    const unsigned j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < hi) comp[j] = ((unsigned long long)(hi - 1 - cmin[bkt[j]]) << sh) | (unsigned long long)(hi - 1 - j);
+}
+__global__ void compose_perm_kernel(const unsigned* __restrict__ cur, const unsigned* __restrict__ ins,
+                                    unsigned long long M, unsigned* __restrict__ perm) {
+    const unsigned long long r = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r < M) perm[r] = ins[cur[r]];
+}
+template <typename T>
+__global__ void permute_rows_kernel(const T* __restrict__ in, T* __restrict__ out, const unsigned* __restrict__ perm,
+                                    unsigned long long M, int width) {
+    const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= M * (unsigned long long)width) return;
+    const unsigned long long r = i / width;
+    out[i] = in[(unsigned long long)perm[r] * width + (i - r * width)];
+}
+
+static const unsigned long long kBuckets[] = {13ull,        29ull,        59ull,        127ull,       257ull,
+                                              541ull,       1109ull,      2357ull,      5087ull,      10273ull,
+                                              20753ull,     42043ull,     85229ull,     172933ull,    351061ull,
+                                              712697ull,    1447153ull,   2938679ull,   5967347ull,   12117689ull,
+                                              24607243ull,  49969847ull,  101473717ull, 206062531ull, 418451333ull,
+                                              849749479ull, 1725587117ull, 3504151727ull};
+
 struct Handle {
     size_t M = 0, fdim = 0, ldim = 0;
     float* d_p = nullptr;
@@ -335,14 +401,93 @@ static void free_handle(Handle* h) {  // stream-ordered pool: no device-wide syn
     delete h;
 }
 
+static int bits_for_value(unsigned long long v);
+
+// Rows are in ascending-key order in the handle; permute them into the reference's hash-iteration order.
+// Reuses the sort workspaces (stream ordered after reduce_kernel): WS_KEYS/WS_KEYS2 (u64), WS_IDX/WS_IDX2 (u32).
+static int reorder_reference(Ctx* c, cudaStream_t s, Handle* h, const unsigned* idx_sorted, const unsigned* starts,
+                             size_t N, unsigned* scratch) {
+    const size_t M = h->M;
+    const unsigned mb = (unsigned)((M + 255) / 256);
+    // idx_sorted lives in WS_IDX or WS_IDX2, starts in WS_STARTS: copy what we need before those buffers are recycled
+    SSDR_TRY(c->ws[WS_HASH].reserve(M * (8 + 4 + 4 + 4 + 4)));
+    unsigned long long* nkey = c->ws[WS_HASH].as<unsigned long long>();  // [M] voxel key by insertion rank
+    unsigned* ins = reinterpret_cast<unsigned*>(nkey + M);               // [M] insertion rank -> voxel (key order)
+    unsigned* cur = ins + M;                                             // [M] list order (node = insertion rank)
+    unsigned* node = cur + M;                                            // [M] epoch sequence -> node
+    unsigned* bkt = node + M;                                            // [M]
+    unsigned long long* ka = c->ws[WS_KEYS].as<unsigned long long>();
+    unsigned long long* kb = c->ws[WS_KEYS2].as<unsigned long long>();
+    unsigned* va = c->ws[WS_IDX].as<unsigned>();
+    unsigned* vb = c->ws[WS_IDX2].as<unsigned>();
+    // 1. insertion order of the voxels = ascending first input index.  first_index_kernel reads idx_sorted/starts and
+    //    writes into the OTHER ping-pong pair, so nothing it still needs is overwritten.
+    const bool sorted_in_b = (idx_sorted == vb);
+    unsigned long long* fk = sorted_in_b ? ka : kb;
+    unsigned* fv = sorted_in_b ? va : vb;
+    first_index_kernel<<<mb, 256, 0, s>>>(idx_sorted, starts, M, fk, fv);
+    // sort (first index, voxel) -- after this the old sorted arrays are dead and both pairs are scratch
+    int curbuf = 0;
+    unsigned long long* k0 = fk;
+    unsigned* v0 = fv;
+    unsigned long long* k1 = sorted_in_b ? kb : ka;
+    unsigned* v1 = sorted_in_b ? vb : va;
+    SSDR_TRY(prim::radix_sort_pairs(k0, v0, k1, v1, M, bits_for_value(N), scratch, &curbuf, s));
+    SSDR_CHECK_CUDA(cudaMemcpyAsync(ins, curbuf ? v1 : v0, M * sizeof(unsigned), cudaMemcpyDeviceToDevice, s));
+    node_key_kernel<<<mb, 256, 0, s>>>(h->d_k, ins, M, nkey);
+    // 2. epochs
+    size_t prev = 0;
+    for (size_t e = 0; e < sizeof(kBuckets) / sizeof(kBuckets[0]) && prev < M; ++e) {
+        const unsigned long long nb = kBuckets[e];
+        const size_t hi = nb < M ? (size_t)nb : M;
+        SSDR_TRY(c->ws[WS_CMIN].reserve((size_t)nb * sizeof(unsigned)));
+        unsigned* cmin = c->ws[WS_CMIN].as<unsigned>();
+        SSDR_CHECK_CUDA(cudaMemsetAsync(cmin, 0xFF, (size_t)nb * sizeof(unsigned), s));
+        const unsigned eb = (unsigned)((hi + 255) / 256);
+        epoch_bucket_kernel<<<eb, 256, 0, s>>>(nkey, cur, (unsigned)prev, (unsigned)hi, nb, node, bkt, cmin);
+        const int sh = bits_for_value(hi);
+        epoch_key_kernel<<<eb, 256, 0, s>>>(bkt, cmin, (unsigned)hi, sh, ka);
+        SSDR_CHECK_CUDA(cudaMemcpyAsync(va, node, hi * sizeof(unsigned), cudaMemcpyDeviceToDevice, s));
+        SSDR_TRY(prim::radix_sort_pairs(ka, va, kb, vb, hi, 2 * sh, scratch, &curbuf, s));
+        SSDR_CHECK_CUDA(cudaMemcpyAsync(cur, curbuf ? vb : va, hi * sizeof(unsigned), cudaMemcpyDeviceToDevice, s));
+        prev = hi;
+    }
+    SSDR_REQUIRE(prev >= M, SSDR_ERR_UNSUPPORTED, "too many voxels for the reference-order emulation");
+    // 3. permute the rows
+    unsigned* perm = node;
+    compose_perm_kernel<<<mb, 256, 0, s>>>(cur, ins, M, perm);
+    auto permute = [&](auto** buf, int width) -> int {
+        typedef typename std::remove_pointer<typename std::remove_pointer<decltype(buf)>::type>::type T;
+        if (!*buf) return SSDR_OK;
+        T* nbuf = nullptr;
+        cudaError_t e2 = cudaMallocAsync((void**)&nbuf, M * width * sizeof(T), s);
+        if (e2 != cudaSuccess) {
+            cudaGetLastError();
+            return set_error(SSDR_ERR_NOMEM, "cudaMallocAsync failed: %s", cudaGetErrorString(e2));
+        }
+        const unsigned long long tot = (unsigned long long)M * width;
+        permute_rows_kernel<T><<<(unsigned)((tot + 255) / 256), 256, 0, s>>>(*buf, nbuf, perm, M, width);
+        cudaFreeAsync(*buf, s);
+        *buf = nbuf;
+        return SSDR_OK;
+    };
+    SSDR_TRY(permute(&h->d_p, 3));
+    SSDR_TRY(permute(&h->d_f, (int)h->fdim));
+    SSDR_TRY(permute(&h->d_c, (int)h->ldim));
+    SSDR_TRY(permute(&h->d_k, 1));
+    SSDR_TRY(permute(&h->d_n, 1));
+    SSDR_CHECK_CUDA(cudaGetLastError());
+    return SSDR_OK;
+}
+
 static int run_dev(Ctx* c, cudaStream_t s, const float* d_p, const float* d_f, const int* d_c, size_t N, size_t fdim,
                    size_t ldim, float dl, int order, size_t* M_out, void** handle) {
     typedef unsigned long long KeyT;
     SSDR_REQUIRE(d_p && M_out && handle, SSDR_ERR_INVALID, "NULL pointer");
     SSDR_REQUIRE(N >= 1, SSDR_ERR_EMPTY, "Error");
     SSDR_REQUIRE(N < 0x7FFFFFFFull, SSDR_ERR_UNSUPPORTED, "N=%zu exceeds 2^31-2 points per call", N);
-    SSDR_REQUIRE(order == SSDR_GRID_ORDER_KEY, SSDR_ERR_UNSUPPORTED,
-                 "order=REFERENCE (libstdc++ hash iteration order) is not implemented on the device yet");
+    SSDR_REQUIRE(order == SSDR_GRID_ORDER_KEY || order == SSDR_GRID_ORDER_REFERENCE, SSDR_ERR_INVALID,
+                 "order must be SSDR_GRID_ORDER_KEY or SSDR_GRID_ORDER_REFERENCE");
     SSDR_REQUIRE(dl > 0.0f, SSDR_ERR_INVALID, "sampleDl must be positive");
     if (!d_f) fdim = 0;
     if (!d_c) ldim = 0;
@@ -362,7 +507,7 @@ static int run_dev(Ctx* c, cudaStream_t s, const float* d_p, const float* d_f, c
     unsigned* starts = c->ws[WS_STARTS].as<unsigned>();
 
     minmax_kernel<<<nparts, MM_BLOCK, 0, s>>>(d_p, N, c->ws[WS_PART].as<float>());
-    setup_kernel<<<1, 32, 0, s>>>(c->ws[WS_PART].as<float>(), nparts, dl, meta);
+    setup_kernel<<<1, 192, 0, s>>>(c->ws[WS_PART].as<float>(), nparts, dl, meta);
     key_kernel<<<(unsigned)((N + 255) / 256), 256, 0, s>>>(d_p, N, meta, keys, idx);
     SSDR_CHECK_CUDA(cudaGetLastError());
     Meta hm;
@@ -437,6 +582,10 @@ static int run_dev(Ctx* c, cudaStream_t s, const float* d_p, const float* d_f, c
         if (rc != SSDR_OK) return fail(rc);
         if (hm.error == 2)
             return fail(set_error(SSDR_ERR_UNSUPPORTED, "more than %d distinct labels inside one voxel", LABEL_CAP));
+    }
+    if (order == SSDR_GRID_ORDER_REFERENCE && M > 1) {
+        int rc = reorder_reference(c, s, h, idx_sorted, starts, N, scratch);
+        if (rc != SSDR_OK) return fail(rc);
     }
     *M_out = h->M;
     *handle = h;

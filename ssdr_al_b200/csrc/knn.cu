@@ -190,19 +190,6 @@ __device__ __forceinline__ void list_insert(float (&dist)[KCAP], unsigned (&idx)
     idx[0] = p_prev ? id : idx[0];
 }
 
-template <int KCAP>
-__device__ __forceinline__ unsigned scan_range(float (&dist)[KCAP], unsigned (&idx)[KCAP],
-                                               const float4* __restrict__ spts, unsigned s, unsigned e, float qx,
-                                               float qy, float qz) {
-    for (unsigned i = s; i < e; ++i) {
-        const float4 p = __ldg(spts + i);
-        const float dx = __fsub_rn(qx, p.x), dy = __fsub_rn(qy, p.y), dz = __fsub_rn(qz, p.z);
-        const float d = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
-        if (d < dist[KCAP - 1]) list_insert<KCAP>(dist, idx, d, (unsigned)__float_as_int(p.w));
-    }
-    return e - s;
-}
-
 // conservative squared distance from coordinate v to the slab of cell c along one axis (0 inside, minus the slack
 // that covers fp32 rounding in the cell assignment)
 __device__ __forceinline__ float slab_gap(float v, float lo, float h, int c, float eps) {
@@ -211,6 +198,12 @@ __device__ __forceinline__ float slab_gap(float v, float lo, float h, int c, flo
     return g > 0.f ? g : 0.f;
 }
 
+// The kernel is WARP-SYNCHRONOUS: the 32 queries of a warp (neighbours in the cell-sorted order) walk the same
+// sequence of cell rows together; a lane whose row is pruned or shorter simply idles.  That makes warp votes legal
+// inside the scan, which is what the deferred insertion needs: a candidate that beats the lane's threshold is parked
+// in a one-deep pending slot, and the (expensive, branch-free) list insertion runs only when SOME lane would overflow
+// its slot -- then every lane with a parked candidate inserts at once.  Lanes therefore insert together instead of
+// one at a time, which is where the thread-per-query version lost two thirds of its issue slots to divergence.
 template <int KCAP, typename OutT>
 __global__ void __launch_bounds__(128) query_kernel(const float4* __restrict__ spts, const float4* __restrict__ sq,
                                                     const unsigned* __restrict__ cell_start,
@@ -218,97 +211,146 @@ __global__ void __launch_bounds__(128) query_kernel(const float4* __restrict__ s
                                                     unsigned total_q, int K, OutT* __restrict__ out,
                                                     unsigned* __restrict__ flag_count, unsigned* __restrict__ flag_list,
                                                     unsigned long long* __restrict__ evals) {
+    constexpr unsigned FULL = 0xffffffffu;
     const unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool valid = t < total_q;
+    const unsigned tq = valid ? t : total_q - 1;  // idle lanes shadow the last query and never emit
     unsigned my_evals = 0;
-    if (t < total_q) {
-        const unsigned b = t / Q;
-        const ItemMeta m = items[b];
-        const float4 q = __ldg(sq + t);
-        const unsigned qid = (unsigned)__float_as_int(q.w);
-        const int gx = m.g[0], gy = m.g[1], gz = m.g[2];
-        const int cx = cell_coord(q.x, m.lo[0], m.inv_h, gx);
-        const int cy = cell_coord(q.y, m.lo[1], m.inv_h, gy);
-        const int cz = cell_coord(q.z, m.lo[2], m.inv_h, gz);
-        const unsigned* cs = cell_start + m.cell_base;
-        float dist[KCAP];
-        unsigned idx[KCAP];
+    const unsigned b = tq / Q;
+    const ItemMeta m = items[b];
+    const float4 q = __ldg(sq + tq);
+    const unsigned qid = (unsigned)__float_as_int(q.w);
+    const int gx = m.g[0], gy = m.g[1], gz = m.g[2];
+    const int cx = cell_coord(q.x, m.lo[0], m.inv_h, gx);
+    const int cy = cell_coord(q.y, m.lo[1], m.inv_h, gy);
+    const int cz = cell_coord(q.z, m.lo[2], m.inv_h, gz);
+    const unsigned* cs = cell_start + m.cell_base;
+    float dist[KCAP];
+    unsigned idx[KCAP];
 #pragma unroll
-        for (int j = 0; j < KCAP; ++j) {
-            dist[j] = INFINITY;
-            idx[j] = 0xFFFFFFFFu;
-        }
-        // one row of cells (fixed y, z; x in [xa, xb]) is contiguous in the cell-sorted array; skip it when even its
-        // nearest possible point cannot enter the list
-        auto scan_row = [&](int z, int y, int xa, int xb) {
-            if (z < 0 || z >= gz || y < 0 || y >= gy) return;
-            xa = max(xa, 0);
-            xb = min(xb, gx - 1);
-            if (xa > xb) return;
-            const float gy_ = slab_gap(q.y, m.lo[1], m.h, y, m.eps_abs), gz_ = slab_gap(q.z, m.lo[2], m.h, z, m.eps_abs);
-            float gx_ = 0.f;
-            if (cx < xa) gx_ = slab_gap(q.x, m.lo[0], m.h, xa, m.eps_abs);
-            else if (cx > xb) gx_ = slab_gap(q.x, m.lo[0], m.h, xb, m.eps_abs);
-            const float lower = (gx_ * gx_ + gy_ * gy_ + gz_ * gz_) * 0.99999f;
-            if (!(lower < dist[KCAP - 1])) return;
-            const unsigned row = (unsigned)((z * gy + y) * gx);
-            my_evals += scan_range<KCAP>(dist, idx, spts, cs[row + xa], cs[row + xb + 1], q.x, q.y, q.z);
-        };
+    for (int j = 0; j < KCAP; ++j) {
+        dist[j] = INFINITY;
+        idx[j] = 0xFFFFFFFFu;
+    }
+    float pend_d = 0.f;
+    unsigned pend_id = 0;
+    bool has_pend = false;
+    bool done = !valid;
 
-        for (int r = 1;; ++r) {
-            // rows of the shell at Chebyshev radius r (for r == 1: the whole 3x3 block, nearest rows first: own row,
-            // the 4 face rows, the 4 diagonal rows).  One call site keeps a single copy of the insertion network.
-            const int w = 2 * r + 1, nrow = w * w;
-            for (int k = 0; k < nrow; ++k) {
-                int dz, dy;
-                if (r == 1) {
-                    dz = (int)((0x2402049u >> (3 * k)) & 7u) - 1;  // packed (offset + 1), 3 bits per entry, order:
-                    dy = (int)((0x2081281u >> (3 * k)) & 7u) - 1;  // (0,0)(0,-1)(0,1)(-1,0)(1,0)(-1,-1)(-1,1)(1,-1)(1,1)
-                } else {
-                    dz = k / w - r;
-                    dy = k % w - r;
+    for (int r = 1; __any_sync(FULL, !done); ++r) {
+        // rows of the shell at Chebyshev radius r (for r == 1: the whole 3x3 block, nearest rows first: own row, the
+        // 4 face rows, the 4 diagonal rows); r, the row order and the segment count are warp-uniform
+        const int w = 2 * r + 1, nrow = w * w;
+        for (int k = 0; k < nrow; ++k) {
+            int dz, dy;
+            if (r == 1) {
+                dz = (int)((0x2402049u >> (3 * k)) & 7u) - 1;  // packed (offset + 1), 3 bits per entry, order:
+                dy = (int)((0x2081281u >> (3 * k)) & 7u) - 1;  // (0,0)(0,-1)(0,1)(-1,0)(1,0)(-1,-1)(-1,1)(1,-1)(1,1)
+            } else {
+                dz = k / w - r;
+                dy = k % w - r;
+            }
+            const bool whole = (r == 1) || dz == -r || dz == r || dy == -r || dy == r;
+            const int nseg = whole ? 1 : 2;
+            for (int sg = 0; sg < nseg; ++sg) {
+                // this lane's slice of the cell-sorted array for the row (empty when done, outside the grid, or when
+                // even the row's nearest possible point cannot enter the list)
+                unsigned s0 = 0, len = 0;
+                if (!done) {
+                    const int z = cz + dz, y = cy + dy;
+                    int xa = whole ? cx - r : (sg == 0 ? cx - r : cx + r);
+                    int xb = whole ? cx + r : xa;
+                    xa = max(xa, 0);
+                    xb = min(xb, gx - 1);
+                    if (z >= 0 && z < gz && y >= 0 && y < gy && xa <= xb) {
+                        const float gy_ = slab_gap(q.y, m.lo[1], m.h, y, m.eps_abs);
+                        const float gz_ = slab_gap(q.z, m.lo[2], m.h, z, m.eps_abs);
+                        float gx_ = 0.f;
+                        if (cx < xa) gx_ = slab_gap(q.x, m.lo[0], m.h, xa, m.eps_abs);
+                        else if (cx > xb) gx_ = slab_gap(q.x, m.lo[0], m.h, xb, m.eps_abs);
+                        const float lower = (gx_ * gx_ + gy_ * gy_ + gz_ * gz_) * 0.99999f;
+                        if (lower < dist[KCAP - 1]) {
+                            const unsigned row = (unsigned)((z * gy + y) * gx);
+                            s0 = cs[row + xa];
+                            len = cs[row + xb + 1] - s0;
+                        }
+                    }
                 }
-                const bool whole = (r == 1) || dz == -r || dz == r || dy == -r || dy == r;
-                const int nseg = whole ? 1 : 2;
-                for (int sg = 0; sg < nseg; ++sg) {
-                    const int xa = whole ? cx - r : (sg == 0 ? cx - r : cx + r);
-                    const int xb = whole ? cx + r : xa;
-                    scan_row(cz + dz, cy + dy, xa, xb);
+                my_evals += len;
+                const unsigned maxlen = __reduce_max_sync(FULL, len);
+                for (unsigned i = 0; i < maxlen; ++i) {
+                    const bool act = i < len;
+                    float d = INFINITY;
+                    unsigned id = 0;
+                    if (act) {
+                        const float4 p = __ldg(spts + s0 + i);
+                        const float dx = __fsub_rn(q.x, p.x), dy_ = __fsub_rn(q.y, p.y), dz_ = __fsub_rn(q.z, p.z);
+                        d = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy_, dy_)), __fmul_rn(dz_, dz_));
+                        id = (unsigned)__float_as_int(p.w);
+                    }
+                    bool pass = d < dist[KCAP - 1];  // inactive lanes carry +inf
+                    if (__any_sync(FULL, pass && has_pend)) {
+                        if (has_pend) {
+                            list_insert<KCAP>(dist, idx, pend_d, pend_id);
+                            has_pend = false;
+                        }
+                        pass = d < dist[KCAP - 1];
+                    }
+                    if (pass) {
+                        pend_d = d;
+                        pend_id = id;
+                        has_pend = true;
+                    }
                 }
             }
+        }
+        // the shell is complete: settle the parked candidates, then test termination per lane
+        if (__any_sync(FULL, has_pend)) {
+            if (has_pend) {
+                if (pend_d < dist[KCAP - 1]) list_insert<KCAP>(dist, idx, pend_d, pend_id);
+                has_pend = false;
+            }
+        }
+        if (!done) {
             const int x0 = max(cx - r, 0), x1 = min(cx + r, gx - 1);
             const int y0 = max(cy - r, 0), y1 = min(cy + r, gy - 1);
             const int z0 = max(cz - r, 0), z1 = min(cz + r, gz - 1);
-            if (x0 == 0 && x1 == gx - 1 && y0 == 0 && y1 == gy - 1 && z0 == 0 && z1 == gz - 1) break;  // whole grid
-            // every unscanned point lies beyond a face of the block: lower-bound its distance
-            float R = INFINITY;
-            if (cx - r >= 0) R = fminf(R, q.x - (m.lo[0] + (float)(cx - r) * m.h));
-            if (cx + r <= gx - 1) R = fminf(R, (m.lo[0] + (float)(cx + r + 1) * m.h) - q.x);
-            if (cy - r >= 0) R = fminf(R, q.y - (m.lo[1] + (float)(cy - r) * m.h));
-            if (cy + r <= gy - 1) R = fminf(R, (m.lo[1] + (float)(cy + r + 1) * m.h) - q.y);
-            if (cz - r >= 0) R = fminf(R, q.z - (m.lo[2] + (float)(cz - r) * m.h));
-            if (cz + r <= gz - 1) R = fminf(R, (m.lo[2] + (float)(cz + r + 1) * m.h) - q.z);
-            R -= m.eps_abs;
-            // the last kept entry (rank KCAP >= K+1) must be strictly inside the guaranteed radius (+inf while fewer
-            // than KCAP candidates were seen)
-            if (R > 0.f && dist[KCAP - 1] < R * R * 0.99999f) break;
+            if (x0 == 0 && x1 == gx - 1 && y0 == 0 && y1 == gy - 1 && z0 == 0 && z1 == gz - 1) {
+                done = true;  // the block covers the whole grid
+            } else {
+                // every unscanned point lies beyond a face of the block: lower-bound its distance
+                float R = INFINITY;
+                if (cx - r >= 0) R = fminf(R, q.x - (m.lo[0] + (float)(cx - r) * m.h));
+                if (cx + r <= gx - 1) R = fminf(R, (m.lo[0] + (float)(cx + r + 1) * m.h) - q.x);
+                if (cy - r >= 0) R = fminf(R, q.y - (m.lo[1] + (float)(cy - r) * m.h));
+                if (cy + r <= gy - 1) R = fminf(R, (m.lo[1] + (float)(cy + r + 1) * m.h) - q.y);
+                if (cz - r >= 0) R = fminf(R, q.z - (m.lo[2] + (float)(cz - r) * m.h));
+                if (cz + r <= gz - 1) R = fminf(R, (m.lo[2] + (float)(cz + r + 1) * m.h) - q.z);
+                R -= m.eps_abs;
+                // the last kept entry (rank KCAP >= K+1) must be strictly inside the guaranteed radius (+inf while
+                // fewer than KCAP candidates were seen)
+                if (R > 0.f && dist[KCAP - 1] < R * R * 0.99999f) done = true;
+            }
         }
+    }
 
-        // ---- emit + tie flags
-        const int valid = (unsigned)K < N ? K : (int)N;
+    // ---- emit + tie flags
+    if (valid) {
+        const int nvalid = (unsigned)K < N ? K : (int)N;
         OutT* o = out + ((size_t)b * Q + qid) * (size_t)K;
         bool flag = false;
 #pragma unroll
         for (int j = 0; j < KCAP - 1; ++j) {
-            if (j < valid) o[j] = (OutT)idx[j];
-            if (j + 1 < valid && dist[j] == dist[j + 1]) flag = true;
+            if (j < nvalid) o[j] = (OutT)idx[j];
+            if (j + 1 < nvalid && dist[j] == dist[j + 1]) flag = true;
             // boundary tie or near tie between rank K and K+1 (pruning-rounding hazard)
             if (j + 1 == K && N > (unsigned)K && dist[j + 1] <= dist[j] * 1.00001f) flag = true;
         }
-        if (KCAP - 1 < valid) o[KCAP - 1] = (OutT)idx[KCAP - 1];
+        if (KCAP - 1 < nvalid) o[KCAP - 1] = (OutT)idx[KCAP - 1];
         if (flag) flag_list[atomicAdd(flag_count, 1u)] = b * Q + qid;
     }
 #pragma unroll
-    for (int mm = 16; mm > 0; mm >>= 1) my_evals += __shfl_xor_sync(0xffffffffu, my_evals, mm);
+    for (int mm = 16; mm > 0; mm >>= 1) my_evals += __shfl_xor_sync(FULL, my_evals, mm);
     if ((threadIdx.x & 31) == 0 && my_evals) atomicAdd(evals, (unsigned long long)my_evals);
 }
 

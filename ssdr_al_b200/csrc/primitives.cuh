@@ -101,15 +101,16 @@ static __global__ void __launch_bounds__(SCAN_THREADS) scan_apply_kernel(const u
     }
 }
 
-// scratch: ntiles + 2 words (tile offsets, ticket); `ticket` must be zero on entry (it is reset on exit).
+// scratch: [0] ticket (must be zero on entry; it is reset on exit), [2 ..] tile offsets.  The ticket sits at a FIXED
+// position so that scans of different sizes can share one scratch area.
 static inline size_t scan_scratch_words(size_t n) { return (n + SCAN_TILE - 1) / SCAN_TILE + 2; }
 
 static int exclusive_scan_u32(const unsigned* d_in, unsigned* d_out, size_t n, unsigned* d_scratch,
                               unsigned* d_total /* nullable */, cudaStream_t s) {
     if (n == 0) return SSDR_OK;
     const unsigned ntiles = (unsigned)((n + SCAN_TILE - 1) / SCAN_TILE);
-    unsigned* tile_off = d_scratch;
-    unsigned* ticket = d_scratch + ntiles;
+    unsigned* ticket = d_scratch;
+    unsigned* tile_off = d_scratch + 2;
     scan_sums_kernel<<<ntiles, SCAN_THREADS, 0, s>>>(d_in, n, tile_off, ntiles, ticket, d_total);
     scan_apply_kernel<<<ntiles, SCAN_THREADS, 0, s>>>(d_in, d_out, n, tile_off);
     SSDR_CHECK_CUDA(cudaGetLastError());
@@ -209,9 +210,9 @@ static int radix_sort_pairs(unsigned long long* keys_a, unsigned* vals_a, unsign
     if (n == 0) return SSDR_OK;
     const unsigned nblocks = (unsigned)((n + RS_TILE - 1) / RS_TILE);
     const size_t nh = (size_t)nblocks * RS_BINS;
-    unsigned* hist = d_scratch;
-    unsigned* offs = d_scratch + nh;
-    unsigned* scan_scr = offs + nh;
+    unsigned* scan_scr = d_scratch;  // scan ticket at a fixed position for every n (see scan_scratch_words)
+    unsigned* hist = d_scratch + scan_scratch_words(nh);
+    unsigned* offs = hist + nh;
     for (int shift = 0; shift < bits; shift += RS_BITS) {
         const unsigned long long* kin = *cur ? keys_b : keys_a;
         const unsigned* vin = *cur ? vals_b : vals_a;

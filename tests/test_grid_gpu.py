@@ -126,3 +126,27 @@ def test_grid_config1_full_size_properties(G):
     # subsampling the barycentres at the same cell size can only merge, never split
     p2, k2, cnt2 = G.compute(p, sampleDl=0.04, return_keys=True)
     assert len(p2) <= len(p) and cnt2.sum() == len(p)
+
+
+def test_grid_reference_row_order_golden(G, golden):
+    """order="reference": rows come out in the reference's own libstdc++ hash-iteration order -- the fixture rows,
+    produced by the unmodified reference, must be reproduced bit for bit INCLUDING their order."""
+    g = golden.grid
+    p, f, c = G.compute(g["pts"], features=g["rgb"], classes=g["lab"], sampleDl=0.1, order="reference")
+    assert p.tobytes() == g["out_pts"].tobytes()
+    assert f.tobytes() == g["out_rgb"].tobytes()
+    assert np.array_equal(c, g["out_lab"])
+    p = G.compute(g["pts"] - 3.0, sampleDl=0.04, order="reference")
+    assert p.tobytes() == g["neg_out_pts"].tobytes()
+    p, c = G.compute(g["pts"], classes=g["lab2"], sampleDl=0.25, order="reference")
+    assert p.tobytes() == g["lab2_out_pts"].tobytes() and np.array_equal(c, g["lab2_out_lab"])
+
+
+@pytest.mark.parametrize("n,dl", [(300_000, 0.04), (50_000, 0.3), (20, 0.5), (2_000_000, 0.05)])
+def test_grid_reference_row_order_vs_oracle(G, oracle, n, dl):
+    rng = np.random.default_rng(n + 1)
+    pts = _room(rng, n)
+    lab = rng.integers(0, 13, n).astype(np.uint8)
+    wp, _, wc = oracle.grid_subsample(pts, None, lab, dl, order="reference")
+    p, c = G.compute(pts, classes=lab, sampleDl=dl, order="reference")
+    assert p.shape == wp.shape and p.tobytes() == wp.tobytes() and np.array_equal(c, wc)
