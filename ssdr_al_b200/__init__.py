@@ -10,7 +10,7 @@ Python only marshals numpy arrays into the C ABI of include/ssdr_b200.h (ctypes 
 There is no CPU fallback: without the built library or without a GPU every call raises.
 """
 from . import _lib  # noqa: F401
-from . import nearest_neighbors, grid_subsampling, selection  # noqa: F401
+from . import nearest_neighbors, grid_subsampling, selection, projection  # noqa: F401
 from .selection import farthest_features_sample, kCenterGreedy  # noqa: F401
 
 __version__ = "0.1.0"
