@@ -114,6 +114,24 @@ int ssdr_grid_subsample_dev(const float* d_points, const float* d_feats, const i
                             void** handle);
 int ssdr_grid_dev_ptrs(void* handle, const float** d_points, const float** d_feats, const int32_t** d_classes);
 
+/* One large cloud over several GPUs ("voxel-layer slabs, halo-free ownership").  The grid geometry
+ * (origin, nX, nY of grid_subsampling.cpp:33-43) comes from the bounding box of the WHOLE cloud, and each rank reduces
+ * only the voxel layers [layer_lo, layer_hi) along `axis`: every voxel has exactly one owner, sees its points in input
+ * order, and so carries the same bits as in a single-GPU run.  With axis == 2 the ranks' rows concatenated in rank
+ * order are the single-GPU SSDR_GRID_ORDER_KEY result.
+ *   bbox : {minx,miny,minz,maxx,maxy,maxz} of the whole cloud (nullable = min/max of d_points, i.e. this call sees the
+ *          whole cloud and only selects its slab); axis == -1 disables the slab selection (all points take part).
+ * An empty slab succeeds with *M_out == 0.  Helpers: ssdr_grid_bbox_dev reduces a chunk's min/max (to be combined
+ * across ranks by the caller), ssdr_grid_point_layers_dev writes each point's layer index along `axis` (clamped to
+ * INT32_MAX) so the caller can histogram layers, balance the slabs and route points to their owner. */
+int ssdr_grid_subsample_slab_dev(const float* d_points, const float* d_feats, const int32_t* d_classes, size_t N,
+                                 size_t fdim, size_t ldim, float sampleDl, int order, const float* bbox, int axis,
+                                 unsigned long long layer_lo, unsigned long long layer_hi, void* stream,
+                                 size_t* M_out, void** handle);
+int ssdr_grid_bbox_dev(const float* d_points, size_t N, void* stream, float* bbox_out /* 6 floats, host */);
+int ssdr_grid_point_layers_dev(const float* d_points, size_t N, const float* bbox /* nullable */, float sampleDl,
+                               int axis, int32_t* d_layers, void* stream, unsigned long long* n_layers_out);
+
 /* ---- farthest-feature sampling / k-center greedy ---------------------------------------------------- */
 /* FPS: out[0] = first; out[s+1] = argmax_i min_{t<=s} sum_j (F[i,j]-F[out[t],j])^2, first index on ties,
  * distances in the input dtype with numpy's pairwise summation order (bit-exact picks). */

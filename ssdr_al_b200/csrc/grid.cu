@@ -29,11 +29,12 @@ struct Meta {
     int key_bits;
     int error;  // 2: more than LABEL_CAP distinct labels in one voxel
     unsigned long long max_key;  // largest key seen (key_kernel) -> number of radix bits worth sorting
+    unsigned long long n_sel;    // points taking part (all of them, or the ones inside the requested slab)
     unsigned long long M;
 };
 
 enum { WS_META = 0, WS_PART = 1, WS_KEYS = 2, WS_KEYS2 = 3, WS_IDX = 4, WS_IDX2 = 5, WS_TEMP = 6, WS_STARTS = 7,
-       WS_IN_P = 9, WS_IN_F = 10, WS_IN_C = 11, WS_HASH = 12, WS_CMIN = 13 };
+       WS_IN_P = 9, WS_IN_F = 10, WS_IN_C = 11, WS_HASH = 12, WS_CMIN = 13, WS_SEL = 14 };
 
 constexpr int LABEL_CAP = 64;
 constexpr int MM_BLOCK = 256;
@@ -117,6 +118,7 @@ __global__ void setup_kernel(const float* __restrict__ partials, int nparts, flo
         m.error = 0;
         m.key_bits = 64;
         m.max_key = 0;
+        m.n_sel = 0;
         m.M = 0;
         *meta = m;
     }
@@ -126,17 +128,20 @@ __global__ void setup_kernel(const float* __restrict__ partials, int nparts, flo
 // Keys are computed in wrapping 64-bit arithmetic exactly like the reference's size_t expression, so even
 // degenerate inputs (a point rounding to one cell below the origin, overflowing nX*nY*nZ) group identically.
 __global__ void key_kernel(const float* __restrict__ pts, unsigned long long N, Meta* __restrict__ meta,
-                           unsigned long long* __restrict__ keys, unsigned* __restrict__ idx) {
-    const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+                           unsigned long long* __restrict__ keys, unsigned* __restrict__ idx,
+                           const unsigned* __restrict__ sel /* nullable: slab members, meta->n_sel of them */) {
+    const unsigned long long j = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned long long n = sel ? meta->n_sel : N;
     unsigned long long key = 0;
-    if (i < N) {
+    if (j < n) {
+        const unsigned long long i = sel ? sel[j] : j;
         const float dl = meta->dl;
         const unsigned long long iX = f2u64(floorf(__fdiv_rn(__fsub_rn(__ldg(pts + 3 * i + 0), meta->origin[0]), dl)));
         const unsigned long long iY = f2u64(floorf(__fdiv_rn(__fsub_rn(__ldg(pts + 3 * i + 1), meta->origin[1]), dl)));
         const unsigned long long iZ = f2u64(floorf(__fdiv_rn(__fsub_rn(__ldg(pts + 3 * i + 2), meta->origin[2]), dl)));
         key = iX + meta->nX * iY + meta->nX * meta->nY * iZ;
-        keys[i] = key;
-        idx[i] = (unsigned)i;
+        keys[j] = key;
+        idx[j] = (unsigned)i;
     }
     unsigned long long mk = key;
 #pragma unroll
@@ -151,6 +156,34 @@ __global__ void key_kernel(const float* __restrict__ pts, unsigned long long N, 
         for (int w = 1; w < (int)(blockDim.x >> 5); ++w) mk = smax[w] > mk ? smax[w] : mk;
         atomicMax(&meta->max_key, mk);
     }
+}
+
+// ---- slabs: a rank of a multi-GPU job subsamples only the voxel layers [lo, hi) along one axis, with the grid
+// geometry of the WHOLE cloud, so every voxel is owned by exactly one rank and its value is bit-identical -----------
+__global__ void slab_flag_kernel(const float* __restrict__ pts, unsigned long long N, const Meta* __restrict__ meta,
+                                 int axis, unsigned long long lo, unsigned long long hi, unsigned* __restrict__ flags) {
+    const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    const unsigned long long layer =
+        f2u64(floorf(__fdiv_rn(__fsub_rn(__ldg(pts + 3 * i + axis), meta->origin[axis]), meta->dl)));
+    flags[i] = (layer >= lo && layer < hi) ? 1u : 0u;
+}
+__global__ void slab_compact_kernel(const unsigned* __restrict__ flags, const unsigned* __restrict__ pos,
+                                    unsigned long long N, unsigned* __restrict__ sel) {
+    const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < N && flags[i]) sel[pos[i]] = (unsigned)i;
+}
+__global__ void point_layers_kernel(const float* __restrict__ pts, unsigned long long N,
+                                    const Meta* __restrict__ meta, int axis, int* __restrict__ layers) {
+    const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    const unsigned long long layer =
+        f2u64(floorf(__fdiv_rn(__fsub_rn(__ldg(pts + 3 * i + axis), meta->origin[axis]), meta->dl)));
+    layers[i] = layer < 0x7FFFFFFFull ? (int)layer : 0x7FFFFFFF;
+}
+__global__ void bbox_fill_kernel(float* partials, float a0, float a1, float a2, float b0, float b1, float b2) {
+    partials[0] = a0; partials[1] = a1; partials[2] = a2;
+    partials[3] = b0; partials[4] = b1; partials[5] = b2;
 }
 
 // ---- 5. voxel segments of the sorted keys ---------------------------------------------------------------------
@@ -480,8 +513,32 @@ static int reorder_reference(Ctx* c, cudaStream_t s, Handle* h, const unsigned* 
     return SSDR_OK;
 }
 
+// min/max of the points (or the caller's bounding box of a larger cloud this chunk belongs to) -> Meta
+static int geometry(Ctx* c, cudaStream_t s, const float* d_p, size_t N, float dl, const float* bbox, Meta* meta) {
+    const int nparts = c->sm_count * 4;
+    SSDR_TRY(c->ws[WS_PART].reserve((size_t)nparts * 6 * sizeof(float)));
+    float* part = c->ws[WS_PART].as<float>();
+    if (bbox) {
+        for (int d = 0; d < 3; ++d)
+            SSDR_REQUIRE(bbox[d] <= bbox[3 + d], SSDR_ERR_INVALID, "bbox min exceeds max (or NaN) on axis %d", d);
+        bbox_fill_kernel<<<1, 1, 0, s>>>(part, bbox[0], bbox[1], bbox[2], bbox[3], bbox[4], bbox[5]);
+        setup_kernel<<<1, 192, 0, s>>>(part, 1, dl, meta);
+    } else {
+        minmax_kernel<<<nparts, MM_BLOCK, 0, s>>>(d_p, N, part);
+        setup_kernel<<<1, 192, 0, s>>>(part, nparts, dl, meta);
+    }
+    SSDR_CHECK_CUDA(cudaGetLastError());
+    return SSDR_OK;
+}
+
+struct Slab {
+    int axis = -1;  // -1: whole cloud
+    unsigned long long lo = 0, hi = 0;
+};
+
 static int run_dev(Ctx* c, cudaStream_t s, const float* d_p, const float* d_f, const int* d_c, size_t N, size_t fdim,
-                   size_t ldim, float dl, int order, size_t* M_out, void** handle) {
+                   size_t ldim, float dl, int order, size_t* M_out, void** handle, Slab slab = Slab(),
+                   const float* bbox = nullptr) {
     typedef unsigned long long KeyT;
     SSDR_REQUIRE(d_p && M_out && handle, SSDR_ERR_INVALID, "NULL pointer");
     SSDR_REQUIRE(N >= 1, SSDR_ERR_EMPTY, "Error");
@@ -491,9 +548,7 @@ static int run_dev(Ctx* c, cudaStream_t s, const float* d_p, const float* d_f, c
     SSDR_REQUIRE(dl > 0.0f, SSDR_ERR_INVALID, "sampleDl must be positive");
     if (!d_f) fdim = 0;
     if (!d_c) ldim = 0;
-    const int nparts = c->sm_count * 4;
     SSDR_TRY(c->ws[WS_META].reserve(sizeof(Meta)));
-    SSDR_TRY(c->ws[WS_PART].reserve((size_t)nparts * 6 * sizeof(float)));
     SSDR_TRY(c->ws[WS_KEYS].reserve(N * sizeof(KeyT)));
     SSDR_TRY(c->ws[WS_KEYS2].reserve(N * sizeof(KeyT)));
     SSDR_TRY(c->ws[WS_IDX].reserve(N * sizeof(unsigned)));
@@ -506,18 +561,43 @@ static int run_dev(Ctx* c, cudaStream_t s, const float* d_p, const float* d_f, c
     unsigned* idx2 = c->ws[WS_IDX2].as<unsigned>();
     unsigned* starts = c->ws[WS_STARTS].as<unsigned>();
 
-    minmax_kernel<<<nparts, MM_BLOCK, 0, s>>>(d_p, N, c->ws[WS_PART].as<float>());
-    setup_kernel<<<1, 192, 0, s>>>(c->ws[WS_PART].as<float>(), nparts, dl, meta);
-    key_kernel<<<(unsigned)((N + 255) / 256), 256, 0, s>>>(d_p, N, meta, keys, idx);
-    SSDR_CHECK_CUDA(cudaGetLastError());
-    Meta hm;
-    SSDR_TRY(d2h_sync(c, &hm, meta, sizeof(Meta), s));  // sync 1: how many key bits are worth sorting
-    const int key_bits = bits_for_value(hm.max_key);
-
-    // 4. stable radix sort over the significant bits; 5. heads -> voxel ids -> starts (M lands in meta->M)
     SSDR_TRY(c->ws[WS_TEMP].reserve((prim::rs_scratch_words(N) + prim::scan_scratch_words(N) + 8) * sizeof(unsigned)));
     unsigned* scratch = c->ws[WS_TEMP].as<unsigned>();
     SSDR_CHECK_CUDA(cudaMemsetAsync(scratch, 0, (prim::rs_scratch_words(N) + prim::scan_scratch_words(N) + 8) * sizeof(unsigned), s));
+    SSDR_TRY(geometry(c, s, d_p, N, dl, bbox, meta));
+    const unsigned* sel = nullptr;
+    if (slab.axis >= 0) {  // members of the slab, in input order (stable compaction)
+        SSDR_REQUIRE(slab.axis < 3 && slab.lo <= slab.hi, SSDR_ERR_INVALID, "bad slab");
+        SSDR_TRY(c->ws[WS_SEL].reserve(N * sizeof(unsigned)));
+        unsigned* flags = reinterpret_cast<unsigned*>(keys2);  // free until the sort
+        unsigned* pos = flags + N;
+        const unsigned nb0 = (unsigned)((N + 255) / 256);
+        slab_flag_kernel<<<nb0, 256, 0, s>>>(d_p, N, meta, slab.axis, slab.lo, slab.hi, flags);
+        SSDR_TRY(prim::exclusive_scan_u32(flags, pos, N, scratch + prim::rs_scratch_words(N),
+                                          reinterpret_cast<unsigned*>(&meta->n_sel), s));
+        slab_compact_kernel<<<nb0, 256, 0, s>>>(flags, pos, N, c->ws[WS_SEL].as<unsigned>());
+        sel = c->ws[WS_SEL].as<unsigned>();
+    }
+    key_kernel<<<(unsigned)((N + 255) / 256), 256, 0, s>>>(d_p, N, meta, keys, idx, sel);
+    SSDR_CHECK_CUDA(cudaGetLastError());
+    Meta hm;
+    SSDR_TRY(d2h_sync(c, &hm, meta, sizeof(Meta), s));  // sync 1: how many key bits are worth sorting (and slab size)
+    const int key_bits = bits_for_value(hm.max_key);
+    if (sel) {
+        N = (size_t)hm.n_sel;  // everything below works on the slab's points only
+        if (N == 0) {          // an empty slab is a valid shard: zero rows
+            Handle* h0 = new Handle();
+            h0->stream = s;
+            h0->device = c->device;
+            h0->fdim = fdim;
+            h0->ldim = ldim;
+            *M_out = 0;
+            *handle = h0;
+            return SSDR_OK;
+        }
+    }
+
+    // 4. stable radix sort over the significant bits; 5. heads -> voxel ids -> starts (M lands in meta->M)
     int cur = 0;
     SSDR_TRY(prim::radix_sort_pairs(keys, idx, keys2, idx2, N, key_bits, scratch, &cur, s));
     const KeyT* keys_sorted = cur ? keys2 : keys;
@@ -606,6 +686,63 @@ int ssdr_grid_subsample_dev(const float* d_points, const float* d_feats, const i
     SSDR_TRY(get_ctx(&c));
     return grid::run_dev(c, (cudaStream_t)stream, d_points, d_feats, d_classes, N, fdim, ldim,
                          sampleDl, order, M_out, handle);
+}
+
+int ssdr_grid_subsample_slab_dev(const float* d_points, const float* d_feats, const int32_t* d_classes, size_t N,
+                                 size_t fdim, size_t ldim, float sampleDl, int order, const float* bbox, int axis,
+                                 unsigned long long layer_lo, unsigned long long layer_hi, void* stream,
+                                 size_t* M_out, void** handle) {
+    Ctx* c;
+    SSDR_TRY(get_ctx(&c));
+    SSDR_REQUIRE(axis >= -1 && axis <= 2, SSDR_ERR_INVALID, "axis must be -1 (no slab), 0, 1 or 2");
+    SSDR_REQUIRE(order == SSDR_GRID_ORDER_KEY || (axis < 0 && !bbox), SSDR_ERR_UNSUPPORTED,
+                 "the reference's hash-iteration order is defined for a whole cloud only; slabs come in key order");
+    grid::Slab slab;
+    slab.axis = axis;
+    slab.lo = layer_lo;
+    slab.hi = layer_hi;
+    return grid::run_dev(c, (cudaStream_t)stream, d_points, d_feats, d_classes, N, fdim, ldim, sampleDl, order,
+                         M_out, handle, slab, bbox);
+}
+
+int ssdr_grid_bbox_dev(const float* d_points, size_t N, void* stream, float* bbox_out) {
+    SSDR_REQUIRE(d_points && bbox_out, SSDR_ERR_INVALID, "NULL pointer");
+    SSDR_REQUIRE(N >= 1, SSDR_ERR_EMPTY, "Error");
+    Ctx* c;
+    SSDR_TRY(get_ctx(&c));
+    cudaStream_t s = (cudaStream_t)stream;
+    SSDR_TRY(c->ws[grid::WS_META].reserve(sizeof(grid::Meta)));
+    grid::Meta* meta = c->ws[grid::WS_META].as<grid::Meta>();
+    SSDR_TRY(grid::geometry(c, s, d_points, N, 1.0f, nullptr, meta));
+    grid::Meta hm;
+    SSDR_TRY(d2h_sync(c, &hm, meta, sizeof(grid::Meta), s));
+    for (int d = 0; d < 3; ++d) {
+        bbox_out[d] = hm.mn[d];
+        bbox_out[3 + d] = hm.mx[d];
+    }
+    return SSDR_OK;
+}
+
+int ssdr_grid_point_layers_dev(const float* d_points, size_t N, const float* bbox, float sampleDl, int axis,
+                               int32_t* d_layers, void* stream, unsigned long long* n_layers_out) {
+    SSDR_REQUIRE(d_points && d_layers, SSDR_ERR_INVALID, "NULL pointer");
+    SSDR_REQUIRE(N >= 1, SSDR_ERR_EMPTY, "Error");
+    SSDR_REQUIRE(axis >= 0 && axis <= 2, SSDR_ERR_INVALID, "axis must be 0, 1 or 2");
+    SSDR_REQUIRE(sampleDl > 0.0f, SSDR_ERR_INVALID, "sampleDl must be positive");
+    Ctx* c;
+    SSDR_TRY(get_ctx(&c));
+    cudaStream_t s = (cudaStream_t)stream;
+    SSDR_TRY(c->ws[grid::WS_META].reserve(sizeof(grid::Meta)));
+    grid::Meta* meta = c->ws[grid::WS_META].as<grid::Meta>();
+    SSDR_TRY(grid::geometry(c, s, d_points, N, sampleDl, bbox, meta));
+    grid::point_layers_kernel<<<(unsigned)((N + 255) / 256), 256, 0, s>>>(d_points, N, meta, axis, d_layers);
+    SSDR_CHECK_CUDA(cudaGetLastError());
+    if (n_layers_out) {
+        grid::Meta hm;
+        SSDR_TRY(d2h_sync(c, &hm, meta, sizeof(grid::Meta), s));
+        *n_layers_out = axis == 0 ? hm.nX : axis == 1 ? hm.nY : hm.nZ;
+    }
+    return SSDR_OK;
 }
 
 int ssdr_grid_subsample(const float* points, const float* feats, const int32_t* classes, size_t N, size_t fdim,

@@ -82,6 +82,8 @@ struct Tree {
     unsigned* gbar;        // [MAX_GROUP_LEVELS*G] group barrier counters (one per level and node slot), zeroed per build
     unsigned* gred;        // [MAX_GROUP_LEVELS*G*8] group reductions: ~min xyz, max xyz, max(left cut coord), ~min(right)
     unsigned* gpart;       // [G*2*G*2] per node slot, per sweep, per member CTA: (true count, false count)
+    unsigned* root_red;    // [B*8] root bbox reduction (order-preserving atomics, identity 0) + ticket, zeroed per build
+    const unsigned* n_flag; // device count of flagged rows (nullptr = build unconditionally)
     unsigned* error;       // bit 0: node capacity, bit 1: level cap, bit 2: DFS stack, bit 3: list capacity
     const unsigned char* item_needed;  // [B] build only where a flagged row lives (nullptr = all)
     unsigned long long* tstamps;       // [16] optional %globaltimer marks (diagnostics; nullptr = off)
@@ -1003,71 +1005,87 @@ __global__ void __launch_bounds__(BT, 1) build_kernel(const float* __restrict__ 
     unsigned phase = 0;
     mark(nullptr, t.tstamps, 0);
 
-    // ---- roots: pp = (point, identity index) (init_vind :1232-1238), data bbox (computeBoundingBox :1241-1263)
-    for (unsigned b = blockIdx.x; b < t.B; b += gridDim.x) {
-        if (t.item_needed && !t.item_needed[b]) continue;
-        const float* pts = pts_all + (size_t)b * t.N * 3;
-        float4* pp = t.pp + (size_t)b * t.N;
-        float mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
-        for (unsigned i = tid; i < t.N; i += BT) {
-            float4 v;
-            v.x = __ldg(pts + 3 * (size_t)i);
-            v.y = __ldg(pts + 3 * (size_t)i + 1);
-            v.z = __ldg(pts + 3 * (size_t)i + 2);
-            v.w = __uint_as_float(i);
-            pp[i] = v;
-            mn[0] = fminf(mn[0], v.x);
-            mx[0] = fmaxf(mx[0], v.x);
-            mn[1] = fminf(mn[1], v.y);
-            mx[1] = fmaxf(mx[1], v.y);
-            mn[2] = fminf(mn[2], v.z);
-            mx[2] = fmaxf(mx[2], v.z);
-        }
-        __syncthreads();
-#pragma unroll
-        for (int d = 0; d < 3; ++d) {
-#pragma unroll
-            for (int m = 16; m > 0; m >>= 1) {
-                mn[d] = fminf(mn[d], __shfl_xor_sync(0xffffffffu, mn[d], m));
-                mx[d] = fmaxf(mx[d], __shfl_xor_sync(0xffffffffu, mx[d], m));
+    // the whole tie path is enqueued without knowing whether any row was flagged: nothing to do in that case
+    if (t.n_flag && __ldcg(t.n_flag) == 0) return;
+
+    // ---- roots: pp = (point, identity index) (init_vind :1232-1238), data bbox (computeBoundingBox :1241-1263).
+    // kroot CTAs share one item; the last of them to finish (ticket) writes the root record and queues it.
+    {
+        const unsigned kroot = max(1u, gridDim.x / t.B);
+        for (unsigned w0 = blockIdx.x; w0 < t.B * kroot; w0 += gridDim.x) {
+            const unsigned b = w0 / kroot, sl = w0 % kroot;
+            if (t.item_needed && !t.item_needed[b]) continue;
+            const float* pts = pts_all + (size_t)b * t.N * 3;
+            float4* pp = t.pp + (size_t)b * t.N;
+            const unsigned len = (t.N + kroot - 1) / kroot;
+            const unsigned a = min(sl * len, t.N), e = min(a + len, t.N);
+            float mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
+            for (unsigned i = a + tid; i < e; i += BT) {
+                float4 v;
+                v.x = __ldg(pts + 3 * (size_t)i);
+                v.y = __ldg(pts + 3 * (size_t)i + 1);
+                v.z = __ldg(pts + 3 * (size_t)i + 2);
+                v.w = __uint_as_float(i);
+                pp[i] = v;
+                mn[0] = fminf(mn[0], v.x);
+                mx[0] = fmaxf(mx[0], v.x);
+                mn[1] = fminf(mn[1], v.y);
+                mx[1] = fmaxf(mx[1], v.y);
+                mn[2] = fminf(mn[2], v.z);
+                mx[2] = fmaxf(mx[2], v.z);
             }
-            if (lane == 0) {
-                s_red[d * NW + warp] = mn[d];
-                s_red[(3 + d) * NW + warp] = mx[d];
-            }
-        }
-        __syncthreads();
-        if (tid == 0) {
-            const unsigned g = b * t.cap;
+            __syncthreads();
+#pragma unroll
             for (int d = 0; d < 3; ++d) {
-                float a = s_red[d * NW], c = s_red[(3 + d) * NW];
-                for (int w = 1; w < NW; ++w) {
-                    a = fminf(a, s_red[d * NW + w]);
-                    c = fmaxf(c, s_red[(3 + d) * NW + w]);
+#pragma unroll
+                for (int m = 16; m > 0; m >>= 1) {
+                    mn[d] = fminf(mn[d], __shfl_xor_sync(0xffffffffu, mn[d], m));
+                    mx[d] = fmaxf(mx[d], __shfl_xor_sync(0xffffffffu, mx[d], m));
                 }
-                t.nlo[(size_t)g * 3 + d] = a;
-                t.nhi[(size_t)g * 3 + d] = c;
-                t.root_lo[b * 3 + d] = a;
-                t.root_hi[b * 3 + d] = c;
+                if (lane == 0) {
+                    s_red[d * NW + warp] = mn[d];
+                    s_red[(3 + d) * NW + warp] = mx[d];
+                }
             }
-            NodeRec root;
-            root.c1 = root.c2 = -1;
-            root.feat = 0;
-            root.pad = 0;
-            root.divlow = root.divhigh = 0.f;
-            root.l = 0;
-            root.r = t.N;
-            t.nodes[g] = root;
-            t.node_count[b] = 1;
-            if (t.N > (unsigned)MED_MAX) {
-                const unsigned pos = atomicAdd(&t.list_cnt[0], 1u);
-                t.list[pos] = g;
-            } else if (t.N > (unsigned)LEAF) {
-                const unsigned pos = atomicAdd(&t.list_cnt[MAX_LEVELS + 1], 1u);
-                t.sublist[pos] = g;
+            __syncthreads();
+            unsigned* rr = t.root_red + (size_t)b * 8;  // [0..2] ~ord(min), [3..5] ord(max), [6] ticket
+            if (tid < 6) {
+                float v = s_red[tid * NW];
+                for (int w = 1; w < NW; ++w) v = tid < 3 ? fminf(v, s_red[tid * NW + w]) : fmaxf(v, s_red[tid * NW + w]);
+                if (tid < 3 && v != INFINITY) atomicMax(&rr[tid], ~f2ord_u(v));
+                if (tid >= 3 && v != -INFINITY) atomicMax(&rr[tid], f2ord_u(v));
             }
+            __threadfence();
+            __syncthreads();
+            if (tid == 0 && atomicAdd(&rr[6], 1u) == kroot - 1) {
+                __threadfence();
+                const unsigned g = b * t.cap;
+                for (int d = 0; d < 3; ++d) {
+                    const float lo_ = ord2f_u(~__ldcg(&rr[d])), hi_ = ord2f_u(__ldcg(&rr[3 + d]));
+                    t.nlo[(size_t)g * 3 + d] = lo_;
+                    t.nhi[(size_t)g * 3 + d] = hi_;
+                    t.root_lo[b * 3 + d] = lo_;
+                    t.root_hi[b * 3 + d] = hi_;
+                }
+                NodeRec root;
+                root.c1 = root.c2 = -1;
+                root.feat = 0;
+                root.pad = 0;
+                root.divlow = root.divhigh = 0.f;
+                root.l = 0;
+                root.r = t.N;
+                t.nodes[g] = root;
+                t.node_count[b] = 1;
+                if (t.N > (unsigned)MED_MAX) {
+                    const unsigned pos = atomicAdd(&t.list_cnt[0], 1u);
+                    t.list[pos] = g;
+                } else if (t.N > (unsigned)LEAF) {
+                    const unsigned pos = atomicAdd(&t.list_cnt[MAX_LEVELS + 1], 1u);
+                    t.sublist[pos] = g;
+                }
+            }
+            __syncthreads();
         }
-        __syncthreads();
     }
     grid_sync(t.barrier, phase);
     mark(nullptr, t.tstamps, 1);
@@ -1097,10 +1115,11 @@ __global__ void __launch_bounds__(BT, 1) build_kernel(const float* __restrict__ 
     if (t.tstamps && threadIdx.x == 0) atomicMax(&t.tstamps[12], gtimer());  // last CTA's end
 }
 
-__global__ void mark_items_kernel(const unsigned* __restrict__ flag_list, unsigned n_flag, unsigned Q,
-                                  unsigned char* __restrict__ item_needed) {
-    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n_flag) item_needed[flag_list[i] / Q] = 1;
+__global__ void mark_items_kernel(const unsigned* __restrict__ flag_list, const unsigned* __restrict__ n_flag_ptr,
+                                  unsigned Q, unsigned char* __restrict__ item_needed) {
+    const unsigned n_flag = *n_flag_ptr;
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n_flag; i += gridDim.x * blockDim.x)
+        item_needed[flag_list[i] / Q] = 1;
 }
 
 __device__ __forceinline__ NodeRec load_node(const NodeRec* p) {
@@ -1125,10 +1144,16 @@ __device__ __forceinline__ NodeRec load_node(const NodeRec* p) {
 template <typename OutT>
 __global__ void __launch_bounds__(32) exact_query_kernel(const float* __restrict__ q_all, const Tree t, unsigned Q,
                                                          int K, const unsigned* __restrict__ flag_list,
-                                                         unsigned n_flag, OutT* __restrict__ out, int per_warp) {
+                                                         const unsigned* __restrict__ n_flag_ptr,
+                                                         OutT* __restrict__ out) {
+    // persistent grid over the flagged rows: with few rows each query gets a warp to itself (walked by lane 0),
+    // with many rows (duplicate-heavy clouds) every thread takes rows
+    const unsigned n_flag = *n_flag_ptr;
+    const bool per_warp = n_flag <= gridDim.x;
     if (per_warp && threadIdx.x != 0) return;
-    const unsigned f = per_warp ? blockIdx.x : blockIdx.x * blockDim.x + threadIdx.x;
-    if (f >= n_flag) return;
+    const unsigned f0 = per_warp ? blockIdx.x : blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned fstride = per_warp ? gridDim.x : gridDim.x * blockDim.x;
+  for (unsigned f = f0; f < n_flag; f += fstride) {
     const unsigned row = flag_list[f];
     const unsigned b = row / Q;
     const float4* pp = t.pp + (size_t)b * t.N;
@@ -1236,6 +1261,7 @@ __global__ void __launch_bounds__(32) exact_query_kernel(const float* __restrict
     }
     OutT* o = out + (size_t)row * K;
     for (int jj = 0; jj < count; ++jj) o[jj] = (OutT)ri[jj];
+  }
 }
 
 enum { TW_BASE = 16 };  // workspace slots TW_BASE.. are owned by this header
@@ -1247,7 +1273,7 @@ static int alloc_tree(Ctx* c, cudaStream_t s, size_t B, size_t N, Tree* out) {
     SSDR_TRY(c->ws[TW_BASE + 0].reserve(B * N * (sizeof(float4) + 4 * sizeof(unsigned))));
     SSDR_TRY(c->ws[TW_BASE + 1].reserve(B * cap * (sizeof(NodeRec) + 6 * sizeof(float))));
     SSDR_TRY(c->ws[TW_BASE + 2].reserve(3 * lcap * sizeof(unsigned)));
-    const size_t ctl_words = 6 * B + B + (size_t)(MAX_LEVELS + 2) + 8 + (B + 3) / 4 + 4;
+    const size_t ctl_words = 6 * B + B + (size_t)(MAX_LEVELS + 2) + 8 + (B + 3) / 4 + 4 + 8 * B;
     SSDR_TRY(c->ws[TW_BASE + 3].reserve(ctl_words * sizeof(unsigned)));
     const size_t G = (size_t)c->sm_count;
     const size_t grp_words = (size_t)MAX_GROUP_LEVELS * G * 9 + G * 2 * G * 2;
@@ -1280,6 +1306,8 @@ static int alloc_tree(Ctx* c, cudaStream_t s, size_t B, size_t N, Tree* out) {
     t.gred = t.gbar + (size_t)MAX_GROUP_LEVELS * G;
     t.gpart = t.gred + (size_t)MAX_GROUP_LEVELS * G * 8;
     SSDR_CHECK_CUDA(cudaMemsetAsync(t.gbar, 0, (size_t)MAX_GROUP_LEVELS * G * 9 * sizeof(unsigned), s));
+    t.root_red = t.error + 4 + (B + 3) / 4 + 1;
+    t.n_flag = nullptr;
     t.item_needed = nullptr;
     t.tstamps = nullptr;
     *out = t;
@@ -1309,25 +1337,33 @@ static int check_tree_error(Ctx* c, cudaStream_t s, const Tree& t) {
     return SSDR_OK;
 }
 
-// Build the trees of the items that own flagged rows, then overwrite those rows with nanoflann's exact answer.
+// Enqueue the whole tie path behind the main kernel WITHOUT a host round trip: mark the items that own flagged rows,
+// build their trees, overwrite the flagged rows with nanoflann's exact answer.  Every kernel reads the flagged-row
+// count on the device and returns at once when it is zero.  The caller checks t_out->error after its final sync.
 template <typename OutT>
-static int resolve_flagged(Ctx* c, cudaStream_t s, const float* d_pts, size_t B, size_t N, const float* d_q, size_t Q,
-                           size_t K, OutT* d_out, const unsigned* flag_list, unsigned n_flag,
-                           unsigned long long* builds, cudaEvent_t ev_mid = nullptr) {
+static int enqueue_tie_path(Ctx* c, cudaStream_t s, const float* d_pts, size_t B, size_t N, const float* d_q, size_t Q,
+                            size_t K, OutT* d_out, const unsigned* flag_list, const unsigned* d_flag_count,
+                            Tree* t_out, cudaEvent_t ev_mid = nullptr) {
     SSDR_REQUIRE(K <= (size_t)MAX_K, SSDR_ERR_UNSUPPORTED, "K=%zu > %d in the exact tie path", K, MAX_K);
     Tree t;
     SSDR_TRY(alloc_tree(c, s, B, N, &t));
     unsigned char* needed = tree_needed_flags(t);
     t.item_needed = needed;
-    mark_items_kernel<<<(n_flag + 255) / 256, 256, 0, s>>>(flag_list, n_flag, (unsigned)Q, needed);
+    t.n_flag = d_flag_count;
+    mark_items_kernel<<<64, 256, 0, s>>>(flag_list, d_flag_count, (unsigned)Q, needed);
     SSDR_TRY(launch_build(c, s, d_pts, t));
     if (ev_mid) SSDR_CHECK_CUDA(cudaEventRecord(ev_mid, s));
-    const int per_warp = n_flag <= 8192u;
-    exact_query_kernel<OutT><<<per_warp ? n_flag : (n_flag + 31) / 32, 32, 0, s>>>(d_q, t, (unsigned)Q, (int)K,
-                                                                                  flag_list, n_flag, d_out, per_warp);
+    exact_query_kernel<OutT><<<(unsigned)c->sm_count * 16, 32, 0, s>>>(d_q, t, (unsigned)Q, (int)K, flag_list,
+                                                                       d_flag_count, d_out);
     SSDR_CHECK_CUDA(cudaGetLastError());
-    SSDR_TRY(check_tree_error(c, s, t));
-    if (builds) *builds = B;  // upper bound; items without flagged rows are skipped inside the kernel
+    *t_out = t;
+    return SSDR_OK;
+}
+
+static int tree_error_to_status(unsigned h_err) {
+    SSDR_REQUIRE(h_err == 0, SSDR_ERR_UNSUPPORTED,
+                 "exact tie path gave up (flags %u: 1 node capacity, 2 more than %d tree levels, 4 search stack deeper "
+                 "than %d, 8 work list capacity)", h_err, MAX_LEVELS, MAX_DEPTH);
     return SSDR_OK;
 }
 

@@ -464,17 +464,31 @@ static int run_dev(Ctx* c, cudaStream_t s, const float* d_pts, size_t B, size_t 
     SSDR_CHECK_CUDA(cudaGetLastError());
     if (stats) SSDR_CHECK_CUDA(cudaEventRecord(c->tev[2], s));
 
-    // ---- C: exact nanoflann replay of the flagged rows
+    // ---- C: exact nanoflann replay of the flagged rows.  With K >= 8 and thousands of queries some row is flagged
+    // almost surely (boundary near-ties alone hit ~1.5e-5*K of the rows), so the tie path is enqueued right behind
+    // the main kernel without a host round trip (its kernels return at once if the device-side count is zero).
+    // Otherwise ties are rare: read the count first and skip the (cooperative, whole-GPU) launch when it is zero.
+    kdtree::Tree tree;
+    tree.error = nullptr;
     DevStats hs;
-    SSDR_TRY(d2h_sync(c, &hs, dstats, sizeof(DevStats), s));
-    unsigned long long builds = 0;
-    if (hs.flag_count > 0) {
-        SSDR_TRY((kdtree::resolve_flagged<OutT>(c, s, d_pts, B, N, d_q, Q, K, d_out, flag_list, hs.flag_count, &builds,
-                                                stats ? c->tev[4] : nullptr)));
+    unsigned h_err = 0;
+    const bool speculate = K >= 8 && totalQ >= 4096;
+    if (!speculate) {
+        SSDR_TRY(d2h_sync(c, &hs, dstats, sizeof(DevStats), s));
+        if (hs.flag_count)
+            SSDR_TRY((kdtree::enqueue_tie_path<OutT>(c, s, d_pts, B, N, d_q, Q, K, d_out, flag_list, &dstats->flag_count,
+                                                     &tree, stats ? c->tev[4] : nullptr)));
+    } else {
+        SSDR_TRY((kdtree::enqueue_tie_path<OutT>(c, s, d_pts, B, N, d_q, Q, K, d_out, flag_list, &dstats->flag_count,
+                                                 &tree, stats ? c->tev[4] : nullptr)));
     }
+    if (stats) SSDR_CHECK_CUDA(cudaEventRecord(c->tev[3], s));
+    if (speculate) SSDR_CHECK_CUDA(cudaMemcpyAsync(&hs, dstats, sizeof(DevStats), cudaMemcpyDeviceToHost, s));
+    if (tree.error) SSDR_CHECK_CUDA(cudaMemcpyAsync(&h_err, tree.error, sizeof(unsigned), cudaMemcpyDeviceToHost, s));
+    SSDR_CHECK_CUDA(cudaStreamSynchronize(s));
+    SSDR_TRY(kdtree::tree_error_to_status(h_err));
+    const unsigned long long builds = hs.flag_count ? B : 0;
     if (stats) {
-        SSDR_CHECK_CUDA(cudaEventRecord(c->tev[3], s));
-        SSDR_CHECK_CUDA(cudaStreamSynchronize(s));
         float ms = 0.f;
         SSDR_CHECK_CUDA(cudaEventElapsedTime(&ms, c->tev[0], c->tev[1]));
         stats->grid_build_ms = ms;
@@ -564,7 +578,11 @@ int ssdr_knn_debug_build_timing(const float* points, size_t B, size_t npts, uint
         SSDR_CHECK_CUDA(cudaMemsetAsync(d_marks, 0, 16 * sizeof(unsigned long long), s));
         t.tstamps = d_marks;
         SSDR_TRY(kdtree::launch_build(c, s, c->ws[knn::WS_IN_P].as<float>(), t));
-        SSDR_TRY(kdtree::check_tree_error(c, s, t));
+        {
+            unsigned h_err2 = 0;
+            SSDR_TRY(d2h_sync(c, &h_err2, t.error, sizeof(unsigned), s));
+            SSDR_TRY(kdtree::tree_error_to_status(h_err2));
+        }
     }
     return d2h_sync(c, marks16, d_marks, 16 * sizeof(unsigned long long), s);
 }
@@ -581,7 +599,11 @@ int ssdr_knn_debug_tree(const float* points, size_t npts, uint32_t* vind_out, ui
     kdtree::Tree t;
     SSDR_TRY(kdtree::alloc_tree(c, s, 1, npts, &t));
     SSDR_TRY(kdtree::launch_build(c, s, c->ws[knn::WS_IN_P].as<float>(), t));
-    SSDR_TRY(kdtree::check_tree_error(c, s, t));
+    {
+            unsigned h_err2 = 0;
+            SSDR_TRY(d2h_sync(c, &h_err2, t.error, sizeof(unsigned), s));
+            SSDR_TRY(kdtree::tree_error_to_status(h_err2));
+        }
     SSDR_TRY(d2h_sync(c, n_nodes_out, t.node_count, sizeof(unsigned), s));
     const size_t nn = *n_nodes_out;
     SSDR_REQUIRE(nn <= t.cap, SSDR_ERR_CUDA, "node count %zu exceeds capacity", nn);

@@ -32,33 +32,69 @@ def knn_batch(pts, queries, K, out=None, want_stats=False, int32=False):
     return out
 
 
-def grid_subsample(points, features=None, classes=None, sampleDl=0.1):
-    """points (N,3) f32, features (N,fdim) f32, classes (N,ldim) i32 cuda tensors -> tuple of cuda tensors."""
+def grid_subsample(points, features=None, classes=None, sampleDl=0.1, bbox=None, slab=None, return_keys=False):
+    """points (N,3) f32, features (N,fdim) f32, classes (N,ldim) i32 cuda tensors -> tuple of cuda tensors.
+
+    bbox: 6 floats (min xyz, max xyz) of the larger cloud these points belong to (default: their own min/max).
+    slab: (axis, layer_lo, layer_hi) -- reduce only the voxel layers [lo, hi) along `axis` (multi-GPU ownership).
+    return_keys: also return (keys uint64, counts int32) as numpy arrays."""
     N = points.shape[0]
     fdim = features.shape[1] if features is not None else 0
     ldim = (1 if classes.dim() == 1 else classes.shape[1]) if classes is not None else 0
     M = C.c_size_t(0)
     h = C.c_void_p()
     L = _lib.lib()
-    _lib.check(L.ssdr_grid_subsample_dev(_p(points), _p(features), _p(classes), N, fdim, ldim, float(sampleDl), 0,
-                                         _stream(), C.byref(M), C.byref(h)))
+    if bbox is None and slab is None:
+        _lib.check(L.ssdr_grid_subsample_dev(_p(points), _p(features), _p(classes), N, fdim, ldim, float(sampleDl),
+                                             0, _stream(), C.byref(M), C.byref(h)))
+    else:
+        box = (C.c_float * 6)(*[float(v) for v in bbox]) if bbox is not None else None
+        axis, lo, hi = slab if slab is not None else (-1, 0, 0)
+        _lib.check(L.ssdr_grid_subsample_slab_dev(_p(points), _p(features), _p(classes), N, fdim, ldim,
+                                                  float(sampleDl), 0, box, int(axis), int(lo), int(hi), _stream(),
+                                                  C.byref(M), C.byref(h)))
     try:
         m = M.value
-        dp, df, dc = C.c_void_p(), C.c_void_p(), C.c_void_p()
-        _lib.check(L.ssdr_grid_dev_ptrs(h, C.byref(dp), C.byref(df), C.byref(dc)))
         out_p = torch.empty((m, 3), dtype=torch.float32, device=points.device)
-        _copy_d2d(out_p, dp, m * 12)
-        out_f = out_c = None
-        if fdim:
-            out_f = torch.empty((m, fdim), dtype=torch.float32, device=points.device)
-            _copy_d2d(out_f, df, m * fdim * 4)
-        if ldim:
-            out_c = torch.empty((m, ldim), dtype=torch.int32, device=points.device)
-            _copy_d2d(out_c, dc, m * ldim * 4)
+        out_f = torch.empty((m, fdim), dtype=torch.float32, device=points.device) if fdim else None
+        out_c = torch.empty((m, ldim), dtype=torch.int32, device=points.device) if ldim else None
+        keys = counts = None
+        if m:
+            dp, df, dc = C.c_void_p(), C.c_void_p(), C.c_void_p()
+            _lib.check(L.ssdr_grid_dev_ptrs(h, C.byref(dp), C.byref(df), C.byref(dc)))
+            _copy_d2d(out_p, dp, m * 12)
+            if fdim:
+                _copy_d2d(out_f, df, m * fdim * 4)
+            if ldim:
+                _copy_d2d(out_c, dc, m * ldim * 4)
+        if return_keys:
+            import numpy as np
+            keys, counts = np.empty(m, np.uint64), np.empty(m, np.int32)
+            if m:
+                _lib.check(L.ssdr_grid_fetch_ex(h, None, None, None, _lib.ptr(keys), _lib.ptr(counts)))
         torch.cuda.current_stream().synchronize()
     finally:
         L.ssdr_grid_free(h)
+    if return_keys:
+        return out_p, out_f, out_c, keys, counts
     return out_p, out_f, out_c
+
+
+def grid_bbox(points):
+    """(N,3) f32 cuda -> [minx, miny, minz, maxx, maxy, maxz] (python floats holding float32 values)."""
+    box = (C.c_float * 6)()
+    _lib.check(_lib.lib().ssdr_grid_bbox_dev(_p(points), points.shape[0], _stream(), box))
+    return [float(v) for v in box]
+
+
+def grid_point_layers(points, sampleDl, axis, bbox=None):
+    """Voxel layer index of every point along `axis` (int32 cuda tensor) and the number of layers of the grid."""
+    out = torch.empty(points.shape[0], dtype=torch.int32, device=points.device)
+    box = (C.c_float * 6)(*[float(v) for v in bbox]) if bbox is not None else None
+    n_layers = C.c_ulonglong(0)
+    _lib.check(_lib.lib().ssdr_grid_point_layers_dev(_p(points), points.shape[0], box, float(sampleDl), int(axis),
+                                                     _p(out), _stream(), C.byref(n_layers)))
+    return out, int(n_layers.value)
 
 
 _cudart = None

@@ -6,6 +6,11 @@
   the packed (distance bits << 32 | ~row) candidates are max-all-reduced (8 bytes) -- `ssdr_fps_f32_sharded` does
   it with NCCL on the device; `pack_candidate` / `unpack_candidate` define the key so that MAX == "largest distance,
   lowest row", i.e. np.argmax semantics across ranks.
+* One large scan over several GPUs (`grid_subsample_sharded`): voxel-layer slabs along z with the grid geometry of
+  the whole cloud; every voxel is owned by one rank and sees its points in input order, so the rows are bit-identical
+  to a single-GPU run and the ranks' outputs concatenated in rank order ARE the single-GPU key-ordered result.  Row
+  chunks are routed to their slab owner with one all-to-all (the only exchange step of the path); a cloud that is
+  already replicated on every rank needs no exchange at all.
 """
 import ctypes as C
 
@@ -80,3 +85,117 @@ def fps_sharded(F, n_samples, first, comm, rows=None):
     _lib.check(_lib.lib().ssdr_fps_f32_sharded(C.c_void_p(F.data_ptr()), N, F.shape[1], begin, end, int(first),
                                                int(n_samples), C.c_void_p(out.data_ptr()), comm.handle, stream))
     return out
+
+
+def balanced_slabs(layer_counts, world):
+    """Cut n_layers voxel layers into `world` contiguous slabs with near-equal point counts.
+
+    Returns bounds (world + 1,) int64 with bounds[0] = 0, bounds[-1] = n_layers, non-decreasing: rank r owns layers
+    [bounds[r], bounds[r+1]).  Deterministic in `layer_counts`, so every rank derives the same cuts."""
+    cnt = np.asarray(layer_counts, dtype=np.int64)
+    n_layers, world = int(cnt.shape[0]), int(world)
+    cum = np.cumsum(cnt)
+    total = int(cum[-1]) if n_layers else 0
+    bounds = np.zeros(world + 1, np.int64)
+    bounds[-1] = n_layers
+    for r in range(1, world):
+        target = (total * r + world - 1) // world  # first layer boundary with at least r/world of the points below
+        bounds[r] = int(np.searchsorted(cum, target, side="left")) + 1 if total else 0
+    bounds[1:-1] = np.minimum(bounds[1:-1], n_layers)
+    return np.maximum.accumulate(bounds)
+
+
+def route_plan(layers, bounds):
+    """Owner rank of each point from its layer index; returns (dest int64 array, per-rank send counts)."""
+    layers = np.asarray(layers, dtype=np.int64)
+    bounds = np.asarray(bounds, dtype=np.int64)
+    dest = np.searchsorted(bounds[1:-1], layers, side="right")
+    return dest, np.bincount(dest, minlength=len(bounds) - 1)
+
+
+MAX_LAYERS = 1 << 24
+
+
+def slab_route(layers, n_layers, tensors, group=None):
+    """The exchange step of sharded subsampling.  `layers`: layer index of each local row (int tensor, any device);
+    `tensors`: row-aligned tensors (None entries pass through).  All-reduces the layer histogram, cuts balanced slabs
+    and sends every row to its owner with all_to_all_single, keeping input order: rows are stably sorted by
+    destination, and the received pieces arrive concatenated in source-rank order == global row order.
+    Returns (bounds, routed tensors)."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    layers = layers.long()
+    hist = torch.bincount(layers, minlength=n_layers)
+    dist.all_reduce(hist, group=group)
+    bounds = balanced_slabs(hist.cpu().numpy(), world)
+    cuts = torch.from_numpy(bounds[1:-1].copy()).to(layers.device)
+    dest = torch.searchsorted(cuts, layers, right=True)
+    order = torch.argsort(dest, stable=True)
+    send = torch.bincount(dest, minlength=world)
+    recv = torch.empty_like(send)
+    dist.all_to_all_single(recv, send, group=group)
+    send_l, recv_l = send.tolist(), recv.tolist()
+
+    def exchange(t):
+        if t is None:
+            return None
+        t = t.contiguous()[order]
+        out = torch.empty((sum(recv_l),) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+        dist.all_to_all_single(out, t, output_split_sizes=recv_l, input_split_sizes=send_l, group=group)
+        return out
+
+    return bounds, tuple(exchange(t) for t in tensors)
+
+
+def grid_subsample_sharded(points, features=None, classes=None, sampleDl=0.1, *, replicated=False, group=None,
+                           axis=2, return_keys=False):
+    """Subsample ONE cloud with all ranks of `group`; returns this rank's slab of the result as cuda tensors.
+
+    replicated=False: `points` (and features / classes) are this rank's contiguous row chunk of the cloud, chunks in
+    rank order.  bbox and layer histogram are all-reduced (a few KB), then every point travels to its slab owner in
+    one all-to-all that keeps input order.  replicated=True: every rank holds the whole cloud; no exchange.
+    Rows of all ranks concatenated in rank order == `device.grid_subsample` of the whole cloud (axis=2)."""
+    import torch
+    import torch.distributed as dist
+    from . import device as dev
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    n_local = points.shape[0]
+    if classes is not None and classes.dim() == 1:
+        classes = classes[:, None]
+    # 1. geometry of the whole cloud
+    if n_local:
+        box = torch.tensor(dev.grid_bbox(points), dtype=torch.float32, device=points.device)
+    else:
+        box = torch.tensor([float("inf")] * 3 + [float("-inf")] * 3, dtype=torch.float32, device=points.device)
+    if not replicated:
+        lo, hi = box[:3].clone(), box[3:].clone()
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN, group=group)
+        dist.all_reduce(hi, op=dist.ReduceOp.MAX, group=group)
+        box = torch.cat([lo, hi])
+    bbox = [float(v) for v in box.cpu()]
+    # 2. balanced slabs from the layer histogram
+    if n_local:
+        layers, n_layers = dev.grid_point_layers(points, sampleDl, axis, bbox)
+    else:
+        layers, n_layers = torch.zeros(0, dtype=torch.int32, device=points.device), 0
+    if not replicated:
+        nl = torch.tensor([n_layers], dtype=torch.int64, device=points.device)
+        dist.all_reduce(nl, op=dist.ReduceOp.MAX, group=group)
+        n_layers = int(nl.item())
+    if n_layers > MAX_LAYERS:
+        raise ValueError("grid has %d layers along axis %d (limit %d): sampleDl too small for this extent"
+                         % (n_layers, axis, MAX_LAYERS))
+    if replicated:
+        hist = torch.bincount(layers.long(), minlength=n_layers)
+        bounds = balanced_slabs(hist.cpu().numpy(), world)
+        slab = (axis, int(bounds[rank]), int(bounds[rank + 1]))
+        return dev.grid_subsample(points, features, classes, sampleDl, bbox=bbox, slab=slab, return_keys=return_keys)
+    # 3. route every point to its slab owner
+    _, (p, f, c) = slab_route(layers, n_layers, (points, features, classes), group=group)
+    if p.shape[0] == 0:
+        e = lambda t, dt: None if t is None else torch.empty((0, t.shape[1]), dtype=dt, device=points.device)
+        res = (torch.empty((0, 3), dtype=torch.float32, device=points.device), e(features, torch.float32),
+               e(classes, torch.int32))
+        return res + (np.empty(0, np.uint64), np.empty(0, np.int32)) if return_keys else res
+    return dev.grid_subsample(p, f, c, sampleDl, bbox=bbox, slab=None, return_keys=return_keys)

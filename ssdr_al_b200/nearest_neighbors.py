@@ -12,11 +12,11 @@ def _check_dim(dim):
 
 def knn(pts, queries, K, omp=False):
     """knn.pyx:33-69.  `omp` only selected threading in the reference; results are identical, so it is ignored."""
-    # knn.pyx:53 allocates np.zeros; every slot is overwritten unless K > npts, so pinned memory is only zeroed then
-    indices = (_lib.pinned_zeros if K > pts.shape[0] else _lib.pinned_empty)((queries.shape[0], K), np.int64)
     pts_c = np.ascontiguousarray(pts, dtype=np.float32)
     queries_c = np.ascontiguousarray(queries, dtype=np.float32)
     _check_dim(pts_c.shape[1])
+    # knn.pyx:53 allocates np.zeros; every slot is overwritten unless K > npts, so pinned memory is only zeroed then
+    indices = (_lib.pinned_zeros if K > pts_c.shape[0] else _lib.pinned_empty)((queries_c.shape[0], K), np.int64)
     _lib.check(_lib.lib().ssdr_knn(_lib.ptr(pts_c), pts_c.shape[0], pts_c.shape[1], _lib.ptr(queries_c),
                                    queries_c.shape[0], int(K), _lib.ptr(indices)))
     return indices
@@ -24,11 +24,11 @@ def knn(pts, queries, K, omp=False):
 
 def knn_batch(pts, queries, K, omp=False):
     """knn.pyx:71-109."""
-    indices = (_lib.pinned_zeros if K > pts.shape[1] else _lib.pinned_empty)((pts.shape[0], queries.shape[1], K),
-                                                                             np.int64)
     pts_c = np.ascontiguousarray(pts, dtype=np.float32)
     queries_c = np.ascontiguousarray(queries, dtype=np.float32)
     _check_dim(pts_c.shape[2])
+    indices = (_lib.pinned_zeros if K > pts_c.shape[1] else _lib.pinned_empty)(
+        (pts_c.shape[0], queries_c.shape[1], K), np.int64)
     _lib.check(_lib.lib().ssdr_knn_batch(_lib.ptr(pts_c), pts_c.shape[0], pts_c.shape[1], pts_c.shape[2],
                                          _lib.ptr(queries_c), queries_c.shape[1], int(K), _lib.ptr(indices)))
     return indices

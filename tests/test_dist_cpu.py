@@ -80,3 +80,56 @@ def test_row_sharded_fps_matches_single_process_oracle(oracle):
         p.join(timeout=60)
         assert p.exitcode == 0
     assert got[0] == got[1] == want.tolist()
+
+
+def test_balanced_slabs_are_contiguous_and_balanced():
+    rng = np.random.default_rng(1)
+    for world in (1, 2, 3, 8):
+        for cnt in (rng.integers(0, 1000, 500), np.array([100, 1, 1, 1]), np.array([0, 0, 0, 9]), np.array([3]),
+                    np.zeros(5, np.int64), np.array([], np.int64)):
+            b = D.balanced_slabs(cnt, world)
+            assert b[0] == 0 and b[-1] == len(cnt) and (np.diff(b) >= 0).all() and len(b) == world + 1
+            per_rank = [int(np.sum(cnt[b[r]:b[r + 1]])) for r in range(world)]
+            assert sum(per_rank) == int(np.sum(cnt))
+            if len(cnt):  # no slab exceeds the ideal share by more than one layer
+                assert max(per_rank) <= -(-int(np.sum(cnt)) // world) + int(np.max(cnt))
+    dest, send = D.route_plan([0, 1, 2, 3, 4, 5], D.balanced_slabs([1, 2, 3, 4, 5, 6], 3))
+    assert dest.tolist() == [0, 0, 0, 0, 1, 2] and send.tolist() == [4, 1, 1]
+
+
+def _route_worker(rank, world, port, layers, rows, out_q):
+    import torch
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    b, e = [(0, 1000), (1000, len(layers))][rank]  # uneven chunks, rank order == row order
+    bounds, (r, none) = D.slab_route(torch.from_numpy(layers[b:e]), int(layers.max()) + 1,
+                                     (torch.from_numpy(rows[b:e]), None))
+    assert none is None
+    out_q.put((rank, bounds.tolist(), r.numpy()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_slab_route_keeps_global_row_order_per_owner():
+    """Every row reaches the rank owning its layer, and each rank sees its rows in global input order (what makes the
+    sharded barycentres bit-identical to a single-GPU run)."""
+    rng = np.random.default_rng(9)
+    n = 3000
+    layers = rng.integers(0, 40, n).astype(np.int32)
+    rows = np.stack([np.arange(n), layers], 1).astype(np.float32)
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_route_worker, args=(r, 2, port, layers, rows, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = {r: (b, a) for r, b, a in (q.get(timeout=120) for _ in procs)}
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    bounds = got[0][0]
+    assert bounds == got[1][0] == D.balanced_slabs(np.bincount(layers, minlength=40), 2).tolist()
+    for r in range(2):
+        mask = (layers >= bounds[r]) & (layers < bounds[r + 1])
+        assert np.array_equal(got[r][1], rows[mask])

@@ -150,3 +150,90 @@ def test_grid_reference_row_order_vs_oracle(G, oracle, n, dl):
     wp, _, wc = oracle.grid_subsample(pts, None, lab, dl, order="reference")
     p, c = G.compute(pts, classes=lab, sampleDl=dl, order="reference")
     assert p.shape == wp.shape and p.tobytes() == wp.tobytes() and np.array_equal(c, wc)
+
+
+# ---- slab ownership (multi-GPU sharding of one cloud), exercised with virtual ranks on one GPU ----------------
+def _slab_cloud(rng, n):
+    p = (rng.random((n, 3)) * np.array([40.0, 30.0, 6.0])).astype(np.float32)
+    p[: n // 3, 2] = rng.normal(1.0, 0.01, n // 3).astype(np.float32)  # a dense floor: unbalanced layers
+    p += np.float32(-7.3)
+    f = rng.random((n, 3)).astype(np.float32)
+    c = rng.integers(0, 13, (n, 1)).astype(np.int32)
+    return p, f, c
+
+
+@pytest.mark.parametrize("world", [2, 3, 5])
+def test_grid_slabs_replicated_cloud_equal_single_run(G, world):
+    """Every virtual rank sees the whole cloud and reduces only its layers: rows concatenated in rank order are the
+    single-run result, bit for bit (points, features, labels, keys, counts)."""
+    import torch
+    from ssdr_al_b200 import device as dev, dist as SD
+    rng = np.random.default_rng(40 + world)
+    p, f, c = _slab_cloud(rng, 300_000)
+    tp, tf, tc = (torch.from_numpy(a).cuda() for a in (p, f, c))
+    want = dev.grid_subsample(tp, tf, tc, 0.11, return_keys=True)
+    layers, n_layers = dev.grid_point_layers(tp, 0.11, 2)
+    assert n_layers == int(layers.max()) + 1
+    bounds = SD.balanced_slabs(torch.bincount(layers.long(), minlength=n_layers).cpu().numpy(), world)
+    parts = [dev.grid_subsample(tp, tf, tc, 0.11, slab=(2, int(bounds[r]), int(bounds[r + 1])), return_keys=True)
+             for r in range(world)]
+    sizes = [len(x[3]) for x in parts]
+    assert sum(sizes) == len(want[3]) and max(sizes) < len(want[3])  # a rank may own nothing (one dense layer)
+    for j in range(3):
+        assert torch.equal(torch.cat([x[j] for x in parts]), want[j])
+    assert np.array_equal(np.concatenate([x[3] for x in parts]), want[3])
+    assert np.array_equal(np.concatenate([x[4] for x in parts]), want[4])
+    # an empty slab is a valid shard
+    e = dev.grid_subsample(tp, tf, tc, 0.11, slab=(2, n_layers + 5, n_layers + 9), return_keys=True)
+    assert e[0].shape == (0, 3) and e[1].shape == (0, 3) and len(e[3]) == 0
+    # slabs along x partition the voxels as well (only the concatenation order differs)
+    lx, nx = dev.grid_point_layers(tp, 0.11, 0)
+    bx = SD.balanced_slabs(torch.bincount(lx.long(), minlength=nx).cpu().numpy(), world)
+    px = [dev.grid_subsample(tp, tf, tc, 0.11, slab=(0, int(bx[r]), int(bx[r + 1])), return_keys=True)
+          for r in range(world)]
+    k = np.concatenate([x[3] for x in px])
+    o = np.argsort(k, kind="stable")
+    assert np.array_equal(k[o], want[3])
+    assert torch.equal(torch.cat([x[0] for x in px])[torch.from_numpy(o).cuda()], want[0])
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_grid_slabs_row_chunks_routed_to_owners_equal_single_run(G, world):
+    """Row-sharded input: chunk bboxes combined, points routed to their slab owner in input order (what the
+    all-to-all of dist.slab_route delivers), each owner run with the whole cloud's bbox."""
+    import torch
+    from ssdr_al_b200 import device as dev, dist as SD
+    rng = np.random.default_rng(50 + world)
+    p, f, c = _slab_cloud(rng, 200_000)
+    tp, tf, tc = (torch.from_numpy(a).cuda() for a in (p, f, c))
+    want = dev.grid_subsample(tp, tf, tc, 0.09, return_keys=True)
+    spans = [SD.shard_range(len(p), world, r) for r in range(world)]
+    boxes = np.array([dev.grid_bbox(tp[b:e]) for b, e in spans], np.float32)
+    bbox = np.concatenate([boxes[:, :3].min(0), boxes[:, 3:].max(0)])
+    assert np.array_equal(bbox, np.concatenate([p.min(0), p.max(0)]))
+    lay = [dev.grid_point_layers(tp[b:e].contiguous(), 0.09, 2, bbox) for b, e in spans]
+    n_layers = max(n for _, n in lay)
+    layers = torch.cat([l for l, _ in lay]).long()
+    bounds = SD.balanced_slabs(torch.bincount(layers, minlength=n_layers).cpu().numpy(), world)
+    dest = torch.searchsorted(torch.from_numpy(bounds[1:-1].copy()).cuda(), layers, right=True)
+    parts = []
+    for r in range(world):
+        m = dest == r
+        parts.append(dev.grid_subsample(tp[m], tf[m], tc[m], 0.09, bbox=bbox, return_keys=True))
+    for j in range(3):
+        assert torch.equal(torch.cat([x[j] for x in parts]), want[j])
+    assert np.array_equal(np.concatenate([x[3] for x in parts]), want[3])
+    assert np.array_equal(np.concatenate([x[4] for x in parts]), want[4])
+
+
+def test_grid_slab_argument_errors(G):
+    import ctypes as C
+    import torch
+    from ssdr_al_b200 import _lib, device as dev
+    tp = torch.rand((100, 3), device="cuda")
+    with pytest.raises(RuntimeError, match="bbox min exceeds max"):
+        dev.grid_subsample(tp, sampleDl=0.1, bbox=[1, 0, 0, 0, 1, 1])
+    M, h = C.c_size_t(0), C.c_void_p()
+    rc = _lib.lib().ssdr_grid_subsample_slab_dev(C.c_void_p(tp.data_ptr()), None, None, 100, 0, 0, 0.1, 1, None, 2,
+                                                 0, 5, None, C.byref(M), C.byref(h))
+    assert rc != 0 and b"whole cloud only" in _lib.lib().ssdr_last_error()

@@ -1,5 +1,6 @@
 """Run under torchrun on >= 2 GPUs: row-sharded FPS (NCCL 8-byte max all-reduce per pick) must return exactly the
-single-GPU picks on every rank; KNN batch items sharded over ranks must equal the single-GPU result.
+single-GPU picks on every rank; KNN batch items sharded over ranks must equal the single-GPU result; one cloud
+subsampled in voxel-layer slabs over the ranks must concatenate to the single-GPU rows.
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 tools/multigpu_check.py
 """
 import os
@@ -46,10 +47,40 @@ def main():
     part = D.knn_batch(pts[mine].contiguous(), pts[mine].contiguous(), 16)
     same = bool(torch.equal(part, full[mine]))
     ok &= same
+    # one cloud over all ranks: voxel-layer slabs, (a) replicated input, (b) row chunks + all-to-all routing
+    n = 2_000_000
+    p = rng.random((n, 3), dtype=np.float32) * np.array([60.0, 40.0, 8.0], np.float32)
+    p[: n // 3, 2] = 1.0 + 0.01 * rng.standard_normal(n // 3).astype(np.float32)
+    tp = torch.from_numpy(p).to(dev)
+    tf = torch.from_numpy(rng.random((n, 3), dtype=np.float32)).to(dev)
+    tc = torch.from_numpy(rng.integers(0, 13, (n, 1)).astype(np.int32)).to(dev)
+    want = D.grid_subsample(tp, tf, tc, 0.08, return_keys=True)
+    grid_same = []
+    for replicated in (True, False):
+        b, e = (0, n) if replicated else SD.shard_range(n, world, rank)
+        torch.cuda.synchronize()
+        dist.barrier()
+        t0 = time.perf_counter()
+        got = SD.grid_subsample_sharded(tp[b:e], tf[b:e], tc[b:e], 0.08, replicated=replicated, return_keys=True)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        sizes = torch.zeros(world, dtype=torch.int64, device=dev)
+        sizes[rank] = got[0].shape[0]
+        dist.all_reduce(sizes)
+        off = int(sizes[:rank].sum())
+        m = got[0].shape[0]
+        gsame = int(sizes.sum()) == want[0].shape[0] and all(
+            torch.equal(got[j], want[j][off:off + m]) for j in range(3)) and np.array_equal(
+                got[3], want[3][off:off + m]) and np.array_equal(got[4], want[4][off:off + m])
+        ok &= bool(gsame)
+        grid_same.append((replicated, gsame, sizes.tolist(), dt))
     flags = torch.tensor([1 if ok else 0], device=dev)
     dist.all_reduce(flags, op=dist.ReduceOp.MIN)
     if rank == 0:
         print("knn_batch sharded by item equal_to_single_gpu=%s" % same, flush=True)
+        for replicated, gs, sizes, dt in grid_same:
+            print("grid_subsample_sharded N=%d replicated=%s rows_per_rank=%s equal_to_single_gpu(rank0)=%s  %.1f ms"
+                  % (n, replicated, sizes, gs, 1e3 * dt), flush=True)
         print("MULTIGPU_CHECK", "OK" if int(flags.item()) == 1 else "FAILED", flush=True)
     comm.destroy()
     dist.destroy_process_group()
