@@ -57,7 +57,9 @@ struct Ctx {
     int sm_count = 0;
     int max_smem_optin = 0;
     cudaStream_t stream = nullptr;  // the library's own stream for host entry points
+    cudaStream_t copy_stream = nullptr;  // result read-back that overlaps later kernels of the same call
     cudaEvent_t ev = nullptr;
+    cudaEvent_t ev_main = nullptr;
     cudaEvent_t tev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};  // timing events (stats paths)
     DevBuf ws[WS_SLOTS];            // workspaces, addressed by the owning module
     PinBuf pin[4];                  // pinned staging

@@ -31,7 +31,7 @@ struct ItemMeta {
 
 enum { WS_ENC = 0, WS_ITEMS = 1, WS_CELL_P = 2, WS_CELL_Q = 3, WS_CNT_P = 4, WS_CNT_Q = 5, WS_START_P = 6,
        WS_START_Q = 7, WS_SORT_P = 8, WS_SORT_Q = 9, WS_FLAGS = 10, WS_TEMP = 11, WS_IN_P = 12, WS_IN_Q = 13,
-       WS_OUT = 14, WS_STATS = 15, WS_TREE = 16 /* .. WS_TREE+5 used by kdtree.cuh */ };
+       WS_OUT = 14, WS_STATS = 15, WS_TREE = 16 /* .. WS_TREE+5 used by kdtree.cuh */, WS_PATCH = 22 };
 
 __device__ __forceinline__ unsigned f2ord(float f) {
     unsigned u = __float_as_uint(f);
@@ -168,6 +168,139 @@ __global__ void cell_scatter_kernel(SortJob jp, SortJob jq) {
     v.z = __ldg(j.xyz + 3 * (size_t)i + 2);
     v.w = __int_as_float((int)(i % j.n));  // index inside the item
     j.sorted[pos] = v;
+}
+
+// ---- A (small clouds): the whole cell-grid build of one item in ONE CTA -- bbox, geometry, cell histogram and scan
+// in shared memory, scatter -- instead of six launches; the lower pyramid levels are pure launch latency otherwise.
+constexpr int SG_THREADS = 512;
+constexpr unsigned SG_MAX_CELLS = 16384;  // cstride limit (64 KB of dynamic shared memory)
+constexpr unsigned SG_MAX_POINTS = 8192;
+
+__device__ __forceinline__ unsigned local_cell(const ItemMeta& m, float x, float y, float z) {
+    const int cx = cell_coord(x, m.lo[0], m.inv_h, m.g[0]);
+    const int cy = cell_coord(y, m.lo[1], m.inv_h, m.g[1]);
+    const int cz = cell_coord(z, m.lo[2], m.inv_h, m.g[2]);
+    return (unsigned)((cz * m.g[1] + cy) * m.g[0] + cx);
+}
+
+// exclusive scan of a[0..n) in shared memory by the whole CTA (every thread owns a contiguous chunk)
+__device__ void block_exclusive_scan(unsigned* a, unsigned n, unsigned* warp_tot /* [SG_THREADS/32 + 1] */) {
+    const unsigned per = (n + SG_THREADS - 1) / SG_THREADS;
+    const unsigned lo = min(threadIdx.x * per, n), hi = min(lo + per, n);
+    unsigned sum = 0;
+    for (unsigned i = lo; i < hi; ++i) sum += a[i];
+    unsigned incl = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned v = __shfl_up_sync(0xffffffffu, incl, o);
+        if ((threadIdx.x & 31) >= (unsigned)o) incl += v;
+    }
+    if ((threadIdx.x & 31) == 31) warp_tot[threadIdx.x >> 5] = incl;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        const unsigned w = threadIdx.x < SG_THREADS / 32 ? warp_tot[threadIdx.x] : 0u;
+        unsigned wi = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned v = __shfl_up_sync(0xffffffffu, wi, o);
+            if (threadIdx.x >= (unsigned)o) wi += v;
+        }
+        if (threadIdx.x < SG_THREADS / 32) warp_tot[threadIdx.x] = wi - w;
+    }
+    __syncthreads();
+    unsigned run = warp_tot[threadIdx.x >> 5] + incl - sum;
+    for (unsigned i = lo; i < hi; ++i) {
+        const unsigned v = a[i];
+        a[i] = run;
+        run += v;
+    }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(SG_THREADS) small_grid_kernel(const float* __restrict__ pts, unsigned N,
+                                                                const float* __restrict__ qs, unsigned Q,
+                                                                unsigned* __restrict__ enc, ItemMeta* __restrict__ items,
+                                                                int B, float occupancy, unsigned cell_cap,
+                                                                unsigned cstride, unsigned* __restrict__ starts_p,
+                                                                float4* __restrict__ sort_p, float4* __restrict__ sort_q) {
+    extern __shared__ unsigned sg_cells[];  // [cstride]
+    __shared__ float s_red[6][SG_THREADS / 32];
+    __shared__ unsigned s_wtot[SG_THREADS / 32 + 1];
+    __shared__ ItemMeta s_m;
+    const unsigned b = blockIdx.x;
+    const float* p = pts + (size_t)b * N * 3;
+    float mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
+    for (unsigned i = threadIdx.x; i < N; i += SG_THREADS) {
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+            const float v = __ldg(p + 3 * (size_t)i + d);
+            mn[d] = fminf(mn[d], v);
+            mx[d] = fmaxf(mx[d], v);
+        }
+    }
+#pragma unroll
+    for (int d = 0; d < 3; ++d)
+#pragma unroll
+        for (int m = 16; m > 0; m >>= 1) {
+            mn[d] = fminf(mn[d], __shfl_xor_sync(0xffffffffu, mn[d], m));
+            mx[d] = fmaxf(mx[d], __shfl_xor_sync(0xffffffffu, mx[d], m));
+        }
+    if ((threadIdx.x & 31) == 0)
+        for (int d = 0; d < 3; ++d) {
+            s_red[d][threadIdx.x >> 5] = mn[d];
+            s_red[3 + d][threadIdx.x >> 5] = mx[d];
+        }
+    for (unsigned i = threadIdx.x; i < cstride; i += SG_THREADS) sg_cells[i] = 0;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int d = 0; d < 3; ++d) {
+            float a = s_red[d][0], z = s_red[3 + d][0];
+            for (int w = 1; w < SG_THREADS / 32; ++w) {
+                a = fminf(a, s_red[d][w]);
+                z = fmaxf(z, s_red[3 + d][w]);
+            }
+            enc[b * 6 + d] = ~f2ord(a);  // same encoding the multi-launch path reduces with atomicMax
+            enc[b * 6 + 3 + d] = f2ord(z);
+        }
+        setup_item(enc, items, (int)b, N, occupancy, cell_cap, cstride);
+        s_m = items[b];
+    }
+    __syncthreads();
+    const ItemMeta m = s_m;
+    // support points: histogram -> scan -> global starts (offset by the item's base) -> scatter
+    for (unsigned i = threadIdx.x; i < N; i += SG_THREADS)
+        atomicAdd(&sg_cells[local_cell(m, __ldg(p + 3 * (size_t)i), __ldg(p + 3 * (size_t)i + 1), __ldg(p + 3 * (size_t)i + 2))], 1u);
+    __syncthreads();
+    block_exclusive_scan(sg_cells, cstride, s_wtot);
+    for (unsigned i = threadIdx.x; i < cstride; i += SG_THREADS) starts_p[(size_t)b * cstride + i] = b * N + sg_cells[i];
+    if (b == (unsigned)B - 1 && threadIdx.x == 0) starts_p[(size_t)B * cstride] = (unsigned)B * N;
+    __syncthreads();
+    for (unsigned i = threadIdx.x; i < N; i += SG_THREADS) {
+        float4 v;
+        v.x = __ldg(p + 3 * (size_t)i);
+        v.y = __ldg(p + 3 * (size_t)i + 1);
+        v.z = __ldg(p + 3 * (size_t)i + 2);
+        v.w = __int_as_float((int)i);
+        sort_p[(size_t)b * N + atomicAdd(&sg_cells[local_cell(m, v.x, v.y, v.z)], 1u)] = v;
+    }
+    if (!qs) return;
+    // queries (a different array): only their cell-sorted order is needed
+    __syncthreads();
+    const float* q = qs + (size_t)b * Q * 3;
+    for (unsigned i = threadIdx.x; i < cstride; i += SG_THREADS) sg_cells[i] = 0;
+    __syncthreads();
+    for (unsigned i = threadIdx.x; i < Q; i += SG_THREADS)
+        atomicAdd(&sg_cells[local_cell(m, __ldg(q + 3 * (size_t)i), __ldg(q + 3 * (size_t)i + 1), __ldg(q + 3 * (size_t)i + 2))], 1u);
+    __syncthreads();
+    block_exclusive_scan(sg_cells, cstride, s_wtot);
+    for (unsigned i = threadIdx.x; i < Q; i += SG_THREADS) {
+        float4 v;
+        v.x = __ldg(q + 3 * (size_t)i);
+        v.y = __ldg(q + 3 * (size_t)i + 1);
+        v.z = __ldg(q + 3 * (size_t)i + 2);
+        v.w = __int_as_float((int)i);
+        sort_q[(size_t)b * Q + atomicAdd(&sg_cells[local_cell(m, v.x, v.y, v.z)], 1u)] = v;
+    }
 }
 
 // ---- B: main query kernel -------------------------------------------------------------------------------------
@@ -362,9 +495,28 @@ struct DevStats {
 
 static float g_occupancy_scale = 0.3f;  // points per cell ~= scale * K (tunable: SSDR_KNN_OCCUPANCY)
 
+// Rows the tie path rewrote, compacted for a small second read-back (the bulk read-back of all rows runs on the copy
+// stream while the tie path works; the host then overwrites these rows).
+template <typename OutT>
+__global__ void gather_rows_kernel(const unsigned* __restrict__ flag_list, const unsigned* __restrict__ n_flag,
+                                   const OutT* __restrict__ out, int K, unsigned cap, OutT* __restrict__ patch) {
+    unsigned n = *n_flag;
+    n = n < cap ? n : cap;
+    const unsigned long long total = (unsigned long long)n * K;
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (unsigned long long)gridDim.x * blockDim.x) {
+        const unsigned r = (unsigned)(i / K), j = (unsigned)(i % K);
+        patch[i] = out[(size_t)flag_list[r] * K + j];
+    }
+}
+
+constexpr unsigned PATCH_CAP = 1u << 15;  // rows; more flagged rows than this fall back to a second full read-back
+
+// h_out (nullable, host entry points only, K <= N): the results are also delivered to this host buffer; the bulk
+// device->host copy starts right behind the main kernel and overlaps the tie path.
 template <typename OutT>
 static int run_dev(Ctx* c, cudaStream_t s, const float* d_pts, size_t B, size_t N, const float* d_q, size_t Q, size_t K,
-                   OutT* d_out, ssdr_knn_stats* stats) {
+                   OutT* d_out, ssdr_knn_stats* stats, OutT* h_out = nullptr) {
     SSDR_REQUIRE(d_pts && d_q && d_out, SSDR_ERR_INVALID, "NULL pointer");
     SSDR_REQUIRE(N >= 1, SSDR_ERR_INVALID, "npts must be >= 1 (the reference asserts npts != 0)");
     SSDR_REQUIRE(K >= 1, SSDR_ERR_INVALID, "K must be >= 1");
@@ -413,39 +565,55 @@ static int run_dev(Ctx* c, cudaStream_t s, const float* d_pts, size_t B, size_t 
     unsigned* flag_list = c->ws[WS_FLAGS].as<unsigned>();
 
     if (stats) SSDR_CHECK_CUDA(cudaEventRecord(c->tev[0], s));
-    SSDR_CHECK_CUDA(cudaMemsetAsync(ctl, 0, ctl_words * 4, s));
-    unsigned bx = (unsigned)((N + 1023) / 1024);
-    if (bx > 256) bx = 256;
-    bbox_setup_kernel<<<dim3(bx, (unsigned)B), 256, 0, s>>>(d_pts, (unsigned)N, enc, ticket, items, (int)B, occupancy,
-                                                           (unsigned)cap, cstride);
-    SortJob jp, jq;
-    jp.xyz = d_pts;
-    jp.n = (unsigned)N;
-    jp.total = totalP;
-    jp.cell_of = c->ws[WS_CELL_P].as<unsigned>();
-    jp.counts = counts;
-    jp.starts = starts;
-    jp.cursor = cursors;
-    jp.sorted = sort_p;
-    jp.start_bias = 0;
-    jq = jp;
-    jq.total = 0;
-    if (!self) {
-        jq.xyz = d_q;
-        jq.n = (unsigned)Q;
-        jq.total = totalQ;
-        jq.cell_of = jp.cell_of + totalP;
-        jq.counts = counts + ncell;
-        jq.starts = starts + ncell;
-        jq.cursor = cursors + ncell;
-        jq.sorted = c->ws[WS_SORT_Q].as<float4>();
-        jq.start_bias = totalP;  // the concatenated scan continues behind the points' total
+    const bool small = cstride <= SG_MAX_CELLS && N <= SG_MAX_POINTS && Q <= 8 * SG_MAX_POINTS;
+    float4* sort_q_buf = self ? nullptr : c->ws[WS_SORT_Q].as<float4>();
+    if (small) {  // one CTA per item does the whole grid build
+        SSDR_CHECK_CUDA(cudaMemsetAsync(ctl, 0, 16 * 4, s));
+        static bool attr_set_dev[64] = {};
+        bool& attr_set = attr_set_dev[c->device & 63];
+        if (!attr_set) {
+            SSDR_CHECK_CUDA(cudaFuncSetAttribute(small_grid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                 (int)(SG_MAX_CELLS * sizeof(unsigned))));
+            attr_set = true;
+        }
+        small_grid_kernel<<<(unsigned)B, SG_THREADS, cstride * sizeof(unsigned), s>>>(
+            d_pts, (unsigned)N, self ? nullptr : d_q, (unsigned)Q, enc, items, (int)B, occupancy, (unsigned)cap, cstride,
+            starts, sort_p, sort_q_buf);
+    } else {
+        SSDR_CHECK_CUDA(cudaMemsetAsync(ctl, 0, ctl_words * 4, s));
+        unsigned bx = (unsigned)((N + 1023) / 1024);
+        if (bx > 256) bx = 256;
+        bbox_setup_kernel<<<dim3(bx, (unsigned)B), 256, 0, s>>>(d_pts, (unsigned)N, enc, ticket, items, (int)B, occupancy,
+                                                               (unsigned)cap, cstride);
+        SortJob jp, jq;
+        jp.xyz = d_pts;
+        jp.n = (unsigned)N;
+        jp.total = totalP;
+        jp.cell_of = c->ws[WS_CELL_P].as<unsigned>();
+        jp.counts = counts;
+        jp.starts = starts;
+        jp.cursor = cursors;
+        jp.sorted = sort_p;
+        jp.start_bias = 0;
+        jq = jp;
+        jq.total = 0;
+        if (!self) {
+            jq.xyz = d_q;
+            jq.n = (unsigned)Q;
+            jq.total = totalQ;
+            jq.cell_of = jp.cell_of + totalP;
+            jq.counts = counts + ncell;
+            jq.starts = starts + ncell;
+            jq.cursor = cursors + ncell;
+            jq.sorted = c->ws[WS_SORT_Q].as<float4>();
+            jq.start_bias = totalP;  // the concatenated scan continues behind the points' total
+        }
+        const unsigned tot = totalP + jq.total;
+        cell_count_kernel<<<(tot + 255) / 256, 256, 0, s>>>(jp, jq, items);
+        SSDR_TRY(prim::exclusive_scan_u32(counts, starts, (size_t)njobs * ncell, ctl + 16 + B * 6, nullptr, s));
+        cell_scatter_kernel<<<(tot + 255) / 256, 256, 0, s>>>(jp, jq);
     }
-    const unsigned tot = totalP + jq.total;
-    cell_count_kernel<<<(tot + 255) / 256, 256, 0, s>>>(jp, jq, items);
-    SSDR_TRY(prim::exclusive_scan_u32(counts, starts, (size_t)njobs * ncell, ctl + 16 + B * 6, nullptr, s));
-    cell_scatter_kernel<<<(tot + 255) / 256, 256, 0, s>>>(jp, jq);
-    const float4* sort_q = self ? sort_p : jq.sorted;
+    const float4* sort_q = self ? sort_p : sort_q_buf;
     SSDR_CHECK_CUDA(cudaGetLastError());
     if (K > N) SSDR_CHECK_CUDA(cudaMemsetAsync(d_out, 0, (size_t)totalQ * K * sizeof(OutT), s));
 
@@ -473,19 +641,55 @@ static int run_dev(Ctx* c, cudaStream_t s, const float* d_pts, size_t B, size_t 
     DevStats hs;
     unsigned h_err = 0;
     const bool speculate = K >= 8 && totalQ >= 4096;
-    if (!speculate) {
-        SSDR_TRY(d2h_sync(c, &hs, dstats, sizeof(DevStats), s));
-        if (hs.flag_count)
-            SSDR_TRY((kdtree::enqueue_tie_path<OutT>(c, s, d_pts, B, N, d_q, Q, K, d_out, flag_list, &dstats->flag_count,
-                                                     &tree, stats ? c->tev[4] : nullptr)));
-    } else {
+    const size_t out_bytes = (size_t)totalQ * K * sizeof(OutT);
+    OutT* d_patch = nullptr;
+    if (h_out) {
+        SSDR_TRY(c->ws[WS_PATCH].reserve((size_t)PATCH_CAP * K * sizeof(OutT)));
+        d_patch = c->ws[WS_PATCH].as<OutT>();
+        SSDR_CHECK_CUDA(cudaEventRecord(c->ev_main, s));
+        SSDR_CHECK_CUDA(cudaStreamWaitEvent(c->copy_stream, c->ev_main, 0));
+    }
+    auto tie_path = [&]() -> int {
         SSDR_TRY((kdtree::enqueue_tie_path<OutT>(c, s, d_pts, B, N, d_q, Q, K, d_out, flag_list, &dstats->flag_count,
                                                  &tree, stats ? c->tev[4] : nullptr)));
+        if (h_out) {
+            gather_rows_kernel<OutT><<<64, 256, 0, s>>>(flag_list, &dstats->flag_count, d_out, (int)K, PATCH_CAP, d_patch);
+            SSDR_CHECK_CUDA(cudaGetLastError());
+        }
+        return SSDR_OK;
+    };
+    if (!speculate) {
+        // (a pageable h_out makes this copy block the host; the count read below then simply follows it)
+        if (h_out) SSDR_CHECK_CUDA(cudaMemcpyAsync(h_out, d_out, out_bytes, cudaMemcpyDeviceToHost, c->copy_stream));
+        SSDR_TRY(d2h_sync(c, &hs, dstats, sizeof(DevStats), s));
+        if (hs.flag_count) SSDR_TRY(tie_path());
+    } else {
+        SSDR_TRY(tie_path());
+        if (h_out) SSDR_CHECK_CUDA(cudaMemcpyAsync(h_out, d_out, out_bytes, cudaMemcpyDeviceToHost, c->copy_stream));
     }
     if (stats) SSDR_CHECK_CUDA(cudaEventRecord(c->tev[3], s));
     if (speculate) SSDR_CHECK_CUDA(cudaMemcpyAsync(&hs, dstats, sizeof(DevStats), cudaMemcpyDeviceToHost, s));
     if (tree.error) SSDR_CHECK_CUDA(cudaMemcpyAsync(&h_err, tree.error, sizeof(unsigned), cudaMemcpyDeviceToHost, s));
     SSDR_CHECK_CUDA(cudaStreamSynchronize(s));
+    if (h_out) {
+        int rc = kdtree::tree_error_to_status(h_err);
+        const unsigned nf = hs.flag_count < PATCH_CAP ? (unsigned)hs.flag_count : PATCH_CAP;
+        std::vector<unsigned> rows(nf);
+        std::vector<OutT> patch((size_t)nf * K);
+        if (rc == SSDR_OK && nf && hs.flag_count <= PATCH_CAP) {
+            SSDR_CHECK_CUDA(cudaMemcpyAsync(rows.data(), flag_list, (size_t)nf * 4, cudaMemcpyDeviceToHost, s));
+            SSDR_CHECK_CUDA(cudaMemcpyAsync(patch.data(), d_patch, (size_t)nf * K * sizeof(OutT), cudaMemcpyDeviceToHost, s));
+            SSDR_CHECK_CUDA(cudaStreamSynchronize(s));
+        }
+        SSDR_CHECK_CUDA(cudaStreamSynchronize(c->copy_stream));  // never return with a copy into h_out in flight
+        SSDR_TRY(rc);
+        if (hs.flag_count > PATCH_CAP) {
+            SSDR_TRY(d2h_sync(c, h_out, d_out, out_bytes, s));
+        } else {
+            for (unsigned i = 0; i < nf; ++i)
+                memcpy(h_out + (size_t)rows[i] * K, patch.data() + (size_t)i * K, K * sizeof(OutT));
+        }
+    }
     SSDR_TRY(kdtree::tree_error_to_status(h_err));
     const unsigned long long builds = hs.flag_count ? B : 0;
     if (stats) {
@@ -527,14 +731,15 @@ static int run_host(const float* pts, size_t B, size_t N, size_t dim, const floa
         d_q = c->ws[WS_IN_Q].as<float>();
     }
     SSDR_TRY(c->ws[WS_OUT].reserve(B * Q * K * sizeof(OutT)));
-    SSDR_TRY((run_dev<OutT>(c, c->stream, c->ws[WS_IN_P].as<float>(), B, N, d_q, Q, K, c->ws[WS_OUT].as<OutT>(), nullptr)));
+    SSDR_TRY((run_dev<OutT>(c, c->stream, c->ws[WS_IN_P].as<float>(), B, N, d_q, Q, K, c->ws[WS_OUT].as<OutT>(), nullptr,
+                            K > N ? nullptr : out)));
     if (K > N) {  // only the first npts slots of each row are defined (knn_.cxx:59-67): leave the rest untouched
         SSDR_CHECK_CUDA(cudaMemcpy2DAsync(out, K * sizeof(OutT), c->ws[WS_OUT].p, K * sizeof(OutT), N * sizeof(OutT),
                                           B * Q, cudaMemcpyDeviceToHost, c->stream));
         SSDR_CHECK_CUDA(cudaStreamSynchronize(c->stream));
         return SSDR_OK;
     }
-    return d2h_sync(c, out, c->ws[WS_OUT].p, B * Q * K * sizeof(OutT), c->stream);
+    return SSDR_OK;  // delivered by run_dev (bulk read-back overlapped with the tie path)
 }
 
 }  // namespace knn

@@ -89,7 +89,9 @@ int get_ctx(Ctx** out) {
             return set_error(SSDR_ERR_CUDA, "device %d (%s, sm_%d%d) is not a Blackwell sm_100 GPU", dev, prop.name,
                              prop.major, prop.minor);
         SSDR_CHECK_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+        SSDR_CHECK_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
         SSDR_CHECK_CUDA(cudaEventCreateWithFlags(&c->ev, cudaEventDisableTiming));
+        SSDR_CHECK_CUDA(cudaEventCreateWithFlags(&c->ev_main, cudaEventDisableTiming));
         for (int i = 0; i < 5; ++i) SSDR_CHECK_CUDA(cudaEventCreate(&c->tev[i]));
         cudaMemPool_t pool;  // keep freed stream-ordered blocks cached instead of returning them to the driver
         if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
