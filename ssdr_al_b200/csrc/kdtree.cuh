@@ -9,7 +9,8 @@
 //   * TOP: nodes with more than MED_MAX points are split level by level from global memory, one CTA per node
 //     (block-wide prefix counts), a grid barrier between levels;
 //   * SUBTREES: every node of <= MED_MAX points is handed to one CTA that loads it into shared memory ONCE and grows
-//     its whole subtree there -- CTA-wide splits for nodes > SMALL_MAX, one warp per node below (ballot/popc prefix
+//     its whole subtree there -- groups of 2..32 warps (named barriers) for nodes > PER_WARP points, and 1..8 nodes
+//     per warp below that (aligned lane slices, masked ballot/popc prefix
 //     counts) -- with block barriers only, then writes the permuted points back;
 //   * computeMinMax is a warp/block min-max reduction; each of planeSplit's two Hoare sweeps is a prefix count: the
 //     k-th misplaced element from the left swaps with the k-th misplaced element from the right (SURVEY.md A.5;
@@ -25,13 +26,14 @@ namespace kdtree {
 
 constexpr int BT = 1024;
 constexpr int NW = BT / 32;
-constexpr int IPT = 4;          // subtree CTA-wide scan: MED_MAX == BT * IPT
 constexpr int IPT_BIG = 4;      // top-level scan chunk per thread (8 and loop unrolling measured slower: spills)
 constexpr int LEAF = 10;
-constexpr int SMALL_MAX = 1024;   // split by one warp (32 slots per lane)
-constexpr int MED_MAX = 4096;     // whole subtree grown in the shared memory of one CTA
-constexpr int LIST_MED = 4;       // > SMALL_MAX nodes inside one subtree level (<= MED_MAX / (SMALL_MAX+1))
-constexpr int LIST_SMALL = 384;   // split-able nodes inside one subtree level (<= MED_MAX / (LEAF+1))
+constexpr int MED_MAX = 4096;     // whole subtree grown in the shared memory of one CTA (<= 8192: 32 warps x PER_WARP)
+constexpr int PER_WARP = 256;     // points per warp when a group of warps splits a node (IPT_SUB rows of 32)
+constexpr int IPT_SUB = PER_WARP / 32;
+constexpr int LIST_BIG = MED_MAX / (PER_WARP + 1) + 1;   // nodes of > PER_WARP points inside one subtree level
+constexpr int LIST_SMALL = MED_MAX / (LEAF + 1) + 1;     // split-able nodes inside one subtree level
+constexpr int MAX_ROUNDS = 8;     // rounds of warp groups scheduled at once
 constexpr int MAX_LEVELS = 512;
 constexpr int MAX_GROUP_LEVELS = 64;  // levels that may use several CTAs per node (node size halves per level)
 constexpr int MAX_DEPTH = 96;
@@ -53,13 +55,11 @@ struct __align__(16) Entry {  // a node waiting to be split inside a subtree (po
 
 // dynamic shared memory of build_kernel (subtree phase)
 constexpr size_t SM_PP = 0;
-constexpr size_t SM_PSAT = SM_PP + (size_t)MED_MAX * 16;
-constexpr size_t SM_PFAIL = SM_PSAT + (size_t)MED_MAX * 2;
-constexpr size_t SM_LPOS = SM_PFAIL + (size_t)MED_MAX * 2;
-constexpr size_t SM_RPOS = SM_LPOS + (size_t)MED_MAX;
-constexpr size_t SM_WSCR = SM_RPOS + (size_t)MED_MAX;
-constexpr size_t SM_LISTS = SM_WSCR + (size_t)NW * SMALL_MAX * 2;  // per warp: sL, sR (u16 x SMALL_MAX/2 each)
-constexpr size_t SM_TOTAL = SM_LISTS + 2 * (size_t)(LIST_MED + LIST_SMALL) * sizeof(Entry);
+constexpr size_t SM_LPOS = SM_PP + (size_t)MED_MAX * 16;   // u16 [MED_MAX]: k-th misplaced position from the left
+constexpr size_t SM_RPOS = SM_LPOS + (size_t)MED_MAX * 2;  // u16 [MED_MAX]: ... from the right
+constexpr size_t SM_LISTS = SM_RPOS + (size_t)MED_MAX * 2;
+constexpr size_t SM_CLS = SM_LISTS + 2 * (size_t)(LIST_BIG + LIST_SMALL) * sizeof(Entry);  // u16 [2][4][LIST_SMALL]
+constexpr size_t SM_TOTAL = SM_CLS + 2 * 4 * (size_t)LIST_SMALL * 2;
 
 struct Tree {
     unsigned N, cap, B;    // points per item, node capacity per item, items
@@ -650,12 +650,11 @@ __device__ __forceinline__ void split_big_group(const Tree& t, unsigned g, int l
 // ---- SUBTREES: everything below lives in the shared memory of one CTA ------------------------------------------
 struct SubCtx {
     float4* spp;            // [count] the subtree's points, position-ordered
-    unsigned short* psat;   // CTA-wide split scratch
-    unsigned short* pfail;
-    unsigned short* lpos;
+    unsigned short* lpos;   // [count] misplaced positions of the running sweep, at [node.l + k]
     unsigned short* rpos;
-    Entry* next;            // next level's lists: [0, LIST_MED) medium, [LIST_MED, ..) small
-    unsigned* cnt_next;     // [2] medium, small
+    Entry* next;            // next level's lists: [0, LIST_BIG) big, [LIST_BIG, ..) small
+    unsigned short* cls_next;  // [4][LIST_SMALL] small entries by size class (slots into next + LIST_BIG)
+    unsigned* cnt_next;     // [6] big, small, then the four size classes (<= 256, 128, 64, 32 points)
     unsigned* nalloc;       // node ids handed out inside the reserved block
     unsigned base_gid;      // global id of the first reserved node
     unsigned nreserved;
@@ -684,80 +683,281 @@ __device__ __forceinline__ void emit_children_sub(const Tree& t, const SubCtx& s
             ce.lo[d] = (k == 1 && d == cf) ? cv : e.lo[d];
             ce.hi[d] = (k == 0 && d == cf) ? cv : e.hi[d];
         }
-        if (cnt[k] > (unsigned)SMALL_MAX) {
+        if (cnt[k] > (unsigned)PER_WARP) {
             const unsigned pos = atomicAdd(&sc.cnt_next[0], 1u);
-            if (pos < (unsigned)LIST_MED) sc.next[pos] = ce;
+            if (pos < (unsigned)LIST_BIG) sc.next[pos] = ce;
             else atomicOr(t.error, 8u);
         } else {
             const unsigned pos = atomicAdd(&sc.cnt_next[1], 1u);
-            if (pos < (unsigned)LIST_SMALL) sc.next[LIST_MED + pos] = ce;
-            else atomicOr(t.error, 8u);
+            if (pos < (unsigned)LIST_SMALL) {
+                sc.next[LIST_BIG + pos] = ce;
+                const int c = cnt[k] > 128u ? 0 : (cnt[k] > 64u ? 1 : (cnt[k] > 32u ? 2 : 3));
+                sc.cls_next[c * LIST_SMALL + atomicAdd(&sc.cnt_next[2 + c], 1u)] = (unsigned short)pos;
+            } else {
+                atomicOr(t.error, 8u);
+            }
         }
     }
 }
 
-// one warp splits one node of <= SMALL_MAX points in place
-__device__ __forceinline__ void split_small_sm(const Tree& t, const SubCtx& sc, const Entry& e, unsigned short* wscr) {
-    const int lane = threadIdx.x & 31;
+// named barrier over the g warps of a group (g == 1: the warp itself); ids 1..15, 0 stays __syncthreads'
+__device__ __forceinline__ void group_bar(int g, int id) {
+    if (g == 1) __syncwarp();
+    else if (g == NW) __syncthreads();  // the whole CTA works on one node: nobody else can be at barrier 0
+    else asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(g * 32) : "memory");
+}
+
+// warps that split a node of `count` points together: a power of two, PER_WARP points per warp
+__device__ __forceinline__ int group_warps(unsigned count) {
+    const unsigned need = (count + PER_WARP - 1) / PER_WARP;
+    int g = 1;
+    while ((unsigned)g < need) g <<= 1;
+    return g;
+}
+
+// One group of g warps (warps [off, off+g) of the CTA) splits one node in place: computeMinMax + middleSplit_
+// (:898-929), planeSplit's two Hoare sweeps (:942-975) as prefix counts, the children's tight cut bounds (:886-887).
+// Every warp owns a contiguous chunk of 32*ipt positions, lanes interleaved inside it, so a position's rank among
+// the predicate-true / -false positions is (warps before) + (rows before in the warp) + (lanes before in the row):
+// two ballots per row and one packed count per warp through shared memory.
+struct GroupScratch {
+    float* red;        // [8 * NW]  per warp: bbox partials (6), cut-bound partials (2)
+    unsigned* tot;     // [NW]      per warp: packed (true count | false count << 16) of the sweep
+    unsigned* m;       // [NW]      per group (at its first warp): misplaced pairs of the sweep
+};
+
+__device__ __forceinline__ void split_node_sm(const Tree& t, const SubCtx& sc, const Entry& e, int g, int off,
+                                              const GroupScratch& gs) {
+    constexpr unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, gw = warp - off;
+    const unsigned G = (unsigned)g * 32u, gt = (unsigned)gw * 32u + (unsigned)lane;
+    const int bid = 1 + (off >> 1);
     const unsigned ltmask = (1u << lane) - 1u;
     float4* sp = sc.spp + e.l;
-    unsigned short* sL = wscr;
-    unsigned short* sR = wscr + SMALL_MAX / 2;
     const unsigned count = (unsigned)(e.r - e.l);
-    const int nslot = (int)((count + 31) / 32);
+
     float mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
-    for (int s = 0; s < nslot; ++s) {
-        const unsigned p = (unsigned)s * 32 + lane;
-        if (p < count) {
-            const float4 v = sp[p];
-            mn[0] = fminf(mn[0], v.x);
-            mx[0] = fmaxf(mx[0], v.x);
-            mn[1] = fminf(mn[1], v.y);
-            mx[1] = fmaxf(mx[1], v.y);
-            mn[2] = fminf(mn[2], v.z);
-            mx[2] = fmaxf(mx[2], v.z);
-        }
+    for (unsigned i = gt; i < count; i += G) {
+        const float4 v = sp[i];
+        mn[0] = fminf(mn[0], v.x);
+        mx[0] = fmaxf(mx[0], v.x);
+        mn[1] = fminf(mn[1], v.y);
+        mx[1] = fmaxf(mx[1], v.y);
+        mn[2] = fminf(mn[2], v.z);
+        mx[2] = fmaxf(mx[2], v.z);
     }
 #pragma unroll
     for (int d = 0; d < 3; ++d)
 #pragma unroll
         for (int m = 16; m > 0; m >>= 1) {
-            mn[d] = fminf(mn[d], __shfl_xor_sync(0xffffffffu, mn[d], m));
-            mx[d] = fmaxf(mx[d], __shfl_xor_sync(0xffffffffu, mx[d], m));
+            mn[d] = fminf(mn[d], __shfl_xor_sync(FULL, mn[d], m));
+            mx[d] = fmaxf(mx[d], __shfl_xor_sync(FULL, mx[d], m));
+        }
+    if (g > 1) {
+        if (lane == 0) {
+#pragma unroll
+            for (int d = 0; d < 3; ++d) {
+                gs.red[d * NW + warp] = mn[d];
+                gs.red[(3 + d) * NW + warp] = mx[d];
+            }
+        }
+        group_bar(g, bid);
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+            mn[d] = lane < g ? gs.red[d * NW + off + lane] : INFINITY;
+            mx[d] = lane < g ? gs.red[(3 + d) * NW + off + lane] : -INFINITY;
+#pragma unroll
+            for (int m = 16; m > 0; m >>= 1) {
+                mn[d] = fminf(mn[d], __shfl_xor_sync(FULL, mn[d], m));
+                mx[d] = fmaxf(mx[d], __shfl_xor_sync(FULL, mx[d], m));
+            }
+        }
+    }
+    int cf;
+    float cv;
+    decide_split(e.lo, e.hi, mn, mx, &cf, &cv);  // every thread, same inputs
+    const float* sval = reinterpret_cast<const float*>(sp) + cf;  // component cf of point p = sval[4*p]
+
+    const unsigned ipt = (count + G - 1) / G;  // rows per warp, <= IPT_SUB
+    const unsigned W = ipt * 32u;
+    unsigned start = 0, lim1 = 0, lim2 = 0;
+    for (int sweep = 0; sweep < 2; ++sweep) {
+        const unsigned base = start + (unsigned)gw * W;
+        unsigned bs[IPT_SUB], bf[IPT_SUB];
+        unsigned wsat = 0, wfail = 0;
+#pragma unroll
+        for (int k = 0; k < IPT_SUB; ++k) {
+            bs[k] = bf[k] = 0u;
+            if ((unsigned)k < ipt) {
+                const unsigned p = base + (unsigned)k * 32u + (unsigned)lane;
+                const bool in = p < count;
+                const float v = in ? sval[4 * p] : 0.f;
+                const bool sat = in && (sweep == 0 ? (v < cv) : (v <= cv));
+                bs[k] = __ballot_sync(FULL, sat);
+                bf[k] = __ballot_sync(FULL, in && !sat);
+                wsat += __popc(bs[k]);
+                wfail += __popc(bf[k]);
+            }
+        }
+        unsigned sat_before = 0, fail_before = 0, tot_sat = wsat;
+        if (g > 1) {
+            if (lane == 0) gs.tot[warp] = wsat | (wfail << 16);
+            group_bar(g, bid);
+            const unsigned x = lane < g ? gs.tot[off + lane] : 0u;
+            unsigned incl = x;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const unsigned n = __shfl_up_sync(FULL, incl, o);
+                if (lane >= o) incl += n;
+            }
+            const unsigned mine = __shfl_sync(FULL, incl - x, gw);
+            sat_before = mine & 0xFFFFu;
+            fail_before = mine >> 16;
+            tot_sat = __shfl_sync(FULL, incl, 31) & 0xFFFFu;
+        }
+        const unsigned lim = start + tot_sat;
+        unsigned sb = sat_before, fb = fail_before;
+#pragma unroll
+        for (int k = 0; k < IPT_SUB; ++k) {
+            if ((unsigned)k < ipt) {
+                const unsigned p = base + (unsigned)k * 32u + (unsigned)lane;
+                const bool sat = (bs[k] >> lane) & 1u, fail = (bf[k] >> lane) & 1u;
+                const unsigned cs = sb + __popc(bs[k] & ltmask) + (sat ? 1u : 0u);   // inclusive ranks
+                const unsigned cfl = fb + __popc(bf[k] & ltmask) + (fail ? 1u : 0u);
+                if (fail && p < lim) sc.lpos[e.l + cfl - 1] = (unsigned short)p;
+                if (sat && p >= lim) sc.rpos[e.l + tot_sat - cs] = (unsigned short)p;
+                if (p + 1 == lim) gs.m[off] = cfl;  // false positions left of lim == pairs to swap
+                sb += __popc(bs[k]);
+                fb += __popc(bf[k]);
+            }
+        }
+        group_bar(g, bid);
+        const unsigned m = lim > start ? gs.m[off] : 0u;
+        for (unsigned k = gt; k < m; k += G) {
+            const unsigned a = sc.lpos[e.l + k], c = sc.rpos[e.l + k];
+            const float4 va = sp[a], vc = sp[c];
+            sp[a] = vc;
+            sp[c] = va;
+        }
+        group_bar(g, bid);
+        if (sweep == 0) {
+            lim1 = lim;
+            start = lim;
+        } else {
+            lim2 = lim;
+        }
+    }
+    unsigned idx;  // :934-936
+    if (lim1 > count / 2) idx = lim1;
+    else if (lim2 < count / 2) idx = lim2;
+    else idx = count / 2;
+    float dlow = -INFINITY, dhigh = INFINITY;
+    for (unsigned i = gt; i < count; i += G) {
+        const float v = sval[4 * i];
+        if (i < idx) dlow = fmaxf(dlow, v);
+        else dhigh = fminf(dhigh, v);
+    }
+#pragma unroll
+    for (int m = 16; m > 0; m >>= 1) {
+        dlow = fmaxf(dlow, __shfl_xor_sync(FULL, dlow, m));
+        dhigh = fminf(dhigh, __shfl_xor_sync(FULL, dhigh, m));
+    }
+    if (g > 1) {
+        if (lane == 0) {
+            gs.red[6 * NW + warp] = dlow;
+            gs.red[7 * NW + warp] = dhigh;
+        }
+        group_bar(g, bid);
+        if (gw == 0) {
+            dlow = lane < g ? gs.red[6 * NW + off + lane] : -INFINITY;
+            dhigh = lane < g ? gs.red[7 * NW + off + lane] : INFINITY;
+#pragma unroll
+            for (int m = 16; m > 0; m >>= 1) {
+                dlow = fmaxf(dlow, __shfl_xor_sync(FULL, dlow, m));
+                dhigh = fminf(dhigh, __shfl_xor_sync(FULL, dhigh, m));
+            }
+        }
+    }
+    if (gt == 0) emit_children_sub(t, sc, e, idx, cf, cv, dlow, dhigh);
+    // the group's scratch slots are free for the warps' next nodes only once everybody has read them
+    group_bar(g, bid);
+}
+
+// Nodes of at most 8*L points, 32/L of them per warp: L lanes (an aligned slice of the warp) split one node, the
+// same way a warp group does (rows of L positions, ranks from masked ballots), with no shared scratch at all.  The
+// deep levels of a subtree hold hundreds of such nodes; one warp per node would walk them eight rounds per level.
+template <int L>
+__device__ __forceinline__ void split_small_nodes(const Tree& t, const SubCtx& sc, const Entry* cl,
+                                                  const unsigned short* ids, unsigned first, unsigned n_class) {
+    constexpr unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const int sub = lane / L, sl = lane % L;
+    const bool valid = first + (unsigned)sub < n_class;
+    const Entry& e = cl[LIST_BIG + ids[valid ? first + sub : first]];
+    const unsigned count = valid ? (unsigned)(e.r - e.l) : 0u;  // idle slices see an empty node and write nothing
+    const unsigned gmask = L == 32 ? FULL : (((1u << L) - 1u) << (sub * L));
+    const unsigned ltmask = gmask & ((1u << lane) - 1u);
+    float4* sp = sc.spp + e.l;
+
+    float mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
+    for (unsigned i = sl; i < count; i += L) {
+        const float4 v = sp[i];
+        mn[0] = fminf(mn[0], v.x);
+        mx[0] = fmaxf(mx[0], v.x);
+        mn[1] = fminf(mn[1], v.y);
+        mx[1] = fmaxf(mx[1], v.y);
+        mn[2] = fminf(mn[2], v.z);
+        mx[2] = fmaxf(mx[2], v.z);
+    }
+#pragma unroll
+    for (int d = 0; d < 3; ++d)
+#pragma unroll
+        for (int m = L / 2; m > 0; m >>= 1) {
+            mn[d] = fminf(mn[d], __shfl_xor_sync(FULL, mn[d], m));
+            mx[d] = fmaxf(mx[d], __shfl_xor_sync(FULL, mx[d], m));
         }
     int cf;
     float cv;
     decide_split(e.lo, e.hi, mn, mx, &cf, &cv);
-    const float* sval = reinterpret_cast<const float*>(sp) + cf;  // component cf of point p = sval[4*p]
+    const float* sval = reinterpret_cast<const float*>(sp) + cf;
+
     unsigned start = 0, lim1 = 0, lim2 = 0;
     for (int sweep = 0; sweep < 2; ++sweep) {
-        unsigned tot = 0;
-        for (int s = 0; s < nslot; ++s) {
-            const unsigned p = (unsigned)s * 32 + lane;
-            const bool in = p < count && p >= start;
+        unsigned bs[IPT_SUB], bf[IPT_SUB];
+        unsigned tot_sat = 0;
+        // rows any slice of the warp still needs (warp-uniform, so the ballots below stay convergent)
+        const unsigned rows = __reduce_max_sync(FULL, (count - start + L - 1) / L);
+#pragma unroll
+        for (int k = 0; k < IPT_SUB; ++k) {
+            bs[k] = bf[k] = 0u;
+            if ((unsigned)k >= rows) continue;
+            const unsigned p = start + (unsigned)(k * L + sl);
+            const bool in = p < count;
             const float v = in ? sval[4 * p] : 0.f;
             const bool sat = in && (sweep == 0 ? (v < cv) : (v <= cv));
-            tot += __popc(__ballot_sync(0xffffffffu, sat));
+            bs[k] = __ballot_sync(FULL, sat) & gmask;
+            bf[k] = __ballot_sync(FULL, in && !sat) & gmask;
+            tot_sat += __popc(bs[k]);
         }
-        const unsigned lim = start + tot;
+        const unsigned lim = start + tot_sat;
         unsigned sb = 0, fb = 0, m = 0;
-        for (int s = 0; s < nslot; ++s) {
-            const unsigned p = (unsigned)s * 32 + lane;
-            const bool in = p < count && p >= start;
-            const float v = in ? sval[4 * p] : 0.f;
-            const bool sat = in && (sweep == 0 ? (v < cv) : (v <= cv));
-            const bool fail = in && !sat;
-            const unsigned bs = __ballot_sync(0xffffffffu, sat), bf = __ballot_sync(0xffffffffu, fail);
-            const bool left_misplaced = fail && p < lim;
-            if (left_misplaced) sL[fb + __popc(bf & ltmask)] = (unsigned short)p;
-            if (sat && p >= lim) sR[tot - (sb + __popc(bs & ltmask) + 1)] = (unsigned short)p;
-            m += __popc(__ballot_sync(0xffffffffu, left_misplaced));
-            sb += __popc(bs);
-            fb += __popc(bf);
+#pragma unroll
+        for (int k = 0; k < IPT_SUB; ++k) {
+            if ((unsigned)k >= rows) continue;
+            const unsigned p = start + (unsigned)(k * L + sl);
+            const bool sat = (bs[k] >> lane) & 1u, fail = (bf[k] >> lane) & 1u;
+            const unsigned cs = sb + __popc(bs[k] & ltmask) + (sat ? 1u : 0u);
+            const unsigned cfl = fb + __popc(bf[k] & ltmask) + (fail ? 1u : 0u);
+            const bool left_mis = fail && p < lim;
+            if (left_mis) sc.lpos[e.l + cfl - 1] = (unsigned short)p;
+            if (sat && p >= lim) sc.rpos[e.l + tot_sat - cs] = (unsigned short)p;
+            m += __popc(__ballot_sync(FULL, left_mis) & gmask);
+            sb += __popc(bs[k]);
+            fb += __popc(bf[k]);
         }
         __syncwarp();
-        for (unsigned k = lane; k < m; k += 32) {
-            const unsigned a = sL[k], c = sR[k];
+        for (unsigned k = sl; k < m; k += L) {
+            const unsigned a = sc.lpos[e.l + k], c = sc.rpos[e.l + k];
             const float4 va = sp[a], vc = sp[c];
             sp[a] = vc;
             sp[c] = va;
@@ -775,165 +975,26 @@ __device__ __forceinline__ void split_small_sm(const Tree& t, const SubCtx& sc, 
     else if (lim2 < count / 2) idx = lim2;
     else idx = count / 2;
     float dlow = -INFINITY, dhigh = INFINITY;
-    for (int s = 0; s < nslot; ++s) {
-        const unsigned p = (unsigned)s * 32 + lane;
-        if (p < count) {
-            const float v = sval[4 * p];
-            if (p < idx) dlow = fmaxf(dlow, v);
-            else dhigh = fminf(dhigh, v);
-        }
-    }
-#pragma unroll
-    for (int m = 16; m > 0; m >>= 1) {
-        dlow = fmaxf(dlow, __shfl_xor_sync(0xffffffffu, dlow, m));
-        dhigh = fminf(dhigh, __shfl_xor_sync(0xffffffffu, dhigh, m));
-    }
-    if (lane == 0) emit_children_sub(t, sc, e, idx, cf, cv, dlow, dhigh);
-    __syncwarp();
-}
-
-// the whole CTA splits one node of SMALL_MAX < count <= MED_MAX points in place (count <= BT*IPT: one scan per sweep)
-__device__ __forceinline__ void split_med_sm(const Tree& t, const SubCtx& sc, const Entry& e, unsigned long long* s_warp,
-                                             float* s_red, float* s_bc) {
-    const unsigned tid = threadIdx.x;
-    const int lane = tid & 31, warp = tid >> 5;
-    float4* sp = sc.spp + e.l;
-    const unsigned count = (unsigned)(e.r - e.l);
-    __syncthreads();
-    float mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
-    for (unsigned i = tid; i < count; i += BT) {
-        const float4 v = sp[i];
-        mn[0] = fminf(mn[0], v.x);
-        mx[0] = fmaxf(mx[0], v.x);
-        mn[1] = fminf(mn[1], v.y);
-        mx[1] = fmaxf(mx[1], v.y);
-        mn[2] = fminf(mn[2], v.z);
-        mx[2] = fmaxf(mx[2], v.z);
-    }
-#pragma unroll
-    for (int d = 0; d < 3; ++d) {
-#pragma unroll
-        for (int m = 16; m > 0; m >>= 1) {
-            mn[d] = fminf(mn[d], __shfl_xor_sync(0xffffffffu, mn[d], m));
-            mx[d] = fmaxf(mx[d], __shfl_xor_sync(0xffffffffu, mx[d], m));
-        }
-        if (lane == 0) {
-            s_red[d * NW + warp] = mn[d];
-            s_red[(3 + d) * NW + warp] = mx[d];
-        }
-    }
-    __syncthreads();
-    if (tid == 0) {
-        float amn[3], amx[3];
-        for (int d = 0; d < 3; ++d) {
-            amn[d] = s_red[d * NW];
-            amx[d] = s_red[(3 + d) * NW];
-            for (int w = 1; w < NW; ++w) {
-                amn[d] = fminf(amn[d], s_red[d * NW + w]);
-                amx[d] = fmaxf(amx[d], s_red[(3 + d) * NW + w]);
-            }
-        }
-        int cf;
-        float cv;
-        decide_split(e.lo, e.hi, amn, amx, &cf, &cv);
-        s_bc[0] = __int_as_float(cf);
-        s_bc[1] = cv;
-    }
-    __syncthreads();
-    const int cf = __float_as_int(s_bc[0]);
-    const float cv = s_bc[1];
-    const float* sval = reinterpret_cast<const float*>(sp) + cf;
-
-    unsigned start = 0, lim1 = 0, lim2 = 0;
-    for (int sweep = 0; sweep < 2; ++sweep) {
-        const unsigned i0 = start + tid * IPT;
-        unsigned long long f[IPT];
-        unsigned long long local = 0;
-#pragma unroll
-        for (int k = 0; k < IPT; ++k) {
-            const unsigned i = i0 + k;
-            unsigned long long fl = 0;
-            if (i < count) {
-                const float v = sval[4 * i];
-                const bool sat = sweep == 0 ? (v < cv) : (v <= cv);
-                fl = sat ? 1ull : (1ull << 32);
-            }
-            local += fl;
-            f[k] = local;
-        }
-        unsigned long long tot;
-        const unsigned long long incl = block_scan_incl(local, s_warp, &tot);
-        const unsigned long long excl = incl - local;
-#pragma unroll
-        for (int k = 0; k < IPT; ++k) {
-            const unsigned i = i0 + k;
-            if (i < count) {
-                const unsigned long long v = excl + f[k];
-                sc.psat[i] = (unsigned short)(v & 0xFFFFull);
-                sc.pfail[i] = (unsigned short)((v >> 32) & 0xFFFFull);
-            }
-        }
-        __syncthreads();
-        const unsigned tot_sat = (unsigned)(tot & 0xFFFFFFFFull);
-        const unsigned lim = start + tot_sat;
-        const unsigned m = lim > start ? sc.pfail[lim - 1] : 0u;
-        for (unsigned i = start + tid; i < count; i += BT) {
-            const unsigned cs = sc.psat[i], cfl = sc.pfail[i];
-            const bool sat = (i == start ? cs : cs - sc.psat[i - 1]) != 0;
-            if (!sat) {
-                if (i < lim) sc.lpos[cfl - 1] = (unsigned short)i;
-            } else {
-                if (i >= lim) sc.rpos[tot_sat - cs] = (unsigned short)i;
-            }
-        }
-        __syncthreads();
-        for (unsigned k = tid; k < m; k += BT) {
-            const unsigned a = sc.lpos[k], c = sc.rpos[k];
-            const float4 va = sp[a], vc = sp[c];
-            sp[a] = vc;
-            sp[c] = va;
-        }
-        __syncthreads();
-        if (sweep == 0) {
-            lim1 = lim;
-            start = lim;
-        } else {
-            lim2 = lim;
-        }
-    }
-    unsigned idx;
-    if (lim1 > count / 2) idx = lim1;
-    else if (lim2 < count / 2) idx = lim2;
-    else idx = count / 2;
-    float dlow = -INFINITY, dhigh = INFINITY;
-    for (unsigned i = tid; i < count; i += BT) {
+    for (unsigned i = sl; i < count; i += L) {
         const float v = sval[4 * i];
         if (i < idx) dlow = fmaxf(dlow, v);
         else dhigh = fminf(dhigh, v);
     }
 #pragma unroll
-    for (int m = 16; m > 0; m >>= 1) {
-        dlow = fmaxf(dlow, __shfl_xor_sync(0xffffffffu, dlow, m));
-        dhigh = fminf(dhigh, __shfl_xor_sync(0xffffffffu, dhigh, m));
+    for (int m = L / 2; m > 0; m >>= 1) {
+        dlow = fmaxf(dlow, __shfl_xor_sync(FULL, dlow, m));
+        dhigh = fminf(dhigh, __shfl_xor_sync(FULL, dhigh, m));
     }
-    if (lane == 0) {
-        s_red[warp] = dlow;
-        s_red[NW + warp] = dhigh;
-    }
-    __syncthreads();
-    if (tid == 0) {
-        for (int w = 1; w < NW; ++w) {
-            dlow = fmaxf(dlow, s_red[w]);
-            dhigh = fminf(dhigh, s_red[NW + w]);
-        }
-        emit_children_sub(t, sc, e, idx, cf, cv, dlow, dhigh);
-    }
-    __syncthreads();
+    if (valid && sl == 0) emit_children_sub(t, sc, e, idx, cf, cv, dlow, dhigh);
+    __syncwarp();
 }
 
-__device__ __forceinline__ void build_subtree(const Tree& t, unsigned groot, unsigned char* dsm,
-                                              unsigned long long* s_warp, float* s_red, float* s_bc, unsigned* s_ctl) {
-    // s_ctl: [0..1] counts of list 0 (medium, small), [2..3] counts of list 1, [4] nalloc, [5] base node id
+__device__ __forceinline__ void build_subtree(const Tree& t, unsigned groot, unsigned char* dsm, float* s_red8,
+                                              unsigned* s_tot, unsigned* s_m, unsigned* s_ctl,
+                                              unsigned char* s_slot /* [MAX_ROUNDS*NW] */,
+                                              unsigned char* s_off /* [LIST_BIG] */) {
+    // s_ctl: [0..5] counts of list 0 (big, small, 4 size classes), [6..11] of list 1, [12] nalloc, [13] base node id,
+    //        [14] big nodes scheduled so far, [15] rounds of the current schedule
     const unsigned tid = threadIdx.x;
     const int warp = tid >> 5;
     float4* spp = reinterpret_cast<float4*>(dsm + SM_PP);
@@ -947,11 +1008,16 @@ __device__ __forceinline__ void build_subtree(const Tree& t, unsigned groot, uns
     if (tid == 0) {
         const unsigned base = atomicAdd(&t.node_count[b], 2u * count);
         if (base + 2u * count > t.cap) atomicOr(t.error, 1u);
-        s_ctl[0] = count > (unsigned)SMALL_MAX ? 1u : 0u;
-        s_ctl[1] = count > (unsigned)SMALL_MAX ? 0u : 1u;
-        s_ctl[2] = s_ctl[3] = 0u;
-        s_ctl[4] = 0u;
-        s_ctl[5] = base;
+        const bool big = count > (unsigned)PER_WARP;
+        const int c0 = count > 128u ? 0 : (count > 64u ? 1 : (count > 32u ? 2 : 3));
+        for (int i = 0; i < 13; ++i) s_ctl[i] = 0u;
+        s_ctl[0] = big ? 1u : 0u;
+        s_ctl[1] = big ? 0u : 1u;
+        if (!big) {
+            s_ctl[2 + c0] = 1u;
+            reinterpret_cast<unsigned short*>(dsm + SM_CLS)[c0 * LIST_SMALL] = 0;
+        }
+        s_ctl[13] = base;
         Entry e;
         e.gid = groot;
         e.l = 0;
@@ -960,35 +1026,81 @@ __device__ __forceinline__ void build_subtree(const Tree& t, unsigned groot, uns
             e.lo[d] = __ldcg(&t.nlo[(size_t)groot * 3 + d]);
             e.hi[d] = __ldcg(&t.nhi[(size_t)groot * 3 + d]);
         }
-        lists[count > (unsigned)SMALL_MAX ? 0 : LIST_MED] = e;
+        lists[count > (unsigned)PER_WARP ? 0 : LIST_BIG] = e;
     }
     __syncthreads();
     SubCtx sc;
     sc.spp = spp;
-    sc.psat = reinterpret_cast<unsigned short*>(dsm + SM_PSAT);
-    sc.pfail = reinterpret_cast<unsigned short*>(dsm + SM_PFAIL);
     sc.lpos = reinterpret_cast<unsigned short*>(dsm + SM_LPOS);
     sc.rpos = reinterpret_cast<unsigned short*>(dsm + SM_RPOS);
-    sc.nalloc = &s_ctl[4];
-    sc.base_gid = b * t.cap + s_ctl[5];
+    sc.nalloc = &s_ctl[12];
+    sc.base_gid = b * t.cap + s_ctl[13];
     sc.nreserved = 2u * count;
     sc.b = b;
     sc.l0 = l0;
-    const bool ok = s_ctl[5] + 2u * count <= t.cap;
+    GroupScratch gs;
+    gs.red = s_red8;
+    gs.tot = s_tot;
+    gs.m = s_m;
+    const bool ok = s_ctl[13] + 2u * count <= t.cap;
+    unsigned short* cls = reinterpret_cast<unsigned short*>(dsm + SM_CLS);  // [2][4][LIST_SMALL]
     for (int lvl = 0; ok; ++lvl) {
         const int cur = lvl & 1;
-        Entry* cl = lists + (size_t)cur * (LIST_MED + LIST_SMALL);
-        sc.next = lists + (size_t)(cur ^ 1) * (LIST_MED + LIST_SMALL);
-        sc.cnt_next = &s_ctl[(cur ^ 1) * 2];
-        const unsigned nmed = min(s_ctl[cur * 2], (unsigned)LIST_MED);
-        const unsigned nsmall = min(s_ctl[cur * 2 + 1], (unsigned)LIST_SMALL);
-        if (nmed == 0 && nsmall == 0) break;
-        for (unsigned m = 0; m < nmed; ++m) split_med_sm(t, sc, cl[m], s_warp, s_red, s_bc);
+        Entry* cl = lists + (size_t)cur * (LIST_BIG + LIST_SMALL);
+        sc.next = lists + (size_t)(cur ^ 1) * (LIST_BIG + LIST_SMALL);
+        sc.cnt_next = &s_ctl[(cur ^ 1) * 6];
+        sc.cls_next = cls + (size_t)(cur ^ 1) * 4 * LIST_SMALL;
+        const unsigned short* ccl = cls + (size_t)cur * 4 * LIST_SMALL;
+        const unsigned nbig = min(s_ctl[cur * 6], (unsigned)LIST_BIG);
+        const unsigned nsmall = min(s_ctl[cur * 6 + 1], (unsigned)LIST_SMALL);
+        if (nbig == 0 && nsmall == 0) break;
+        // nodes of more than PER_WARP points: groups of warps, packed into rounds by thread 0
+        for (unsigned done = 0; done < nbig;) {
+            if (tid == 0) {
+                unsigned* w32 = reinterpret_cast<unsigned*>(s_slot);
+                for (int i = 0; i < MAX_ROUNDS * NW / 4; ++i) w32[i] = 0xFFFFFFFFu;
+                unsigned r = 0, at = 0, j = done;
+                for (; j < nbig; ++j) {
+                    const unsigned g = (unsigned)group_warps((unsigned)(cl[j].r - cl[j].l));
+                    if (at + g > (unsigned)NW || (g == 2u && at == (unsigned)NW - 2u)) {  // (barrier ids stop at 15)
+                        ++r;
+                        at = 0;
+                    }
+                    if (r == (unsigned)MAX_ROUNDS) break;
+                    s_off[j] = (unsigned char)at;
+                    for (unsigned w = at; w < at + g; ++w) s_slot[r * NW + w] = (unsigned char)j;
+                    at += g;
+                }
+                s_ctl[14] = j;
+                s_ctl[15] = r < (unsigned)MAX_ROUNDS ? r + 1u : (unsigned)MAX_ROUNDS;
+            }
+            __syncthreads();
+            const unsigned upto = s_ctl[14], rounds = s_ctl[15];
+            for (unsigned r = 0; r < rounds; ++r) {
+                // a warp may sit in differently shaped groups in consecutive rounds, and a barrier id must never be
+                // used with two thread counts at once: rounds are separated CTA-wide (levels rarely need two)
+                if (r) __syncthreads();
+                const unsigned j = s_slot[r * NW + warp];
+                if (j != 0xFFu) split_node_sm(t, sc, cl[j], group_warps((unsigned)(cl[j].r - cl[j].l)), (int)s_off[j], gs);
+            }
+            done = upto;
+            if (done < nbig) __syncthreads();  // the schedule tables are rewritten
+        }
+        // nodes of at most PER_WARP points: 1, 2, 4 or 8 of them per warp by size class
+        if (nsmall) {
+            const unsigned n0 = min(s_ctl[cur * 6 + 2], nsmall), n1 = min(s_ctl[cur * 6 + 3], nsmall);
+            const unsigned n2 = min(s_ctl[cur * 6 + 4], nsmall), n3 = min(s_ctl[cur * 6 + 5], nsmall);
+            const unsigned u0 = n0, u1 = u0 + (n1 + 1) / 2, u2 = u1 + (n2 + 3) / 4, u3 = u2 + (n3 + 7) / 8;
+            for (unsigned u = warp; u < u3; u += NW) {
+                if (u < u0) split_small_nodes<32>(t, sc, cl, ccl, u, n0);
+                else if (u < u1) split_small_nodes<16>(t, sc, cl, ccl + LIST_SMALL, (u - u0) * 2, n1);
+                else if (u < u2) split_small_nodes<8>(t, sc, cl, ccl + 2 * LIST_SMALL, (u - u1) * 4, n2);
+                else split_small_nodes<4>(t, sc, cl, ccl + 3 * LIST_SMALL, (u - u2) * 8, n3);
+            }
+        }
         __syncthreads();
-        for (unsigned w = warp; w < nsmall; w += NW)
-            split_small_sm(t, sc, cl[LIST_MED + w], reinterpret_cast<unsigned short*>(dsm + SM_WSCR) + (size_t)warp * SMALL_MAX);
-        __syncthreads();
-        if (tid == 0) s_ctl[cur * 2] = s_ctl[cur * 2 + 1] = 0u;
+        if (tid < 6) s_ctl[cur * 6 + tid] = 0u;
+        if (t.tstamps && t.N <= (unsigned)MED_MAX && lvl < 8) mark(nullptr, t.tstamps, 2 + lvl);  // diagnostics
         __syncthreads();
     }
     for (unsigned i = tid; i < count; i += BT) pp[i] = spp[i];
@@ -997,9 +1109,12 @@ __device__ __forceinline__ void build_subtree(const Tree& t, unsigned groot, uns
 __global__ void __launch_bounds__(BT, 1) build_kernel(const float* __restrict__ pts_all, const Tree t) {
     extern __shared__ __align__(16) unsigned char dyn_smem[];
     __shared__ unsigned long long s_warp[32];
-    __shared__ float s_red[6 * NW];
+    __shared__ float s_red[8 * NW];
     __shared__ float s_bc[4];
-    __shared__ unsigned s_ctl[8];
+    __shared__ unsigned s_ctl[16];
+    __shared__ unsigned s_tot[NW], s_m[NW];
+    __shared__ __align__(4) unsigned char s_slot[MAX_ROUNDS * NW];
+    __shared__ unsigned char s_off[LIST_BIG];
     const unsigned tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
     unsigned phase = 0;
@@ -1110,7 +1225,7 @@ __global__ void __launch_bounds__(BT, 1) build_kernel(const float* __restrict__ 
     // ---- SUBTREES (independent; no further grid barrier)
     const unsigned nsub = min(__ldcg(&t.list_cnt[MAX_LEVELS + 1]), t.lcap);
     for (unsigned i = blockIdx.x; i < nsub; i += gridDim.x)
-        build_subtree(t, __ldcg(t.sublist + i), dyn_smem, s_warp, s_red, s_bc, s_ctl);
+        build_subtree(t, __ldcg(t.sublist + i), dyn_smem, s_red, s_tot, s_m, s_ctl, s_slot, s_off);
     mark(nullptr, t.tstamps, 11);  // CTA 0's own end
     if (t.tstamps && threadIdx.x == 0) atomicMax(&t.tstamps[12], gtimer());  // last CTA's end
 }
@@ -1141,7 +1256,24 @@ __device__ __forceinline__ NodeRec load_node(const NodeRec* p) {
 // per_warp != 0: one query per 32-thread CTA, walked by lane 0 alone -- a pointer-chasing DFS gains nothing from SIMT
 // and loses to divergence, so with few flagged rows every query gets its own warp scheduler slot; per_warp == 0
 // (duplicate-heavy clouds, most rows flagged): one query per thread.
-template <typename OutT>
+// KNNResultSet::addPoint (:72-96) on a register-resident list: strict '>' shifting == the new entry lands behind
+// entries of equal distance.  Requires d < rd[KC-1].  Branch-free: 2 FMNMX + 1 FSETP + 2 SEL per slot.
+template <int KC>
+__device__ __forceinline__ void rs_insert(float (&rd)[KC], unsigned (&ri)[KC], float d, unsigned id) {
+    bool p_prev = true;
+#pragma unroll
+    for (int j = KC - 1; j > 0; --j) {
+        const bool p = d < rd[j - 1];
+        const float nd = fmaxf(rd[j - 1], fminf(rd[j], d));
+        ri[j] = p ? ri[j - 1] : (p_prev ? id : ri[j]);
+        rd[j] = nd;
+        p_prev = p;
+    }
+    rd[0] = fminf(rd[0], d);
+    ri[0] = p_prev ? id : ri[0];
+}
+
+template <typename OutT, int KC>
 __global__ void __launch_bounds__(32) exact_query_kernel(const float* __restrict__ q_all, const Tree t, unsigned Q,
                                                          int K, const unsigned* __restrict__ flag_list,
                                                          const unsigned* __restrict__ n_flag_ptr,
@@ -1160,10 +1292,16 @@ __global__ void __launch_bounds__(32) exact_query_kernel(const float* __restrict
     const NodeRec* nodes = t.nodes + (size_t)b * t.cap;
     const float q[3] = {q_all[3 * (size_t)row], q_all[3 * (size_t)row + 1], q_all[3 * (size_t)row + 2]};
 
-    float rd[MAX_K];
-    unsigned ri[MAX_K];
+    // result set in registers (KC >= K slots; slots behind K-1 only ever receive entries pushed out of the top K)
+    float rd[KC];
+    unsigned ri[KC];
+#pragma unroll
+    for (int j = 0; j < KC; ++j) {
+        rd[j] = 3.402823466e+38f;
+        ri[j] = 0u;
+    }
     int count = 0;
-    rd[K - 1] = 3.402823466e+38f;  // KNNResultSet::init (:47-53)
+    float worst = 3.402823466e+38f;  // == rd[K-1]; KNNResultSet::init (:47-53)
 
     // computeInitialDistances (:977-995) against the root bbox
     float d0[3] = {0.f, 0.f, 0.f};
@@ -1195,7 +1333,7 @@ __global__ void __launch_bounds__(32) exact_query_kernel(const float* __restrict
         const int node = st_node[sp];
         const float mind = st_min[sp];
         float dd[3] = {st_d[sp][0], st_d[sp][1], st_d[sp][2]};
-        if (!first && !(mind <= rd[K - 1])) continue;  // mindistsq*epsError <= worstDist()  (:1319)
+        if (!first && !(mind <= worst)) continue;  // mindistsq*epsError <= worstDist()  (:1319)
         first = false;
         NodeRec nd = load_node(nodes + node);
         while (nd.c1 >= 0) {
@@ -1232,27 +1370,19 @@ __global__ void __launch_bounds__(32) exact_query_kernel(const float* __restrict
 #pragma unroll
         for (int k = 0; k < LEAF; ++k)
             if (k < n) buf[k] = __ldg(pp + nd.l + k);
-        const float worst = rd[K - 1];  // snapshot once per leaf (:1277)
+        const float wsnap = worst;  // snapshot once per leaf (:1277)
 #pragma unroll
         for (int k = 0; k < LEAF; ++k) {
             if (k < n) {
                 const float dx = __fsub_rn(q[0], buf[k].x), dy = __fsub_rn(q[1], buf[k].y), dz = __fsub_rn(q[2], buf[k].z);
                 const float dist = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
-                if (dist < worst) {  // KNNResultSet::addPoint (:72-96), strict '>' shifting
-                    const unsigned index = __float_as_uint(buf[k].w);
-                    int jj;
-                    for (jj = count; jj > 0; --jj) {
-                        if (rd[jj - 1] > dist) {
-                            if (jj < K) {
-                                rd[jj] = rd[jj - 1];
-                                ri[jj] = ri[jj - 1];
-                            }
-                        } else
-                            break;
-                    }
-                    if (jj < K) {
-                        rd[jj] = dist;
-                        ri[jj] = index;
+                if (dist < wsnap) {  // addPoint is called; it stores nothing once the set is full and dist >= worst
+                    if (dist < worst) {
+                        rs_insert<KC>(rd, ri, dist, __float_as_uint(buf[k].w));
+                        float w = rd[0];
+#pragma unroll
+                        for (int j = 1; j < KC; ++j) w = (j == K - 1) ? rd[j] : w;
+                        worst = w;
                     }
                     if (count < K) ++count;
                 }
@@ -1260,7 +1390,9 @@ __global__ void __launch_bounds__(32) exact_query_kernel(const float* __restrict
         }
     }
     OutT* o = out + (size_t)row * K;
-    for (int jj = 0; jj < count; ++jj) o[jj] = (OutT)ri[jj];
+#pragma unroll
+    for (int jj = 0; jj < KC; ++jj)
+        if (jj < count) o[jj] = (OutT)ri[jj];
   }
 }
 
@@ -1353,8 +1485,17 @@ static int enqueue_tie_path(Ctx* c, cudaStream_t s, const float* d_pts, size_t B
     mark_items_kernel<<<64, 256, 0, s>>>(flag_list, d_flag_count, (unsigned)Q, needed);
     SSDR_TRY(launch_build(c, s, d_pts, t));
     if (ev_mid) SSDR_CHECK_CUDA(cudaEventRecord(ev_mid, s));
-    exact_query_kernel<OutT><<<(unsigned)c->sm_count * 16, 32, 0, s>>>(d_q, t, (unsigned)Q, (int)K, flag_list,
-                                                                       d_flag_count, d_out);
+#define SSDR_EXACT(KCV)                                                                                       \
+    exact_query_kernel<OutT, KCV><<<(unsigned)c->sm_count * 16, 32, 0, s>>>(d_q, t, (unsigned)Q, (int)K, flag_list, \
+                                                                            d_flag_count, d_out)
+    if (K == 1) SSDR_EXACT(1);
+    else if (K <= 2) SSDR_EXACT(2);
+    else if (K <= 4) SSDR_EXACT(4);
+    else if (K <= 8) SSDR_EXACT(8);
+    else if (K <= 16) SSDR_EXACT(16);
+    else if (K <= 32) SSDR_EXACT(32);
+    else SSDR_EXACT(64);
+#undef SSDR_EXACT
     SSDR_CHECK_CUDA(cudaGetLastError());
     *t_out = t;
     return SSDR_OK;
