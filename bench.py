@@ -43,6 +43,16 @@ def make_clouds(seed):
     return (rng.uniform(-1, 1, (B, N0, 3)) * np.array([2.0, 2.0, 1.5])).astype(np.float32)
 
 
+def ncu_traffic(kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture of this
+    kernel (profiles/traffic.json, written by tools/ncu_summary.py traffic); None when no capture is recorded."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            return float(json.load(f)[kernel]["dram_bytes_per_launch"])
+    except Exception:
+        return None
+
+
 def measured_peak():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -185,9 +195,8 @@ def run_ours(args):
         return launches
 
     def count_launches(stats):
-        # our kernels per call: bbox_setup, cell_count, scan_sums, scan_apply, cell_scatter, query
-        # (+ mark_items, build, exact_query when a tie row exists); memsets and torch's slicing copies not counted
-        return sum(6 + (3 if st["tie_rows"] else 0) for _, _, st in stats)
+        # counted inside the library where the launches happen (memsets and torch's slicing copies not included)
+        return sum(int(st["kernel_launches"]) for _, _, st in stats)
 
     for _ in range(max(args.warmup, 3)):
         gpu_pyramid()
@@ -290,7 +299,7 @@ def run_ours(args):
                 "api": "ssdr_al_b200.nearest_neighbors.knn_batch (numpy in/out, int64 indices)"},
         "gpu_launches": launches_per_step * args.steps,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": None, "peak_source": peak_src, "kernel": "knn::query_kernel<17,int64> level 0 (6x40960)",
+                     "traffic": ncu_traffic("knn_query_kernel_level0"), "peak_source": peak_src, "kernel": "knn::query_kernel<17,int64> level 0 (6x40960)",
                      "kernel_ms": dom_ms_avg, "algorithmic_bytes": algo_bytes,
                      "note": "KNN is FP32/issue bound, not HBM bound (SURVEY.md 8d); see dist_evals_per_s",
                      "dist_evals_per_s": evals0 / (dom_ms_avg * 1e-3), "dist_evals_per_query": evals0 / q0},

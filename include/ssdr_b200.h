@@ -74,6 +74,7 @@ typedef struct {
     double main_kernel_ms;    /* device time of the main query kernel alone (CUDA events on the launch stream) */
     double tie_path_ms;       /* device time of the tie path (tree build + exact replay), 0 when unused */
     double tree_build_ms;     /* part of tie_path_ms spent before the exact replay starts (tree build) */
+    uint64_t kernel_launches; /* kernels of this library the call launched (memsets and copies not counted) */
 } ssdr_knn_stats;
 
 /* Device-resident variant: d_points (B,npts,3), d_queries (B,nqueries,3), d_indices (B,nqueries,K) int64.

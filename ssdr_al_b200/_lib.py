@@ -20,7 +20,7 @@ vp = C.c_void_p
 class KnnStats(C.Structure):
     _fields_ = [("queries", C.c_uint64), ("tie_rows", C.c_uint64), ("tree_builds", C.c_uint64),
                 ("dist_evals", C.c_uint64), ("grid_build_ms", C.c_double), ("main_kernel_ms", C.c_double),
-                ("tie_path_ms", C.c_double), ("tree_build_ms", C.c_double)]
+                ("tie_path_ms", C.c_double), ("tree_build_ms", C.c_double), ("kernel_launches", C.c_uint64)]
 
 
 # name -> argtypes (every function returns int status unless listed in _RESTYPE)

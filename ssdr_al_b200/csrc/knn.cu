@@ -564,6 +564,7 @@ static int run_dev(Ctx* c, cudaStream_t s, const float* d_pts, size_t B, size_t 
     float4* sort_p = c->ws[WS_SORT_P].as<float4>();
     unsigned* flag_list = c->ws[WS_FLAGS].as<unsigned>();
 
+    unsigned long long n_launch = 0;
     if (stats) SSDR_CHECK_CUDA(cudaEventRecord(c->tev[0], s));
     const bool small = cstride <= SG_MAX_CELLS && N <= SG_MAX_POINTS && Q <= 8 * SG_MAX_POINTS;
     float4* sort_q_buf = self ? nullptr : c->ws[WS_SORT_Q].as<float4>();
@@ -579,6 +580,7 @@ static int run_dev(Ctx* c, cudaStream_t s, const float* d_pts, size_t B, size_t 
         small_grid_kernel<<<(unsigned)B, SG_THREADS, cstride * sizeof(unsigned), s>>>(
             d_pts, (unsigned)N, self ? nullptr : d_q, (unsigned)Q, enc, items, (int)B, occupancy, (unsigned)cap, cstride,
             starts, sort_p, sort_q_buf);
+        n_launch += 1;
     } else {
         SSDR_CHECK_CUDA(cudaMemsetAsync(ctl, 0, ctl_words * 4, s));
         unsigned bx = (unsigned)((N + 1023) / 1024);
@@ -612,6 +614,7 @@ static int run_dev(Ctx* c, cudaStream_t s, const float* d_pts, size_t B, size_t 
         cell_count_kernel<<<(tot + 255) / 256, 256, 0, s>>>(jp, jq, items);
         SSDR_TRY(prim::exclusive_scan_u32(counts, starts, (size_t)njobs * ncell, ctl + 16 + B * 6, nullptr, s));
         cell_scatter_kernel<<<(tot + 255) / 256, 256, 0, s>>>(jp, jq);
+        n_launch += 5;  // bbox_setup, cell_count, scan_sums, scan_apply, cell_scatter
     }
     const float4* sort_q = self ? sort_p : sort_q_buf;
     SSDR_CHECK_CUDA(cudaGetLastError());
@@ -630,6 +633,7 @@ static int run_dev(Ctx* c, cudaStream_t s, const float* d_pts, size_t B, size_t 
     else SSDR_QUERY(65);
 #undef SSDR_QUERY
     SSDR_CHECK_CUDA(cudaGetLastError());
+    n_launch += 1;
     if (stats) SSDR_CHECK_CUDA(cudaEventRecord(c->tev[2], s));
 
     // ---- C: exact nanoflann replay of the flagged rows.  With K >= 8 and thousands of queries some row is flagged
@@ -652,9 +656,11 @@ static int run_dev(Ctx* c, cudaStream_t s, const float* d_pts, size_t B, size_t 
     auto tie_path = [&]() -> int {
         SSDR_TRY((kdtree::enqueue_tie_path<OutT>(c, s, d_pts, B, N, d_q, Q, K, d_out, flag_list, &dstats->flag_count,
                                                  &tree, stats ? c->tev[4] : nullptr)));
+        n_launch += 3;  // mark_items, build, exact_query
         if (h_out) {
             gather_rows_kernel<OutT><<<64, 256, 0, s>>>(flag_list, &dstats->flag_count, d_out, (int)K, PATCH_CAP, d_patch);
             SSDR_CHECK_CUDA(cudaGetLastError());
+            n_launch += 1;
         }
         return SSDR_OK;
     };
@@ -709,6 +715,7 @@ static int run_dev(Ctx* c, cudaStream_t s, const float* d_pts, size_t B, size_t 
         stats->tie_rows = hs.flag_count;
         stats->tree_builds = builds;
         stats->dist_evals = hs.evals;
+        stats->kernel_launches = n_launch;
     }
     return SSDR_OK;
 }

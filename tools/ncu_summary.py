@@ -1,5 +1,6 @@
 """Summarise .ncu-rep captures (ncu --set full) and launch lists (gpu__time_duration) into small text files for
-profiles/.  Usage: python tools/ncu_summary.py rep <file.ncu-rep> | launches <file.csv>"""
+profiles/.  Usage: python tools/ncu_summary.py rep <file.ncu-rep> | launches <file.csv> |
+traffic <file.ncu-rep> [key profiles/traffic.json]"""
 import collections
 import csv
 import subprocess
@@ -58,5 +59,29 @@ def launches(path):
     print("total_us %.1f  (ncu per-launch times are cold-cache and serialised: compare shares, not absolutes)" % tot)
 
 
+def traffic(path, key=None, out_json=None):
+    """dram bytes (read + write) per launch of the first kernel in an `ncu --set full` report; with key and out_json the
+    value is merged into that json file (profiles/traffic.json, read by bench.py for roofline.traffic)."""
+    import json
+    out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(out.splitlines()))
+    hdr, units, r = rows[0], rows[1], rows[2]
+    idx = {h: i for i, h in enumerate(hdr)}
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    tot = 0.0
+    for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+        tot += float(r[idx[k]].replace(",", "")) * scale[units[idx[k]]]
+    dur = float(r[idx["gpu__time_duration.sum"]].replace(",", ""))
+    print("%s: dram bytes per launch %.0f (%s %s under ncu)" % (r[idx["Kernel Name"]][:80], tot, dur,
+                                                                 units[idx["gpu__time_duration.sum"]]))
+    if key and out_json:
+        try:
+            d = json.load(open(out_json))
+        except Exception:
+            d = {}
+        d[key] = {"dram_bytes_per_launch": tot, "kernel": r[idx["Kernel Name"]][:120], "source": path.split("/")[-1]}
+        json.dump(d, open(out_json, "w"), indent=1, sort_keys=True)
+
+
 if __name__ == "__main__":
-    {"rep": rep, "launches": launches}[sys.argv[1]](sys.argv[2])
+    {"rep": rep, "launches": launches, "traffic": traffic}[sys.argv[1]](*sys.argv[2:])
