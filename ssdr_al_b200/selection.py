@@ -74,10 +74,13 @@ class kCenterGreedy(object):
 
     def select_batch_(self, already_selected, N, **kwargs):
         already = np.asarray(already_selected, dtype=np.int64).reshape(-1)
-        if len(self.already_selected):
-            # kcenterGreedy.py:74-75 (only_new=True): centres seen by an earlier call are not re-applied; a fresh
-            # object per call (gcn.py:247-249) never takes this branch.
-            raise RuntimeError("ssdr_al_b200.kCenterGreedy: call select_batch_ once per object (as gcn.py does)")
+        if len(self.already_selected) and not np.isin(np.asarray(self.already_selected, dtype=np.int64), already).all():
+            # Every call rebuilds min_distances from its own `already_selected` (kcenterGreedy.py:104, reset_dist=True),
+            # so a later call is a fresh computation -- unless a centre of the EARLIER call is missing from the new
+            # list: the reference then refuses to apply it as a new centre (only_new filter, :74-75) and repeats the
+            # same pick.  That corner is not reproduced.
+            raise RuntimeError("ssdr_al_b200.kCenterGreedy: a later select_batch_ must keep the earlier call's "
+                               "already_selected entries (gcn.py builds a fresh object per call)")
         picks = kcenter(self.features, already, N)
         clash = np.intersect1d(picks, already)
         assert clash.size == 0  # kcenterGreedy.py:118

@@ -82,6 +82,21 @@ def test_kcenter_golden(S, golden, tag):
     assert np.array_equal(np.asarray(got), want)
 
 
+def test_kcenter_object_reused_like_an_active_learning_loop(S, oracle):
+    """A second select_batch_ with the grown labelled set is a fresh computation (kcenterGreedy.py:104 resets the
+    distances); dropping an earlier centre is the one corner that is refused."""
+    rng = np.random.default_rng(77)
+    X = rng.standard_normal((5000, 32)).astype(np.float32)
+    kc = S.kCenterGreedy(X)
+    first = kc.select_batch_([3, 17], 20)
+    assert np.array_equal(first, oracle.kcenter(X, np.array([3, 17]), 20))
+    grown = [3, 17] + [int(i) for i in first]
+    second = kc.select_batch_(grown, 15)
+    assert np.array_equal(second, oracle.kcenter(X, np.array(grown), 15))
+    with pytest.raises(RuntimeError, match="keep the earlier call"):
+        kc.select_batch_([5], 3)
+
+
 @pytest.mark.parametrize("N,D,dt", [(20000, 32, np.float32), (8000, 129, np.float64), (6000, 256, np.float32),
                                     (3000, 7, np.float64)])
 def test_kcenter_vs_oracle(S, oracle, N, D, dt):
