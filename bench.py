@@ -346,7 +346,19 @@ def secondary_metrics(torch, D, dev, flush):
             ts.append(a.elapsed_time(b))
         return float(np.median(ts)), r
 
+    def cpu_time(fn):
+        t0 = time.perf_counter()
+        fn()
+        return (time.perf_counter() - t0) * 1e3
+
     try:
+        from oracle import oracle as O
+        O.lib()
+    except Exception:
+        O = None
+
+    try:
+        import ssdr_al_b200 as S
         rng = np.random.default_rng(0)
         n = 1_000_000
         face = rng.integers(0, 3, n)
@@ -356,15 +368,40 @@ def secondary_metrics(torch, D, dev, flush):
         p[face == 2, 0] = 0
         p += rng.normal(0, 0.005, p.shape)
         p -= p.min(0)
-        pts = torch.from_numpy(p.astype(np.float32)).to(dev)
-        rgb = torch.from_numpy(rng.integers(0, 256, (n, 3)).astype(np.float32)).to(dev)
-        lab = torch.from_numpy(((p[:, 0] * 1.7).astype(np.int32) % 13)).to(dev)
+        p = p.astype(np.float32)
+        rgb_h = rng.integers(0, 256, (n, 3)).astype(np.uint8)
+        lab_h = ((p[:, 0] * 1.7).astype(np.int32) % 13).astype(np.uint8)
+        pts = torch.from_numpy(p).to(dev)
+        rgb = torch.from_numpy(rgb_h.astype(np.float32)).to(dev)
+        lab = torch.from_numpy(lab_h.astype(np.int32)).to(dev)
         D.grid_subsample(pts, rgb, lab, 0.04)
         ms, r = timed(lambda: D.grid_subsample(pts, rgb, lab, 0.04), 5)
         m = r[0].shape[0]
         algo = n * 28 + m * 28
-        out["grid_subsample"] = {"points": n, "voxels": int(m), "ms": ms, "mpts_per_s": n / ms / 1e3,
-                                 "algorithmic_gbs": algo / ms / 1e6, "frac_of_hbm_peak": algo / ms / 1e6 / peak}
+        g = {"points": n, "voxels": int(m), "ms": ms, "mpts_per_s": n / ms / 1e3,
+             "algorithmic_gbs": algo / ms / 1e6, "frac_of_hbm_peak": algo / ms / 1e6 / peak}
+        # the same call through the reference-facing API (uint8 colours / labels in, conversions + PCIe inside)
+        S.grid_subsampling.compute(p, features=rgb_h, classes=lab_h, sampleDl=0.04)
+        g["e2e_ms"] = float(np.median([cpu_time(lambda: S.grid_subsampling.compute(
+            p, features=rgb_h, classes=lab_h, sampleDl=0.04)) for _ in range(3)]))
+        g["e2e_mpts_per_s"] = n / g["e2e_ms"] / 1e3
+        if O is not None:
+            ref = O.ref_grid_subsample if O.have_ref() else O.grid_subsample
+            g["cpu_ms"] = cpu_time(lambda: ref(p, rgb_h.astype(np.float32), lab_h.astype(np.int32), 0.04))
+            g["cpu_kind"] = "reference (1 thread, one run)" if O.have_ref() else "port (1 thread, one run)"
+        out["grid_subsample"] = g
+        # config 1, second half: k=16 KNN of the sub-sampled cloud on itself (one cloud, N = Q = M)
+        sub = r[0].contiguous()[None]
+        D.knn_batch(sub, sub, K)
+        ms, _ = timed(lambda: D.knn_batch(sub, sub, K), 5)
+        out["knn_cfg1"] = {"points": int(m), "k": K, "ms": ms, "queries_per_s": m / ms * 1e3}
+        # worst case for the subsampler: uniform in volume, M ~ 0.88 N
+        u = torch.from_numpy((rng.random((n, 3)) * np.array([7.0, 5.0, 3.0])).astype(np.float32)).to(dev)
+        D.grid_subsample(u, rgb, lab, 0.04)
+        ms, r = timed(lambda: D.grid_subsample(u, rgb, lab, 0.04), 5)
+        out["grid_subsample_uniform"] = {"points": n, "voxels": int(r[0].shape[0]), "ms": ms,
+                                         "mpts_per_s": n / ms / 1e3}
+        del pts, rgb, lab, u, sub
     except Exception as e:
         out["grid_subsample"] = {"error": repr(e)}
     for d_, picks in ((32, 2000), (256, 1000)):
@@ -385,6 +422,15 @@ def secondary_metrics(torch, D, dev, flush):
             algo = 500_000 * (4 * d_ + 8 + 8)
             out["kcenter_d%d" % d_] = {"rows": 500_000, "picks": picks, "ms_per_pick": per, "picks_per_s": 1e3 / per,
                                        "algorithmic_gbs": algo / per / 1e6, "frac_of_hbm_peak": algo / per / 1e6 / peak}
+            if O is not None:  # the reference loops on the host, a few picks, extrapolated linearly
+                Fh = F.cpu().numpy()
+                npk = 8 if d_ == 32 else 4
+                out["fps_d%d" % d_]["cpu_ms_per_pick"] = cpu_time(lambda: O.fps_numpy(Fh, npk + 1, 12345)) / npk
+                out["fps_d%d" % d_]["cpu_kind"] = "numpy loop of fps_gcn_cpu.py:137-146, %d picks, 1 process" % npk
+                selh = np.arange(500_000 - 4, 500_000)
+                out["kcenter_d%d" % d_]["cpu_ms_per_pick"] = cpu_time(lambda: O.kcenter(Fh, selh, npk)) / (npk + 4)
+                out["kcenter_d%d" % d_]["cpu_kind"] = "sklearn-formula restatement, %d centres, host BLAS threads" % (npk + 4)
+                del Fh
             del F
         except Exception as e:
             out["fps_d%d" % d_] = {"error": repr(e)}

@@ -84,6 +84,30 @@ def test_config3_scan_scale_subsample(S, oracle):
     assert len(p2) <= len(p) and int(cnt2.sum()) == len(p)
 
 
+def test_config3_knn_on_a_multi_million_point_subsampled_scan(S, oracle):
+    """Config 3, second half: k=16 KNN of the full sub-sampled scan on itself (one cloud of a few million points with
+    1/r^2 density, so cell occupancy varies by orders of magnitude).  Exact against the oracle for 200 000 query rows
+    spread over the cloud (external-query call on the same support), properties for every row of the self call."""
+    rng = np.random.default_rng(21)
+    n = 12_000_000
+    r = 1.0 / np.sqrt(rng.random(n, dtype=np.float32) * np.float32(1 - 1e-4) + np.float32(1e-4))
+    th = rng.random(n, dtype=np.float32) * np.float32(2 * np.pi)
+    pts = np.stack([r * np.cos(th) + 100, r * np.sin(th) + 100,
+                    rng.standard_normal(n, dtype=np.float32) * np.float32(0.02) + 1], 1).astype(np.float32)
+    wall = rng.random(n) < 0.3
+    pts[wall, 2] = rng.random(int(wall.sum()), dtype=np.float32) * 30
+    sub = S.grid_subsampling.compute(pts, sampleDl=0.06)
+    m = len(sub)
+    assert m > 1_500_000
+    idx = S.nearest_neighbors.knn(sub, sub, 16, omp=True)
+    assert idx.shape == (m, 16) and (idx[:, 0] == np.arange(m)).all() and idx.min() >= 0 and idx.max() < m
+    rows = np.arange(0, m, max(1, m // 200_000))
+    want = oracle.knn(sub, sub[rows], 16, threads=8)
+    assert np.array_equal(idx[rows], want)
+    got_q = S.nearest_neighbors.knn(sub, sub[rows], 16)
+    assert np.array_equal(got_q, want)
+
+
 @pytest.mark.parametrize("D,exact_picks", [(32, 300), (256, 80)])
 def test_config4_selection_500k(S, oracle, D, exact_picks):
     """Config 4: 500k feature vectors, budget 2 % = 10,000 picks.  Exact prefix vs the oracle, then the full budget:
