@@ -103,6 +103,14 @@ int ssdr_knn_debug_build_timing(const float* points, size_t B, size_t npts, uint
 int ssdr_grid_subsample(const float* points /* (N,3) */, const float* feats /* (N,fdim) */,
                         const int32_t* classes /* (N,ldim) */, size_t N, size_t fdim, size_t ldim, float sampleDl,
                         int order, size_t* M_out, void** handle);
+/* Same, with the element type of feats / classes stated: every data-prep caller of the reference passes uint8
+ * colours and uint8 labels (e.g. utils/data_prepare_s3dis.py:58), which wrapper.cpp:100-106 widens on the host to
+ * float32 / int32.  SSDR_DTYPE_U8 uploads the bytes as they are and widens them on the device (exact). */
+#define SSDR_DTYPE_NATIVE 0 /* float32 features, int32 classes */
+#define SSDR_DTYPE_U8 1
+int ssdr_grid_subsample_typed(const float* points, const void* feats, int feats_dtype, const void* classes,
+                              int classes_dtype, size_t N, size_t fdim, size_t ldim, float sampleDl, int order,
+                              size_t* M_out, void** handle);
 int ssdr_grid_fetch(void* handle, float* points_out, float* feats_out, int32_t* classes_out);
 int ssdr_grid_fetch_ex(void* handle, float* points_out, float* feats_out, int32_t* classes_out,
                        uint64_t* keys_out, int32_t* counts_out);

@@ -44,6 +44,8 @@ SIGNATURES = {
     "ssdr_grid_fetch": [vp, vp, vp, vp],
     "ssdr_grid_fetch_ex": [vp, vp, vp, vp, vp, vp],
     "ssdr_grid_free": [vp],
+    "ssdr_grid_subsample_typed": [vp, vp, C.c_int, vp, C.c_int, sz, sz, sz, C.c_float, C.c_int, C.POINTER(sz),
+                                  C.POINTER(vp)],
     "ssdr_grid_subsample_dev": [vp, vp, vp, sz, sz, sz, C.c_float, C.c_int, vp, C.POINTER(sz), C.POINTER(vp)],
     "ssdr_grid_dev_ptrs": [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)],
     "ssdr_grid_subsample_slab_dev": [vp, vp, vp, sz, sz, sz, C.c_float, C.c_int, vp, C.c_int, C.c_ulonglong,

@@ -34,7 +34,7 @@ struct Meta {
 };
 
 enum { WS_META = 0, WS_PART = 1, WS_KEYS = 2, WS_KEYS2 = 3, WS_IDX = 4, WS_IDX2 = 5, WS_TEMP = 6, WS_STARTS = 7,
-       WS_IN_P = 9, WS_IN_F = 10, WS_IN_C = 11, WS_HASH = 12, WS_CMIN = 13, WS_SEL = 14 };
+       WS_IN_P = 9, WS_IN_F = 10, WS_IN_C = 11, WS_HASH = 12, WS_CMIN = 13, WS_SEL = 14, WS_RAW = 15 };
 
 constexpr int LABEL_CAP = 64;
 constexpr int MM_BLOCK = 256;
@@ -184,6 +184,17 @@ __global__ void point_layers_kernel(const float* __restrict__ pts, unsigned long
 __global__ void bbox_fill_kernel(float* partials, float a0, float a1, float a2, float b0, float b1, float b2) {
     partials[0] = a0; partials[1] = a1; partials[2] = a2;
     partials[3] = b0; partials[4] = b1; partials[5] = b2;
+}
+
+// widen uint8 colours / labels on the device (exact in float32 / int32): the callers' arrays are uint8 and the
+// reference converts them on the host (wrapper.cpp:100-106); uploading the bytes is 4x less PCIe and no host pass
+__global__ void widen_u8_f32_kernel(const unsigned char* __restrict__ in, unsigned long long n, float* __restrict__ out) {
+    const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = (float)in[i];
+}
+__global__ void widen_u8_i32_kernel(const unsigned char* __restrict__ in, unsigned long long n, int* __restrict__ out) {
+    const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = (int)in[i];
 }
 
 // ---- 5. voxel segments of the sorted keys ---------------------------------------------------------------------
@@ -769,6 +780,53 @@ int ssdr_grid_subsample(const float* points, const float* feats, const int32_t* 
     }
     return grid::run_dev(c, c->stream, c->ws[grid::WS_IN_P].as<float>(), d_f, d_c, N, fdim, ldim, sampleDl, order,
                          M_out, handle);
+}
+
+int ssdr_grid_subsample_typed(const float* points, const void* feats, int feats_dtype, const void* classes,
+                              int classes_dtype, size_t N, size_t fdim, size_t ldim, float sampleDl, int order,
+                              size_t* M_out, void** handle) {
+    SSDR_REQUIRE(points && M_out && handle, SSDR_ERR_INVALID, "NULL pointer");
+    SSDR_REQUIRE(N >= 1, SSDR_ERR_EMPTY, "Error");
+    SSDR_REQUIRE(feats_dtype == SSDR_DTYPE_NATIVE || feats_dtype == SSDR_DTYPE_U8, SSDR_ERR_INVALID,
+                 "feats_dtype must be SSDR_DTYPE_NATIVE (float32) or SSDR_DTYPE_U8");
+    SSDR_REQUIRE(classes_dtype == SSDR_DTYPE_NATIVE || classes_dtype == SSDR_DTYPE_U8, SSDR_ERR_INVALID,
+                 "classes_dtype must be SSDR_DTYPE_NATIVE (int32) or SSDR_DTYPE_U8");
+    Ctx* c;
+    SSDR_TRY(get_ctx(&c));
+    if (!feats) fdim = 0;
+    if (!classes) ldim = 0;
+    cudaStream_t s = c->stream;
+    SSDR_TRY(c->ws[grid::WS_IN_P].reserve(N * 3 * sizeof(float)));
+    SSDR_TRY(h2d(c, c->ws[grid::WS_IN_P].p, points, N * 3 * sizeof(float), s));
+    const size_t nf = N * fdim, nc = N * ldim;
+    const size_t raw_f = (fdim && feats_dtype == SSDR_DTYPE_U8) ? align_up(nf, 256) : 0;
+    const size_t raw_c = (ldim && classes_dtype == SSDR_DTYPE_U8) ? align_up(nc, 256) : 0;
+    if (raw_f + raw_c) SSDR_TRY(c->ws[grid::WS_RAW].reserve(raw_f + raw_c));
+    unsigned char* raw = c->ws[grid::WS_RAW].as<unsigned char>();
+    const float* d_f = nullptr;
+    const int* d_c = nullptr;
+    if (fdim) {
+        SSDR_TRY(c->ws[grid::WS_IN_F].reserve(nf * sizeof(float)));
+        if (raw_f) {
+            SSDR_TRY(h2d(c, raw, feats, nf, s));
+            grid::widen_u8_f32_kernel<<<(unsigned)((nf + 255) / 256), 256, 0, s>>>(raw, nf, c->ws[grid::WS_IN_F].as<float>());
+        } else {
+            SSDR_TRY(h2d(c, c->ws[grid::WS_IN_F].p, feats, nf * sizeof(float), s));
+        }
+        d_f = c->ws[grid::WS_IN_F].as<float>();
+    }
+    if (ldim) {
+        SSDR_TRY(c->ws[grid::WS_IN_C].reserve(nc * sizeof(int)));
+        if (raw_c) {
+            SSDR_TRY(h2d(c, raw + raw_f, classes, nc, s));
+            grid::widen_u8_i32_kernel<<<(unsigned)((nc + 255) / 256), 256, 0, s>>>(raw + raw_f, nc, c->ws[grid::WS_IN_C].as<int>());
+        } else {
+            SSDR_TRY(h2d(c, c->ws[grid::WS_IN_C].p, classes, nc * sizeof(int), s));
+        }
+        d_c = c->ws[grid::WS_IN_C].as<int>();
+    }
+    SSDR_CHECK_CUDA(cudaGetLastError());
+    return grid::run_dev(c, s, c->ws[grid::WS_IN_P].as<float>(), d_f, d_c, N, fdim, ldim, sampleDl, order, M_out, handle);
 }
 
 int ssdr_grid_fetch_ex(void* handle, float* points_out, float* feats_out, int32_t* classes_out, uint64_t* keys_out,

@@ -9,6 +9,8 @@ from . import _lib
 
 ORDER_KEY = 0
 ORDER_REFERENCE = 1
+DTYPE_NATIVE = 0
+DTYPE_U8 = 1
 _default_order = ORDER_KEY
 
 
@@ -33,8 +35,12 @@ def compute(points, *, features=None, classes=None, sampleDl=0.1, method="baryce
     use_feature = features is not None
     use_classes = classes is not None
     pts = _to_array(points, np.float32, "points")
-    feats = _to_array(features, np.float32, "features") if use_feature else None
-    cls = _to_array(classes, np.int32, "classes") if use_classes else None
+    # uint8 colours / labels (what every data-prep caller passes) travel as bytes and are widened on the device --
+    # the values are the ones PyArray_FROM_OTF(NPY_FLOAT / NPY_INT) would produce (wrapper.cpp:100-106)
+    f_u8 = use_feature and isinstance(features, np.ndarray) and features.dtype == np.uint8
+    c_u8 = use_classes and isinstance(classes, np.ndarray) and classes.dtype == np.uint8
+    feats = _to_array(features, np.uint8 if f_u8 else np.float32, "features") if use_feature else None
+    cls = _to_array(classes, np.uint8 if c_u8 else np.int32, "classes") if use_classes else None
     if pts.ndim != 2 or pts.shape[1] != 3:
         raise RuntimeError("Wrong dimensions : points.shape is not (N, 3)")
     if use_feature and feats.ndim != 2:
@@ -58,10 +64,12 @@ def compute(points, *, features=None, classes=None, sampleDl=0.1, method="baryce
     L = _lib.lib()
     M = C.c_size_t(0)
     h = C.c_void_p()
-    _lib.check(L.ssdr_grid_subsample(_lib.ptr(pts), _lib.ptr(feats), _lib.ptr(cls), N, fdim, ldim if use_classes else 0,
-                                     float(sampleDl), _default_order if order is None else
-                                     {"key": ORDER_KEY, "reference": ORDER_REFERENCE}.get(order, order),
-                                     C.byref(M), C.byref(h)))
+    _lib.check(L.ssdr_grid_subsample_typed(_lib.ptr(pts), _lib.ptr(feats), DTYPE_U8 if f_u8 else DTYPE_NATIVE,
+                                           _lib.ptr(cls), DTYPE_U8 if c_u8 else DTYPE_NATIVE, N, fdim,
+                                           ldim if use_classes else 0, float(sampleDl),
+                                           _default_order if order is None else
+                                           {"key": ORDER_KEY, "reference": ORDER_REFERENCE}.get(order, order),
+                                           C.byref(M), C.byref(h)))
     try:
         m = M.value
         if m < 1:

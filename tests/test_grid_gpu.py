@@ -237,3 +237,19 @@ def test_grid_slab_argument_errors(G):
     rc = _lib.lib().ssdr_grid_subsample_slab_dev(C.c_void_p(tp.data_ptr()), None, None, 100, 0, 0, 0.1, 1, None, 2,
                                                  0, 5, None, C.byref(M), C.byref(h))
     assert rc != 0 and b"whole cloud only" in _lib.lib().ssdr_last_error()
+
+
+def test_grid_uint8_inputs_widened_on_device_equal_host_conversion(G):
+    """uint8 colours / labels (what the reference's callers pass) are uploaded as bytes and widened on the device;
+    the result must be the bits of the host-converted float32 / int32 call, for 1 and 2 label columns."""
+    rng = np.random.default_rng(12)
+    p = _room(rng, 120_000)
+    rgb = rng.integers(0, 256, (len(p), 3)).astype(np.uint8)
+    for lab in (rng.integers(0, 13, len(p)).astype(np.uint8), rng.integers(0, 200, (len(p), 2)).astype(np.uint8)):
+        a = G.compute(p, features=rgb, classes=lab, sampleDl=0.05)
+        b = G.compute(p, features=rgb.astype(np.float32), classes=lab.astype(np.int32), sampleDl=0.05)
+        assert all(x.dtype == y.dtype and x.shape == y.shape and x.tobytes() == y.tobytes() for x, y in zip(a, b))
+        c = G.compute(p, features=rgb, classes=lab.astype(np.int32), sampleDl=0.05)  # mixed
+        assert all(x.tobytes() == y.tobytes() for x, y in zip(a, c))
+    only = G.compute(p, classes=rng.integers(0, 13, len(p)).astype(np.uint8), sampleDl=0.05)
+    assert only[1].dtype == np.int32 and only[1].shape[1] == 1
