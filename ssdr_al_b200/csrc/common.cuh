@@ -60,6 +60,7 @@ struct Ctx {
     cudaStream_t copy_stream = nullptr;  // result read-back that overlaps later kernels of the same call
     cudaEvent_t ev = nullptr;
     cudaEvent_t ev_main = nullptr;
+    cudaEvent_t ev_chunk[8] = {};   // one per result chunk in flight on the copy stream
     cudaEvent_t tev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};  // timing events (stats paths)
     DevBuf ws[WS_SLOTS];            // workspaces, addressed by the owning module
     PinBuf pin[4];                  // pinned staging

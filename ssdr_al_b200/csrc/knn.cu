@@ -341,13 +341,13 @@ template <int KCAP, typename OutT>
 __global__ void __launch_bounds__(128) query_kernel(const float4* __restrict__ spts, const float4* __restrict__ sq,
                                                     const unsigned* __restrict__ cell_start,
                                                     const ItemMeta* __restrict__ items, unsigned N, unsigned Q,
-                                                    unsigned total_q, int K, OutT* __restrict__ out,
+                                                    unsigned q_begin, unsigned q_end, int K, OutT* __restrict__ out,
                                                     unsigned* __restrict__ flag_count, unsigned* __restrict__ flag_list,
                                                     unsigned long long* __restrict__ evals) {
     constexpr unsigned FULL = 0xffffffffu;
-    const unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
-    const bool valid = t < total_q;
-    const unsigned tq = valid ? t : total_q - 1;  // idle lanes shadow the last query and never emit
+    const unsigned t = q_begin + blockIdx.x * blockDim.x + threadIdx.x;  // this launch covers sorted rows [begin, end)
+    const bool valid = t < q_end;
+    const unsigned tq = valid ? t : q_end - 1;  // idle lanes shadow the last query and never emit
     unsigned my_evals = 0;
     const unsigned b = tq / Q;
     const ItemMeta m = items[b];
@@ -510,6 +510,7 @@ __global__ void gather_rows_kernel(const unsigned* __restrict__ flag_list, const
     }
 }
 
+constexpr unsigned MAX_CHUNKS = 2;
 constexpr unsigned PATCH_CAP = 1u << 15;  // rows; more flagged rows than this fall back to a second full read-back
 
 // h_out (nullable, host entry points only, K <= N): the results are also delivered to this host buffer; the bulk
@@ -620,20 +621,43 @@ static int run_dev(Ctx* c, cudaStream_t s, const float* d_pts, size_t B, size_t 
     SSDR_CHECK_CUDA(cudaGetLastError());
     if (K > N) SSDR_CHECK_CUDA(cudaMemsetAsync(d_out, 0, (size_t)totalQ * K * sizeof(OutT), s));
 
-    const unsigned qblocks = (totalQ + 127) / 128;
     if (stats) SSDR_CHECK_CUDA(cudaEventRecord(c->tev[1], s));
-#define SSDR_QUERY(KC)                                                                                            \
-    query_kernel<KC, OutT><<<qblocks, 128, 0, s>>>(sort_p, sort_q, start_p, items, (unsigned)N, (unsigned)Q, totalQ, \
+    // Host entry points with a large result: the items are queried in a few launches and every finished chunk of rows
+    // starts its device->host copy at once (copy stream), so PCIe runs under the remaining launches.
+    const size_t out_bytes = (size_t)totalQ * K * sizeof(OutT);
+    struct CopyFence {  // no return path, error or not, may leave a copy into the caller's buffer in flight
+        cudaStream_t cs;
+        bool armed;
+        ~CopyFence() {
+            if (armed) cudaStreamSynchronize(cs);
+        }
+    } fence{c->copy_stream, h_out != nullptr};
+    // (two chunks only, and only for big results: a launch over fewer queries is hardly shorter -- its duration is set
+    // by the slowest warps -- so more chunks cost more kernel time than the copy overlap returns; measured)
+    const unsigned nchunk = (h_out && B >= 2 && out_bytes >= ((size_t)16 << 20)) ? MAX_CHUNKS : 1u;
+    for (unsigned ch = 0; ch < nchunk; ++ch) {
+        const unsigned b0 = (unsigned)(B * ch / nchunk), b1 = (unsigned)(B * (ch + 1) / nchunk);
+        const unsigned qb = b0 * (unsigned)Q, qe = b1 * (unsigned)Q;
+        const unsigned qblocks = (qe - qb + 127) / 128;
+#define SSDR_QUERY(KC)                                                                                          \
+    query_kernel<KC, OutT><<<qblocks, 128, 0, s>>>(sort_p, sort_q, start_p, items, (unsigned)N, (unsigned)Q, qb, qe, \
                                                    (int)K, d_out, &dstats->flag_count, flag_list, &dstats->evals)
-    if (K == 1) SSDR_QUERY(2);
-    else if (K <= 4) SSDR_QUERY(5);
-    else if (K <= 8) SSDR_QUERY(9);
-    else if (K <= 16) SSDR_QUERY(17);
-    else if (K <= 32) SSDR_QUERY(33);
-    else SSDR_QUERY(65);
+        if (K == 1) SSDR_QUERY(2);
+        else if (K <= 4) SSDR_QUERY(5);
+        else if (K <= 8) SSDR_QUERY(9);
+        else if (K <= 16) SSDR_QUERY(17);
+        else if (K <= 32) SSDR_QUERY(33);
+        else SSDR_QUERY(65);
 #undef SSDR_QUERY
-    SSDR_CHECK_CUDA(cudaGetLastError());
-    n_launch += 1;
+        SSDR_CHECK_CUDA(cudaGetLastError());
+        n_launch += 1;
+        if (nchunk > 1) {
+            SSDR_CHECK_CUDA(cudaEventRecord(c->ev_chunk[ch], s));
+            SSDR_CHECK_CUDA(cudaStreamWaitEvent(c->copy_stream, c->ev_chunk[ch], 0));
+            SSDR_CHECK_CUDA(cudaMemcpyAsync(h_out + (size_t)qb * K, d_out + (size_t)qb * K,
+                                            (size_t)(qe - qb) * K * sizeof(OutT), cudaMemcpyDeviceToHost, c->copy_stream));
+        }
+    }
     if (stats) SSDR_CHECK_CUDA(cudaEventRecord(c->tev[2], s));
 
     // ---- C: exact nanoflann replay of the flagged rows.  With K >= 8 and thousands of queries some row is flagged
@@ -645,13 +669,15 @@ static int run_dev(Ctx* c, cudaStream_t s, const float* d_pts, size_t B, size_t 
     DevStats hs;
     unsigned h_err = 0;
     const bool speculate = K >= 8 && totalQ >= 4096;
-    const size_t out_bytes = (size_t)totalQ * K * sizeof(OutT);
+    const bool bulk_copy = h_out && nchunk == 1;  // otherwise the rows are already on their way, chunk by chunk
     OutT* d_patch = nullptr;
     if (h_out) {
         SSDR_TRY(c->ws[WS_PATCH].reserve((size_t)PATCH_CAP * K * sizeof(OutT)));
         d_patch = c->ws[WS_PATCH].as<OutT>();
-        SSDR_CHECK_CUDA(cudaEventRecord(c->ev_main, s));
-        SSDR_CHECK_CUDA(cudaStreamWaitEvent(c->copy_stream, c->ev_main, 0));
+        if (bulk_copy) {
+            SSDR_CHECK_CUDA(cudaEventRecord(c->ev_main, s));
+            SSDR_CHECK_CUDA(cudaStreamWaitEvent(c->copy_stream, c->ev_main, 0));
+        }
     }
     auto tie_path = [&]() -> int {
         SSDR_TRY((kdtree::enqueue_tie_path<OutT>(c, s, d_pts, B, N, d_q, Q, K, d_out, flag_list, &dstats->flag_count,
@@ -666,12 +692,12 @@ static int run_dev(Ctx* c, cudaStream_t s, const float* d_pts, size_t B, size_t 
     };
     if (!speculate) {
         // (a pageable h_out makes this copy block the host; the count read below then simply follows it)
-        if (h_out) SSDR_CHECK_CUDA(cudaMemcpyAsync(h_out, d_out, out_bytes, cudaMemcpyDeviceToHost, c->copy_stream));
+        if (bulk_copy) SSDR_CHECK_CUDA(cudaMemcpyAsync(h_out, d_out, out_bytes, cudaMemcpyDeviceToHost, c->copy_stream));
         SSDR_TRY(d2h_sync(c, &hs, dstats, sizeof(DevStats), s));
         if (hs.flag_count) SSDR_TRY(tie_path());
     } else {
         SSDR_TRY(tie_path());
-        if (h_out) SSDR_CHECK_CUDA(cudaMemcpyAsync(h_out, d_out, out_bytes, cudaMemcpyDeviceToHost, c->copy_stream));
+        if (bulk_copy) SSDR_CHECK_CUDA(cudaMemcpyAsync(h_out, d_out, out_bytes, cudaMemcpyDeviceToHost, c->copy_stream));
     }
     if (stats) SSDR_CHECK_CUDA(cudaEventRecord(c->tev[3], s));
     if (speculate) SSDR_CHECK_CUDA(cudaMemcpyAsync(&hs, dstats, sizeof(DevStats), cudaMemcpyDeviceToHost, s));

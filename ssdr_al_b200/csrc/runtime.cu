@@ -92,6 +92,7 @@ int get_ctx(Ctx** out) {
         SSDR_CHECK_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
         SSDR_CHECK_CUDA(cudaEventCreateWithFlags(&c->ev, cudaEventDisableTiming));
         SSDR_CHECK_CUDA(cudaEventCreateWithFlags(&c->ev_main, cudaEventDisableTiming));
+        for (int i = 0; i < 8; ++i) SSDR_CHECK_CUDA(cudaEventCreateWithFlags(&c->ev_chunk[i], cudaEventDisableTiming));
         for (int i = 0; i < 5; ++i) SSDR_CHECK_CUDA(cudaEventCreate(&c->tev[i]));
         cudaMemPool_t pool;  // keep freed stream-ordered blocks cached instead of returning them to the driver
         if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
