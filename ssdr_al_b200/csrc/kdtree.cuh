@@ -1399,7 +1399,10 @@ __global__ void __launch_bounds__(32) exact_query_kernel(const float* __restrict
 enum { TW_BASE = 16 };  // workspace slots TW_BASE.. are owned by this header
 
 // Carve the tree arrays out of workspace slabs and zero the small control block.
+static void invalidate_tree_cache(const Ctx* c);
+
 static int alloc_tree(Ctx* c, cudaStream_t s, size_t B, size_t N, Tree* out) {
+    invalidate_tree_cache(c);  // the workspaces carved below are the ones a kept tree lives in
     const size_t cap = 3 * N + 64;
     const size_t lcap = B * (N / (LEAF + 1) + 2) + 16;
     SSDR_TRY(c->ws[TW_BASE + 0].reserve(B * N * (sizeof(float4) + 4 * sizeof(unsigned))));
@@ -1469,21 +1472,112 @@ static int check_tree_error(Ctx* c, cudaStream_t s, const Tree& t) {
     return SSDR_OK;
 }
 
+// ---- tree reuse across calls ------------------------------------------------------------------------------------
+// RandLA's pyramid asks for the same support cloud twice in a row (1-NN up-sampling onto level l+1, then the k=16
+// self-query of level l+1), and a tree is a pure function of its points: the last trees built by this thread stay
+// valid in their workspace until the next build, and a call with the same (B, N) first checks on the device that
+// every tree it needs was built and that its position-ordered points are bit-identical to the new cloud
+// (pp[i].xyz == pts[pp[i].index] for all i <=> same cloud, because the indices are a permutation).
+struct TreeCache {
+    const Ctx* owner = nullptr;
+    bool valid = false, pending = false;
+    size_t B = 0, N = 0;
+    Tree t;
+};
+static thread_local TreeCache g_tree_cache;
+
+static void invalidate_tree_cache(const Ctx* c) {
+    if (g_tree_cache.owner == c) g_tree_cache.valid = g_tree_cache.pending = false;
+}
+// after the call's final synchronisation: the trees enqueued by this call exist iff some row was flagged (the build
+// returns at once otherwise) and the build reported no error
+static void settle_tree_cache(const Ctx* c, bool trees_exist) {
+    if (g_tree_cache.owner == c && g_tree_cache.pending) {
+        g_tree_cache.valid = trees_exist;
+        g_tree_cache.pending = false;
+    }
+}
+
+__global__ void verify_tree_kernel(const float* __restrict__ pts_all, const float4* __restrict__ pp, unsigned B,
+                                   unsigned N, const unsigned char* __restrict__ needed,
+                                   const unsigned char* __restrict__ built, unsigned* __restrict__ mismatch) {
+    const unsigned long long total = (unsigned long long)B * N;
+    bool bad = false;
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (unsigned long long)gridDim.x * blockDim.x) {
+        const unsigned b = (unsigned)(i / N);
+        if (!needed[b]) continue;
+        if (!built[b]) {
+            bad = true;
+            continue;
+        }
+        const float4 v = pp[i];
+        const unsigned w = __float_as_uint(v.w);
+        if (w >= N) {
+            bad = true;
+            continue;
+        }
+        const float* p = pts_all + ((size_t)b * N + w) * 3;
+        bad |= __float_as_uint(v.x) != __float_as_uint(__ldg(p)) || __float_as_uint(v.y) != __float_as_uint(__ldg(p + 1)) ||
+               __float_as_uint(v.z) != __float_as_uint(__ldg(p + 2));
+    }
+    if (__any_sync(0xffffffffu, bad) && (threadIdx.x & 31) == 0) atomicOr(mismatch, 1u);
+}
+
 // Enqueue the whole tie path behind the main kernel WITHOUT a host round trip: mark the items that own flagged rows,
 // build their trees, overwrite the flagged rows with nanoflann's exact answer.  Every kernel reads the flagged-row
-// count on the device and returns at once when it is zero.  The caller checks t_out->error after its final sync.
+// count on the device and returns at once when it is zero.  The caller checks t_out->error after its final sync and
+// then calls settle_tree_cache.  *n_launch is advanced by the kernels launched here.
 template <typename OutT>
 static int enqueue_tie_path(Ctx* c, cudaStream_t s, const float* d_pts, size_t B, size_t N, const float* d_q, size_t Q,
                             size_t K, OutT* d_out, const unsigned* flag_list, const unsigned* d_flag_count,
-                            Tree* t_out, cudaEvent_t ev_mid = nullptr) {
+                            Tree* t_out, cudaEvent_t ev_mid, unsigned long long* n_launch, bool* reused) {
     SSDR_REQUIRE(K <= (size_t)MAX_K, SSDR_ERR_UNSUPPORTED, "K=%zu > %d in the exact tie path", K, MAX_K);
     Tree t;
-    SSDR_TRY(alloc_tree(c, s, B, N, &t));
-    unsigned char* needed = tree_needed_flags(t);
-    t.item_needed = needed;
-    t.n_flag = d_flag_count;
-    mark_items_kernel<<<64, 256, 0, s>>>(flag_list, d_flag_count, (unsigned)Q, needed);
-    SSDR_TRY(launch_build(c, s, d_pts, t));
+    *reused = false;
+    TreeCache& tc = g_tree_cache;
+    if (tc.valid && tc.owner == c && tc.B == B && tc.N == N) {
+        SSDR_TRY(c->ws[TW_BASE + 5].reserve(B + 64));
+        unsigned char* scratch = c->ws[TW_BASE + 5].as<unsigned char>();
+        unsigned* mismatch = reinterpret_cast<unsigned*>(scratch);
+        unsigned char* needed2 = scratch + 16;
+        SSDR_CHECK_CUDA(cudaMemsetAsync(scratch, 0, B + 64, s));
+        mark_items_kernel<<<64, 256, 0, s>>>(flag_list, d_flag_count, (unsigned)Q, needed2);
+        verify_tree_kernel<<<(unsigned)c->sm_count * 2, 256, 0, s>>>(d_pts, tc.t.pp, (unsigned)B, (unsigned)N, needed2,
+                                                                    tree_needed_flags(tc.t), mismatch);
+        SSDR_CHECK_CUDA(cudaGetLastError());
+        *n_launch += 2;
+        unsigned h_mismatch = 1;
+        SSDR_TRY(d2h_sync(c, &h_mismatch, mismatch, sizeof(unsigned), s));
+        if (!h_mismatch) {
+            t = tc.t;
+            t.n_flag = d_flag_count;
+            t.tstamps = nullptr;
+            *reused = true;
+        } else {
+            tc.valid = false;
+        }
+    }
+    if (!*reused) {
+        SSDR_TRY(alloc_tree(c, s, B, N, &t));
+        unsigned char* needed = tree_needed_flags(t);
+        t.item_needed = needed;
+        t.n_flag = d_flag_count;
+        if (B <= 8) {  // a handful of items: build them all (same latency), so that the next call can reuse every tree
+            SSDR_CHECK_CUDA(cudaMemsetAsync(needed, 1, B, s));
+        } else {
+            mark_items_kernel<<<64, 256, 0, s>>>(flag_list, d_flag_count, (unsigned)Q, needed);
+            *n_launch += 1;
+        }
+        SSDR_TRY(launch_build(c, s, d_pts, t));
+        *n_launch += 1;
+        tc.owner = c;
+        tc.B = B;
+        tc.N = N;
+        tc.t = t;
+        tc.valid = false;
+        tc.pending = true;
+    }
     if (ev_mid) SSDR_CHECK_CUDA(cudaEventRecord(ev_mid, s));
 #define SSDR_EXACT(KCV)                                                                                       \
     exact_query_kernel<OutT, KCV><<<(unsigned)c->sm_count * 16, 32, 0, s>>>(d_q, t, (unsigned)Q, (int)K, flag_list, \
@@ -1497,6 +1591,7 @@ static int enqueue_tie_path(Ctx* c, cudaStream_t s, const float* d_pts, size_t B
     else SSDR_EXACT(64);
 #undef SSDR_EXACT
     SSDR_CHECK_CUDA(cudaGetLastError());
+    *n_launch += 1;
     *t_out = t;
     return SSDR_OK;
 }

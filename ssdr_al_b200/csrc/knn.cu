@@ -679,10 +679,10 @@ static int run_dev(Ctx* c, cudaStream_t s, const float* d_pts, size_t B, size_t 
             SSDR_CHECK_CUDA(cudaStreamWaitEvent(c->copy_stream, c->ev_main, 0));
         }
     }
+    bool tree_reused = false;
     auto tie_path = [&]() -> int {
         SSDR_TRY((kdtree::enqueue_tie_path<OutT>(c, s, d_pts, B, N, d_q, Q, K, d_out, flag_list, &dstats->flag_count,
-                                                 &tree, stats ? c->tev[4] : nullptr)));
-        n_launch += 3;  // mark_items, build, exact_query
+                                                 &tree, stats ? c->tev[4] : nullptr, &n_launch, &tree_reused)));
         if (h_out) {
             gather_rows_kernel<OutT><<<64, 256, 0, s>>>(flag_list, &dstats->flag_count, d_out, (int)K, PATCH_CAP, d_patch);
             SSDR_CHECK_CUDA(cudaGetLastError());
@@ -722,8 +722,9 @@ static int run_dev(Ctx* c, cudaStream_t s, const float* d_pts, size_t B, size_t 
                 memcpy(h_out + (size_t)rows[i] * K, patch.data() + (size_t)i * K, K * sizeof(OutT));
         }
     }
+    kdtree::settle_tree_cache(c, hs.flag_count > 0 && h_err == 0);
     SSDR_TRY(kdtree::tree_error_to_status(h_err));
-    const unsigned long long builds = hs.flag_count ? B : 0;
+    const unsigned long long builds = (hs.flag_count && !tree_reused) ? B : 0;
     if (stats) {
         float ms = 0.f;
         SSDR_CHECK_CUDA(cudaEventElapsedTime(&ms, c->tev[0], c->tev[1]));

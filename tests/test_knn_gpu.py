@@ -168,3 +168,27 @@ def test_knn_interface_contract(NN):
         NN.knn(np.zeros((10, 2), np.float32), np.zeros((3, 2), np.float32), 2)
     with pytest.raises(NotImplementedError):
         NN.knn_batch_distance_pick(p[None], 10, 4)
+
+
+def test_tree_reuse_between_calls_is_content_checked(NN, oracle):
+    """The tie path keeps the last trees and reuses them when the next call brings the same support cloud (the
+    pyramid's 1-NN up-sampling followed by the k=16 self query).  Same shape with different content -- another
+    batch, or one moved point -- must rebuild; every answer equals the oracle."""
+    rng = np.random.default_rng(31)
+
+    def cloud(seed):  # quantised coordinates: ties in most rows, so the tie path always runs
+        r = np.random.default_rng(seed)
+        return (np.round(r.random((4, 3000, 3)) * 40) / 40).astype(np.float32)
+
+    a, b = cloud(1), cloud(2)
+    q = rng.random((4, 5000, 3)).astype(np.float32)
+    assert np.array_equal(NN.knn_batch(a, q, 1), oracle.knn_batch(a, q, 1, threads=4))       # builds the trees of a
+    assert np.array_equal(NN.knn_batch(a, a, 16), oracle.knn_batch(a, a, 16, threads=4))     # same cloud: reuse
+    assert np.array_equal(NN.knn_batch(a, q, 8), oracle.knn_batch(a, q, 8, threads=4))       # reuse again
+    assert np.array_equal(NN.knn_batch(b, b, 16), oracle.knn_batch(b, b, 16, threads=4))     # same shape, new content
+    c = b.copy()
+    c[2, 1234] += np.float32(0.5)                                                              # one point moved
+    assert np.array_equal(NN.knn_batch(c, c, 16), oracle.knn_batch(c, c, 16, threads=4))
+    assert np.array_equal(NN.knn_batch(b, b, 16), oracle.knn_batch(b, b, 16, threads=4))     # and back
+    one = a[:1]                                                                                # other batch size
+    assert np.array_equal(NN.knn_batch(one, one, 16), oracle.knn_batch(one, one, 16, threads=4))
