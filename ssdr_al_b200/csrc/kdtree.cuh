@@ -313,8 +313,10 @@ __device__ __forceinline__ void split_big(const Tree& t, unsigned g, int level, 
     const int cf = __float_as_int(s_bc[0]);
     const float cv = s_bc[1];
 
-    // planeSplit (:948-975)
+    // planeSplit (:948-975).  The second sweep ("<= cutval" over what the first left on the right) only moves points
+    // that EQUAL cutval: when the node has none (the usual case for an unclamped mid-plane) it is a no-op and skipped.
     unsigned start = l, lim1 = l, lim2 = l;
+    bool has_eq = false;
     for (int sweep = 0; sweep < 2; ++sweep) {
         unsigned long long carry = 0;
         for (unsigned base = start; base < r; base += BT * IPT_BIG) {
@@ -332,6 +334,7 @@ __device__ __forceinline__ void split_big(const Tree& t, unsigned g, int level, 
                     const float v = vals[k];
                     const bool sat = sweep == 0 ? (v < cv) : (v <= cv);
                     fl = sat ? 1ull : (1ull << 32);
+                    has_eq |= v == cv;
                 }
                 local += fl;
                 f[k] = local;
@@ -350,7 +353,7 @@ __device__ __forceinline__ void split_big(const Tree& t, unsigned g, int level, 
             }
             carry += tot;
         }
-        __syncthreads();
+        const bool any_eq = __syncthreads_or(has_eq) != 0;
         const unsigned tot_sat = r > start ? psat[r - 1] : 0u;
         const unsigned lim = start + tot_sat;
         const unsigned m = lim > start ? pfail[lim - 1] : 0u;  // misplaced pairs
@@ -374,6 +377,10 @@ __device__ __forceinline__ void split_big(const Tree& t, unsigned g, int level, 
         if (sweep == 0) {
             lim1 = lim;
             start = lim;
+            if (!any_eq) {
+                lim2 = lim;
+                break;
+            }
         } else {
             lim2 = lim;
         }
@@ -499,8 +506,10 @@ __device__ __forceinline__ void split_big_group(const Tree& t, unsigned g, int l
     float cv;
     decide_split(lo, hi, tmn, tmx, &cf, &cv);
 
-    // ---- planeSplit (:948-975), two sweeps
+    // ---- planeSplit (:948-975), two sweeps; the second one is skipped when no point of the node equals cutval
+    // (every member learns that from bit 31 of the members' false counts)
     unsigned start = l, lim1 = l, lim2 = l;
+    bool has_eq = false;
     for (int sweep = 0; sweep < 2; ++sweep) {
         unsigned* part = t.gpart + (((size_t)slot * 2 + sweep) * G) * 2;
         const unsigned cnt = r - start;
@@ -520,6 +529,7 @@ __device__ __forceinline__ void split_big_group(const Tree& t, unsigned g, int l
                     const float v = comp(__ldcg(pp + i), cf);
                     const bool sat = sweep == 0 ? (v < cv) : (v <= cv);
                     fl = sat ? 1ull : (1ull << 32);
+                    has_eq |= v == cv;
                 }
                 local += fl;
                 f[q] = local;
@@ -538,23 +548,27 @@ __device__ __forceinline__ void split_big_group(const Tree& t, unsigned g, int l
             }
             carry += tot;
         }
+        const bool cta_eq = __syncthreads_or(has_eq) != 0;
         if (tid == 0) {
             part[2 * s] = (unsigned)(carry & 0xFFFFFFFFull);
-            part[2 * s + 1] = (unsigned)(carry >> 32);
+            part[2 * s + 1] = (unsigned)(carry >> 32) | (cta_eq ? 0x80000000u : 0u);
         }
         group_sync(bar, k, phase);
         // A2: global ranks = member base + local counts (warp 0 sums the member totals, smem broadcasts them)
         if (warp == 0) {
-            unsigned bs = 0, bf = 0, ts = 0, mm = 0;
+            unsigned bs = 0, bf = 0, ts = 0, mm = 0, eqf = 0;
             const unsigned lim_guess_len = len;
             for (unsigned q = lane; q < k; q += 32) {
-                const unsigned ps = __ldcg(&part[2 * q]), pf = __ldcg(&part[2 * q + 1]);
+                const unsigned ps = __ldcg(&part[2 * q]), pfw = __ldcg(&part[2 * q + 1]);
+                const unsigned pf = pfw & 0x7FFFFFFFu;
+                eqf |= pfw >> 31;
                 if (q < s) {
                     bs += ps;
                     bf += pf;
                 }
                 ts += ps;
             }
+            eqf = __any_sync(0xffffffffu, eqf != 0) ? 1u : 0u;
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) {
                 bs += __shfl_xor_sync(0xffffffffu, bs, o);
@@ -564,7 +578,7 @@ __device__ __forceinline__ void split_big_group(const Tree& t, unsigned g, int l
             const unsigned lim_w = start + ts;
             if (lim_w > start) {  // misplaced pairs = predicate-false positions in [start, lim)
                 const unsigned sq = (lim_w - 1 - start) / lim_guess_len;  // member that owns position lim-1
-                for (unsigned q = lane; q < sq; q += 32) mm += __ldcg(&part[2 * q + 1]);
+                for (unsigned q = lane; q < sq; q += 32) mm += __ldcg(&part[2 * q + 1]) & 0x7FFFFFFFu;
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) mm += __shfl_xor_sync(0xffffffffu, mm, o);
                 mm += __ldcg(&pfail[lim_w - 1]);
@@ -574,11 +588,13 @@ __device__ __forceinline__ void split_big_group(const Tree& t, unsigned g, int l
                 s_red[1] = __uint_as_float(bf);
                 s_red[2] = __uint_as_float(ts);
                 s_red[3] = __uint_as_float(mm);
+                s_red[4] = __uint_as_float(eqf);
             }
         }
         __syncthreads();
         const unsigned base_sat = __float_as_uint(s_red[0]), base_fail = __float_as_uint(s_red[1]);
         const unsigned tot_sat = __float_as_uint(s_red[2]), m = __float_as_uint(s_red[3]);
+        const bool any_eq = __float_as_uint(s_red[4]) != 0u;
         const unsigned lim = start + tot_sat;
         for (unsigned i = a + tid; i < e; i += BT) {
             const unsigned ls = psat[i], lf = pfail[i];
@@ -601,6 +617,10 @@ __device__ __forceinline__ void split_big_group(const Tree& t, unsigned g, int l
         if (sweep == 0) {
             lim1 = lim;
             start = lim;
+            if (!any_eq) {  // same decision in every member: the barrier phases stay aligned
+                lim2 = lim;
+                break;
+            }
         } else {
             lim2 = lim;
         }
@@ -724,6 +744,7 @@ struct GroupScratch {
     float* red;        // [8 * NW]  per warp: bbox partials (6), cut-bound partials (2)
     unsigned* tot;     // [NW]      per warp: packed (true count | false count << 16) of the sweep
     unsigned* m;       // [NW]      per group (at its first warp): misplaced pairs of the sweep
+    unsigned* eq;      // [NW]      per warp: some point of its chunk equals the cut value
 };
 
 __device__ __forceinline__ void split_node_sm(const Tree& t, const SubCtx& sc, const Entry& e, int g, int off,
@@ -785,6 +806,7 @@ __device__ __forceinline__ void split_node_sm(const Tree& t, const SubCtx& sc, c
         const unsigned base = start + (unsigned)gw * W;
         unsigned bs[IPT_SUB], bf[IPT_SUB];
         unsigned wsat = 0, wfail = 0;
+        bool eq = false;
 #pragma unroll
         for (int k = 0; k < IPT_SUB; ++k) {
             bs[k] = bf[k] = 0u;
@@ -793,16 +815,22 @@ __device__ __forceinline__ void split_node_sm(const Tree& t, const SubCtx& sc, c
                 const bool in = p < count;
                 const float v = in ? sval[4 * p] : 0.f;
                 const bool sat = in && (sweep == 0 ? (v < cv) : (v <= cv));
+                eq |= in && v == cv;
                 bs[k] = __ballot_sync(FULL, sat);
                 bf[k] = __ballot_sync(FULL, in && !sat);
                 wsat += __popc(bs[k]);
                 wfail += __popc(bf[k]);
             }
         }
+        bool any_eq = __any_sync(FULL, eq);
         unsigned sat_before = 0, fail_before = 0, tot_sat = wsat;
         if (g > 1) {
-            if (lane == 0) gs.tot[warp] = wsat | (wfail << 16);
+            if (lane == 0) {
+                gs.tot[warp] = wsat | (wfail << 16);
+                gs.eq[warp] = any_eq ? 1u : 0u;
+            }
             group_bar(g, bid);
+            any_eq = __any_sync(FULL, lane < g && gs.eq[off + lane] != 0u);
             const unsigned x = lane < g ? gs.tot[off + lane] : 0u;
             unsigned incl = x;
 #pragma unroll
@@ -843,6 +871,10 @@ __device__ __forceinline__ void split_node_sm(const Tree& t, const SubCtx& sc, c
         if (sweep == 0) {
             lim1 = lim;
             start = lim;
+            if (!any_eq) {  // no point equals cutval: the "<=" sweep cannot move anything (group-uniform decision)
+                lim2 = lim;
+                break;
+            }
         } else {
             lim2 = lim;
         }
@@ -927,6 +959,7 @@ __device__ __forceinline__ void split_small_nodes(const Tree& t, const SubCtx& s
         unsigned tot_sat = 0;
         // rows any slice of the warp still needs (warp-uniform, so the ballots below stay convergent)
         const unsigned rows = __reduce_max_sync(FULL, (count - start + L - 1) / L);
+        bool eq = false;
 #pragma unroll
         for (int k = 0; k < IPT_SUB; ++k) {
             bs[k] = bf[k] = 0u;
@@ -935,6 +968,7 @@ __device__ __forceinline__ void split_small_nodes(const Tree& t, const SubCtx& s
             const bool in = p < count;
             const float v = in ? sval[4 * p] : 0.f;
             const bool sat = in && (sweep == 0 ? (v < cv) : (v <= cv));
+            eq |= in && v == cv;
             bs[k] = __ballot_sync(FULL, sat) & gmask;
             bf[k] = __ballot_sync(FULL, in && !sat) & gmask;
             tot_sat += __popc(bs[k]);
@@ -966,6 +1000,10 @@ __device__ __forceinline__ void split_small_nodes(const Tree& t, const SubCtx& s
         if (sweep == 0) {
             lim1 = lim;
             start = lim;
+            if (!__any_sync(FULL, eq)) {  // no node of this warp holds a point equal to its cutval: "<=" sweep is a no-op
+                lim2 = lim;
+                break;
+            }
         } else {
             lim2 = lim;
         }
@@ -990,7 +1028,7 @@ __device__ __forceinline__ void split_small_nodes(const Tree& t, const SubCtx& s
 }
 
 __device__ __forceinline__ void build_subtree(const Tree& t, unsigned groot, unsigned char* dsm, float* s_red8,
-                                              unsigned* s_tot, unsigned* s_m, unsigned* s_ctl,
+                                              unsigned* s_tot, unsigned* s_m, unsigned* s_eq, unsigned* s_ctl,
                                               unsigned char* s_slot /* [MAX_ROUNDS*NW] */,
                                               unsigned char* s_off /* [LIST_BIG] */) {
     // s_ctl: [0..5] counts of list 0 (big, small, 4 size classes), [6..11] of list 1, [12] nalloc, [13] base node id,
@@ -1042,6 +1080,7 @@ __device__ __forceinline__ void build_subtree(const Tree& t, unsigned groot, uns
     gs.red = s_red8;
     gs.tot = s_tot;
     gs.m = s_m;
+    gs.eq = s_eq;
     const bool ok = s_ctl[13] + 2u * count <= t.cap;
     unsigned short* cls = reinterpret_cast<unsigned short*>(dsm + SM_CLS);  // [2][4][LIST_SMALL]
     for (int lvl = 0; ok; ++lvl) {
@@ -1112,7 +1151,7 @@ __global__ void __launch_bounds__(BT, 1) build_kernel(const float* __restrict__ 
     __shared__ float s_red[8 * NW];
     __shared__ float s_bc[4];
     __shared__ unsigned s_ctl[16];
-    __shared__ unsigned s_tot[NW], s_m[NW];
+    __shared__ unsigned s_tot[NW], s_m[NW], s_eq[NW];
     __shared__ __align__(4) unsigned char s_slot[MAX_ROUNDS * NW];
     __shared__ unsigned char s_off[LIST_BIG];
     const unsigned tid = threadIdx.x;
@@ -1225,7 +1264,7 @@ __global__ void __launch_bounds__(BT, 1) build_kernel(const float* __restrict__ 
     // ---- SUBTREES (independent; no further grid barrier)
     const unsigned nsub = min(__ldcg(&t.list_cnt[MAX_LEVELS + 1]), t.lcap);
     for (unsigned i = blockIdx.x; i < nsub; i += gridDim.x)
-        build_subtree(t, __ldcg(t.sublist + i), dyn_smem, s_red, s_tot, s_m, s_ctl, s_slot, s_off);
+        build_subtree(t, __ldcg(t.sublist + i), dyn_smem, s_red, s_tot, s_m, s_eq, s_ctl, s_slot, s_off);
     mark(nullptr, t.tstamps, 11);  // CTA 0's own end
     if (t.tstamps && threadIdx.x == 0) atomicMax(&t.tstamps[12], gtimer());  // last CTA's end
 }
