@@ -72,6 +72,8 @@ struct Tree {
     NodeRec* nodes;        // [B*cap]
     float* nlo;            // [B*cap*3] loose bbox of top-level nodes and subtree roots
     float* nhi;
+    float* tmn;            // [B*cap*3] tight min / max of the node's points (computeMinMax), handed down by the parent's
+    float* tmx;            //           last pass so that a split starts without a pass of its own
     float* root_lo;        // [B*3] tight root bbox (computeBoundingBox :1241-1263)
     float* root_hi;
     unsigned* node_count;  // [B]
@@ -87,6 +89,51 @@ struct Tree {
     unsigned* error;       // bit 0: node capacity, bit 1: level cap, bit 2: DFS stack, bit 3: list capacity
     const unsigned char* item_needed;  // [B] build only where a flagged row lives (nullptr = all)
     unsigned long long* tstamps;       // [16] optional %globaltimer marks (diagnostics; nullptr = off)
+};
+
+__device__ __forceinline__ unsigned f2ord_u(float f) {
+    unsigned u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float ord2f_u(unsigned u) {
+    return __uint_as_float((u & 0x80000000u) ? (u & 0x7FFFFFFFu) : ~u);
+}
+// both children's tight bboxes, accumulated point by point (identity = +-inf)
+struct ChildBox {
+    float mn[2][3], mx[2][3];
+    __device__ __forceinline__ void init() {
+#pragma unroll
+        for (int c = 0; c < 2; ++c)
+#pragma unroll
+            for (int d = 0; d < 3; ++d) {
+                mn[c][d] = INFINITY;
+                mx[c][d] = -INFINITY;
+            }
+    }
+    __device__ __forceinline__ void add(const float4& v, bool right) {
+        mn[0][0] = fminf(mn[0][0], right ? INFINITY : v.x);
+        mn[0][1] = fminf(mn[0][1], right ? INFINITY : v.y);
+        mn[0][2] = fminf(mn[0][2], right ? INFINITY : v.z);
+        mx[0][0] = fmaxf(mx[0][0], right ? -INFINITY : v.x);
+        mx[0][1] = fmaxf(mx[0][1], right ? -INFINITY : v.y);
+        mx[0][2] = fmaxf(mx[0][2], right ? -INFINITY : v.z);
+        mn[1][0] = fminf(mn[1][0], right ? v.x : INFINITY);
+        mn[1][1] = fminf(mn[1][1], right ? v.y : INFINITY);
+        mn[1][2] = fminf(mn[1][2], right ? v.z : INFINITY);
+        mx[1][0] = fmaxf(mx[1][0], right ? v.x : -INFINITY);
+        mx[1][1] = fmaxf(mx[1][1], right ? v.y : -INFINITY);
+        mx[1][2] = fmaxf(mx[1][2], right ? v.z : -INFINITY);
+    }
+    // reduce over the lanes named in `mask` (redux.sync on order-preserving encodings); every lane of the mask gets it
+    __device__ __forceinline__ void reduce(unsigned mask) {
+#pragma unroll
+        for (int c = 0; c < 2; ++c)
+#pragma unroll
+            for (int d = 0; d < 3; ++d) {
+                mn[c][d] = ord2f_u(__reduce_min_sync(mask, f2ord_u(mn[c][d])));
+                mx[c][d] = ord2f_u(__reduce_max_sync(mask, f2ord_u(mx[c][d])));
+            }
+    }
 };
 
 __device__ __forceinline__ unsigned long long gtimer() {
@@ -212,8 +259,11 @@ __device__ __forceinline__ void store_split(const Tree& t, unsigned g, unsigned 
 
 // divideTree's bookkeeping for one TOP-LEVEL split (:877-892): children records, loose bboxes, work lists
 __device__ __forceinline__ void emit_children_top(const Tree& t, unsigned g, unsigned b, unsigned l, unsigned r,
-                                                  unsigned idx, int cf, float cv, float divlow, float divhigh,
-                                                  const float lo[3], const float hi[3], int level) {
+                                                  unsigned idx, int cf, float cv, const float cmn[2][3],
+                                                  const float cmx[2][3], const float lo[3], const float hi[3],
+                                                  int level) {
+    const float divlow = cf == 0 ? cmx[0][0] : (cf == 1 ? cmx[0][1] : cmx[0][2]);   // :886-887
+    const float divhigh = cf == 0 ? cmn[1][0] : (cf == 1 ? cmn[1][1] : cmn[1][2]);
     const unsigned a = atomicAdd(&t.node_count[b], 2u);
     if (a + 1 >= t.cap) {
         atomicOr(t.error, 1u);
@@ -227,6 +277,10 @@ __device__ __forceinline__ void emit_children_top(const Tree& t, unsigned g, uns
         t.nhi[(size_t)ga * 3 + d] = (d == cf) ? cv : hi[d];
         t.nlo[(size_t)gb * 3 + d] = (d == cf) ? cv : lo[d];
         t.nhi[(size_t)gb * 3 + d] = hi[d];
+        t.tmn[(size_t)ga * 3 + d] = cmn[0][d];
+        t.tmx[(size_t)ga * 3 + d] = cmx[0][d];
+        t.tmn[(size_t)gb * 3 + d] = cmn[1][d];
+        t.tmx[(size_t)gb * 3 + d] = cmx[1][d];
     }
     if (level + 1 >= MAX_LEVELS) {
         atomicOr(t.error, 2u);
@@ -269,49 +323,17 @@ __device__ __forceinline__ void split_big(const Tree& t, unsigned g, int level, 
         lo[d] = __ldcg(&t.nlo[(size_t)g * 3 + d]);
         hi[d] = __ldcg(&t.nhi[(size_t)g * 3 + d]);
     }
-    // computeMinMax (:827-836)
-    float mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
-    for (unsigned i = l + tid; i < r; i += BT) {
-        const float4 v = __ldcg(pp + i);
-        mn[0] = fminf(mn[0], v.x);
-        mx[0] = fmaxf(mx[0], v.x);
-        mn[1] = fminf(mn[1], v.y);
-        mx[1] = fmaxf(mx[1], v.y);
-        mn[2] = fminf(mn[2], v.z);
-        mx[2] = fmaxf(mx[2], v.z);
-    }
+    // computeMinMax (:827-836) was done by the parent's last pass (roots: the data bbox)
+    float amn[3], amx[3];
 #pragma unroll
     for (int d = 0; d < 3; ++d) {
-#pragma unroll
-        for (int m = 16; m > 0; m >>= 1) {
-            mn[d] = fminf(mn[d], __shfl_xor_sync(0xffffffffu, mn[d], m));
-            mx[d] = fmaxf(mx[d], __shfl_xor_sync(0xffffffffu, mx[d], m));
-        }
-        if (lane == 0) {
-            s_red[d * NW + warp] = mn[d];
-            s_red[(3 + d) * NW + warp] = mx[d];
-        }
+        amn[d] = __ldcg(&t.tmn[(size_t)g * 3 + d]);
+        amx[d] = __ldcg(&t.tmx[(size_t)g * 3 + d]);
     }
-    __syncthreads();
-    if (tid == 0) {
-        float amn[3], amx[3];
-        for (int d = 0; d < 3; ++d) {
-            amn[d] = s_red[d * NW];
-            amx[d] = s_red[(3 + d) * NW];
-            for (int w = 1; w < NW; ++w) {
-                amn[d] = fminf(amn[d], s_red[d * NW + w]);
-                amx[d] = fmaxf(amx[d], s_red[(3 + d) * NW + w]);
-            }
-        }
-        int cf;
-        float cv;
-        decide_split(lo, hi, amn, amx, &cf, &cv);
-        s_bc[0] = __int_as_float(cf);
-        s_bc[1] = cv;
-    }
-    __syncthreads();
-    const int cf = __float_as_int(s_bc[0]);
-    const float cv = s_bc[1];
+    int cf;
+    float cv;
+    decide_split(lo, hi, amn, amx, &cf, &cv);
+    (void)s_bc;
 
     // planeSplit (:948-975).  The second sweep ("<= cutval" over what the first left on the right) only moves points
     // that EQUAL cutval: when the node has none (the usual case for an unclamped mid-plane) it is a no-op and skipped.
@@ -390,28 +412,32 @@ __device__ __forceinline__ void split_big(const Tree& t, unsigned g, int level, 
     if (l1 > count / 2) idx = l1;
     else if (l2 < count / 2) idx = l2;
     else idx = count / 2;
-    float dlow = -INFINITY, dhigh = INFINITY;
-    for (unsigned i = l + tid; i < r; i += BT) {
-        const float v = comp(__ldcg(pp + i), cf);
-        if (i - l < idx) dlow = fmaxf(dlow, v);
-        else dhigh = fminf(dhigh, v);
-    }
-#pragma unroll
-    for (int m = 16; m > 0; m >>= 1) {
-        dlow = fmaxf(dlow, __shfl_xor_sync(0xffffffffu, dlow, m));
-        dhigh = fminf(dhigh, __shfl_xor_sync(0xffffffffu, dhigh, m));
-    }
+    // tight bboxes of both children in one pass (their computeMinMax; divlow/divhigh are two of the twelve values)
+    ChildBox cb;
+    cb.init();
+    for (unsigned i = l + tid; i < r; i += BT) cb.add(__ldcg(pp + i), i - l >= idx);
+    cb.reduce(0xffffffffu);
+    unsigned* sr = reinterpret_cast<unsigned*>(s_red);
+    __syncthreads();  // s_red may still be read by the sweeps' stragglers
+    if (tid < 12) sr[tid] = (tid % 6 < 3) ? 0xFFFFFFFFu : 0u;
+    __syncthreads();
     if (lane == 0) {
-        s_red[warp] = dlow;
-        s_red[NW + warp] = dhigh;
+#pragma unroll
+        for (int c2 = 0; c2 < 2; ++c2)
+#pragma unroll
+            for (int d = 0; d < 3; ++d) {
+                atomicMin(&sr[c2 * 6 + d], f2ord_u(cb.mn[c2][d]));
+                atomicMax(&sr[c2 * 6 + 3 + d], f2ord_u(cb.mx[c2][d]));
+            }
     }
     __syncthreads();
     if (tid == 0) {
-        for (int w = 1; w < NW; ++w) {
-            dlow = fmaxf(dlow, s_red[w]);
-            dhigh = fminf(dhigh, s_red[NW + w]);
-        }
-        emit_children_top(t, g, b, l, r, idx, cf, cv, dlow, dhigh, lo, hi, level);
+        for (int c2 = 0; c2 < 2; ++c2)
+            for (int d = 0; d < 3; ++d) {
+                cb.mn[c2][d] = ord2f_u(sr[c2 * 6 + d]);
+                cb.mx[c2][d] = ord2f_u(sr[c2 * 6 + 3 + d]);
+            }
+        emit_children_top(t, g, b, l, r, idx, cf, cv, cb.mn, cb.mx, lo, hi, level);
     }
 }
 
@@ -431,13 +457,6 @@ __device__ __forceinline__ void group_sync(unsigned* counter, unsigned k, unsign
     }
     __syncthreads();
 }
-__device__ __forceinline__ unsigned f2ord_u(float f) {
-    unsigned u = __float_as_uint(f);
-    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
-}
-__device__ __forceinline__ float ord2f_u(unsigned u) {
-    return __uint_as_float((u & 0x80000000u) ? (u & 0x7FFFFFFFu) : ~u);
-}
 
 __device__ __forceinline__ void split_big_group(const Tree& t, unsigned g, int level, unsigned slot, unsigned k,
                                                 unsigned s, unsigned long long* s_warp, float* s_red) {
@@ -451,7 +470,7 @@ __device__ __forceinline__ void split_big_group(const Tree& t, unsigned g, int l
     unsigned* psat = t.psat + (size_t)b * t.N;
     unsigned* pfail = t.pfail + (size_t)b * t.N;
     unsigned* bar = t.gbar + (size_t)level * G + slot;
-    unsigned* red = t.gred + ((size_t)level * G + slot) * 8;
+    unsigned* red = t.gred + ((size_t)level * G + slot) * 12;
     unsigned phase = 0;
     const unsigned l = __ldcg(&t.nodes[g].l), r = __ldcg(&t.nodes[g].r);
     const unsigned count = r - l;
@@ -461,46 +480,12 @@ __device__ __forceinline__ void split_big_group(const Tree& t, unsigned g, int l
         lo[d] = __ldcg(&t.nlo[(size_t)g * 3 + d]);
         hi[d] = __ldcg(&t.nhi[(size_t)g * 3 + d]);
     }
-    // ---- M: computeMinMax over the member's slice, combined with order-preserving atomics (identity 0)
-    {
-        const unsigned len = (count + k - 1) / k;
-        const unsigned a = min(l + s * len, r), e = min(a + len, r);
-        float mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
-        for (unsigned i = a + tid; i < e; i += BT) {
-            const float4 v = __ldcg(pp + i);
-            mn[0] = fminf(mn[0], v.x);
-            mx[0] = fmaxf(mx[0], v.x);
-            mn[1] = fminf(mn[1], v.y);
-            mx[1] = fmaxf(mx[1], v.y);
-            mn[2] = fminf(mn[2], v.z);
-            mx[2] = fmaxf(mx[2], v.z);
-        }
-#pragma unroll
-        for (int d = 0; d < 3; ++d) {
-#pragma unroll
-            for (int m = 16; m > 0; m >>= 1) {
-                mn[d] = fminf(mn[d], __shfl_xor_sync(0xffffffffu, mn[d], m));
-                mx[d] = fmaxf(mx[d], __shfl_xor_sync(0xffffffffu, mx[d], m));
-            }
-            if (lane == 0) {
-                s_red[d * NW + warp] = mn[d];
-                s_red[(3 + d) * NW + warp] = mx[d];
-            }
-        }
-        __syncthreads();
-        if (tid < 6) {  // one atomic per CTA and quantity; +-inf (empty slice) never reaches the atomics
-            float v = s_red[tid * NW];
-            for (int w = 1; w < NW; ++w) v = tid < 3 ? fminf(v, s_red[tid * NW + w]) : fmaxf(v, s_red[tid * NW + w]);
-            if (tid < 3 && v != INFINITY) atomicMax(&red[tid], ~f2ord_u(v));
-            if (tid >= 3 && v != -INFINITY) atomicMax(&red[tid], f2ord_u(v));
-        }
-    }
-    group_sync(bar, k, phase);
+    // computeMinMax was done by the parent's last pass (roots: the data bbox)
     float tmn[3], tmx[3];
 #pragma unroll
     for (int d = 0; d < 3; ++d) {
-        tmn[d] = ord2f_u(~__ldcg(&red[d]));
-        tmx[d] = ord2f_u(__ldcg(&red[3 + d]));
+        tmn[d] = __ldcg(&t.tmn[(size_t)g * 3 + d]);
+        tmx[d] = __ldcg(&t.tmx[(size_t)g * 3 + d]);
     }
     int cf;
     float cv;
@@ -630,40 +615,39 @@ __device__ __forceinline__ void split_big_group(const Tree& t, unsigned g, int l
     if (l1 > count / 2) idx = l1;
     else if (l2 < count / 2) idx = l2;
     else idx = count / 2;
-    // ---- F: divlow / divhigh over the member's slice
+    // ---- F: both children's tight bboxes over the member's slice (identity 0: [c*6+d] = ~ord(min), [c*6+3+d] = ord(max))
     {
         const unsigned len = (count + k - 1) / k;
         const unsigned a = min(l + s * len, r), e = min(a + len, r);
-        float dlow = -INFINITY, dhigh = INFINITY;
-        for (unsigned i = a + tid; i < e; i += BT) {
-            const float v = comp(__ldcg(pp + i), cf);
-            if (i - l < idx) dlow = fmaxf(dlow, v);
-            else dhigh = fminf(dhigh, v);
-        }
-#pragma unroll
-        for (int m = 16; m > 0; m >>= 1) {
-            dlow = fmaxf(dlow, __shfl_xor_sync(0xffffffffu, dlow, m));
-            dhigh = fminf(dhigh, __shfl_xor_sync(0xffffffffu, dhigh, m));
-        }
+        ChildBox cb;
+        cb.init();
+        for (unsigned i = a + tid; i < e; i += BT) cb.add(__ldcg(pp + i), i - l >= idx);
+        cb.reduce(0xffffffffu);
+        unsigned* sr = reinterpret_cast<unsigned*>(s_red);
         __syncthreads();  // s_red still holds the A2 broadcast of the last sweep
+        if (tid < 12) sr[tid] = 0u;
+        __syncthreads();
         if (lane == 0) {
-            s_red[warp] = dlow;
-            s_red[NW + warp] = dhigh;
+#pragma unroll
+            for (int c2 = 0; c2 < 2; ++c2)
+#pragma unroll
+                for (int d = 0; d < 3; ++d) {
+                    if (cb.mn[c2][d] != INFINITY) atomicMax(&sr[c2 * 6 + d], ~f2ord_u(cb.mn[c2][d]));
+                    if (cb.mx[c2][d] != -INFINITY) atomicMax(&sr[c2 * 6 + 3 + d], f2ord_u(cb.mx[c2][d]));
+                }
         }
         __syncthreads();
-        if (tid == 0) {
-            for (int w = 1; w < NW; ++w) {
-                dlow = fmaxf(dlow, s_red[w]);
-                dhigh = fminf(dhigh, s_red[NW + w]);
-            }
-            if (dlow != -INFINITY) atomicMax(&red[6], f2ord_u(dlow));
-            if (dhigh != INFINITY) atomicMax(&red[7], ~f2ord_u(dhigh));
-        }
+        if (tid < 12 && sr[tid] != 0u) atomicMax(&red[tid], sr[tid]);
     }
     group_sync(bar, k, phase);
     if (s == 0 && tid == 0) {
-        const float dlow = ord2f_u(__ldcg(&red[6])), dhigh = ord2f_u(~__ldcg(&red[7]));
-        emit_children_top(t, g, b, l, r, idx, cf, cv, dlow, dhigh, lo, hi, level);
+        float cmn[2][3], cmx[2][3];
+        for (int c2 = 0; c2 < 2; ++c2)
+            for (int d = 0; d < 3; ++d) {
+                cmn[c2][d] = ord2f_u(~__ldcg(&red[c2 * 6 + d]));
+                cmx[c2][d] = ord2f_u(__ldcg(&red[c2 * 6 + 3 + d]));
+            }
+        emit_children_top(t, g, b, l, r, idx, cf, cv, cmn, cmx, lo, hi, level);
     }
 }
 
@@ -1148,7 +1132,7 @@ __device__ __forceinline__ void build_subtree(const Tree& t, unsigned groot, uns
 __global__ void __launch_bounds__(BT, 1) build_kernel(const float* __restrict__ pts_all, const Tree t) {
     extern __shared__ __align__(16) unsigned char dyn_smem[];
     __shared__ unsigned long long s_warp[32];
-    __shared__ float s_red[8 * NW];
+    __shared__ float s_red[12 * NW];
     __shared__ float s_bc[4];
     __shared__ unsigned s_ctl[16];
     __shared__ unsigned s_tot[NW], s_m[NW], s_eq[NW];
@@ -1218,6 +1202,8 @@ __global__ void __launch_bounds__(BT, 1) build_kernel(const float* __restrict__ 
                     const float lo_ = ord2f_u(~__ldcg(&rr[d])), hi_ = ord2f_u(__ldcg(&rr[3 + d]));
                     t.nlo[(size_t)g * 3 + d] = lo_;
                     t.nhi[(size_t)g * 3 + d] = hi_;
+                    t.tmn[(size_t)g * 3 + d] = lo_;  // the root's loose bbox IS the data min/max
+                    t.tmx[(size_t)g * 3 + d] = hi_;
                     t.root_lo[b * 3 + d] = lo_;
                     t.root_hi[b * 3 + d] = hi_;
                 }
@@ -1445,12 +1431,12 @@ static int alloc_tree(Ctx* c, cudaStream_t s, size_t B, size_t N, Tree* out) {
     const size_t cap = 3 * N + 64;
     const size_t lcap = B * (N / (LEAF + 1) + 2) + 16;
     SSDR_TRY(c->ws[TW_BASE + 0].reserve(B * N * (sizeof(float4) + 4 * sizeof(unsigned))));
-    SSDR_TRY(c->ws[TW_BASE + 1].reserve(B * cap * (sizeof(NodeRec) + 6 * sizeof(float))));
+    SSDR_TRY(c->ws[TW_BASE + 1].reserve(B * cap * (sizeof(NodeRec) + 12 * sizeof(float))));
     SSDR_TRY(c->ws[TW_BASE + 2].reserve(3 * lcap * sizeof(unsigned)));
     const size_t ctl_words = 6 * B + B + (size_t)(MAX_LEVELS + 2) + 8 + (B + 3) / 4 + 4 + 8 * B;
     SSDR_TRY(c->ws[TW_BASE + 3].reserve(ctl_words * sizeof(unsigned)));
     const size_t G = (size_t)c->sm_count;
-    const size_t grp_words = (size_t)MAX_GROUP_LEVELS * G * 9 + G * 2 * G * 2;
+    const size_t grp_words = (size_t)MAX_GROUP_LEVELS * G * 13 + G * 2 * G * 2;
     SSDR_TRY(c->ws[TW_BASE + 4].reserve(grp_words * sizeof(unsigned)));
     Tree t;
     t.N = (unsigned)N;
@@ -1466,6 +1452,8 @@ static int alloc_tree(Ctx* c, cudaStream_t s, size_t B, size_t N, Tree* out) {
     t.nodes = c->ws[TW_BASE + 1].as<NodeRec>();
     t.nlo = reinterpret_cast<float*>(t.nodes + B * cap);
     t.nhi = t.nlo + B * cap * 3;
+    t.tmn = t.nhi + B * cap * 3;
+    t.tmx = t.tmn + B * cap * 3;
     t.list = c->ws[TW_BASE + 2].as<unsigned>();
     t.sublist = t.list + 2 * lcap;
     unsigned* ctl = c->ws[TW_BASE + 3].as<unsigned>();
@@ -1478,8 +1466,8 @@ static int alloc_tree(Ctx* c, cudaStream_t s, size_t B, size_t N, Tree* out) {
     t.error = t.barrier + 4;
     t.gbar = c->ws[TW_BASE + 4].as<unsigned>();
     t.gred = t.gbar + (size_t)MAX_GROUP_LEVELS * G;
-    t.gpart = t.gred + (size_t)MAX_GROUP_LEVELS * G * 8;
-    SSDR_CHECK_CUDA(cudaMemsetAsync(t.gbar, 0, (size_t)MAX_GROUP_LEVELS * G * 9 * sizeof(unsigned), s));
+    t.gpart = t.gred + (size_t)MAX_GROUP_LEVELS * G * 12;
+    SSDR_CHECK_CUDA(cudaMemsetAsync(t.gbar, 0, (size_t)MAX_GROUP_LEVELS * G * 13 * sizeof(unsigned), s));
     t.root_red = t.error + 4 + (B + 3) / 4 + 1;
     t.n_flag = nullptr;
     t.item_needed = nullptr;
