@@ -6,16 +6,19 @@
 // divfeat/divlow/divhigh -- as ONE persistent cooperative launch for all batch items.  The working array is
 // position-ordered float4 (x, y, z, point index), i.e. nanoflann's vind with the coordinates carried along, so
 // every pass is a coalesced stream and the later search reads a leaf with one load per point:
-//   * TOP: nodes with more than MED_MAX points are split level by level from global memory, one CTA per node
-//     (block-wide prefix counts), a grid barrier between levels;
+//   * TOP: nodes with more than MED_MAX points are split level by level from global memory -- one CTA per node, or a
+//     group of CTAs per node (private group barrier, per-member partial counts) while a level has fewer nodes than
+//     SMs -- with a grid barrier between levels; a node's tight bbox (computeMinMax) comes from its parent's last pass;
 //   * SUBTREES: every node of <= MED_MAX points is handed to one CTA that loads it into shared memory ONCE and grows
 //     its whole subtree there -- groups of 2..32 warps (named barriers) for nodes > PER_WARP points, and 1..8 nodes
-//     per warp below that (aligned lane slices, masked ballot/popc prefix
-//     counts) -- with block barriers only, then writes the permuted points back;
-//   * computeMinMax is a warp/block min-max reduction; each of planeSplit's two Hoare sweeps is a prefix count: the
-//     k-th misplaced element from the left swaps with the k-th misplaced element from the right (SURVEY.md A.5;
-//     checked against the sequential code in tools/proto_kdtree.py and
-//     tests/test_knn_gpu.py::test_device_tree_equals_sequential_tree).
+//     per warp below that (aligned lane slices, masked ballot/popc prefix counts) -- then writes the permuted
+//     points back;
+//   * each of planeSplit's two Hoare sweeps is a prefix count: the k-th misplaced element from the left swaps with
+//     the k-th misplaced element from the right (checked against the sequential code in
+//     tools/proto_kdtree.py and tests/test_knn_gpu.py::test_device_tree_equals_sequential_tree); the second sweep
+//     only moves points equal to the cut value and is skipped when the node has none;
+//   * the last trees stay valid in their workspace: a later call with the same support cloud (checked on the device)
+//     reuses them instead of building again.
 // exact_query_kernel replays findNeighbors/searchLevel (:1163-1178, :1270-1328) and KNNResultSet::addPoint
 // (:72-96) with one thread per flagged query, an explicit stack and one 32-byte node record per visit.
 #pragma once
@@ -305,7 +308,7 @@ __device__ __forceinline__ void emit_children_top(const Tree& t, unsigned g, uns
 
 // ---- TOP: one CTA splits one node of > MED_MAX points over global memory ----------------------------------------
 __device__ __forceinline__ void split_big(const Tree& t, unsigned g, int level, unsigned long long* s_warp,
-                                          float* s_red, float* s_bc) {
+                                          float* s_red) {
     const unsigned tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
     const unsigned b = g / t.cap;
@@ -333,7 +336,6 @@ __device__ __forceinline__ void split_big(const Tree& t, unsigned g, int level, 
     int cf;
     float cv;
     decide_split(lo, hi, amn, amx, &cf, &cv);
-    (void)s_bc;
 
     // planeSplit (:948-975).  The second sweep ("<= cutval" over what the first left on the right) only moves points
     // that EQUAL cutval: when the node has none (the usual case for an unclamped mid-plane) it is a no-op and skipped.
@@ -1133,7 +1135,6 @@ __global__ void __launch_bounds__(BT, 1) build_kernel(const float* __restrict__ 
     extern __shared__ __align__(16) unsigned char dyn_smem[];
     __shared__ unsigned long long s_warp[32];
     __shared__ float s_red[12 * NW];
-    __shared__ float s_bc[4];
     __shared__ unsigned s_ctl[16];
     __shared__ unsigned s_tot[NW], s_m[NW], s_eq[NW];
     __shared__ __align__(4) unsigned char s_slot[MAX_ROUNDS * NW];
@@ -1241,7 +1242,7 @@ __global__ void __launch_bounds__(BT, 1) build_kernel(const float* __restrict__ 
             if (slot < nbig) split_big_group(t, __ldcg(cur + slot), level, slot, kgrp, blockIdx.x % kgrp, s_warp, s_red);
         } else {
             for (unsigned i = blockIdx.x; i < nbig; i += gridDim.x)
-                split_big(t, __ldcg(cur + i), level, s_warp, s_red, s_bc);
+                split_big(t, __ldcg(cur + i), level, s_warp, s_red);
         }
         grid_sync(t.barrier, phase);
         if (level < 8) mark(nullptr, t.tstamps, 2 + level);
@@ -1487,15 +1488,6 @@ static int launch_build(Ctx* c, cudaStream_t s, const float* d_pts, const Tree& 
     Tree tt = t;
     void* args[] = {(void*)&pts, (void*)&tt};
     SSDR_CHECK_CUDA(cudaLaunchCooperativeKernel((void*)build_kernel, dim3(c->sm_count), dim3(BT), args, smem, s));
-    return SSDR_OK;
-}
-
-static int check_tree_error(Ctx* c, cudaStream_t s, const Tree& t) {
-    unsigned h_err = 0;
-    SSDR_TRY(d2h_sync(c, &h_err, t.error, sizeof(unsigned), s));
-    SSDR_REQUIRE(h_err == 0, SSDR_ERR_UNSUPPORTED,
-                 "exact tie path gave up (flags %u: 1 node capacity, 2 more than %d tree levels, 4 search stack deeper "
-                 "than %d, 8 work list capacity)", h_err, MAX_LEVELS, MAX_DEPTH);
     return SSDR_OK;
 }
 
