@@ -174,7 +174,7 @@ __global__ void cell_scatter_kernel(SortJob jp, SortJob jq) {
 // in shared memory, scatter -- instead of six launches; the lower pyramid levels are pure launch latency otherwise.
 constexpr int SG_THREADS = 512;
 constexpr unsigned SG_MAX_CELLS = 16384;  // cstride limit (64 KB of dynamic shared memory)
-constexpr unsigned SG_MAX_POINTS = 8192;
+constexpr unsigned SG_MAX_POINTS = 16384;
 
 __device__ __forceinline__ unsigned local_cell(const ItemMeta& m, float x, float y, float z) {
     const int cx = cell_coord(x, m.lo[0], m.inv_h, m.g[0]);
