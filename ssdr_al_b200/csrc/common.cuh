@@ -40,14 +40,6 @@ struct DevBuf {
     template <typename T>
     T* as() const { return reinterpret_cast<T*>(p); }
 };
-struct PinBuf {
-    void* p = nullptr;
-    size_t cap = 0;
-    int reserve(size_t bytes);
-    void release();
-    template <typename T>
-    T* as() const { return reinterpret_cast<T*>(p); }
-};
 
 enum { WS_SLOTS = 24 };
 
@@ -63,14 +55,13 @@ struct Ctx {
     cudaEvent_t ev_chunk[8] = {};   // one per result chunk in flight on the copy stream
     cudaEvent_t tev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};  // timing events (stats paths)
     DevBuf ws[WS_SLOTS];            // workspaces, addressed by the owning module
-    PinBuf pin[4];                  // pinned staging
 };
 
 // Returns the calling thread's context for its current device (creating it on first use).
 int get_ctx(Ctx** out);
 
-// Host -> device copy of `bytes` from an arbitrary host pointer.  Pinned/registered sources go straight to
-// cudaMemcpyAsync; pageable sources are pipelined through two pinned staging chunks.
+// Host -> device copy of `bytes` from an arbitrary host pointer on stream s (pinned sources are truly asynchronous;
+// pageable ones are staged by the driver and return once the source may be reused).
 int h2d(Ctx* c, void* dst, const void* src, size_t bytes, cudaStream_t s);
 // Device -> host, synchronous on return (the caller's buffer is valid afterwards).
 int d2h_sync(Ctx* c, void* dst, const void* src, size_t bytes, cudaStream_t s);

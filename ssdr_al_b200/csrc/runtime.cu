@@ -42,26 +42,6 @@ void DevBuf::release() {
     p = nullptr;
     cap = 0;
 }
-int PinBuf::reserve(size_t bytes) {
-    if (bytes <= cap) return SSDR_OK;
-    if (p) cudaFreeHost(p);
-    p = nullptr;
-    cap = 0;
-    cudaError_t e = cudaHostAlloc(&p, bytes, cudaHostAllocDefault);
-    if (e != cudaSuccess) {
-        p = nullptr;
-        cudaGetLastError();
-        return set_error(SSDR_ERR_NOMEM, "cudaHostAlloc(%zu bytes) failed: %s", bytes, cudaGetErrorString(e));
-    }
-    cap = bytes;
-    return SSDR_OK;
-}
-void PinBuf::release() {
-    if (p) cudaFreeHost(p);
-    p = nullptr;
-    cap = 0;
-}
-
 enum { MAX_DEV = 16 };
 static thread_local Ctx g_ctx[MAX_DEV];
 
