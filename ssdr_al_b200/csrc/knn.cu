@@ -510,6 +510,99 @@ __global__ void gather_rows_kernel(const unsigned* __restrict__ flag_list, const
     }
 }
 
+// ---- B' (tiny clouds): brute force, one warp per query -------------------------------------------------------------
+// Up to 1024 support points per item (the lowest pyramid levels): no cell grid at all.  The CTA keeps the item's points
+// in shared memory, every lane of a warp holds the distances to SLOTS of them in registers (same fp32 expression as
+// everywhere), and min(K+1, N) rounds of a warp-wide arg-min on (distance, index) peel off the neighbours in order.
+// Rows with equal distances inside the top K, or a (near) tie between rank K and K+1, are flagged for the tie path
+// exactly like in query_kernel, so the contract is the same: unflagged rows are final.
+constexpr int TINY_MAX_POINTS = 1024;
+constexpr int TINY_WARPS = 16;
+constexpr int TINY_Q_PER_WARP = 1;
+
+template <int SLOTS, typename OutT>
+__global__ void __launch_bounds__(TINY_WARPS * 32) tiny_query_kernel(const float* __restrict__ pts_all,
+                                                                    const float* __restrict__ q_all, unsigned N,
+                                                                    unsigned Q, int K, OutT* __restrict__ out,
+                                                                    unsigned* __restrict__ flag_count,
+                                                                    unsigned* __restrict__ flag_list,
+                                                                    unsigned long long* __restrict__ evals) {
+    constexpr unsigned FULL = 0xffffffffu;
+    __shared__ float sx[TINY_MAX_POINTS], sy[TINY_MAX_POINTS], sz[TINY_MAX_POINTS];
+    const unsigned qblocks = (Q + TINY_WARPS * TINY_Q_PER_WARP - 1) / (TINY_WARPS * TINY_Q_PER_WARP);
+    const unsigned b = blockIdx.x / qblocks, qblk = blockIdx.x % qblocks;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const float* p = pts_all + (size_t)b * N * 3;
+    for (unsigned i = threadIdx.x; i < N; i += blockDim.x) {
+        sx[i] = __ldg(p + 3 * (size_t)i);
+        sy[i] = __ldg(p + 3 * (size_t)i + 1);
+        sz[i] = __ldg(p + 3 * (size_t)i + 2);
+    }
+    __syncthreads();
+    const int nvalid = (unsigned)K < N ? K : (int)N;
+    const int rounds = N > (unsigned)K ? K + 1 : (int)N;
+    const unsigned q0 = (qblk * TINY_WARPS + warp) * TINY_Q_PER_WARP;
+    for (unsigned qi = q0; qi < q0 + TINY_Q_PER_WARP && qi < Q; ++qi) {
+        const float* qp = q_all + ((size_t)b * Q + qi) * 3;
+        const float qx = __ldg(qp), qy = __ldg(qp + 1), qz = __ldg(qp + 2);
+        float d[SLOTS];
+#pragma unroll
+        for (int s = 0; s < SLOTS; ++s) {
+            const unsigned i = (unsigned)s * 32u + (unsigned)lane;  // slot order == index order inside a lane
+            d[s] = INFINITY;
+            if (i < N) {
+                const float dx = __fsub_rn(qx, sx[i]), dy = __fsub_rn(qy, sy[i]), dz = __fsub_rn(qz, sz[i]);
+                d[s] = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+            }
+        }
+        OutT* o = out + ((size_t)b * Q + qi) * (size_t)K;
+        bool flag = false;
+        float prev = 0.f;
+        for (int j = 0; j < rounds; ++j) {
+            // lane-local minimum, lowest index first (strict '<' over ascending slots)
+            float bd = d[0];
+            int bs = 0;
+#pragma unroll
+            for (int s = 1; s < SLOTS; ++s)
+                if (d[s] < bd) {
+                    bd = d[s];
+                    bs = s;
+                }
+            unsigned bi = (unsigned)bs * 32u + (unsigned)lane;
+            // warp arg-min on (distance, index)
+            float wd = bd;
+            unsigned wi = bi;
+#pragma unroll
+            for (int m = 16; m > 0; m >>= 1) {
+                const float od = __shfl_xor_sync(FULL, wd, m);
+                const unsigned oi = __shfl_xor_sync(FULL, wi, m);
+                if (od < wd || (od == wd && oi < wi)) {
+                    wd = od;
+                    wi = oi;
+                }
+            }
+            if (wi == bi) {  // the owner retires the slot
+#pragma unroll
+                for (int s = 0; s < SLOTS; ++s)
+                    if (s == bs) d[s] = INFINITY;
+            }
+            if (j < nvalid) {
+                if (lane == 0) o[j] = (OutT)wi;
+                if (j > 0 && wd == prev) flag = true;
+            } else if (wd <= prev * 1.00001f) {  // j == K: (near) tie between rank K and K+1
+                flag = true;
+            }
+            prev = wd;
+        }
+        if (flag && lane == 0) flag_list[atomicAdd(flag_count, 1u)] = b * Q + qi;
+    }
+    if (threadIdx.x == 0) {
+        const unsigned first = qblk * TINY_WARPS * TINY_Q_PER_WARP;
+        const unsigned nq = first < Q ? min(Q - first, (unsigned)(TINY_WARPS * TINY_Q_PER_WARP)) : 0u;
+        if (nq) atomicAdd(evals, (unsigned long long)nq * N);
+    }
+}
+
 constexpr unsigned MAX_CHUNKS = 2;
 constexpr unsigned PATCH_CAP = 1u << 15;  // rows; more flagged rows than this fall back to a second full read-back
 
@@ -567,9 +660,15 @@ static int run_dev(Ctx* c, cudaStream_t s, const float* d_pts, size_t B, size_t 
 
     unsigned long long n_launch = 0;
     if (stats) SSDR_CHECK_CUDA(cudaEventRecord(c->tev[0], s));
-    const bool small = cstride <= SG_MAX_CELLS && N <= SG_MAX_POINTS && Q <= 8 * SG_MAX_POINTS;
+    // tiny clouds: brute force beats any index (and needs none) while the evaluations stay in the tens of millions
+    // (its cost is ~220 warp instructions per arg-min round and query; beyond ~160k rounds the indexed kernel's better
+    // instruction economy wins over its latency)
+    const bool tiny = N <= (size_t)TINY_MAX_POINTS && (size_t)totalQ * ((K < N ? K + 1 : N)) <= (size_t)160 * 1024;
+    const bool small = !tiny && cstride <= SG_MAX_CELLS && N <= SG_MAX_POINTS && Q <= 8 * SG_MAX_POINTS;
     float4* sort_q_buf = self ? nullptr : c->ws[WS_SORT_Q].as<float4>();
-    if (small) {  // one CTA per item does the whole grid build
+    if (tiny) {
+        SSDR_CHECK_CUDA(cudaMemsetAsync(ctl, 0, 16 * 4, s));  // counters only: no cell grid
+    } else if (small) {  // one CTA per item does the whole grid build
         SSDR_CHECK_CUDA(cudaMemsetAsync(ctl, 0, 16 * 4, s));
         static bool attr_set_dev[64] = {};
         bool& attr_set = attr_set_dev[c->device & 63];
@@ -634,8 +733,22 @@ static int run_dev(Ctx* c, cudaStream_t s, const float* d_pts, size_t B, size_t 
     } fence{c->copy_stream, h_out != nullptr};
     // (two chunks only, and only for big results: a launch over fewer queries is hardly shorter -- its duration is set
     // by the slowest warps -- so more chunks cost more kernel time than the copy overlap returns; measured)
-    const unsigned nchunk = (h_out && B >= 2 && out_bytes >= ((size_t)16 << 20)) ? MAX_CHUNKS : 1u;
-    for (unsigned ch = 0; ch < nchunk; ++ch) {
+    const unsigned nchunk = (!tiny && h_out && B >= 2 && out_bytes >= ((size_t)16 << 20)) ? MAX_CHUNKS : 1u;
+    if (tiny) {
+        const unsigned per_cta = TINY_WARPS * TINY_Q_PER_WARP;
+        const unsigned tblocks = (unsigned)B * (unsigned)((Q + per_cta - 1) / per_cta);
+#define SSDR_TINY(SL)                                                                                              \
+    tiny_query_kernel<SL, OutT><<<tblocks, TINY_WARPS * 32, 0, s>>>(d_pts, d_q, (unsigned)N, (unsigned)Q, (int)K, d_out, \
+                                                                    &dstats->flag_count, flag_list, &dstats->evals)
+        if (N <= 128) SSDR_TINY(4);
+        else if (N <= 256) SSDR_TINY(8);
+        else if (N <= 512) SSDR_TINY(16);
+        else SSDR_TINY(32);
+#undef SSDR_TINY
+        SSDR_CHECK_CUDA(cudaGetLastError());
+        n_launch += 1;
+    }
+    for (unsigned ch = 0; !tiny && ch < nchunk; ++ch) {
         const unsigned b0 = (unsigned)(B * ch / nchunk), b1 = (unsigned)(B * (ch + 1) / nchunk);
         const unsigned qb = b0 * (unsigned)Q, qe = b1 * (unsigned)Q;
         const unsigned qblocks = (qe - qb + 127) / 128;
@@ -660,15 +773,15 @@ static int run_dev(Ctx* c, cudaStream_t s, const float* d_pts, size_t B, size_t 
     }
     if (stats) SSDR_CHECK_CUDA(cudaEventRecord(c->tev[2], s));
 
-    // ---- C: exact nanoflann replay of the flagged rows.  With K >= 8 and thousands of queries some row is flagged
-    // almost surely (boundary near-ties alone hit ~1.5e-5*K of the rows), so the tie path is enqueued right behind
-    // the main kernel without a host round trip (its kernels return at once if the device-side count is zero).
+    // ---- C: exact nanoflann replay of the flagged rows.  Boundary near-ties alone flag ~1.5e-5*K of the rows, so a
+    // call with K * queries >= 131072 has flagged rows almost surely and the tie path is enqueued right behind the
+    // main kernel without a host round trip (its kernels return at once if the device-side count is zero).
     // Otherwise ties are rare: read the count first and skip the (cooperative, whole-GPU) launch when it is zero.
     kdtree::Tree tree;
     tree.error = nullptr;
     DevStats hs;
     unsigned h_err = 0;
-    const bool speculate = K >= 8 && totalQ >= 4096;
+    const bool speculate = (size_t)totalQ * K >= 131072;  // expected flagged rows ~ 1.5e-5 * K * queries >= 2
     const bool bulk_copy = h_out && nchunk == 1;  // otherwise the rows are already on their way, chunk by chunk
     OutT* d_patch = nullptr;
     if (h_out) {
