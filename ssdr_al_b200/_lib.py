@@ -92,8 +92,10 @@ def check(status):
 
 
 def ptr(a):
-    """void* of a numpy array (None -> NULL)."""
-    return None if a is None else a.ctypes.data_as(vp)
+    """Address of a numpy array for a c_void_p argument (None -> NULL).  The integer from __array_interface__ is
+    several times cheaper than a.ctypes.data_as(...), which matters for the small calls of the pyramid's lower levels;
+    the caller keeps `a` alive across the foreign call."""
+    return None if a is None else a.__array_interface__["data"][0]
 
 
 def device_count():
@@ -110,10 +112,10 @@ class _PinnedBlock(object):
     """A CUDA pinned host allocation that returns itself to the pool when the last numpy view dies."""
     __slots__ = ("ptr", "nbytes", "__array_interface__", "__weakref__")
 
-    def __init__(self, ptr, nbytes):
+    def __init__(self, ptr, nbytes, shape, typestr):
         self.ptr = ptr
         self.nbytes = nbytes
-        self.__array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 3}
+        self.__array_interface__ = {"shape": shape, "typestr": typestr, "data": (ptr, False), "version": 3}
 
     def __del__(self):
         try:
@@ -131,8 +133,10 @@ def pinned_empty(shape, dtype):
     The memory goes back to a pool when the array is garbage collected, so every call still returns an independent
     array like np.empty does."""
     dtype = np.dtype(dtype)
-    count = int(np.prod(shape))
-    nbytes = count * dtype.itemsize
+    shape = tuple(int(v) for v in shape)
+    nbytes = dtype.itemsize
+    for v in shape:
+        nbytes *= v
     if nbytes == 0:
         return np.empty(shape, dtype)
     cls = 1 << max(12, (nbytes - 1).bit_length())  # power-of-two size classes
@@ -143,8 +147,7 @@ def pinned_empty(shape, dtype):
         p = vp()
         check(lib().ssdr_host_alloc(C.byref(p), cls))
         ptr = p.value
-    block = _PinnedBlock(ptr, cls)
-    return np.asarray(block)[:nbytes].view(dtype).reshape(shape)
+    return np.asarray(_PinnedBlock(ptr, cls, shape, dtype.str))  # one array object; its base keeps the block alive
 
 
 def pinned_zeros(shape, dtype):

@@ -730,7 +730,7 @@ static int run_dev(Ctx* c, cudaStream_t s, const float* d_pts, size_t B, size_t 
         ~CopyFence() {
             if (armed) cudaStreamSynchronize(cs);
         }
-    } fence{c->copy_stream, h_out != nullptr};
+    } fence{c->copy_stream, false};
     // (two chunks only, and only for big results: a launch over fewer queries is hardly shorter -- its duration is set
     // by the slowest warps -- so more chunks cost more kernel time than the copy overlap returns; measured)
     const unsigned nchunk = (!tiny && h_out && B >= 2 && out_bytes >= ((size_t)16 << 20)) ? MAX_CHUNKS : 1u;
@@ -765,6 +765,7 @@ static int run_dev(Ctx* c, cudaStream_t s, const float* d_pts, size_t B, size_t 
         SSDR_CHECK_CUDA(cudaGetLastError());
         n_launch += 1;
         if (nchunk > 1) {
+            fence.armed = true;
             SSDR_CHECK_CUDA(cudaEventRecord(c->ev_chunk[ch], s));
             SSDR_CHECK_CUDA(cudaStreamWaitEvent(c->copy_stream, c->ev_chunk[ch], 0));
             SSDR_CHECK_CUDA(cudaMemcpyAsync(h_out + (size_t)qb * K, d_out + (size_t)qb * K,
@@ -783,11 +784,15 @@ static int run_dev(Ctx* c, cudaStream_t s, const float* d_pts, size_t B, size_t 
     unsigned h_err = 0;
     const bool speculate = (size_t)totalQ * K >= 131072;  // expected flagged rows ~ 1.5e-5 * K * queries >= 2
     const bool bulk_copy = h_out && nchunk == 1;  // otherwise the rows are already on their way, chunk by chunk
+    // small results are not worth a second stream (event + wait + extra synchronisation cost more than they hide)
+    const bool side_copy = bulk_copy && out_bytes >= ((size_t)1 << 20);
+    cudaStream_t cs = side_copy ? c->copy_stream : s;
     OutT* d_patch = nullptr;
     if (h_out) {
         SSDR_TRY(c->ws[WS_PATCH].reserve((size_t)PATCH_CAP * K * sizeof(OutT)));
         d_patch = c->ws[WS_PATCH].as<OutT>();
-        if (bulk_copy) {
+        if (side_copy) {
+            fence.armed = true;
             SSDR_CHECK_CUDA(cudaEventRecord(c->ev_main, s));
             SSDR_CHECK_CUDA(cudaStreamWaitEvent(c->copy_stream, c->ev_main, 0));
         }
@@ -805,12 +810,12 @@ static int run_dev(Ctx* c, cudaStream_t s, const float* d_pts, size_t B, size_t 
     };
     if (!speculate) {
         // (a pageable h_out makes this copy block the host; the count read below then simply follows it)
-        if (bulk_copy) SSDR_CHECK_CUDA(cudaMemcpyAsync(h_out, d_out, out_bytes, cudaMemcpyDeviceToHost, c->copy_stream));
+        if (bulk_copy) SSDR_CHECK_CUDA(cudaMemcpyAsync(h_out, d_out, out_bytes, cudaMemcpyDeviceToHost, cs));
         SSDR_TRY(d2h_sync(c, &hs, dstats, sizeof(DevStats), s));
         if (hs.flag_count) SSDR_TRY(tie_path());
     } else {
         SSDR_TRY(tie_path());
-        if (bulk_copy) SSDR_CHECK_CUDA(cudaMemcpyAsync(h_out, d_out, out_bytes, cudaMemcpyDeviceToHost, c->copy_stream));
+        if (bulk_copy) SSDR_CHECK_CUDA(cudaMemcpyAsync(h_out, d_out, out_bytes, cudaMemcpyDeviceToHost, cs));
     }
     if (stats) SSDR_CHECK_CUDA(cudaEventRecord(c->tev[3], s));
     if (speculate) SSDR_CHECK_CUDA(cudaMemcpyAsync(&hs, dstats, sizeof(DevStats), cudaMemcpyDeviceToHost, s));
@@ -826,7 +831,7 @@ static int run_dev(Ctx* c, cudaStream_t s, const float* d_pts, size_t B, size_t 
             SSDR_CHECK_CUDA(cudaMemcpyAsync(patch.data(), d_patch, (size_t)nf * K * sizeof(OutT), cudaMemcpyDeviceToHost, s));
             SSDR_CHECK_CUDA(cudaStreamSynchronize(s));
         }
-        SSDR_CHECK_CUDA(cudaStreamSynchronize(c->copy_stream));  // never return with a copy into h_out in flight
+        if (fence.armed) SSDR_CHECK_CUDA(cudaStreamSynchronize(c->copy_stream));  // all rows have landed
         SSDR_TRY(rc);
         if (hs.flag_count > PATCH_CAP) {
             SSDR_TRY(d2h_sync(c, h_out, d_out, out_bytes, s));
