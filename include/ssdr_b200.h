@@ -77,6 +77,14 @@ typedef struct {
     uint64_t kernel_launches; /* kernels of this library the call launched (memsets and copies not counted) */
 } ssdr_knn_stats;
 
+/* knn_batch on batch items that are slices of larger arrays: item b of the points starts at
+ * batch_data + b * data_item_stride floats (>= npts * dim; 0 = dense), likewise for the queries.  This is what
+ * RandLA-Net's pyramid passes (s3dis_dataset.py:166 `batch_xyz[:, :N // ratio, :]`); the reference first packs such a
+ * view on the host (np.ascontiguousarray, knn.pyx:95-96), here the copy engine packs it during the upload. */
+int ssdr_knn_batch_strided(const float* batch_data, size_t batch_size, size_t npts, size_t dim, size_t data_item_stride,
+                           const float* queries, size_t nqueries, size_t query_item_stride, size_t K,
+                           int64_t* batch_indices);
+
 /* Device-resident variant: d_points (B,npts,3), d_queries (B,nqueries,3), d_indices (B,nqueries,K) int64.
  * Enqueues on `stream`; stats (nullable, host struct) forces a stream synchronisation when requested. */
 int ssdr_knn_batch_dev(const float* d_points, size_t batch_size, size_t npts, const float* d_queries,

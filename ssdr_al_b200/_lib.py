@@ -36,6 +36,7 @@ SIGNATURES = {
     "ssdr_host_free": [vp],
     "ssdr_knn": [vp, sz, sz, vp, sz, sz, vp],
     "ssdr_knn_batch": [vp, sz, sz, sz, vp, sz, sz, vp],
+    "ssdr_knn_batch_strided": [vp, sz, sz, sz, sz, vp, sz, sz, sz, vp],
     "ssdr_knn_batch_dev": [vp, sz, sz, vp, sz, sz, vp, vp, C.POINTER(KnnStats)],
     "ssdr_knn_batch_dev_i32": [vp, sz, sz, vp, sz, sz, vp, vp, C.POINTER(KnnStats)],
     "ssdr_knn_debug_tree": [vp, sz, vp, vp, vp, vp, vp, vp, vp, vp, vp],

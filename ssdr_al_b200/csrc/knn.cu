@@ -866,20 +866,31 @@ static int run_dev(Ctx* c, cudaStream_t s, const float* d_pts, size_t B, size_t 
 }
 
 template <typename OutT>
-static int run_host(const float* pts, size_t B, size_t N, size_t dim, const float* q, size_t Q, size_t K, OutT* out) {
+static int run_host(const float* pts, size_t B, size_t N, size_t dim, const float* q, size_t Q, size_t K, OutT* out,
+                    size_t pts_stride = 0, size_t q_stride = 0) {  // floats between batch items (0 = dense)
     SSDR_REQUIRE(pts && q && out, SSDR_ERR_INVALID, "NULL pointer");
     SSDR_REQUIRE(dim == 3, SSDR_ERR_UNSUPPORTED, "dim=%zu: only 3-D points are supported", dim);
     Ctx* c;
     SSDR_TRY(get_ctx(&c));
     if (B == 0 || Q == 0) return SSDR_OK;
     SSDR_REQUIRE(N >= 1, SSDR_ERR_INVALID, "npts must be >= 1 (the reference asserts npts != 0)");
-    const bool self = (q == pts && Q == N);
+    if (pts_stride == 0) pts_stride = N * 3;
+    if (q_stride == 0) q_stride = Q * 3;
+    SSDR_REQUIRE(pts_stride >= N * 3 && q_stride >= Q * 3, SSDR_ERR_INVALID, "item stride shorter than one item");
+    const bool self = (q == pts && Q == N && q_stride == pts_stride);
+    // items that are slices of a larger array (the pyramid's xyz[:, :N/ratio, :]) are packed by the copy engine
+    auto upload = [&](void* dst, const float* src, size_t n, size_t stride) -> int {
+        if (stride == n * 3 || B == 1) return h2d(c, dst, src, B * n * 3 * sizeof(float), c->stream);
+        SSDR_CHECK_CUDA(cudaMemcpy2DAsync(dst, n * 3 * sizeof(float), src, stride * sizeof(float), n * 3 * sizeof(float), B,
+                                          cudaMemcpyHostToDevice, c->stream));
+        return SSDR_OK;
+    };
     SSDR_TRY(c->ws[WS_IN_P].reserve(B * N * 3 * sizeof(float)));
-    SSDR_TRY(h2d(c, c->ws[WS_IN_P].p, pts, B * N * 3 * sizeof(float), c->stream));
+    SSDR_TRY(upload(c->ws[WS_IN_P].p, pts, N, pts_stride));
     const float* d_q = c->ws[WS_IN_P].as<float>();
     if (!self) {
         SSDR_TRY(c->ws[WS_IN_Q].reserve(B * Q * 3 * sizeof(float)));
-        SSDR_TRY(h2d(c, c->ws[WS_IN_Q].p, q, B * Q * 3 * sizeof(float), c->stream));
+        SSDR_TRY(upload(c->ws[WS_IN_Q].p, q, Q, q_stride));
         d_q = c->ws[WS_IN_Q].as<float>();
     }
     SSDR_TRY(c->ws[WS_OUT].reserve(B * Q * K * sizeof(OutT)));
@@ -908,6 +919,12 @@ int ssdr_knn_batch(const float* batch_data, size_t batch_size, size_t npts, size
                    size_t nqueries, size_t K, int64_t* batch_indices) {
     return knn::run_host<long long>(batch_data, batch_size, npts, dim, queries, nqueries, K,
                                     reinterpret_cast<long long*>(batch_indices));
+}
+int ssdr_knn_batch_strided(const float* batch_data, size_t batch_size, size_t npts, size_t dim, size_t data_item_stride,
+                           const float* queries, size_t nqueries, size_t query_item_stride, size_t K,
+                           int64_t* batch_indices) {
+    return knn::run_host<long long>(batch_data, batch_size, npts, dim, queries, nqueries, K,
+                                    reinterpret_cast<long long*>(batch_indices), data_item_stride, query_item_stride);
 }
 int ssdr_knn_batch_dev(const float* d_points, size_t batch_size, size_t npts, const float* d_queries, size_t nqueries,
                        size_t K, int64_t* d_indices, void* stream, ssdr_knn_stats* stats) {

@@ -22,15 +22,28 @@ def knn(pts, queries, K, omp=False):
     return indices
 
 
+def _batch_view(a):
+    """(array, item stride in floats) for a (B, n, 3) float32 array whose items are dense but possibly spaced out --
+    a slice `x[:, :n, :]` of a C-contiguous array -- so that it can be uploaded without packing it on the host first;
+    anything else goes through np.ascontiguousarray like in knn.pyx:95-96."""
+    if (isinstance(a, np.ndarray) and a.dtype == np.float32 and a.ndim == 3 and a.shape[0] > 0 and a.shape[1] > 0
+            and a.strides[2] == 4 and a.strides[1] == 4 * a.shape[2] and a.strides[0] % 4 == 0
+            and a.strides[0] >= a.shape[1] * a.shape[2] * 4):
+        return a, a.strides[0] // 4
+    c = np.ascontiguousarray(a, dtype=np.float32)
+    return c, (c.shape[1] * c.shape[2] if c.ndim == 3 else 0)
+
+
 def knn_batch(pts, queries, K, omp=False):
     """knn.pyx:71-109."""
-    pts_c = np.ascontiguousarray(pts, dtype=np.float32)
-    queries_c = np.ascontiguousarray(queries, dtype=np.float32)
+    pts_c, ps = _batch_view(pts)
+    queries_c, qs = (pts_c, ps) if queries is pts else _batch_view(queries)
     _check_dim(pts_c.shape[2])
     indices = (_lib.pinned_zeros if K > pts_c.shape[1] else _lib.pinned_empty)(
         (pts_c.shape[0], queries_c.shape[1], K), np.int64)
-    _lib.check(_lib.lib().ssdr_knn_batch(_lib.ptr(pts_c), pts_c.shape[0], pts_c.shape[1], pts_c.shape[2],
-                                         _lib.ptr(queries_c), queries_c.shape[1], int(K), _lib.ptr(indices)))
+    _lib.check(_lib.lib().ssdr_knn_batch_strided(_lib.ptr(pts_c), pts_c.shape[0], pts_c.shape[1], pts_c.shape[2], ps,
+                                                 _lib.ptr(queries_c), queries_c.shape[1], qs, int(K),
+                                                 _lib.ptr(indices)))
     return indices
 
 

@@ -192,3 +192,22 @@ def test_tree_reuse_between_calls_is_content_checked(NN, oracle):
     assert np.array_equal(NN.knn_batch(b, b, 16), oracle.knn_batch(b, b, 16, threads=4))     # and back
     one = a[:1]                                                                                # other batch size
     assert np.array_equal(NN.knn_batch(one, one, 16), oracle.knn_batch(one, one, 16, threads=4))
+
+
+def test_knn_batch_accepts_slices_views_and_other_dtypes(NN, oracle):
+    """Batch items that are slices of a larger array are uploaded without a host-side packing copy; every other
+    layout (reversed, transposed, float64, lists) takes the reference's np.ascontiguousarray route.  Same answers."""
+    rng = np.random.default_rng(8)
+    base = rng.random((3, 5000, 3)).astype(np.float32)
+    want = oracle.knn_batch(np.ascontiguousarray(base[:, :1200]), np.ascontiguousarray(base[:, 100:4100]), 5, threads=4)
+    pts, q = base[:, :1200], base[:, 100:4100]
+    assert not pts.flags["C_CONTIGUOUS"]
+    assert np.array_equal(NN.knn_batch(pts, q, 5), want)
+    assert np.array_equal(NN.knn_batch(pts.astype(np.float64), q.tolist(), 5), want)
+    rev = np.ascontiguousarray(base[:, :1200][:, ::-1])[:, ::-1]          # negative stride view of the same values
+    assert np.array_equal(NN.knn_batch(rev, q, 5), want)
+    t = np.ascontiguousarray(base.transpose(1, 0, 2)).transpose(1, 0, 2)   # item-interleaved memory
+    assert np.array_equal(NN.knn_batch(t[:, :1200], t[:, 100:4100], 5), want)
+    self_want = oracle.knn_batch(np.ascontiguousarray(pts), np.ascontiguousarray(pts), 16, threads=4)
+    assert np.array_equal(NN.knn_batch(pts, pts, 16), self_want)
+    assert np.array_equal(NN.knn_batch(base[1:2, :1200], base[1:2, :1200], 16), self_want[1:2])
