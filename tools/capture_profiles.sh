@@ -15,8 +15,8 @@ ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file $O/${
     python tools/prof_select.py grid > /dev/null 2>&1
 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file $O/${R}_launches_fps32.csv \
     python tools/prof_select.py fps32 50 > /dev/null 2>&1
-# full captures (query: first launch of the 3rd pyramid = level 0, k=16, 245760 queries)
-$NCU_FULL -k regex:^query_kernel -s 20 -c 1 -o $O/${R}_ncu_knn_query python tools/prof_knn.py 3 > /dev/null 2>&1
+# full captures (query: first of the five query_kernel launches of the 3rd pyramid = level 0, k=16, 245760 queries)
+$NCU_FULL -k regex:^query_kernel -s 10 -c 1 -o $O/${R}_ncu_knn_query python tools/prof_knn.py 3 > /dev/null 2>&1
 $NCU_FULL -k regex:^build_kernel -s 2 -c 1 -o $O/${R}_ncu_knn_build python tools/prof_tree.py 6 40960 > /dev/null 2>&1
 $NCU_FULL -k regex:^exact_query_kernel -s 0 -c 3 -o $O/${R}_ncu_knn_exact python tools/prof_knn.py 1 > /dev/null 2>&1
 $NCU_FULL -k regex:^small_grid_kernel -s 0 -c 2 -o $O/${R}_ncu_knn_small_grid python tools/prof_knn.py 1 > /dev/null 2>&1
