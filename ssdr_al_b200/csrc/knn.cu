@@ -44,8 +44,28 @@ __device__ __forceinline__ float ord2f(unsigned u) {
 // ---- A1+A2: bounding box per item, then (last block) the cell grid geometry --------------------------------------
 // enc holds order-preserving encodings combined with atomicMax and identity 0: [0..2] = ~ord(min), [3..5] = ord(max),
 // so one memset prepares it together with the counters.
+// Occupancy probe: non-empty cubes of the bbox at two nested resolutions (r2 cubes along the longest edge, and half of
+// that).  Their ratio is the cloud's box-counting dimension d at the scale that matters -- ~3 for points filling a
+// volume, ~2 for scanned surfaces, which is what the real inputs are -- and n2 anchors the density, so the cell edge
+// can be chosen for a target number of points per NON-EMPTY cell instead of per bbox volume (for surfaces the latter
+// puts tens of points into every occupied cell and multiplies the distance evaluations per query).
+struct Probe {
+    unsigned r2;      // 0: no probe (small clouds), volumetric rule
+    unsigned n1, n2;  // non-empty cubes at edge 2*E/r2 and E/r2
+};
+constexpr unsigned PROBE_MIN_POINTS = 4096;
+constexpr unsigned PROBE_MAX_R = 64;
+constexpr unsigned PROBE_WORDS = PROBE_MAX_R * PROBE_MAX_R * PROBE_MAX_R / 32 + (PROBE_MAX_R / 2) * (PROBE_MAX_R / 2) * (PROBE_MAX_R / 2) / 32;
+
+__host__ __device__ inline unsigned probe_resolution(unsigned N) {
+    if (N < PROBE_MIN_POINTS) return 0;
+    unsigned r = (unsigned)cbrtf((float)N / 16.f);  // ~16 points per cube if the cloud filled its bbox
+    r &= ~1u;                                       // even, so that the coarse cubes are unions of 8 fine ones
+    return r < 4 ? 4 : (r > PROBE_MAX_R ? PROBE_MAX_R : r);
+}
+
 __device__ void setup_item(const unsigned* __restrict__ enc, ItemMeta* __restrict__ items, int b, unsigned N,
-                           float occupancy, unsigned cell_cap, unsigned cstride) {
+                           float occupancy, unsigned cell_cap, unsigned cstride, Probe pr = Probe{0, 0, 0}) {
     ItemMeta m;
     float ext[3], E = 0.f, amax = 0.f;
     for (int d = 0; d < 3; ++d) {
@@ -62,6 +82,13 @@ __device__ void setup_item(const unsigned* __restrict__ enc, ItemMeta* __restric
         float vol = 1.f;
         for (int d = 0; d < 3; ++d) vol *= fmaxf(ext[d], E * 1e-3f);
         float h = cbrtf(vol * occupancy / (float)N);
+        if (pr.r2 && pr.n1 >= 1 && pr.n2 >= pr.n1) {
+            float dim = log2f((float)pr.n2 / (float)pr.n1);
+            dim = fminf(fmaxf(dim, 1.f), 3.f);
+            const float per_cube = (float)N / (float)pr.n2;          // points per non-empty cube of edge E / r2
+            const float target = occupancy * (1.f + 0.75f * (3.f - dim));  // flatter clouds: fewer occupied neighbours
+            h = (E / (float)pr.r2) * powf(target / per_cube, 1.f / dim);
+        }
         h = fmaxf(h, E * (1.f / 1000.f));
         for (;;) {
             double cells = 1.0;
@@ -83,7 +110,7 @@ __device__ void setup_item(const unsigned* __restrict__ enc, ItemMeta* __restric
 
 __global__ void bbox_setup_kernel(const float* __restrict__ pts, unsigned N, unsigned* __restrict__ enc,
                                   unsigned* __restrict__ ticket, ItemMeta* __restrict__ items, int B, float occupancy,
-                                  unsigned cell_cap, unsigned cstride) {
+                                  unsigned cell_cap, unsigned cstride, bool defer_setup) {
     const unsigned b = blockIdx.y;
     const float* p = pts + (size_t)b * N * 3;
     float mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
@@ -109,6 +136,7 @@ __global__ void bbox_setup_kernel(const float* __restrict__ pts, unsigned N, uns
             if (mx[d] != -INFINITY) atomicMax(&enc[b * 6 + 3 + d], f2ord(mx[d]));
         }
     }
+    if (defer_setup) return;  // probe_kernel derives the geometry
     // last block done -> geometry of every item
     __shared__ bool s_last;
     __threadfence();
@@ -170,10 +198,75 @@ __global__ void cell_scatter_kernel(SortJob jp, SortJob jq) {
     j.sorted[pos] = v;
 }
 
+// cube index of a point at the probe's fine resolution (edge = E / r2, anchored at the bbox minimum)
+__device__ __forceinline__ void probe_cubes(float x, float y, float z, const float lo[3], float inv_edge, unsigned r2,
+                                            unsigned* fine, unsigned* coarse) {
+    const unsigned cx = min((unsigned)fmaxf((x - lo[0]) * inv_edge, 0.f), r2 - 1);
+    const unsigned cy = min((unsigned)fmaxf((y - lo[1]) * inv_edge, 0.f), r2 - 1);
+    const unsigned cz = min((unsigned)fmaxf((z - lo[2]) * inv_edge, 0.f), r2 - 1);
+    const unsigned r1 = r2 >> 1;
+    *fine = (cz * r2 + cy) * r2 + cx;
+    *coarse = ((cz >> 1) * r1 + (cy >> 1)) * r1 + (cx >> 1);
+}
+
+// multi-launch path: marks the cubes of every item in global bitmaps; new bits are counted per block, the last block
+// to finish derives every item's geometry (what bbox_setup_kernel's last block does when there is no probe)
+__global__ void probe_kernel(const float* __restrict__ pts, unsigned N, const unsigned* __restrict__ enc,
+                             unsigned* __restrict__ bitmaps /* [B][PROBE_WORDS] */,
+                             unsigned* __restrict__ counts /* [B][2] */, unsigned* __restrict__ ticket,
+                             ItemMeta* __restrict__ items, int B, float occupancy, unsigned cell_cap, unsigned cstride,
+                             unsigned r2) {
+    const unsigned b = blockIdx.y;
+    const float* p = pts + (size_t)b * N * 3;
+    float lo[3], E = 0.f;
+    for (int d = 0; d < 3; ++d) {
+        lo[d] = ord2f(~__ldcg(&enc[b * 6 + d]));
+        E = fmaxf(E, ord2f(__ldcg(&enc[b * 6 + 3 + d])) - lo[d]);
+    }
+    unsigned* fine_bm = bitmaps + (size_t)b * PROBE_WORDS;
+    unsigned* coarse_bm = fine_bm + PROBE_MAX_R * PROBE_MAX_R * PROBE_MAX_R / 32;
+    unsigned new1 = 0, new2 = 0;
+    if (E > 0.f && isfinite(E)) {
+        const float inv_edge = (float)r2 / E;
+        for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < N; i += gridDim.x * blockDim.x) {
+            unsigned f, c2;
+            probe_cubes(__ldg(p + 3 * (size_t)i), __ldg(p + 3 * (size_t)i + 1), __ldg(p + 3 * (size_t)i + 2), lo, inv_edge,
+                        r2, &f, &c2);
+            const unsigned fb = 1u << (f & 31), cb = 1u << (c2 & 31);
+            if (!(__ldcg(&fine_bm[f >> 5]) & fb)) new2 += (atomicOr(&fine_bm[f >> 5], fb) & fb) ? 0u : 1u;
+            if (!(__ldcg(&coarse_bm[c2 >> 5]) & cb)) new1 += (atomicOr(&coarse_bm[c2 >> 5], cb) & cb) ? 0u : 1u;
+        }
+    }
+    __shared__ unsigned s_new[2];
+    __shared__ bool s_last;
+    if (threadIdx.x < 2) s_new[threadIdx.x] = 0;
+    __syncthreads();
+    new1 = __reduce_add_sync(0xffffffffu, new1);
+    new2 = __reduce_add_sync(0xffffffffu, new2);
+    if ((threadIdx.x & 31) == 0) {
+        if (new1) atomicAdd(&s_new[0], new1);
+        if (new2) atomicAdd(&s_new[1], new2);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        if (s_new[0]) atomicAdd(&counts[b * 2], s_new[0]);
+        if (s_new[1]) atomicAdd(&counts[b * 2 + 1], s_new[1]);
+        __threadfence();
+        s_last = atomicAdd(ticket, 1u) == gridDim.x * gridDim.y - 1;
+    }
+    __syncthreads();
+    if (s_last) {
+        __threadfence();
+        for (int it = threadIdx.x; it < B; it += blockDim.x)
+            setup_item(enc, items, it, N, occupancy, cell_cap, cstride,
+                       Probe{r2, __ldcg(&counts[it * 2]), __ldcg(&counts[it * 2 + 1])});
+    }
+}
+
 // ---- A (small clouds): the whole cell-grid build of one item in ONE CTA -- bbox, geometry, cell histogram and scan
 // in shared memory, scatter -- instead of six launches; the lower pyramid levels are pure launch latency otherwise.
 constexpr int SG_THREADS = 512;
-constexpr unsigned SG_MAX_CELLS = 16384;  // cstride limit (64 KB of dynamic shared memory)
+constexpr unsigned SG_MAX_CELLS = 40960;  // cstride limit (160 KB of dynamic shared memory)
 constexpr unsigned SG_MAX_POINTS = 16384;
 
 __device__ __forceinline__ unsigned local_cell(const ItemMeta& m, float x, float y, float z) {
@@ -222,11 +315,14 @@ __global__ void __launch_bounds__(SG_THREADS) small_grid_kernel(const float* __r
                                                                 unsigned* __restrict__ enc, ItemMeta* __restrict__ items,
                                                                 int B, float occupancy, unsigned cell_cap,
                                                                 unsigned cstride, unsigned* __restrict__ starts_p,
-                                                                float4* __restrict__ sort_p, float4* __restrict__ sort_q) {
-    extern __shared__ unsigned sg_cells[];  // [cstride]
+                                                                float4* __restrict__ sort_p, float4* __restrict__ sort_q,
+                                                                unsigned r2) {
+    extern __shared__ unsigned sg_cells[];  // [max(cstride, PROBE_WORDS when probing)]
     __shared__ float s_red[6][SG_THREADS / 32];
     __shared__ unsigned s_wtot[SG_THREADS / 32 + 1];
     __shared__ ItemMeta s_m;
+    __shared__ float s_box[4];
+    __shared__ unsigned s_new[2];
     const unsigned b = blockIdx.x;
     const float* p = pts + (size_t)b * N * 3;
     float mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
@@ -250,9 +346,11 @@ __global__ void __launch_bounds__(SG_THREADS) small_grid_kernel(const float* __r
             s_red[d][threadIdx.x >> 5] = mn[d];
             s_red[3 + d][threadIdx.x >> 5] = mx[d];
         }
-    for (unsigned i = threadIdx.x; i < cstride; i += SG_THREADS) sg_cells[i] = 0;
+    if (r2)
+        for (unsigned i = threadIdx.x; i < PROBE_WORDS; i += SG_THREADS) sg_cells[i] = 0;  // the probe's two bitmaps
     __syncthreads();
     if (threadIdx.x == 0) {
+        float E = 0.f;
         for (int d = 0; d < 3; ++d) {
             float a = s_red[d][0], z = s_red[3 + d][0];
             for (int w = 1; w < SG_THREADS / 32; ++w) {
@@ -261,18 +359,52 @@ __global__ void __launch_bounds__(SG_THREADS) small_grid_kernel(const float* __r
             }
             enc[b * 6 + d] = ~f2ord(a);  // same encoding the multi-launch path reduces with atomicMax
             enc[b * 6 + 3 + d] = f2ord(z);
+            s_box[d] = a;
+            E = fmaxf(E, z - a);
         }
-        setup_item(enc, items, (int)b, N, occupancy, cell_cap, cstride);
+        s_box[3] = E;
+        s_new[0] = s_new[1] = 0;
+    }
+    __syncthreads();
+    Probe pr{0, 0, 0};
+    if (r2 && s_box[3] > 0.f && isfinite(s_box[3])) {  // occupied cubes at two resolutions (see Probe)
+        const float lo[3] = {s_box[0], s_box[1], s_box[2]};
+        const float inv_edge = (float)r2 / s_box[3];
+        unsigned* fine_bm = sg_cells;
+        unsigned* coarse_bm = sg_cells + PROBE_MAX_R * PROBE_MAX_R * PROBE_MAX_R / 32;
+        unsigned new1 = 0, new2 = 0;
+        for (unsigned i = threadIdx.x; i < N; i += SG_THREADS) {
+            unsigned f, c2;
+            probe_cubes(__ldg(p + 3 * (size_t)i), __ldg(p + 3 * (size_t)i + 1), __ldg(p + 3 * (size_t)i + 2), lo, inv_edge,
+                        r2, &f, &c2);
+            const unsigned fb = 1u << (f & 31), cb = 1u << (c2 & 31);
+            new2 += (atomicOr(&fine_bm[f >> 5], fb) & fb) ? 0u : 1u;
+            new1 += (atomicOr(&coarse_bm[c2 >> 5], cb) & cb) ? 0u : 1u;
+        }
+        new1 = __reduce_add_sync(0xffffffffu, new1);
+        new2 = __reduce_add_sync(0xffffffffu, new2);
+        if ((threadIdx.x & 31) == 0) {
+            atomicAdd(&s_new[0], new1);
+            atomicAdd(&s_new[1], new2);
+        }
+        __syncthreads();
+        pr = Probe{r2, s_new[0], s_new[1]};
+    }
+    if (threadIdx.x == 0) {
+        setup_item(enc, items, (int)b, N, occupancy, cell_cap, cstride, pr);
         s_m = items[b];
     }
     __syncthreads();
     const ItemMeta m = s_m;
+    const unsigned ncell = (unsigned)(m.g[0] * m.g[1] * m.g[2]) + 1u;  // cells in use (+1: end of the last one), <= cstride
+    for (unsigned i = threadIdx.x; i < ncell; i += SG_THREADS) sg_cells[i] = 0;
+    __syncthreads();
     // support points: histogram -> scan -> global starts (offset by the item's base) -> scatter
     for (unsigned i = threadIdx.x; i < N; i += SG_THREADS)
         atomicAdd(&sg_cells[local_cell(m, __ldg(p + 3 * (size_t)i), __ldg(p + 3 * (size_t)i + 1), __ldg(p + 3 * (size_t)i + 2))], 1u);
     __syncthreads();
-    block_exclusive_scan(sg_cells, cstride, s_wtot);
-    for (unsigned i = threadIdx.x; i < cstride; i += SG_THREADS) starts_p[(size_t)b * cstride + i] = b * N + sg_cells[i];
+    block_exclusive_scan(sg_cells, ncell, s_wtot);
+    for (unsigned i = threadIdx.x; i < ncell; i += SG_THREADS) starts_p[(size_t)b * cstride + i] = b * N + sg_cells[i];
     if (b == (unsigned)B - 1 && threadIdx.x == 0) starts_p[(size_t)B * cstride] = (unsigned)B * N;
     __syncthreads();
     for (unsigned i = threadIdx.x; i < N; i += SG_THREADS) {
@@ -287,12 +419,12 @@ __global__ void __launch_bounds__(SG_THREADS) small_grid_kernel(const float* __r
     // queries (a different array): only their cell-sorted order is needed
     __syncthreads();
     const float* q = qs + (size_t)b * Q * 3;
-    for (unsigned i = threadIdx.x; i < cstride; i += SG_THREADS) sg_cells[i] = 0;
+    for (unsigned i = threadIdx.x; i < ncell; i += SG_THREADS) sg_cells[i] = 0;
     __syncthreads();
     for (unsigned i = threadIdx.x; i < Q; i += SG_THREADS)
         atomicAdd(&sg_cells[local_cell(m, __ldg(q + 3 * (size_t)i), __ldg(q + 3 * (size_t)i + 1), __ldg(q + 3 * (size_t)i + 2))], 1u);
     __syncthreads();
-    block_exclusive_scan(sg_cells, cstride, s_wtot);
+    block_exclusive_scan(sg_cells, ncell, s_wtot);
     for (unsigned i = threadIdx.x; i < Q; i += SG_THREADS) {
         float4 v;
         v.x = __ldg(q + 3 * (size_t)i);
@@ -625,10 +757,21 @@ static int run_dev(Ctx* c, cudaStream_t s, const float* d_pts, size_t B, size_t 
     }
     float occupancy = g_occupancy_scale * (float)K;
     occupancy = occupancy < 0.6f ? 0.6f : (occupancy > 24.f ? 24.f : occupancy);
-    // cells per item: h is chosen so that cells ~= N / occupancy; 3x head-room for the +1 per axis and flat clouds
-    // (setup_item grows h until the grid fits, so the bound costs speed at worst, never correctness)
+    // cells per item: for a cloud that fills its bbox h gives cells ~= N / occupancy (3x head-room for the +1 per axis);
+    // a cloud of surfaces needs the same number of OCCUPIED cells inside a mostly empty bbox, hence up to 4 cells per
+    // point when the occupancy probe runs (setup_item grows h until the grid fits, so the bound costs speed at worst,
+    // never correctness)
+    static int probe_on = -1;  // SSDR_KNN_PROBE=0 switches the occupancy probe off (A/B measurements)
+    if (probe_on < 0) {
+        const char* e = getenv("SSDR_KNN_PROBE");
+        probe_on = (e && e[0] == '0') ? 0 : 1;
+    }
+    const unsigned r2 = probe_on ? probe_resolution((unsigned)N) : 0u;
     size_t cap = (size_t)(3.0 * (double)N / occupancy) + 64;
+    if (r2 && cap < 4 * N) cap = 4 * N;
     if (cap > (1u << 24)) cap = (1u << 24);
+    if (N <= SG_MAX_POINTS && cap > SG_MAX_CELLS - 1 && (size_t)(3.0 * (double)N / occupancy) + 64 <= SG_MAX_CELLS - 1)
+        cap = SG_MAX_CELLS - 1;  // stay within the shared memory of the single-CTA build
     const unsigned cstride = (unsigned)cap + 1;
     const size_t ncell = B * (size_t)cstride + 1;
     const bool self = (d_q == d_pts && Q == N);
@@ -637,7 +780,8 @@ static int run_dev(Ctx* c, cudaStream_t s, const float* d_pts, size_t B, size_t 
 
     // one zero-initialised control slab: stats | ticket | bbox encodings | counts (P,Q) | cursors (P,Q)
     const size_t nscan_words = prim::scan_scratch_words((size_t)njobs * ncell);
-    const size_t hdr_words = 16 + B * 6 + nscan_words;  // stats, ticket, bbox encodings, scan scratch (zeroed)
+    const size_t probe_words = r2 ? B * (size_t)(PROBE_WORDS + 2) + 2 : 0;  // multi-launch path: bitmaps, counts, ticket
+    const size_t hdr_words = 16 + B * 6 + nscan_words + probe_words;  // stats, ticket, bbox, scan scratch, probe (zeroed)
     const size_t ctl_words = hdr_words + 2 * (size_t)njobs * ncell;
     SSDR_TRY(c->ws[WS_CNT_P].reserve(ctl_words * 4));
     SSDR_TRY(c->ws[WS_ITEMS].reserve(B * sizeof(ItemMeta)));
@@ -677,16 +821,23 @@ static int run_dev(Ctx* c, cudaStream_t s, const float* d_pts, size_t B, size_t 
                                                  (int)(SG_MAX_CELLS * sizeof(unsigned))));
             attr_set = true;
         }
-        small_grid_kernel<<<(unsigned)B, SG_THREADS, cstride * sizeof(unsigned), s>>>(
+        const size_t sg_words = (r2 && cstride < PROBE_WORDS) ? (size_t)PROBE_WORDS : (size_t)cstride;
+        small_grid_kernel<<<(unsigned)B, SG_THREADS, sg_words * sizeof(unsigned), s>>>(
             d_pts, (unsigned)N, self ? nullptr : d_q, (unsigned)Q, enc, items, (int)B, occupancy, (unsigned)cap, cstride,
-            starts, sort_p, sort_q_buf);
+            starts, sort_p, sort_q_buf, r2);
         n_launch += 1;
     } else {
         SSDR_CHECK_CUDA(cudaMemsetAsync(ctl, 0, ctl_words * 4, s));
         unsigned bx = (unsigned)((N + 1023) / 1024);
         if (bx > 256) bx = 256;
         bbox_setup_kernel<<<dim3(bx, (unsigned)B), 256, 0, s>>>(d_pts, (unsigned)N, enc, ticket, items, (int)B, occupancy,
-                                                               (unsigned)cap, cstride);
+                                                               (unsigned)cap, cstride, r2 != 0);
+        if (r2) {
+            unsigned* pbase = ctl + 16 + B * 6 + nscan_words;  // [ticket, pad][B][2 counts][B][PROBE_WORDS]
+            probe_kernel<<<dim3(bx, (unsigned)B), 256, 0, s>>>(d_pts, (unsigned)N, enc, pbase + 2 + 2 * B, pbase + 2, pbase,
+                                                              items, (int)B, occupancy, (unsigned)cap, cstride, r2);
+            n_launch += 1;
+        }
         SortJob jp, jq;
         jp.xyz = d_pts;
         jp.n = (unsigned)N;
