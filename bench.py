@@ -413,6 +413,37 @@ def secondary_metrics(torch, D, dev, flush):
         del pts, rgb, lab, u, sub, sub2
     except Exception as e:
         out["grid_subsample"] = {"error": repr(e)}
+    try:  # the same pyramid on SURFACE crops: what the real pipeline feeds (40960 nearest points of a random centre
+        # in a room made of planes, shuffled) -- the headline config is uniform-in-volume by definition
+        rng = np.random.default_rng(5)
+        n = 400_000
+        kk = rng.integers(0, 8, n)
+        room = rng.random((n, 3)) * np.array([7.0, 5.0, 3.0])
+        for v, (ax, val) in enumerate(((2, 0.0), (2, 3.0), (1, 0.0), (1, 5.0), (0, 0.0), (0, 7.0))):
+            room[kk == v, ax] = val
+        room[kk >= 6, 2] = 0.75
+        room += rng.normal(0, 0.004, room.shape)
+        room = room.astype(np.float32)
+        crops = []
+        for _ in range(B):
+            dd = ((room - room[rng.integers(0, n)]) ** 2).sum(1)
+            crops.append(room[rng.permutation(np.argpartition(dd, N0)[:N0])])
+        cx = torch.from_numpy(np.stack(crops)).to(dev)
+
+        def crop_pyramid():
+            xyz = cx
+            for ratio in RATIOS:
+                D.knn_batch(xyz, xyz, K)
+                sub = xyz[:, : xyz.shape[1] // ratio, :].contiguous()
+                D.knn_batch(sub, xyz, 1)
+                xyz = sub
+
+        crop_pyramid()
+        ms, _ = timed(crop_pyramid, 7)
+        out["pyramid_surface_crops"] = {"batch": B, "points": N0, "ms": ms, "k16_queries_per_s": K16_QUERIES / ms * 1e3}
+        del cx
+    except Exception as e:
+        out["pyramid_surface_crops"] = {"error": repr(e)}
     for d_, picks in ((32, 2000), (256, 1000)):
         try:
             g = torch.Generator(device=dev)
