@@ -55,6 +55,7 @@ struct Probe {
 };
 constexpr unsigned PROBE_MIN_POINTS = 4096;
 constexpr unsigned PROBE_MAX_R = 64;
+constexpr unsigned PROBE_SAMPLE = 1u << 18;  // points looked at per item
 constexpr unsigned PROBE_WORDS = PROBE_MAX_R * PROBE_MAX_R * PROBE_MAX_R / 32 + (PROBE_MAX_R / 2) * (PROBE_MAX_R / 2) * (PROBE_MAX_R / 2) / 32;
 
 __host__ __device__ inline unsigned probe_resolution(unsigned N) {
@@ -162,7 +163,6 @@ struct SortJob {
     unsigned* cell_of;    // [total]
     unsigned* counts;     // [ncell]
     const unsigned* starts;  // [ncell] exclusive scan of counts (this job's block of the concatenated scan)
-    unsigned* cursor;     // [ncell]
     float4* sorted;       // [total]
     unsigned start_bias;  // subtracted from starts (the queries' counts are scanned behind the points')
 };
@@ -189,7 +189,8 @@ __global__ void cell_scatter_kernel(SortJob jp, SortJob jq) {
     if (isq) i -= jp.total;
     if (i >= j.total) return;
     const unsigned cell = j.cell_of[i];
-    const unsigned pos = j.starts[cell] - j.start_bias + atomicAdd(&j.cursor[cell], 1u);
+    // the counts are consumed as slot tickets (no separate cursor array to zero): order inside a cell is arbitrary
+    const unsigned pos = j.starts[cell] - j.start_bias + (atomicSub(&j.counts[cell], 1u) - 1u);
     float4 v;
     v.x = __ldg(j.xyz + 3 * (size_t)i);
     v.y = __ldg(j.xyz + 3 * (size_t)i + 1);
@@ -215,7 +216,7 @@ __global__ void probe_kernel(const float* __restrict__ pts, unsigned N, const un
                              unsigned* __restrict__ bitmaps /* [B][PROBE_WORDS] */,
                              unsigned* __restrict__ counts /* [B][2] */, unsigned* __restrict__ ticket,
                              ItemMeta* __restrict__ items, int B, float occupancy, unsigned cell_cap, unsigned cstride,
-                             unsigned r2) {
+                             unsigned r2, unsigned stride /* probe every stride-th point (large clouds) */) {
     const unsigned b = blockIdx.y;
     const float* p = pts + (size_t)b * N * 3;
     float lo[3], E = 0.f;
@@ -228,10 +229,11 @@ __global__ void probe_kernel(const float* __restrict__ pts, unsigned N, const un
     unsigned new1 = 0, new2 = 0;
     if (E > 0.f && isfinite(E)) {
         const float inv_edge = (float)r2 / E;
-        for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < N; i += gridDim.x * blockDim.x) {
+        const unsigned ns = (N + stride - 1) / stride;
+        for (unsigned j = blockIdx.x * blockDim.x + threadIdx.x; j < ns; j += gridDim.x * blockDim.x) {
+            const size_t i = (size_t)j * stride;
             unsigned f, c2;
-            probe_cubes(__ldg(p + 3 * (size_t)i), __ldg(p + 3 * (size_t)i + 1), __ldg(p + 3 * (size_t)i + 2), lo, inv_edge,
-                        r2, &f, &c2);
+            probe_cubes(__ldg(p + 3 * i), __ldg(p + 3 * i + 1), __ldg(p + 3 * i + 2), lo, inv_edge, r2, &f, &c2);
             const unsigned fb = 1u << (f & 31), cb = 1u << (c2 & 31);
             if (!(__ldcg(&fine_bm[f >> 5]) & fb)) new2 += (atomicOr(&fine_bm[f >> 5], fb) & fb) ? 0u : 1u;
             if (!(__ldcg(&coarse_bm[c2 >> 5]) & cb)) new1 += (atomicOr(&coarse_bm[c2 >> 5], cb) & cb) ? 0u : 1u;
@@ -766,7 +768,9 @@ static int run_dev(Ctx* c, cudaStream_t s, const float* d_pts, size_t B, size_t 
         const char* e = getenv("SSDR_KNN_PROBE");
         probe_on = (e && e[0] == '0') ? 0 : 1;
     }
-    const unsigned r2 = probe_on ? probe_resolution((unsigned)N) : 0u;
+    // large clouds are probed on a strided sample (the cube counts only need occupancies well above one)
+    const unsigned pstride = (unsigned)((N + PROBE_SAMPLE - 1) / PROBE_SAMPLE);
+    const unsigned r2 = probe_on ? probe_resolution((unsigned)((N + pstride - 1) / pstride)) : 0u;
     size_t cap = (size_t)(3.0 * (double)N / occupancy) + 64;
     if (r2 && cap < 4 * N) cap = 4 * N;
     if (cap > (1u << 24)) cap = (1u << 24);
@@ -778,11 +782,11 @@ static int run_dev(Ctx* c, cudaStream_t s, const float* d_pts, size_t B, size_t 
     const unsigned totalP = (unsigned)(B * N), totalQ = (unsigned)(B * Q);
     const int njobs = self ? 1 : 2;
 
-    // one zero-initialised control slab: stats | ticket | bbox encodings | counts (P,Q) | cursors (P,Q)
+    // one zero-initialised control slab: stats | ticket | bbox encodings | scan scratch | probe | counts (P,Q)
     const size_t nscan_words = prim::scan_scratch_words((size_t)njobs * ncell);
     const size_t probe_words = r2 ? B * (size_t)(PROBE_WORDS + 2) + 2 : 0;  // multi-launch path: bitmaps, counts, ticket
     const size_t hdr_words = 16 + B * 6 + nscan_words + probe_words;  // stats, ticket, bbox, scan scratch, probe (zeroed)
-    const size_t ctl_words = hdr_words + 2 * (size_t)njobs * ncell;
+    const size_t ctl_words = hdr_words + (size_t)njobs * ncell;
     SSDR_TRY(c->ws[WS_CNT_P].reserve(ctl_words * 4));
     SSDR_TRY(c->ws[WS_ITEMS].reserve(B * sizeof(ItemMeta)));
     SSDR_TRY(c->ws[WS_CELL_P].reserve(((size_t)totalP + (self ? 0 : totalQ)) * 4));
@@ -795,7 +799,6 @@ static int run_dev(Ctx* c, cudaStream_t s, const float* d_pts, size_t B, size_t 
     unsigned* ticket = ctl + 8;
     unsigned* enc = ctl + 16;
     unsigned* counts = ctl + hdr_words;                       // [njobs][ncell]
-    unsigned* cursors = counts + (size_t)njobs * ncell;       // [njobs][ncell]
     unsigned* starts = c->ws[WS_START_P].as<unsigned>();      // [njobs][ncell], one concatenated exclusive scan
     ItemMeta* items = c->ws[WS_ITEMS].as<ItemMeta>();
     unsigned* start_p = starts;
@@ -829,13 +832,13 @@ static int run_dev(Ctx* c, cudaStream_t s, const float* d_pts, size_t B, size_t 
     } else {
         SSDR_CHECK_CUDA(cudaMemsetAsync(ctl, 0, ctl_words * 4, s));
         unsigned bx = (unsigned)((N + 1023) / 1024);
-        if (bx > 256) bx = 256;
+        if (bx > 1024) bx = 1024;
         bbox_setup_kernel<<<dim3(bx, (unsigned)B), 256, 0, s>>>(d_pts, (unsigned)N, enc, ticket, items, (int)B, occupancy,
                                                                (unsigned)cap, cstride, r2 != 0);
         if (r2) {
             unsigned* pbase = ctl + 16 + B * 6 + nscan_words;  // [ticket, pad][B][2 counts][B][PROBE_WORDS]
             probe_kernel<<<dim3(bx, (unsigned)B), 256, 0, s>>>(d_pts, (unsigned)N, enc, pbase + 2 + 2 * B, pbase + 2, pbase,
-                                                              items, (int)B, occupancy, (unsigned)cap, cstride, r2);
+                                                              items, (int)B, occupancy, (unsigned)cap, cstride, r2, pstride);
             n_launch += 1;
         }
         SortJob jp, jq;
@@ -845,7 +848,6 @@ static int run_dev(Ctx* c, cudaStream_t s, const float* d_pts, size_t B, size_t 
         jp.cell_of = c->ws[WS_CELL_P].as<unsigned>();
         jp.counts = counts;
         jp.starts = starts;
-        jp.cursor = cursors;
         jp.sorted = sort_p;
         jp.start_bias = 0;
         jq = jp;
@@ -857,7 +859,6 @@ static int run_dev(Ctx* c, cudaStream_t s, const float* d_pts, size_t B, size_t 
             jq.cell_of = jp.cell_of + totalP;
             jq.counts = counts + ncell;
             jq.starts = starts + ncell;
-            jq.cursor = cursors + ncell;
             jq.sorted = c->ws[WS_SORT_Q].as<float4>();
             jq.start_bias = totalP;  // the concatenated scan continues behind the points' total
         }
