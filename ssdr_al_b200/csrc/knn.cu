@@ -830,6 +830,8 @@ static int run_dev(Ctx* c, cudaStream_t s, const float* d_pts, size_t B, size_t 
             starts, sort_p, sort_q_buf, r2);
         n_launch += 1;
     } else {
+        SSDR_REQUIRE(B <= 65535, SSDR_ERR_UNSUPPORTED, "more than 65535 batch items of more than %u points each",
+                     SG_MAX_POINTS);
         SSDR_CHECK_CUDA(cudaMemsetAsync(ctl, 0, ctl_words * 4, s));
         unsigned bx = (unsigned)((N + 1023) / 1024);
         if (bx > 1024) bx = 1024;
