@@ -114,3 +114,21 @@ def test_product_never_imports_the_oracle():
                 text = open(os.path.join(dirpath, f)).read()
                 for pat in ("import oracle", "from oracle", "liboracle", "oracle/", "oracle.", "_ref/"):
                     assert pat not in text, "%s mentions %r" % (os.path.join(dirpath, f), pat)
+
+
+def test_batch_view_picks_the_upload_route_without_a_device():
+    """knn_batch uploads slices of a larger float32 array as they are (item stride passed to the C ABI) and packs
+    everything else on the host like knn.pyx:95-96 does."""
+    from ssdr_al_b200.nearest_neighbors import _batch_view
+    base = np.arange(4 * 100 * 3, dtype=np.float32).reshape(4, 100, 3)
+    a, st = _batch_view(base)
+    assert a is base and st == 300
+    v = base[:, :25, :]
+    a, st = _batch_view(v)
+    assert a is v and st == 300 and not v.flags["C_CONTIGUOUS"]
+    a, st = _batch_view(base[1:3, 10:20])            # offset slices keep the parent's item stride
+    assert st == 300 and a.shape == (2, 10, 3)
+    for odd in (base[:, ::2, :], base[:, :, ::-1], base.astype(np.float64), base.tolist(), base[::-1]):
+        a, st = _batch_view(odd)
+        assert a.flags["C_CONTIGUOUS"] and a.dtype == np.float32 and st == a.shape[1] * 3
+        assert np.array_equal(a, np.asarray(odd, dtype=np.float32))
