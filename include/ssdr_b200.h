@@ -170,6 +170,16 @@ int ssdr_kcenter_f32_dev(const float* d_X, size_t N, size_t D, const int64_t* d_
 int ssdr_kcenter_f64_dev(const double* d_X, size_t N, size_t D, const int64_t* d_selected, size_t n_sel,
                          size_t n_pick, int64_t* d_out, void* stream);
 
+/* ---- chamfer adjacency of the superpoints of one room ------------------------------------------------- */
+/* create_cd / chamfer_distance (fps_gcn_cpu.py:12-38), the step that feeds the FPS loop: S small clouds, already
+ * centred by the caller, concatenated in `points` (T,3) float64 with `offsets` (S+1, offsets[0] = 0);
+ * out (S,S) float64: out[c][i] = mean_{p in i} min_{q in c} |p-q| + mean_{q in c} min_{p in i} |q-p|, 0 on the
+ * diagonal.  Distances as sklearn's KDTree computes them (float64, sqrt(((dx^2+dy^2)+dz^2))), means in numpy's
+ * pairwise order.  The _dev variant takes device pointers plus a host copy of the offsets (sizes the scratch). */
+int ssdr_chamfer_matrix_f64(const double* points, const int64_t* offsets, size_t S, double* out);
+int ssdr_chamfer_matrix_f64_dev(const double* d_points, const int64_t* d_offsets, const int64_t* h_offsets, size_t S,
+                                double* d_out, void* stream);
+
 /* Row-sharded multi-GPU selection (one process per GPU).  Every rank holds the FULL matrix d_F (so the chosen
  * centre row is local) but scans only rows [row_begin,row_end); after each step the packed (distance, index)
  * candidates are combined across ranks by an 8-byte max all-reduce over NCCL.  `nccl_comm` is an ncclComm_t.

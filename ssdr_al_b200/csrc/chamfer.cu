@@ -1,0 +1,229 @@
+// chamfer.cu -- chamfer adjacency between the S small clouds ("superpoints") of one room:
+// fps_gcn_cpu.py:12-38 (create_cd / chamfer_distance), the step that feeds the FPS loop.
+//
+// Reference: every cloud is centred on its bbox centre (float64), a sklearn KDTree per cloud answers 1-NN queries, and
+//   cd[c][i] = mean_{p in cloud i} min_{q in cloud c} |p - q|  +  mean_{q in cloud c} min_{p in cloud i} |q - p|
+// with |.| = sqrt(((dx*dx + dy*dy) + dz*dz)) in float64 (sklearn's EuclideanDistance.rdist accumulates the squares in
+// this order, the square root is taken once on the minimum) and np.mean = numpy's pairwise summation / n.
+// Only DISTANCES leave the function, so no tie order is involved: brute force over all pairs gives the same minima,
+// and the mean is reproduced with numpy's exact pairwise order -- the result is bit-identical to the reference unless
+// the KD tree's own bound rounding hides a neighbour that is closer by less than an ulp (tests allow 1e-12 relative).
+//
+// Kernel: block (a, g) owns source cloud a and the target clouds b = g, g+G, ...; a target is streamed through shared
+// memory in tiles, every thread keeps the running squared minima of a few source points in registers (float64, no FMA),
+// the square roots land in a per-block scratch row, and the block sums that row in numpy's order:
+// leaves of <= 128 values with eight strided accumulators, combined by the recursive halving of pairwise_sum.
+#include "common.cuh"
+
+namespace ssdr {
+namespace chamfer {
+
+enum { WS_PTS = 0, WS_OFF = 1, WS_DIR = 2, WS_SCRATCH = 3, WS_OUT = 4 };
+
+constexpr int CT = 256;          // threads per block
+constexpr int PA = 4;            // source points per thread and pass
+constexpr int TB = 1024;         // target points per shared-memory tile
+constexpr int MAX_LEAVES = 1024; // pairwise-sum leaves per source cloud (<= 128 values each, >= 57 once split)
+constexpr unsigned MAX_CLOUD = 50000;
+
+// numpy's pairwise_sum for n <= 128 (loops_utils.h.src: @TYPE@_pairwise_sum)
+__device__ double leaf_sum(const double* a, unsigned n) {
+    if (n < 8) {
+        double r = 0.0;
+        for (unsigned i = 0; i < n; ++i) r = __dadd_rn(r, a[i]);
+        return r;
+    }
+    double r[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) r[j] = a[j];
+    unsigned i = 8;
+    for (; i < n - (n % 8); i += 8) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) r[j] = __dadd_rn(r[j], a[i + j]);
+    }
+    double res = __dadd_rn(__dadd_rn(__dadd_rn(r[0], r[1]), __dadd_rn(r[2], r[3])),
+                           __dadd_rn(__dadd_rn(r[4], r[5]), __dadd_rn(r[6], r[7])));
+    for (; i < n; ++i) res = __dadd_rn(res, a[i]);
+    return res;
+}
+
+struct Frame {
+    unsigned lo, n;
+    int phase;
+    double left;
+};
+
+// Walks pairwise_sum's recursion over [0, n).  With sums == nullptr it only records the leaves (lo, len); otherwise it
+// consumes the leaf sums in the same left-to-right order and returns the total.
+__device__ double walk(unsigned n, unsigned* leaf_lo, unsigned* leaf_n, unsigned* n_leaves, const double* sums) {
+    Frame st[40];
+    int sp = 0;
+    unsigned next = 0;
+    double ret = 0.0;
+    st[sp++] = Frame{0u, n, 0, 0.0};
+    while (sp > 0) {
+        Frame& f = st[sp - 1];
+        if (f.n <= 128u) {
+            if (sums) ret = sums[next];
+            else if (next < (unsigned)MAX_LEAVES) {
+                leaf_lo[next] = f.lo;
+                leaf_n[next] = f.n;
+            }
+            ++next;
+            --sp;
+            continue;
+        }
+        unsigned n2 = f.n / 2;
+        n2 -= n2 % 8;
+        if (f.phase == 0) {
+            f.phase = 1;
+            st[sp++] = Frame{f.lo, n2, 0, 0.0};
+        } else if (f.phase == 1) {
+            f.left = ret;
+            f.phase = 2;
+            st[sp++] = Frame{f.lo + n2, f.n - n2, 0, 0.0};
+        } else {
+            ret = __dadd_rn(f.left, ret);
+            --sp;
+        }
+    }
+    if (n_leaves) *n_leaves = next;
+    return ret;
+}
+
+__global__ void __launch_bounds__(CT) directed_kernel(const double* __restrict__ pts, const long long* __restrict__ off,
+                                                      unsigned S, unsigned G, unsigned long long T,
+                                                      double* __restrict__ scratch /* [G][T] */,
+                                                      double* __restrict__ A /* [S][S]: A[a][b] = mean_a min_b */) {
+    __shared__ double sx[TB], sy[TB], sz[TB];
+    __shared__ unsigned s_lo[MAX_LEAVES], s_n[MAX_LEAVES];
+    __shared__ double s_sum[MAX_LEAVES];
+    __shared__ unsigned s_nleaf;
+    const unsigned a = blockIdx.x, g = blockIdx.y;
+    const unsigned long long a0 = (unsigned long long)off[a];
+    const unsigned na = (unsigned)(off[a + 1] - off[a]);
+    if (na == 0) return;
+    double* mins = scratch + (size_t)g * T + a0;
+    if (threadIdx.x == 0) walk(na, s_lo, s_n, &s_nleaf, nullptr);  // the leaf layout depends on na only
+    for (unsigned b = g; b < S; b += G) {
+        if (b == a) continue;
+        const unsigned long long b0 = (unsigned long long)off[b];
+        const unsigned nb = (unsigned)(off[b + 1] - off[b]);
+        if (nb == 0) continue;
+        for (unsigned k0 = 0; k0 < na; k0 += CT * PA) {
+            double ax[PA], ay[PA], az[PA], best[PA];
+#pragma unroll
+            for (int u = 0; u < PA; ++u) {
+                const unsigned k = k0 + (unsigned)u * CT + threadIdx.x;
+                const unsigned kk = k < na ? k : na - 1;
+                ax[u] = pts[3 * (a0 + kk)];
+                ay[u] = pts[3 * (a0 + kk) + 1];
+                az[u] = pts[3 * (a0 + kk) + 2];
+                best[u] = INFINITY;
+            }
+            for (unsigned t0 = 0; t0 < nb; t0 += TB) {
+                const unsigned nt = min((unsigned)TB, nb - t0);
+                __syncthreads();
+                for (unsigned j = threadIdx.x; j < nt; j += CT) {
+                    sx[j] = pts[3 * (b0 + t0 + j)];
+                    sy[j] = pts[3 * (b0 + t0 + j) + 1];
+                    sz[j] = pts[3 * (b0 + t0 + j) + 2];
+                }
+                __syncthreads();
+                for (unsigned j = 0; j < nt; ++j) {
+                    const double bx = sx[j], by = sy[j], bz = sz[j];
+#pragma unroll
+                    for (int u = 0; u < PA; ++u) {
+                        const double dx = __dsub_rn(ax[u], bx), dy = __dsub_rn(ay[u], by), dz = __dsub_rn(az[u], bz);
+                        const double d = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+                        best[u] = d < best[u] ? d : best[u];
+                    }
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < PA; ++u) {
+                const unsigned k = k0 + (unsigned)u * CT + threadIdx.x;
+                if (k < na) mins[k] = __dsqrt_rn(best[u]);
+            }
+        }
+        __syncthreads();  // mins complete (global writes of this block are visible to it after the barrier)
+        const unsigned nleaf = s_nleaf;
+        for (unsigned l = threadIdx.x; l < nleaf && l < (unsigned)MAX_LEAVES; l += CT) s_sum[l] = leaf_sum(mins + s_lo[l], s_n[l]);
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const double total = walk(na, nullptr, nullptr, nullptr, s_sum);
+            A[(size_t)a * S + b] = __ddiv_rn(total, (double)na);
+        }
+        __syncthreads();  // the next target overwrites mins and s_sum
+    }
+}
+
+__global__ void symmetrize_kernel(const double* __restrict__ A, unsigned S, double* __restrict__ out) {
+    const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (unsigned long long)S * S) return;
+    const unsigned r = (unsigned)(i / S), c = (unsigned)(i % S);
+    // cd[c_idx][i] = mean over cloud i of the distance to cloud c_idx + mean over cloud c_idx of the distance to cloud i
+    out[i] = r == c ? 0.0 : __dadd_rn(A[(size_t)c * S + r], A[(size_t)r * S + c]);
+}
+
+static int run_dev(Ctx* c, cudaStream_t s, const double* d_pts, const long long* d_off, const long long* h_off, size_t S,
+                   double* d_out) {
+    SSDR_REQUIRE(S >= 1, SSDR_ERR_INVALID, "no clouds");
+    SSDR_REQUIRE(S <= 46340, SSDR_ERR_UNSUPPORTED, "more than 46340 clouds");
+    const size_t T = (size_t)h_off[S];
+    for (size_t i = 0; i < S; ++i) {
+        SSDR_REQUIRE(h_off[i + 1] >= h_off[i], SSDR_ERR_INVALID, "offsets must not decrease");
+        SSDR_REQUIRE((size_t)(h_off[i + 1] - h_off[i]) <= MAX_CLOUD, SSDR_ERR_UNSUPPORTED,
+                     "cloud %zu has more than %u points", i, MAX_CLOUD);
+    }
+    unsigned G = (unsigned)((4 * (size_t)c->sm_count + S - 1) / S);
+    if (G < 1) G = 1;
+    if (G > S) G = (unsigned)S;
+    SSDR_TRY(c->ws[WS_DIR].reserve(S * S * sizeof(double)));
+    SSDR_TRY(c->ws[WS_SCRATCH].reserve((size_t)G * (T ? T : 1) * sizeof(double)));
+    double* A = c->ws[WS_DIR].as<double>();
+    SSDR_CHECK_CUDA(cudaMemsetAsync(A, 0, S * S * sizeof(double), s));
+    if (T) {
+        directed_kernel<<<dim3((unsigned)S, G), CT, 0, s>>>(d_pts, d_off, (unsigned)S, G, (unsigned long long)T,
+                                                           c->ws[WS_SCRATCH].as<double>(), A);
+        SSDR_CHECK_CUDA(cudaGetLastError());
+    }
+    symmetrize_kernel<<<(unsigned)((S * S + 255) / 256), 256, 0, s>>>(A, (unsigned)S, d_out);
+    SSDR_CHECK_CUDA(cudaGetLastError());
+    return SSDR_OK;
+}
+
+}  // namespace chamfer
+}  // namespace ssdr
+
+using namespace ssdr;
+
+extern "C" {
+
+int ssdr_chamfer_matrix_f64(const double* points, const int64_t* offsets, size_t S, double* out) {
+    SSDR_REQUIRE(points && offsets && out, SSDR_ERR_INVALID, "NULL pointer");
+    SSDR_REQUIRE(S >= 1 && offsets[0] == 0, SSDR_ERR_INVALID, "offsets must start at 0 and hold S + 1 entries");
+    Ctx* c;
+    SSDR_TRY(get_ctx(&c));
+    const size_t T = (size_t)offsets[S];
+    SSDR_TRY(c->ws[chamfer::WS_PTS].reserve((T ? T : 1) * 3 * sizeof(double)));
+    SSDR_TRY(c->ws[chamfer::WS_OFF].reserve((S + 1) * sizeof(long long)));
+    SSDR_TRY(c->ws[chamfer::WS_OUT].reserve(S * S * sizeof(double)));
+    SSDR_TRY(h2d(c, c->ws[chamfer::WS_PTS].p, points, T * 3 * sizeof(double), c->stream));
+    SSDR_TRY(h2d(c, c->ws[chamfer::WS_OFF].p, offsets, (S + 1) * sizeof(long long), c->stream));
+    SSDR_TRY(chamfer::run_dev(c, c->stream, c->ws[chamfer::WS_PTS].as<double>(), c->ws[chamfer::WS_OFF].as<long long>(),
+                              reinterpret_cast<const long long*>(offsets), S, c->ws[chamfer::WS_OUT].as<double>()));
+    return d2h_sync(c, out, c->ws[chamfer::WS_OUT].p, S * S * sizeof(double), c->stream);
+}
+
+int ssdr_chamfer_matrix_f64_dev(const double* d_points, const int64_t* d_offsets, const int64_t* h_offsets, size_t S,
+                                double* d_out, void* stream) {
+    SSDR_REQUIRE(d_points && d_offsets && h_offsets && d_out, SSDR_ERR_INVALID, "NULL pointer");
+    SSDR_REQUIRE(S >= 1 && h_offsets[0] == 0, SSDR_ERR_INVALID, "offsets must start at 0 and hold S + 1 entries");
+    Ctx* c;
+    SSDR_TRY(get_ctx(&c));
+    return chamfer::run_dev(c, (cudaStream_t)stream, d_points, reinterpret_cast<const long long*>(d_offsets),
+                            reinterpret_cast<const long long*>(h_offsets), S, d_out);
+}
+
+}  // extern "C"

@@ -114,5 +114,41 @@ def main():
         print(f, os.path.getsize(os.path.join(HERE, f + ".npz")) // 1024, "KiB")
 
 
+def superpoints(rng, sizes):
+    """Superpoint-like clouds of one room: small float32 patches (planar, elongated, blobs, duplicates) and the bbox
+    centres fps_adj_all computes for them (fps_gcn_cpu.py:84-88)."""
+    sps, cents = [], []
+    for n in sizes:
+        c = rng.random(3) * np.array([7.0, 5.0, 3.0])
+        p = c + rng.normal(0, 0.25, (n, 3)) * rng.choice([1.0, 0.02], 3)
+        if n > 6:
+            p[n // 2] = p[0]  # an exact duplicate
+        p = p.astype(np.float32)
+        sps.append(p)
+        cents.append([(np.min(p[:, d]) + np.max(p[:, d])) / 2.0 for d in range(3)])
+    return sps, np.array(cents)
+
+
+def make_chamfer():
+    """create_cd of the unmodified reference (fps_gcn_cpu.py:25-38, sklearn KDTree underneath)."""
+    sys.path.insert(0, "/root/reference/SSDR_AL_s3dis")
+    from fps_gcn_cpu import create_cd
+    rng = np.random.default_rng(20)
+    out = {}
+    for tag, sizes in (("small", [1, 2, 7, 8, 9, 33, 127, 128, 129, 300]),
+                       ("room", [int(v) for v in rng.integers(40, 900, 24)] + [2600])):
+        sps, cents = superpoints(rng, sizes)
+        out[tag + "_points"] = np.concatenate(sps)
+        out[tag + "_offsets"] = np.concatenate([[0], np.cumsum([len(p) for p in sps])]).astype(np.int64)
+        out[tag + "_centroids"] = cents
+        out[tag + "_cd"] = create_cd(sps, cents)
+    np.savez_compressed(os.path.join(HERE, "chamfer.npz"), **out)
+    print("chamfer", os.path.getsize(os.path.join(HERE, "chamfer.npz")) // 1024, "KiB")
+
+
 if __name__ == "__main__":
-    main()
+    if sys.argv[1:] == ["chamfer"]:
+        make_chamfer()  # added later with its own generator: the other fixtures stay byte-identical
+    else:
+        main()
+        make_chamfer()

@@ -104,3 +104,14 @@ def test_hash_order_small_cases(oracle):
     assert list(oracle.hash_order([3, 7, 1, 12])) == [3, 2, 1, 0]
     # 1 and 14 share bucket 1: the later one goes to the FRONT of that bucket's chain, bucket keeps its place
     assert list(oracle.hash_order([1, 5, 14])) == [1, 2, 0]
+
+
+@pytest.mark.parametrize("tag", ["small", "room"])
+def test_chamfer_restatement_equals_reference_golden(oracle, golden, tag):
+    """oracle.create_cd (brute force, numpy) vs the matrices the unmodified reference produced with its KD trees."""
+    g = golden.chamfer
+    pts, off = g[tag + "_points"], g[tag + "_offsets"]
+    sps = [pts[off[i]:off[i + 1]] for i in range(len(off) - 1)]
+    got = oracle.create_cd(sps, g[tag + "_centroids"])
+    np.testing.assert_allclose(got, g[tag + "_cd"], rtol=1e-12, atol=0)
+    assert np.mean(got == g[tag + "_cd"]) > 0.99
