@@ -444,6 +444,31 @@ def secondary_metrics(torch, D, dev, flush):
         del cx
     except Exception as e:
         out["pyramid_surface_crops"] = {"error": repr(e)}
+    try:  # chamfer adjacency of one room's superpoints (fps_gcn_cpu.py:25-38), host arrays in / matrix out
+        import ssdr_al_b200 as S
+        rng = np.random.default_rng(9)
+        sizes = rng.integers(60, 700, 300)
+        sps, cents = [], []
+        for nn_ in sizes:
+            cc = rng.random(3) * np.array([7.0, 5.0, 3.0])
+            pp = (cc + rng.normal(0, 0.2, (int(nn_), 3)) * rng.choice([1.0, 0.05], 3)).astype(np.float32)
+            sps.append(pp)
+            cents.append((pp.min(0).astype(np.float64) + pp.max(0)) / 2.0)
+        cents = np.array(cents)
+        S.chamfer.create_cd(sps, cents)
+        ms = float(np.median([cpu_time(lambda: S.chamfer.create_cd(sps, cents)) for _ in range(3)]))
+        tot = int(sizes.sum())
+        out["chamfer_adjacency"] = {"superpoints": len(sps), "points": tot, "e2e_ms": ms,
+                                    "pair_evals_per_s": float(tot) * tot / ms * 1e3}
+        if O is not None:  # the reference's KD-tree loop on the first 24 superpoints, scaled by the pair count
+            sub = 24
+            t_ref = cpu_time(lambda: (O.ref_create_cd if os.path.isdir("/root/reference") else O.create_cd)(
+                sps[:sub], cents[:sub]))
+            out["chamfer_adjacency"]["cpu_ms_extrapolated"] = t_ref * (len(sps) * (len(sps) - 1)) / (sub * (sub - 1))
+            out["chamfer_adjacency"]["cpu_kind"] = "create_cd on %d superpoints, scaled by pairs (%s)" % (
+                sub, "reference KD trees" if os.path.isdir("/root/reference") else "numpy restatement")
+    except Exception as e:
+        out["chamfer_adjacency"] = {"error": repr(e)}
     for d_, picks in ((32, 2000), (256, 1000)):
         try:
             g = torch.Generator(device=dev)

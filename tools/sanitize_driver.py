@@ -30,6 +30,9 @@ def main():
     S.selection.fps(F, 40, 7)
     S.selection.kcenter(F.astype(np.float64), np.arange(5), 20)
     S.selection.fps(rng.standard_normal((3000, 100)).astype(np.float32), 20, 1)
+    # chamfer adjacency
+    sps = [rng.random((int(n), 3)).astype(np.float32) + i for i, n in enumerate((5, 130, 300, 1100))]
+    S.chamfer.create_cd(sps, np.array([p.mean(0) for p in sps], np.float64))
     print("sanitize_driver done", flush=True)
 
 
