@@ -21,7 +21,7 @@ namespace chamfer {
 enum { WS_PTS = 0, WS_OFF = 1, WS_DIR = 2, WS_SCRATCH = 3, WS_OUT = 4 };
 
 constexpr int CT = 256;          // threads per block
-constexpr int PA = 4;            // source points per thread and pass
+constexpr int PA = 8;            // source points per thread and pass
 constexpr int TB = 1024;         // target points per shared-memory tile
 constexpr int MAX_LEAVES = 1024; // pairwise-sum leaves per source cloud (<= 128 values each, >= 57 once split)
 constexpr unsigned MAX_CLOUD = 50000;

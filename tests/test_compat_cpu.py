@@ -61,5 +61,6 @@ def test_selection_patch_rebinds_reference_modules(monkeypatch):
     done = patch.install(modules=("fps_gcn_cpu",))
     assert "fps_gcn_cpu.farthest_features_sample" in done
     assert fps_mod.farthest_features_sample is ssdr_al_b200.selection.farthest_features_sample
+    assert "fps_gcn_cpu.create_cd" in done and fps_mod.create_cd is ssdr_al_b200.chamfer.create_cd
     for m in ("fps_gcn_cpu", "kcenterGreedy", "ssdr_b200_patch"):
         sys.modules.pop(m, None)
