@@ -21,7 +21,7 @@ namespace chamfer {
 enum { WS_PTS = 0, WS_OFF = 1, WS_DIR = 2, WS_SCRATCH = 3, WS_OUT = 4 };
 
 constexpr int CT = 256;          // threads per block
-constexpr int PA = 8;            // source points per thread and pass
+constexpr int PA = 4;            // source points per thread and pass
 constexpr int TB = 1024;         // target points per shared-memory tile
 constexpr int MAX_LEAVES = 1024; // pairwise-sum leaves per source cloud (<= 128 values each, >= 57 once split)
 constexpr unsigned MAX_CLOUD = 50000;
@@ -91,6 +91,22 @@ __device__ double walk(unsigned n, unsigned* leaf_lo, unsigned* leaf_n, unsigned
     return ret;
 }
 
+// squared distances of PU register-resident source points to the nt target points of the tile, running minima
+template <int PU>
+__device__ __forceinline__ void scan_tile(const double* sx, const double* sy, const double* sz, unsigned nt,
+                                          const double (&ax)[PA], const double (&ay)[PA], const double (&az)[PA],
+                                          double (&best)[PA]) {
+    for (unsigned j = 0; j < nt; ++j) {
+        const double bx = sx[j], by = sy[j], bz = sz[j];
+#pragma unroll
+        for (int u = 0; u < PU; ++u) {
+            const double dx = __dsub_rn(ax[u], bx), dy = __dsub_rn(ay[u], by), dz = __dsub_rn(az[u], bz);
+            const double d = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+            best[u] = d < best[u] ? d : best[u];
+        }
+    }
+}
+
 __global__ void __launch_bounds__(CT) directed_kernel(const double* __restrict__ pts, const long long* __restrict__ off,
                                                       unsigned S, unsigned G, unsigned long long T,
                                                       double* __restrict__ scratch /* [G][T] */,
@@ -111,6 +127,7 @@ __global__ void __launch_bounds__(CT) directed_kernel(const double* __restrict__
         const unsigned nb = (unsigned)(off[b + 1] - off[b]);
         if (nb == 0) continue;
         for (unsigned k0 = 0; k0 < na; k0 += CT * PA) {
+            const int pu = (int)min((unsigned)PA, (na - k0 + CT - 1) / CT);
             double ax[PA], ay[PA], az[PA], best[PA];
 #pragma unroll
             for (int u = 0; u < PA; ++u) {
@@ -130,14 +147,13 @@ __global__ void __launch_bounds__(CT) directed_kernel(const double* __restrict__
                     sz[j] = pts[3 * (b0 + t0 + j) + 2];
                 }
                 __syncthreads();
-                for (unsigned j = 0; j < nt; ++j) {
-                    const double bx = sx[j], by = sy[j], bz = sz[j];
-#pragma unroll
-                    for (int u = 0; u < PA; ++u) {
-                        const double dx = __dsub_rn(ax[u], bx), dy = __dsub_rn(ay[u], by), dz = __dsub_rn(az[u], bz);
-                        const double d = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
-                        best[u] = d < best[u] ? d : best[u];
-                    }
+                // only as many register slots as this pass has source points for (block-uniform): small clouds would
+                // otherwise spend most of the FP64 issue slots on duplicates of their last point
+                switch (pu) {
+                    case 1: scan_tile<1>(sx, sy, sz, nt, ax, ay, az, best); break;
+                    case 2: scan_tile<2>(sx, sy, sz, nt, ax, ay, az, best); break;
+                    case 3: scan_tile<3>(sx, sy, sz, nt, ax, ay, az, best); break;
+                    default: scan_tile<PA>(sx, sy, sz, nt, ax, ay, az, best); break;
                 }
             }
 #pragma unroll
