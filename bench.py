@@ -460,6 +460,12 @@ def secondary_metrics(torch, D, dev, flush):
         tot = int(sizes.sum())
         out["chamfer_adjacency"] = {"superpoints": len(sps), "points": tot, "e2e_ms": ms,
                                     "pair_evals_per_s": float(tot) * tot / ms * 1e3}
+        S.chamfer.farthest_superpoint_sample(sps, cents, 8, 0)
+        n_pick = 60
+        ms_f = float(np.median([cpu_time(lambda: S.chamfer.farthest_superpoint_sample(sps, cents, n_pick, 0))
+                                for _ in range(3)]))
+        out["superpoint_fps"] = {"superpoints": len(sps), "picks": n_pick, "e2e_ms": ms_f,
+                                 "ms_per_pick": ms_f / (n_pick - 1)}
         if O is not None:  # the reference's KD-tree loop on the first 24 superpoints, scaled by the pair count
             sub = 24
             t_ref = cpu_time(lambda: (O.ref_create_cd if os.path.isdir("/root/reference") else O.create_cd)(

@@ -5,7 +5,8 @@
 farthest_features_sample is defined inside fps_gcn_cpu.py / fps_gcn_cuda.py themselves (fps_gcn_cpu.py:119,
 fps_gcn_cuda.py:123) and looked up as a module global by GCN_FPS_sampling (fps_gcn_cpu.py:170), so rebinding the
 module attribute is enough; kCenterGreedy is rebound in gcn.py's namespace (gcn.py:10 star-import); create_cd
-(fps_gcn_cpu.py:25, called as a module global by fps_adj_all at :93) is rebound the same way."""
+(fps_gcn_cpu.py:25, called as a module global by fps_adj_all at :93) and sampler2.farthest_superpoint_sample
+(sampler2.py:49, called at :577) are rebound the same way."""
 import importlib
 import os
 import sys
@@ -15,9 +16,9 @@ if _REPO not in sys.path:
     sys.path.insert(0, _REPO)
 
 
-def install(modules=("fps_gcn_cpu", "fps_gcn_cuda", "gcn", "kcenterGreedy")):
+def install(modules=("fps_gcn_cpu", "fps_gcn_cuda", "gcn", "kcenterGreedy", "sampler2")):
     from ssdr_al_b200.selection import farthest_features_sample, kCenterGreedy
-    from ssdr_al_b200.chamfer import create_cd
+    from ssdr_al_b200.chamfer import create_cd, farthest_superpoint_sample
     patched = []
     for name in modules:
         try:
@@ -33,4 +34,7 @@ def install(modules=("fps_gcn_cpu", "fps_gcn_cuda", "gcn", "kcenterGreedy")):
         if name == "fps_gcn_cpu" and hasattr(mod, "create_cd"):  # (fps_gcn_cuda's create_cd is a torch/chamfer3D op)
             mod.create_cd = create_cd
             patched.append(name + ".create_cd")
+        if name == "sampler2" and hasattr(mod, "farthest_superpoint_sample"):  # sampler2.py:49, called at :577
+            mod.farthest_superpoint_sample = farthest_superpoint_sample
+            patched.append(name + ".farthest_superpoint_sample")
     return patched

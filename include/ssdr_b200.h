@@ -177,6 +177,11 @@ int ssdr_kcenter_f64_dev(const double* d_X, size_t N, size_t D, const int64_t* d
  * diagonal.  Distances as sklearn's KDTree computes them (float64, sqrt(((dx^2+dy^2)+dz^2))), means in numpy's
  * pairwise order.  The _dev variant takes device pointers plus a host copy of the offsets (sizes the scratch). */
 int ssdr_chamfer_matrix_f64(const double* points, const int64_t* offsets, size_t S, double* out);
+/* farthest_superpoint_sample (sampler2.py:49-80): FPS over the S clouds with distance = squared distance of the
+ * centroids (S,3 float64) + chamfer distance to the current pick (the chamfer row of each pick is computed on demand,
+ * like the reference's loop); out[0] = trigger_idx, first arg-max on ties, strict '<' minimum update from 1e10. */
+int ssdr_superpoint_fps_f64(const double* points, const int64_t* offsets, size_t S, const double* centroids,
+                            int32_t trigger_idx, size_t n_samples, int32_t* out);
 int ssdr_chamfer_matrix_f64_dev(const double* d_points, const int64_t* d_offsets, const int64_t* h_offsets, size_t S,
                                 double* d_out, void* stream);
 

@@ -62,6 +62,7 @@ SIGNATURES = {
     "ssdr_kcenter_f32_dev": [vp, sz, sz, vp, sz, sz, vp, vp],
     "ssdr_kcenter_f64_dev": [vp, sz, sz, vp, sz, sz, vp, vp],
     "ssdr_chamfer_matrix_f64": [vp, vp, sz, vp],
+    "ssdr_superpoint_fps_f64": [vp, vp, sz, vp, C.c_int32, sz, vp],
     "ssdr_chamfer_matrix_f64_dev": [vp, vp, vp, sz, vp, vp],
     "ssdr_fps_f32_sharded": [vp, sz, sz, sz, sz, C.c_int32, sz, vp, vp, vp],
     "ssdr_nccl_unique_id": [vp],

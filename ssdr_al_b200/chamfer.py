@@ -22,3 +22,21 @@ def create_cd(superpoint_list, superpoint_centroid_list):
     out = np.empty((sp_num, sp_num), np.float64)
     _lib.check(_lib.lib().ssdr_chamfer_matrix_f64(_lib.ptr(pts), _lib.ptr(offsets), sp_num, _lib.ptr(out)))
     return out
+
+
+def farthest_superpoint_sample(superpoint_list, superpoint_centroid_list, sample_number, trigger_idx):
+    """sampler2.py:49-80: farthest point sampling over superpoints, distance = squared centroid distance + chamfer
+    distance to the current pick.  Returns (sample_number,) int32 starting with trigger_idx."""
+    sp_num = len(superpoint_list)
+    cents = np.ascontiguousarray(superpoint_centroid_list, dtype=np.float64).reshape(sp_num, 3)
+    aligned = [np.asarray(superpoint_list[i] - superpoint_centroid_list[i], dtype=np.float64).reshape(-1, 3)
+               for i in range(sp_num)]
+    offsets = np.zeros(sp_num + 1, np.int64)
+    np.cumsum([len(a) for a in aligned], out=offsets[1:])
+    if sp_num == 0 or (np.diff(offsets) == 0).any():
+        raise RuntimeError("ssdr_al_b200.chamfer.farthest_superpoint_sample: no or empty superpoints")
+    pts = np.ascontiguousarray(np.concatenate(aligned, axis=0))
+    out = np.zeros(int(sample_number), np.int32)
+    _lib.check(_lib.lib().ssdr_superpoint_fps_f64(_lib.ptr(pts), _lib.ptr(offsets), sp_num, _lib.ptr(cents),
+                                                  int(trigger_idx), int(sample_number), _lib.ptr(out)))
+    return out

@@ -107,71 +107,165 @@ __device__ __forceinline__ void scan_tile(const double* sx, const double* sy, co
     }
 }
 
+// shared memory of one block working on directed pairs
+struct PairSmem {
+    double sx[TB], sy[TB], sz[TB];
+    unsigned lo[MAX_LEAVES], n[MAX_LEAVES];
+    double sum[MAX_LEAVES];
+    unsigned nleaf;
+};
+
+// mean over the points of cloud a of the distance to the nearest point of cloud b (whole block; every thread returns
+// the value).  `mins` is the block's private scratch of na doubles; sm.lo / sm.n / sm.nleaf hold the leaf layout of na.
+__device__ double directed_mean(const double* __restrict__ pts, unsigned long long a0, unsigned na,
+                                unsigned long long b0, unsigned nb, double* __restrict__ mins, PairSmem& sm) {
+    for (unsigned k0 = 0; k0 < na; k0 += CT * PA) {
+        const int pu = (int)min((unsigned)PA, (na - k0 + CT - 1) / CT);
+        double ax[PA], ay[PA], az[PA], best[PA];
+#pragma unroll
+        for (int u = 0; u < PA; ++u) {
+            const unsigned k = k0 + (unsigned)u * CT + threadIdx.x;
+            const unsigned kk = k < na ? k : na - 1;
+            ax[u] = pts[3 * (a0 + kk)];
+            ay[u] = pts[3 * (a0 + kk) + 1];
+            az[u] = pts[3 * (a0 + kk) + 2];
+            best[u] = INFINITY;
+        }
+        for (unsigned t0 = 0; t0 < nb; t0 += TB) {
+            const unsigned nt = min((unsigned)TB, nb - t0);
+            __syncthreads();
+            for (unsigned j = threadIdx.x; j < nt; j += CT) {
+                sm.sx[j] = pts[3 * (b0 + t0 + j)];
+                sm.sy[j] = pts[3 * (b0 + t0 + j) + 1];
+                sm.sz[j] = pts[3 * (b0 + t0 + j) + 2];
+            }
+            __syncthreads();
+            // only as many register slots as this pass has source points for (block-uniform): small clouds would
+            // otherwise spend most of the FP64 issue slots on duplicates of their last point
+            switch (pu) {
+                case 1: scan_tile<1>(sm.sx, sm.sy, sm.sz, nt, ax, ay, az, best); break;
+                case 2: scan_tile<2>(sm.sx, sm.sy, sm.sz, nt, ax, ay, az, best); break;
+                case 3: scan_tile<3>(sm.sx, sm.sy, sm.sz, nt, ax, ay, az, best); break;
+                default: scan_tile<PA>(sm.sx, sm.sy, sm.sz, nt, ax, ay, az, best); break;
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < PA; ++u) {
+            const unsigned k = k0 + (unsigned)u * CT + threadIdx.x;
+            if (k < na) mins[k] = __dsqrt_rn(best[u]);
+        }
+    }
+    __syncthreads();  // mins complete (global writes of this block are visible to it after the barrier)
+    const unsigned nleaf = sm.nleaf;
+    for (unsigned l = threadIdx.x; l < nleaf && l < (unsigned)MAX_LEAVES; l += CT) sm.sum[l] = leaf_sum(mins + sm.lo[l], sm.n[l]);
+    __syncthreads();
+    __shared__ double s_mean;
+    if (threadIdx.x == 0) s_mean = __ddiv_rn(walk(na, nullptr, nullptr, nullptr, sm.sum), (double)na);
+    __syncthreads();
+    const double r = s_mean;
+    __syncthreads();  // the next pair overwrites mins, sm.sum and s_mean
+    return r;
+}
+
 __global__ void __launch_bounds__(CT) directed_kernel(const double* __restrict__ pts, const long long* __restrict__ off,
                                                       unsigned S, unsigned G, unsigned long long T,
                                                       double* __restrict__ scratch /* [G][T] */,
                                                       double* __restrict__ A /* [S][S]: A[a][b] = mean_a min_b */) {
-    __shared__ double sx[TB], sy[TB], sz[TB];
-    __shared__ unsigned s_lo[MAX_LEAVES], s_n[MAX_LEAVES];
-    __shared__ double s_sum[MAX_LEAVES];
-    __shared__ unsigned s_nleaf;
+    __shared__ PairSmem sm;
     const unsigned a = blockIdx.x, g = blockIdx.y;
     const unsigned long long a0 = (unsigned long long)off[a];
     const unsigned na = (unsigned)(off[a + 1] - off[a]);
     if (na == 0) return;
     double* mins = scratch + (size_t)g * T + a0;
-    if (threadIdx.x == 0) walk(na, s_lo, s_n, &s_nleaf, nullptr);  // the leaf layout depends on na only
+    if (threadIdx.x == 0) walk(na, sm.lo, sm.n, &sm.nleaf, nullptr);  // the leaf layout depends on na only
+    __syncthreads();
     for (unsigned b = g; b < S; b += G) {
         if (b == a) continue;
         const unsigned long long b0 = (unsigned long long)off[b];
         const unsigned nb = (unsigned)(off[b + 1] - off[b]);
         if (nb == 0) continue;
-        for (unsigned k0 = 0; k0 < na; k0 += CT * PA) {
-            const int pu = (int)min((unsigned)PA, (na - k0 + CT - 1) / CT);
-            double ax[PA], ay[PA], az[PA], best[PA];
-#pragma unroll
-            for (int u = 0; u < PA; ++u) {
-                const unsigned k = k0 + (unsigned)u * CT + threadIdx.x;
-                const unsigned kk = k < na ? k : na - 1;
-                ax[u] = pts[3 * (a0 + kk)];
-                ay[u] = pts[3 * (a0 + kk) + 1];
-                az[u] = pts[3 * (a0 + kk) + 2];
-                best[u] = INFINITY;
-            }
-            for (unsigned t0 = 0; t0 < nb; t0 += TB) {
-                const unsigned nt = min((unsigned)TB, nb - t0);
-                __syncthreads();
-                for (unsigned j = threadIdx.x; j < nt; j += CT) {
-                    sx[j] = pts[3 * (b0 + t0 + j)];
-                    sy[j] = pts[3 * (b0 + t0 + j) + 1];
-                    sz[j] = pts[3 * (b0 + t0 + j) + 2];
-                }
-                __syncthreads();
-                // only as many register slots as this pass has source points for (block-uniform): small clouds would
-                // otherwise spend most of the FP64 issue slots on duplicates of their last point
-                switch (pu) {
-                    case 1: scan_tile<1>(sx, sy, sz, nt, ax, ay, az, best); break;
-                    case 2: scan_tile<2>(sx, sy, sz, nt, ax, ay, az, best); break;
-                    case 3: scan_tile<3>(sx, sy, sz, nt, ax, ay, az, best); break;
-                    default: scan_tile<PA>(sx, sy, sz, nt, ax, ay, az, best); break;
-                }
-            }
-#pragma unroll
-            for (int u = 0; u < PA; ++u) {
-                const unsigned k = k0 + (unsigned)u * CT + threadIdx.x;
-                if (k < na) mins[k] = __dsqrt_rn(best[u]);
-            }
-        }
-        __syncthreads();  // mins complete (global writes of this block are visible to it after the barrier)
-        const unsigned nleaf = s_nleaf;
-        for (unsigned l = threadIdx.x; l < nleaf && l < (unsigned)MAX_LEAVES; l += CT) s_sum[l] = leaf_sum(mins + s_lo[l], s_n[l]);
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            const double total = walk(na, nullptr, nullptr, nullptr, s_sum);
-            A[(size_t)a * S + b] = __ddiv_rn(total, (double)na);
-        }
-        __syncthreads();  // the next target overwrites mins and s_sum
+        const double m = directed_mean(pts, a0, na, b0, nb, mins, sm);
+        if (threadIdx.x == 0) A[(size_t)a * S + b] = m;
     }
+}
+
+// ---- farthest_superpoint_sample (sampler2.py:49-80): FPS over superpoints, distance = squared centroid distance +
+// chamfer distance to the current pick; the chamfer ROW of the pick is computed when it is needed, like the reference
+// does.  row_kernel: block i -> row[i] = mean_i min_c + mean_c min_i; step_kernel: one block folds the row into the
+// running minimum (strict '<', sampler2.py:75-76) and takes the first arg-max (:78).  The pick travels between the
+// kernels in device memory, so the whole loop is enqueued without a host round trip.
+__global__ void __launch_bounds__(CT) row_kernel(const double* __restrict__ pts, const long long* __restrict__ off, unsigned S,
+                                                 const int* __restrict__ picks, unsigned step, unsigned long long T,
+                                                 unsigned nmax, double* __restrict__ scratch /* [T] + [S][nmax] */,
+                                                 double* __restrict__ row) {
+    __shared__ PairSmem sm;
+    const unsigned i = blockIdx.x;
+    const unsigned c = (unsigned)picks[step];
+    if (i == c) {
+        if (threadIdx.x == 0) row[i] = 0.0;
+        return;
+    }
+    const unsigned long long i0 = (unsigned long long)off[i], c0 = (unsigned long long)off[c];
+    const unsigned ni = (unsigned)(off[i + 1] - off[i]), nc = (unsigned)(off[c + 1] - off[c]);
+    if (threadIdx.x == 0) walk(ni, sm.lo, sm.n, &sm.nleaf, nullptr);
+    __syncthreads();
+    const double av1 = directed_mean(pts, i0, ni, c0, nc, scratch + i0, sm);                      // :18, :20
+    if (threadIdx.x == 0) walk(nc, sm.lo, sm.n, &sm.nleaf, nullptr);
+    __syncthreads();
+    const double av2 = directed_mean(pts, c0, nc, i0, ni, scratch + T + (size_t)i * nmax, sm);    // :19, :21
+    if (threadIdx.x == 0) row[i] = __dadd_rn(av1, av2);
+}
+
+__global__ void __launch_bounds__(1024) step_kernel(const double* __restrict__ cent, unsigned S, const double* __restrict__ row,
+                                                    double* __restrict__ distance, int* __restrict__ picks, unsigned step) {
+    __shared__ double s_d[32];
+    __shared__ unsigned s_i[32];
+    const unsigned c = (unsigned)picks[step];
+    const double cx = cent[3 * c], cy = cent[3 * c + 1], cz = cent[3 * c + 2];
+    double bd = -INFINITY;
+    unsigned bi = 0xFFFFFFFFu;
+    for (unsigned i = threadIdx.x; i < S; i += blockDim.x) {
+        const double dx = __dsub_rn(cent[3 * i], cx), dy = __dsub_rn(cent[3 * i + 1], cy), dz = __dsub_rn(cent[3 * i + 2], cz);
+        // np.sum(.., axis=-1) over three values: sequential adds
+        const double e = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+        const double d = __dadd_rn(e, row[i]);
+        double cur = distance[i];
+        if (d < cur) {
+            cur = d;
+            distance[i] = d;
+        }
+        if (cur > bd) {  // ascending i inside a thread: strict '>' keeps the lowest index
+            bd = cur;
+            bi = i;
+        }
+    }
+#pragma unroll
+    for (int m = 16; m > 0; m >>= 1) {
+        const double od = __shfl_xor_sync(0xffffffffu, bd, m);
+        const unsigned oi = __shfl_xor_sync(0xffffffffu, bi, m);
+        if (od > bd || (od == bd && oi < bi)) {
+            bd = od;
+            bi = oi;
+        }
+    }
+    if ((threadIdx.x & 31) == 0) {
+        s_d[threadIdx.x >> 5] = bd;
+        s_i[threadIdx.x >> 5] = bi;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (unsigned w = 1; w < blockDim.x / 32; ++w)
+            if (s_d[w] > bd || (s_d[w] == bd && s_i[w] < bi)) {
+                bd = s_d[w];
+                bi = s_i[w];
+            }
+        picks[step + 1] = (int)bi;
+    }
+}
+
+__global__ void fill_f64_kernel(double* p, unsigned n, double v) {
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
 }
 
 __global__ void symmetrize_kernel(const double* __restrict__ A, unsigned S, double* __restrict__ out) {
@@ -209,6 +303,36 @@ static int run_dev(Ctx* c, cudaStream_t s, const double* d_pts, const long long*
     return SSDR_OK;
 }
 
+static int run_superpoint_fps(Ctx* c, cudaStream_t s, const double* d_pts, const long long* d_off, const long long* h_off,
+                              size_t S, const double* d_cent, int trigger, size_t n_samples, int* d_picks) {
+    SSDR_REQUIRE(S >= 1 && n_samples >= 1, SSDR_ERR_INVALID, "no clouds or no samples");
+    SSDR_REQUIRE(trigger >= 0 && (size_t)trigger < S, SSDR_ERR_INVALID, "trigger_idx out of range");
+    const size_t T = (size_t)h_off[S];
+    size_t nmax = 0;
+    for (size_t i = 0; i < S; ++i) {
+        SSDR_REQUIRE(h_off[i + 1] > h_off[i], SSDR_ERR_INVALID, "empty or negative-size cloud %zu", i);
+        const size_t n = (size_t)(h_off[i + 1] - h_off[i]);
+        SSDR_REQUIRE(n <= MAX_CLOUD, SSDR_ERR_UNSUPPORTED, "cloud %zu has more than %u points", i, MAX_CLOUD);
+        nmax = n > nmax ? n : nmax;
+    }
+    SSDR_REQUIRE((T + S * nmax) * sizeof(double) <= ((size_t)8 << 30), SSDR_ERR_UNSUPPORTED,
+                 "scratch for %zu clouds of up to %zu points exceeds 8 GB", S, nmax);
+    SSDR_TRY(c->ws[WS_SCRATCH].reserve((T + S * nmax) * sizeof(double)));
+    SSDR_TRY(c->ws[WS_DIR].reserve(2 * S * sizeof(double)));
+    double* row = c->ws[WS_DIR].as<double>();
+    double* distance = row + S;
+    fill_f64_kernel<<<(unsigned)((S + 255) / 256), 256, 0, s>>>(distance, (unsigned)S, 1e10);  // sampler2.py:64
+    SSDR_CHECK_CUDA(cudaMemsetAsync(d_picks, 0, n_samples * sizeof(int), s));
+    SSDR_CHECK_CUDA(cudaMemcpyAsync(d_picks, &trigger, sizeof(int), cudaMemcpyHostToDevice, s));
+    for (size_t st = 0; st + 1 < n_samples; ++st) {
+        row_kernel<<<(unsigned)S, CT, 0, s>>>(d_pts, d_off, (unsigned)S, d_picks, (unsigned)st, (unsigned long long)T,
+                                             (unsigned)nmax, c->ws[WS_SCRATCH].as<double>(), row);
+        step_kernel<<<1, 1024, 0, s>>>(d_cent, (unsigned)S, row, distance, d_picks, (unsigned)st);
+    }
+    SSDR_CHECK_CUDA(cudaGetLastError());
+    return SSDR_OK;
+}
+
 }  // namespace chamfer
 }  // namespace ssdr
 
@@ -230,6 +354,28 @@ int ssdr_chamfer_matrix_f64(const double* points, const int64_t* offsets, size_t
     SSDR_TRY(chamfer::run_dev(c, c->stream, c->ws[chamfer::WS_PTS].as<double>(), c->ws[chamfer::WS_OFF].as<long long>(),
                               reinterpret_cast<const long long*>(offsets), S, c->ws[chamfer::WS_OUT].as<double>()));
     return d2h_sync(c, out, c->ws[chamfer::WS_OUT].p, S * S * sizeof(double), c->stream);
+}
+
+int ssdr_superpoint_fps_f64(const double* points, const int64_t* offsets, size_t S, const double* centroids,
+                            int32_t trigger_idx, size_t n_samples, int32_t* out) {
+    SSDR_REQUIRE(points && offsets && centroids && out, SSDR_ERR_INVALID, "NULL pointer");
+    SSDR_REQUIRE(S >= 1 && offsets[0] == 0, SSDR_ERR_INVALID, "offsets must start at 0 and hold S + 1 entries");
+    Ctx* c;
+    SSDR_TRY(get_ctx(&c));
+    const size_t T = (size_t)offsets[S];
+    SSDR_TRY(c->ws[chamfer::WS_PTS].reserve((T ? T : 1) * 3 * sizeof(double)));
+    SSDR_TRY(c->ws[chamfer::WS_OFF].reserve((S + 1) * sizeof(long long)));
+    SSDR_TRY(c->ws[chamfer::WS_OUT].reserve(S * 3 * sizeof(double) + (n_samples + 1) * sizeof(int)));
+    double* d_cent = c->ws[chamfer::WS_OUT].as<double>();
+    int* d_picks = reinterpret_cast<int*>(d_cent + S * 3);
+    SSDR_TRY(h2d(c, c->ws[chamfer::WS_PTS].p, points, T * 3 * sizeof(double), c->stream));
+    SSDR_TRY(h2d(c, c->ws[chamfer::WS_OFF].p, offsets, (S + 1) * sizeof(long long), c->stream));
+    SSDR_TRY(h2d(c, d_cent, centroids, S * 3 * sizeof(double), c->stream));
+    SSDR_TRY(chamfer::run_superpoint_fps(c, c->stream, c->ws[chamfer::WS_PTS].as<double>(),
+                                         c->ws[chamfer::WS_OFF].as<long long>(),
+                                         reinterpret_cast<const long long*>(offsets), S, d_cent, trigger_idx, n_samples,
+                                         d_picks));
+    return d2h_sync(c, out, d_picks, n_samples * sizeof(int), c->stream);
 }
 
 int ssdr_chamfer_matrix_f64_dev(const double* d_points, const int64_t* d_offsets, const int64_t* h_offsets, size_t S,

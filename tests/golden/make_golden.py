@@ -142,6 +142,10 @@ def make_chamfer():
         out[tag + "_offsets"] = np.concatenate([[0], np.cumsum([len(p) for p in sps])]).astype(np.int64)
         out[tag + "_centroids"] = cents
         out[tag + "_cd"] = create_cd(sps, cents)
+        # farthest_superpoint_sample (sampler2.py:49-80), run from the reference's own source
+        n_pick = min(len(sps), 10 if tag == "small" else 16)
+        out[tag + "_fps_picks"] = O.ref_farthest_superpoint_sample(sps, cents, n_pick, 0 if tag == "small" else 3)
+        out[tag + "_fps_trigger"] = np.int32(0 if tag == "small" else 3)
     np.savez_compressed(os.path.join(HERE, "chamfer.npz"), **out)
     print("chamfer", os.path.getsize(os.path.join(HERE, "chamfer.npz")) // 1024, "KiB")
 

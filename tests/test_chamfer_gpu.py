@@ -51,3 +51,29 @@ def test_chamfer_interface(oracle):
     sps = [rng.random((40, 3)), rng.random((60, 3)) + 2]
     cents = [list(s.mean(0)) for s in sps]
     assert np.array_equal(S.chamfer.create_cd(sps, cents), oracle.create_cd(sps, cents))
+
+
+@pytest.mark.parametrize("tag", ["small", "room"])
+def test_superpoint_fps_golden(golden, tag):
+    """farthest_superpoint_sample (sampler2.py:49-80) vs the picks of the reference's own function."""
+    import ssdr_al_b200 as S
+    g = golden.chamfer
+    sps, cents, _ = _split(g, tag)
+    want = g[tag + "_fps_picks"]
+    got = S.chamfer.farthest_superpoint_sample(sps, cents, len(want), int(g[tag + "_fps_trigger"]))
+    assert got.dtype == np.int32 and np.array_equal(got, want)
+
+
+def test_superpoint_fps_vs_oracle(oracle):
+    import ssdr_al_b200 as S
+    rng = np.random.default_rng(11)
+    sps, cents = [], []
+    for n in [int(v) for v in rng.integers(3, 500, 60)] + [1500]:
+        c = rng.random(3) * 8
+        p = (c + rng.normal(0, 0.3, (n, 3)) * rng.choice([1.0, 0.05], 3)).astype(np.float32)
+        sps.append(p)
+        cents.append((p.min(0).astype(np.float64) + p.max(0)) / 2.0)
+    cents = np.array(cents)
+    assert np.array_equal(S.chamfer.farthest_superpoint_sample(sps, cents, 25, 7),
+                          oracle.farthest_superpoint_sample(sps, cents, 25, 7))
+    assert np.array_equal(S.chamfer.farthest_superpoint_sample(sps, cents, 1, 5), np.array([5], np.int32))

@@ -115,3 +115,13 @@ def test_chamfer_restatement_equals_reference_golden(oracle, golden, tag):
     got = oracle.create_cd(sps, g[tag + "_centroids"])
     np.testing.assert_allclose(got, g[tag + "_cd"], rtol=1e-12, atol=0)
     assert np.mean(got == g[tag + "_cd"]) > 0.99
+
+
+@pytest.mark.parametrize("tag", ["small", "room"])
+def test_superpoint_fps_restatement_equals_reference_golden(oracle, golden, tag):
+    g = golden.chamfer
+    pts, off = g[tag + "_points"], g[tag + "_offsets"]
+    sps = [pts[off[i]:off[i + 1]] for i in range(len(off) - 1)]
+    want = g[tag + "_fps_picks"]
+    got = oracle.farthest_superpoint_sample(sps, g[tag + "_centroids"], len(want), int(g[tag + "_fps_trigger"]))
+    assert np.array_equal(got, want)

@@ -33,6 +33,7 @@ def main():
     # chamfer adjacency
     sps = [rng.random((int(n), 3)).astype(np.float32) + i for i, n in enumerate((5, 130, 300, 1100))]
     S.chamfer.create_cd(sps, np.array([p.mean(0) for p in sps], np.float64))
+    S.chamfer.farthest_superpoint_sample(sps, np.array([p.mean(0) for p in sps], np.float64), 3, 1)
     print("sanitize_driver done", flush=True)
 
 
