@@ -1,5 +1,7 @@
 """CPU: live comparison of the oracle restatement with the UNMODIFIED reference compiled as oracle/_ref/*.so
 (built by oracle/Makefile where /root/reference exists; the prebuilt .so files travel to the GPU box)."""
+import os
+
 import numpy as np
 import pytest
 
@@ -43,3 +45,20 @@ def test_grid_live(dl):
     b = O.ref_grid_subsample(p, rgb, lab, dl)
     for x, y in zip(a, b):
         assert x.tobytes() == y.tobytes()
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/SSDR_AL_s3dis"), reason="reference checkout not present")
+def test_chamfer_and_superpoint_fps_live():
+    """Restatements vs the reference's own create_cd (fps_gcn_cpu.py) and farthest_superpoint_sample (sampler2.py, run
+    from its source text) on fresh random superpoints: matrices within the KD tree's bound rounding, picks identical."""
+    rng = np.random.default_rng(8)
+    sps, cents = [], []
+    for n in [int(v) for v in rng.integers(2, 260, 18)]:
+        c = rng.random(3) * 4
+        p = (c + rng.normal(0, 0.3, (n, 3)) * rng.choice([1.0, 0.03], 3)).astype(np.float32)
+        sps.append(p)
+        cents.append(np.asarray([(np.min(p[:, d]) + np.max(p[:, d])) / 2.0 for d in range(3)]))
+    cents = np.asarray(cents)
+    np.testing.assert_allclose(O.create_cd(sps, cents), O.ref_create_cd(sps, cents), rtol=1e-12, atol=0)
+    assert np.array_equal(O.farthest_superpoint_sample(sps, cents, 9, 2),
+                          O.ref_farthest_superpoint_sample(sps, cents, 9, 2))
