@@ -6,16 +6,26 @@ SSDR_AL_s3dis/s3dis_dataset.py:164-177.
 One "step" = one full pyramid for one batch of 6 synthetic clouds (seeded uniform box).
   value  = k=16 KNN queries/s with the clouds already resident in HBM (device-pointer C ABI, CUDA-event timed; the
            1-NN up-sampling work is inside the timed region but only k=16 queries are counted).
-  e2e    = the same metric through the reference-facing Python API (`nearest_neighbors.knn_batch`, host numpy in,
-           host int64 out), host<->device copies inside the timed region.
-  roofline     = the dominant kernel (level-0 k=16 query kernel) against the measured HBM copy peak.
+  e2e    = the same metric through the reference-facing Python API (`nearest_neighbors.knn_batch`, pageable host
+           numpy in, host int64 out), host<->device copies inside the timed region.
+  roofline     = the dominant kernel (level-0 k=16 query kernel) against the measured HBM copy peak, with the
+                 issue-side numbers that actually bound it.
   cpu_baseline = the reference's own nanoflann/OpenMP code (oracle/_ref, or the C port when _ref is absent) timed on
-                 this box's host cores on the same pyramid.
+                 this box's host cores on the same pyramid, OpenMP team pinned explicitly.
 `--impl reference` runs only that CPU reference, as the driver's reference arm.
-Multi-GPU (torchrun, one rank per GPU): batch items are independent, every rank runs its own batch of 6 clouds,
-no data-path collective (weak scaling).
+
+Multi-GPU (torchrun, one rank per GPU):
+  * headline: batch items are independent, every rank runs its own batch of 6 clouds, no data-path collective (weak).
+  * `extra.multi_gpu` (strong scaling, total work fixed as N grows; the same section runs at N = 1 so the driver's
+    N = 1, 2, 4, 8 lines are comparable): config 3 (one Semantic3D-scale scan: slab-sharded subsampling -> all-gather
+    of the slabs -> query-sharded k=16 KNN), config 4 (row-sharded FPS / k-center, the per-pick exchange fused into the
+    persistent kernel over NVLink peer memory), config 5 (272 rooms round-robin + one global selection).
+  * at N > 1 every sharded result is compared bit for bit with the single-GPU result IN THIS PROCESS
+    (tools/multigpu_check.py + the full-size checks below); a mismatch is printed in the line and the exit code is 1.
 """
 import argparse
+import contextlib
+import io
 import json
 import os
 import subprocess
@@ -36,6 +46,11 @@ K16_QUERIES = B * sum(LEVELS)                    # 327,360 per step
 K1_QUERIES = B * sum(LEVELS)                     # up-sampling: queries = the level's points, support = next level
 METRIC = "k16_knn_queries_per_s"
 WORKLOAD = "randla_s3dis_pyramid_b6x40960_k16_plus_1nn_upsampling"
+# identical in both arms (the driver compares the dicts)
+CONFIG = {"workload": WORKLOAD, "batch_per_gpu": B, "points": N0, "k": K, "levels": LEVELS,
+          "l2": "flushed between timed iterations (256 MiB write)", "timing": "CUDA events per step, summed",
+          "k1_queries_per_step": K1_QUERIES, "k16_queries_per_step": K16_QUERIES}
+CPU_THREADS = min(B, os.cpu_count() or 1)  # knn_batch(omp=True) parallelises over the 6 batch items (knn_.cxx:108-109)
 
 
 def make_clouds(seed):
@@ -49,6 +64,16 @@ def ncu_traffic(kernel):
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
             return float(json.load(f)[kernel]["dram_bytes_per_launch"])
+    except Exception:
+        return None
+
+
+def ncu_issue(kernel):
+    """Issue-side numbers of the same capture (issue slots busy, warp instructions per query, lanes active)."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            d = json.load(f)[kernel]
+        return {k: d[k] for k in ("issue_active_pct", "warp_inst_per_query", "lanes_active", "fma_pipe_pct") if k in d}
     except Exception:
         return None
 
@@ -118,12 +143,13 @@ def cpu_pyramid(xyz, fn):
 
 
 def cpu_reference_fn():
+    """(knn_batch callable, kind, OpenMP threads).  torchrun exports OMP_NUM_THREADS=1 to every rank; the team size is
+    therefore set explicitly (and reported) instead of inherited."""
     from oracle import oracle as O
-    cores = os.cpu_count() or 1
+    t = O.set_omp_threads(CPU_THREADS)
     if O.have_ref():
-        return (lambda p, q, k: O.ref_knn_batch(p, q, k, omp=True)), "reference", min(B, cores)
+        return (lambda p, q, k: O.ref_knn_batch(p, q, k, omp=True)), "reference", t
     O.lib()
-    t = min(B, cores)
     return (lambda p, q, k: O.knn_batch(p, q, k, threads=t)), "port", t
 
 
@@ -144,10 +170,11 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": val, "unit": "queries/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "batch": B, "points": N0, "k": K, "levels": LEVELS},
+        "config": CONFIG,
         "cpu_baseline": {"value": val, "unit": "queries/s", "cores": cores, "kind": kind,
-                         "sample": "%d full pyramid steps, knn_batch(omp=True): OpenMP over the %d batch items" %
-                                   (args.steps, B)},
+                         "omp_num_threads": cores, "host_cpus": os.cpu_count(),
+                         "sample": "%d full pyramid steps, knn_batch(omp=True): OpenMP over the %d batch items, one "
+                                   "host process (rank 0) whatever --gpus says" % (args.steps, B)},
         "e2e": {"value": val, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -180,9 +207,8 @@ def run_ours(args):
     outs16 = [torch.zeros((B, n, K), dtype=torch.int64, device=dev) for n in LEVELS]
     outs1 = [torch.zeros((B, n, 1), dtype=torch.int64, device=dev) for n in LEVELS]
 
-    def gpu_pyramid(collect=None):
-        xyz = xyz0
-        launches = 0
+    def gpu_pyramid(collect=None, xyz=None):
+        xyz = xyz0 if xyz is None else xyz
         for li, ratio in enumerate(RATIOS):
             r = D.knn_batch(xyz, xyz, K, out=outs16[li], want_stats=collect is not None)
             if collect is not None:
@@ -192,7 +218,6 @@ def run_ours(args):
             if collect is not None:
                 collect.append(("k1", li, r1[1]))
             xyz = sub
-        return launches
 
     def count_launches(stats):
         # counted inside the library where the launches happen (memsets and torch's slicing copies not included)
@@ -237,13 +262,14 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         total_ms = float(t.item())
 
-    # ---- e2e through the reference-facing API: host numpy in (pinned), host int64 out
+    # ---- e2e through the reference-facing API: host numpy in, host int64 out.  The caller's arrays are ordinary
+    # (pageable) numpy memory, like the dataset loader's (s3dis_dataset.py:152-166); a second figure with the input
+    # placed in pinned memory is kept beside it.
     NN = S.nearest_neighbors
     pinned = _lib.pinned_empty(host_clouds.shape, np.float32)
     pinned[...] = host_clouds
 
-    def api_pyramid():
-        xyz = pinned
+    def api_pyramid(xyz):
         h2d = d2h = 0
         for ratio in RATIOS:
             idx = NN.knn_batch(xyz, xyz, K, omp=True)
@@ -256,30 +282,48 @@ def run_ours(args):
             xyz = sub
         return h2d, d2h
 
-    for _ in range(2):
-        h2d_b, d2h_b = api_pyramid()
-    e2e_steps = max(3, min(args.steps, 10))
-    if world > 1:
-        dist.barrier()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        api_pyramid()
-    e2e_dt = time.perf_counter() - t0
-    if world > 1:
-        t = torch.tensor([e2e_dt], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_dt = float(t.item())
+    def time_api(src):
+        for _ in range(2):
+            hb, db = api_pyramid(src)
+        steps = max(3, min(args.steps, 10))
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            api_pyramid(src)
+        dt = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([dt], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        return K16_QUERIES * world * steps / dt, hb, db, steps
+
+    e2e_val, h2d_b, d2h_b, e2e_steps = time_api(host_clouds)
+    e2e_pinned, _, _, _ = time_api(pinned)
     clocks = sampler.stop() if rank == 0 else None
 
-    # ---- secondary numbers of the same hot path (rank 0, short): grid subsampling and FPS, device resident
+    # ---- secondary numbers of the same hot path (rank 0, short): grid subsampling, config-1 KNN, FPS / k-center
     extra = {}
     if rank == 0 and not args.no_extra:
-        extra = secondary_metrics(torch, D, dev, flush)
+        extra = secondary_metrics(torch, D, dev, flush, gpu_pyramid)
+    # ---- sharded paths: all ranks take part (at N = 1 the same workloads run on the one GPU)
+    mg_ok = True
+    if not args.no_extra and not args.no_multi:
+        try:
+            mg, mg_ok = multi_gpu_metrics(torch, dist, D, dev, rank, world, flush)
+        except Exception as e:  # a failure here must not hide the headline: it is recorded in the line
+            mg, mg_ok = {"error": repr(e)}, True
+        if world > 1:
+            flag = torch.tensor([1 if mg_ok else 0], device=dev)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+            mg_ok = int(flag.item()) == 1
+        extra["multi_gpu"] = mg
 
     if rank != 0:
         if world > 1:
+            dist.barrier()
             dist.destroy_process_group()
-        return
+        sys.exit(0 if mg_ok else 1)
 
     peak, peak_src = measured_peak()
     q0 = B * N0
@@ -291,18 +335,20 @@ def run_ours(args):
         "metric": METRIC, "value": K16_QUERIES * world * args.steps / (total_ms * 1e-3), "unit": "queries/s",
         "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "batch_per_gpu": B, "points": N0, "k": K, "levels": LEVELS,
-                   "l2": "flushed between timed iterations (256 MiB write)", "timing": "CUDA events per step, summed",
-                   "k1_queries_per_step": K1_QUERIES, "k16_queries_per_step": K16_QUERIES},
-        "e2e": {"value": K16_QUERIES * world * e2e_steps / e2e_dt, "unit": "queries/s",
+        "config": CONFIG,
+        "e2e": {"value": e2e_val, "unit": "queries/s",
                 "h2d_bytes_per_step": int(h2d_b), "d2h_bytes_per_step": int(d2h_b), "steps": e2e_steps,
+                "input": "pageable numpy arrays (what the dataset loader passes)", "pinned_input_value": e2e_pinned,
                 "api": "ssdr_al_b200.nearest_neighbors.knn_batch (numpy in/out, int64 indices)"},
         "gpu_launches": launches_per_step * args.steps,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": ncu_traffic("knn_query_kernel_level0"), "peak_source": peak_src, "kernel": "knn::query_kernel<17,int64> level 0 (6x40960)",
+                     "traffic": ncu_traffic("knn_query_kernel_level0"), "peak_source": peak_src,
+                     "kernel": "knn::query_kernel<17,int64> level 0 (6x40960)",
                      "kernel_ms": dom_ms_avg, "algorithmic_bytes": algo_bytes,
-                     "note": "KNN is FP32/issue bound, not HBM bound (SURVEY.md 8d); see dist_evals_per_s",
-                     "dist_evals_per_s": evals0 / (dom_ms_avg * 1e-3), "dist_evals_per_query": evals0 / q0},
+                     "note": "KNN is FP32/issue bound, not HBM bound (SURVEY.md 8d): the numbers that bound it are "
+                             "dist_evals_per_s and `issue` (ncu capture of the same launch)",
+                     "dist_evals_per_s": evals0 / (dom_ms_avg * 1e-3), "dist_evals_per_query": evals0 / q0,
+                     "issue": ncu_issue("knn_query_kernel_level0")},
         "clocks": clocks,
         "knn_detail": {"tie_rows_per_step": int(tie_rows), "stage_ms": [
             {"call": kind, "level_points": LEVELS[li], "grid_build_ms": st["grid_build_ms"],
@@ -311,7 +357,7 @@ def run_ours(args):
             for kind, li, st in stats]},
         "extra": extra,
     }
-    # CPU baseline (bounded sample: 2 pyramid steps after 1 warm-up)
+    # CPU baseline (bounded sample: 2 pyramid steps after 1 warm-up), team size pinned like the reference arm's
     try:
         fn, kind, cores = cpu_reference_fn()
         cpu_pyramid(host_clouds, fn)
@@ -320,74 +366,78 @@ def run_ours(args):
             cpu_pyramid(host_clouds, fn)
         dt = time.perf_counter() - t0
         line["cpu_baseline"] = {"value": K16_QUERIES * 2 / dt, "unit": "queries/s", "cores": cores, "kind": kind,
-                                "sample": "2 full pyramid steps (same 6x40960 clouds), knn_batch(omp=True), host has "
-                                          "%d cpus" % (os.cpu_count() or 0)}
+                                "omp_num_threads": cores, "host_cpus": os.cpu_count(),
+                                "sample": "2 full pyramid steps (same 6x40960 clouds), knn_batch(omp=True), OpenMP team "
+                                          "set to %d explicitly, host has %d cpus" % (cores, os.cpu_count() or 0)}
     except Exception as e:  # the oracle is test infrastructure; its absence must not hide the GPU number
         line["cpu_baseline"] = {"value": None, "unit": "queries/s", "cores": 0, "kind": "port", "sample": "failed: %r" % e}
     print(json.dumps(line), flush=True)
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
+    sys.exit(0 if mg_ok else 1)
 
 
-def secondary_metrics(torch, D, dev, flush):
-    """Grid subsampling (config-1 shape) and FPS / k-center (config-4 shape), device resident, CUDA-event timed."""
-    out = {}
-    peak, _ = measured_peak()
+def _timed(torch, flush, fn, reps):
+    ts = []
+    r = None
+    for _ in range(reps):
+        flush.zero_()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        r = fn()
+        b.record()
+        torch.cuda.synchronize()
+        ts.append(a.elapsed_time(b))
+    return float(np.median(ts)), r
 
-    def timed(fn, reps):
-        ts = []
-        for _ in range(reps):
-            flush.zero_()
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record()
-            r = fn()
-            b.record()
-            torch.cuda.synchronize()
-            ts.append(a.elapsed_time(b))
-        return float(np.median(ts)), r
 
-    def cpu_time(fn):
-        t0 = time.perf_counter()
-        fn()
-        return (time.perf_counter() - t0) * 1e3
+def _cpu_ms(fn):
+    t0 = time.perf_counter()
+    fn()
+    return (time.perf_counter() - t0) * 1e3
 
+
+def _oracle():
     try:
         from oracle import oracle as O
         O.lib()
+        return O
     except Exception:
-        O = None
+        return None
+
+
+def secondary_metrics(torch, D, dev, flush, gpu_pyramid):
+    """Grid subsampling + KNN (config-1 shape), FPS / k-center (config-4 shape), the tie-heavy pyramid (8f-1), chamfer
+    adjacency: device resident, CUDA-event timed, each with its end-to-end and CPU-reference figure beside it."""
+    from tools import synth
+    out = {}
+    peak, _ = measured_peak()
+    O = _oracle()
+    timed = lambda fn, reps: _timed(torch, flush, fn, reps)  # noqa: E731
 
     try:
         import ssdr_al_b200 as S
-        rng = np.random.default_rng(0)
         n = 1_000_000
-        face = rng.integers(0, 3, n)
-        p = rng.random((n, 3)) * np.array([7.0, 5.0, 3.0])
-        p[face == 0, 2] = 0
-        p[face == 1, 1] = 0
-        p[face == 2, 0] = 0
-        p += rng.normal(0, 0.005, p.shape)
-        p -= p.min(0)
-        p = p.astype(np.float32)
-        rgb_h = rng.integers(0, 256, (n, 3)).astype(np.uint8)
-        lab_h = ((p[:, 0] * 1.7).astype(np.int32) % 13).astype(np.uint8)
+        p, rgb_h, lab_h = synth.room_cloud(n, 0)  # SURVEY.md 8d: floor, ceiling, walls, furniture; ~9 points / voxel
         pts = torch.from_numpy(p).to(dev)
         rgb = torch.from_numpy(rgb_h.astype(np.float32)).to(dev)
         lab = torch.from_numpy(lab_h.astype(np.int32)).to(dev)
         D.grid_subsample(pts, rgb, lab, 0.04)
-        ms, r = timed(lambda: D.grid_subsample(pts, rgb, lab, 0.04), 5)
+        ms, r = timed(lambda: D.grid_subsample(pts, rgb, lab, 0.04), 7)
         m = r[0].shape[0]
         algo = n * 28 + m * 28
         g = {"points": n, "voxels": int(m), "ms": ms, "mpts_per_s": n / ms / 1e3,
-             "algorithmic_gbs": algo / ms / 1e6, "frac_of_hbm_peak": algo / ms / 1e6 / peak}
+             "algorithmic_gbs": algo / ms / 1e6, "frac_of_hbm_peak": algo / ms / 1e6 / peak,
+             "traffic_bytes": ncu_traffic("grid_subsample_1m")}
         # the same call through the reference-facing API (uint8 colours / labels in, conversions + PCIe inside)
         S.grid_subsampling.compute(p, features=rgb_h, classes=lab_h, sampleDl=0.04)
-        g["e2e_ms"] = float(np.median([cpu_time(lambda: S.grid_subsampling.compute(
+        g["e2e_ms"] = float(np.median([_cpu_ms(lambda: S.grid_subsampling.compute(
             p, features=rgb_h, classes=lab_h, sampleDl=0.04)) for _ in range(3)]))
         g["e2e_mpts_per_s"] = n / g["e2e_ms"] / 1e3
         if O is not None:
             ref = O.ref_grid_subsample if O.have_ref() else O.grid_subsample
-            g["cpu_ms"] = cpu_time(lambda: ref(p, rgb_h.astype(np.float32), lab_h.astype(np.int32), 0.04))
+            g["cpu_ms"] = _cpu_ms(lambda: ref(p, rgb_h.astype(np.float32), lab_h.astype(np.int32), 0.04))
             g["cpu_kind"] = "reference (1 thread, one run)" if O.have_ref() else "port (1 thread, one run)"
         out["grid_subsample"] = g
         # config 1, second half: k=16 KNN of the sub-sampled cloud on itself (one cloud, N = Q = M)
@@ -403,8 +453,27 @@ def secondary_metrics(torch, D, dev, flush):
             return D.knn_batch(c, c, K)
 
         ms, _ = timed(knn_once, 6)
-        out["knn_cfg1"] = {"points": int(m), "k": K, "ms": ms, "queries_per_s": m / ms * 1e3}
+        kc = {"points": int(m), "k": K, "ms": ms, "queries_per_s": m / ms * 1e3}
+        sub_h = [c[0].cpu().numpy() for c in clouds2]
+        S.nearest_neighbors.knn(sub_h[0], sub_h[0], K, omp=True)
+
+        def knn_api():
+            turn[0] ^= 1
+            return S.nearest_neighbors.knn(sub_h[turn[0]], sub_h[turn[0]], K, omp=True)
+
+        kc["e2e_ms"] = float(np.median([_cpu_ms(knn_api) for _ in range(4)]))
+        kc["e2e_queries_per_s"] = m / kc["e2e_ms"] * 1e3
+        if O is not None:
+            threads = O.set_omp_threads(os.cpu_count() or 1)  # cpp_knn_omp parallelises over the queries
+            fn = (lambda: O.ref_knn(sub_h[0], sub_h[0], K, omp=True)) if O.have_ref() else (
+                lambda: O.knn(sub_h[0], sub_h[0], K, threads=threads))
+            kc["cpu_ms"] = _cpu_ms(fn)
+            kc["cpu_kind"] = "%s knn(omp=True), %d OpenMP threads, one run" % (
+                "reference" if O.have_ref() else "port", threads)
+            O.set_omp_threads(CPU_THREADS)
+        out["knn_cfg1"] = kc
         # worst case for the subsampler: uniform in volume, M ~ 0.88 N
+        rng = np.random.default_rng(0)
         u = torch.from_numpy((rng.random((n, 3)) * np.array([7.0, 5.0, 3.0])).astype(np.float32)).to(dev)
         D.grid_subsample(u, rgb, lab, 0.04)
         ms, r = timed(lambda: D.grid_subsample(u, rgb, lab, 0.04), 5)
@@ -416,32 +485,36 @@ def secondary_metrics(torch, D, dev, flush):
     try:  # the same pyramid on SURFACE crops: what the real pipeline feeds (40960 nearest points of a random centre
         # in a room made of planes, shuffled) -- the headline config is uniform-in-volume by definition
         rng = np.random.default_rng(5)
-        n = 400_000
-        kk = rng.integers(0, 8, n)
-        room = rng.random((n, 3)) * np.array([7.0, 5.0, 3.0])
-        for v, (ax, val) in enumerate(((2, 0.0), (2, 3.0), (1, 0.0), (1, 5.0), (0, 0.0), (0, 7.0))):
-            room[kk == v, ax] = val
-        room[kk >= 6, 2] = 0.75
-        room += rng.normal(0, 0.004, room.shape)
-        room = room.astype(np.float32)
+        room, _, _ = synth.room_cloud(400_000, 5, noise=0.004)
         crops = []
         for _ in range(B):
-            dd = ((room - room[rng.integers(0, n)]) ** 2).sum(1)
+            dd = ((room - room[rng.integers(0, len(room))]) ** 2).sum(1)
             crops.append(room[rng.permutation(np.argpartition(dd, N0)[:N0])])
-        cx = torch.from_numpy(np.stack(crops)).to(dev)
-
-        def crop_pyramid():
-            xyz = cx
-            for ratio in RATIOS:
-                D.knn_batch(xyz, xyz, K)
-                sub = xyz[:, : xyz.shape[1] // ratio, :].contiguous()
-                D.knn_batch(sub, xyz, 1)
-                xyz = sub
-
-        crop_pyramid()
-        ms, _ = timed(crop_pyramid, 7)
+        crops = np.stack(crops)
+        cx = torch.from_numpy(crops).to(dev)
+        gpu_pyramid(xyz=cx)
+        ms, _ = timed(lambda: gpu_pyramid(xyz=cx), 7)
         out["pyramid_surface_crops"] = {"batch": B, "points": N0, "ms": ms, "k16_queries_per_s": K16_QUERIES / ms * 1e3}
-        del cx
+        # duplicate-heavy input -- the loader's data_aug pads short crops by REPEATING points
+        # (s3dis_dataset.py:147-150), so most rows of such a batch hold exact distance ties and take the tie path
+        dup = crops.copy()
+        for b in range(B):
+            keep = N0 // 2
+            dup[b, keep:] = dup[b, rng.integers(0, keep, N0 - keep)]
+            dup[b] = dup[b, rng.permutation(N0)]
+        cd = torch.from_numpy(dup).to(dev)
+        st = []
+        gpu_pyramid(collect=st, xyz=cd)
+        ms, _ = timed(lambda: gpu_pyramid(xyz=cd), 5)
+        out["pyramid_duplicated_points"] = {
+            "batch": B, "points": N0, "duplicated_fraction": 0.5, "ms": ms, "k16_queries_per_s": K16_QUERIES / ms * 1e3,
+            "tie_rows_per_step": int(sum(s_[2]["tie_rows"] for s_ in st)),
+            "tie_path_ms": float(sum(s_[2]["tie_path_ms"] for s_ in st))}
+        if O is not None:
+            fn, kind, cores = cpu_reference_fn()
+            out["pyramid_duplicated_points"]["cpu_ms"] = _cpu_ms(lambda: cpu_pyramid(dup, fn))
+            out["pyramid_duplicated_points"]["cpu_kind"] = "%s, %d threads" % (kind, cores)
+        del cx, cd
     except Exception as e:
         out["pyramid_surface_crops"] = {"error": repr(e)}
     try:  # chamfer adjacency of one room's superpoints (fps_gcn_cpu.py:25-38), host arrays in / matrix out
@@ -456,23 +529,23 @@ def secondary_metrics(torch, D, dev, flush):
             cents.append((pp.min(0).astype(np.float64) + pp.max(0)) / 2.0)
         cents = np.array(cents)
         S.chamfer.create_cd(sps, cents)
-        ms = float(np.median([cpu_time(lambda: S.chamfer.create_cd(sps, cents)) for _ in range(3)]))
+        ms = float(np.median([_cpu_ms(lambda: S.chamfer.create_cd(sps, cents)) for _ in range(3)]))
         tot = int(sizes.sum())
         out["chamfer_adjacency"] = {"superpoints": len(sps), "points": tot, "e2e_ms": ms,
                                     "pair_evals_per_s": float(tot) * tot / ms * 1e3}
         S.chamfer.farthest_superpoint_sample(sps, cents, 8, 0)
         n_pick = 60
-        ms_f = float(np.median([cpu_time(lambda: S.chamfer.farthest_superpoint_sample(sps, cents, n_pick, 0))
+        ms_f = float(np.median([_cpu_ms(lambda: S.chamfer.farthest_superpoint_sample(sps, cents, n_pick, 0))
                                 for _ in range(3)]))
         out["superpoint_fps"] = {"superpoints": len(sps), "picks": n_pick, "e2e_ms": ms_f,
                                  "ms_per_pick": ms_f / (n_pick - 1)}
         if O is not None:  # the reference's KD-tree loop on the first 24 superpoints, scaled by the pair count
             sub = 24
-            t_ref = cpu_time(lambda: (O.ref_create_cd if os.path.isdir("/root/reference") else O.create_cd)(
-                sps[:sub], cents[:sub]))
+            have = O.have_ref_py()
+            t_ref = _cpu_ms(lambda: (O.ref_py("fps_gcn_cpu").create_cd if have else O.create_cd)(sps[:sub], cents[:sub]))
             out["chamfer_adjacency"]["cpu_ms_extrapolated"] = t_ref * (len(sps) * (len(sps) - 1)) / (sub * (sub - 1))
             out["chamfer_adjacency"]["cpu_kind"] = "create_cd on %d superpoints, scaled by pairs (%s)" % (
-                sub, "reference KD trees" if os.path.isdir("/root/reference") else "numpy restatement")
+                sub, "reference KD trees" if have else "numpy restatement")
     except Exception as e:
         out["chamfer_adjacency"] = {"error": repr(e)}
     for d_, picks in ((32, 2000), (256, 1000)):
@@ -485,7 +558,8 @@ def secondary_metrics(torch, D, dev, flush):
             per = ms / (picks - 1)
             algo = 500_000 * (4 * d_ + 8)
             out["fps_d%d" % d_] = {"rows": 500_000, "picks": picks, "ms_per_pick": per, "picks_per_s": 1e3 / per,
-                                   "algorithmic_gbs": algo / per / 1e6, "frac_of_hbm_peak": algo / per / 1e6 / peak}
+                                   "algorithmic_gbs": algo / per / 1e6, "frac_of_hbm_peak": algo / per / 1e6 / peak,
+                                   "traffic_bytes_per_pick": ncu_traffic("fps_d%d" % d_)}
             sel = torch.arange(500_000 - 16, 500_000, device=dev, dtype=torch.int64)
             D.kcenter(F, sel, 16)
             ms, _ = timed(lambda: D.kcenter(F, sel, picks), 3)
@@ -493,19 +567,233 @@ def secondary_metrics(torch, D, dev, flush):
             algo = 500_000 * (4 * d_ + 8 + 8)
             out["kcenter_d%d" % d_] = {"rows": 500_000, "picks": picks, "ms_per_pick": per, "picks_per_s": 1e3 / per,
                                        "algorithmic_gbs": algo / per / 1e6, "frac_of_hbm_peak": algo / per / 1e6 / peak}
-            if O is not None:  # the reference loops on the host, a few picks, extrapolated linearly
+            if O is not None:  # the reference's own loops on the host, a few picks, extrapolated linearly
                 Fh = F.cpu().numpy()
                 npk = 8 if d_ == 32 else 4
-                out["fps_d%d" % d_]["cpu_ms_per_pick"] = cpu_time(lambda: O.fps_numpy(Fh, npk + 1, 12345)) / npk
-                out["fps_d%d" % d_]["cpu_kind"] = "numpy loop of fps_gcn_cpu.py:137-146, %d picks, 1 process" % npk
                 selh = np.arange(500_000 - 4, 500_000)
-                out["kcenter_d%d" % d_]["cpu_ms_per_pick"] = cpu_time(lambda: O.kcenter(Fh, selh, npk)) / (npk + 4)
-                out["kcenter_d%d" % d_]["cpu_kind"] = "sklearn-formula restatement, %d centres, host BLAS threads" % (npk + 4)
+                if O.have_ref_py():
+                    fps_ref = O.ref_py("fps_gcn_cpu").farthest_features_sample
+                    kcg = O.ref_py("kcenterGreedy").kCenterGreedy
+                    out["fps_d%d" % d_]["cpu_ms_per_pick"] = _cpu_ms(lambda: fps_ref(Fh, npk + 1)) / npk
+                    out["fps_d%d" % d_]["cpu_kind"] = ("reference farthest_features_sample (fps_gcn_cpu.py:119-147), "
+                                                       "%d picks, 1 process" % npk)
+                    with contextlib.redirect_stdout(io.StringIO()):  # the reference prints progress lines
+                        out["kcenter_d%d" % d_]["cpu_ms_per_pick"] = _cpu_ms(
+                            lambda: kcg(Fh).select_batch_(selh, npk)) / (npk + 4)
+                    out["kcenter_d%d" % d_]["cpu_kind"] = ("reference kCenterGreedy.select_batch_ (sklearn %s), %d "
+                                                           "centres, host BLAS threads" % (_sklearn_version(), npk + 4))
+                else:
+                    out["fps_d%d" % d_]["cpu_ms_per_pick"] = _cpu_ms(lambda: O.fps_numpy(Fh, npk + 1, 12345)) / npk
+                    out["fps_d%d" % d_]["cpu_kind"] = "port: numpy loop of fps_gcn_cpu.py:137-146, %d picks" % npk
+                    out["kcenter_d%d" % d_]["cpu_ms_per_pick"] = _cpu_ms(lambda: O.kcenter(Fh, selh, npk)) / (npk + 4)
+                    out["kcenter_d%d" % d_]["cpu_kind"] = "port: sklearn-formula restatement, %d centres" % (npk + 4)
                 del Fh
             del F
         except Exception as e:
             out["fps_d%d" % d_] = {"error": repr(e)}
     return out
+
+
+def _sklearn_version():
+    try:
+        import sklearn
+        return sklearn.__version__
+    except Exception:
+        return "?"
+
+
+def _max_ms(torch, dist, dev, world, ms):
+    if world == 1:
+        return float(ms)
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def multi_gpu_metrics(torch, dist, D, dev, rank, world, flush):
+    """Strong-scaling lines of the sharded paths (total work fixed; N = 1 runs the same work on one GPU), each checked
+    bit for bit against the single-GPU result when N > 1.  Device time = CUDA events, max over ranks."""
+    from ssdr_al_b200 import dist as SD
+    from tools import synth
+    out = {"world": world}
+    ok = True
+    comm = None
+    peak, _ = measured_peak()
+    if world > 1:
+        from tools import multigpu_check as MC
+        comm = MC.make_comm(dev)
+        out["selection_transport"] = ("peer-memory mailboxes inside the persistent kernel (CUDA IPC over NVLink)"
+                                      if isinstance(comm, SD.PeerGroup) else "nccl 8-byte all-reduce per pick (fallback)")
+        chk_ok, chk = MC.run_checks(dev, rank, world, comm)
+        out["equality_checks"] = {"all_equal": chk_ok, "results": chk}
+        ok &= chk_ok
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+
+    def ev_pair():
+        return torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+    # ---- config 4: 500k x {32, 256} float32, row-sharded FPS and k-center ------------------------------------------
+    for d_, picks in ((32, 2000), (256, 1000)):
+        try:
+            g = torch.Generator(device=dev)
+            g.manual_seed(3)  # the same matrix on every rank
+            F = torch.randn((500_000, d_), generator=g, device=dev, dtype=torch.float32)
+            sel = torch.arange(500_000 - 16, 500_000, device=dev, dtype=torch.int64)
+            p2p = isinstance(comm, SD.PeerGroup)
+
+            def run_fps():
+                return D.fps(F, picks, 12345) if world == 1 else SD.fps_sharded(F, picks, 12345, comm)
+
+            def run_kc():
+                return D.kcenter(F, sel, picks) if world == 1 else SD.kcenter_sharded(F, sel, picks, comm)
+
+            for name, fn, steps, extra_b in (("fps", run_fps, picks - 1, 8), ("kcenter", run_kc, picks + 15, 16)):
+                if name == "kcenter" and world > 1 and not p2p:
+                    continue
+                fn()
+                ts = []
+                for _ in range(3):
+                    barrier()
+                    a, b = ev_pair()
+                    a.record()
+                    r = fn()
+                    b.record()
+                    torch.cuda.synchronize()
+                    ts.append(_max_ms(torch, dist, dev, world, a.elapsed_time(b)))
+                per = float(np.median(ts)) / steps
+                algo = 500_000 * (4 * d_ + extra_b)
+                e = {"rows": 500_000, "picks": picks, "us_per_pick": 1e3 * per, "picks_per_s": 1e3 / per,
+                     "algorithmic_gbs_all_gpus": algo / per / 1e6,
+                     "frac_of_hbm_peak_per_gpu": algo / per / 1e6 / peak / world}
+                if world > 1:
+                    single = D.fps(F, picks, 12345) if name == "fps" else D.kcenter(F, sel, picks)
+                    e["equal_to_single_gpu"] = bool(torch.equal(single, r))
+                    ok &= e["equal_to_single_gpu"]
+                    if p2p:  # per pick and rank: one 16-byte mailbox write to each peer (2 x 8-byte words, float32)
+                        e["nvlink_bytes_per_pick_per_rank"] = 16 * (world - 1)
+                out["%s_d%d" % (name, d_)] = e
+            del F
+        except Exception as e:  # recorded in the line; only a MISMATCH fails the run
+            out["fps_d%d_error" % d_] = repr(e)
+
+    # ---- config 3: one Semantic3D-scale scan.  subsample 0.06 (voxel-layer slabs) -> all-gather -> k=16 KNN ----------
+    try:
+        n_scan = int(os.environ.get("SSDR_BENCH_SCAN_POINTS", "80000000"))
+        xyz, rgb, lab = synth.scan_cloud(n_scan, 2, dev)  # replicated on every rank (seeded device generator)
+        lab2 = lab[:, None].contiguous()
+
+        def scan_once():
+            evs = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+            evs[0].record()
+            if world == 1:
+                sp, sf, sc = D.grid_subsample(xyz, rgb, lab2, 0.06)
+                evs[1].record()
+                evs[2].record()
+                idx = D.knn_batch(sp[None], sp[None], K)[0]
+                full, span = sp, (0, sp.shape[0])
+            else:
+                sp, sf, sc = SD.grid_subsample_sharded(xyz, rgb, lab2, 0.06, replicated=True)
+                evs[1].record()
+                full, span = SD.gather_rows(sp)       # the exchange step: every rank needs the whole support cloud
+                evs[2].record()
+                idx = D.knn_batch(full[None], sp[None], K)[0] if sp.shape[0] else torch.zeros((0, K), dtype=torch.int64, device=dev)
+            evs[3].record()
+            torch.cuda.synchronize()
+            t = [evs[i].elapsed_time(evs[i + 1]) for i in range(3)]
+            return t, (sp, sf, sc, idx, full, span)
+
+        scan_once()
+        runs = []
+        for _ in range(3):
+            flush.zero_()
+            barrier()
+            t, res = scan_once()
+            runs.append([_max_ms(torch, dist, dev, world, v) for v in t] + [_max_ms(torch, dist, dev, world, sum(t))])
+        med = np.median(np.array(runs), axis=0)
+        sp, sf, sc, idx, full, span = res
+        m_total = int(full.shape[0])
+        c3 = {"points": n_scan, "sampleDl": 0.06, "voxels": m_total, "subsample_ms": float(med[0]),
+              "gather_ms": float(med[1]), "knn_ms": float(med[2]), "total_ms": float(med[3]),
+              "subsample_mpts_per_s": n_scan / med[0] / 1e3, "knn_queries_per_s": m_total / med[2] * 1e3,
+              "pipeline_mpts_per_s": n_scan / med[3] / 1e3,
+              "subsample_algorithmic_gbs": (n_scan * 28 + m_total * 28) / med[0] / 1e6,
+              "input": "replicated on every rank (seeded on-device generator); slabs by balanced voxel layers along z",
+              "note": "the cell grid and the nanoflann-identical tree of the tie path are built on every rank over the "
+                      "WHOLE cloud (replicated work); only the query scan shards"}
+        if world > 1:  # full-size check: this rank's rows against its own single-GPU run of the whole scan
+            wp, wf, wc = D.grid_subsample(xyz, rgb, lab2, 0.06)
+            widx = D.knn_batch(wp[None], wp[None], K)[0]
+            b, e = span
+            same = (wp.shape[0] == m_total and torch.equal(wp[b:e], sp) and torch.equal(wf[b:e], sf)
+                    and torch.equal(wc[b:e], sc) and torch.equal(widx[b:e], idx) and torch.equal(wp, full))
+            c3["equal_to_single_gpu"] = bool(same)
+            ok &= bool(same)
+            del wp, wf, wc, widx
+        out["cfg3_scan"] = c3
+        del xyz, rgb, lab, lab2, sp, sf, sc, idx, full, res
+    except Exception as e:
+        out["cfg3_scan"] = {"error": repr(e)}
+
+    # ---- config 5: 272 rooms (per-room subsample 0.04 + k=16 KNN, rooms round-robin over the ranks), then ONE global
+    # selection over ~500k superpoint feature rows (D = 32, 10,000 picks = 2 %) --------------------------------------
+    try:
+        n_rooms = int(os.environ.get("SSDR_BENCH_ROOMS", "272"))
+        sizes = synth.room_sizes(n_rooms)
+        mine = SD.shard_items(n_rooms, world, rank)
+        room_ms = 0.0
+        raw = vox = 0
+        csum = torch.zeros(2, dtype=torch.int64, device=dev)
+        for i in mine:
+            p, f, c = synth.room_cloud_device(int(sizes[i]), 100 + i, dev)
+            c2 = c[:, None].contiguous()
+            a, b = ev_pair()
+            a.record()
+            sp, _, _ = D.grid_subsample(p, f, c2, 0.04)
+            idx = D.knn_batch(sp[None], sp[None], K)
+            b.record()
+            torch.cuda.synchronize()
+            room_ms += a.elapsed_time(b)
+            raw += int(sizes[i])
+            vox += int(sp.shape[0])
+            csum[0] += idx.sum()
+            csum[1] += sp.shape[0]
+            del p, f, c, c2, sp, idx
+        tot = torch.tensor([raw, vox], dtype=torch.int64, device=dev)
+        if world > 1:
+            dist.all_reduce(tot)
+            dist.all_reduce(csum)
+        room_ms = _max_ms(torch, dist, dev, world, room_ms)
+        g = torch.Generator(device=dev)
+        g.manual_seed(5)
+        F = torch.randn((500_000, 32), generator=g, device=dev, dtype=torch.float32)
+        picks = 10_000
+        fn = (lambda: D.fps(F, picks, 4242)) if world == 1 else (lambda: SD.fps_sharded(F, picks, 4242, comm))
+        fn()
+        barrier()
+        a, b = ev_pair()
+        a.record()
+        r = fn()
+        b.record()
+        torch.cuda.synchronize()
+        sel_ms = _max_ms(torch, dist, dev, world, a.elapsed_time(b))
+        c5 = {"rooms": n_rooms, "raw_points": int(tot[0]), "subsampled_points": int(tot[1]),
+              "rooms_ms": room_ms, "rooms_per_s": n_rooms / room_ms * 1e3, "raw_mpts_per_s": int(tot[0]) / room_ms / 1e3,
+              "knn_index_checksum": int(csum[0]), "selection_rows": 500_000, "selection_picks": picks,
+              "selection_ms": sel_ms, "picks_per_s": picks / sel_ms * 1e3, "round_ms": room_ms + sel_ms}
+        if world > 1:
+            c5["selection_equal_to_single_gpu"] = bool(torch.equal(r, D.fps(F, picks, 4242)))
+            ok &= c5["selection_equal_to_single_gpu"]
+        out["cfg5_round"] = c5
+    except Exception as e:
+        out["cfg5_round"] = {"error": repr(e)}
+    if comm is not None:
+        barrier()
+        comm.destroy()
+    return out, ok
 
 
 def main():
@@ -515,6 +803,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-extra", action="store_true", help="skip the secondary grid/FPS measurements")
+    ap.add_argument("--no-multi", action="store_true", help="skip the sharded-path section (configs 3, 4, 5)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

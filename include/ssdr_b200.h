@@ -191,6 +191,30 @@ int ssdr_chamfer_matrix_f64_dev(const double* d_points, const int64_t* d_offsets
  * All ranks receive identical picks. */
 int ssdr_fps_f32_sharded(const float* d_F, size_t N, size_t D, size_t row_begin, size_t row_end, int32_t first,
                          size_t n_samples, int32_t* d_out, void* nccl_comm, void* stream);
+/* The same row-sharded selection with the per-pick exchange FUSED into the persistent kernel: CTA 0 of every rank
+ * stores the rank's (distance, index) winner straight into every peer's mailbox over NVLink (peer memory mapped with
+ * CUDA IPC), every CTA of every rank polls its local copy -- one launch for all picks, no collective call per pick.
+ * Peer group life cycle (one process per GPU; `handles` = the world 64-byte handles in rank order, exchanged by the
+ * caller, e.g. with torch.distributed.all_gather):
+ *     ssdr_peer_group_create(world, rank, &g); ssdr_peer_group_export(g, h64); <all-gather h64>;
+ *     ssdr_peer_group_connect(g, handles); <barrier>; ... sharded calls ...; <barrier>; ssdr_peer_group_destroy(g);
+ * All ranks must issue the same sequence of sharded calls on a group.  FPS (farthest_features_sample) and k-center
+ * (kCenterGreedy) in float32 or float64; every rank receives identical picks, bit-equal to the single-GPU entry points.
+ * A rank whose peers do not answer within SSDR_PEER_TIMEOUT_MS (default 20000) fails with SSDR_ERR_CUDA instead of
+ * hanging.  max_ctas = 0 uses every SM (tests run several virtual ranks on one device with a smaller grid each,
+ * connected with ssdr_peer_group_connect_local).  These calls synchronise `stream` before returning. */
+#define SSDR_F32 0
+#define SSDR_F64 1
+int ssdr_peer_group_create(int world, int rank, void** group);
+int ssdr_peer_group_export(void* group, void* handle64 /* 64 bytes: cudaIpcMemHandle_t */);
+int ssdr_peer_group_connect(void* group, const void* handles /* world x 64 bytes */);
+int ssdr_peer_group_connect_local(void** groups, int world);
+int ssdr_peer_group_destroy(void* group);
+int ssdr_fps_sharded_p2p(int dtype, const void* d_F, size_t N, size_t D, size_t row_begin, size_t row_end, int32_t first,
+                         size_t n_samples, int32_t* d_out, void* group, void* stream, int max_ctas);
+int ssdr_kcenter_sharded_p2p(int dtype, const void* d_X, size_t N, size_t D, size_t row_begin, size_t row_end,
+                             const int64_t* d_selected, size_t n_sel, size_t n_pick, int64_t* d_out, void* group,
+                             void* stream, int max_ctas);
 /* NCCL bootstrap helpers so the host side can create the communicator without linking NCCL itself. */
 int ssdr_nccl_unique_id(void* id128 /* 128 bytes */);
 int ssdr_nccl_comm_init(void** comm, int nranks, const void* id128, int rank);

@@ -65,6 +65,13 @@ SIGNATURES = {
     "ssdr_superpoint_fps_f64": [vp, vp, sz, vp, C.c_int32, sz, vp],
     "ssdr_chamfer_matrix_f64_dev": [vp, vp, vp, sz, vp, vp],
     "ssdr_fps_f32_sharded": [vp, sz, sz, sz, sz, C.c_int32, sz, vp, vp, vp],
+    "ssdr_peer_group_create": [C.c_int, C.c_int, C.POINTER(vp)],
+    "ssdr_peer_group_export": [vp, vp],
+    "ssdr_peer_group_connect": [vp, vp],
+    "ssdr_peer_group_connect_local": [C.POINTER(vp), C.c_int],
+    "ssdr_peer_group_destroy": [vp],
+    "ssdr_fps_sharded_p2p": [C.c_int, vp, sz, sz, sz, sz, C.c_int32, sz, vp, vp, vp, C.c_int],
+    "ssdr_kcenter_sharded_p2p": [C.c_int, vp, sz, sz, sz, sz, vp, sz, sz, vp, vp, vp, C.c_int],
     "ssdr_nccl_unique_id": [vp],
     "ssdr_nccl_comm_init": [C.POINTER(vp), C.c_int, vp, C.c_int],
     "ssdr_nccl_comm_destroy": [vp],
@@ -122,14 +129,33 @@ class _PinnedBlock(object):
         self.__array_interface__ = {"shape": shape, "typestr": typestr, "data": (ptr, False), "version": 3}
 
     def __del__(self):
+        global _POOL_BYTES
         try:
-            _POOL.setdefault(self.nbytes, []).append(self.ptr)
+            if _POOL_BYTES + self.nbytes > _POOL_LIMIT:  # the pool is full: give the pages back to the OS
+                _lib.ssdr_host_free(vp(self.ptr))
+            else:
+                _POOL.setdefault(self.nbytes, []).append(self.ptr)
+                _POOL_BYTES += self.nbytes
         except Exception:  # interpreter shutdown
             pass
 
 
 _POOL = {}          # size class -> free pinned pointers
-_POOL_LIMIT = 1 << 30
+_POOL_BYTES = 0     # bytes parked in _POOL (blocks in use by live arrays are not counted)
+_POOL_LIMIT = int(os.environ.get("SSDR_PINNED_POOL_BYTES", 1 << 30))
+
+
+def pinned_pool_bytes():
+    return _POOL_BYTES
+
+
+def pinned_pool_trim():
+    """Release every parked pinned block (long-running data preparation can call this between scans)."""
+    global _POOL_BYTES
+    for cls, ptrs in list(_POOL.items()):
+        while ptrs:
+            lib().ssdr_host_free(vp(ptrs.pop()))
+    _POOL_BYTES = 0
 
 
 def pinned_empty(shape, dtype):
@@ -143,10 +169,18 @@ def pinned_empty(shape, dtype):
         nbytes *= v
     if nbytes == 0:
         return np.empty(shape, dtype)
-    cls = 1 << max(12, (nbytes - 1).bit_length())  # power-of-two size classes
+    global _POOL_BYTES
+    # size classes: powers of two up to 1 MiB, then multiples of 1/8 of the next lower power of two (<= 12.5 % slack
+    # instead of up to 100 % on large results)
+    if nbytes <= (1 << 20):
+        cls = 1 << max(12, (nbytes - 1).bit_length())
+    else:
+        step = 1 << ((nbytes - 1).bit_length() - 4)
+        cls = (nbytes + step - 1) // step * step
     free = _POOL.get(cls)
     if free:
         ptr = free.pop()
+        _POOL_BYTES -= cls
     else:
         p = vp()
         check(lib().ssdr_host_alloc(C.byref(p), cls))

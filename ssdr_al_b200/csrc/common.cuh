@@ -55,6 +55,8 @@ struct Ctx {
     cudaEvent_t ev_chunk[8] = {};   // one per result chunk in flight on the copy stream
     cudaEvent_t tev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};  // timing events (stats paths)
     DevBuf ws[WS_SLOTS];            // workspaces, addressed by the owning module
+    // A calling thread that exits gives its streams, events and workspaces back (loader thread pools come and go).
+    ~Ctx();
 };
 
 // Returns the calling thread's context for its current device (creating it on first use).

@@ -13,6 +13,8 @@
 //   C. nanoflann's own order differs from (distance, index) ONLY when the top-(K+1) holds equal or almost equal
 //      distances (tree-visit order decides ties, nanoflann.hpp:72-96,1317; pruning compares differently rounded
 //      sums).  Such rows are flagged by B and re-resolved by an exact replay of the nanoflann tree (kdtree.cuh).
+#include <atomic>
+#include <mutex>
 #include <vector>
 
 #include "common.cuh"
@@ -628,6 +630,7 @@ struct DevStats {
 };
 
 static float g_occupancy_scale = 0.3f;  // points per cell ~= scale * K (tunable: SSDR_KNN_OCCUPANCY)
+static bool g_probe_on = true;
 
 // Rows the tie path rewrote, compacted for a small second read-back (the bulk read-back of all rows runs on the copy
 // stream while the tie path works; the host then overwrites these rows).
@@ -751,23 +754,20 @@ static int run_dev(Ctx* c, cudaStream_t s, const float* d_pts, size_t B, size_t 
     SSDR_REQUIRE(K <= 64, SSDR_ERR_UNSUPPORTED, "K=%zu > 64 is not supported", K);
     SSDR_REQUIRE(B * N < 0x7FFFFFFFull && B * Q < 0x7FFFFFFFull, SSDR_ERR_UNSUPPORTED, "batch too large");
     if (B == 0 || Q == 0) return SSDR_OK;
-    static bool env_read = false;
-    if (!env_read) {
+    static std::once_flag env_once;  // the library is re-entrant per calling thread: read the knobs exactly once
+    std::call_once(env_once, [] {
         const char* e = getenv("SSDR_KNN_OCCUPANCY");
         if (e && atof(e) > 0) g_occupancy_scale = (float)atof(e);
-        env_read = true;
-    }
+        const char* pr = getenv("SSDR_KNN_PROBE");  // SSDR_KNN_PROBE=0 switches the occupancy probe off (A/B runs)
+        g_probe_on = !(pr && pr[0] == '0');
+    });
     float occupancy = g_occupancy_scale * (float)K;
     occupancy = occupancy < 0.6f ? 0.6f : (occupancy > 24.f ? 24.f : occupancy);
     // cells per item: for a cloud that fills its bbox h gives cells ~= N / occupancy (3x head-room for the +1 per axis);
     // a cloud of surfaces needs the same number of OCCUPIED cells inside a mostly empty bbox, hence up to 4 cells per
     // point when the occupancy probe runs (setup_item grows h until the grid fits, so the bound costs speed at worst,
     // never correctness)
-    static int probe_on = -1;  // SSDR_KNN_PROBE=0 switches the occupancy probe off (A/B measurements)
-    if (probe_on < 0) {
-        const char* e = getenv("SSDR_KNN_PROBE");
-        probe_on = (e && e[0] == '0') ? 0 : 1;
-    }
+    const bool probe_on = g_probe_on;
     // large clouds are probed on a strided sample (the cube counts only need occupancies well above one)
     const unsigned pstride = (unsigned)((N + PROBE_SAMPLE - 1) / PROBE_SAMPLE);
     const unsigned r2 = probe_on ? probe_resolution((unsigned)((N + pstride - 1) / pstride)) : 0u;
@@ -817,12 +817,12 @@ static int run_dev(Ctx* c, cudaStream_t s, const float* d_pts, size_t B, size_t 
         SSDR_CHECK_CUDA(cudaMemsetAsync(ctl, 0, 16 * 4, s));  // counters only: no cell grid
     } else if (small) {  // one CTA per item does the whole grid build
         SSDR_CHECK_CUDA(cudaMemsetAsync(ctl, 0, 16 * 4, s));
-        static bool attr_set_dev[64] = {};
-        bool& attr_set = attr_set_dev[c->device & 63];
-        if (!attr_set) {
+        static std::atomic<bool> attr_set_dev[64];  // per device; setting the attribute twice is harmless
+        std::atomic<bool>& attr_set = attr_set_dev[c->device & 63];
+        if (!attr_set.load(std::memory_order_acquire)) {
             SSDR_CHECK_CUDA(cudaFuncSetAttribute(small_grid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                  (int)(SG_MAX_CELLS * sizeof(unsigned))));
-            attr_set = true;
+            attr_set.store(true, std::memory_order_release);
         }
         const size_t sg_words = (r2 && cstride < PROBE_WORDS) ? (size_t)PROBE_WORDS : (size_t)cstride;
         small_grid_kernel<<<(unsigned)B, SG_THREADS, sg_words * sizeof(unsigned), s>>>(

@@ -42,6 +42,29 @@ void DevBuf::release() {
     p = nullptr;
     cap = 0;
 }
+Ctx::~Ctx() {
+    if (device < 0 || getpid() != g_init_pid) return;  // never initialised, or a fork()ed child that owns no CUDA state
+    int cur = -1;
+    if (cudaGetDevice(&cur) != cudaSuccess || cudaSetDevice(device) != cudaSuccess) {
+        cudaGetLastError();  // the runtime is already shutting down (process exit): nothing left to release
+        return;
+    }
+    if (stream) cudaStreamSynchronize(stream);
+    if (copy_stream) cudaStreamSynchronize(copy_stream);
+    for (int i = 0; i < WS_SLOTS; ++i) ws[i].release();
+    if (ev) cudaEventDestroy(ev);
+    if (ev_main) cudaEventDestroy(ev_main);
+    for (int i = 0; i < 8; ++i)
+        if (ev_chunk[i]) cudaEventDestroy(ev_chunk[i]);
+    for (int i = 0; i < 5; ++i)
+        if (tev[i]) cudaEventDestroy(tev[i]);
+    if (stream) cudaStreamDestroy(stream);
+    if (copy_stream) cudaStreamDestroy(copy_stream);
+    if (cur >= 0) cudaSetDevice(cur);
+    cudaGetLastError();
+    device = -1;
+}
+
 enum { MAX_DEV = 16 };
 static thread_local Ctx g_ctx[MAX_DEV];
 

@@ -38,7 +38,12 @@ def grid_subsample(points, features=None, classes=None, sampleDl=0.1, bbox=None,
     bbox: 6 floats (min xyz, max xyz) of the larger cloud these points belong to (default: their own min/max).
     slab: (axis, layer_lo, layer_hi) -- reduce only the voxel layers [lo, hi) along `axis` (multi-GPU ownership).
     return_keys: also return (keys uint64, counts int32) as numpy arrays."""
+    points = _grid_arg(points, torch.float32, "points", 3)
+    features = _grid_arg(features, torch.float32, "features")
+    classes = _grid_arg(classes, torch.int32, "classes")
     N = points.shape[0]
+    if (features is not None and features.shape[0] != N) or (classes is not None and classes.shape[0] != N):
+        raise ValueError("features / classes must have one row per point")
     fdim = features.shape[1] if features is not None else 0
     ldim = (1 if classes.dim() == 1 else classes.shape[1]) if classes is not None else 0
     M = C.c_size_t(0)
@@ -80,8 +85,25 @@ def grid_subsample(points, features=None, classes=None, sampleDl=0.1, bbox=None,
     return out_p, out_f, out_c
 
 
+def _grid_arg(t, dtype, name, width=None):
+    """The C ABI reads raw device memory: refuse anything that is not a contiguous CUDA tensor of the stated dtype
+    instead of reinterpreting its bytes (torch's default int64 labels, float64 points, strided views ...)."""
+    if t is None:
+        return None
+    if not (isinstance(t, torch.Tensor) and t.is_cuda):
+        raise TypeError("%s must be a CUDA tensor" % name)
+    if t.dtype != dtype:
+        raise TypeError("%s must be %s, got %s (convert explicitly: the library does not cast)" % (name, dtype, t.dtype))
+    if width is not None and (t.dim() != 2 or t.shape[1] != width):
+        raise ValueError("%s must have shape (N, %d)" % (name, width))
+    if width is None and t.dim() not in (1, 2):
+        raise ValueError("%s must be 1-D or 2-D" % name)
+    return t.contiguous()
+
+
 def grid_bbox(points):
     """(N,3) f32 cuda -> [minx, miny, minz, maxx, maxy, maxz] (python floats holding float32 values)."""
+    points = _grid_arg(points, torch.float32, "points", 3)
     box = (C.c_float * 6)()
     _lib.check(_lib.lib().ssdr_grid_bbox_dev(_p(points), points.shape[0], _stream(), box))
     return [float(v) for v in box]
@@ -89,6 +111,7 @@ def grid_bbox(points):
 
 def grid_point_layers(points, sampleDl, axis, bbox=None):
     """Voxel layer index of every point along `axis` (int32 cuda tensor) and the number of layers of the grid."""
+    points = _grid_arg(points, torch.float32, "points", 3)
     out = torch.empty(points.shape[0], dtype=torch.int32, device=points.device)
     box = (C.c_float * 6)(*[float(v) for v in bbox]) if bbox is not None else None
     n_layers = C.c_ulonglong(0)
@@ -122,6 +145,11 @@ def fps(F, n_samples, first, out=None):
 def kcenter(X, selected, n_pick, out=None):
     """X (N,D) f32/f64 cuda, selected int64 cuda -> (n_pick,) int64 cuda."""
     X = X.contiguous()
+    if selected.dtype != torch.int64 or not selected.is_cuda:
+        raise TypeError("selected must be an int64 CUDA tensor")
+    selected = selected.contiguous()
+    if selected.numel() and (int(selected.min()) < 0 or int(selected.max()) >= X.shape[0]):
+        raise ValueError("selected holds a row index outside [0, %d)" % X.shape[0])  # the host entry checks the same
     if out is None:
         out = torch.zeros(n_pick, dtype=torch.int64, device=X.device)
     fn = _lib.lib().ssdr_kcenter_f32_dev if X.dtype == torch.float32 else _lib.lib().ssdr_kcenter_f64_dev

@@ -72,19 +72,149 @@ class NcclComm(object):
             self.handle = None
 
 
-def fps_sharded(F, n_samples, first, comm, rows=None):
-    """Row-sharded FPS: F is the FULL (N, D) float32 cuda tensor on every rank; returns (n_samples,) int32 picks
-    (identical on all ranks)."""
+class PeerGroup(object):
+    """The ranks of one node whose persistent selection kernels exchange each pick through peer memory (NVLink):
+    every rank owns a small mailbox block, all blocks are mapped into every process with CUDA IPC (include/ssdr_b200.h,
+    "peer groups").  `local(world)` builds `world` virtual ranks inside ONE process (tests on a single GPU)."""
+
+    def __init__(self, handle, world, rank):
+        self.handle, self.world, self.rank = handle, world, rank
+
+    @classmethod
+    def from_torch(cls, device, group=None):
+        import torch
+        import torch.distributed as dist
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
+        L = _lib.lib()
+        h = C.c_void_p()
+        _lib.check(L.ssdr_peer_group_create(world, rank, C.byref(h)))
+        mine = np.zeros(64, np.uint8)
+        _lib.check(L.ssdr_peer_group_export(h, _lib.ptr(mine)))
+        cuda = dist.get_backend(group) == "nccl"
+        t = torch.from_numpy(mine)
+        t = t.to(device) if cuda else t
+        every = [torch.empty_like(t) for _ in range(world)]
+        dist.all_gather(every, t, group=group)
+        handles = np.ascontiguousarray(np.stack([e.cpu().numpy() for e in every]))
+        try:
+            _lib.check(L.ssdr_peer_group_connect(h, _lib.ptr(handles)))
+            ok = 1
+        except RuntimeError:
+            ok = 0
+        flag = torch.tensor([ok], dtype=torch.int32, device=device if cuda else "cpu")
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)  # also the barrier that orders creation before use
+        if int(flag.item()) == 0:
+            L.ssdr_peer_group_destroy(h)
+            return None
+        return cls(h, world, rank)
+
+    @classmethod
+    def local(cls, world):
+        L = _lib.lib()
+        hs = (C.c_void_p * world)()
+        for r in range(world):
+            h = C.c_void_p()
+            _lib.check(L.ssdr_peer_group_create(world, r, C.byref(h)))
+            hs[r] = h
+        _lib.check(L.ssdr_peer_group_connect_local(hs, world))
+        return [cls(C.c_void_p(hs[r]), world, r) for r in range(world)]
+
+    def destroy(self):
+        if self.handle:
+            _lib.lib().ssdr_peer_group_destroy(self.handle)
+            self.handle = None
+
+
+def _rows(N, rows, world, rank):
+    return rows if rows is not None else shard_range(N, world, rank)
+
+
+def fps_sharded(F, n_samples, first, comm, rows=None, max_ctas=0):
+    """Row-sharded FPS: F is the FULL (N, D) float32/float64 cuda tensor on every rank; returns (n_samples,) int32
+    picks, identical on all ranks and equal to the single-GPU picks.  `comm` is a PeerGroup (the per-pick exchange runs
+    inside the persistent kernel over NVLink peer memory) or an NcclComm (one launch + 8-byte all-reduce per pick;
+    float32 only)."""
     import torch
-    import torch.distributed as dist
     F = F.contiguous()
     N = F.shape[0]
-    begin, end = rows if rows is not None else shard_range(N, dist.get_world_size(), dist.get_rank())
     out = torch.zeros(n_samples, dtype=torch.int32, device=F.device)
     stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    if isinstance(comm, PeerGroup):
+        begin, end = _rows(N, rows, comm.world, comm.rank)
+        dt = 0 if F.dtype == torch.float32 else 1
+        _lib.check(_lib.lib().ssdr_fps_sharded_p2p(dt, C.c_void_p(F.data_ptr()), N, F.shape[1], begin, end, int(first),
+                                                   int(n_samples), C.c_void_p(out.data_ptr()), comm.handle, stream,
+                                                   int(max_ctas)))
+        return out
+    import torch.distributed as dist
+    begin, end = _rows(N, rows, dist.get_world_size(), dist.get_rank())
     _lib.check(_lib.lib().ssdr_fps_f32_sharded(C.c_void_p(F.data_ptr()), N, F.shape[1], begin, end, int(first),
                                                int(n_samples), C.c_void_p(out.data_ptr()), comm.handle, stream))
     return out
+
+
+def kcenter_sharded(X, selected, n_pick, comm, rows=None, max_ctas=0):
+    """Row-sharded k-center greedy (kCenterGreedy.select_batch_): X is the FULL (N, D) cuda tensor on every rank,
+    `selected` the already chosen rows (int64 cuda); returns (n_pick,) int64 picks, identical on all ranks."""
+    import torch
+    X = X.contiguous()
+    N = X.shape[0]
+    out = torch.zeros(n_pick, dtype=torch.int64, device=X.device)
+    stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    begin, end = _rows(N, rows, comm.world, comm.rank)
+    dt = 0 if X.dtype == torch.float32 else 1
+    sel = selected.contiguous() if selected is not None and selected.numel() else None
+    _lib.check(_lib.lib().ssdr_kcenter_sharded_p2p(dt, C.c_void_p(X.data_ptr()), N, X.shape[1], begin, end,
+                                                   C.c_void_p(sel.data_ptr()) if sel is not None else None,
+                                                   sel.numel() if sel is not None else 0, int(n_pick),
+                                                   C.c_void_p(out.data_ptr()), comm.handle, stream, int(max_ctas)))
+    return out
+
+
+def knn_sharded(pts, queries, K, group=None, gather=False, int32=False):
+    """k-NN of ONE cloud with all ranks: the support cloud `pts` (N,3) (and with it the cell grid built on the device)
+    is replicated on every rank, the queries (Q,3) are sharded by contiguous block -- the loop the reference
+    parallelises with OpenMP (knn_.cxx:57-58).  Returns (rows of this rank's block (q_end-q_begin, K), (q_begin, q_end)),
+    or with gather=True the full (Q, K) result on every rank (one all-gather of the index rows)."""
+    import torch
+    import torch.distributed as dist
+    from . import device as dev
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    Q = queries.shape[0]
+    b, e = shard_range(Q, world, rank)
+    if e > b:
+        mine = dev.knn_batch(pts[None], queries[None, b:e], K, int32=int32)[0]
+    else:
+        mine = torch.zeros((0, K), dtype=torch.int32 if int32 else torch.int64, device=pts.device)
+    if not gather:
+        return mine, (b, e)
+    spans = [shard_range(Q, world, r) for r in range(world)]
+    width = max(s[1] - s[0] for s in spans)  # equal-sized pieces for the collective (blocks differ by at most one row)
+    padded = torch.zeros((width, K), dtype=mine.dtype, device=pts.device)
+    padded[: e - b] = mine
+    every = torch.empty((world, width, K), dtype=mine.dtype, device=pts.device)
+    dist.all_gather_into_tensor(every, padded, group=group)
+    return torch.cat([every[r, : s[1] - s[0]] for r, s in enumerate(spans)]), (b, e)
+
+
+def gather_rows(rows, group=None):
+    """All-gather row blocks of different lengths (the slabs of a sharded subsampling) into the full array, rank
+    order == row order.  Returns (full (sum m_r, ...), (begin, end) of this rank's block)."""
+    import torch
+    import torch.distributed as dist
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    sizes = torch.zeros(world, dtype=torch.int64, device=rows.device)
+    sizes[rank] = rows.shape[0]
+    dist.all_reduce(sizes, group=group)
+    sizes = sizes.tolist()
+    width = max(max(sizes), 1)
+    padded = torch.zeros((width,) + tuple(rows.shape[1:]), dtype=rows.dtype, device=rows.device)
+    padded[: rows.shape[0]] = rows
+    every = torch.empty((world, width) + tuple(rows.shape[1:]), dtype=rows.dtype, device=rows.device)
+    dist.all_gather_into_tensor(every, padded, group=group)
+    full = torch.cat([every[r, : sizes[r]] for r in range(world)])
+    begin = sum(sizes[:rank])
+    return full, (begin, begin + sizes[rank])
 
 
 def balanced_slabs(layer_counts, world):

@@ -104,3 +104,86 @@ def test_kcenter_vs_oracle(S, oracle, N, D, dt):
     X = rng.standard_normal((N, D)).astype(dt)
     sel = np.arange(N - 100, N)
     assert np.array_equal(S.selection.kcenter(X, sel, 150), oracle.kcenter(X, sel, 150))
+
+
+# ---- row-sharded selection with the pick exchange fused into the persistent kernel (peer mailboxes) -----------------
+def _virtual_ranks(world, fn):
+    """Run fn(rank, group) on `world` threads: the virtual ranks of a peer group that lives in this one process and on
+    this one GPU (each rank launches its persistent kernel with sm_count // world CTAs on its own stream, so all of
+    them are resident together and talk through the same mailbox protocol real ranks use over NVLink)."""
+    import threading
+    import torch
+    from ssdr_al_b200 import dist as SD
+    groups = SD.PeerGroup.local(world)
+    res, err = [None] * world, []
+
+    def work(r):
+        try:
+            torch.cuda.set_device(0)
+            with torch.cuda.stream(torch.cuda.Stream()):
+                res[r] = fn(r, groups[r])
+                torch.cuda.current_stream().synchronize()
+        except Exception as e:  # noqa: BLE001
+            err.append((r, repr(e)))
+
+    ts = [threading.Thread(target=work, args=(r,)) for r in range(world)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    for g in groups:
+        g.destroy()
+    assert not err, err
+    return res
+
+
+@pytest.mark.parametrize("world", [2, 4])
+@pytest.mark.parametrize("N,D,dt,picks", [(60_001, 32, np.float32, 200), (20_000, 256, np.float32, 80),
+                                          (9_000, 129, np.float64, 60), (15_000, 64, np.float32, 70),
+                                          (7_003, 20, np.float32, 50)])
+def test_sharded_fps_virtual_ranks_equal_single_gpu(S, oracle, monkeypatch, world, N, D, dt, picks):
+    import torch
+    from ssdr_al_b200 import device as dev, dist as SD
+    monkeypatch.setenv("SSDR_PEER_TIMEOUT_MS", "4000")
+    rng = np.random.default_rng(N + D + world)
+    Fh = rng.standard_normal((N, D)).astype(dt)
+    Fh[N // 3:N // 3 + 50] = Fh[5]  # ties across shard boundaries: the lowest global row must win on every rank
+    F = torch.from_numpy(Fh).cuda()
+    want = dev.fps(F, picks, 11).cpu().numpy()
+    assert np.array_equal(want, oracle.fps(Fh, picks, 11))
+    sms = torch.cuda.get_device_properties(0).multi_processor_count
+    for rep in range(2):  # the second call continues the tag sequence of the first (no mailbox is ever cleared)
+        got = _virtual_ranks(world, lambda r, g: SD.fps_sharded(F, picks, 11, g, max_ctas=sms // world).cpu().numpy())
+        for r in range(world):
+            assert np.array_equal(got[r], want), (rep, r)
+
+
+@pytest.mark.parametrize("N,D,dt", [(30_000, 32, np.float32), (6_000, 129, np.float64)])
+def test_sharded_kcenter_virtual_ranks_equal_single_gpu(S, oracle, monkeypatch, N, D, dt):
+    import torch
+    from ssdr_al_b200 import device as dev, dist as SD
+    monkeypatch.setenv("SSDR_PEER_TIMEOUT_MS", "4000")
+    rng = np.random.default_rng(N)
+    Xh = rng.standard_normal((N, D)).astype(dt)
+    X = torch.from_numpy(Xh).cuda()
+    sel = torch.arange(N - 40, N, device="cuda", dtype=torch.int64)
+    want = dev.kcenter(X, sel, 90).cpu().numpy()
+    assert np.array_equal(want, oracle.kcenter(Xh, np.arange(N - 40, N), 90))
+    sms = torch.cuda.get_device_properties(0).multi_processor_count
+    got = _virtual_ranks(2, lambda r, g: SD.kcenter_sharded(X, sel, 90, g, max_ctas=sms // 2).cpu().numpy())
+    assert np.array_equal(got[0], want) and np.array_equal(got[1], want)
+
+
+def test_sharded_peer_timeout_is_an_error_not_a_hang(S, monkeypatch):
+    """A rank whose peer never shows up gives up after SSDR_PEER_TIMEOUT_MS with a RuntimeError."""
+    import torch
+    from ssdr_al_b200 import dist as SD
+    monkeypatch.setenv("SSDR_PEER_TIMEOUT_MS", "300")
+    F = torch.randn((5000, 32), device="cuda")
+    groups = SD.PeerGroup.local(2)
+    try:
+        with pytest.raises(RuntimeError, match="peer rank did not post"):
+            SD.fps_sharded(F, 10, 0, groups[0], max_ctas=8)
+    finally:
+        for g in groups:
+            g.destroy()
