@@ -223,9 +223,21 @@ def run_ours(args):
         # counted inside the library where the launches happen (memsets and torch's slicing copies not included)
         return sum(int(st["kernel_launches"]) for _, _, st in stats)
 
+    def gpu_pyramid_fused():
+        # the same ten queries through ONE C-ABI call (ssdr_knn_pyramid_dev): no host round trip between the levels
+        D.knn_pyramid(xyz0, RATIOS, K, neigh=outs16, up=outs1)
+
+    headline = gpu_pyramid if args.per_call else gpu_pyramid_fused
     for _ in range(max(args.warmup, 3)):
         gpu_pyramid()
+        headline()
     torch.cuda.synchronize()
+    _lib.check(_lib.lib().ssdr_knn_status(None))
+    # the fused call must return the rows of the ten separate calls, bit for bit
+    want16, want1 = [o.clone() for o in outs16], [o.clone() for o in outs1]
+    gpu_pyramid()
+    torch.cuda.synchronize()
+    pyramid_equal = all(torch.equal(a, b_) for a, b_ in zip(want16 + want1, outs16 + outs1))
 
     # one instrumented pass (untimed) for per-kernel timing, tie statistics and launch counts
     stats = []
@@ -233,6 +245,10 @@ def run_ours(args):
     gpu_pyramid(stats)
     torch.cuda.synchronize()
     launches_per_step = count_launches(stats)
+    if not args.per_call:
+        gpu_pyramid_fused()
+        torch.cuda.synchronize()
+        launches_per_step = int(_lib.lib().ssdr_knn_pyramid_launches())
     # dominant kernel, measured cold (L2 flushed) a few times
     dom_ms = []
     for _ in range(5):
@@ -251,7 +267,7 @@ def run_ours(args):
     for s in range(args.steps):
         flush.zero_()  # L2 flush between timed iterations (outside the event pair)
         ev[s][0].record()
-        gpu_pyramid()
+        headline()
         ev[s][1].record()
     torch.cuda.synchronize()
     if world > 1:
@@ -350,6 +366,9 @@ def run_ours(args):
                      "dist_evals_per_s": evals0 / (dom_ms_avg * 1e-3), "dist_evals_per_query": evals0 / q0,
                      "issue": ncu_issue("knn_query_kernel_level0")},
         "clocks": clocks,
+        "headline_call": ("ten ssdr_knn_batch_dev calls" if args.per_call else
+                          "one ssdr_knn_pyramid_dev call (all levels enqueued without a host round trip)"),
+        "pyramid_call_equals_per_call_results": bool(pyramid_equal),
         "knn_detail": {"tie_rows_per_step": int(tie_rows), "stage_ms": [
             {"call": kind, "level_points": LEVELS[li], "grid_build_ms": st["grid_build_ms"],
              "main_kernel_ms": st["main_kernel_ms"], "tie_path_ms": st["tie_path_ms"], "tree_build_ms": st["tree_build_ms"],
@@ -804,6 +823,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-extra", action="store_true", help="skip the secondary grid/FPS measurements")
     ap.add_argument("--no-multi", action="store_true", help="skip the sharded-path section (configs 3, 4, 5)")
+    ap.add_argument("--per-call", action="store_true", help="time the pyramid as ten knn_batch calls (round-1 headline)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

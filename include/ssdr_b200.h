@@ -93,6 +93,20 @@ int ssdr_knn_batch_dev(const float* d_points, size_t batch_size, size_t npts, co
 int ssdr_knn_batch_dev_i32(const float* d_points, size_t batch_size, size_t npts, const float* d_queries,
                            size_t nqueries, size_t K, int32_t* d_indices, void* stream, ssdr_knn_stats* stats);
 
+/* RandLA-Net's whole input pyramid in ONE call -- the loop of s3dis_dataset.py:164-177 / helper_tool.py:173-183, which
+ * the reference runs as 2 * n_levels knn_batch calls:  N_0 = npts, N_{l+1} = N_l / ratios[l]; level l+1 holds the first
+ * N_{l+1} points of every item of level l (`batch_xyz[:, :N // ratio, :]`);
+ *     d_neigh[l] (B, N_l, K) = knn_batch(level l, level l, K)      d_up[l] (B, N_l, 1) = knn_batch(level l+1, level l, 1)
+ * d_points (B, npts, 3) and the output arrays are device pointers; `ratios` and the two pointer tables are host arrays.
+ * Every level is enqueued on `stream` behind the previous one WITHOUT a host round trip (the exact tie path runs
+ * speculatively on the device; the nanoflann-identical trees of a level are built at most once for its two queries).
+ * The call returns as soon as the work is enqueued; ssdr_knn_status(stream) waits for the stream and reports (and
+ * clears) an error of the asynchronous tie path. */
+int ssdr_knn_pyramid_dev(const float* d_points, size_t batch_size, size_t npts, const int32_t* ratios, size_t n_levels,
+                         size_t K, int64_t* const* d_neigh, int64_t* const* d_up, void* stream);
+int ssdr_knn_status(void* stream);
+unsigned long long ssdr_knn_pyramid_launches(void); /* kernels launched by the calling thread's last pyramid call */
+
 /* Diagnostic only: the nanoflann-identical tree built on the device for one cloud (node arrays: 3*npts+64 entries). */
 int ssdr_knn_debug_tree(const float* points, size_t npts, uint32_t* vind_out, uint32_t* n_nodes_out, uint32_t* left,
                         uint32_t* right, int32_t* child1, int32_t* child2, int32_t* divfeat, float* divlow,

@@ -39,6 +39,9 @@ SIGNATURES = {
     "ssdr_knn_batch_strided": [vp, sz, sz, sz, sz, vp, sz, sz, sz, vp],
     "ssdr_knn_batch_dev": [vp, sz, sz, vp, sz, sz, vp, vp, C.POINTER(KnnStats)],
     "ssdr_knn_batch_dev_i32": [vp, sz, sz, vp, sz, sz, vp, vp, C.POINTER(KnnStats)],
+    "ssdr_knn_pyramid_dev": [vp, sz, sz, vp, sz, sz, vp, vp, vp],
+    "ssdr_knn_status": [vp],
+    "ssdr_knn_pyramid_launches": [],
     "ssdr_knn_debug_tree": [vp, sz, vp, vp, vp, vp, vp, vp, vp, vp, vp],
     "ssdr_knn_debug_build_timing": [vp, sz, sz, vp],
     "ssdr_grid_subsample": [vp, vp, vp, sz, sz, sz, C.c_float, C.c_int, C.POINTER(sz), C.POINTER(vp)],
@@ -76,7 +79,7 @@ SIGNATURES = {
     "ssdr_nccl_comm_init": [C.POINTER(vp), C.c_int, vp, C.c_int],
     "ssdr_nccl_comm_destroy": [vp],
 }
-_RESTYPE = {"ssdr_last_error": C.c_char_p}
+_RESTYPE = {"ssdr_last_error": C.c_char_p, "ssdr_knn_pyramid_launches": C.c_ulonglong}
 
 
 def lib():

@@ -59,8 +59,10 @@ def build(force=False, verbose=False):
         f.write("\n".join(log))
     if verbose:
         print("\n".join(log))
-    cmd = [nvcc, "-shared", "-o", OUT] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-ldl"]
+    tmp = OUT + ".tmp"  # link beside the target and rename: a reader never sees a half-written library
+    cmd = [nvcc, "-shared", "-o", tmp] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-ldl"]
     subprocess.check_call(cmd)
+    os.replace(tmp, OUT)
     return OUT
 
 

@@ -2,18 +2,27 @@
 //
 // Replaces grid_subsampling() (utils/cpp_wrappers/cpp_subsampling/grid_subsampling/grid_subsampling.cpp:5-106),
 // a single-threaded unordered_map loop, by a sort + segmented sequential reduce that reproduces the reference
-// bit for bit:
-//   1. min/max corners                         (cloud.cpp:27-67)                     -> minmax_kernel
-//   2. origin = floor(min * (1/dl)) * dl, nX, nY (grid_subsampling.cpp:27-31)        -> setup_kernel
-//   3. key = iX + nX*iY + nX*nY*iZ with i* = floor((p-origin)/dl) in IEEE fp32, true division
-//      (grid_subsampling.cpp:53-56)                                                  -> key_kernel
-//   4. STABLE LSD radix sort of (key, input index) over the significant key bits only -> prim::radix_sort_pairs
-//   5. segment heads -> exclusive scan -> voxel start offsets, M                     -> head_flag/voxel_start kernels
-//   6. one thread per voxel walks its points IN INPUT ORDER (the stable sort keeps ascending index inside a
-//      voxel), accumulating fp32 sums exactly like SampledData::update_* (grid_subsampling.h:42-79), then
-//      bary = sum * float(1.0/count), feat = sum / float(count) (grid_subsampling.cpp:87-95) and the label vote
-//      with libstdc++'s unordered_map iteration order as tie-break (grid_subsampling.cpp:97-102)  -> reduce_kernel
-//   7. optional (SSDR_GRID_ORDER_REFERENCE): rows permuted into the reference's libstdc++ hash-iteration order.
+// bit for bit.  TWO launches, no host round trip in between (the host reads the voxel count once, at the end):
+//
+//   sort_kernel   (persistent, cooperative, one CTA per SM; phases separated by a grid barrier)
+//     P0  min/max corners (cloud.cpp:27-67) -> origin = floor(min * (1/dl)) * dl, nX, nY (grid_subsampling.cpp:27-31)
+//     P1  key = iX + nX*iY + nX*nY*iZ with i* = floor((p-origin)/dl) in IEEE fp32, true division
+//         (grid_subsampling.cpp:53-56); points stream through shared memory as float4; slab members (multi-GPU) are
+//         compacted in input order; the digit histogram of the first radix pass is taken on the fly
+//     P2  STABLE LSD radix sort of (key, input index), 8 bits per pass, over the significant key bits only -- the
+//         number of passes is decided ON THE DEVICE from the largest key.  Per pass: per-CTA digit histogram, barrier,
+//         every CTA derives its digit offsets from the CTA-major histogram matrix, stable scatter of its contiguous
+//         chunk (warp match_any ranking keeps equal keys in input order), barrier
+//     P3  segment heads -> voxel start offsets, M
+//   reduce_kernel (M known only on the device: grid-stride over voxels)
+//         eight lanes per voxel: the lanes gather up to eight points of the voxel in parallel (index, xyz, features,
+//         label) into shared memory, then every lane owns ONE CHANNEL (x, y, z, feature j) and adds the staged values
+//         IN INPUT ORDER (the stable sort keeps ascending index inside a voxel) exactly like SampledData::update_*
+//         (grid_subsampling.h:42-79); bary = sum * float(1.0/count), feat = sum / float(count)
+//         (grid_subsampling.cpp:87-95); the label vote counts in a per-voxel shared-memory table that keeps
+//         first-occurrence order, ties resolved by libstdc++'s unordered_map iteration order
+//         (grid_subsampling.cpp:97-102)
+//   optional (SSDR_GRID_ORDER_REFERENCE): rows permuted into the reference's libstdc++ hash-iteration order.
 // Rows come out in ascending voxel-key order by default (SSDR_GRID_ORDER_KEY).
 #include "common.cuh"
 #include "primitives.cuh"
@@ -28,18 +37,60 @@ struct Meta {
     unsigned long long nX, nY, nZ;
     int key_bits;
     int error;  // 2: more than LABEL_CAP distinct labels in one voxel
-    unsigned long long max_key;  // largest key seen (key_kernel) -> number of radix bits worth sorting
+    unsigned long long max_key;  // largest key seen -> number of radix bits worth sorting
     unsigned long long n_sel;    // points taking part (all of them, or the ones inside the requested slab)
     unsigned long long M;
+    int cur;                     // which ping-pong pair holds the sorted (key, index) arrays
+    int pad;
 };
 
 enum { WS_META = 0, WS_PART = 1, WS_KEYS = 2, WS_KEYS2 = 3, WS_IDX = 4, WS_IDX2 = 5, WS_TEMP = 6, WS_STARTS = 7,
-       WS_IN_P = 9, WS_IN_F = 10, WS_IN_C = 11, WS_HASH = 12, WS_CMIN = 13, WS_SEL = 14, WS_RAW = 15 };
+       WS_IN_P = 9, WS_IN_F = 10, WS_IN_C = 11, WS_HASH = 12, WS_CMIN = 13, WS_SEL = 14, WS_RAW = 15, WS_CTL = 16 };
 
 constexpr int LABEL_CAP = 64;
 constexpr int MM_BLOCK = 256;
 
-// ---- 1. min / max ------------------------------------------------------------------------------------
+// float -> size_t the way x86-64 gcc does it for |v| < 2^63 (truncate to int64, reinterpret)
+__device__ __forceinline__ unsigned long long f2u64(float v) { return (unsigned long long)(long long)v; }
+
+static int bits_for_value(unsigned long long v) {  // radix bits needed to order values <= v
+    int b = 1;
+    while (b < 64 && (v >> b)) ++b;
+    return b;
+}
+__device__ __forceinline__ int dev_bits_for_value(unsigned long long v) { return v ? 64 - __clzll((long long)v) : 1; }
+
+struct Geo {
+    float mn[3], mx[3], origin[3];
+    float dl;
+    unsigned long long nX, nY, nZ;
+};
+// origin / grid size from the corners (grid_subsampling.cpp:27-31), the same IEEE operations as the reference
+__device__ __forceinline__ void geometry_from_corners(const float* mn, const float* mx, float dl, Geo* g) {
+    const float inv = __fdiv_rn(1.0f, dl);
+    for (int d = 0; d < 3; ++d) {
+        g->mn[d] = mn[d];
+        g->mx[d] = mx[d];
+        g->origin[d] = __fmul_rn(floorf(__fmul_rn(mn[d], inv)), dl);
+    }
+    g->dl = dl;
+    g->nX = f2u64(floorf(__fdiv_rn(__fsub_rn(mx[0], g->origin[0]), dl))) + 1ull;
+    g->nY = f2u64(floorf(__fdiv_rn(__fsub_rn(mx[1], g->origin[1]), dl))) + 1ull;
+    g->nZ = f2u64(floorf(__fdiv_rn(__fsub_rn(mx[2], g->origin[2]), dl))) + 1ull;
+}
+// Keys are computed in wrapping 64-bit arithmetic exactly like the reference's size_t expression, so even
+// degenerate inputs (a point rounding to one cell below the origin, overflowing nX*nY*nZ) group identically.
+__device__ __forceinline__ unsigned long long voxel_key(const Geo& g, float x, float y, float z) {
+    const unsigned long long iX = f2u64(floorf(__fdiv_rn(__fsub_rn(x, g.origin[0]), g.dl)));
+    const unsigned long long iY = f2u64(floorf(__fdiv_rn(__fsub_rn(y, g.origin[1]), g.dl)));
+    const unsigned long long iZ = f2u64(floorf(__fdiv_rn(__fsub_rn(z, g.origin[2]), g.dl)));
+    return iX + g.nX * iY + g.nX * g.nY * iZ;
+}
+__device__ __forceinline__ unsigned long long voxel_layer(const Geo& g, float v, int axis) {
+    return f2u64(floorf(__fdiv_rn(__fsub_rn(v, g.origin[axis]), g.dl)));
+}
+
+// ---- stand-alone min / max and geometry (helpers of the multi-GPU slab logic: bbox of a chunk, layer of each point) -
 __global__ void minmax_kernel(const float* __restrict__ pts, unsigned long long N, float* __restrict__ partials) {
     float mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
     const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
@@ -74,17 +125,6 @@ __global__ void minmax_kernel(const float* __restrict__ pts, unsigned long long 
         partials[blockIdx.x * 6 + threadIdx.x] = v;
     }
 }
-
-// float -> size_t the way x86-64 gcc does it for |v| < 2^63 (truncate to int64, reinterpret)
-__device__ __forceinline__ unsigned long long f2u64(float v) { return (unsigned long long)(long long)v; }
-
-static int bits_for_value(unsigned long long v) {  // radix bits needed to order values <= v
-    int b = 1;
-    while (b < 64 && (v >> b)) ++b;
-    return b;
-}
-
-// ---- 2. grid geometry ---------------------------------------------------------------------------------
 __global__ void setup_kernel(const float* __restrict__ partials, int nparts, float dl, Meta* meta) {
     // one warp per quantity (3 mins, 3 maxes): strided loads + shuffle reduction
     const int t = threadIdx.x, q = t >> 5, lane = t & 31;
@@ -104,74 +144,27 @@ __global__ void setup_kernel(const float* __restrict__ partials, int nparts, flo
     }
     __syncthreads();
     if (t == 0) {
+        Geo g;
+        geometry_from_corners(r, r + 3, dl, &g);
         Meta m;
-        const float inv = __fdiv_rn(1.0f, dl);
         for (int d = 0; d < 3; ++d) {
-            m.mn[d] = r[d];
-            m.mx[d] = r[3 + d];
-            m.origin[d] = __fmul_rn(floorf(__fmul_rn(r[d], inv)), dl);
+            m.mn[d] = g.mn[d];
+            m.mx[d] = g.mx[d];
+            m.origin[d] = g.origin[d];
         }
         m.dl = dl;
-        m.nX = f2u64(floorf(__fdiv_rn(__fsub_rn(m.mx[0], m.origin[0]), dl))) + 1ull;
-        m.nY = f2u64(floorf(__fdiv_rn(__fsub_rn(m.mx[1], m.origin[1]), dl))) + 1ull;
-        m.nZ = f2u64(floorf(__fdiv_rn(__fsub_rn(m.mx[2], m.origin[2]), dl))) + 1ull;
+        m.nX = g.nX;
+        m.nY = g.nY;
+        m.nZ = g.nZ;
         m.error = 0;
         m.key_bits = 64;
         m.max_key = 0;
         m.n_sel = 0;
         m.M = 0;
+        m.cur = 0;
+        m.pad = 0;
         *meta = m;
     }
-}
-
-// ---- 3. voxel keys --------------------------------------------------------------------------------------
-// Keys are computed in wrapping 64-bit arithmetic exactly like the reference's size_t expression, so even
-// degenerate inputs (a point rounding to one cell below the origin, overflowing nX*nY*nZ) group identically.
-__global__ void key_kernel(const float* __restrict__ pts, unsigned long long N, Meta* __restrict__ meta,
-                           unsigned long long* __restrict__ keys, unsigned* __restrict__ idx,
-                           const unsigned* __restrict__ sel /* nullable: slab members, meta->n_sel of them */) {
-    const unsigned long long j = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const unsigned long long n = sel ? meta->n_sel : N;
-    unsigned long long key = 0;
-    if (j < n) {
-        const unsigned long long i = sel ? sel[j] : j;
-        const float dl = meta->dl;
-        const unsigned long long iX = f2u64(floorf(__fdiv_rn(__fsub_rn(__ldg(pts + 3 * i + 0), meta->origin[0]), dl)));
-        const unsigned long long iY = f2u64(floorf(__fdiv_rn(__fsub_rn(__ldg(pts + 3 * i + 1), meta->origin[1]), dl)));
-        const unsigned long long iZ = f2u64(floorf(__fdiv_rn(__fsub_rn(__ldg(pts + 3 * i + 2), meta->origin[2]), dl)));
-        key = iX + meta->nX * iY + meta->nX * meta->nY * iZ;
-        keys[j] = key;
-        idx[j] = (unsigned)i;
-    }
-    unsigned long long mk = key;
-#pragma unroll
-    for (int m = 16; m > 0; m >>= 1) {
-        unsigned long long o = __shfl_xor_sync(0xffffffffu, mk, m);
-        mk = o > mk ? o : mk;
-    }
-    __shared__ unsigned long long smax[8];
-    if ((threadIdx.x & 31) == 0) smax[threadIdx.x >> 5] = mk;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        for (int w = 1; w < (int)(blockDim.x >> 5); ++w) mk = smax[w] > mk ? smax[w] : mk;
-        atomicMax(&meta->max_key, mk);
-    }
-}
-
-// ---- slabs: a rank of a multi-GPU job subsamples only the voxel layers [lo, hi) along one axis, with the grid
-// geometry of the WHOLE cloud, so every voxel is owned by exactly one rank and its value is bit-identical -----------
-__global__ void slab_flag_kernel(const float* __restrict__ pts, unsigned long long N, const Meta* __restrict__ meta,
-                                 int axis, unsigned long long lo, unsigned long long hi, unsigned* __restrict__ flags) {
-    const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= N) return;
-    const unsigned long long layer =
-        f2u64(floorf(__fdiv_rn(__fsub_rn(__ldg(pts + 3 * i + axis), meta->origin[axis]), meta->dl)));
-    flags[i] = (layer >= lo && layer < hi) ? 1u : 0u;
-}
-__global__ void slab_compact_kernel(const unsigned* __restrict__ flags, const unsigned* __restrict__ pos,
-                                    unsigned long long N, unsigned* __restrict__ sel) {
-    const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < N && flags[i]) sel[pos[i]] = (unsigned)i;
 }
 __global__ void point_layers_kernel(const float* __restrict__ pts, unsigned long long N,
                                     const Meta* __restrict__ meta, int axis, int* __restrict__ layers) {
@@ -186,27 +179,477 @@ __global__ void bbox_fill_kernel(float* partials, float a0, float a1, float a2, 
     partials[3] = b0; partials[4] = b1; partials[5] = b2;
 }
 
-// widen uint8 colours / labels on the device (exact in float32 / int32): the callers' arrays are uint8 and the
-// reference converts them on the host (wrapper.cpp:100-106); uploading the bytes is 4x less PCIe and no host pass
-__global__ void widen_u8_f32_kernel(const unsigned char* __restrict__ in, unsigned long long n, float* __restrict__ out) {
-    const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) out[i] = (float)in[i];
+// ---- the persistent sort kernel -------------------------------------------------------------------------------------
+constexpr int PA_THREADS = 1024;
+constexpr int PA_WARPS = PA_THREADS / 32;
+constexpr int BINS = 256;
+
+struct SortParams {
+    const float* pts;
+    unsigned long long N;
+    float dl;
+    int has_bbox;
+    float bbox[6];
+    int slab_axis;  // -1: the whole cloud takes part
+    unsigned long long slab_lo, slab_hi;
+    Meta* meta;
+    unsigned long long* keys[2];
+    unsigned* idx[2];
+    unsigned* hist;             // [G][BINS] CTA-major digit histograms of the current pass
+    float* partials;            // [G][6]
+    unsigned long long* pmax;   // [G] largest key per CTA
+    unsigned* cta_count;        // [G] slab members, later segment heads, per CTA
+    unsigned* starts;           // [N + 1] voxel start offsets
+    unsigned* barrier;          // monotonic arrival counter, zero at launch
+};
+
+__device__ __forceinline__ unsigned ld_acquire_gpu_u32(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];\n" : "=r"(v) : "l"(p) : "memory");
+    return v;
 }
-__global__ void widen_u8_i32_kernel(const unsigned char* __restrict__ in, unsigned long long n, int* __restrict__ out) {
-    const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) out[i] = (int)in[i];
+// All CTAs of the (cooperative, hence co-resident) grid meet here.  The counter only grows: barrier k is passed when it
+// reaches k * G.  __threadfence after the wait also drops stale L1 lines before the next phase reads other CTAs' data.
+__device__ __forceinline__ void grid_barrier(unsigned* counter, unsigned G, unsigned* target) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        *target += G;
+        __threadfence();
+        atomicAdd(counter, 1u);
+        while (ld_acquire_gpu_u32(counter) < *target) {
+        }
+        __threadfence();
+    }
+    __syncthreads();
 }
 
-// ---- 5. voxel segments of the sorted keys ---------------------------------------------------------------------
-__global__ void head_flag_kernel(const unsigned long long* __restrict__ keys, unsigned long long N,
-                                 unsigned* __restrict__ flags) {
-    const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < N) flags[i] = (i == 0 || keys[i] != keys[i - 1]) ? 1u : 0u;
+// exclusive scan of v over the 1024 threads of the CTA; *total = sum.  s_w: PA_WARPS + 1 words of shared memory.
+__device__ __forceinline__ unsigned block_excl_scan(unsigned v, unsigned* s_w, unsigned* total) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned n = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += n;
+    }
+    __syncthreads();  // s_w may still be read from a previous call
+    if (lane == 31) s_w[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        unsigned w = s_w[lane];
+        unsigned wi = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned n = __shfl_up_sync(0xffffffffu, wi, o);
+            if (lane >= o) wi += n;
+        }
+        s_w[lane] = wi - w;
+        if (lane == 31) s_w[PA_WARPS] = wi;
+    }
+    __syncthreads();
+    *total = s_w[PA_WARPS];
+    return s_w[warp] + inc - v;
 }
-__global__ void voxel_start_kernel(const unsigned* __restrict__ flags, const unsigned* __restrict__ vid,
-                                   unsigned long long N, unsigned* __restrict__ starts) {
-    const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < N && flags[i]) starts[vid[i]] = (unsigned)i;
+
+// One tile = PA_THREADS consecutive points staged through shared memory as float4 (coalesced 16-byte loads; the
+// 12-byte records are then read back with stride 3 words, which is conflict free).  base % 4 == 0 and pts 16-byte
+// aligned are guaranteed by the caller; otherwise the scalar path loads the three floats directly.
+__device__ __forceinline__ void load_xyz_tile(const float* __restrict__ pts, unsigned long long base, unsigned cnt,
+                                              bool aligned, float* s_xyz, float* x, float* y, float* z) {
+    const unsigned t = threadIdx.x;
+    if (aligned) {
+        __syncthreads();  // the previous tile has been consumed
+        const unsigned nfl = cnt * 3u, nv = nfl >> 2;
+        const float4* src = reinterpret_cast<const float4*>(pts + base * 3ull);
+        if (t < nv) reinterpret_cast<float4*>(s_xyz)[t] = __ldg(src + t);
+        if (t < (nfl & 3u)) s_xyz[(nv << 2) + t] = __ldg(pts + base * 3ull + (nv << 2) + t);
+        __syncthreads();
+        if (t < cnt) {
+            *x = s_xyz[3 * t];
+            *y = s_xyz[3 * t + 1];
+            *z = s_xyz[3 * t + 2];
+        }
+    } else if (t < cnt) {
+        const float* q = pts + (base + t) * 3ull;
+        *x = __ldg(q);
+        *y = __ldg(q + 1);
+        *z = __ldg(q + 2);
+    }
+}
+
+__global__ void __launch_bounds__(PA_THREADS, 1) sort_kernel(const SortParams p) {
+    __shared__ __align__(16) unsigned s_cnt[PA_WARPS][BINS];     // radix ranking counters (P2) ...
+    float* s_xyz = reinterpret_cast<float*>(&s_cnt[0][0]);       // ... and the float4 staging tile of P0 / P1
+    __shared__ unsigned s_base[BINS], s_tot[BINS], s_pre[BINS];
+    __shared__ unsigned s_w[PA_WARPS + 1];
+    __shared__ float s_red[6][PA_WARPS];
+    __shared__ unsigned long long s_red64[PA_WARPS];
+    __shared__ Geo s_geo;
+    __shared__ unsigned long long s_n, s_maxkey;
+    __shared__ unsigned s_bar_target;
+    const unsigned t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const unsigned G = gridDim.x, c = blockIdx.x;
+    if (t == 0) s_bar_target = 0;
+    const bool aligned = (reinterpret_cast<unsigned long long>(p.pts) & 15ull) == 0;
+    // contiguous chunk of all N points for this CTA (tile aligned)
+    const unsigned long long perN = (((p.N + G - 1) / G) + PA_THREADS - 1) / PA_THREADS * PA_THREADS;
+    const unsigned long long cb = min((unsigned long long)c * perN, p.N), ce = min(cb + perN, p.N);
+
+    // ---- P0: corners -> geometry (identical in every CTA)
+    if (!p.has_bbox) {
+        float mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
+        for (unsigned long long b = cb; b < ce; b += PA_THREADS) {
+            const unsigned cnt = (unsigned)min((unsigned long long)PA_THREADS, ce - b);
+            float x = 0.f, y = 0.f, z = 0.f;
+            load_xyz_tile(p.pts, b, cnt, aligned, s_xyz, &x, &y, &z);
+            if (t < cnt) {
+                mn[0] = x < mn[0] ? x : mn[0];
+                mx[0] = x > mx[0] ? x : mx[0];
+                mn[1] = y < mn[1] ? y : mn[1];
+                mx[1] = y > mx[1] ? y : mx[1];
+                mn[2] = z < mn[2] ? z : mn[2];
+                mx[2] = z > mx[2] ? z : mx[2];
+            }
+        }
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+#pragma unroll
+            for (int m = 16; m > 0; m >>= 1) {
+                mn[d] = fminf(mn[d], __shfl_xor_sync(0xffffffffu, mn[d], m));
+                mx[d] = fmaxf(mx[d], __shfl_xor_sync(0xffffffffu, mx[d], m));
+            }
+        }
+        if (lane == 0)
+            for (int d = 0; d < 3; ++d) {
+                s_red[d][warp] = mn[d];
+                s_red[3 + d][warp] = mx[d];
+            }
+        __syncthreads();
+        if (t < 6) {
+            float v = s_red[t][0];
+            for (int w = 1; w < PA_WARPS; ++w) v = t < 3 ? fminf(v, s_red[t][w]) : fmaxf(v, s_red[t][w]);
+            p.partials[c * 6 + t] = v;
+        }
+        grid_barrier(p.barrier, G, &s_bar_target);
+        if (warp < 6) {  // one warp per quantity
+            float v = warp < 3 ? INFINITY : -INFINITY;
+            for (unsigned b = lane; b < G; b += 32) {
+                const float o = __ldcg(p.partials + b * 6 + warp);
+                v = warp < 3 ? fminf(v, o) : fmaxf(v, o);
+            }
+#pragma unroll
+            for (int m = 16; m > 0; m >>= 1) {
+                const float o = __shfl_xor_sync(0xffffffffu, v, m);
+                v = warp < 3 ? fminf(v, o) : fmaxf(v, o);
+            }
+            if (lane == 0) s_red[warp][0] = v;
+        }
+        __syncthreads();
+    } else if (t < 6) {
+        s_red[t][0] = p.bbox[t];
+    }
+    __syncthreads();
+    if (t == 0) {
+        float mn[3] = {s_red[0][0], s_red[1][0], s_red[2][0]}, mx[3] = {s_red[3][0], s_red[4][0], s_red[5][0]};
+        geometry_from_corners(mn, mx, p.dl, &s_geo);
+    }
+    __syncthreads();
+    const Geo geo = s_geo;
+    const bool slab = p.slab_axis >= 0;
+
+    // ---- P1: keys (slab members compacted in input order), digit histogram of the first pass, largest key
+    unsigned long long member_base = cb;  // where this CTA's first (member) point goes
+    if (slab) {
+        unsigned mine = 0;
+        for (unsigned long long b = cb; b < ce; b += PA_THREADS) {
+            const unsigned cnt = (unsigned)min((unsigned long long)PA_THREADS, ce - b);
+            float x = 0.f, y = 0.f, z = 0.f;
+            load_xyz_tile(p.pts, b, cnt, aligned, s_xyz, &x, &y, &z);
+            if (t < cnt) {
+                const unsigned long long layer = voxel_layer(geo, p.slab_axis == 0 ? x : (p.slab_axis == 1 ? y : z), p.slab_axis);
+                mine += (layer >= p.slab_lo && layer < p.slab_hi) ? 1u : 0u;
+            }
+        }
+        unsigned tot;
+        block_excl_scan(mine, s_w, &tot);
+        if (t == 0) p.cta_count[c] = tot;
+        grid_barrier(p.barrier, G, &s_bar_target);
+        unsigned long long pre = 0, all = 0;
+        for (unsigned b = t; b < G; b += PA_THREADS) {
+            const unsigned v = __ldcg(p.cta_count + b);
+            all += v;
+            if (b < c) pre += v;
+        }
+        // G <= PA_THREADS on any real device: one value per thread, reduce the two sums through shared memory
+#pragma unroll
+        for (int m = 16; m > 0; m >>= 1) {
+            pre += __shfl_xor_sync(0xffffffffu, pre, m);
+            all += __shfl_xor_sync(0xffffffffu, all, m);
+        }
+        __syncthreads();
+        if (lane == 0) s_red64[warp] = pre;
+        __syncthreads();
+        if (t == 0) {
+            unsigned long long v = 0;
+            for (int w = 0; w < PA_WARPS; ++w) v += s_red64[w];
+            s_maxkey = v;  // borrowed: prefix
+        }
+        __syncthreads();
+        member_base = s_maxkey;
+        __syncthreads();
+        if (lane == 0) s_red64[warp] = all;
+        __syncthreads();
+        if (t == 0) {
+            unsigned long long v = 0;
+            for (int w = 0; w < PA_WARPS; ++w) v += s_red64[w];
+            s_n = v;
+        }
+        __syncthreads();
+    } else if (t == 0) {
+        s_n = p.N;
+    }
+    for (unsigned i = t; i < BINS; i += PA_THREADS) s_tot[i] = 0;  // first-pass histogram of this CTA's members
+    __syncthreads();
+    unsigned long long kmax = 0;
+    {
+        unsigned long long run = member_base;
+        for (unsigned long long b = cb; b < ce; b += PA_THREADS) {
+            const unsigned cnt = (unsigned)min((unsigned long long)PA_THREADS, ce - b);
+            float x = 0.f, y = 0.f, z = 0.f;
+            load_xyz_tile(p.pts, b, cnt, aligned, s_xyz, &x, &y, &z);
+            bool member = t < cnt;
+            unsigned long long key = 0;
+            if (member) {
+                key = voxel_key(geo, x, y, z);
+                if (slab) {
+                    const unsigned long long layer =
+                        voxel_layer(geo, p.slab_axis == 0 ? x : (p.slab_axis == 1 ? y : z), p.slab_axis);
+                    member = layer >= p.slab_lo && layer < p.slab_hi;
+                }
+            }
+            unsigned long long pos = b + t;
+            if (slab) {
+                unsigned tot;
+                const unsigned rank = block_excl_scan(member ? 1u : 0u, s_w, &tot);
+                pos = run + rank;
+                run += tot;
+            }
+            if (member) {
+                p.keys[0][pos] = key;
+                if (slab) p.idx[0][pos] = (unsigned)(b + t);
+                kmax = key > kmax ? key : kmax;
+            }
+            // warp-aggregated histogram of the low digit
+            const unsigned digit = member ? (unsigned)(key & (BINS - 1)) : BINS;
+            const unsigned peers = __match_any_sync(0xffffffffu, digit);
+            if (member && (peers & ((1u << lane) - 1u)) == 0) atomicAdd(&s_tot[digit], __popc(peers));
+        }
+    }
+#pragma unroll
+    for (int m = 16; m > 0; m >>= 1) {
+        const unsigned long long o = __shfl_xor_sync(0xffffffffu, kmax, m);
+        kmax = o > kmax ? o : kmax;
+    }
+    __syncthreads();
+    if (lane == 0) s_red64[warp] = kmax;
+    __syncthreads();
+    if (t == 0) {
+        unsigned long long v = 0;
+        for (int w = 0; w < PA_WARPS; ++w) v = s_red64[w] > v ? s_red64[w] : v;
+        p.pmax[c] = v;
+    }
+    for (unsigned i = t; i < BINS; i += PA_THREADS) p.hist[(size_t)c * BINS + i] = s_tot[i];
+    grid_barrier(p.barrier, G, &s_bar_target);
+    {
+        unsigned long long v = 0;
+        for (unsigned b = t; b < G; b += PA_THREADS) {
+            const unsigned long long o = __ldcg(p.pmax + b);
+            v = o > v ? o : v;
+        }
+#pragma unroll
+        for (int m = 16; m > 0; m >>= 1) {
+            const unsigned long long o = __shfl_xor_sync(0xffffffffu, v, m);
+            v = o > v ? o : v;
+        }
+        __syncthreads();
+        if (lane == 0) s_red64[warp] = v;
+        __syncthreads();
+        if (t == 0) {
+            unsigned long long m = 0;
+            for (int w = 0; w < PA_WARPS; ++w) m = s_red64[w] > m ? s_red64[w] : m;
+            s_maxkey = m;
+        }
+        __syncthreads();
+    }
+    const unsigned long long n = s_n;
+    const int key_bits = dev_bits_for_value(s_maxkey);
+    if (c == 0 && t == 0) {
+        Meta m;
+        for (int d = 0; d < 3; ++d) {
+            m.mn[d] = geo.mn[d];
+            m.mx[d] = geo.mx[d];
+            m.origin[d] = geo.origin[d];
+        }
+        m.dl = geo.dl;
+        m.nX = geo.nX;
+        m.nY = geo.nY;
+        m.nZ = geo.nZ;
+        m.key_bits = key_bits;
+        m.error = 0;
+        m.max_key = s_maxkey;
+        m.n_sel = n;
+        m.M = 0;
+        m.cur = 0;
+        m.pad = 0;
+        *p.meta = m;
+    }
+    if (n == 0) return;  // an empty slab (uniform decision: every CTA leaves)
+
+    // contiguous chunk of the n participating elements for this CTA
+    const unsigned long long per = (((n + G - 1) / G) + PA_THREADS - 1) / PA_THREADS * PA_THREADS;
+    const unsigned long long sb = min((unsigned long long)c * per, n), se = min(sb + per, n);
+
+    // ---- P2: LSD radix passes
+    int cur = 0;
+    for (int shift = 0; shift < key_bits; shift += 8) {
+        const unsigned long long* kin = p.keys[cur];
+        const unsigned* vin = p.idx[cur];
+        unsigned long long* kout = p.keys[cur ^ 1];
+        unsigned* vout = p.idx[cur ^ 1];
+        const bool implicit_idx = shift == 0 && !slab;  // the first pass of a whole cloud: value = position
+        const bool chunk_matches = shift == 0 && !slab; // the P1 histogram was taken over [cb, ce), which is [sb, se)
+        if (shift > 0 || !chunk_matches) {
+            // (slab: P1 counted the members of this CTA's POINT chunk, the sort chunks partition the compacted array)
+            for (unsigned i = t; i < BINS; i += PA_THREADS) s_tot[i] = 0;
+            __syncthreads();
+            for (unsigned long long b = sb; b < se; b += PA_THREADS) {
+                const bool in = b + t < se;
+                const unsigned digit = in ? (unsigned)(__ldcg(kin + b + t) >> shift) & (BINS - 1) : BINS;
+                const unsigned peers = __match_any_sync(0xffffffffu, digit);
+                if (in && (peers & ((1u << lane) - 1u)) == 0) atomicAdd(&s_tot[digit], __popc(peers));
+            }
+            __syncthreads();
+            for (unsigned i = t; i < BINS; i += PA_THREADS) p.hist[(size_t)c * BINS + i] = s_tot[i];
+            grid_barrier(p.barrier, G, &s_bar_target);
+        }
+        // digit offsets of this CTA: (sum over all digits below) + (same digit, CTAs before this one)
+        {
+            const unsigned d = t & (BINS - 1), part = t >> 8;  // 4 x 256 threads: each quarter sums a quarter of the CTAs
+            const unsigned q0 = part * ((G + 3) / 4), q1 = min(q0 + (G + 3) / 4, G);
+            unsigned pre = 0, all = 0;
+            for (unsigned b = q0; b < q1; ++b) {
+                const unsigned v = __ldcg(p.hist + (size_t)b * BINS + d);
+                all += v;
+                if (b < c) pre += v;
+            }
+            __syncthreads();
+            s_cnt[part][d] = pre;
+            s_cnt[4 + part][d] = all;
+            __syncthreads();
+            if (t < BINS) {
+                s_pre[t] = s_cnt[0][t] + s_cnt[1][t] + s_cnt[2][t] + s_cnt[3][t];
+                s_tot[t] = s_cnt[4][t] + s_cnt[5][t] + s_cnt[6][t] + s_cnt[7][t];
+            }
+            __syncthreads();
+            unsigned tot;
+            const unsigned ex = block_excl_scan(t < BINS ? s_tot[t] : 0u, s_w, &tot);
+            if (t < BINS) s_base[t] = ex + s_pre[t];
+            __syncthreads();
+        }
+        // stable scatter of the chunk, PA_THREADS consecutive elements per round
+        for (unsigned long long b = sb; b < se; b += PA_THREADS) {
+            for (unsigned i = t; i < PA_WARPS * BINS; i += PA_THREADS) (&s_cnt[0][0])[i] = 0;
+            __syncthreads();
+            const bool in = b + t < se;
+            unsigned long long key = 0;
+            unsigned val = 0, digit = BINS;
+            if (in) {
+                key = __ldcg(kin + b + t);
+                val = implicit_idx ? (unsigned)(b + t) : __ldcg(vin + b + t);
+                digit = (unsigned)(key >> shift) & (BINS - 1);
+            }
+            const unsigned peers = __match_any_sync(0xffffffffu, digit);
+            const unsigned rank_in_warp = __popc(peers & ((1u << lane) - 1u));
+            if (in && rank_in_warp == 0) s_cnt[warp][digit] = __popc(peers);
+            __syncthreads();
+            if (t < BINS) {
+                unsigned run = s_base[t];
+#pragma unroll 8
+                for (int w = 0; w < PA_WARPS; ++w) {
+                    const unsigned cnt = s_cnt[w][t];
+                    s_cnt[w][t] = run;
+                    run += cnt;
+                }
+                s_base[t] = run;
+            }
+            __syncthreads();
+            if (in) {
+                const unsigned pos = s_cnt[warp][digit] + rank_in_warp;
+                kout[pos] = key;
+                vout[pos] = val;
+            }
+            __syncthreads();
+        }
+        cur ^= 1;
+        grid_barrier(p.barrier, G, &s_bar_target);
+    }
+
+    // ---- P3: segment heads -> voxel starts
+    const unsigned long long* ks = p.keys[cur];
+    unsigned heads = 0;
+    for (unsigned long long b = sb; b < se; b += PA_THREADS) {
+        const unsigned long long i = b + t;
+        if (i < se) heads += (i == 0 || __ldcg(ks + i) != __ldcg(ks + i - 1)) ? 1u : 0u;
+    }
+    unsigned tot;
+    block_excl_scan(heads, s_w, &tot);
+    if (t == 0) p.cta_count[c] = tot;
+    grid_barrier(p.barrier, G, &s_bar_target);
+    {
+        unsigned long long pre = 0, all = 0;
+        for (unsigned b = t; b < G; b += PA_THREADS) {
+            const unsigned v = __ldcg(p.cta_count + b);
+            all += v;
+            if (b < c) pre += v;
+        }
+#pragma unroll
+        for (int m = 16; m > 0; m >>= 1) {
+            pre += __shfl_xor_sync(0xffffffffu, pre, m);
+            all += __shfl_xor_sync(0xffffffffu, all, m);
+        }
+        __syncthreads();
+        if (lane == 0) s_red64[warp] = pre;
+        __syncthreads();
+        if (t == 0) {
+            unsigned long long v = 0;
+            for (int w = 0; w < PA_WARPS; ++w) v += s_red64[w];
+            s_maxkey = v;  // borrowed: voxel id of this CTA's first head
+        }
+        __syncthreads();
+        if (lane == 0) s_red64[warp] = all;
+        __syncthreads();
+        if (t == 0) {
+            unsigned long long v = 0;
+            for (int w = 0; w < PA_WARPS; ++w) v += s_red64[w];
+            s_n = v;  // borrowed: M
+        }
+        __syncthreads();
+    }
+    unsigned long long vbase = s_maxkey;
+    const unsigned long long M = s_n;
+    for (unsigned long long b = sb; b < se; b += PA_THREADS) {
+        const unsigned long long i = b + t;
+        const bool head = i < se && (i == 0 || __ldcg(ks + i) != __ldcg(ks + i - 1));
+        unsigned tt;
+        const unsigned rank = block_excl_scan(head ? 1u : 0u, s_w, &tt);
+        if (head) p.starts[vbase + rank] = (unsigned)i;
+        vbase += tt;
+    }
+    if (c == 0 && t == 0) {
+        p.starts[M] = (unsigned)n;
+        p.meta->M = M;
+        p.meta->cur = cur;
+    }
 }
 
 // ---- label vote: libstdc++ unordered_map<int,int> iteration order (identity hash, unique keys) ----------
@@ -270,102 +713,174 @@ __device__ int label_first_in_iteration_order(const int* labels, const int* coun
     return labels[0];
 }
 
-// ---- 6. per-voxel sequential reduce -----------------------------------------------------------------------
-template <int FD>  // FD = compile-time feature width, -1 = generic (accumulate in the output row)
-__global__ void reduce_kernel(const float* __restrict__ pts, const float* __restrict__ feats,
-                              const int* __restrict__ cls, int fdim, int ldim, const unsigned long long* __restrict__ keys,
-                              const unsigned* __restrict__ idx, const unsigned* __restrict__ starts,
-                              unsigned long long N, unsigned long long M, float* __restrict__ out_p,
-                              float* __restrict__ out_f, int* __restrict__ out_c,
-                              unsigned long long* __restrict__ out_k, int* __restrict__ out_n, Meta* meta) {
-    const unsigned long long v = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (v >= M) return;
-    const unsigned long long s = starts[v];
-    const unsigned long long e = v + 1 < M ? (unsigned long long)starts[v + 1] : N;
-    float sx = 0.f, sy = 0.f, sz = 0.f;
-    float fs[FD > 0 ? FD : 1];
-#pragma unroll
-    for (int j = 0; j < (FD > 0 ? FD : 1); ++j) fs[j] = 0.f;
-    if (FD < 0)
-        for (int j = 0; j < fdim; ++j) out_f[v * fdim + j] = 0.f;
-    int labs[LABEL_CAP], cnts[LABEL_CAP];
-    int nl = 0;
+// ---- per-voxel sequential reduce: eight lanes per voxel --------------------------------------------------------------
+constexpr int RB_THREADS = 256;
+constexpr int RB_GROUPS = RB_THREADS / 8;
+constexpr int STAGE_STRIDE = 72;  // 8 points x (8 channels + 1 pad): stores (stride 9) and loads of the four groups of a warp are conflict free
+constexpr int MAX_CB = 4;         // channel blocks of 8 held in registers per walk over a voxel (32 channels)
+
+struct ReduceParams {
+    const float* pts;
+    const void* feats;  // float32 or uint8 rows
+    const void* cls;    // int32 or uint8 rows
+    int feat_u8, cls_u8;
+    int fdim, ldim;
+    const unsigned long long* keys[2];
+    const unsigned* idx[2];
+    const unsigned* starts;
+    Meta* meta;
+    float* out_p;
+    float* out_f;
+    int* out_c;
+    unsigned long long* out_k;
+    int* out_n;
+};
+
+__device__ __forceinline__ float load_feat(const ReduceParams& p, unsigned long long row, int j) {
+    const unsigned long long o = row * (unsigned long long)p.fdim + j;
+    return p.feat_u8 ? (float)__ldg(reinterpret_cast<const unsigned char*>(p.feats) + o)
+                     : __ldg(reinterpret_cast<const float*>(p.feats) + o);
+}
+__device__ __forceinline__ int load_label(const ReduceParams& p, unsigned long long row, int col) {
+    const unsigned long long o = row * (unsigned long long)p.ldim + col;
+    return p.cls_u8 ? (int)__ldg(reinterpret_cast<const unsigned char*>(p.cls) + o)
+                    : __ldg(reinterpret_cast<const int*>(p.cls) + o);
+}
+
+// The label table of one voxel (first-occurrence order, like the reference's unordered_map insertions); every lane of
+// the group calls this with the same arguments.  Returns false on overflow.
+__device__ __forceinline__ bool table_add(int* labs, int* cnts, int* nl, int label, int weight, unsigned gmask, int gshift,
+                                          int l) {
+    int found = -1;
+    for (int q0 = 0; q0 < *nl && found < 0; q0 += 8) {
+        const int q = q0 + l;
+        const bool hit = q < *nl && labs[q] == label;
+        const unsigned b = (__ballot_sync(gmask, hit) >> gshift) & 0xFFu;
+        if (b) found = q0 + __ffs((int)b) - 1;
+    }
+    bool ok = true;
+    if (found >= 0) {
+        if (l == 0) cnts[found] += weight;
+    } else if (*nl < LABEL_CAP) {
+        if (l == 0) {
+            labs[*nl] = label;
+            cnts[*nl] = weight;
+        }
+        *nl += 1;
+    } else {
+        ok = false;
+    }
+    __syncwarp(gmask);
+    return ok;
+}
+
+__global__ void __launch_bounds__(RB_THREADS) reduce_kernel(const ReduceParams p) {
+    __shared__ float s_stage[RB_GROUPS][STAGE_STRIDE];
+    __shared__ int s_labs[RB_GROUPS][LABEL_CAP], s_cnts[RB_GROUPS][LABEL_CAP];
+    const unsigned long long M = p.meta->M;
+    const int cur = p.meta->cur;
+    const unsigned long long* keys = p.keys[cur];
+    const unsigned* idx = p.idx[cur];
+    const int tid = threadIdx.x, g = tid >> 3, l = tid & 7, lane = tid & 31;
+    const int gshift = (lane >> 3) * 8;
+    const unsigned gmask = 0xFFu << gshift;
+    float* stage = s_stage[g];
+    int* labs = s_labs[g];
+    int* cnts = s_cnts[g];
+    const int CH = 3 + p.fdim;
     bool overflow = false;
-    for (unsigned long long i = s; i < e; ++i) {
-        const unsigned long long p = idx[i];
-        sx = __fadd_rn(sx, __ldg(pts + 3 * p + 0));
-        sy = __fadd_rn(sy, __ldg(pts + 3 * p + 1));
-        sz = __fadd_rn(sz, __ldg(pts + 3 * p + 2));
-        if (FD > 0) {
+    const unsigned long long ngroups = (unsigned long long)gridDim.x * RB_GROUPS;
+    for (unsigned long long v = (unsigned long long)blockIdx.x * RB_GROUPS + g; v < M; v += ngroups) {
+        const unsigned long long s = p.starts[v], e = p.starts[v + 1];
+        const unsigned cnt = (unsigned)(e - s);
+        const float a = (float)(1.0 / (double)cnt);  // grid_subsampling.cpp:87: double reciprocal narrowed to float
+        const float cf = (float)cnt;
+        // walks over the voxel: 32 channels per walk (one walk for every reference caller: xyz + rgb)
+        for (int ch0 = 0; ch0 < CH; ch0 += 8 * MAX_CB) {
+            float acc[MAX_CB];
 #pragma unroll
-            for (int j = 0; j < (FD > 0 ? FD : 1); ++j) fs[j] = __fadd_rn(fs[j], __ldg(feats + p * FD + j));
-        } else if (FD < 0) {
-            for (int j = 0; j < fdim; ++j)
-                out_f[v * fdim + j] = __fadd_rn(out_f[v * fdim + j], __ldg(feats + p * fdim + j));
-        }
-        if (ldim >= 1) {  // first label column in the same pass
-            const int lab = __ldg(cls + p * ldim);
-            int q = 0;
-            while (q < nl && labs[q] != lab) ++q;
-            if (q == nl) {
-                if (nl < LABEL_CAP) {
-                    labs[nl] = lab;
-                    cnts[nl] = 0;
-                    ++nl;
-                } else {
-                    overflow = true;
-                    q = 0;
-                }
-            }
-            cnts[q] += 1;
-        }
-    }
-    const int count = (int)(e - s);
-    const float a = (float)(1.0 / (double)count);  // grid_subsampling.cpp:87: double reciprocal narrowed to float
-    out_p[3 * v + 0] = __fmul_rn(sx, a);
-    out_p[3 * v + 1] = __fmul_rn(sy, a);
-    out_p[3 * v + 2] = __fmul_rn(sz, a);
-    const float cf = (float)count;
-    if (FD > 0) {
+            for (int cb = 0; cb < MAX_CB; ++cb) acc[cb] = 0.f;
+            int nl = 0;
+            const bool vote = ch0 == 0 && p.ldim >= 1;
+            for (unsigned c0 = 0; c0 < cnt; c0 += 8) {
+                const int m = (int)min(8u, cnt - c0);
+                const unsigned long long row = l < m ? (unsigned long long)idx[s + c0 + l] : 0ull;
 #pragma unroll
-        for (int j = 0; j < (FD > 0 ? FD : 1); ++j) out_f[v * FD + j] = __fdiv_rn(fs[j], cf);
-    } else if (FD < 0) {
-        for (int j = 0; j < fdim; ++j) out_f[v * fdim + j] = __fdiv_rn(out_f[v * fdim + j], cf);
-    }
-    for (int col = 0; col < ldim; ++col) {
-        if (col > 0) {  // further label columns: one more walk each (rare: ldim is 1 for every reference caller)
-            nl = 0;
-            for (unsigned long long i = s; i < e; ++i) {
-                const int lab = __ldg(cls + (unsigned long long)idx[i] * ldim + col);
-                int q = 0;
-                while (q < nl && labs[q] != lab) ++q;
-                if (q == nl) {
-                    if (nl < LABEL_CAP) {
-                        labs[nl] = lab;
-                        cnts[nl] = 0;
-                        ++nl;
-                    } else {
-                        overflow = true;
-                        q = 0;
+                for (int cb = 0; cb < MAX_CB; ++cb) {
+                    const int cbase = ch0 + 8 * cb;
+                    if (cbase < CH) {
+                        if (l < m) {  // this lane stages the (up to) eight channels of ITS point
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) {
+                                const int ch = cbase + j;
+                                if (ch < CH) stage[l * 9 + j] = ch < 3 ? __ldg(p.pts + 3ull * row + ch) : load_feat(p, row, ch - 3);
+                            }
+                        }
+                        __syncwarp(gmask);
+                        if (cbase + l < CH) {  // this lane owns channel cbase + l: add the points in input order
+#pragma unroll
+                            for (int t = 0; t < 8; ++t)
+                                if (t < m) acc[cb] = __fadd_rn(acc[cb], stage[t * 9 + l]);
+                        }
+                        __syncwarp(gmask);
                     }
                 }
-                cnts[q] += 1;
+                if (vote) {
+                    const int lab = l < m ? load_label(p, row, 0) : 0;
+                    const int first = __shfl_sync(gmask, lab, gshift);
+                    const bool same = l >= m || lab == first;
+                    if (((__ballot_sync(gmask, same) >> gshift) & 0xFFu) == 0xFFu) {
+                        overflow |= !table_add(labs, cnts, &nl, first, m, gmask, gshift, l);
+                    } else {
+                        for (int t = 0; t < m; ++t)
+                            overflow |= !table_add(labs, cnts, &nl, __shfl_sync(gmask, lab, gshift + t), 1, gmask, gshift, l);
+                    }
+                }
+            }
+#pragma unroll
+            for (int cb = 0; cb < MAX_CB; ++cb) {
+                const int ch = ch0 + 8 * cb + l;
+                if (ch < CH) {
+                    if (ch < 3) p.out_p[3ull * v + ch] = __fmul_rn(acc[cb], a);
+                    else p.out_f[v * (unsigned long long)p.fdim + (ch - 3)] = __fdiv_rn(acc[cb], cf);
+                }
+            }
+            if (vote) {
+                for (int col = 0;;) {
+                    // winner of the table: largest count, ties by the reference's hash-iteration order
+                    int best = -1;
+                    for (int q = l; q < nl; q += 8) best = max(best, cnts[q]);
+#pragma unroll
+                    for (int mm = 1; mm < 8; mm <<= 1) best = max(best, __shfl_xor_sync(gmask, best, mm));
+                    int nbest = 0, arg = -1;
+                    for (int q0 = 0; q0 < nl; q0 += 8) {
+                        const int q = q0 + l;
+                        const unsigned b = (__ballot_sync(gmask, q < nl && cnts[q] == best) >> gshift) & 0xFFu;
+                        if (b && arg < 0) arg = q0 + __ffs((int)b) - 1;
+                        nbest += __popc(b);
+                    }
+                    if (l == 0)
+                        p.out_c[v * (unsigned long long)p.ldim + col] =
+                            nbest == 1 ? labs[arg] : label_first_in_iteration_order(labs, cnts, nl, best);
+                    __syncwarp(gmask);
+                    if (++col >= p.ldim) break;
+                    // further label columns: one more walk each (rare: ldim is 1 for every reference caller)
+                    nl = 0;
+                    for (unsigned c0 = 0; c0 < cnt; c0 += 8) {
+                        const int m = (int)min(8u, cnt - c0);
+                        const int lab = l < m ? load_label(p, (unsigned long long)idx[s + c0 + l], col) : 0;
+                        for (int t = 0; t < m; ++t)
+                            overflow |= !table_add(labs, cnts, &nl, __shfl_sync(gmask, lab, gshift + t), 1, gmask, gshift, l);
+                    }
+                }
             }
         }
-        int best = -1, nbest = 0, arg = 0;
-        for (int q = 0; q < nl; ++q) {
-            if (cnts[q] > best) {
-                best = cnts[q];
-                nbest = 1;
-                arg = q;
-            } else if (cnts[q] == best)
-                ++nbest;
+        if (l == 0) {
+            p.out_k[v] = keys[s];
+            p.out_n[v] = (int)cnt;
         }
-        out_c[v * ldim + col] = nbest == 1 ? labs[arg] : label_first_in_iteration_order(labs, cnts, nl, best);
     }
-    if (overflow) meta->error = 2;
-    out_k[v] = keys[s];
-    out_n[v] = count;
+    if (overflow) p.meta->error = 2;
 }
 
 // ---- 7. reference row order: libstdc++ unordered_map<size_t,...> iteration order, epoch by epoch ----------------
@@ -444,8 +959,6 @@ static void free_handle(Handle* h) {  // stream-ordered pool: no device-wide syn
     if (h->d_n) cudaFreeAsync(h->d_n, h->stream);
     delete h;
 }
-
-static int bits_for_value(unsigned long long v);
 
 // Rows are in ascending-key order in the handle; permute them into the reference's hash-iteration order.
 // Reuses the sort workspaces (stream ordered after reduce_kernel): WS_KEYS/WS_KEYS2 (u64), WS_IDX/WS_IDX2 (u32).
@@ -547,88 +1060,68 @@ struct Slab {
     unsigned long long lo = 0, hi = 0;
 };
 
-static int run_dev(Ctx* c, cudaStream_t s, const float* d_p, const float* d_f, const int* d_c, size_t N, size_t fdim,
-                   size_t ldim, float dl, int order, size_t* M_out, void** handle, Slab slab = Slab(),
-                   const float* bbox = nullptr) {
+struct Inputs {
+    const float* p = nullptr;
+    const void* f = nullptr;  // float32 rows, or uint8 rows when f_u8
+    const void* c = nullptr;  // int32 rows, or uint8 rows when c_u8
+    bool f_u8 = false, c_u8 = false;
+};
+
+static int run_dev(Ctx* c, cudaStream_t s, const Inputs& in, size_t N, size_t fdim, size_t ldim, float dl, int order,
+                   size_t* M_out, void** handle, Slab slab = Slab(), const float* bbox = nullptr) {
     typedef unsigned long long KeyT;
-    SSDR_REQUIRE(d_p && M_out && handle, SSDR_ERR_INVALID, "NULL pointer");
+    SSDR_REQUIRE(in.p && M_out && handle, SSDR_ERR_INVALID, "NULL pointer");
     SSDR_REQUIRE(N >= 1, SSDR_ERR_EMPTY, "Error");
     SSDR_REQUIRE(N < 0x7FFFFFFFull, SSDR_ERR_UNSUPPORTED, "N=%zu exceeds 2^31-2 points per call", N);
     SSDR_REQUIRE(order == SSDR_GRID_ORDER_KEY || order == SSDR_GRID_ORDER_REFERENCE, SSDR_ERR_INVALID,
                  "order must be SSDR_GRID_ORDER_KEY or SSDR_GRID_ORDER_REFERENCE");
     SSDR_REQUIRE(dl > 0.0f, SSDR_ERR_INVALID, "sampleDl must be positive");
-    if (!d_f) fdim = 0;
-    if (!d_c) ldim = 0;
+    if (!in.f) fdim = 0;
+    if (!in.c) ldim = 0;
+    if (bbox)
+        for (int d = 0; d < 3; ++d)
+            SSDR_REQUIRE(bbox[d] <= bbox[3 + d], SSDR_ERR_INVALID, "bbox min exceeds max (or NaN) on axis %d", d);
+    if (slab.axis >= 0) SSDR_REQUIRE(slab.axis < 3 && slab.lo <= slab.hi, SSDR_ERR_INVALID, "bad slab");
+    const int G = c->sm_count;
     SSDR_TRY(c->ws[WS_META].reserve(sizeof(Meta)));
     SSDR_TRY(c->ws[WS_KEYS].reserve(N * sizeof(KeyT)));
     SSDR_TRY(c->ws[WS_KEYS2].reserve(N * sizeof(KeyT)));
     SSDR_TRY(c->ws[WS_IDX].reserve(N * sizeof(unsigned)));
     SSDR_TRY(c->ws[WS_IDX2].reserve(N * sizeof(unsigned)));
     SSDR_TRY(c->ws[WS_STARTS].reserve((N + 1) * sizeof(unsigned)));
+    // control block: barrier counter | per-CTA partials, largest keys, counts | histogram matrix
+    const size_t ctl_bytes = 256 + (size_t)G * (6 * sizeof(float) + sizeof(KeyT) + sizeof(unsigned)) + 256 +
+                             (size_t)G * BINS * sizeof(unsigned);
+    SSDR_TRY(c->ws[WS_CTL].reserve(ctl_bytes));
+    char* ctl = c->ws[WS_CTL].as<char>();
     Meta* meta = c->ws[WS_META].as<Meta>();
-    KeyT* keys = c->ws[WS_KEYS].as<KeyT>();
-    KeyT* keys2 = c->ws[WS_KEYS2].as<KeyT>();
-    unsigned* idx = c->ws[WS_IDX].as<unsigned>();
-    unsigned* idx2 = c->ws[WS_IDX2].as<unsigned>();
-    unsigned* starts = c->ws[WS_STARTS].as<unsigned>();
 
-    SSDR_TRY(c->ws[WS_TEMP].reserve((prim::rs_scratch_words(N) + prim::scan_scratch_words(N) + 8) * sizeof(unsigned)));
-    unsigned* scratch = c->ws[WS_TEMP].as<unsigned>();
-    SSDR_CHECK_CUDA(cudaMemsetAsync(scratch, 0, (prim::rs_scratch_words(N) + prim::scan_scratch_words(N) + 8) * sizeof(unsigned), s));
-    SSDR_TRY(geometry(c, s, d_p, N, dl, bbox, meta));
-    const unsigned* sel = nullptr;
-    if (slab.axis >= 0) {  // members of the slab, in input order (stable compaction)
-        SSDR_REQUIRE(slab.axis < 3 && slab.lo <= slab.hi, SSDR_ERR_INVALID, "bad slab");
-        SSDR_TRY(c->ws[WS_SEL].reserve(N * sizeof(unsigned)));
-        unsigned* flags = reinterpret_cast<unsigned*>(keys2);  // free until the sort
-        unsigned* pos = flags + N;
-        const unsigned nb0 = (unsigned)((N + 255) / 256);
-        slab_flag_kernel<<<nb0, 256, 0, s>>>(d_p, N, meta, slab.axis, slab.lo, slab.hi, flags);
-        SSDR_TRY(prim::exclusive_scan_u32(flags, pos, N, scratch + prim::rs_scratch_words(N),
-                                          reinterpret_cast<unsigned*>(&meta->n_sel), s));
-        slab_compact_kernel<<<nb0, 256, 0, s>>>(flags, pos, N, c->ws[WS_SEL].as<unsigned>());
-        sel = c->ws[WS_SEL].as<unsigned>();
-    }
-    key_kernel<<<(unsigned)((N + 255) / 256), 256, 0, s>>>(d_p, N, meta, keys, idx, sel);
-    SSDR_CHECK_CUDA(cudaGetLastError());
-    Meta hm;
-    SSDR_TRY(d2h_sync(c, &hm, meta, sizeof(Meta), s));  // sync 1: how many key bits are worth sorting (and slab size)
-    const int key_bits = bits_for_value(hm.max_key);
-    if (sel) {
-        N = (size_t)hm.n_sel;  // everything below works on the slab's points only
-        if (N == 0) {          // an empty slab is a valid shard: zero rows
-            Handle* h0 = new Handle();
-            h0->stream = s;
-            h0->device = c->device;
-            h0->fdim = fdim;
-            h0->ldim = ldim;
-            *M_out = 0;
-            *handle = h0;
-            return SSDR_OK;
-        }
-    }
+    SortParams sp;
+    sp.pts = in.p;
+    sp.N = N;
+    sp.dl = dl;
+    sp.has_bbox = bbox ? 1 : 0;
+    for (int d = 0; d < 6; ++d) sp.bbox[d] = bbox ? bbox[d] : 0.f;
+    sp.slab_axis = slab.axis;
+    sp.slab_lo = slab.lo;
+    sp.slab_hi = slab.hi;
+    sp.meta = meta;
+    sp.keys[0] = c->ws[WS_KEYS].as<KeyT>();
+    sp.keys[1] = c->ws[WS_KEYS2].as<KeyT>();
+    sp.idx[0] = c->ws[WS_IDX].as<unsigned>();
+    sp.idx[1] = c->ws[WS_IDX2].as<unsigned>();
+    sp.barrier = reinterpret_cast<unsigned*>(ctl);
+    sp.pmax = reinterpret_cast<KeyT*>(ctl + 256);
+    sp.partials = reinterpret_cast<float*>(ctl + 256 + (size_t)G * sizeof(KeyT));
+    sp.cta_count = reinterpret_cast<unsigned*>(ctl + 256 + (size_t)G * (sizeof(KeyT) + 6 * sizeof(float)));
+    sp.hist = reinterpret_cast<unsigned*>(ctl + (256 + (size_t)G * (6 * sizeof(float) + sizeof(KeyT) + sizeof(unsigned)) + 255) / 256 * 256);
+    sp.starts = c->ws[WS_STARTS].as<unsigned>();
+    SSDR_CHECK_CUDA(cudaMemsetAsync(sp.barrier, 0, 256, s));
 
-    // 4. stable radix sort over the significant bits; 5. heads -> voxel ids -> starts (M lands in meta->M)
-    int cur = 0;
-    SSDR_TRY(prim::radix_sort_pairs(keys, idx, keys2, idx2, N, key_bits, scratch, &cur, s));
-    const KeyT* keys_sorted = cur ? keys2 : keys;
-    const unsigned* idx_sorted = cur ? idx2 : idx;
-    unsigned* flags = reinterpret_cast<unsigned*>(cur ? keys : keys2);  // the other key buffer is free now: 8 B/pt
-    unsigned* vid = flags + N;
-    const unsigned nb = (unsigned)((N + 255) / 256);
-    head_flag_kernel<<<nb, 256, 0, s>>>(keys_sorted, N, flags);
-    SSDR_TRY(prim::exclusive_scan_u32(flags, vid, N, scratch + prim::rs_scratch_words(N),
-                                      reinterpret_cast<unsigned*>(&meta->M), s));
-    voxel_start_kernel<<<nb, 256, 0, s>>>(flags, vid, N, starts);
-    SSDR_CHECK_CUDA(cudaGetLastError());
-    SSDR_TRY(d2h_sync(c, &hm, meta, sizeof(Meta), s));  // sync 2: M, to size the outputs
-    const size_t M = (size_t)hm.M;
-    SSDR_REQUIRE(M >= 1 && M <= N, SSDR_ERR_EMPTY, "Error");
-
+    // outputs are sized for the worst case (every point its own voxel): M is known only on the device
     Handle* h = new Handle();
     h->stream = s;
     h->device = c->device;
-    h->M = M;
     h->fdim = fdim;
     h->ldim = ldim;
     auto fail = [&](int rc) {
@@ -643,39 +1136,66 @@ static int run_dev(Ctx* c, cudaStream_t s, const float* d_p, const float* d_f, c
             return fail(set_error(SSDR_ERR_NOMEM, "cudaMallocAsync(%zu) failed: %s", (size_t)(bytes), cudaGetErrorString(_e))); \
         }                                                                                                 \
     } while (0)
-    SSDR_ALLOC(h->d_p, M * 3 * sizeof(float));
-    if (fdim) SSDR_ALLOC(h->d_f, M * fdim * sizeof(float));
-    if (ldim) SSDR_ALLOC(h->d_c, M * ldim * sizeof(int));
-    SSDR_ALLOC(h->d_k, M * sizeof(unsigned long long));
-    SSDR_ALLOC(h->d_n, M * sizeof(int));
+    SSDR_ALLOC(h->d_p, N * 3 * sizeof(float));
+    if (fdim) SSDR_ALLOC(h->d_f, N * fdim * sizeof(float));
+    if (ldim) SSDR_ALLOC(h->d_c, N * ldim * sizeof(int));
+    SSDR_ALLOC(h->d_k, N * sizeof(unsigned long long));
+    SSDR_ALLOC(h->d_n, N * sizeof(int));
 #undef SSDR_ALLOC
-    const unsigned vblocks = (unsigned)((M + 127) / 128);
-#define SSDR_REDUCE(FDV)                                                                                         \
-    reduce_kernel<FDV><<<vblocks, 128, 0, s>>>(d_p, d_f, d_c, (int)fdim, (int)ldim, keys_sorted, idx_sorted, \
-                                               starts, N, M, h->d_p, h->d_f, h->d_c, h->d_k, h->d_n, meta)
-    switch (fdim) {
-        case 0: SSDR_REDUCE(0); break;
-        case 1: SSDR_REDUCE(1); break;
-        case 2: SSDR_REDUCE(2); break;
-        case 3: SSDR_REDUCE(3); break;
-        case 4: SSDR_REDUCE(4); break;
-        case 6: SSDR_REDUCE(6); break;
-        case 8: SSDR_REDUCE(8); break;
-        default: SSDR_REDUCE(-1); break;
-    }
-#undef SSDR_REDUCE
+
     {
+        void* args[] = {(void*)&sp};
+        cudaError_t e = cudaLaunchCooperativeKernel((void*)sort_kernel, dim3(G), dim3(PA_THREADS), args, 0, s);
+        if (e != cudaSuccess) return fail(set_error(SSDR_ERR_CUDA, "sort_kernel launch failed: %s", cudaGetErrorString(e)));
+    }
+    ReduceParams rp;
+    rp.pts = in.p;
+    rp.feats = fdim ? in.f : nullptr;
+    rp.cls = ldim ? in.c : nullptr;
+    rp.feat_u8 = in.f_u8 ? 1 : 0;
+    rp.cls_u8 = in.c_u8 ? 1 : 0;
+    rp.fdim = (int)fdim;
+    rp.ldim = (int)ldim;
+    rp.keys[0] = sp.keys[0];
+    rp.keys[1] = sp.keys[1];
+    rp.idx[0] = sp.idx[0];
+    rp.idx[1] = sp.idx[1];
+    rp.starts = sp.starts;
+    rp.meta = meta;
+    rp.out_p = h->d_p;
+    rp.out_f = h->d_f;
+    rp.out_c = h->d_c;
+    rp.out_k = h->d_k;
+    rp.out_n = h->d_n;
+    {
+        size_t want = (N + RB_GROUPS - 1) / RB_GROUPS;  // M <= N voxels, one group each at most
+        const size_t cap = (size_t)c->sm_count * 8;
+        const unsigned blocks = (unsigned)(want < cap ? (want ? want : 1) : cap);
+        reduce_kernel<<<blocks, RB_THREADS, 0, s>>>(rp);
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) return fail(set_error(SSDR_ERR_CUDA, "reduce_kernel launch failed: %s", cudaGetErrorString(e)));
     }
-    if (ldim) {  // the only late failure mode is a label-table overflow; surface it before results are used
+    // the ONE host round trip of the call: voxel count (the caller sizes its arrays with it) and the error flag
+    Meta hm;
+    {
         int rc = d2h_sync(c, &hm, meta, sizeof(Meta), s);
         if (rc != SSDR_OK) return fail(rc);
-        if (hm.error == 2)
-            return fail(set_error(SSDR_ERR_UNSUPPORTED, "more than %d distinct labels inside one voxel", LABEL_CAP));
     }
-    if (order == SSDR_GRID_ORDER_REFERENCE && M > 1) {
-        int rc = reorder_reference(c, s, h, idx_sorted, starts, N, scratch);
+    if (hm.error == 2)
+        return fail(set_error(SSDR_ERR_UNSUPPORTED, "more than %d distinct labels inside one voxel", LABEL_CAP));
+    h->M = (size_t)hm.M;
+    if (slab.axis >= 0 && hm.n_sel == 0) {  // an empty slab is a valid shard: zero rows
+        *M_out = 0;
+        *handle = h;
+        return SSDR_OK;
+    }
+    if (!(h->M >= 1 && h->M <= N)) return fail(set_error(SSDR_ERR_EMPTY, "Error"));
+    if (order == SSDR_GRID_ORDER_REFERENCE && h->M > 1) {
+        const size_t n_sel = (size_t)hm.n_sel;
+        SSDR_TRY(c->ws[WS_TEMP].reserve((prim::rs_scratch_words(n_sel) + prim::scan_scratch_words(n_sel) + 8) * sizeof(unsigned)));
+        unsigned* scratch = c->ws[WS_TEMP].as<unsigned>();
+        SSDR_CHECK_CUDA(cudaMemsetAsync(scratch, 0, (prim::rs_scratch_words(n_sel) + prim::scan_scratch_words(n_sel) + 8) * sizeof(unsigned), s));
+        int rc = reorder_reference(c, s, h, sp.idx[hm.cur], sp.starts, N, scratch);
         if (rc != SSDR_OK) return fail(rc);
     }
     *M_out = h->M;
@@ -695,8 +1215,11 @@ int ssdr_grid_subsample_dev(const float* d_points, const float* d_feats, const i
                             void** handle) {
     Ctx* c;
     SSDR_TRY(get_ctx(&c));
-    return grid::run_dev(c, (cudaStream_t)stream, d_points, d_feats, d_classes, N, fdim, ldim,
-                         sampleDl, order, M_out, handle);
+    grid::Inputs in;
+    in.p = d_points;
+    in.f = d_feats;
+    in.c = d_classes;
+    return grid::run_dev(c, (cudaStream_t)stream, in, N, fdim, ldim, sampleDl, order, M_out, handle);
 }
 
 int ssdr_grid_subsample_slab_dev(const float* d_points, const float* d_feats, const int32_t* d_classes, size_t N,
@@ -712,8 +1235,11 @@ int ssdr_grid_subsample_slab_dev(const float* d_points, const float* d_feats, co
     slab.axis = axis;
     slab.lo = layer_lo;
     slab.hi = layer_hi;
-    return grid::run_dev(c, (cudaStream_t)stream, d_points, d_feats, d_classes, N, fdim, ldim, sampleDl, order,
-                         M_out, handle, slab, bbox);
+    grid::Inputs in;
+    in.p = d_points;
+    in.f = d_feats;
+    in.c = d_classes;
+    return grid::run_dev(c, (cudaStream_t)stream, in, N, fdim, ldim, sampleDl, order, M_out, handle, slab, bbox);
 }
 
 int ssdr_grid_bbox_dev(const float* d_points, size_t N, void* stream, float* bbox_out) {
@@ -756,32 +1282,6 @@ int ssdr_grid_point_layers_dev(const float* d_points, size_t N, const float* bbo
     return SSDR_OK;
 }
 
-int ssdr_grid_subsample(const float* points, const float* feats, const int32_t* classes, size_t N, size_t fdim,
-                        size_t ldim, float sampleDl, int order, size_t* M_out, void** handle) {
-    SSDR_REQUIRE(points && M_out && handle, SSDR_ERR_INVALID, "NULL pointer");
-    SSDR_REQUIRE(N >= 1, SSDR_ERR_EMPTY, "Error");
-    Ctx* c;
-    SSDR_TRY(get_ctx(&c));
-    if (!feats) fdim = 0;
-    if (!classes) ldim = 0;
-    SSDR_TRY(c->ws[grid::WS_IN_P].reserve(N * 3 * sizeof(float)));
-    SSDR_TRY(h2d(c, c->ws[grid::WS_IN_P].p, points, N * 3 * sizeof(float), c->stream));
-    const float* d_f = nullptr;
-    const int* d_c = nullptr;
-    if (fdim) {
-        SSDR_TRY(c->ws[grid::WS_IN_F].reserve(N * fdim * sizeof(float)));
-        SSDR_TRY(h2d(c, c->ws[grid::WS_IN_F].p, feats, N * fdim * sizeof(float), c->stream));
-        d_f = c->ws[grid::WS_IN_F].as<float>();
-    }
-    if (ldim) {
-        SSDR_TRY(c->ws[grid::WS_IN_C].reserve(N * ldim * sizeof(int)));
-        SSDR_TRY(h2d(c, c->ws[grid::WS_IN_C].p, classes, N * ldim * sizeof(int), c->stream));
-        d_c = c->ws[grid::WS_IN_C].as<int>();
-    }
-    return grid::run_dev(c, c->stream, c->ws[grid::WS_IN_P].as<float>(), d_f, d_c, N, fdim, ldim, sampleDl, order,
-                         M_out, handle);
-}
-
 int ssdr_grid_subsample_typed(const float* points, const void* feats, int feats_dtype, const void* classes,
                               int classes_dtype, size_t N, size_t fdim, size_t ldim, float sampleDl, int order,
                               size_t* M_out, void** handle) {
@@ -796,37 +1296,33 @@ int ssdr_grid_subsample_typed(const float* points, const void* feats, int feats_
     if (!feats) fdim = 0;
     if (!classes) ldim = 0;
     cudaStream_t s = c->stream;
+    // the bytes travel as they are (uint8 colours / labels: 4x less PCIe than the float32 / int32 the reference's
+    // wrapper widens them to on the host, wrapper.cpp:100-106); the reduce kernel widens on the fly (exact)
+    grid::Inputs in;
     SSDR_TRY(c->ws[grid::WS_IN_P].reserve(N * 3 * sizeof(float)));
     SSDR_TRY(h2d(c, c->ws[grid::WS_IN_P].p, points, N * 3 * sizeof(float), s));
-    const size_t nf = N * fdim, nc = N * ldim;
-    const size_t raw_f = (fdim && feats_dtype == SSDR_DTYPE_U8) ? align_up(nf, 256) : 0;
-    const size_t raw_c = (ldim && classes_dtype == SSDR_DTYPE_U8) ? align_up(nc, 256) : 0;
-    if (raw_f + raw_c) SSDR_TRY(c->ws[grid::WS_RAW].reserve(raw_f + raw_c));
-    unsigned char* raw = c->ws[grid::WS_RAW].as<unsigned char>();
-    const float* d_f = nullptr;
-    const int* d_c = nullptr;
+    in.p = c->ws[grid::WS_IN_P].as<float>();
     if (fdim) {
-        SSDR_TRY(c->ws[grid::WS_IN_F].reserve(nf * sizeof(float)));
-        if (raw_f) {
-            SSDR_TRY(h2d(c, raw, feats, nf, s));
-            grid::widen_u8_f32_kernel<<<(unsigned)((nf + 255) / 256), 256, 0, s>>>(raw, nf, c->ws[grid::WS_IN_F].as<float>());
-        } else {
-            SSDR_TRY(h2d(c, c->ws[grid::WS_IN_F].p, feats, nf * sizeof(float), s));
-        }
-        d_f = c->ws[grid::WS_IN_F].as<float>();
+        in.f_u8 = feats_dtype == SSDR_DTYPE_U8;
+        const size_t bytes = N * fdim * (in.f_u8 ? 1 : sizeof(float));
+        SSDR_TRY(c->ws[grid::WS_IN_F].reserve(bytes));
+        SSDR_TRY(h2d(c, c->ws[grid::WS_IN_F].p, feats, bytes, s));
+        in.f = c->ws[grid::WS_IN_F].p;
     }
     if (ldim) {
-        SSDR_TRY(c->ws[grid::WS_IN_C].reserve(nc * sizeof(int)));
-        if (raw_c) {
-            SSDR_TRY(h2d(c, raw + raw_f, classes, nc, s));
-            grid::widen_u8_i32_kernel<<<(unsigned)((nc + 255) / 256), 256, 0, s>>>(raw + raw_f, nc, c->ws[grid::WS_IN_C].as<int>());
-        } else {
-            SSDR_TRY(h2d(c, c->ws[grid::WS_IN_C].p, classes, nc * sizeof(int), s));
-        }
-        d_c = c->ws[grid::WS_IN_C].as<int>();
+        in.c_u8 = classes_dtype == SSDR_DTYPE_U8;
+        const size_t bytes = N * ldim * (in.c_u8 ? 1 : sizeof(int));
+        SSDR_TRY(c->ws[grid::WS_IN_C].reserve(bytes));
+        SSDR_TRY(h2d(c, c->ws[grid::WS_IN_C].p, classes, bytes, s));
+        in.c = c->ws[grid::WS_IN_C].p;
     }
-    SSDR_CHECK_CUDA(cudaGetLastError());
-    return grid::run_dev(c, s, c->ws[grid::WS_IN_P].as<float>(), d_f, d_c, N, fdim, ldim, sampleDl, order, M_out, handle);
+    return grid::run_dev(c, s, in, N, fdim, ldim, sampleDl, order, M_out, handle);
+}
+
+int ssdr_grid_subsample(const float* points, const float* feats, const int32_t* classes, size_t N, size_t fdim,
+                        size_t ldim, float sampleDl, int order, size_t* M_out, void** handle) {
+    return ssdr_grid_subsample_typed(points, feats, SSDR_DTYPE_NATIVE, classes, SSDR_DTYPE_NATIVE, N, fdim, ldim, sampleDl,
+                                     order, M_out, handle);
 }
 
 int ssdr_grid_fetch_ex(void* handle, float* points_out, float* feats_out, int32_t* classes_out, uint64_t* keys_out,

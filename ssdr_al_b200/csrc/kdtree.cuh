@@ -92,6 +92,9 @@ struct Tree {
     unsigned* error;       // bit 0: node capacity, bit 1: level cap, bit 2: DFS stack, bit 3: list capacity
     const unsigned char* item_needed;  // [B] build only where a flagged row lives (nullptr = all)
     unsigned long long* tstamps;       // [16] optional %globaltimer marks (diagnostics; nullptr = off)
+    unsigned char* item_flags;         // [B] storage of the item_needed flags inside the control block
+    unsigned* built;                   // control word: 1 once the trees of this workspace have been built
+    int skip_if_built;                 // asynchronous reuse: a later call on the SAME cloud builds only if nobody did
 };
 
 __device__ __forceinline__ unsigned f2ord_u(float f) {
@@ -1146,6 +1149,10 @@ __global__ void __launch_bounds__(BT, 1) build_kernel(const float* __restrict__ 
 
     // the whole tie path is enqueued without knowing whether any row was flagged: nothing to do in that case
     if (t.n_flag && __ldcg(t.n_flag) == 0) return;
+    // a call that shares its support cloud with the previous one (the pyramid's 1-NN up-sampling and the k=16 query of
+    // the next level) finds the trees in place; every CTA reads the word before CTA 0 sets it behind the first barrier
+    const bool already = t.skip_if_built && __ldcg(t.built) != 0;
+    if (already) return;
 
     // ---- roots: pp = (point, identity index) (init_vind :1232-1238), data bbox (computeBoundingBox :1241-1263).
     // kroot CTAs share one item; the last of them to finish (ticket) writes the root record and queues it.
@@ -1230,6 +1237,7 @@ __global__ void __launch_bounds__(BT, 1) build_kernel(const float* __restrict__ 
     }
     grid_sync(t.barrier, phase);
     mark(nullptr, t.tstamps, 1);
+    if (blockIdx.x == 0 && tid == 0) *t.built = 1u;
 
     // ---- TOP levels
     for (int level = 0; level < MAX_LEVELS; ++level) {
@@ -1434,7 +1442,7 @@ static int alloc_tree(Ctx* c, cudaStream_t s, size_t B, size_t N, Tree* out) {
     SSDR_TRY(c->ws[TW_BASE + 0].reserve(B * N * (sizeof(float4) + 4 * sizeof(unsigned))));
     SSDR_TRY(c->ws[TW_BASE + 1].reserve(B * cap * (sizeof(NodeRec) + 12 * sizeof(float))));
     SSDR_TRY(c->ws[TW_BASE + 2].reserve(3 * lcap * sizeof(unsigned)));
-    const size_t ctl_words = 6 * B + B + (size_t)(MAX_LEVELS + 2) + 8 + (B + 3) / 4 + 4 + 8 * B;
+    const size_t ctl_words = 6 * B + B + (size_t)(MAX_LEVELS + 2) + 8 + (B + 3) / 4 + 4 + 8 * B + 4;
     SSDR_TRY(c->ws[TW_BASE + 3].reserve(ctl_words * sizeof(unsigned)));
     const size_t G = (size_t)c->sm_count;
     const size_t grp_words = (size_t)MAX_GROUP_LEVELS * G * 13 + G * 2 * G * 2;
@@ -1470,13 +1478,16 @@ static int alloc_tree(Ctx* c, cudaStream_t s, size_t B, size_t N, Tree* out) {
     t.gpart = t.gred + (size_t)MAX_GROUP_LEVELS * G * 12;
     SSDR_CHECK_CUDA(cudaMemsetAsync(t.gbar, 0, (size_t)MAX_GROUP_LEVELS * G * 13 * sizeof(unsigned), s));
     t.root_red = t.error + 4 + (B + 3) / 4 + 1;
+    t.item_flags = reinterpret_cast<unsigned char*>(t.error + 4);
+    t.built = ctl + ctl_words - 4;
+    t.skip_if_built = 0;
     t.n_flag = nullptr;
     t.item_needed = nullptr;
     t.tstamps = nullptr;
     *out = t;
     return SSDR_OK;
 }
-static unsigned char* tree_needed_flags(const Tree& t) { return reinterpret_cast<unsigned char*>(t.error + 4); }
+static unsigned char* tree_needed_flags(const Tree& t) { return t.item_flags; }
 
 static int launch_build(Ctx* c, cudaStream_t s, const float* d_pts, const Tree& t) {
     const size_t smem = SM_TOTAL;
@@ -1612,6 +1623,48 @@ static int enqueue_tie_path(Ctx* c, cudaStream_t s, const float* d_pts, size_t B
     SSDR_CHECK_CUDA(cudaGetLastError());
     *n_launch += 1;
     *t_out = t;
+    return SSDR_OK;
+}
+
+// The same without ANY host round trip, for callers that enqueue several KNN calls back to back (the pyramid): errors
+// accumulate in the caller's persistent device word `status`; `shared` carries the tree workspace from one call to the
+// next, and reuse_shared says that this call's support cloud IS the previous call's (known structurally, so no content
+// check): the build then runs only if the previous call did not need the trees.
+template <typename OutT>
+static int enqueue_tie_path_async(Ctx* c, cudaStream_t s, const float* d_pts, size_t B, size_t N, const float* d_q,
+                                  size_t Q, size_t K, OutT* d_out, const unsigned* flag_list,
+                                  const unsigned* d_flag_count, Tree* shared, bool reuse_shared, unsigned* status,
+                                  unsigned long long* n_launch) {
+    SSDR_REQUIRE(K <= (size_t)MAX_K, SSDR_ERR_UNSUPPORTED, "K=%zu > %d in the exact tie path", K, MAX_K);
+    Tree t;
+    if (reuse_shared) {
+        t = *shared;
+        SSDR_REQUIRE(t.B == B && t.N == N, SSDR_ERR_INVALID, "shared tree geometry mismatch");
+        t.skip_if_built = 1;
+    } else {
+        SSDR_TRY(alloc_tree(c, s, B, N, &t));  // also drops the thread's synchronous tree cache
+        SSDR_CHECK_CUDA(cudaMemsetAsync(t.item_flags, 1, B, s));
+        t.item_needed = nullptr;  // all items: the next call may need any of them
+    }
+    t.n_flag = d_flag_count;
+    t.error = status;
+    t.tstamps = nullptr;
+    SSDR_TRY(launch_build(c, s, d_pts, t));
+    *n_launch += 1;
+#define SSDR_EXACT(KCV)                                                                                       \
+    exact_query_kernel<OutT, KCV><<<(unsigned)c->sm_count * 16, 32, 0, s>>>(d_q, t, (unsigned)Q, (int)K, flag_list, \
+                                                                            d_flag_count, d_out)
+    if (K == 1) SSDR_EXACT(1);
+    else if (K <= 2) SSDR_EXACT(2);
+    else if (K <= 4) SSDR_EXACT(4);
+    else if (K <= 8) SSDR_EXACT(8);
+    else if (K <= 16) SSDR_EXACT(16);
+    else if (K <= 32) SSDR_EXACT(32);
+    else SSDR_EXACT(64);
+#undef SSDR_EXACT
+    SSDR_CHECK_CUDA(cudaGetLastError());
+    *n_launch += 1;
+    *shared = t;
     return SSDR_OK;
 }
 

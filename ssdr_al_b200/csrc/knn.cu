@@ -33,7 +33,17 @@ struct ItemMeta {
 
 enum { WS_ENC = 0, WS_ITEMS = 1, WS_CELL_P = 2, WS_CELL_Q = 3, WS_CNT_P = 4, WS_CNT_Q = 5, WS_START_P = 6,
        WS_START_Q = 7, WS_SORT_P = 8, WS_SORT_Q = 9, WS_FLAGS = 10, WS_TEMP = 11, WS_IN_P = 12, WS_IN_Q = 13,
-       WS_OUT = 14, WS_STATS = 15, WS_TREE = 16 /* .. WS_TREE+5 used by kdtree.cuh */, WS_PATCH = 22 };
+       WS_OUT = 14, WS_STATS = 15, WS_TREE = 16 /* .. WS_TREE+5 used by kdtree.cuh */, WS_PATCH = 22, WS_ASYNC = 23 };
+
+// Calls enqueued back to back without a host round trip (the pyramid): the tree workspace travels from call to call and
+// errors of the tie path accumulate in a persistent device word that ssdr_knn_status reads.
+static thread_local unsigned long long g_last_launches = 0;  // kernels launched by this thread's last pyramid call
+
+struct AsyncCtx {
+    kdtree::Tree tree;
+    bool reuse = false;      // this call's support cloud is the previous call's: trees are built at most once
+    unsigned* status = nullptr;
+};
 
 __device__ __forceinline__ unsigned f2ord(float f) {
     unsigned u = __float_as_uint(f);
@@ -747,7 +757,7 @@ constexpr unsigned PATCH_CAP = 1u << 15;  // rows; more flagged rows than this f
 // device->host copy starts right behind the main kernel and overlaps the tie path.
 template <typename OutT>
 static int run_dev(Ctx* c, cudaStream_t s, const float* d_pts, size_t B, size_t N, const float* d_q, size_t Q, size_t K,
-                   OutT* d_out, ssdr_knn_stats* stats, OutT* h_out = nullptr) {
+                   OutT* d_out, ssdr_knn_stats* stats, OutT* h_out = nullptr, AsyncCtx* ac = nullptr) {
     SSDR_REQUIRE(d_pts && d_q && d_out, SSDR_ERR_INVALID, "NULL pointer");
     SSDR_REQUIRE(N >= 1, SSDR_ERR_INVALID, "npts must be >= 1 (the reference asserts npts != 0)");
     SSDR_REQUIRE(K >= 1, SSDR_ERR_INVALID, "K must be >= 1");
@@ -932,6 +942,12 @@ static int run_dev(Ctx* c, cudaStream_t s, const float* d_pts, size_t B, size_t 
     // call with K * queries >= 131072 has flagged rows almost surely and the tie path is enqueued right behind the
     // main kernel without a host round trip (its kernels return at once if the device-side count is zero).
     // Otherwise ties are rare: read the count first and skip the (cooperative, whole-GPU) launch when it is zero.
+    if (ac) {  // asynchronous flavour: the tie path is enqueued unconditionally, nothing is read back
+        SSDR_TRY((kdtree::enqueue_tie_path_async<OutT>(c, s, d_pts, B, N, d_q, Q, K, d_out, flag_list, &dstats->flag_count,
+                                                       &ac->tree, ac->reuse, ac->status, &n_launch)));
+        g_last_launches += n_launch;
+        return SSDR_OK;
+    }
     kdtree::Tree tree;
     tree.error = nullptr;
     DevStats hs;
@@ -1059,12 +1075,80 @@ static int run_host(const float* pts, size_t B, size_t N, size_t dim, const floa
     return SSDR_OK;  // delivered by run_dev (bulk read-back overlapped with the tie path)
 }
 
+static int async_status_word(Ctx* c, cudaStream_t s, unsigned** out) {
+    const void* before = c->ws[WS_ASYNC].p;
+    SSDR_TRY(c->ws[WS_ASYNC].reserve(64));
+    if (c->ws[WS_ASYNC].p != before) SSDR_CHECK_CUDA(cudaMemsetAsync(c->ws[WS_ASYNC].p, 0, 64, s));
+    *out = c->ws[WS_ASYNC].as<unsigned>();
+    return SSDR_OK;
+}
+
+// The loop of s3dis_dataset.py:164-177 in one call, every level enqueued behind the previous one.
+static int pyramid_dev(Ctx* c, cudaStream_t s, const float* d_points, size_t B, size_t npts, const int32_t* ratios,
+                       size_t n_levels, size_t K, long long* const* d_neigh, long long* const* d_up) {
+    SSDR_REQUIRE(d_points && ratios && d_neigh && d_up, SSDR_ERR_INVALID, "NULL pointer");
+    SSDR_REQUIRE(n_levels >= 1 && n_levels <= 16, SSDR_ERR_INVALID, "n_levels must be in [1, 16]");
+    SSDR_REQUIRE(npts >= 1 && K >= 1, SSDR_ERR_INVALID, "npts and K must be >= 1");
+    if (B == 0) return SSDR_OK;
+    size_t n[17];
+    n[0] = npts;
+    size_t packed = 0;
+    for (size_t l = 0; l < n_levels; ++l) {
+        SSDR_REQUIRE(ratios[l] >= 1, SSDR_ERR_INVALID, "sub-sampling ratio %d of level %zu is not positive", ratios[l], l);
+        n[l + 1] = n[l] / (size_t)ratios[l];
+        SSDR_REQUIRE(n[l + 1] >= 1, SSDR_ERR_INVALID, "level %zu would be empty", l + 1);
+        SSDR_REQUIRE(d_neigh[l] && d_up[l], SSDR_ERR_INVALID, "NULL output of level %zu", l);
+        packed += B * n[l + 1] * 3;
+    }
+    SSDR_TRY(c->ws[WS_IN_Q].reserve(packed * sizeof(float)));
+    // level l+1 = the first N_{l+1} points of every item of level l (the loader's random order makes a prefix a random
+    // sub-sample, s3dis_dataset.py:166): packed by the copy engine
+    const float* level[17];
+    level[0] = d_points;
+    float* w = c->ws[WS_IN_Q].as<float>();
+    for (size_t l = 0; l < n_levels; ++l) {
+        SSDR_CHECK_CUDA(cudaMemcpy2DAsync(w, n[l + 1] * 3 * sizeof(float), level[l], n[l] * 3 * sizeof(float),
+                                          n[l + 1] * 3 * sizeof(float), B, cudaMemcpyDeviceToDevice, s));
+        level[l + 1] = w;
+        w += B * n[l + 1] * 3;
+    }
+    AsyncCtx ac;
+    SSDR_TRY(async_status_word(c, s, &ac.status));
+    g_last_launches = 0;
+    for (size_t l = 0; l < n_levels; ++l) {
+        ac.reuse = l > 0;  // the trees of this level's cloud belong to the previous level's up-sampling query
+        SSDR_TRY((run_dev<long long>(c, s, level[l], B, n[l], level[l], n[l], K, d_neigh[l], nullptr, nullptr, &ac)));
+        ac.reuse = false;
+        SSDR_TRY((run_dev<long long>(c, s, level[l + 1], B, n[l + 1], level[l], n[l], 1, d_up[l], nullptr, nullptr, &ac)));
+    }
+    return SSDR_OK;
+}
+
 }  // namespace knn
 }  // namespace ssdr
 
 using namespace ssdr;
 
 extern "C" {
+int ssdr_knn_pyramid_dev(const float* d_points, size_t batch_size, size_t npts, const int32_t* ratios, size_t n_levels,
+                         size_t K, int64_t* const* d_neigh, int64_t* const* d_up, void* stream) {
+    Ctx* c;
+    SSDR_TRY(get_ctx(&c));
+    return knn::pyramid_dev(c, (cudaStream_t)stream, d_points, batch_size, npts, ratios, n_levels, K,
+                            reinterpret_cast<long long* const*>(d_neigh), reinterpret_cast<long long* const*>(d_up));
+}
+unsigned long long ssdr_knn_pyramid_launches(void) { return knn::g_last_launches; }
+int ssdr_knn_status(void* stream) {
+    Ctx* c;
+    SSDR_TRY(get_ctx(&c));
+    cudaStream_t s = (cudaStream_t)stream;
+    unsigned* w = nullptr;
+    SSDR_TRY(knn::async_status_word(c, s, &w));
+    unsigned h = 0;
+    SSDR_TRY(d2h_sync(c, &h, w, sizeof(h), s));
+    if (h) SSDR_CHECK_CUDA(cudaMemsetAsync(w, 0, sizeof(unsigned), s));
+    return kdtree::tree_error_to_status(h);
+}
 int ssdr_knn(const float* points, size_t npts, size_t dim, const float* queries, size_t nqueries, size_t K,
              int64_t* indices) {
     return knn::run_host<long long>(points, 1, npts, dim, queries, nqueries, K, reinterpret_cast<long long*>(indices));

@@ -956,14 +956,11 @@ static unsigned long long peer_timeout_ms() {  // read per call: a test shortens
     const unsigned long long v = e ? strtoull(e, nullptr, 10) : 0ull;
     return v > 0 ? v : 20000ull;
 }
-static const Tunables& tunables() {
-    static Tunables t;
-    static std::once_flag once;
-    std::call_once(once, [] {
-        if (const char* e = getenv("SSDR_SEL_FEED")) t.feed = atoi(e) != 0;
-        if (const char* e = getenv("SSDR_SEL_STAGES")) t.stages = atoi(e);
-        if (const char* e = getenv("SSDR_SEL_WARPS")) t.warps = atoi(e);
-    });
+static Tunables tunables() {  // read per call (cheap): one process can sweep the knobs
+    Tunables t;
+    if (const char* e = getenv("SSDR_SEL_FEED")) t.feed = atoi(e) != 0;
+    if (const char* e = getenv("SSDR_SEL_STAGES")) t.stages = atoi(e);
+    if (const char* e = getenv("SSDR_SEL_WARPS")) t.warps = atoi(e);
     return t;
 }
 
@@ -999,7 +996,7 @@ template <int MODE>
 static int configure32(Ctx* c, Launch<float>& L, const float* dF, size_t N) {
     EncodeTiledFn enc = encode_tiled_fn();
     if (!enc) return -1;  // no driver entry point: the caller falls back to the bulk-copy variant
-    const Tunables& tn = tunables();
+    const Tunables tn = tunables();
     Params<float>& p = L.p;
     int nw = tn.warps > 0 ? tn.warps : WARPS, nst = tn.stages > 0 ? tn.stages : 3;
     nw = nw < 1 ? 1 : (nw > WARPS ? WARPS : nw);
@@ -1036,7 +1033,7 @@ static int configure32(Ctx* c, Launch<float>& L, const float* dF, size_t N) {
 template <typename T, int MODE>
 static int configure(Ctx* c, Launch<T>& L, const T* dF, size_t N, size_t D) {
     Params<T>& p = L.p;
-    const Tunables& tn = tunables();
+    const Tunables tn = tunables();
     p.F = dF;
     p.N = N;
     p.D = (int)D;

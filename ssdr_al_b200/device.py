@@ -32,6 +32,30 @@ def knn_batch(pts, queries, K, out=None, want_stats=False, int32=False):
     return out
 
 
+def knn_pyramid(xyz, ratios, K, neigh=None, up=None, check=False):
+    """RandLA-Net's input pyramid (s3dis_dataset.py:164-177) in one asynchronous call: xyz (B,N,3) f32 cuda ->
+    (neigh, up) lists with neigh[l] (B,N_l,K) and up[l] (B,N_l,1) int64, N_{l+1} = N_l // ratios[l].  Nothing is read
+    back; check=True waits for the stream and raises if the exact tie path reported an error."""
+    assert xyz.is_cuda and xyz.dtype == torch.float32 and xyz.dim() == 3 and xyz.shape[2] == 3
+    xyz = xyz.contiguous()
+    B, N, _ = xyz.shape
+    L = len(ratios)
+    sizes = [N]
+    for r in ratios:
+        sizes.append(sizes[-1] // int(r))
+    if neigh is None:
+        neigh = [torch.zeros((B, sizes[l], K), dtype=torch.int64, device=xyz.device) for l in range(L)]
+    if up is None:
+        up = [torch.zeros((B, sizes[l], 1), dtype=torch.int64, device=xyz.device) for l in range(L)]
+    rat = (C.c_int32 * L)(*[int(r) for r in ratios])
+    pn = (C.c_void_p * L)(*[t.data_ptr() for t in neigh])
+    pu = (C.c_void_p * L)(*[t.data_ptr() for t in up])
+    _lib.check(_lib.lib().ssdr_knn_pyramid_dev(_p(xyz), B, N, rat, L, int(K), pn, pu, _stream()))
+    if check:
+        _lib.check(_lib.lib().ssdr_knn_status(_stream()))
+    return neigh, up
+
+
 def grid_subsample(points, features=None, classes=None, sampleDl=0.1, bbox=None, slab=None, return_keys=False):
     """points (N,3) f32, features (N,fdim) f32, classes (N,ldim) i32 cuda tensors -> tuple of cuda tensors.
 

@@ -132,18 +132,58 @@ def test_knn_external_queries_outside_bbox(NN, oracle):
         assert np.array_equal(NN.knn(p, q, K), oracle.knn(p, q, K, threads=8))
 
 
-def test_knn_batch_randla_pyramid_config2_shapes(NN, oracle):
-    """BASELINE config 2 (scaled to 2 x 40960 so the oracle finishes in seconds): the loop of s3dis_dataset.py:164-177."""
+def _ref_knn_batch(oracle):
+    """The reference's own cpp_knn_batch_omp when oracle/_ref was built, else the C restatement."""
+    if oracle.have_ref():
+        oracle.set_omp_threads(6)
+        return lambda p, q, k: oracle.ref_knn_batch(p, q, k, omp=True)
+    return lambda p, q, k: oracle.knn_batch(p, q, k, threads=8)
+
+
+def test_knn_batch_randla_pyramid_config2_full_size(NN, oracle):
+    """BASELINE config 2 at its stated size (6 x 40960, five levels, k = 16 + 1-NN up-sampling): the loop of
+    s3dis_dataset.py:164-177, every call compared with the reference."""
     rng = np.random.default_rng(1)
-    B, N = 2, 40960
+    B, N = 6, 40960
     xyz = (rng.uniform(-1, 1, (B, N, 3)) * np.array([2.0, 2.0, 1.5])).astype(np.float32)
+    ref = _ref_knn_batch(oracle)
     for ratio in (4, 4, 4, 4, 2):
         neigh = NN.knn_batch(xyz, xyz, 16, omp=True)
-        assert np.array_equal(neigh, oracle.knn_batch(xyz, xyz, 16, threads=8))
+        assert np.array_equal(neigh, ref(xyz, xyz, 16))
         sub = xyz[:, : xyz.shape[1] // ratio, :]
         up = NN.knn_batch(sub, xyz, 1, omp=True)
-        assert np.array_equal(up, oracle.knn_batch(sub, xyz, 1, threads=8))
+        assert np.array_equal(up, ref(np.ascontiguousarray(sub), xyz, 1))
         xyz = sub
+
+
+@pytest.mark.parametrize("kind", ["uniform", "duplicated", "quantised"])
+def test_knn_pyramid_single_call_equals_reference(oracle, kind):
+    """ssdr_knn_pyramid_dev: the ten queries of the pyramid enqueued by ONE call without a host round trip (the trees
+    of a level built at most once for its two queries, decided on the device).  Tie-free, duplicate-heavy (the
+    loader's data_aug repeats points, s3dis_dataset.py:147-150) and quantised clouds; twice in a row on different
+    data so that nothing stale survives between calls."""
+    import torch
+    from ssdr_al_b200 import _lib, device as dev
+    ref = _ref_knn_batch(oracle)
+    ratios = (4, 4, 4, 4, 2)
+    for seed in (3, 4):
+        rng = np.random.default_rng(seed)
+        B, N = 6, 40960
+        xyz = (rng.uniform(-1, 1, (B, N, 3)) * np.array([2.0, 2.0, 1.5])).astype(np.float32)
+        if kind == "duplicated":
+            for b in range(B):
+                xyz[b, N // 2:] = xyz[b, rng.integers(0, N // 2, N - N // 2)]
+                xyz[b] = xyz[b, rng.permutation(N)]
+        elif kind == "quantised":
+            xyz = (np.round(xyz * 64) / 64).astype(np.float32)
+        neigh, up = dev.knn_pyramid(torch.from_numpy(xyz).cuda(), ratios, 16, check=True)
+        assert int(_lib.lib().ssdr_knn_pyramid_launches()) > 0
+        cur = xyz
+        for l, ratio in enumerate(ratios):
+            assert np.array_equal(neigh[l].cpu().numpy(), ref(cur, cur, 16)), (kind, seed, l)
+            sub = np.ascontiguousarray(cur[:, : cur.shape[1] // ratio, :])
+            assert np.array_equal(up[l].cpu().numpy(), ref(sub, cur, 1)), (kind, seed, l)
+            cur = sub
 
 
 def test_knn_config1_full_size_properties(NN):
