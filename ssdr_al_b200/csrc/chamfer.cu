@@ -384,6 +384,7 @@ int ssdr_chamfer_matrix_f64_dev(const double* d_points, const int64_t* d_offsets
     SSDR_REQUIRE(S >= 1 && h_offsets[0] == 0, SSDR_ERR_INVALID, "offsets must start at 0 and hold S + 1 entries");
     Ctx* c;
     SSDR_TRY(get_ctx(&c));
+    SSDR_TRY(ctx_order(c, (cudaStream_t)stream));
     return chamfer::run_dev(c, (cudaStream_t)stream, d_points, reinterpret_cast<const long long*>(d_offsets),
                             reinterpret_cast<const long long*>(h_offsets), S, d_out);
 }

@@ -54,13 +54,25 @@ struct Ctx {
     cudaEvent_t ev_main = nullptr;
     cudaEvent_t ev_chunk[8] = {};   // one per result chunk in flight on the copy stream
     cudaEvent_t tev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};  // timing events (stats paths)
+    // an entry point that returns before its work is done (ssdr_knn_pyramid_dev) leaves this behind: the stream it ran
+    // on and an event behind its last kernel.  The workspaces are shared by every call of the thread, so a later call
+    // on ANOTHER stream is ordered behind that event (get_ctx / ctx_order); the same stream is ordered anyway.
+    cudaEvent_t ev_async = nullptr;
+    cudaStream_t async_stream = nullptr;
+    bool async_pending = false;
     DevBuf ws[WS_SLOTS];            // workspaces, addressed by the owning module
     // A calling thread that exits gives its streams, events and workspaces back (loader thread pools come and go).
     ~Ctx();
 };
 
-// Returns the calling thread's context for its current device (creating it on first use).
+// Returns the calling thread's context for its current device (creating it on first use).  The library's own stream
+// (host entry points) is ordered behind a pending asynchronous call.
 int get_ctx(Ctx** out);
+// Device entry points that enqueue on the caller's stream `s`: order it behind a pending asynchronous call that ran on
+// a different stream (the per-thread workspaces are about to be reused).
+int ctx_order(Ctx* c, cudaStream_t s);
+// Marks `s` as carrying an asynchronous call that ends here.
+int ctx_mark_async(Ctx* c, cudaStream_t s);
 
 // Host -> device copy of `bytes` from an arbitrary host pointer on stream s (pinned sources are truly asynchronous;
 // pageable ones are staged by the driver and return once the source may be reused).

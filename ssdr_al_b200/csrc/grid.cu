@@ -1215,6 +1215,7 @@ int ssdr_grid_subsample_dev(const float* d_points, const float* d_feats, const i
                             void** handle) {
     Ctx* c;
     SSDR_TRY(get_ctx(&c));
+    SSDR_TRY(ctx_order(c, (cudaStream_t)stream));
     grid::Inputs in;
     in.p = d_points;
     in.f = d_feats;
@@ -1228,6 +1229,7 @@ int ssdr_grid_subsample_slab_dev(const float* d_points, const float* d_feats, co
                                  size_t* M_out, void** handle) {
     Ctx* c;
     SSDR_TRY(get_ctx(&c));
+    SSDR_TRY(ctx_order(c, (cudaStream_t)stream));
     SSDR_REQUIRE(axis >= -1 && axis <= 2, SSDR_ERR_INVALID, "axis must be -1 (no slab), 0, 1 or 2");
     SSDR_REQUIRE(order == SSDR_GRID_ORDER_KEY || (axis < 0 && !bbox), SSDR_ERR_UNSUPPORTED,
                  "the reference's hash-iteration order is defined for a whole cloud only; slabs come in key order");
@@ -1247,6 +1249,7 @@ int ssdr_grid_bbox_dev(const float* d_points, size_t N, void* stream, float* bbo
     SSDR_REQUIRE(N >= 1, SSDR_ERR_EMPTY, "Error");
     Ctx* c;
     SSDR_TRY(get_ctx(&c));
+    SSDR_TRY(ctx_order(c, (cudaStream_t)stream));
     cudaStream_t s = (cudaStream_t)stream;
     SSDR_TRY(c->ws[grid::WS_META].reserve(sizeof(grid::Meta)));
     grid::Meta* meta = c->ws[grid::WS_META].as<grid::Meta>();
@@ -1268,6 +1271,7 @@ int ssdr_grid_point_layers_dev(const float* d_points, size_t N, const float* bbo
     SSDR_REQUIRE(sampleDl > 0.0f, SSDR_ERR_INVALID, "sampleDl must be positive");
     Ctx* c;
     SSDR_TRY(get_ctx(&c));
+    SSDR_TRY(ctx_order(c, (cudaStream_t)stream));
     cudaStream_t s = (cudaStream_t)stream;
     SSDR_TRY(c->ws[grid::WS_META].reserve(sizeof(grid::Meta)));
     grid::Meta* meta = c->ws[grid::WS_META].as<grid::Meta>();

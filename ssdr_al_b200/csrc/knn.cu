@@ -1121,7 +1121,7 @@ static int pyramid_dev(Ctx* c, cudaStream_t s, const float* d_points, size_t B, 
         ac.reuse = false;
         SSDR_TRY((run_dev<long long>(c, s, level[l + 1], B, n[l + 1], level[l], n[l], 1, d_up[l], nullptr, nullptr, &ac)));
     }
-    return SSDR_OK;
+    return ctx_mark_async(c, s);  // the call returns with its work in flight: later calls are ordered behind it
 }
 
 }  // namespace knn
@@ -1134,6 +1134,7 @@ int ssdr_knn_pyramid_dev(const float* d_points, size_t batch_size, size_t npts, 
                          size_t K, int64_t* const* d_neigh, int64_t* const* d_up, void* stream) {
     Ctx* c;
     SSDR_TRY(get_ctx(&c));
+    SSDR_TRY(ctx_order(c, (cudaStream_t)stream));
     return knn::pyramid_dev(c, (cudaStream_t)stream, d_points, batch_size, npts, ratios, n_levels, K,
                             reinterpret_cast<long long* const*>(d_neigh), reinterpret_cast<long long* const*>(d_up));
 }
@@ -1141,6 +1142,7 @@ unsigned long long ssdr_knn_pyramid_launches(void) { return knn::g_last_launches
 int ssdr_knn_status(void* stream) {
     Ctx* c;
     SSDR_TRY(get_ctx(&c));
+    SSDR_TRY(ctx_order(c, (cudaStream_t)stream));
     cudaStream_t s = (cudaStream_t)stream;
     unsigned* w = nullptr;
     SSDR_TRY(knn::async_status_word(c, s, &w));
@@ -1168,6 +1170,7 @@ int ssdr_knn_batch_dev(const float* d_points, size_t batch_size, size_t npts, co
                        size_t K, int64_t* d_indices, void* stream, ssdr_knn_stats* stats) {
     Ctx* c;
     SSDR_TRY(get_ctx(&c));
+    SSDR_TRY(ctx_order(c, (cudaStream_t)stream));
     return knn::run_dev<long long>(c, (cudaStream_t)stream, d_points, batch_size, npts, d_queries,
                                    nqueries, K, reinterpret_cast<long long*>(d_indices), stats);
 }
@@ -1270,6 +1273,7 @@ int ssdr_knn_batch_dev_i32(const float* d_points, size_t batch_size, size_t npts
                            size_t nqueries, size_t K, int32_t* d_indices, void* stream, ssdr_knn_stats* stats) {
     Ctx* c;
     SSDR_TRY(get_ctx(&c));
+    SSDR_TRY(ctx_order(c, (cudaStream_t)stream));
     return knn::run_dev<int>(c, (cudaStream_t)stream, d_points, batch_size, npts, d_queries,
                              nqueries, K, d_indices, stats);
 }

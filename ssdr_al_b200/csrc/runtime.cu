@@ -54,6 +54,7 @@ Ctx::~Ctx() {
     for (int i = 0; i < WS_SLOTS; ++i) ws[i].release();
     if (ev) cudaEventDestroy(ev);
     if (ev_main) cudaEventDestroy(ev_main);
+    if (ev_async) cudaEventDestroy(ev_async);
     for (int i = 0; i < 8; ++i)
         if (ev_chunk[i]) cudaEventDestroy(ev_chunk[i]);
     for (int i = 0; i < 5; ++i)
@@ -97,6 +98,7 @@ int get_ctx(Ctx** out) {
         SSDR_CHECK_CUDA(cudaEventCreateWithFlags(&c->ev_main, cudaEventDisableTiming));
         for (int i = 0; i < 8; ++i) SSDR_CHECK_CUDA(cudaEventCreateWithFlags(&c->ev_chunk[i], cudaEventDisableTiming));
         for (int i = 0; i < 5; ++i) SSDR_CHECK_CUDA(cudaEventCreate(&c->tev[i]));
+        SSDR_CHECK_CUDA(cudaEventCreateWithFlags(&c->ev_async, cudaEventDisableTiming));
         cudaMemPool_t pool;  // keep freed stream-ordered blocks cached instead of returning them to the driver
         if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
             unsigned long long keep = ~0ull;
@@ -107,7 +109,24 @@ int get_ctx(Ctx** out) {
         c->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
         c->device = dev;
     }
+    if (c->async_pending) {
+        if (cudaEventQuery(c->ev_async) == cudaSuccess) c->async_pending = false;
+        else if (c->async_stream != c->stream) SSDR_CHECK_CUDA(cudaStreamWaitEvent(c->stream, c->ev_async, 0));
+        cudaGetLastError();
+    }
     *out = c;
+    return SSDR_OK;
+}
+
+int ctx_order(Ctx* c, cudaStream_t s) {
+    if (c->async_pending && s != c->async_stream) SSDR_CHECK_CUDA(cudaStreamWaitEvent(s, c->ev_async, 0));
+    return SSDR_OK;
+}
+
+int ctx_mark_async(Ctx* c, cudaStream_t s) {
+    SSDR_CHECK_CUDA(cudaEventRecord(c->ev_async, s));
+    c->async_stream = s;
+    c->async_pending = true;
     return SSDR_OK;
 }
 

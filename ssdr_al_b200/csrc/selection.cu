@@ -1313,17 +1313,20 @@ int ssdr_fps_f64(const double* F, size_t N, size_t D, int32_t first, size_t n, i
 int ssdr_fps_f32_dev(const float* F, size_t N, size_t D, int32_t first, size_t n, int32_t* out, void* stream) {
     Ctx* c;
     SSDR_TRY(get_ctx(&c));
+    SSDR_TRY(ctx_order(c, (cudaStream_t)stream));
     return sel::fps_dev<float>(c, F, N, D, first, n, out, (cudaStream_t)stream, 0, N);
 }
 int ssdr_fps_f64_dev(const double* F, size_t N, size_t D, int32_t first, size_t n, int32_t* out, void* stream) {
     Ctx* c;
     SSDR_TRY(get_ctx(&c));
+    SSDR_TRY(ctx_order(c, (cudaStream_t)stream));
     return sel::fps_dev<double>(c, F, N, D, first, n, out, (cudaStream_t)stream, 0, N);
 }
 int ssdr_fps_f32_sharded(const float* d_F, size_t N, size_t D, size_t row_begin, size_t row_end, int32_t first,
                          size_t n_samples, int32_t* d_out, void* nccl_comm, void* stream) {
     Ctx* c;
     SSDR_TRY(get_ctx(&c));
+    SSDR_TRY(ctx_order(c, (cudaStream_t)stream));
     return sel::fps_sharded_dev(c, d_F, N, D, row_begin, row_end, first, n_samples, d_out, nccl_comm,
                                 (cudaStream_t)stream);
 }
@@ -1337,12 +1340,14 @@ int ssdr_kcenter_f32_dev(const float* X, size_t N, size_t D, const int64_t* sel_
                          int64_t* out, void* stream) {
     Ctx* c;
     SSDR_TRY(get_ctx(&c));
+    SSDR_TRY(ctx_order(c, (cudaStream_t)stream));
     return sel::kcenter_dev<float>(c, X, N, D, sel_, n_sel, n_pick, out, (cudaStream_t)stream, 0, N);
 }
 int ssdr_kcenter_f64_dev(const double* X, size_t N, size_t D, const int64_t* sel_, size_t n_sel, size_t n_pick,
                          int64_t* out, void* stream) {
     Ctx* c;
     SSDR_TRY(get_ctx(&c));
+    SSDR_TRY(ctx_order(c, (cudaStream_t)stream));
     return sel::kcenter_dev<double>(c, X, N, D, sel_, n_sel, n_pick, out, (cudaStream_t)stream, 0, N);
 }
 
@@ -1435,6 +1440,7 @@ int ssdr_fps_sharded_p2p(int dtype, const void* d_F, size_t N, size_t D, size_t 
     SSDR_REQUIRE(dtype == SSDR_F32 || dtype == SSDR_F64, SSDR_ERR_INVALID, "dtype must be SSDR_F32 or SSDR_F64");
     Ctx* c;
     SSDR_TRY(get_ctx(&c));
+    SSDR_TRY(ctx_order(c, (cudaStream_t)stream));
     sel::PeerGroup* g = (sel::PeerGroup*)group;
     cudaStream_t s = (cudaStream_t)stream;
     if (dtype == SSDR_F32)
@@ -1450,6 +1456,7 @@ int ssdr_kcenter_sharded_p2p(int dtype, const void* d_X, size_t N, size_t D, siz
     SSDR_REQUIRE(dtype == SSDR_F32 || dtype == SSDR_F64, SSDR_ERR_INVALID, "dtype must be SSDR_F32 or SSDR_F64");
     Ctx* c;
     SSDR_TRY(get_ctx(&c));
+    SSDR_TRY(ctx_order(c, (cudaStream_t)stream));
     sel::PeerGroup* g = (sel::PeerGroup*)group;
     cudaStream_t s = (cudaStream_t)stream;
     if (dtype == SSDR_F32)
