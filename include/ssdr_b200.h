@@ -43,6 +43,10 @@ typedef enum {
     SSDR_ERR_EMPTY = 6        /* grid subsampling produced no point (reference: RuntimeError("Error")) */
 } ssdr_status;
 
+/* element types of arguments that exist in float32 and float64 flavours */
+#define SSDR_F32 0
+#define SSDR_F64 1
+
 /* ---- runtime ------------------------------------------------------------------------------------ */
 const char* ssdr_last_error(void);
 int ssdr_version(void);               /* major*10000 + minor*100 + patch */
@@ -137,6 +141,9 @@ int ssdr_grid_fetch(void* handle, float* points_out, float* feats_out, int32_t* 
 int ssdr_grid_fetch_ex(void* handle, float* points_out, float* feats_out, int32_t* classes_out,
                        uint64_t* keys_out, int32_t* counts_out);
 int ssdr_grid_free(void* handle);
+/* Diagnostic only: %globaltimer marks (ns) of the calling thread's last subsampling call -- [0] start, [1] geometry,
+ * [2] keys, [3..10] end of radix pass k, [11] heads counted, [12] voxel starts written, [13] / [14] reduce start / end. */
+int ssdr_grid_debug_timing(uint64_t* marks16, int* key_bits);
 
 /* Device-resident variant: inputs are device pointers; results stay on the device inside the handle and can be
  * read back with ssdr_grid_fetch or borrowed with ssdr_grid_dev_ptrs (valid until ssdr_grid_free). */
@@ -196,6 +203,11 @@ int ssdr_chamfer_matrix_f64(const double* points, const int64_t* offsets, size_t
  * like the reference's loop); out[0] = trigger_idx, first arg-max on ties, strict '<' minimum update from 1e10. */
 int ssdr_superpoint_fps_f64(const double* points, const int64_t* offsets, size_t S, const double* centroids,
                             int32_t trigger_idx, size_t n_samples, int32_t* out);
+/* Same with the centroids in their own dtype (SSDR_F32 / SSDR_F64, defined below): the reference evaluates
+ * np.sum((centroids - current) ** 2, axis=-1) in the dtype of the centroid array -- float32 for ply coordinates -- and
+ * only widens when the float64 chamfer row is added (sampler2.py:68-73). */
+int ssdr_superpoint_fps(const double* points, const int64_t* offsets, size_t S, const void* centroids, int centroid_dtype,
+                        int32_t trigger_idx, size_t n_samples, int32_t* out);
 int ssdr_chamfer_matrix_f64_dev(const double* d_points, const int64_t* d_offsets, const int64_t* h_offsets, size_t S,
                                 double* d_out, void* stream);
 
@@ -217,8 +229,6 @@ int ssdr_fps_f32_sharded(const float* d_F, size_t N, size_t D, size_t row_begin,
  * A rank whose peers do not answer within SSDR_PEER_TIMEOUT_MS (default 20000) fails with SSDR_ERR_CUDA instead of
  * hanging.  max_ctas = 0 uses every SM (tests run several virtual ranks on one device with a smaller grid each,
  * connected with ssdr_peer_group_connect_local).  These calls synchronise `stream` before returning. */
-#define SSDR_F32 0
-#define SSDR_F64 1
 int ssdr_peer_group_create(int world, int rank, void** group);
 int ssdr_peer_group_export(void* group, void* handle64 /* 64 bytes: cudaIpcMemHandle_t */);
 int ssdr_peer_group_connect(void* group, const void* handles /* world x 64 bytes */);

@@ -48,6 +48,7 @@ SIGNATURES = {
     "ssdr_grid_fetch": [vp, vp, vp, vp],
     "ssdr_grid_fetch_ex": [vp, vp, vp, vp, vp, vp],
     "ssdr_grid_free": [vp],
+    "ssdr_grid_debug_timing": [vp, C.POINTER(C.c_int)],
     "ssdr_grid_subsample_typed": [vp, vp, C.c_int, vp, C.c_int, sz, sz, sz, C.c_float, C.c_int, C.POINTER(sz),
                                   C.POINTER(vp)],
     "ssdr_grid_subsample_dev": [vp, vp, vp, sz, sz, sz, C.c_float, C.c_int, vp, C.POINTER(sz), C.POINTER(vp)],
@@ -66,6 +67,7 @@ SIGNATURES = {
     "ssdr_kcenter_f64_dev": [vp, sz, sz, vp, sz, sz, vp, vp],
     "ssdr_chamfer_matrix_f64": [vp, vp, sz, vp],
     "ssdr_superpoint_fps_f64": [vp, vp, sz, vp, C.c_int32, sz, vp],
+    "ssdr_superpoint_fps": [vp, vp, sz, vp, C.c_int, C.c_int32, sz, vp],
     "ssdr_chamfer_matrix_f64_dev": [vp, vp, vp, sz, vp, vp],
     "ssdr_fps_f32_sharded": [vp, sz, sz, sz, sz, C.c_int32, sz, vp, vp, vp],
     "ssdr_peer_group_create": [C.c_int, C.c_int, C.POINTER(vp)],

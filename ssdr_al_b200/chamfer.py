@@ -28,7 +28,10 @@ def farthest_superpoint_sample(superpoint_list, superpoint_centroid_list, sample
     """sampler2.py:49-80: farthest point sampling over superpoints, distance = squared centroid distance + chamfer
     distance to the current pick.  Returns (sample_number,) int32 starting with trigger_idx."""
     sp_num = len(superpoint_list)
-    cents = np.ascontiguousarray(superpoint_centroid_list, dtype=np.float64).reshape(sp_num, 3)
+    # the squared centroid distance is evaluated in the centroids' own dtype, like np.sum((cents - cur) ** 2, -1) does
+    # (sampler2.py:68-69): float32 ply coordinates stay float32 until the float64 chamfer row is added
+    cents = np.asarray(superpoint_centroid_list)
+    cents = np.ascontiguousarray(cents if cents.dtype == np.float32 else cents.astype(np.float64)).reshape(sp_num, 3)
     aligned = [np.asarray(superpoint_list[i] - superpoint_centroid_list[i], dtype=np.float64).reshape(-1, 3)
                for i in range(sp_num)]
     offsets = np.zeros(sp_num + 1, np.int64)
@@ -37,6 +40,7 @@ def farthest_superpoint_sample(superpoint_list, superpoint_centroid_list, sample
         raise RuntimeError("ssdr_al_b200.chamfer.farthest_superpoint_sample: no or empty superpoints")
     pts = np.ascontiguousarray(np.concatenate(aligned, axis=0))
     out = np.zeros(int(sample_number), np.int32)
-    _lib.check(_lib.lib().ssdr_superpoint_fps_f64(_lib.ptr(pts), _lib.ptr(offsets), sp_num, _lib.ptr(cents),
-                                                  int(trigger_idx), int(sample_number), _lib.ptr(out)))
+    _lib.check(_lib.lib().ssdr_superpoint_fps(_lib.ptr(pts), _lib.ptr(offsets), sp_num, _lib.ptr(cents),
+                                              0 if cents.dtype == np.float32 else 1, int(trigger_idx),
+                                              int(sample_number), _lib.ptr(out)))
     return out

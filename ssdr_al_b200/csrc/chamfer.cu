@@ -24,7 +24,9 @@ constexpr int CT = 256;          // threads per block
 constexpr int PA = 4;            // source points per thread and pass
 constexpr int TB = 1024;         // target points per shared-memory tile
 constexpr int MAX_LEAVES = 1024; // pairwise-sum leaves per source cloud (<= 128 values each, >= 57 once split)
-constexpr unsigned MAX_CLOUD = 50000;
+// number of pairwise-sum leaves of n values is at most n / LEAF_MIN + 2 (a split leaf holds >= 57 values)
+constexpr unsigned LEAF_MIN = 57;
+__host__ __device__ inline size_t leaf_slots(size_t n) { return n / LEAF_MIN + 2; }
 
 // numpy's pairwise_sum for n <= 128 (loops_utils.h.src: @TYPE@_pairwise_sum)
 __device__ double leaf_sum(const double* a, unsigned n) {
@@ -53,9 +55,11 @@ struct Frame {
     double left;
 };
 
-// Walks pairwise_sum's recursion over [0, n).  With sums == nullptr it only records the leaves (lo, len); otherwise it
-// consumes the leaf sums in the same left-to-right order and returns the total.
-__device__ double walk(unsigned n, unsigned* leaf_lo, unsigned* leaf_n, unsigned* n_leaves, const double* sums) {
+// Walks pairwise_sum's recursion over [0, n).  With sums == nullptr it only records the leaves (lo, len) number
+// first .. first + MAX_LEAVES - 1 (a window: the tables live in shared memory, a large cloud has more leaves than that);
+// otherwise it consumes the leaf sums in the same left-to-right order and returns the total.
+__device__ double walk(unsigned n, unsigned* leaf_lo, unsigned* leaf_n, unsigned* n_leaves, const double* sums,
+                       unsigned first = 0) {
     Frame st[40];
     int sp = 0;
     unsigned next = 0;
@@ -65,9 +69,9 @@ __device__ double walk(unsigned n, unsigned* leaf_lo, unsigned* leaf_n, unsigned
         Frame& f = st[sp - 1];
         if (f.n <= 128u) {
             if (sums) ret = sums[next];
-            else if (next < (unsigned)MAX_LEAVES) {
-                leaf_lo[next] = f.lo;
-                leaf_n[next] = f.n;
+            else if (leaf_lo && next >= first && next - first < (unsigned)MAX_LEAVES) {
+                leaf_lo[next - first] = f.lo;
+                leaf_n[next - first] = f.n;
             }
             ++next;
             --sp;
@@ -117,8 +121,10 @@ struct PairSmem {
 
 // mean over the points of cloud a of the distance to the nearest point of cloud b (whole block; every thread returns
 // the value).  `mins` is the block's private scratch of na doubles; sm.lo / sm.n / sm.nleaf hold the leaf layout of na.
+// `big_sums`: leaf_slots(na) doubles of global scratch, used when the cloud has more leaves than the shared table.
 __device__ double directed_mean(const double* __restrict__ pts, unsigned long long a0, unsigned na,
-                                unsigned long long b0, unsigned nb, double* __restrict__ mins, PairSmem& sm) {
+                                unsigned long long b0, unsigned nb, double* __restrict__ mins, PairSmem& sm,
+                                double* __restrict__ big_sums) {
     for (unsigned k0 = 0; k0 < na; k0 += CT * PA) {
         const int pu = (int)min((unsigned)PA, (na - k0 + CT - 1) / CT);
         double ax[PA], ay[PA], az[PA], best[PA];
@@ -157,10 +163,19 @@ __device__ double directed_mean(const double* __restrict__ pts, unsigned long lo
     }
     __syncthreads();  // mins complete (global writes of this block are visible to it after the barrier)
     const unsigned nleaf = sm.nleaf;
-    for (unsigned l = threadIdx.x; l < nleaf && l < (unsigned)MAX_LEAVES; l += CT) sm.sum[l] = leaf_sum(mins + sm.lo[l], sm.n[l]);
-    __syncthreads();
+    const bool big = nleaf > (unsigned)MAX_LEAVES;  // the leaf table is then filled window by window
+    double* sums = big ? big_sums : sm.sum;
+    for (unsigned first = 0; first < nleaf; first += MAX_LEAVES) {
+        if (big) {
+            if (threadIdx.x == 0) walk(na, sm.lo, sm.n, nullptr, nullptr, first);
+            __syncthreads();
+        }
+        const unsigned cnt = min((unsigned)MAX_LEAVES, nleaf - first);
+        for (unsigned l = threadIdx.x; l < cnt; l += CT) sums[first + l] = leaf_sum(mins + sm.lo[l], sm.n[l]);
+        __syncthreads();
+    }
     __shared__ double s_mean;
-    if (threadIdx.x == 0) s_mean = __ddiv_rn(walk(na, nullptr, nullptr, nullptr, sm.sum), (double)na);
+    if (threadIdx.x == 0) s_mean = __ddiv_rn(walk(na, nullptr, nullptr, nullptr, sums), (double)na);
     __syncthreads();
     const double r = s_mean;
     __syncthreads();  // the next pair overwrites mins, sm.sum and s_mean
@@ -169,7 +184,7 @@ __device__ double directed_mean(const double* __restrict__ pts, unsigned long lo
 
 __global__ void __launch_bounds__(CT) directed_kernel(const double* __restrict__ pts, const long long* __restrict__ off,
                                                       unsigned S, unsigned G, unsigned long long T,
-                                                      double* __restrict__ scratch /* [G][T] */,
+                                                      double* __restrict__ scratch /* [G][T] mins, then [G][leaf area] */,
                                                       double* __restrict__ A /* [S][S]: A[a][b] = mean_a min_b */) {
     __shared__ PairSmem sm;
     const unsigned a = blockIdx.x, g = blockIdx.y;
@@ -177,6 +192,9 @@ __global__ void __launch_bounds__(CT) directed_kernel(const double* __restrict__
     const unsigned na = (unsigned)(off[a + 1] - off[a]);
     if (na == 0) return;
     double* mins = scratch + (size_t)g * T + a0;
+    // leaf sums of a large cloud: block (a, g) owns leaf_slots(na) doubles at a0 / LEAF_MIN + 2a inside g's leaf area
+    const size_t leaf_area = (size_t)(T / LEAF_MIN) + 2 * (size_t)S + 2;
+    double* big_sums = scratch + (size_t)G * T + (size_t)g * leaf_area + (size_t)(a0 / LEAF_MIN) + 2 * (size_t)a;
     if (threadIdx.x == 0) walk(na, sm.lo, sm.n, &sm.nleaf, nullptr);  // the leaf layout depends on na only
     __syncthreads();
     for (unsigned b = g; b < S; b += G) {
@@ -184,7 +202,7 @@ __global__ void __launch_bounds__(CT) directed_kernel(const double* __restrict__
         const unsigned long long b0 = (unsigned long long)off[b];
         const unsigned nb = (unsigned)(off[b + 1] - off[b]);
         if (nb == 0) continue;
-        const double m = directed_mean(pts, a0, na, b0, nb, mins, sm);
+        const double m = directed_mean(pts, a0, na, b0, nb, mins, sm, big_sums);
         if (threadIdx.x == 0) A[(size_t)a * S + b] = m;
     }
 }
@@ -196,7 +214,8 @@ __global__ void __launch_bounds__(CT) directed_kernel(const double* __restrict__
 // kernels in device memory, so the whole loop is enqueued without a host round trip.
 __global__ void __launch_bounds__(CT) row_kernel(const double* __restrict__ pts, const long long* __restrict__ off, unsigned S,
                                                  const int* __restrict__ picks, unsigned step, unsigned long long T,
-                                                 unsigned nmax, double* __restrict__ scratch /* [T] + [S][nmax] */,
+                                                 unsigned nmax,
+                                                 double* __restrict__ scratch /* [T] + [S][nmax] + [S][leaf_slots(nmax)] */,
                                                  double* __restrict__ row) {
     __shared__ PairSmem sm;
     const unsigned i = blockIdx.x;
@@ -209,25 +228,36 @@ __global__ void __launch_bounds__(CT) row_kernel(const double* __restrict__ pts,
     const unsigned ni = (unsigned)(off[i + 1] - off[i]), nc = (unsigned)(off[c + 1] - off[c]);
     if (threadIdx.x == 0) walk(ni, sm.lo, sm.n, &sm.nleaf, nullptr);
     __syncthreads();
-    const double av1 = directed_mean(pts, i0, ni, c0, nc, scratch + i0, sm);                      // :18, :20
+    double* big_sums = scratch + T + (size_t)S * nmax + (size_t)i * leaf_slots(nmax);
+    const double av1 = directed_mean(pts, i0, ni, c0, nc, scratch + i0, sm, big_sums);                      // :18, :20
     if (threadIdx.x == 0) walk(nc, sm.lo, sm.n, &sm.nleaf, nullptr);
     __syncthreads();
-    const double av2 = directed_mean(pts, c0, nc, i0, ni, scratch + T + (size_t)i * nmax, sm);    // :19, :21
+    const double av2 = directed_mean(pts, c0, nc, i0, ni, scratch + T + (size_t)i * nmax, sm, big_sums);    // :19, :21
     if (threadIdx.x == 0) row[i] = __dadd_rn(av1, av2);
 }
 
-__global__ void __launch_bounds__(1024) step_kernel(const double* __restrict__ cent, unsigned S, const double* __restrict__ row,
+// squared centroid distance in the centroids' OWN dtype (the caller's float32 ply coordinates stay float32 through
+// `np.sum((cents - cur) ** 2, axis=-1)`, sampler2.py:69; only np.add with the float64 chamfer row widens the result)
+__device__ __forceinline__ double centroid_sqdist(const double* c, unsigned i, double cx, double cy, double cz) {
+    const double dx = __dsub_rn(c[3 * i], cx), dy = __dsub_rn(c[3 * i + 1], cy), dz = __dsub_rn(c[3 * i + 2], cz);
+    return __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));  // np.sum of 3: sequential
+}
+__device__ __forceinline__ double centroid_sqdist(const float* c, unsigned i, float cx, float cy, float cz) {
+    const float dx = __fsub_rn(c[3 * i], cx), dy = __fsub_rn(c[3 * i + 1], cy), dz = __fsub_rn(c[3 * i + 2], cz);
+    return (double)__fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+}
+
+template <typename CT_>
+__global__ void __launch_bounds__(1024) step_kernel(const CT_* __restrict__ cent, unsigned S, const double* __restrict__ row,
                                                     double* __restrict__ distance, int* __restrict__ picks, unsigned step) {
     __shared__ double s_d[32];
     __shared__ unsigned s_i[32];
     const unsigned c = (unsigned)picks[step];
-    const double cx = cent[3 * c], cy = cent[3 * c + 1], cz = cent[3 * c + 2];
+    const CT_ cx = cent[3 * c], cy = cent[3 * c + 1], cz = cent[3 * c + 2];
     double bd = -INFINITY;
     unsigned bi = 0xFFFFFFFFu;
     for (unsigned i = threadIdx.x; i < S; i += blockDim.x) {
-        const double dx = __dsub_rn(cent[3 * i], cx), dy = __dsub_rn(cent[3 * i + 1], cy), dz = __dsub_rn(cent[3 * i + 2], cz);
-        // np.sum(.., axis=-1) over three values: sequential adds
-        const double e = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+        const double e = centroid_sqdist(cent, i, cx, cy, cz);
         const double d = __dadd_rn(e, row[i]);
         double cur = distance[i];
         if (d < cur) {
@@ -283,14 +313,15 @@ static int run_dev(Ctx* c, cudaStream_t s, const double* d_pts, const long long*
     const size_t T = (size_t)h_off[S];
     for (size_t i = 0; i < S; ++i) {
         SSDR_REQUIRE(h_off[i + 1] >= h_off[i], SSDR_ERR_INVALID, "offsets must not decrease");
-        SSDR_REQUIRE((size_t)(h_off[i + 1] - h_off[i]) <= MAX_CLOUD, SSDR_ERR_UNSUPPORTED,
-                     "cloud %zu has more than %u points", i, MAX_CLOUD);
+        SSDR_REQUIRE((size_t)(h_off[i + 1] - h_off[i]) < 0xFFFFFFFFull, SSDR_ERR_UNSUPPORTED,
+                     "cloud %zu has more than 2^32-2 points", i);
     }
     unsigned G = (unsigned)((4 * (size_t)c->sm_count + S - 1) / S);
     if (G < 1) G = 1;
     if (G > S) G = (unsigned)S;
     SSDR_TRY(c->ws[WS_DIR].reserve(S * S * sizeof(double)));
-    SSDR_TRY(c->ws[WS_SCRATCH].reserve((size_t)G * (T ? T : 1) * sizeof(double)));
+    const size_t leaf_area = T / LEAF_MIN + 2 * S + 2;  // see directed_kernel
+    SSDR_TRY(c->ws[WS_SCRATCH].reserve((size_t)G * ((T ? T : 1) + leaf_area) * sizeof(double)));
     double* A = c->ws[WS_DIR].as<double>();
     SSDR_CHECK_CUDA(cudaMemsetAsync(A, 0, S * S * sizeof(double), s));
     if (T) {
@@ -304,7 +335,7 @@ static int run_dev(Ctx* c, cudaStream_t s, const double* d_pts, const long long*
 }
 
 static int run_superpoint_fps(Ctx* c, cudaStream_t s, const double* d_pts, const long long* d_off, const long long* h_off,
-                              size_t S, const double* d_cent, int trigger, size_t n_samples, int* d_picks) {
+                              size_t S, const void* d_cent, bool cent_f32, int trigger, size_t n_samples, int* d_picks) {
     SSDR_REQUIRE(S >= 1 && n_samples >= 1, SSDR_ERR_INVALID, "no clouds or no samples");
     SSDR_REQUIRE(trigger >= 0 && (size_t)trigger < S, SSDR_ERR_INVALID, "trigger_idx out of range");
     const size_t T = (size_t)h_off[S];
@@ -312,12 +343,13 @@ static int run_superpoint_fps(Ctx* c, cudaStream_t s, const double* d_pts, const
     for (size_t i = 0; i < S; ++i) {
         SSDR_REQUIRE(h_off[i + 1] > h_off[i], SSDR_ERR_INVALID, "empty or negative-size cloud %zu", i);
         const size_t n = (size_t)(h_off[i + 1] - h_off[i]);
-        SSDR_REQUIRE(n <= MAX_CLOUD, SSDR_ERR_UNSUPPORTED, "cloud %zu has more than %u points", i, MAX_CLOUD);
+        SSDR_REQUIRE(n < 0xFFFFFFFFull, SSDR_ERR_UNSUPPORTED, "cloud %zu has more than 2^32-2 points", i);
         nmax = n > nmax ? n : nmax;
     }
-    SSDR_REQUIRE((T + S * nmax) * sizeof(double) <= ((size_t)8 << 30), SSDR_ERR_UNSUPPORTED,
-                 "scratch for %zu clouds of up to %zu points exceeds 8 GB", S, nmax);
-    SSDR_TRY(c->ws[WS_SCRATCH].reserve((T + S * nmax) * sizeof(double)));
+    const size_t scratch_doubles = T + S * nmax + S * leaf_slots(nmax);
+    SSDR_REQUIRE(scratch_doubles * sizeof(double) <= ((size_t)64 << 30), SSDR_ERR_UNSUPPORTED,
+                 "scratch for %zu clouds of up to %zu points exceeds 64 GB", S, nmax);
+    SSDR_TRY(c->ws[WS_SCRATCH].reserve(scratch_doubles * sizeof(double)));
     SSDR_TRY(c->ws[WS_DIR].reserve(2 * S * sizeof(double)));
     double* row = c->ws[WS_DIR].as<double>();
     double* distance = row + S;
@@ -327,7 +359,10 @@ static int run_superpoint_fps(Ctx* c, cudaStream_t s, const double* d_pts, const
     for (size_t st = 0; st + 1 < n_samples; ++st) {
         row_kernel<<<(unsigned)S, CT, 0, s>>>(d_pts, d_off, (unsigned)S, d_picks, (unsigned)st, (unsigned long long)T,
                                              (unsigned)nmax, c->ws[WS_SCRATCH].as<double>(), row);
-        step_kernel<<<1, 1024, 0, s>>>(d_cent, (unsigned)S, row, distance, d_picks, (unsigned)st);
+        if (cent_f32)
+            step_kernel<float><<<1, 1024, 0, s>>>((const float*)d_cent, (unsigned)S, row, distance, d_picks, (unsigned)st);
+        else
+            step_kernel<double><<<1, 1024, 0, s>>>((const double*)d_cent, (unsigned)S, row, distance, d_picks, (unsigned)st);
     }
     SSDR_CHECK_CUDA(cudaGetLastError());
     return SSDR_OK;
@@ -356,9 +391,12 @@ int ssdr_chamfer_matrix_f64(const double* points, const int64_t* offsets, size_t
     return d2h_sync(c, out, c->ws[chamfer::WS_OUT].p, S * S * sizeof(double), c->stream);
 }
 
-int ssdr_superpoint_fps_f64(const double* points, const int64_t* offsets, size_t S, const double* centroids,
-                            int32_t trigger_idx, size_t n_samples, int32_t* out) {
+int ssdr_superpoint_fps(const double* points, const int64_t* offsets, size_t S, const void* centroids, int centroid_dtype,
+                        int32_t trigger_idx, size_t n_samples, int32_t* out) {
     SSDR_REQUIRE(points && offsets && centroids && out, SSDR_ERR_INVALID, "NULL pointer");
+    SSDR_REQUIRE(centroid_dtype == SSDR_F32 || centroid_dtype == SSDR_F64, SSDR_ERR_INVALID,
+                 "centroid_dtype must be SSDR_F32 or SSDR_F64");
+    const size_t csize = centroid_dtype == SSDR_F32 ? sizeof(float) : sizeof(double);
     SSDR_REQUIRE(S >= 1 && offsets[0] == 0, SSDR_ERR_INVALID, "offsets must start at 0 and hold S + 1 entries");
     Ctx* c;
     SSDR_TRY(get_ctx(&c));
@@ -366,16 +404,20 @@ int ssdr_superpoint_fps_f64(const double* points, const int64_t* offsets, size_t
     SSDR_TRY(c->ws[chamfer::WS_PTS].reserve((T ? T : 1) * 3 * sizeof(double)));
     SSDR_TRY(c->ws[chamfer::WS_OFF].reserve((S + 1) * sizeof(long long)));
     SSDR_TRY(c->ws[chamfer::WS_OUT].reserve(S * 3 * sizeof(double) + (n_samples + 1) * sizeof(int)));
-    double* d_cent = c->ws[chamfer::WS_OUT].as<double>();
-    int* d_picks = reinterpret_cast<int*>(d_cent + S * 3);
+    void* d_cent = c->ws[chamfer::WS_OUT].p;
+    int* d_picks = reinterpret_cast<int*>(c->ws[chamfer::WS_OUT].as<double>() + S * 3);
     SSDR_TRY(h2d(c, c->ws[chamfer::WS_PTS].p, points, T * 3 * sizeof(double), c->stream));
     SSDR_TRY(h2d(c, c->ws[chamfer::WS_OFF].p, offsets, (S + 1) * sizeof(long long), c->stream));
-    SSDR_TRY(h2d(c, d_cent, centroids, S * 3 * sizeof(double), c->stream));
+    SSDR_TRY(h2d(c, d_cent, centroids, S * 3 * csize, c->stream));
     SSDR_TRY(chamfer::run_superpoint_fps(c, c->stream, c->ws[chamfer::WS_PTS].as<double>(),
                                          c->ws[chamfer::WS_OFF].as<long long>(),
-                                         reinterpret_cast<const long long*>(offsets), S, d_cent, trigger_idx, n_samples,
-                                         d_picks));
+                                         reinterpret_cast<const long long*>(offsets), S, d_cent,
+                                         centroid_dtype == SSDR_F32, trigger_idx, n_samples, d_picks));
     return d2h_sync(c, out, d_picks, n_samples * sizeof(int), c->stream);
+}
+int ssdr_superpoint_fps_f64(const double* points, const int64_t* offsets, size_t S, const double* centroids,
+                            int32_t trigger_idx, size_t n_samples, int32_t* out) {
+    return ssdr_superpoint_fps(points, offsets, S, centroids, SSDR_F64, trigger_idx, n_samples, out);
 }
 
 int ssdr_chamfer_matrix_f64_dev(const double* d_points, const int64_t* d_offsets, const int64_t* h_offsets, size_t S,

@@ -42,6 +42,9 @@ struct Meta {
     unsigned long long M;
     int cur;                     // which ping-pong pair holds the sorted (key, index) arrays
     int pad;
+    // %globaltimer marks (ns) of CTA 0: [0] start, [1] geometry, [2] keys, [3..10] end of radix pass k, [11] heads
+    // counted, [12] starts written, [13] reduce start (first CTA), [14] reduce end (last CTA)
+    unsigned long long tmark[16];
 };
 
 enum { WS_META = 0, WS_PART = 1, WS_KEYS = 2, WS_KEYS2 = 3, WS_IDX = 4, WS_IDX2 = 5, WS_TEMP = 6, WS_STARTS = 7,
@@ -163,6 +166,7 @@ __global__ void setup_kernel(const float* __restrict__ partials, int nparts, flo
         m.M = 0;
         m.cur = 0;
         m.pad = 0;
+        for (int k = 0; k < 16; ++k) m.tmark[k] = 0;
         *meta = m;
     }
 }
@@ -203,6 +207,11 @@ struct SortParams {
     unsigned* barrier;          // monotonic arrival counter, zero at launch
 };
 
+__device__ __forceinline__ unsigned long long gtimer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;\n" : "=l"(t));
+    return t;
+}
 __device__ __forceinline__ unsigned ld_acquire_gpu_u32(const unsigned* p) {
     unsigned v;
     asm volatile("ld.acquire.gpu.global.u32 %0, [%1];\n" : "=r"(v) : "l"(p) : "memory");
@@ -287,9 +296,13 @@ __global__ void __launch_bounds__(PA_THREADS, 1) sort_kernel(const SortParams p)
     __shared__ Geo s_geo;
     __shared__ unsigned long long s_n, s_maxkey;
     __shared__ unsigned s_bar_target;
+    __shared__ unsigned long long s_mark[16];
     const unsigned t = threadIdx.x, lane = t & 31, warp = t >> 5;
     const unsigned G = gridDim.x, c = blockIdx.x;
     if (t == 0) s_bar_target = 0;
+    if (t < 16) s_mark[t] = 0;
+    __syncthreads();
+    if (t == 0) s_mark[0] = gtimer_ns();
     const bool aligned = (reinterpret_cast<unsigned long long>(p.pts) & 15ull) == 0;
     // contiguous chunk of all N points for this CTA (tile aligned)
     const unsigned long long perN = (((p.N + G - 1) / G) + PA_THREADS - 1) / PA_THREADS * PA_THREADS;
@@ -356,6 +369,7 @@ __global__ void __launch_bounds__(PA_THREADS, 1) sort_kernel(const SortParams p)
     __syncthreads();
     const Geo geo = s_geo;
     const bool slab = p.slab_axis >= 0;
+    if (t == 0) s_mark[1] = gtimer_ns();
 
     // ---- P1: keys (slab members compacted in input order), digit histogram of the first pass, largest key
     unsigned long long member_base = cb;  // where this CTA's first (member) point goes
@@ -483,6 +497,7 @@ __global__ void __launch_bounds__(PA_THREADS, 1) sort_kernel(const SortParams p)
     }
     const unsigned long long n = s_n;
     const int key_bits = dev_bits_for_value(s_maxkey);
+    if (t == 0) s_mark[2] = gtimer_ns();
     if (c == 0 && t == 0) {
         Meta m;
         for (int d = 0; d < 3; ++d) {
@@ -501,6 +516,7 @@ __global__ void __launch_bounds__(PA_THREADS, 1) sort_kernel(const SortParams p)
         m.M = 0;
         m.cur = 0;
         m.pad = 0;
+        for (int k = 0; k < 16; ++k) m.tmark[k] = s_mark[k];
         *p.meta = m;
     }
     if (n == 0) return;  // an empty slab (uniform decision: every CTA leaves)
@@ -592,6 +608,7 @@ __global__ void __launch_bounds__(PA_THREADS, 1) sort_kernel(const SortParams p)
         }
         cur ^= 1;
         grid_barrier(p.barrier, G, &s_bar_target);
+        if (t == 0 && shift / 8 < 8) s_mark[3 + shift / 8] = gtimer_ns();
     }
 
     // ---- P3: segment heads -> voxel starts
@@ -637,6 +654,7 @@ __global__ void __launch_bounds__(PA_THREADS, 1) sort_kernel(const SortParams p)
     }
     unsigned long long vbase = s_maxkey;
     const unsigned long long M = s_n;
+    if (t == 0) s_mark[11] = gtimer_ns();
     for (unsigned long long b = sb; b < se; b += PA_THREADS) {
         const unsigned long long i = b + t;
         const bool head = i < se && (i == 0 || __ldcg(ks + i) != __ldcg(ks + i - 1));
@@ -649,6 +667,8 @@ __global__ void __launch_bounds__(PA_THREADS, 1) sort_kernel(const SortParams p)
         p.starts[M] = (unsigned)n;
         p.meta->M = M;
         p.meta->cur = cur;
+        s_mark[12] = gtimer_ns();
+        for (int k = 3; k < 13; ++k) p.meta->tmark[k] = s_mark[k];
     }
 }
 
@@ -779,6 +799,7 @@ __global__ void __launch_bounds__(RB_THREADS) reduce_kernel(const ReduceParams p
     __shared__ int s_labs[RB_GROUPS][LABEL_CAP], s_cnts[RB_GROUPS][LABEL_CAP];
     const unsigned long long M = p.meta->M;
     const int cur = p.meta->cur;
+    if (blockIdx.x == 0 && threadIdx.x == 0) p.meta->tmark[13] = gtimer_ns();
     const unsigned long long* keys = p.keys[cur];
     const unsigned* idx = p.idx[cur];
     const int tid = threadIdx.x, g = tid >> 3, l = tid & 7, lane = tid & 31;
@@ -881,6 +902,7 @@ __global__ void __launch_bounds__(RB_THREADS) reduce_kernel(const ReduceParams p
         }
     }
     if (overflow) p.meta->error = 2;
+    if (threadIdx.x == 0) atomicMax(&p.meta->tmark[14], gtimer_ns());
 }
 
 // ---- 7. reference row order: libstdc++ unordered_map<size_t,...> iteration order, epoch by epoch ----------------
@@ -1055,6 +1077,8 @@ static int geometry(Ctx* c, cudaStream_t s, const float* d_p, size_t N, float dl
     return SSDR_OK;
 }
 
+static thread_local Meta g_last_meta;  // of the calling thread's last run (ssdr_grid_debug_timing)
+
 struct Slab {
     int axis = -1;  // -1: whole cloud
     unsigned long long lo = 0, hi = 0;
@@ -1181,6 +1205,7 @@ static int run_dev(Ctx* c, cudaStream_t s, const Inputs& in, size_t N, size_t fd
         int rc = d2h_sync(c, &hm, meta, sizeof(Meta), s);
         if (rc != SSDR_OK) return fail(rc);
     }
+    g_last_meta = hm;
     if (hm.error == 2)
         return fail(set_error(SSDR_ERR_UNSUPPORTED, "more than %d distinct labels inside one voxel", LABEL_CAP));
     h->M = (size_t)hm.M;
@@ -1357,6 +1382,13 @@ int ssdr_grid_dev_ptrs(void* handle, const float** d_points, const float** d_fea
     if (d_points) *d_points = h->d_p;
     if (d_feats) *d_feats = h->d_f;
     if (d_classes) *d_classes = h->d_c;
+    return SSDR_OK;
+}
+
+int ssdr_grid_debug_timing(uint64_t* marks16, int* key_bits) {
+    SSDR_REQUIRE(marks16, SSDR_ERR_INVALID, "NULL pointer");
+    for (int k = 0; k < 16; ++k) marks16[k] = grid::g_last_meta.tmark[k];
+    if (key_bits) *key_bits = grid::g_last_meta.key_bits;
     return SSDR_OK;
 }
 

@@ -943,6 +943,7 @@ struct Launch {
     size_t smem = 0;
     void* fn = nullptr;
     bool lane_per_row = false;  // select32_kernel: second kernel argument is the tensor map
+    bool partial_grid = false;  // virtual ranks sharing one device (tests): several small grids must run side by side
     CUtensorMap tmap;
 };
 
@@ -998,7 +999,10 @@ static int configure32(Ctx* c, Launch<float>& L, const float* dF, size_t N) {
     if (!enc) return -1;  // no driver entry point: the caller falls back to the bulk-copy variant
     const Tunables tn = tunables();
     Params<float>& p = L.p;
-    int nw = tn.warps > 0 ? tn.warps : WARPS, nst = tn.stages > 0 ? tn.stages : 3;
+    // measured on B200 (tools/sweep_select.py, N = 500k): FPS is fastest with 8 warps x 4 stages (10.0 us/pick against
+    // 11.6 with 16 warps: fewer, longer streams), the fp64 dot products of k-center want 12 warps x 2 stages
+    int nw = tn.warps > 0 ? tn.warps : (MODE == MODE_FPS ? 8 : 12);
+    int nst = tn.stages > 0 ? tn.stages : (MODE == MODE_FPS ? 4 : 2);
     nw = nw < 1 ? 1 : (nw > WARPS ? WARPS : nw);
     nst = nst < 2 ? 2 : (nst > MAX_STAGES ? MAX_STAGES : nst);
     const size_t budget = (size_t)c->max_smem_optin - 1024;
@@ -1068,8 +1072,12 @@ static int configure(Ctx* c, Launch<T>& L, const T* dF, size_t N, size_t D) {
         groups = (int)(3072 / (4 * row_bytes));
         groups = groups < 1 ? 1 : (groups > 8 ? 8 : groups);
     }
-    if (bulk && tn.warps > 0) nw = tn.warps > WARPS ? WARPS : tn.warps;
-    if (bulk && tn.stages > 0) nst = tn.stages > MAX_STAGES ? MAX_STAGES : (tn.stages < 2 ? 2 : tn.stages);
+    if (bulk) {  // measured (tools/sweep_select.py): D = 256 FPS streams best with 8 warps x 2 stages (90 vs 103 us/pick)
+        if (D == 256 && MODE == MODE_FPS) nw = 8;
+        nst = 2;
+        if (tn.warps > 0) nw = tn.warps > WARPS ? WARPS : tn.warps;
+        if (tn.stages > 0) nst = tn.stages > MAX_STAGES ? MAX_STAGES : (tn.stages < 2 ? 2 : tn.stages);
+    }
     while (nst > 3 && need(groups, nst, nw) > budget) --nst;
     while (nw > 1 && need(groups, nst, nw) > budget) nw /= 2;
     while (nst > 2 && need(groups, nst, nw) > budget) --nst;
@@ -1115,7 +1123,11 @@ static int launch_steps(Launch<T>& L, int step_begin, int step_end, cudaStream_t
     // mailbox tags are step+1 and unique per launch range, but a previous call may have left equal tags behind
     SSDR_CHECK_CUDA(cudaMemsetAsync(L.p.cand, 0, (size_t)2 * L.grid * sizeof(Mailbox), s));
     void* args[] = {(void*)&L.p, (void*)&L.tmap};
-    SSDR_CHECK_CUDA(cudaLaunchCooperativeKernel(L.fn, dim3(L.grid), dim3(L.p.nwarps * 32), args, L.smem, s));
+    if (L.partial_grid)  // co-residency comes from the grids being small (the spin waits are bounded by the time-out);
+                         // cooperative launches of different streams do not overlap
+        SSDR_CHECK_CUDA(cudaLaunchKernel(L.fn, dim3(L.grid), dim3(L.p.nwarps * 32), args, L.smem, s));
+    else
+        SSDR_CHECK_CUDA(cudaLaunchCooperativeKernel(L.fn, dim3(L.grid), dim3(L.p.nwarps * 32), args, L.smem, s));
     return SSDR_OK;
 }
 
@@ -1126,7 +1138,10 @@ static int prepare(Ctx* c, Launch<T>& L, const T* dF, size_t N, size_t D, size_t
     SSDR_REQUIRE(N >= 1 && N < 0xFFFFFFFFull, SSDR_ERR_INVALID, "N=%zu out of range", N);
     SSDR_REQUIRE(D >= 1 && D <= 8192, SSDR_ERR_UNSUPPORTED, "feature dimension D=%zu not in [1, 8192]", D);
     SSDR_TRY((configure<T, MODE>(c, L, dF, N, D)));
-    if (max_ctas > 0 && max_ctas < L.grid) L.grid = max_ctas;
+    if (max_ctas > 0 && max_ctas < L.grid) {
+        L.grid = max_ctas;
+        L.partial_grid = true;
+    }
     Params<T>& p = L.p;
     p.row_begin = row_begin;
     p.row_end = row_end;
