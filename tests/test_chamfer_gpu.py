@@ -77,3 +77,39 @@ def test_superpoint_fps_vs_oracle(oracle):
     assert np.array_equal(S.chamfer.farthest_superpoint_sample(sps, cents, 25, 7),
                           oracle.farthest_superpoint_sample(sps, cents, 25, 7))
     assert np.array_equal(S.chamfer.farthest_superpoint_sample(sps, cents, 1, 5), np.array([5], np.int32))
+
+
+def test_superpoint_fps_float32_centroids(oracle):
+    """The real caller passes float32 centroids (ply coordinates, sampler2.py:563-577): the squared centroid distance is
+    then a float32 quantity (np.sum((cents - cur) ** 2, -1)) that is only widened by np.add with the float64 chamfer
+    row.  Near-ties between candidates are decided by that rounding, so the dtype has to be kept."""
+    import ssdr_al_b200 as S
+    rng = np.random.default_rng(21)
+    sps, cents = [], []
+    for n in [int(v) for v in rng.integers(5, 300, 80)]:
+        c = rng.random(3) * 30
+        p = (c + rng.normal(0, 0.25, (n, 3))).astype(np.float32)
+        sps.append(p)
+        cents.append(((p.min(0) + p.max(0)) / np.float32(2)).astype(np.float32))
+    cents32 = np.array(cents, dtype=np.float32)
+    want32 = oracle.farthest_superpoint_sample(sps, cents32, 40, 3)
+    assert np.array_equal(S.chamfer.farthest_superpoint_sample(sps, cents32, 40, 3), want32)
+    assert np.array_equal(S.chamfer.farthest_superpoint_sample(sps, list(cents32), 40, 3), want32)  # list of f32 rows
+    cents64 = cents32.astype(np.float64)
+    assert np.array_equal(S.chamfer.farthest_superpoint_sample(sps, cents64, 40, 3),
+                          oracle.farthest_superpoint_sample(sps, cents64, 40, 3))
+
+
+def test_chamfer_large_superpoint(oracle):
+    """A floor or a wall can hold far more points than the shared leaf table of the pairwise mean covers (57 values per
+    leaf at least, 1024 leaves): such clouds go through the windowed table; the reference has no size limit either."""
+    import ssdr_al_b200 as S
+    rng = np.random.default_rng(5)
+    big = (rng.random((70_001, 3)) * np.array([7.0, 5.0, 0.02])).astype(np.float32)
+    sps = [big] + [(rng.random(3) * 5 + rng.normal(0, 0.2, (n, 3))).astype(np.float32) for n in (40, 333, 1500)]
+    cents = np.array([(p.min(0).astype(np.float64) + p.max(0)) / 2.0 for p in sps])
+    got = S.chamfer.create_cd(sps, cents)
+    want = oracle.create_cd(sps, cents)
+    assert np.array_equal(got, want)
+    assert np.array_equal(S.chamfer.farthest_superpoint_sample(sps, cents, 4, 1),
+                          oracle.farthest_superpoint_sample(sps, cents, 4, 1))

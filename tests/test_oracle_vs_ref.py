@@ -62,3 +62,7 @@ def test_chamfer_and_superpoint_fps_live():
     np.testing.assert_allclose(O.create_cd(sps, cents), O.ref_create_cd(sps, cents), rtol=1e-12, atol=0)
     assert np.array_equal(O.farthest_superpoint_sample(sps, cents, 9, 2),
                           O.ref_farthest_superpoint_sample(sps, cents, 9, 2))
+    # float32 centroids, as the real caller passes them: the centroid term stays float32 in both
+    c32 = [np.asarray(c, dtype=np.float32) for c in cents]
+    assert np.array_equal(O.farthest_superpoint_sample(sps, c32, 9, 2),
+                          O.ref_farthest_superpoint_sample(sps, c32, 9, 2))
