@@ -166,9 +166,31 @@ int ssdr_grid_subsample_slab_dev(const float* d_points, const float* d_feats, co
                                  size_t fdim, size_t ldim, float sampleDl, int order, const float* bbox, int axis,
                                  unsigned long long layer_lo, unsigned long long layer_hi, void* stream,
                                  size_t* M_out, void** handle);
+/* The same into caller-owned device arrays of `capacity` >= N rows each (the voxel count is known only on the device, so
+ * the worst case of one voxel per point must fit): no handle, no allocation, ONE stream synchronisation (the read-back
+ * of *M_out).  Rows in ascending voxel key.  bbox nullable, axis == -1 = whole cloud (see ssdr_grid_subsample_slab_dev);
+ * d_keys_out / d_counts_out nullable. */
+int ssdr_grid_subsample_into_dev(const float* d_points, const float* d_feats, const int32_t* d_classes, size_t N,
+                                 size_t fdim, size_t ldim, float sampleDl, const float* bbox, int axis,
+                                 unsigned long long layer_lo, unsigned long long layer_hi, float* d_points_out,
+                                 float* d_feats_out, int32_t* d_classes_out, uint64_t* d_keys_out, int32_t* d_counts_out,
+                                 size_t capacity, void* stream, size_t* M_out);
 int ssdr_grid_bbox_dev(const float* d_points, size_t N, void* stream, float* bbox_out /* 6 floats, host */);
 int ssdr_grid_point_layers_dev(const float* d_points, size_t N, const float* bbox /* nullable */, float sampleDl,
                                int axis, int32_t* d_layers, void* stream, unsigned long long* n_layers_out);
+
+/* The exchange step of slab sharding when every rank starts with a row chunk of the cloud: ssdr_grid_layer_hist_dev
+ * counts this chunk's points per voxel layer (to be summed over the ranks and cut into balanced slabs by the caller),
+ * ssdr_grid_route_dev groups the chunk's rows by destination rank -- rank r owns the layers [bounds[r], bounds[r+1]) --
+ * with a stable device-side partition (input order kept inside every destination), ready for one all-to-all; it
+ * returns the number of rows per destination in counts_out (host).  bbox = corners of the WHOLE cloud. */
+int ssdr_grid_layer_hist_dev(const float* d_points, size_t N, const float* bbox, float sampleDl, int axis,
+                             unsigned long long* d_hist /* n_layers, device */, size_t n_layers, void* stream);
+int ssdr_grid_route_dev(const float* d_points, const float* d_feats, const int32_t* d_classes, size_t N, size_t fdim,
+                        size_t ldim, float sampleDl, const float* bbox, int axis,
+                        const unsigned long long* bounds /* world + 1, host */, int world, float* d_points_out,
+                        float* d_feats_out, int32_t* d_classes_out, unsigned long long* counts_out /* world, host */,
+                        void* stream);
 
 /* ---- farthest-feature sampling / k-center greedy ---------------------------------------------------- */
 /* FPS: out[0] = first; out[s+1] = argmax_i min_{t<=s} sum_j (F[i,j]-F[out[t],j])^2, first index on ties,

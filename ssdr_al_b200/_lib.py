@@ -55,8 +55,12 @@ SIGNATURES = {
     "ssdr_grid_dev_ptrs": [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)],
     "ssdr_grid_subsample_slab_dev": [vp, vp, vp, sz, sz, sz, C.c_float, C.c_int, vp, C.c_int, C.c_ulonglong,
                                      C.c_ulonglong, vp, C.POINTER(sz), C.POINTER(vp)],
+    "ssdr_grid_subsample_into_dev": [vp, vp, vp, sz, sz, sz, C.c_float, vp, C.c_int, C.c_ulonglong, C.c_ulonglong, vp, vp,
+                                     vp, vp, vp, sz, vp, C.POINTER(sz)],
     "ssdr_grid_bbox_dev": [vp, sz, vp, vp],
     "ssdr_grid_point_layers_dev": [vp, sz, vp, C.c_float, C.c_int, vp, vp, C.POINTER(C.c_ulonglong)],
+    "ssdr_grid_layer_hist_dev": [vp, sz, vp, C.c_float, C.c_int, vp, sz, vp],
+    "ssdr_grid_route_dev": [vp, vp, vp, sz, sz, sz, C.c_float, vp, C.c_int, vp, C.c_int, vp, vp, vp, vp, vp],
     "ssdr_fps_f32": [vp, sz, sz, C.c_int32, sz, vp],
     "ssdr_fps_f64": [vp, sz, sz, C.c_int32, sz, vp],
     "ssdr_fps_f32_dev": [vp, sz, sz, C.c_int32, sz, vp, vp],

@@ -47,8 +47,9 @@ struct Meta {
     unsigned long long tmark[16];
 };
 
+// slots 16.. belong to kdtree.cuh (its tree workspaces must survive between KNN calls): never used here
 enum { WS_META = 0, WS_PART = 1, WS_KEYS = 2, WS_KEYS2 = 3, WS_IDX = 4, WS_IDX2 = 5, WS_TEMP = 6, WS_STARTS = 7,
-       WS_IN_P = 9, WS_IN_F = 10, WS_IN_C = 11, WS_HASH = 12, WS_CMIN = 13, WS_SEL = 14, WS_RAW = 15, WS_CTL = 16 };
+       WS_CTL = 8, WS_IN_P = 9, WS_IN_F = 10, WS_IN_C = 11, WS_HASH = 12, WS_CMIN = 13, WS_HEADS = 14, WS_REC = 15 };
 
 constexpr int LABEL_CAP = 64;
 constexpr int MM_BLOCK = 256;
@@ -178,6 +179,46 @@ __global__ void point_layers_kernel(const float* __restrict__ pts, unsigned long
         f2u64(floorf(__fdiv_rn(__fsub_rn(__ldg(pts + 3 * i + axis), meta->origin[axis]), meta->dl)));
     layers[i] = layer < 0x7FFFFFFFull ? (int)layer : 0x7FFFFFFF;
 }
+// histogram of the voxel layers along one axis (slab balancing of a multi-GPU job): warp-aggregated atomics
+__global__ void layer_hist_kernel(const float* __restrict__ pts, unsigned long long N, const Meta* __restrict__ meta,
+                                  int axis, unsigned long long* __restrict__ hist, unsigned long long n_layers) {
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    const unsigned long long rounds = (N + stride - 1) / stride;
+    const float o = meta->origin[axis], dl = meta->dl;
+    for (unsigned long long r = 0; r < rounds; ++r) {
+        const unsigned long long i = r * stride + (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+        unsigned long long layer = ~0ull;
+        if (i < N) {
+            layer = f2u64(floorf(__fdiv_rn(__fsub_rn(__ldg(pts + 3 * i + axis), o), dl)));
+            if (layer >= n_layers) layer = n_layers - 1;
+        }
+        const unsigned peers = __match_any_sync(0xffffffffu, layer);
+        if (i < N && (peers & ((1u << (threadIdx.x & 31)) - 1u)) == 0) atomicAdd(&hist[layer], (unsigned long long)__popc(peers));
+    }
+}
+// destination rank of every point from its layer and the slab bounds (bounds[r] <= layer < bounds[r+1] -> r); written as
+// the sort key of a one-pass stable radix sort, together with the identity permutation; per-destination counts
+constexpr int MAX_ROUTE_WORLD = 64;
+struct RouteBounds {
+    unsigned long long b[MAX_ROUTE_WORLD + 1];
+    int world;
+};
+__global__ void route_key_kernel(const float* __restrict__ pts, unsigned long long N, const Meta* __restrict__ meta,
+                                 int axis, const RouteBounds rb, unsigned long long* __restrict__ keys,
+                                 unsigned* __restrict__ idx, unsigned long long* __restrict__ counts) {
+    const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned dest = 0xFFFFFFFFu;
+    if (i < N) {
+        const unsigned long long layer =
+            f2u64(floorf(__fdiv_rn(__fsub_rn(__ldg(pts + 3 * i + axis), meta->origin[axis]), meta->dl)));
+        dest = 0;
+        for (int r = 1; r < rb.world; ++r) dest += layer >= rb.b[r] ? 1u : 0u;  // bounds are non-decreasing
+        keys[i] = dest;
+        idx[i] = (unsigned)i;
+    }
+    const unsigned peers = __match_any_sync(0xffffffffu, dest);
+    if (i < N && (peers & ((1u << (threadIdx.x & 31)) - 1u)) == 0) atomicAdd(&counts[dest], (unsigned long long)__popc(peers));
+}
 __global__ void bbox_fill_kernel(float* partials, float a0, float a1, float a2, float b0, float b1, float b2) {
     partials[0] = a0; partials[1] = a1; partials[2] = a2;
     partials[3] = b0; partials[4] = b1; partials[5] = b2;
@@ -204,8 +245,11 @@ struct SortParams {
     unsigned long long* pmax;   // [G] largest key per CTA
     unsigned* cta_count;        // [G] slab members, later segment heads, per CTA
     unsigned* starts;           // [N + 1] voxel start offsets
+    unsigned* headmask;         // [N / 32 + 1] bit t of word c: sorted record 32c + t starts a voxel
+    unsigned* first_vid;        // [N / 32 + 1] voxel id of the first head inside chunk c (NO_HEAD if none)
     unsigned* barrier;          // monotonic arrival counter, zero at launch
 };
+constexpr unsigned NO_HEAD = 0xFFFFFFFFu;
 
 __device__ __forceinline__ unsigned long long gtimer_ns() {
     unsigned long long t;
@@ -661,6 +705,13 @@ __global__ void __launch_bounds__(PA_THREADS, 1) sort_kernel(const SortParams p)
         unsigned tt;
         const unsigned rank = block_excl_scan(head ? 1u : 0u, s_w, &tt);
         if (head) p.starts[vbase + rank] = (unsigned)i;
+        // a warp covers one aligned 32-record chunk: its head bitmap and the voxel id of its first head
+        const unsigned hb = __ballot_sync(0xffffffffu, head);
+        const unsigned fv = (unsigned)vbase + __shfl_sync(0xffffffffu, rank, hb ? __ffs((int)hb) - 1 : 0);
+        if (lane == 0 && i < se) {
+            p.headmask[i >> 5] = hb;
+            p.first_vid[i >> 5] = hb ? fv : NO_HEAD;
+        }
         vbase += tt;
     }
     if (c == 0 && t == 0) {
@@ -905,6 +956,171 @@ __global__ void __launch_bounds__(RB_THREADS) reduce_kernel(const ReduceParams p
     if (threadIdx.x == 0) atomicMax(&p.meta->tmark[14], gtimer_ns());
 }
 
+// ---- fast reduce (3 + fdim + ldim <= 32 columns, ldim <= 1): gather the sorted records, then segmented sequential sums --
+// gather_kernel: a pure permutation -- one thread per 32-bit word of the sorted record table rec[i][0..RS) =
+// (x, y, z, features..., label) of the point with the i-th smallest (key, index); coalesced writes, the reads gather.
+struct RecParams {
+    const float* pts;
+    const void* feats;
+    const void* cls;
+    int feat_u8, cls_u8;
+    int fdim, ldim, RS;
+    const unsigned* idx[2];
+    const Meta* meta;
+    float* rec;
+};
+__global__ void __launch_bounds__(256) gather_kernel(const RecParams p) {
+    const unsigned long long n = p.meta->n_sel;
+    const unsigned* idx = p.idx[p.meta->cur];
+    const unsigned long long total = n * (unsigned long long)p.RS;
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    for (unsigned long long w = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; w < total; w += stride) {
+        const unsigned long long i = w / (unsigned)p.RS;
+        const int col = (int)(w - i * (unsigned)p.RS);
+        const unsigned long long row = idx[i];
+        float v;
+        if (col < 3) v = __ldg(p.pts + 3ull * row + col);
+        else if (col < 3 + p.fdim) {
+            const unsigned long long o = row * (unsigned long long)p.fdim + (col - 3);
+            v = p.feat_u8 ? (float)__ldg(reinterpret_cast<const unsigned char*>(p.feats) + o)
+                          : __ldg(reinterpret_cast<const float*>(p.feats) + o);
+        } else {
+            const unsigned long long o = row * (unsigned long long)p.ldim + (col - 3 - p.fdim);
+            v = __int_as_float(p.cls_u8 ? (int)__ldg(reinterpret_cast<const unsigned char*>(p.cls) + o)
+                                        : __ldg(reinterpret_cast<const int*>(p.cls) + o));
+        }
+        p.rec[w] = v;
+    }
+}
+
+// segsum_kernel: eight lanes per 32-record chunk, lane = column.  A group owns the voxels whose FIRST record lies in its
+// chunk and follows the last of them into the next chunks until the next head.  Every lane loads its column of 32
+// consecutive records up front (32 independent loads in flight, 8 lanes x 4 bytes contiguous per record), then adds them
+// IN ORDER -- the per-voxel sequential sums of SampledData::update_* (grid_subsampling.h:42-79) -- closing a voxel at
+// every head bit.  The label column counts in a per-group table that keeps first-occurrence order.
+constexpr int SS_THREADS = 256;
+constexpr int SS_GROUPS = SS_THREADS / 8;
+struct SegParams {
+    const float* rec;
+    int RS, fdim, ldim;
+    const unsigned long long* keys[2];
+    Meta* meta;
+    const unsigned* headmask;
+    const unsigned* first_vid;
+    float* out_p;
+    float* out_f;
+    int* out_c;
+    unsigned long long* out_k;
+    int* out_n;
+};
+
+__global__ void __launch_bounds__(SS_THREADS) segsum_kernel(const SegParams p) {
+    __shared__ int s_labs[SS_GROUPS][LABEL_CAP], s_cnts[SS_GROUPS][LABEL_CAP];
+    const unsigned long long n = p.meta->n_sel;
+    const unsigned long long nchunks = (n + 31) / 32;
+    const unsigned long long* keys = p.keys[p.meta->cur];
+    const int tid = threadIdx.x, g = tid >> 3, l = tid & 7;
+    int* labs = s_labs[g];
+    int* cnts = s_cnts[g];
+    const int nsum = 3 + p.fdim;
+    bool overflow = false;
+    if (blockIdx.x == 0 && tid == 0) p.meta->tmark[13] = gtimer_ns();
+    const unsigned long long ngroups = (unsigned long long)gridDim.x * SS_GROUPS;
+    for (unsigned long long chunk = (unsigned long long)blockIdx.x * SS_GROUPS + g; chunk < nchunks; chunk += ngroups) {
+        const unsigned fv = p.first_vid[chunk];
+        if (fv == NO_HEAD) continue;  // the whole chunk continues a voxel that began earlier
+        for (int col = l; col < p.RS; col += 8) {
+            const bool is_label = col >= nsum;
+            unsigned long long blk = chunk * 32ull;
+            unsigned hm = p.headmask[chunk];
+            unsigned vid = fv - 1u;
+            bool open = false, done = false;
+            float acc = 0.f;
+            int nl = 0, last = 0;
+            unsigned long long seg_start = 0;
+            while (!done) {
+                float v[32];
+#pragma unroll
+                for (int tt = 0; tt < 32; ++tt) {
+                    const unsigned long long i = blk + tt;
+                    v[tt] = i < n ? __ldg(p.rec + i * (unsigned)p.RS + col) : 0.f;
+                }
+#pragma unroll
+                for (int tt = 0; tt < 32; ++tt) {
+                    if (!done) {
+                        const unsigned long long i = blk + tt;
+                        const bool beyond = i >= n;
+                        const bool head = !beyond && ((hm >> tt) & 1u);
+                        if (head || beyond) {
+                            if (open) {  // close the voxel [seg_start, i)
+                                const unsigned cnt = (unsigned)(i - seg_start);
+                                if (!is_label) {
+                                    if (col < 3) p.out_p[3ull * vid + col] = __fmul_rn(acc, (float)(1.0 / (double)cnt));
+                                    else p.out_f[(unsigned long long)vid * p.fdim + (col - 3)] = __fdiv_rn(acc, (float)cnt);
+                                    if (col == 0) {
+                                        p.out_k[vid] = keys[seg_start];
+                                        p.out_n[vid] = (int)cnt;
+                                    }
+                                } else {
+                                    int best = -1, nbest = 0, arg = 0;
+                                    for (int q = 0; q < nl; ++q) {
+                                        if (cnts[q] > best) {
+                                            best = cnts[q];
+                                            nbest = 1;
+                                            arg = q;
+                                        } else if (cnts[q] == best)
+                                            ++nbest;
+                                    }
+                                    p.out_c[vid] = nbest == 1 ? labs[arg] : label_first_in_iteration_order(labs, cnts, nl, best);
+                                }
+                                open = false;
+                            }
+                            if (beyond || blk != chunk * 32ull) {
+                                done = true;  // heads of later chunks belong to their own groups; or the data ended
+                            } else {
+                                open = true;
+                                acc = 0.f;
+                                nl = 0;
+                                seg_start = i;
+                                ++vid;
+                            }
+                        }
+                        if (open && !done) {
+                            if (!is_label) {
+                                acc = __fadd_rn(acc, v[tt]);
+                            } else {
+                                const int lab = __float_as_int(v[tt]);
+                                if (nl > 0 && labs[last] == lab) {
+                                    cnts[last] += 1;
+                                } else {
+                                    int q = 0;
+                                    while (q < nl && labs[q] != lab) ++q;
+                                    if (q == nl) {
+                                        if (nl < LABEL_CAP) {
+                                            labs[nl] = lab;
+                                            cnts[nl] = 0;
+                                            ++nl;
+                                        } else {
+                                            overflow = true;
+                                            q = 0;
+                                        }
+                                    }
+                                    cnts[q] += 1;
+                                    last = q;
+                                }
+                            }
+                        }
+                    }
+                }
+                blk += 32;
+                if (!done) hm = blk < n ? p.headmask[blk >> 5] : 0u;
+            }
+        }
+    }
+    if (overflow) p.meta->error = 2;
+    if (tid == 0) atomicMax(&p.meta->tmark[14], gtimer_ns());
+}
+
 // ---- 7. reference row order: libstdc++ unordered_map<size_t,...> iteration order, epoch by epoch ----------------
 // The map is rehashed through a fixed prime sequence; within one bucket count ("epoch") the list is the sequence of
 // bucket runs in REVERSE order of bucket creation, each run in REVERSE insertion order, where the epoch's insertion
@@ -1091,21 +1307,18 @@ struct Inputs {
     bool f_u8 = false, c_u8 = false;
 };
 
-static int run_dev(Ctx* c, cudaStream_t s, const Inputs& in, size_t N, size_t fdim, size_t ldim, float dl, int order,
-                   size_t* M_out, void** handle, Slab slab = Slab(), const float* bbox = nullptr) {
+struct Outputs {  // device arrays with room for `capacity` rows (N in the worst case); nullable where noted
+    float* p = nullptr;
+    float* f = nullptr;               // needed when fdim > 0
+    int* c = nullptr;                 // needed when ldim > 0
+    unsigned long long* k = nullptr;  // voxel keys
+    int* n = nullptr;                 // points per voxel
+};
+
+// Everything up to the single host round trip: sort_kernel, the reduce, the read-back of Meta (voxel count, error flag).
+static int run_core(Ctx* c, cudaStream_t s, const Inputs& in, size_t N, size_t fdim, size_t ldim, float dl, Slab slab,
+                    const float* bbox, const Outputs& out, Meta* hm_out, SortParams* sp_out) {
     typedef unsigned long long KeyT;
-    SSDR_REQUIRE(in.p && M_out && handle, SSDR_ERR_INVALID, "NULL pointer");
-    SSDR_REQUIRE(N >= 1, SSDR_ERR_EMPTY, "Error");
-    SSDR_REQUIRE(N < 0x7FFFFFFFull, SSDR_ERR_UNSUPPORTED, "N=%zu exceeds 2^31-2 points per call", N);
-    SSDR_REQUIRE(order == SSDR_GRID_ORDER_KEY || order == SSDR_GRID_ORDER_REFERENCE, SSDR_ERR_INVALID,
-                 "order must be SSDR_GRID_ORDER_KEY or SSDR_GRID_ORDER_REFERENCE");
-    SSDR_REQUIRE(dl > 0.0f, SSDR_ERR_INVALID, "sampleDl must be positive");
-    if (!in.f) fdim = 0;
-    if (!in.c) ldim = 0;
-    if (bbox)
-        for (int d = 0; d < 3; ++d)
-            SSDR_REQUIRE(bbox[d] <= bbox[3 + d], SSDR_ERR_INVALID, "bbox min exceeds max (or NaN) on axis %d", d);
-    if (slab.axis >= 0) SSDR_REQUIRE(slab.axis < 3 && slab.lo <= slab.hi, SSDR_ERR_INVALID, "bad slab");
     const int G = c->sm_count;
     SSDR_TRY(c->ws[WS_META].reserve(sizeof(Meta)));
     SSDR_TRY(c->ws[WS_KEYS].reserve(N * sizeof(KeyT)));
@@ -1113,6 +1326,7 @@ static int run_dev(Ctx* c, cudaStream_t s, const Inputs& in, size_t N, size_t fd
     SSDR_TRY(c->ws[WS_IDX].reserve(N * sizeof(unsigned)));
     SSDR_TRY(c->ws[WS_IDX2].reserve(N * sizeof(unsigned)));
     SSDR_TRY(c->ws[WS_STARTS].reserve((N + 1) * sizeof(unsigned)));
+    SSDR_TRY(c->ws[WS_HEADS].reserve(2 * (N / 32 + 2) * sizeof(unsigned)));
     // control block: barrier counter | per-CTA partials, largest keys, counts | histogram matrix
     const size_t ctl_bytes = 256 + (size_t)G * (6 * sizeof(float) + sizeof(KeyT) + sizeof(unsigned)) + 256 +
                              (size_t)G * BINS * sizeof(unsigned);
@@ -1140,8 +1354,107 @@ static int run_dev(Ctx* c, cudaStream_t s, const Inputs& in, size_t N, size_t fd
     sp.cta_count = reinterpret_cast<unsigned*>(ctl + 256 + (size_t)G * (sizeof(KeyT) + 6 * sizeof(float)));
     sp.hist = reinterpret_cast<unsigned*>(ctl + (256 + (size_t)G * (6 * sizeof(float) + sizeof(KeyT) + sizeof(unsigned)) + 255) / 256 * 256);
     sp.starts = c->ws[WS_STARTS].as<unsigned>();
+    sp.headmask = c->ws[WS_HEADS].as<unsigned>();
+    sp.first_vid = sp.headmask + (N / 32 + 2);
     SSDR_CHECK_CUDA(cudaMemsetAsync(sp.barrier, 0, 256, s));
+    {
+        void* args[] = {(void*)&sp};
+        SSDR_CHECK_CUDA(cudaLaunchCooperativeKernel((void*)sort_kernel, dim3(G), dim3(PA_THREADS), args, 0, s));
+    }
+    const size_t RS = 3 + fdim + ldim;
+    if (ldim <= 1 && RS <= 32) {
+        // fast reduce: sorted record table (a permutation of the inputs), then segmented sequential sums
+        SSDR_TRY(c->ws[WS_REC].reserve(N * RS * sizeof(float)));
+        RecParams gp;
+        gp.pts = in.p;
+        gp.feats = fdim ? in.f : nullptr;
+        gp.cls = ldim ? in.c : nullptr;
+        gp.feat_u8 = in.f_u8 ? 1 : 0;
+        gp.cls_u8 = in.c_u8 ? 1 : 0;
+        gp.fdim = (int)fdim;
+        gp.ldim = (int)ldim;
+        gp.RS = (int)RS;
+        gp.idx[0] = sp.idx[0];
+        gp.idx[1] = sp.idx[1];
+        gp.meta = meta;
+        gp.rec = c->ws[WS_REC].as<float>();
+        const size_t words = N * RS;
+        const size_t cap = (size_t)c->sm_count * 16;
+        const size_t gb = (words + 255) / 256;
+        gather_kernel<<<(unsigned)(gb < cap ? gb : cap), 256, 0, s>>>(gp);
+        SegParams qp;
+        qp.rec = gp.rec;
+        qp.RS = (int)RS;
+        qp.fdim = (int)fdim;
+        qp.ldim = (int)ldim;
+        qp.keys[0] = sp.keys[0];
+        qp.keys[1] = sp.keys[1];
+        qp.meta = meta;
+        qp.headmask = sp.headmask;
+        qp.first_vid = sp.first_vid;
+        qp.out_p = out.p;
+        qp.out_f = out.f;
+        qp.out_c = out.c;
+        qp.out_k = out.k;
+        qp.out_n = out.n;
+        const size_t chunks = (N + 31) / 32;
+        const size_t sb = (chunks + SS_GROUPS - 1) / SS_GROUPS;
+        segsum_kernel<<<(unsigned)(sb < cap ? sb : cap), SS_THREADS, 0, s>>>(qp);
+    } else {
+        ReduceParams rp;
+        rp.pts = in.p;
+        rp.feats = fdim ? in.f : nullptr;
+        rp.cls = ldim ? in.c : nullptr;
+        rp.feat_u8 = in.f_u8 ? 1 : 0;
+        rp.cls_u8 = in.c_u8 ? 1 : 0;
+        rp.fdim = (int)fdim;
+        rp.ldim = (int)ldim;
+        rp.keys[0] = sp.keys[0];
+        rp.keys[1] = sp.keys[1];
+        rp.idx[0] = sp.idx[0];
+        rp.idx[1] = sp.idx[1];
+        rp.starts = sp.starts;
+        rp.meta = meta;
+        rp.out_p = out.p;
+        rp.out_f = out.f;
+        rp.out_c = out.c;
+        rp.out_k = out.k;
+        rp.out_n = out.n;
+        size_t want = (N + RB_GROUPS - 1) / RB_GROUPS;  // M <= N voxels, one group each at most
+        const size_t cap = (size_t)c->sm_count * 8;
+        const unsigned blocks = (unsigned)(want < cap ? (want ? want : 1) : cap);
+        reduce_kernel<<<blocks, RB_THREADS, 0, s>>>(rp);
+    }
+    SSDR_CHECK_CUDA(cudaGetLastError());
+    // the ONE host round trip of the call: voxel count (the caller sizes its arrays with it) and the error flag
+    SSDR_TRY(d2h_sync(c, hm_out, meta, sizeof(Meta), s));
+    g_last_meta = *hm_out;
+    SSDR_REQUIRE(hm_out->error != 2, SSDR_ERR_UNSUPPORTED, "more than %d distinct labels inside one voxel", LABEL_CAP);
+    if (sp_out) *sp_out = sp;
+    return SSDR_OK;
+}
 
+static int check_args(const Inputs& in, size_t N, size_t& fdim, size_t& ldim, float dl, int order, const Slab& slab,
+                      const float* bbox) {
+    SSDR_REQUIRE(in.p, SSDR_ERR_INVALID, "NULL pointer");
+    SSDR_REQUIRE(N >= 1, SSDR_ERR_EMPTY, "Error");
+    SSDR_REQUIRE(N < 0x7FFFFFFFull, SSDR_ERR_UNSUPPORTED, "N=%zu exceeds 2^31-2 points per call", N);
+    SSDR_REQUIRE(order == SSDR_GRID_ORDER_KEY || order == SSDR_GRID_ORDER_REFERENCE, SSDR_ERR_INVALID,
+                 "order must be SSDR_GRID_ORDER_KEY or SSDR_GRID_ORDER_REFERENCE");
+    SSDR_REQUIRE(dl > 0.0f, SSDR_ERR_INVALID, "sampleDl must be positive");
+    if (!in.f) fdim = 0;
+    if (!in.c) ldim = 0;
+    if (bbox)
+        for (int d = 0; d < 3; ++d)
+            SSDR_REQUIRE(bbox[d] <= bbox[3 + d], SSDR_ERR_INVALID, "bbox min exceeds max (or NaN) on axis %d", d);
+    if (slab.axis >= 0) SSDR_REQUIRE(slab.axis < 3 && slab.lo <= slab.hi, SSDR_ERR_INVALID, "bad slab");
+    return SSDR_OK;
+}
+
+static int run_dev(Ctx* c, cudaStream_t s, const Inputs& in, size_t N, size_t fdim, size_t ldim, float dl, int order,
+                   size_t* M_out, void** handle, Slab slab = Slab(), const float* bbox = nullptr) {
+    SSDR_REQUIRE(M_out && handle, SSDR_ERR_INVALID, "NULL pointer");
+    SSDR_TRY(check_args(in, N, fdim, ldim, dl, order, slab, bbox));
     // outputs are sized for the worst case (every point its own voxel): M is known only on the device
     Handle* h = new Handle();
     h->stream = s;
@@ -1166,48 +1479,18 @@ static int run_dev(Ctx* c, cudaStream_t s, const Inputs& in, size_t N, size_t fd
     SSDR_ALLOC(h->d_k, N * sizeof(unsigned long long));
     SSDR_ALLOC(h->d_n, N * sizeof(int));
 #undef SSDR_ALLOC
-
-    {
-        void* args[] = {(void*)&sp};
-        cudaError_t e = cudaLaunchCooperativeKernel((void*)sort_kernel, dim3(G), dim3(PA_THREADS), args, 0, s);
-        if (e != cudaSuccess) return fail(set_error(SSDR_ERR_CUDA, "sort_kernel launch failed: %s", cudaGetErrorString(e)));
-    }
-    ReduceParams rp;
-    rp.pts = in.p;
-    rp.feats = fdim ? in.f : nullptr;
-    rp.cls = ldim ? in.c : nullptr;
-    rp.feat_u8 = in.f_u8 ? 1 : 0;
-    rp.cls_u8 = in.c_u8 ? 1 : 0;
-    rp.fdim = (int)fdim;
-    rp.ldim = (int)ldim;
-    rp.keys[0] = sp.keys[0];
-    rp.keys[1] = sp.keys[1];
-    rp.idx[0] = sp.idx[0];
-    rp.idx[1] = sp.idx[1];
-    rp.starts = sp.starts;
-    rp.meta = meta;
-    rp.out_p = h->d_p;
-    rp.out_f = h->d_f;
-    rp.out_c = h->d_c;
-    rp.out_k = h->d_k;
-    rp.out_n = h->d_n;
-    {
-        size_t want = (N + RB_GROUPS - 1) / RB_GROUPS;  // M <= N voxels, one group each at most
-        const size_t cap = (size_t)c->sm_count * 8;
-        const unsigned blocks = (unsigned)(want < cap ? (want ? want : 1) : cap);
-        reduce_kernel<<<blocks, RB_THREADS, 0, s>>>(rp);
-        cudaError_t e = cudaGetLastError();
-        if (e != cudaSuccess) return fail(set_error(SSDR_ERR_CUDA, "reduce_kernel launch failed: %s", cudaGetErrorString(e)));
-    }
-    // the ONE host round trip of the call: voxel count (the caller sizes its arrays with it) and the error flag
+    Outputs out;
+    out.p = h->d_p;
+    out.f = h->d_f;
+    out.c = h->d_c;
+    out.k = h->d_k;
+    out.n = h->d_n;
     Meta hm;
+    SortParams sp;
     {
-        int rc = d2h_sync(c, &hm, meta, sizeof(Meta), s);
+        int rc = run_core(c, s, in, N, fdim, ldim, dl, slab, bbox, out, &hm, &sp);
         if (rc != SSDR_OK) return fail(rc);
     }
-    g_last_meta = hm;
-    if (hm.error == 2)
-        return fail(set_error(SSDR_ERR_UNSUPPORTED, "more than %d distinct labels inside one voxel", LABEL_CAP));
     h->M = (size_t)hm.M;
     if (slab.axis >= 0 && hm.n_sel == 0) {  // an empty slab is a valid shard: zero rows
         *M_out = 0;
@@ -1269,6 +1552,44 @@ int ssdr_grid_subsample_slab_dev(const float* d_points, const float* d_feats, co
     return grid::run_dev(c, (cudaStream_t)stream, in, N, fdim, ldim, sampleDl, order, M_out, handle, slab, bbox);
 }
 
+int ssdr_grid_subsample_into_dev(const float* d_points, const float* d_feats, const int32_t* d_classes, size_t N,
+                                 size_t fdim, size_t ldim, float sampleDl, const float* bbox, int axis,
+                                 unsigned long long layer_lo, unsigned long long layer_hi, float* d_points_out,
+                                 float* d_feats_out, int32_t* d_classes_out, uint64_t* d_keys_out, int32_t* d_counts_out,
+                                 size_t capacity, void* stream, size_t* M_out) {
+    SSDR_REQUIRE(d_points_out && M_out, SSDR_ERR_INVALID, "NULL pointer");
+    Ctx* c;
+    SSDR_TRY(get_ctx(&c));
+    SSDR_TRY(ctx_order(c, (cudaStream_t)stream));
+    cudaStream_t s = (cudaStream_t)stream;
+    SSDR_REQUIRE(axis >= -1 && axis <= 2, SSDR_ERR_INVALID, "axis must be -1 (no slab), 0, 1 or 2");
+    grid::Slab slab;
+    slab.axis = axis;
+    slab.lo = layer_lo;
+    slab.hi = layer_hi;
+    grid::Inputs in;
+    in.p = d_points;
+    in.f = d_feats;
+    in.c = d_classes;
+    SSDR_TRY(grid::check_args(in, N, fdim, ldim, sampleDl, SSDR_GRID_ORDER_KEY, slab, bbox));
+    SSDR_REQUIRE(capacity >= N, SSDR_ERR_INVALID,
+                 "output capacity %zu is below the worst case of one voxel per point (%zu rows)", capacity, N);
+    SSDR_REQUIRE((!fdim || d_feats_out) && (!ldim || d_classes_out), SSDR_ERR_INVALID, "NULL output array");
+    grid::Outputs out;
+    out.p = d_points_out;
+    out.f = d_feats_out;
+    out.c = d_classes_out;
+    // keys / counts are optional for the caller; the kernels always write them
+    SSDR_TRY(c->ws[grid::WS_TEMP].reserve(N * (sizeof(unsigned long long) + sizeof(int))));
+    out.k = d_keys_out ? reinterpret_cast<unsigned long long*>(d_keys_out) : c->ws[grid::WS_TEMP].as<unsigned long long>();
+    out.n = d_counts_out ? d_counts_out : reinterpret_cast<int*>(c->ws[grid::WS_TEMP].as<unsigned long long>() + N);
+    grid::Meta hm;
+    SSDR_TRY(grid::run_core(c, s, in, N, fdim, ldim, sampleDl, slab, bbox, out, &hm, nullptr));
+    if (!(slab.axis >= 0 && hm.n_sel == 0)) SSDR_REQUIRE(hm.M >= 1 && hm.M <= N, SSDR_ERR_EMPTY, "Error");
+    *M_out = (size_t)hm.M;
+    return SSDR_OK;
+}
+
 int ssdr_grid_bbox_dev(const float* d_points, size_t N, void* stream, float* bbox_out) {
     SSDR_REQUIRE(d_points && bbox_out, SSDR_ERR_INVALID, "NULL pointer");
     SSDR_REQUIRE(N >= 1, SSDR_ERR_EMPTY, "Error");
@@ -1309,6 +1630,77 @@ int ssdr_grid_point_layers_dev(const float* d_points, size_t N, const float* bbo
         *n_layers_out = axis == 0 ? hm.nX : axis == 1 ? hm.nY : hm.nZ;
     }
     return SSDR_OK;
+}
+
+int ssdr_grid_layer_hist_dev(const float* d_points, size_t N, const float* bbox, float sampleDl, int axis,
+                             unsigned long long* d_hist, size_t n_layers, void* stream) {
+    SSDR_REQUIRE(d_points && d_hist && bbox, SSDR_ERR_INVALID, "NULL pointer");
+    SSDR_REQUIRE(N >= 1 && n_layers >= 1, SSDR_ERR_EMPTY, "Error");
+    SSDR_REQUIRE(axis >= 0 && axis <= 2, SSDR_ERR_INVALID, "axis must be 0, 1 or 2");
+    SSDR_REQUIRE(sampleDl > 0.0f, SSDR_ERR_INVALID, "sampleDl must be positive");
+    Ctx* c;
+    SSDR_TRY(get_ctx(&c));
+    SSDR_TRY(ctx_order(c, (cudaStream_t)stream));
+    cudaStream_t s = (cudaStream_t)stream;
+    SSDR_TRY(c->ws[grid::WS_META].reserve(sizeof(grid::Meta)));
+    grid::Meta* meta = c->ws[grid::WS_META].as<grid::Meta>();
+    SSDR_TRY(grid::geometry(c, s, d_points, N, sampleDl, bbox, meta));
+    SSDR_CHECK_CUDA(cudaMemsetAsync(d_hist, 0, n_layers * sizeof(unsigned long long), s));
+    grid::layer_hist_kernel<<<(unsigned)c->sm_count * 8, 256, 0, s>>>(d_points, N, meta, axis, d_hist, n_layers);
+    SSDR_CHECK_CUDA(cudaGetLastError());
+    return SSDR_OK;
+}
+
+int ssdr_grid_route_dev(const float* d_points, const float* d_feats, const int32_t* d_classes, size_t N, size_t fdim,
+                        size_t ldim, float sampleDl, const float* bbox, int axis, const unsigned long long* bounds,
+                        int world, float* d_points_out, float* d_feats_out, int32_t* d_classes_out,
+                        unsigned long long* counts_out, void* stream) {
+    SSDR_REQUIRE(d_points && bbox && bounds && d_points_out && counts_out, SSDR_ERR_INVALID, "NULL pointer");
+    SSDR_REQUIRE(world >= 1 && world <= grid::MAX_ROUTE_WORLD, SSDR_ERR_INVALID, "world must be in [1, %d]",
+                 grid::MAX_ROUTE_WORLD);
+    SSDR_REQUIRE(axis >= 0 && axis <= 2, SSDR_ERR_INVALID, "axis must be 0, 1 or 2");
+    SSDR_REQUIRE(N < 0x7FFFFFFFull, SSDR_ERR_UNSUPPORTED, "N=%zu exceeds 2^31-2 points per call", N);
+    Ctx* c;
+    SSDR_TRY(get_ctx(&c));
+    SSDR_TRY(ctx_order(c, (cudaStream_t)stream));
+    cudaStream_t s = (cudaStream_t)stream;
+    for (int r = 0; r < world; ++r) counts_out[r] = 0;
+    if (N == 0) return SSDR_OK;
+    if (!d_feats) fdim = 0;
+    if (!d_classes) ldim = 0;
+    typedef unsigned long long KeyT;
+    SSDR_TRY(c->ws[grid::WS_META].reserve(sizeof(grid::Meta)));
+    SSDR_TRY(c->ws[grid::WS_KEYS].reserve(N * sizeof(KeyT)));
+    SSDR_TRY(c->ws[grid::WS_KEYS2].reserve(N * sizeof(KeyT)));
+    SSDR_TRY(c->ws[grid::WS_IDX].reserve(N * sizeof(unsigned)));
+    SSDR_TRY(c->ws[grid::WS_IDX2].reserve(N * sizeof(unsigned)));
+    SSDR_TRY(c->ws[grid::WS_CTL].reserve(1024));
+    const size_t scr = (prim::rs_scratch_words(N) + 8) * sizeof(unsigned);
+    SSDR_TRY(c->ws[grid::WS_TEMP].reserve(scr));
+    grid::Meta* meta = c->ws[grid::WS_META].as<grid::Meta>();
+    SSDR_TRY(grid::geometry(c, s, d_points, N, sampleDl, bbox, meta));
+    grid::RouteBounds rb;
+    rb.world = world;
+    for (int r = 0; r <= world; ++r) rb.b[r] = bounds[r];
+    unsigned long long* d_counts = c->ws[grid::WS_CTL].as<unsigned long long>();
+    SSDR_CHECK_CUDA(cudaMemsetAsync(d_counts, 0, grid::MAX_ROUTE_WORLD * sizeof(unsigned long long), s));
+    SSDR_CHECK_CUDA(cudaMemsetAsync(c->ws[grid::WS_TEMP].p, 0, scr, s));
+    KeyT* ka = c->ws[grid::WS_KEYS].as<KeyT>();
+    KeyT* kb = c->ws[grid::WS_KEYS2].as<KeyT>();
+    unsigned* va = c->ws[grid::WS_IDX].as<unsigned>();
+    unsigned* vb = c->ws[grid::WS_IDX2].as<unsigned>();
+    grid::route_key_kernel<<<(unsigned)((N + 255) / 256), 256, 0, s>>>(d_points, N, meta, axis, rb, ka, va, d_counts);
+    int cur = 0;  // one stable 8-bit pass orders the rows by destination and keeps the input order inside each
+    SSDR_TRY(prim::radix_sort_pairs(ka, va, kb, vb, N, 8, c->ws[grid::WS_TEMP].as<unsigned>(), &cur, s));
+    const unsigned* perm = cur ? vb : va;
+    const unsigned long long tot3 = (unsigned long long)N * 3;
+    grid::permute_rows_kernel<float><<<(unsigned)((tot3 + 255) / 256), 256, 0, s>>>(d_points, d_points_out, perm, N, 3);
+    if (fdim && d_feats_out)
+        grid::permute_rows_kernel<float><<<(unsigned)((N * fdim + 255) / 256), 256, 0, s>>>(d_feats, d_feats_out, perm, N, (int)fdim);
+    if (ldim && d_classes_out)
+        grid::permute_rows_kernel<int><<<(unsigned)((N * ldim + 255) / 256), 256, 0, s>>>(d_classes, d_classes_out, perm, N, (int)ldim);
+    SSDR_CHECK_CUDA(cudaGetLastError());
+    return d2h_sync(c, counts_out, d_counts, (size_t)world * sizeof(unsigned long long), s);
 }
 
 int ssdr_grid_subsample_typed(const float* points, const void* feats, int feats_dtype, const void* classes,

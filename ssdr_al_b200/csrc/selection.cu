@@ -472,7 +472,22 @@ __device__ __forceinline__ Cand grid_exchange(const Params<T>& p, Cand c, int st
         }
         dead = __any_sync(0xffffffffu, dead);
         if (dead) {
-            if (lane == 0) atomicExch(p.peer.error, 1u);
+            if (lane == 0 && atomicExch(p.peer.error, 1u) == 0u) {
+                // first CTA to give up leaves a trace for the host's error message: step, expected tag, and the tag /
+                // payload words found in this rank's block for the current parity
+                unsigned* dbg = p.peer.error;
+                dbg[1] = (unsigned)step;
+                dbg[2] = gtag;
+                dbg[3] = blockIdx.x;
+                for (int r = 0; r < W && r < 8; ++r) {
+                    const unsigned long long w0 = ld_relaxed_u64<true>(&mine[r].w[0]);
+                    const unsigned long long w1 = ld_relaxed_u64<true>(&mine[r].w[1]);
+                    dbg[4 + 4 * r] = (unsigned)w0;
+                    dbg[5 + 4 * r] = (unsigned)(w0 >> 32);
+                    dbg[6 + 4 * r] = (unsigned)w1;
+                    dbg[7 + 4 * r] = (unsigned)(w1 >> 32);
+                }
+            }
             *abort = true;
         }
         w = warp_max<T>(o);
@@ -480,11 +495,25 @@ __device__ __forceinline__ Cand grid_exchange(const Params<T>& p, Cand c, int st
     return w;
 }
 
+// One fetch of a centre row per CTA (16-byte chunks by the lanes of warp 0) instead of one per warp: every CTA of the
+// grid wants the same row at the same moment, and 148 x 16 warps asking one L2 slice for the same line was measured
+// as 0.3 us per warp of a CTA on the critical path of every pick.
+template <typename T>
+__device__ __forceinline__ void fetch_center(const Params<T>& p, unsigned long long c_row, T* s_center, double* s_xx,
+                                             int lane) {
+    const int chunks = (int)((unsigned)p.D * sizeof(T) / 16u);
+    const float4* src = reinterpret_cast<const float4*>(p.F + c_row * (unsigned long long)p.D);
+    for (int i = lane; i < chunks; i += 32) reinterpret_cast<float4*>(s_center)[i] = __ldcg(src + i);
+    if (p.xx && lane == 0) *s_xx = __ldcg(p.xx + c_row);  // k-center: the centre's squared norm travels with its row
+}
+
 // Everything after the row scan of a pick: CTA candidate -> exchange -> next centre (and the pick record).  Called by all
-// threads; returns false when the pick loop must be left (peer time-out).
+// threads; returns false when the pick loop must be left (peer time-out).  s_center (nullable): staging of the next
+// centre row for kernels whose rows are 16-byte multiples.
 template <typename T>
 __device__ __forceinline__ bool finish_pick(const Params<T>& p, Cand best, int step, int lane, int warp, int nwarp,
-                                            Cand* s_red, unsigned long long* s_next_center, int* s_abort) {
+                                            Cand* s_red, unsigned long long* s_next_center, int* s_abort,
+                                            T* s_center = nullptr, double* s_xx = nullptr) {
     best = warp_max<T>(best);
     if (lane == 0) s_red[warp] = best;
     __syncthreads();
@@ -493,6 +522,11 @@ __device__ __forceinline__ bool finish_pick(const Params<T>& p, Cand best, int s
         c = warp_max<T>(c);
         bool abort = false;
         const Cand w = grid_exchange<T>(p, c, step, lane, &abort);
+        if (s_center && !abort && step + 1 < p.step_end) {
+            const int next = step + 1;
+            fetch_center<T>(p, next < p.n_forced ? (unsigned long long)p.forced[next] : cand_row<T>(w), s_center, s_xx,
+                            lane);
+        }
         if (lane == 0) {
             *s_next_center = cand_row<T>(w);
             if (abort) *s_abort = 1;
@@ -503,7 +537,7 @@ __device__ __forceinline__ bool finish_pick(const Params<T>& p, Cand best, int s
             }
         }
     }
-    __syncthreads();  // publishes s_next_center / s_abort
+    __syncthreads();  // publishes s_next_center / s_abort / the staged centre row
     return *s_abort == 0;
 }
 
@@ -588,6 +622,7 @@ __global__ void __launch_bounds__(THREADS, 1) select_kernel(const Params<T> p) {
     const unsigned unit_elems = (unsigned)RW * (unsigned)stride;
     T* ring = reinterpret_cast<T*>(smem_raw + off) + (size_t)warp * S * unit_elems;
     __shared__ unsigned long long s_next_center;
+    __shared__ double s_xx_c;
     __shared__ int s_abort;
     if (tid == 0) s_abort = 0;
     if (FEED == 1) {
@@ -660,14 +695,19 @@ __global__ void __launch_bounds__(THREADS, 1) select_kernel(const Params<T> p) {
         const unsigned long long c_row = step_center<T>(p, step, s_next_center);
         T creg[DT > 0 ? DT / 8 : 1];
         if (DT > 0) {
+            if (step == p.step_begin) {  // later picks find the row staged by finish_pick
+                if (warp == 0) fetch_center<T>(p, c_row, s_center, &s_xx_c, lane);
+                __syncthreads();
+            }
 #pragma unroll
-            for (int k = 0; k < (DT > 0 ? DT / 8 : 1); ++k) creg[k] = __ldcg(p.F + c_row * (unsigned long long)D + 8 * k + j);
+            for (int k = 0; k < (DT > 0 ? DT / 8 : 1); ++k) creg[k] = s_center[8 * k + j];
         } else {
             for (int i = tid; i < D; i += NWARP * 32) s_center[i] = p.F[c_row * (unsigned long long)D + i];
+            if (MODE == MODE_KCENTER && tid == 0) s_xx_c = p.xx[c_row];
             __syncthreads();
         }
         double xx_c = 0.0;
-        if (MODE == MODE_KCENTER) xx_c = p.xx[c_row];
+        if (MODE == MODE_KCENTER) xx_c = s_xx_c;
 
         Cand best;
         best.hi = 0;
@@ -713,7 +753,9 @@ __global__ void __launch_bounds__(THREADS, 1) select_kernel(const Params<T> p) {
             if (lane < rows) update_row<T, MODE, RowVal>(p, mine, m_old, xx_r, xx_c, r0 + lane, &best);
             __syncwarp();  // every lane is done with this stage before a later issue() overwrites it
         }
-        if (!finish_pick<T>(p, best, step, lane, warp, NWARP, s_red, &s_next_center, &s_abort)) break;
+        if (!finish_pick<T>(p, best, step, lane, warp, NWARP, s_red, &s_next_center, &s_abort,
+                            DT > 0 ? s_center : (T*)nullptr, &s_xx_c))
+            break;
     }
     // drain: copies still in flight must land before the CTA's shared memory is released
     if (FEED == 1) {
@@ -753,7 +795,10 @@ __global__ void __launch_bounds__(THREADS, 1) select32_kernel(const Params<float
     unsigned long long* bars = reinterpret_cast<unsigned long long*>(smem_al + off) + warp * MAX_STAGES;
     off += WARPS * MAX_STAGES * 8;
     Cand* s_red = reinterpret_cast<Cand*>(smem_al + off);
+    off += WARPS * (unsigned)sizeof(Cand);
+    float* s_center = reinterpret_cast<float*>(smem_al + off);  // 32 floats: the current centre row, fetched once per CTA
     __shared__ unsigned long long s_next_center;
+    __shared__ double s_xx_c;
     __shared__ int s_abort;
     if (tid == 0) s_abort = 0;
     if (lane == 0) {
@@ -791,11 +836,15 @@ __global__ void __launch_bounds__(THREADS, 1) select32_kernel(const Params<float
         // the centre row in registers (every lane holds all 32 values; the loads are warp-uniform broadcasts)
         typedef typename std::conditional<MODE == MODE_KCENTER, double, float>::type CVal;
         CVal creg[32];
+        if (step == p.step_begin) {  // later picks find the row staged by finish_pick
+            if (warp == 0) fetch_center<float>(p, c_row, s_center, &s_xx_c, lane);
+            __syncthreads();
+        }
         {
-            const float4* c4 = reinterpret_cast<const float4*>(p.F + c_row * 32ull);
+            const float4* c4 = reinterpret_cast<const float4*>(s_center);
 #pragma unroll
             for (int c = 0; c < 8; ++c) {
-                const float4 v = __ldcg(c4 + c);
+                const float4 v = c4[c];
                 creg[4 * c + 0] = (CVal)v.x;
                 creg[4 * c + 1] = (CVal)v.y;
                 creg[4 * c + 2] = (CVal)v.z;
@@ -803,7 +852,7 @@ __global__ void __launch_bounds__(THREADS, 1) select32_kernel(const Params<float
             }
         }
         double xx_c = 0.0;
-        if (MODE == MODE_KCENTER) xx_c = p.xx[c_row];
+        if (MODE == MODE_KCENTER) xx_c = s_xx_c;
         Cand best;
         best.hi = 0;
         best.lo = 0;
@@ -866,7 +915,7 @@ __global__ void __launch_bounds__(THREADS, 1) select32_kernel(const Params<float
             }
             __syncwarp();  // every lane has read the stage before lane 0 re-arms it
         }
-        if (!finish_pick<T>(p, best, step, lane, warp, NWARP, s_red, &s_next_center, &s_abort)) break;
+        if (!finish_pick<T>(p, best, step, lane, warp, NWARP, s_red, &s_next_center, &s_abort, s_center, &s_xx_c)) break;
     }
     long long outstanding = waits_left - loads_left;  // issued - consumed
     while (outstanding-- > 0) {
@@ -1007,7 +1056,7 @@ static int configure32(Ctx* c, Launch<float>& L, const float* dF, size_t N) {
     nst = nst < 2 ? 2 : (nst > MAX_STAGES ? MAX_STAGES : nst);
     const size_t budget = (size_t)c->max_smem_optin - 1024;
     auto need = [&](int st, int w) {
-        return (size_t)1024 + (size_t)w * st * L32_UNIT_BYTES + WARPS * MAX_STAGES * 8 + WARPS * sizeof(Cand) + 64;
+        return (size_t)1024 + (size_t)w * st * L32_UNIT_BYTES + WARPS * MAX_STAGES * 8 + WARPS * sizeof(Cand) + 128 + 64;
     };
     while (nst > 2 && need(nst, nw) > budget) --nst;
     while (nw > 1 && need(nst, nw) > budget) --nw;
@@ -1274,13 +1323,18 @@ static int fps_sharded_dev(Ctx* c, const float* dF, size_t N, size_t D, size_t r
 
 // after a sharded call was enqueued and the stream synchronised: did a peer fail to answer?
 static int peer_check(PeerGroup* g, cudaStream_t s) {
-    unsigned e = 0;
-    SSDR_CHECK_CUDA(cudaMemcpyAsync(&e, g->error_flag(), sizeof(e), cudaMemcpyDeviceToHost, s));
+    unsigned e[40] = {};
+    SSDR_CHECK_CUDA(cudaMemcpyAsync(e, g->error_flag(), sizeof(e), cudaMemcpyDeviceToHost, s));
     SSDR_CHECK_CUDA(cudaStreamSynchronize(s));
-    SSDR_REQUIRE(e == 0, SSDR_ERR_CUDA,
-                 "a peer rank did not post its pick within %llu ms (SSDR_PEER_TIMEOUT_MS): ranks out of step or a rank died",
-                 peer_timeout_ms());
-    return SSDR_OK;
+    if (e[0] == 0) return SSDR_OK;
+    char tags[160] = "";
+    size_t o = 0;
+    for (int r = 0; r < g->world && r < 8 && o + 24 < sizeof(tags); ++r)
+        o += (size_t)snprintf(tags + o, sizeof(tags) - o, " r%d:%u/%u", r, e[4 + 4 * r], e[6 + 4 * r]);
+    return set_error(SSDR_ERR_CUDA,
+                     "a peer rank did not post its pick within %llu ms (SSDR_PEER_TIMEOUT_MS): ranks out of step or a rank "
+                     "died [rank %d step %u expects tag %u, CTA %u; tags in its block:%s]",
+                     peer_timeout_ms(), g->rank, e[1], e[2], e[3], tags);
 }
 
 // host-pointer wrappers: stage in, run, copy picks out

@@ -56,12 +56,16 @@ def knn_pyramid(xyz, ratios, K, neigh=None, up=None, check=False):
     return neigh, up
 
 
-def grid_subsample(points, features=None, classes=None, sampleDl=0.1, bbox=None, slab=None, return_keys=False):
+def grid_subsample(points, features=None, classes=None, sampleDl=0.1, bbox=None, slab=None, return_keys=False,
+                   compact=None):
     """points (N,3) f32, features (N,fdim) f32, classes (N,ldim) i32 cuda tensors -> tuple of cuda tensors.
 
     bbox: 6 floats (min xyz, max xyz) of the larger cloud these points belong to (default: their own min/max).
     slab: (axis, layer_lo, layer_hi) -- reduce only the voxel layers [lo, hi) along `axis` (multi-GPU ownership).
-    return_keys: also return (keys uint64, counts int32) as numpy arrays."""
+    return_keys: also return (keys uint64, counts int32) as numpy arrays.
+    The kernels write straight into torch tensors sized for the worst case (one voxel per point: the voxel count is
+    only known on the device) and the first M rows are returned -- as views when that wastes little, as compact copies
+    when M is much smaller than N (compact=None decides by size; True / False force it).  One stream synchronisation."""
     points = _grid_arg(points, torch.float32, "points", 3)
     features = _grid_arg(features, torch.float32, "features")
     classes = _grid_arg(classes, torch.int32, "classes")
@@ -70,43 +74,27 @@ def grid_subsample(points, features=None, classes=None, sampleDl=0.1, bbox=None,
         raise ValueError("features / classes must have one row per point")
     fdim = features.shape[1] if features is not None else 0
     ldim = (1 if classes.dim() == 1 else classes.shape[1]) if classes is not None else 0
+    dev = points.device
+    out_p = torch.empty((N, 3), dtype=torch.float32, device=dev)
+    out_f = torch.empty((N, fdim), dtype=torch.float32, device=dev) if fdim else None
+    out_c = torch.empty((N, ldim), dtype=torch.int32, device=dev) if ldim else None
+    out_k = torch.empty(N, dtype=torch.int64, device=dev) if return_keys else None
+    out_n = torch.empty(N, dtype=torch.int32, device=dev) if return_keys else None
+    box = (C.c_float * 6)(*[float(v) for v in bbox]) if bbox is not None else None
+    axis, lo, hi = slab if slab is not None else (-1, 0, 0)
     M = C.c_size_t(0)
-    h = C.c_void_p()
-    L = _lib.lib()
-    if bbox is None and slab is None:
-        _lib.check(L.ssdr_grid_subsample_dev(_p(points), _p(features), _p(classes), N, fdim, ldim, float(sampleDl),
-                                             0, _stream(), C.byref(M), C.byref(h)))
-    else:
-        box = (C.c_float * 6)(*[float(v) for v in bbox]) if bbox is not None else None
-        axis, lo, hi = slab if slab is not None else (-1, 0, 0)
-        _lib.check(L.ssdr_grid_subsample_slab_dev(_p(points), _p(features), _p(classes), N, fdim, ldim,
-                                                  float(sampleDl), 0, box, int(axis), int(lo), int(hi), _stream(),
-                                                  C.byref(M), C.byref(h)))
-    try:
-        m = M.value
-        out_p = torch.empty((m, 3), dtype=torch.float32, device=points.device)
-        out_f = torch.empty((m, fdim), dtype=torch.float32, device=points.device) if fdim else None
-        out_c = torch.empty((m, ldim), dtype=torch.int32, device=points.device) if ldim else None
-        keys = counts = None
-        if m:
-            dp, df, dc = C.c_void_p(), C.c_void_p(), C.c_void_p()
-            _lib.check(L.ssdr_grid_dev_ptrs(h, C.byref(dp), C.byref(df), C.byref(dc)))
-            _copy_d2d(out_p, dp, m * 12)
-            if fdim:
-                _copy_d2d(out_f, df, m * fdim * 4)
-            if ldim:
-                _copy_d2d(out_c, dc, m * ldim * 4)
-        if return_keys:
-            import numpy as np
-            keys, counts = np.empty(m, np.uint64), np.empty(m, np.int32)
-            if m:
-                _lib.check(L.ssdr_grid_fetch_ex(h, None, None, None, _lib.ptr(keys), _lib.ptr(counts)))
-        torch.cuda.current_stream().synchronize()
-    finally:
-        L.ssdr_grid_free(h)
+    _lib.check(_lib.lib().ssdr_grid_subsample_into_dev(
+        _p(points), _p(features), _p(classes), N, fdim, ldim, float(sampleDl), box, int(axis), int(lo), int(hi),
+        _p(out_p), _p(out_f), _p(out_c), _p(out_k), _p(out_n), N, _stream(), C.byref(M)))
+    m = M.value
+    if compact is None:
+        compact = N * (12 + 4 * fdim + 4 * ldim) > (32 << 20) and 2 * m < N
+    cut = (lambda t: None if t is None else (t[:m].clone() if compact else t[:m]))
+    res = (cut(out_p), cut(out_f), cut(out_c))
     if return_keys:
-        return out_p, out_f, out_c, keys, counts
-    return out_p, out_f, out_c
+        import numpy as np
+        return res + (out_k[:m].cpu().numpy().view(np.uint64), out_n[:m].cpu().numpy())
+    return res
 
 
 def _grid_arg(t, dtype, name, width=None):
@@ -142,6 +130,49 @@ def grid_point_layers(points, sampleDl, axis, bbox=None):
     _lib.check(_lib.lib().ssdr_grid_point_layers_dev(_p(points), points.shape[0], box, float(sampleDl), int(axis),
                                                      _p(out), _stream(), C.byref(n_layers)))
     return out, int(n_layers.value)
+
+
+def grid_layers(bbox, sampleDl, axis):
+    """Number of voxel layers of the grid along `axis` (the float32 arithmetic of grid_subsampling.cpp:27-31)."""
+    import numpy as np
+    dl = np.float32(sampleDl)
+    mn, mx = np.float32(bbox[axis]), np.float32(bbox[3 + axis])
+    origin = np.floor(mn * (np.float32(1) / dl)) * dl
+    return int(np.int64(np.floor((mx - origin) / dl))) + 1
+
+
+def grid_layer_hist(points, sampleDl, axis, bbox):
+    """Points per voxel layer along `axis` (int64 cuda tensor of grid_layers(...) entries), counted by the library."""
+    points = _grid_arg(points, torch.float32, "points", 3)
+    n_layers = grid_layers(bbox, sampleDl, axis)
+    hist = torch.zeros(n_layers, dtype=torch.int64, device=points.device)
+    if points.shape[0]:
+        box = (C.c_float * 6)(*[float(v) for v in bbox])
+        _lib.check(_lib.lib().ssdr_grid_layer_hist_dev(_p(points), points.shape[0], box, float(sampleDl), int(axis),
+                                                       _p(hist), n_layers, _stream()))
+    return hist
+
+
+def grid_route(points, features, classes, sampleDl, axis, bbox, bounds):
+    """Stable device-side partition of the rows by slab owner (rank r owns layers [bounds[r], bounds[r+1])): returns
+    (points, features, classes grouped by destination in input order, per-destination row counts as a python list)."""
+    points = _grid_arg(points, torch.float32, "points", 3)
+    features = _grid_arg(features, torch.float32, "features")
+    classes = _grid_arg(classes, torch.int32, "classes")
+    world = len(bounds) - 1
+    N = points.shape[0]
+    fdim = features.shape[1] if features is not None else 0
+    ldim = (1 if classes.dim() == 1 else classes.shape[1]) if classes is not None else 0
+    op = torch.empty_like(points)
+    of = torch.empty_like(features) if features is not None else None
+    oc = torch.empty_like(classes) if classes is not None else None
+    counts = (C.c_ulonglong * world)()
+    if N:
+        box = (C.c_float * 6)(*[float(v) for v in bbox])
+        bnd = (C.c_ulonglong * (world + 1))(*[int(b) for b in bounds])
+        _lib.check(_lib.lib().ssdr_grid_route_dev(_p(points), _p(features), _p(classes), N, fdim, ldim, float(sampleDl),
+                                                  box, int(axis), bnd, world, _p(op), _p(of), _p(oc), counts, _stream()))
+    return op, of, oc, [int(v) for v in counts]
 
 
 _cudart = None

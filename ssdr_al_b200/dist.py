@@ -246,23 +246,14 @@ def route_plan(layers, bounds):
 MAX_LAYERS = 1 << 24
 
 
-def slab_route(layers, n_layers, tensors, group=None):
-    """The exchange step of sharded subsampling.  `layers`: layer index of each local row (int tensor, any device);
-    `tensors`: row-aligned tensors (None entries pass through).  All-reduces the layer histogram, cuts balanced slabs
-    and sends every row to its owner with all_to_all_single, keeping input order: rows are stably sorted by
-    destination, and the received pieces arrive concatenated in source-rank order == global row order.
-    Returns (bounds, routed tensors)."""
+def exchange_groups(tensors, send_counts, group=None):
+    """One all-to-all of row-aligned tensors whose rows are already grouped by destination rank (send_counts[r] rows
+    for rank r, in that order).  The received pieces arrive concatenated in source-rank order, so rows that were in
+    global input order inside every group stay in global input order on their owner.  None entries pass through."""
     import torch
     import torch.distributed as dist
-    world = dist.get_world_size(group)
-    layers = layers.long()
-    hist = torch.bincount(layers, minlength=n_layers)
-    dist.all_reduce(hist, group=group)
-    bounds = balanced_slabs(hist.cpu().numpy(), world)
-    cuts = torch.from_numpy(bounds[1:-1].copy()).to(layers.device)
-    dest = torch.searchsorted(cuts, layers, right=True)
-    order = torch.argsort(dest, stable=True)
-    send = torch.bincount(dest, minlength=world)
+    first = next(t for t in tensors if t is not None)
+    send = torch.tensor([int(v) for v in send_counts], dtype=torch.int64, device=first.device)
     recv = torch.empty_like(send)
     dist.all_to_all_single(recv, send, group=group)
     send_l, recv_l = send.tolist(), recv.tolist()
@@ -270,12 +261,19 @@ def slab_route(layers, n_layers, tensors, group=None):
     def exchange(t):
         if t is None:
             return None
-        t = t.contiguous()[order]
         out = torch.empty((sum(recv_l),) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
-        dist.all_to_all_single(out, t, output_split_sizes=recv_l, input_split_sizes=send_l, group=group)
+        dist.all_to_all_single(out, t.contiguous(), output_split_sizes=recv_l, input_split_sizes=send_l, group=group)
         return out
 
-    return bounds, tuple(exchange(t) for t in tensors)
+    return tuple(exchange(t) for t in tensors)
+
+
+def slab_exchange(points, features, classes, sampleDl, axis, bbox, bounds, group=None):
+    """The exchange step of sharded subsampling: the library groups this rank's rows by slab owner on the device (stable
+    partition, input order kept: ssdr_grid_route_dev), one all-to-all moves every group to its owner."""
+    from . import device as dev
+    p, f, c, send_l = dev.grid_route(points, features, classes, sampleDl, axis, bbox, bounds)
+    return exchange_groups((p, f, c), send_l, group=group)
 
 
 def grid_subsample_sharded(points, features=None, classes=None, sampleDl=0.1, *, replicated=False, group=None,
@@ -304,25 +302,20 @@ def grid_subsample_sharded(points, features=None, classes=None, sampleDl=0.1, *,
         dist.all_reduce(hi, op=dist.ReduceOp.MAX, group=group)
         box = torch.cat([lo, hi])
     bbox = [float(v) for v in box.cpu()]
-    # 2. balanced slabs from the layer histogram
-    if n_local:
-        layers, n_layers = dev.grid_point_layers(points, sampleDl, axis, bbox)
-    else:
-        layers, n_layers = torch.zeros(0, dtype=torch.int32, device=points.device), 0
-    if not replicated:
-        nl = torch.tensor([n_layers], dtype=torch.int64, device=points.device)
-        dist.all_reduce(nl, op=dist.ReduceOp.MAX, group=group)
-        n_layers = int(nl.item())
+    # 2. balanced slabs from the layer histogram (counted by the library; summed over the ranks for row chunks)
+    n_layers = dev.grid_layers(bbox, sampleDl, axis)
     if n_layers > MAX_LAYERS:
         raise ValueError("grid has %d layers along axis %d (limit %d): sampleDl too small for this extent"
                          % (n_layers, axis, MAX_LAYERS))
+    hist = dev.grid_layer_hist(points, sampleDl, axis, bbox)
+    if not replicated:
+        dist.all_reduce(hist, group=group)
+    bounds = balanced_slabs(hist.cpu().numpy(), world)
     if replicated:
-        hist = torch.bincount(layers.long(), minlength=n_layers)
-        bounds = balanced_slabs(hist.cpu().numpy(), world)
         slab = (axis, int(bounds[rank]), int(bounds[rank + 1]))
         return dev.grid_subsample(points, features, classes, sampleDl, bbox=bbox, slab=slab, return_keys=return_keys)
     # 3. route every point to its slab owner
-    _, (p, f, c) = slab_route(layers, n_layers, (points, features, classes), group=group)
+    p, f, c = slab_exchange(points, features, classes, sampleDl, axis, bbox, bounds, group=group)
     if p.shape[0] == 0:
         e = lambda t, dt: None if t is None else torch.empty((0, t.shape[1]), dtype=dt, device=points.device)
         res = (torch.empty((0, 3), dtype=torch.float32, device=points.device), e(features, torch.float32),

@@ -103,8 +103,14 @@ def _route_worker(rank, world, port, layers, rows, out_q):
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     b, e = [(0, 1000), (1000, len(layers))][rank]  # uneven chunks, rank order == row order
-    bounds, (r, none) = D.slab_route(torch.from_numpy(layers[b:e]), int(layers.max()) + 1,
-                                     (torch.from_numpy(rows[b:e]), None))
+    # slab bounds from the summed layer histogram, then this rank's rows grouped by owner in input order (on a GPU the
+    # library does this partition, ssdr_grid_route_dev; here numpy's stable sort stands in) and one all-to-all
+    hist = torch.from_numpy(np.bincount(layers[b:e], minlength=int(layers.max()) + 1))
+    dist.all_reduce(hist)
+    bounds = D.balanced_slabs(hist.numpy(), world)
+    dest, send = D.route_plan(layers[b:e], bounds)
+    order = np.argsort(dest, kind="stable")
+    r, none = D.exchange_groups((torch.from_numpy(rows[b:e][order]), None), send.tolist())
     assert none is None
     out_q.put((rank, bounds.tolist(), r.numpy()))
     dist.barrier()

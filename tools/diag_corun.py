@@ -1,0 +1,68 @@
+"""Diagnostic: do kernels launched from two Python threads on two streams run side by side on this box, and does the
+virtual-rank peer exchange work?  Prints timings and the library's own error text."""
+import os
+import sys
+import threading
+import time
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+
+torch.cuda.set_device(0)
+torch.cuda.init()
+x = torch.zeros(1, device="cuda")
+cyc = int(1.0e9)  # ~0.5 s at 1.9 GHz
+
+
+def spin(res, i):
+    with torch.cuda.stream(torch.cuda.Stream()):
+        torch.cuda._sleep(cyc)
+        torch.cuda.current_stream().synchronize()
+    res[i] = time.perf_counter()
+
+
+t0 = time.perf_counter()
+res = [0, 0]
+ts = [threading.Thread(target=spin, args=(res, i)) for i in range(2)]
+[t.start() for t in ts]
+[t.join() for t in ts]
+print("two spin kernels from two threads: %.2f s (one alone ~%.2f s)" % (max(res) - t0, cyc / 1.9e9), flush=True)
+
+os.environ["SSDR_PEER_TIMEOUT_MS"] = "3000"
+from ssdr_al_b200 import device as D, dist as SD
+F = torch.randn((60_000, 32), device="cuda")
+want = D.fps(F, 50, 11)
+sms = torch.cuda.get_device_properties(0).multi_processor_count
+for world in (2,):
+    groups = SD.PeerGroup.local(world)
+    out = [None] * world
+
+    def work(r):
+        try:
+            with torch.cuda.stream(torch.cuda.Stream()):
+                t1 = time.perf_counter()
+                out[r] = SD.fps_sharded(F, 50, 11, groups[r], max_ctas=sms // world)
+                torch.cuda.current_stream().synchronize()
+                print("rank", r, "ok in %.3f s" % (time.perf_counter() - t1), bool(torch.equal(out[r], want)), flush=True)
+        except Exception as e:  # noqa: BLE001
+            print("rank", r, "failed:", e, flush=True)
+
+    ts = [threading.Thread(target=work, args=(r,)) for r in range(world)]
+    [t.start() for t in ts]
+    [t.join() for t in ts]
+    # the same with the second rank started late: is the first one really waiting for it?
+    groups2 = SD.PeerGroup.local(world)
+    ts = [threading.Thread(target=lambda r=r: (time.sleep(0.5 * r), work_g(r, groups2))) for r in range(world)]
+
+    def work_g(r, gs):
+        try:
+            with torch.cuda.stream(torch.cuda.Stream()):
+                t1 = time.perf_counter()
+                o = SD.fps_sharded(F, 50, 11, gs[r], max_ctas=sms // world)
+                torch.cuda.current_stream().synchronize()
+                print("late-start rank", r, "ok in %.3f s" % (time.perf_counter() - t1), bool(torch.equal(o, want)), flush=True)
+        except Exception as e:  # noqa: BLE001
+            print("late-start rank", r, "failed:", e, flush=True)
+
+    [t.start() for t in ts]
+    [t.join() for t in ts]
