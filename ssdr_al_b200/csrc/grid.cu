@@ -305,30 +305,52 @@ __device__ __forceinline__ unsigned block_excl_scan(unsigned v, unsigned* s_w, u
 }
 
 // One tile = PA_THREADS consecutive points staged through shared memory as float4 (coalesced 16-byte loads; the
-// 12-byte records are then read back with stride 3 words, which is conflict free).  base % 4 == 0 and pts 16-byte
-// aligned are guaranteed by the caller; otherwise the scalar path loads the three floats directly.
-__device__ __forceinline__ void load_xyz_tile(const float* __restrict__ pts, unsigned long long base, unsigned cnt,
-                                              bool aligned, float* s_xyz, float* x, float* y, float* z) {
-    const unsigned t = threadIdx.x;
-    if (aligned) {
-        __syncthreads();  // the previous tile has been consumed
-        const unsigned nfl = cnt * 3u, nv = nfl >> 2;
-        const float4* src = reinterpret_cast<const float4*>(pts + base * 3ull);
-        if (t < nv) reinterpret_cast<float4*>(s_xyz)[t] = __ldg(src + t);
-        if (t < (nfl & 3u)) s_xyz[(nv << 2) + t] = __ldg(pts + base * 3ull + (nv << 2) + t);
-        __syncthreads();
-        if (t < cnt) {
-            *x = s_xyz[3 * t];
-            *y = s_xyz[3 * t + 1];
-            *z = s_xyz[3 * t + 2];
+// 12-byte records are then read back with stride 3 words, which is conflict free).  The NEXT tile's float4 is already in
+// a register while the current one is consumed, so the global-load latency overlaps the work on the tile.
+// base % 4 == 0 and pts 16-byte aligned are guaranteed by the caller; otherwise the scalar path loads the three floats.
+struct TileLoader {
+    const float* pts;
+    bool aligned;
+    float* s_xyz;
+    float4 pre;
+    float sx, sy, sz;  // scalar path: this thread's point of the prefetched tile
+
+    __device__ __forceinline__ void prefetch(unsigned long long base, unsigned cnt) {
+        const unsigned t = threadIdx.x;
+        if (aligned) {
+            const unsigned nv = (cnt * 3u) >> 2;
+            if (t < nv) pre = __ldg(reinterpret_cast<const float4*>(pts + base * 3ull) + t);
+        } else if (t < cnt) {
+            const float* q = pts + (base + t) * 3ull;
+            sx = __ldg(q);
+            sy = __ldg(q + 1);
+            sz = __ldg(q + 2);
         }
-    } else if (t < cnt) {
-        const float* q = pts + (base + t) * 3ull;
-        *x = __ldg(q);
-        *y = __ldg(q + 1);
-        *z = __ldg(q + 2);
     }
-}
+    // hands out the prefetched tile (base, cnt) and starts the load of the next one (nbase, ncnt; ncnt == 0: none)
+    __device__ __forceinline__ void next(unsigned long long base, unsigned cnt, unsigned long long nbase, unsigned ncnt,
+                                         float* x, float* y, float* z) {
+        const unsigned t = threadIdx.x;
+        if (aligned) {
+            __syncthreads();  // the previous tile has been consumed
+            const unsigned nfl = cnt * 3u, nv = nfl >> 2;
+            if (t < nv) reinterpret_cast<float4*>(s_xyz)[t] = pre;
+            if (t < (nfl & 3u)) s_xyz[(nv << 2) + t] = __ldg(pts + base * 3ull + (nv << 2) + t);
+            if (ncnt) prefetch(nbase, ncnt);
+            __syncthreads();
+            if (t < cnt) {
+                *x = s_xyz[3 * t];
+                *y = s_xyz[3 * t + 1];
+                *z = s_xyz[3 * t + 2];
+            }
+        } else {
+            *x = sx;
+            *y = sy;
+            *z = sz;
+            if (ncnt) prefetch(nbase, ncnt);
+        }
+    }
+};
 
 __global__ void __launch_bounds__(PA_THREADS, 1) sort_kernel(const SortParams p) {
     __shared__ __align__(16) unsigned s_cnt[PA_WARPS][BINS];     // radix ranking counters (P2) ...
@@ -351,14 +373,20 @@ __global__ void __launch_bounds__(PA_THREADS, 1) sort_kernel(const SortParams p)
     // contiguous chunk of all N points for this CTA (tile aligned)
     const unsigned long long perN = (((p.N + G - 1) / G) + PA_THREADS - 1) / PA_THREADS * PA_THREADS;
     const unsigned long long cb = min((unsigned long long)c * perN, p.N), ce = min(cb + perN, p.N);
+    TileLoader tl;
+    tl.pts = p.pts;
+    tl.aligned = aligned;
+    tl.s_xyz = s_xyz;
 
     // ---- P0: corners -> geometry (identical in every CTA)
     if (!p.has_bbox) {
         float mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
+        if (cb < ce) tl.prefetch(cb, (unsigned)min((unsigned long long)PA_THREADS, ce - cb));
         for (unsigned long long b = cb; b < ce; b += PA_THREADS) {
             const unsigned cnt = (unsigned)min((unsigned long long)PA_THREADS, ce - b);
+            const unsigned long long nb = b + PA_THREADS;
             float x = 0.f, y = 0.f, z = 0.f;
-            load_xyz_tile(p.pts, b, cnt, aligned, s_xyz, &x, &y, &z);
+            tl.next(b, cnt, nb, nb < ce ? (unsigned)min((unsigned long long)PA_THREADS, ce - nb) : 0u, &x, &y, &z);
             if (t < cnt) {
                 mn[0] = x < mn[0] ? x : mn[0];
                 mx[0] = x > mx[0] ? x : mx[0];
@@ -419,10 +447,12 @@ __global__ void __launch_bounds__(PA_THREADS, 1) sort_kernel(const SortParams p)
     unsigned long long member_base = cb;  // where this CTA's first (member) point goes
     if (slab) {
         unsigned mine = 0;
+        if (cb < ce) tl.prefetch(cb, (unsigned)min((unsigned long long)PA_THREADS, ce - cb));
         for (unsigned long long b = cb; b < ce; b += PA_THREADS) {
             const unsigned cnt = (unsigned)min((unsigned long long)PA_THREADS, ce - b);
+            const unsigned long long nb = b + PA_THREADS;
             float x = 0.f, y = 0.f, z = 0.f;
-            load_xyz_tile(p.pts, b, cnt, aligned, s_xyz, &x, &y, &z);
+            tl.next(b, cnt, nb, nb < ce ? (unsigned)min((unsigned long long)PA_THREADS, ce - nb) : 0u, &x, &y, &z);
             if (t < cnt) {
                 const unsigned long long layer = voxel_layer(geo, p.slab_axis == 0 ? x : (p.slab_axis == 1 ? y : z), p.slab_axis);
                 mine += (layer >= p.slab_lo && layer < p.slab_hi) ? 1u : 0u;
@@ -471,10 +501,12 @@ __global__ void __launch_bounds__(PA_THREADS, 1) sort_kernel(const SortParams p)
     unsigned long long kmax = 0;
     {
         unsigned long long run = member_base;
+        if (cb < ce) tl.prefetch(cb, (unsigned)min((unsigned long long)PA_THREADS, ce - cb));
         for (unsigned long long b = cb; b < ce; b += PA_THREADS) {
             const unsigned cnt = (unsigned)min((unsigned long long)PA_THREADS, ce - b);
+            const unsigned long long nb = b + PA_THREADS;
             float x = 0.f, y = 0.f, z = 0.f;
-            load_xyz_tile(p.pts, b, cnt, aligned, s_xyz, &x, &y, &z);
+            tl.next(b, cnt, nb, nb < ce ? (unsigned)min((unsigned long long)PA_THREADS, ce - nb) : 0u, &x, &y, &z);
             bool member = t < cnt;
             unsigned long long key = 0;
             if (member) {
@@ -582,11 +614,20 @@ __global__ void __launch_bounds__(PA_THREADS, 1) sort_kernel(const SortParams p)
             // (slab: P1 counted the members of this CTA's POINT chunk, the sort chunks partition the compacted array)
             for (unsigned i = t; i < BINS; i += PA_THREADS) s_tot[i] = 0;
             __syncthreads();
-            for (unsigned long long b = sb; b < se; b += PA_THREADS) {
-                const bool in = b + t < se;
-                const unsigned digit = in ? (unsigned)(__ldcg(kin + b + t) >> shift) & (BINS - 1) : BINS;
-                const unsigned peers = __match_any_sync(0xffffffffu, digit);
-                if (in && (peers & ((1u << lane) - 1u)) == 0) atomicAdd(&s_tot[digit], __popc(peers));
+            for (unsigned long long b = sb; b < se; b += 4ull * PA_THREADS) {  // four rounds of keys in flight
+                unsigned long long kk[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const unsigned long long i = b + (unsigned long long)u * PA_THREADS + t;
+                    kk[u] = i < se ? __ldcg(kin + i) : 0ull;
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const bool in = b + (unsigned long long)u * PA_THREADS + t < se;
+                    const unsigned digit = in ? (unsigned)(kk[u] >> shift) & (BINS - 1) : BINS;
+                    const unsigned peers = __match_any_sync(0xffffffffu, digit);
+                    if (in && (peers & ((1u << lane) - 1u)) == 0) atomicAdd(&s_tot[digit], __popc(peers));
+                }
             }
             __syncthreads();
             for (unsigned i = t; i < BINS; i += PA_THREADS) p.hist[(size_t)c * BINS + i] = s_tot[i];
@@ -617,17 +658,26 @@ __global__ void __launch_bounds__(PA_THREADS, 1) sort_kernel(const SortParams p)
             __syncthreads();
         }
         // stable scatter of the chunk, PA_THREADS consecutive elements per round
+        unsigned long long key_n = 0;  // the next round's pair is loaded while the current one is ranked
+        unsigned val_n = 0;
+        if (sb + t < se) {
+            key_n = __ldcg(kin + sb + t);
+            val_n = implicit_idx ? (unsigned)(sb + t) : __ldcg(vin + sb + t);
+        }
         for (unsigned long long b = sb; b < se; b += PA_THREADS) {
             for (unsigned i = t; i < PA_WARPS * BINS; i += PA_THREADS) (&s_cnt[0][0])[i] = 0;
-            __syncthreads();
             const bool in = b + t < se;
-            unsigned long long key = 0;
-            unsigned val = 0, digit = BINS;
-            if (in) {
-                key = __ldcg(kin + b + t);
-                val = implicit_idx ? (unsigned)(b + t) : __ldcg(vin + b + t);
-                digit = (unsigned)(key >> shift) & (BINS - 1);
+            const unsigned long long key = key_n;
+            const unsigned val = val_n;
+            const unsigned digit = in ? (unsigned)(key >> shift) & (BINS - 1) : BINS;
+            {
+                const unsigned long long i2 = b + PA_THREADS + t;
+                if (i2 < se) {
+                    key_n = __ldcg(kin + i2);
+                    val_n = implicit_idx ? (unsigned)i2 : __ldcg(vin + i2);
+                }
             }
+            __syncthreads();
             const unsigned peers = __match_any_sync(0xffffffffu, digit);
             const unsigned rank_in_warp = __popc(peers & ((1u << lane) - 1u));
             if (in && rank_in_warp == 0) s_cnt[warp][digit] = __popc(peers);
@@ -956,54 +1006,24 @@ __global__ void __launch_bounds__(RB_THREADS) reduce_kernel(const ReduceParams p
     if (threadIdx.x == 0) atomicMax(&p.meta->tmark[14], gtimer_ns());
 }
 
-// ---- fast reduce (3 + fdim + ldim <= 32 columns, ldim <= 1): gather the sorted records, then segmented sequential sums --
-// gather_kernel: a pure permutation -- one thread per 32-bit word of the sorted record table rec[i][0..RS) =
-// (x, y, z, features..., label) of the point with the i-th smallest (key, index); coalesced writes, the reads gather.
-struct RecParams {
+// ---- fast reduce (3 + fdim + ldim <= 32 columns, ldim <= 1): segmented sequential sums over the sorted order ----------
+// Eight lanes per 32-record chunk of the sorted (key, index) array, lane = column (x, y, z, feature j, label).  A group
+// owns the voxels whose FIRST record lies in its chunk and follows the last of them into the next chunks until the next
+// head bit.  Every lane gathers ITS column of eight consecutive records at a time (index -> value, the next eight already
+// in flight while the current eight are added), and adds them IN ORDER -- the per-voxel sequential sums of
+// SampledData::update_* (grid_subsampling.h:42-79) -- closing a voxel at every head bit.  All groups walk the same number
+// of records per chunk, so the warp does not serialise on voxel sizes; a heavy voxel costs its owner one add per record.
+// The label column counts in a per-group table that keeps first-occurrence order.
+constexpr int SS_THREADS = 256;
+constexpr int SS_GROUPS = SS_THREADS / 8;
+struct SegParams {
     const float* pts;
     const void* feats;
     const void* cls;
     int feat_u8, cls_u8;
-    int fdim, ldim, RS;
-    const unsigned* idx[2];
-    const Meta* meta;
-    float* rec;
-};
-__global__ void __launch_bounds__(256) gather_kernel(const RecParams p) {
-    const unsigned long long n = p.meta->n_sel;
-    const unsigned* idx = p.idx[p.meta->cur];
-    const unsigned long long total = n * (unsigned long long)p.RS;
-    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
-    for (unsigned long long w = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; w < total; w += stride) {
-        const unsigned long long i = w / (unsigned)p.RS;
-        const int col = (int)(w - i * (unsigned)p.RS);
-        const unsigned long long row = idx[i];
-        float v;
-        if (col < 3) v = __ldg(p.pts + 3ull * row + col);
-        else if (col < 3 + p.fdim) {
-            const unsigned long long o = row * (unsigned long long)p.fdim + (col - 3);
-            v = p.feat_u8 ? (float)__ldg(reinterpret_cast<const unsigned char*>(p.feats) + o)
-                          : __ldg(reinterpret_cast<const float*>(p.feats) + o);
-        } else {
-            const unsigned long long o = row * (unsigned long long)p.ldim + (col - 3 - p.fdim);
-            v = __int_as_float(p.cls_u8 ? (int)__ldg(reinterpret_cast<const unsigned char*>(p.cls) + o)
-                                        : __ldg(reinterpret_cast<const int*>(p.cls) + o));
-        }
-        p.rec[w] = v;
-    }
-}
-
-// segsum_kernel: eight lanes per 32-record chunk, lane = column.  A group owns the voxels whose FIRST record lies in its
-// chunk and follows the last of them into the next chunks until the next head.  Every lane loads its column of 32
-// consecutive records up front (32 independent loads in flight, 8 lanes x 4 bytes contiguous per record), then adds them
-// IN ORDER -- the per-voxel sequential sums of SampledData::update_* (grid_subsampling.h:42-79) -- closing a voxel at
-// every head bit.  The label column counts in a per-group table that keeps first-occurrence order.
-constexpr int SS_THREADS = 256;
-constexpr int SS_GROUPS = SS_THREADS / 8;
-struct SegParams {
-    const float* rec;
     int RS, fdim, ldim;
     const unsigned long long* keys[2];
+    const unsigned* idx[2];
     Meta* meta;
     const unsigned* headmask;
     const unsigned* first_vid;
@@ -1014,11 +1034,51 @@ struct SegParams {
     int* out_n;
 };
 
-__global__ void __launch_bounds__(SS_THREADS) segsum_kernel(const SegParams p) {
+// value of column `col` of input row `row` as 32 bits (labels travel as int bits)
+__device__ __forceinline__ float seg_load(const SegParams& p, unsigned long long row, int col) {
+    if (col < 3) return __ldg(p.pts + 3ull * row + col);
+    if (col < 3 + p.fdim) {
+        const unsigned long long o = row * (unsigned long long)p.fdim + (col - 3);
+        return p.feat_u8 ? (float)__ldg(reinterpret_cast<const unsigned char*>(p.feats) + o)
+                         : __ldg(reinterpret_cast<const float*>(p.feats) + o);
+    }
+    const unsigned long long o = row * (unsigned long long)p.ldim + (col - 3 - p.fdim);
+    return __int_as_float(p.cls_u8 ? (int)__ldg(reinterpret_cast<const unsigned char*>(p.cls) + o)
+                                   : __ldg(reinterpret_cast<const int*>(p.cls) + o));
+}
+
+// closes voxel `vid` = sorted records [seg_start, seg_start + cnt) for one column
+__device__ __noinline__ void seg_emit(const SegParams& p, const unsigned long long* keys, int col, unsigned vid, float acc,
+                                      unsigned cnt, unsigned long long seg_start, const int* labs, const int* cnts, int nl) {
+    if (col < 3 + p.fdim) {
+        // grid_subsampling.cpp:87: double reciprocal narrowed to float for the barycentre; :90-95 true division for features
+        if (col < 3) p.out_p[3ull * vid + col] = __fmul_rn(acc, (float)(1.0 / (double)cnt));
+        else p.out_f[(unsigned long long)vid * p.fdim + (col - 3)] = __fdiv_rn(acc, (float)cnt);
+        if (col == 0) {
+            p.out_k[vid] = keys[seg_start];
+            p.out_n[vid] = (int)cnt;
+        }
+    } else {
+        int best = -1, nbest = 0, arg = 0;
+        for (int q = 0; q < nl; ++q) {
+            if (cnts[q] > best) {
+                best = cnts[q];
+                nbest = 1;
+                arg = q;
+            } else if (cnts[q] == best)
+                ++nbest;
+        }
+        p.out_c[vid] = nbest == 1 ? labs[arg] : label_first_in_iteration_order(labs, cnts, nl, best);
+    }
+}
+
+__global__ void __launch_bounds__(SS_THREADS, 3) segsum_kernel(const SegParams p) {
     __shared__ int s_labs[SS_GROUPS][LABEL_CAP], s_cnts[SS_GROUPS][LABEL_CAP];
     const unsigned long long n = p.meta->n_sel;
     const unsigned long long nchunks = (n + 31) / 32;
-    const unsigned long long* keys = p.keys[p.meta->cur];
+    const int cur = p.meta->cur;
+    const unsigned long long* keys = p.keys[cur];
+    const unsigned* idx = p.idx[cur];
     const int tid = threadIdx.x, g = tid >> 3, l = tid & 7;
     int* labs = s_labs[g];
     int* cnts = s_cnts[g];
@@ -1038,44 +1098,25 @@ __global__ void __launch_bounds__(SS_THREADS) segsum_kernel(const SegParams p) {
             float acc = 0.f;
             int nl = 0, last = 0;
             unsigned long long seg_start = 0;
+            float cur8[8], nxt8[8];
+#pragma unroll
+            for (int tt = 0; tt < 8; ++tt) cur8[tt] = blk + tt < n ? seg_load(p, idx[blk + tt], col) : 0.f;
             while (!done) {
-                float v[32];
 #pragma unroll
-                for (int tt = 0; tt < 32; ++tt) {
-                    const unsigned long long i = blk + tt;
-                    v[tt] = i < n ? __ldg(p.rec + i * (unsigned)p.RS + col) : 0.f;
-                }
+                for (int tt = 0; tt < 8; ++tt) nxt8[tt] = blk + 8 + tt < n ? seg_load(p, idx[blk + 8 + tt], col) : 0.f;
+                const unsigned hm8 = (hm >> (unsigned)(blk & 31ull)) & 0xFFu;
 #pragma unroll
-                for (int tt = 0; tt < 32; ++tt) {
+                for (int tt = 0; tt < 8; ++tt) {
                     if (!done) {
                         const unsigned long long i = blk + tt;
                         const bool beyond = i >= n;
-                        const bool head = !beyond && ((hm >> tt) & 1u);
+                        const bool head = !beyond && ((hm8 >> tt) & 1u);
                         if (head || beyond) {
-                            if (open) {  // close the voxel [seg_start, i)
-                                const unsigned cnt = (unsigned)(i - seg_start);
-                                if (!is_label) {
-                                    if (col < 3) p.out_p[3ull * vid + col] = __fmul_rn(acc, (float)(1.0 / (double)cnt));
-                                    else p.out_f[(unsigned long long)vid * p.fdim + (col - 3)] = __fdiv_rn(acc, (float)cnt);
-                                    if (col == 0) {
-                                        p.out_k[vid] = keys[seg_start];
-                                        p.out_n[vid] = (int)cnt;
-                                    }
-                                } else {
-                                    int best = -1, nbest = 0, arg = 0;
-                                    for (int q = 0; q < nl; ++q) {
-                                        if (cnts[q] > best) {
-                                            best = cnts[q];
-                                            nbest = 1;
-                                            arg = q;
-                                        } else if (cnts[q] == best)
-                                            ++nbest;
-                                    }
-                                    p.out_c[vid] = nbest == 1 ? labs[arg] : label_first_in_iteration_order(labs, cnts, nl, best);
-                                }
+                            if (open) {
+                                seg_emit(p, keys, col, vid, acc, (unsigned)(i - seg_start), seg_start, labs, cnts, nl);
                                 open = false;
                             }
-                            if (beyond || blk != chunk * 32ull) {
+                            if (beyond || (i >> 5) != chunk) {
                                 done = true;  // heads of later chunks belong to their own groups; or the data ended
                             } else {
                                 open = true;
@@ -1087,9 +1128,9 @@ __global__ void __launch_bounds__(SS_THREADS) segsum_kernel(const SegParams p) {
                         }
                         if (open && !done) {
                             if (!is_label) {
-                                acc = __fadd_rn(acc, v[tt]);
+                                acc = __fadd_rn(acc, cur8[tt]);
                             } else {
-                                const int lab = __float_as_int(v[tt]);
+                                const int lab = __float_as_int(cur8[tt]);
                                 if (nl > 0 && labs[last] == lab) {
                                     cnts[last] += 1;
                                 } else {
@@ -1112,8 +1153,10 @@ __global__ void __launch_bounds__(SS_THREADS) segsum_kernel(const SegParams p) {
                         }
                     }
                 }
-                blk += 32;
-                if (!done) hm = blk < n ? p.headmask[blk >> 5] : 0u;
+                blk += 8;
+#pragma unroll
+                for (int tt = 0; tt < 8; ++tt) cur8[tt] = nxt8[tt];
+                if (!done && (blk & 31ull) == 0) hm = blk < n ? p.headmask[blk >> 5] : 0u;
             }
         }
     }
@@ -1363,32 +1406,20 @@ static int run_core(Ctx* c, cudaStream_t s, const Inputs& in, size_t N, size_t f
     }
     const size_t RS = 3 + fdim + ldim;
     if (ldim <= 1 && RS <= 32) {
-        // fast reduce: sorted record table (a permutation of the inputs), then segmented sequential sums
-        SSDR_TRY(c->ws[WS_REC].reserve(N * RS * sizeof(float)));
-        RecParams gp;
-        gp.pts = in.p;
-        gp.feats = fdim ? in.f : nullptr;
-        gp.cls = ldim ? in.c : nullptr;
-        gp.feat_u8 = in.f_u8 ? 1 : 0;
-        gp.cls_u8 = in.c_u8 ? 1 : 0;
-        gp.fdim = (int)fdim;
-        gp.ldim = (int)ldim;
-        gp.RS = (int)RS;
-        gp.idx[0] = sp.idx[0];
-        gp.idx[1] = sp.idx[1];
-        gp.meta = meta;
-        gp.rec = c->ws[WS_REC].as<float>();
-        const size_t words = N * RS;
-        const size_t cap = (size_t)c->sm_count * 16;
-        const size_t gb = (words + 255) / 256;
-        gather_kernel<<<(unsigned)(gb < cap ? gb : cap), 256, 0, s>>>(gp);
+        // fast reduce: segmented sequential sums straight over the sorted order
         SegParams qp;
-        qp.rec = gp.rec;
+        qp.pts = in.p;
+        qp.feats = fdim ? in.f : nullptr;
+        qp.cls = ldim ? in.c : nullptr;
+        qp.feat_u8 = in.f_u8 ? 1 : 0;
+        qp.cls_u8 = in.c_u8 ? 1 : 0;
         qp.RS = (int)RS;
         qp.fdim = (int)fdim;
         qp.ldim = (int)ldim;
         qp.keys[0] = sp.keys[0];
         qp.keys[1] = sp.keys[1];
+        qp.idx[0] = sp.idx[0];
+        qp.idx[1] = sp.idx[1];
         qp.meta = meta;
         qp.headmask = sp.headmask;
         qp.first_vid = sp.first_vid;
@@ -1397,6 +1428,7 @@ static int run_core(Ctx* c, cudaStream_t s, const Inputs& in, size_t N, size_t f
         qp.out_c = out.c;
         qp.out_k = out.k;
         qp.out_n = out.n;
+        const size_t cap = (size_t)c->sm_count * 16;
         const size_t chunks = (N + 31) / 32;
         const size_t sb = (chunks + SS_GROUPS - 1) / SS_GROUPS;
         segsum_kernel<<<(unsigned)(sb < cap ? sb : cap), SS_THREADS, 0, s>>>(qp);

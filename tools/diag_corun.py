@@ -33,36 +33,37 @@ from ssdr_al_b200 import device as D, dist as SD
 F = torch.randn((60_000, 32), device="cuda")
 want = D.fps(F, 50, 11)
 sms = torch.cuda.get_device_properties(0).multi_processor_count
-for world in (2,):
+T0 = time.perf_counter()
+
+
+def attempt(tag, world, warm, delay):
     groups = SD.PeerGroup.local(world)
-    out = [None] * world
+    gate = threading.Barrier(world)
 
     def work(r):
         try:
             with torch.cuda.stream(torch.cuda.Stream()):
+                if warm:  # creates this thread's context, streams and workspaces before the ranks depend on each other
+                    D.fps(F, 5, 11)
+                    torch.cuda.current_stream().synchronize()
+                gate.wait()
+                time.sleep(delay * r)
                 t1 = time.perf_counter()
-                out[r] = SD.fps_sharded(F, 50, 11, groups[r], max_ctas=sms // world)
+                print("%s rank %d enters at %.3f" % (tag, r, t1 - T0), flush=True)
+                o = SD.fps_sharded(F, 50, 11, groups[r], max_ctas=sms // world)
                 torch.cuda.current_stream().synchronize()
-                print("rank", r, "ok in %.3f s" % (time.perf_counter() - t1), bool(torch.equal(out[r], want)), flush=True)
+                print("%s rank %d ok after %.3f s equal=%s" % (tag, r, time.perf_counter() - t1, bool(torch.equal(o, want))), flush=True)
         except Exception as e:  # noqa: BLE001
-            print("rank", r, "failed:", e, flush=True)
+            print("%s rank %d FAILED after %.3f s: %s" % (tag, r, time.perf_counter() - t1, e), flush=True)
 
     ts = [threading.Thread(target=work, args=(r,)) for r in range(world)]
     [t.start() for t in ts]
     [t.join() for t in ts]
-    # the same with the second rank started late: is the first one really waiting for it?
-    groups2 = SD.PeerGroup.local(world)
-    ts = [threading.Thread(target=lambda r=r: (time.sleep(0.5 * r), work_g(r, groups2))) for r in range(world)]
+    for g in groups:
+        g.destroy()
 
-    def work_g(r, gs):
-        try:
-            with torch.cuda.stream(torch.cuda.Stream()):
-                t1 = time.perf_counter()
-                o = SD.fps_sharded(F, 50, 11, gs[r], max_ctas=sms // world)
-                torch.cuda.current_stream().synchronize()
-                print("late-start rank", r, "ok in %.3f s" % (time.perf_counter() - t1), bool(torch.equal(o, want)), flush=True)
-        except Exception as e:  # noqa: BLE001
-            print("late-start rank", r, "failed:", e, flush=True)
 
-    [t.start() for t in ts]
-    [t.join() for t in ts]
+attempt("cold", 2, False, 0.0)
+attempt("warm", 2, True, 0.0)
+attempt("warm+late", 2, True, 0.3)
+attempt("warm4", 4, True, 0.0)
