@@ -179,9 +179,19 @@ __global__ void point_layers_kernel(const float* __restrict__ pts, unsigned long
         f2u64(floorf(__fdiv_rn(__fsub_rn(__ldg(pts + 3 * i + axis), meta->origin[axis]), meta->dl)));
     layers[i] = layer < 0x7FFFFFFFull ? (int)layer : 0x7FFFFFFF;
 }
-// histogram of the voxel layers along one axis (slab balancing of a multi-GPU job): warp-aggregated atomics
-__global__ void layer_hist_kernel(const float* __restrict__ pts, unsigned long long N, const Meta* __restrict__ meta,
-                                  int axis, unsigned long long* __restrict__ hist, unsigned long long n_layers) {
+// histogram of the voxel layers along one axis (slab balancing of a multi-GPU job).  A scan has a few hundred layers
+// and most of its points in a handful of them (the ground), so the counts are taken in shared memory per CTA
+// (warp-aggregated) and flushed once; grids with more layers than fit there count straight into global memory.
+constexpr unsigned HIST_SMEM_LAYERS = 8192;
+__global__ void __launch_bounds__(256) layer_hist_kernel(const float* __restrict__ pts, unsigned long long N,
+                                                         const Meta* __restrict__ meta, int axis,
+                                                         unsigned long long* __restrict__ hist, unsigned long long n_layers) {
+    __shared__ unsigned s_h[HIST_SMEM_LAYERS];
+    const bool local = n_layers <= HIST_SMEM_LAYERS;
+    if (local) {
+        for (unsigned i = threadIdx.x; i < (unsigned)n_layers; i += blockDim.x) s_h[i] = 0;
+        __syncthreads();
+    }
     const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
     const unsigned long long rounds = (N + stride - 1) / stride;
     const float o = meta->origin[axis], dl = meta->dl;
@@ -193,7 +203,15 @@ __global__ void layer_hist_kernel(const float* __restrict__ pts, unsigned long l
             if (layer >= n_layers) layer = n_layers - 1;
         }
         const unsigned peers = __match_any_sync(0xffffffffu, layer);
-        if (i < N && (peers & ((1u << (threadIdx.x & 31)) - 1u)) == 0) atomicAdd(&hist[layer], (unsigned long long)__popc(peers));
+        if (i < N && (peers & ((1u << (threadIdx.x & 31)) - 1u)) == 0) {
+            if (local) atomicAdd(&s_h[layer], (unsigned)__popc(peers));
+            else atomicAdd(&hist[layer], (unsigned long long)__popc(peers));
+        }
+    }
+    if (local) {
+        __syncthreads();
+        for (unsigned i = threadIdx.x; i < (unsigned)n_layers; i += blockDim.x)
+            if (s_h[i]) atomicAdd(&hist[i], (unsigned long long)s_h[i]);
     }
 }
 // destination rank of every point from its layer and the slab bounds (bounds[r] <= layer < bounds[r+1] -> r); written as

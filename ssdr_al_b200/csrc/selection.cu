@@ -1048,10 +1048,10 @@ static int configure32(Ctx* c, Launch<float>& L, const float* dF, size_t N) {
     if (!enc) return -1;  // no driver entry point: the caller falls back to the bulk-copy variant
     const Tunables tn = tunables();
     Params<float>& p = L.p;
-    // measured on B200 (tools/sweep_select.py, N = 500k): FPS is fastest with 8 warps x 4 stages (10.0 us/pick against
-    // 11.6 with 16 warps: fewer, longer streams), the fp64 dot products of k-center want 12 warps x 2 stages
-    int nw = tn.warps > 0 ? tn.warps : (MODE == MODE_FPS ? 8 : 12);
-    int nst = tn.stages > 0 ? tn.stages : (MODE == MODE_FPS ? 4 : 2);
+    // measured on B200 (tools/sweep_select.py, N = 500k, centre row staged once per CTA): 16 warps x 2 stages -- FPS
+    // 7.9 us/pick (8 warps: 9.1, 4 warps: 12.7), k-center 11.1 us/pick (8 warps: 14.3); deeper rings change nothing
+    int nw = tn.warps > 0 ? tn.warps : WARPS;
+    int nst = tn.stages > 0 ? tn.stages : 2;
     nw = nw < 1 ? 1 : (nw > WARPS ? WARPS : nw);
     nst = nst < 2 ? 2 : (nst > MAX_STAGES ? MAX_STAGES : nst);
     const size_t budget = (size_t)c->max_smem_optin - 1024;

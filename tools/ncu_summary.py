@@ -59,9 +59,10 @@ def launches(path):
     print("total_us %.1f  (ncu per-launch times are cold-cache and serialised: compare shares, not absolutes)" % tot)
 
 
-def traffic(path, key=None, out_json=None):
+def traffic(path, key=None, out_json=None, units_per_launch=None):
     """dram bytes (read + write) per launch of the first kernel in an `ncu --set full` report; with key and out_json the
-    value is merged into that json file (profiles/traffic.json, read by bench.py for roofline.traffic)."""
+    value is merged into that json file (profiles/traffic.json, read by bench.py for roofline.traffic) together with the
+    issue-side numbers of the same launch.  units_per_launch (queries, picks ...): per-unit figures are added."""
     import json
     out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(out.splitlines()))
@@ -79,7 +80,26 @@ def traffic(path, key=None, out_json=None):
             d = json.load(open(out_json))
         except Exception:
             d = {}
-        d[key] = {"dram_bytes_per_launch": tot, "kernel": r[idx["Kernel Name"]][:120], "source": path.split("/")[-1]}
+        e = {"dram_bytes_per_launch": tot, "kernel": r[idx["Kernel Name"]][:120], "source": path.split("/")[-1]}
+
+        def num(k):
+            try:
+                return float(r[idx[k]].replace(",", ""))
+            except Exception:
+                return None
+
+        e["issue_active_pct"] = num("smsp__issue_active.avg.pct_of_peak_sustained_active")
+        e["lanes_active"] = num("smsp__thread_inst_executed_per_inst_executed.ratio")
+        e["fma_pipe_pct"] = num("sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active")
+        e["l2_hit_pct"] = num("lts__t_sector_hit_rate.pct")
+        inst = num("smsp__inst_executed.sum")
+        if units_per_launch:
+            u = float(units_per_launch)
+            e["units_per_launch"] = u
+            e["dram_bytes_per_unit"] = tot / u
+            if inst is not None:
+                e["warp_inst_per_query"] = inst / u
+        d[key] = e
         json.dump(d, open(out_json, "w"), indent=1, sort_keys=True)
 
 

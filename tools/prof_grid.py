@@ -50,3 +50,40 @@ report("uniform 1M", u, torch.from_numpy(rgb.astype(np.float32)).to(dev), torch.
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 20_000_000
 x, f, c = synth.scan_cloud(n, 2, dev)
 report("scan %dM" % (n // 1_000_000), x, f, c[:, None].contiguous(), 0.06)
+
+# ---- the multi-GPU slab path on one device: what each of `world` ranks would run on the replicated scan
+from ssdr_al_b200 import dist as SD  # noqa: E402
+
+
+def ev_ms(fn):
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    r = fn()
+    b.record()
+    torch.cuda.synchronize()
+    return a.elapsed_time(b), r
+
+
+c2 = c[:, None].contiguous()
+for world in (2, 8):
+    t_box, box = ev_ms(lambda: D.grid_bbox(x))
+    t_hist, hist = ev_ms(lambda: D.grid_layer_hist(x, 0.06, 2, box))
+    bounds = SD.balanced_slabs(hist.cpu().numpy(), world)
+    print("slab path world=%d: bbox %.3f ms, layer hist %.3f ms (%d layers), bounds %s" % (
+        world, t_box, t_hist, hist.numel(), bounds.tolist()), flush=True)
+    for r in range(world):
+        slab = (2, int(bounds[r]), int(bounds[r + 1]))
+        D.grid_subsample(x, f, c2, 0.06, bbox=box, slab=slab)
+        t, res = ev_ms(lambda: D.grid_subsample(x, f, c2, 0.06, bbox=box, slab=slab))
+        m = (C.c_uint64 * 16)()
+        kb = C.c_int(0)
+        _lib.lib().ssdr_grid_debug_timing(m, C.byref(kb))
+        m = list(m)
+        parts, prev = [], m[0]
+        for i, name in enumerate(NAMES):
+            v = m[i + 1]
+            if v:
+                parts.append("%s %.1f" % (name, (v - prev) / 1e3))
+                prev = v
+        print("  rank %d layers [%d,%d): rows %d  event %.3f ms | %s" % (r, slab[1], slab[2], res[0].shape[0], t,
+                                                                       " ".join(parts)), flush=True)

@@ -23,12 +23,12 @@ if which.startswith("fps") or which.startswith("kc"):
         b.record(); torch.cuda.synchronize()
         print(which, "rows", nrows, "picks", picks, "ms", a.elapsed_time(b), "us/pick", 1e3 * a.elapsed_time(b) / picks, flush=True)
 elif which == "grid":
-    rng = np.random.default_rng(0)
+    from tools import synth
     n = 1_000_000
-    p = (rng.random((n, 3)) * [7, 5, 3]).astype(np.float32); p[: n // 2, 2] = 0
+    p, rgb_h, lab_h = synth.room_cloud(n, 0)  # BASELINE config 1 (what bench.py's extra.grid_subsample times)
     pts = torch.from_numpy(p).to(dev)
-    rgb = torch.from_numpy(rng.integers(0, 256, (n, 3)).astype(np.float32)).to(dev)
-    lab = torch.from_numpy(rng.integers(0, 13, n).astype(np.int32)).to(dev)
+    rgb = torch.from_numpy(rgb_h.astype(np.float32)).to(dev)
+    lab = torch.from_numpy(lab_h.astype(np.int32)).to(dev)
     for rep in range(3):
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record(); r = D.grid_subsample(pts, rgb, lab, 0.04); b.record(); torch.cuda.synchronize()
