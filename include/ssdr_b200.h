@@ -185,7 +185,9 @@ int ssdr_grid_point_layers_dev(const float* d_points, size_t N, const float* bbo
  * with a stable device-side partition (input order kept inside every destination), ready for one all-to-all; it
  * returns the number of rows per destination in counts_out (host).  bbox = corners of the WHOLE cloud. */
 int ssdr_grid_layer_hist_dev(const float* d_points, size_t N, const float* bbox, float sampleDl, int axis,
-                             unsigned long long* d_hist /* n_layers, device */, size_t n_layers, void* stream);
+                             unsigned long long* d_hist /* n_layers, device */, size_t n_layers,
+                             size_t sample_stride /* count every k-th point: balancing needs no exact counts */,
+                             void* stream);
 int ssdr_grid_route_dev(const float* d_points, const float* d_feats, const int32_t* d_classes, size_t N, size_t fdim,
                         size_t ldim, float sampleDl, const float* bbox, int axis,
                         const unsigned long long* bounds /* world + 1, host */, int world, float* d_points_out,
@@ -256,6 +258,9 @@ int ssdr_peer_group_export(void* group, void* handle64 /* 64 bytes: cudaIpcMemHa
 int ssdr_peer_group_connect(void* group, const void* handles /* world x 64 bytes */);
 int ssdr_peer_group_connect_local(void** groups, int world);
 int ssdr_peer_group_destroy(void* group);
+/* With SSDR_PEER_DEFER_CHECK=1 in the environment the two sharded entry points below return once their kernel is
+ * enqueued; ssdr_peer_group_check then synchronises `stream` and reports a peer time-out. */
+int ssdr_peer_group_check(void* group, void* stream);
 int ssdr_fps_sharded_p2p(int dtype, const void* d_F, size_t N, size_t D, size_t row_begin, size_t row_end, int32_t first,
                          size_t n_samples, int32_t* d_out, void* group, void* stream, int max_ctas);
 int ssdr_kcenter_sharded_p2p(int dtype, const void* d_X, size_t N, size_t D, size_t row_begin, size_t row_end,

@@ -59,7 +59,7 @@ SIGNATURES = {
                                      vp, vp, vp, sz, vp, C.POINTER(sz)],
     "ssdr_grid_bbox_dev": [vp, sz, vp, vp],
     "ssdr_grid_point_layers_dev": [vp, sz, vp, C.c_float, C.c_int, vp, vp, C.POINTER(C.c_ulonglong)],
-    "ssdr_grid_layer_hist_dev": [vp, sz, vp, C.c_float, C.c_int, vp, sz, vp],
+    "ssdr_grid_layer_hist_dev": [vp, sz, vp, C.c_float, C.c_int, vp, sz, sz, vp],
     "ssdr_grid_route_dev": [vp, vp, vp, sz, sz, sz, C.c_float, vp, C.c_int, vp, C.c_int, vp, vp, vp, vp, vp],
     "ssdr_fps_f32": [vp, sz, sz, C.c_int32, sz, vp],
     "ssdr_fps_f64": [vp, sz, sz, C.c_int32, sz, vp],
@@ -79,6 +79,7 @@ SIGNATURES = {
     "ssdr_peer_group_connect": [vp, vp],
     "ssdr_peer_group_connect_local": [C.POINTER(vp), C.c_int],
     "ssdr_peer_group_destroy": [vp],
+    "ssdr_peer_group_check": [vp, vp],
     "ssdr_fps_sharded_p2p": [C.c_int, vp, sz, sz, sz, sz, C.c_int32, sz, vp, vp, vp, C.c_int],
     "ssdr_kcenter_sharded_p2p": [C.c_int, vp, sz, sz, sz, sz, vp, sz, sz, vp, vp, vp, C.c_int],
     "ssdr_nccl_unique_id": [vp],

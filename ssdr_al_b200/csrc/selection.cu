@@ -1337,6 +1337,13 @@ static int peer_check(PeerGroup* g, cudaStream_t s) {
                      peer_timeout_ms(), g->rank, e[1], e[2], e[3], tags);
 }
 
+// SSDR_PEER_DEFER_CHECK=1: the sharded entry points return as soon as their kernel is enqueued and the caller asks
+// ssdr_peer_group_check for the outcome (several virtual ranks of one process enqueue first, then wait)
+static bool defer_check() {
+    const char* e = getenv("SSDR_PEER_DEFER_CHECK");
+    return e && e[0] == '1';
+}
+
 // host-pointer wrappers: stage in, run, copy picks out
 template <typename T>
 static int fps_host(const T* F, size_t N, size_t D, int32_t first, size_t n_samples, int32_t* out) {
@@ -1516,7 +1523,12 @@ int ssdr_fps_sharded_p2p(int dtype, const void* d_F, size_t N, size_t D, size_t 
         SSDR_TRY(sel::fps_dev<float>(c, (const float*)d_F, N, D, first, n_samples, d_out, s, row_begin, row_end, g, max_ctas));
     else
         SSDR_TRY(sel::fps_dev<double>(c, (const double*)d_F, N, D, first, n_samples, d_out, s, row_begin, row_end, g, max_ctas));
-    return g->world > 1 ? sel::peer_check(g, s) : SSDR_OK;
+    return (g->world > 1 && !sel::defer_check()) ? sel::peer_check(g, s) : SSDR_OK;
+}
+int ssdr_peer_group_check(void* group, void* stream) {
+    SSDR_REQUIRE(group, SSDR_ERR_INVALID, "group is NULL");
+    sel::PeerGroup* g = (sel::PeerGroup*)group;
+    return g->world > 1 ? sel::peer_check(g, (cudaStream_t)stream) : SSDR_OK;
 }
 int ssdr_kcenter_sharded_p2p(int dtype, const void* d_X, size_t N, size_t D, size_t row_begin, size_t row_end,
                              const int64_t* d_selected, size_t n_sel, size_t n_pick, int64_t* d_out, void* group,
@@ -1532,6 +1544,6 @@ int ssdr_kcenter_sharded_p2p(int dtype, const void* d_X, size_t N, size_t D, siz
         SSDR_TRY(sel::kcenter_dev<float>(c, (const float*)d_X, N, D, d_selected, n_sel, n_pick, d_out, s, row_begin, row_end, g, max_ctas));
     else
         SSDR_TRY(sel::kcenter_dev<double>(c, (const double*)d_X, N, D, d_selected, n_sel, n_pick, d_out, s, row_begin, row_end, g, max_ctas));
-    return g->world > 1 ? sel::peer_check(g, s) : SSDR_OK;
+    return (g->world > 1 && !sel::defer_check()) ? sel::peer_check(g, s) : SSDR_OK;
 }
 }

@@ -141,15 +141,16 @@ def grid_layers(bbox, sampleDl, axis):
     return int(np.int64(np.floor((mx - origin) / dl))) + 1
 
 
-def grid_layer_hist(points, sampleDl, axis, bbox):
-    """Points per voxel layer along `axis` (int64 cuda tensor of grid_layers(...) entries), counted by the library."""
+def grid_layer_hist(points, sampleDl, axis, bbox, sample_stride=1):
+    """Points per voxel layer along `axis` (int64 cuda tensor of grid_layers(...) entries), counted by the library;
+    sample_stride = k counts every k-th point only (slab balancing does not need exact counts)."""
     points = _grid_arg(points, torch.float32, "points", 3)
     n_layers = grid_layers(bbox, sampleDl, axis)
     hist = torch.zeros(n_layers, dtype=torch.int64, device=points.device)
     if points.shape[0]:
         box = (C.c_float * 6)(*[float(v) for v in bbox])
         _lib.check(_lib.lib().ssdr_grid_layer_hist_dev(_p(points), points.shape[0], box, float(sampleDl), int(axis),
-                                                       _p(hist), n_layers, _stream()))
+                                                       _p(hist), n_layers, int(sample_stride), _stream()))
     return hist
 
 

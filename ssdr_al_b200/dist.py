@@ -119,6 +119,11 @@ class PeerGroup(object):
         _lib.check(L.ssdr_peer_group_connect_local(hs, world))
         return [cls(C.c_void_p(hs[r]), world, r) for r in range(world)]
 
+    def check(self):
+        """With SSDR_PEER_DEFER_CHECK=1: wait for the current stream and raise if a peer timed out."""
+        import torch
+        _lib.check(_lib.lib().ssdr_peer_group_check(self.handle, C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+
     def destroy(self):
         if self.handle:
             _lib.lib().ssdr_peer_group_destroy(self.handle)
@@ -276,14 +281,46 @@ def slab_exchange(points, features, classes, sampleDl, axis, bbox, bounds, group
     return exchange_groups((p, f, c), send_l, group=group)
 
 
+def choose_slabs(points, sampleDl, bbox, world, axis, replicated, group=None, sample_stride=16):
+    """(axis, bounds): balanced voxel-layer slabs.  axis = 0/1/2 keeps the caller's axis; "auto" takes the axis whose
+    balanced cut has the lightest heaviest slab (a terrestrial scan has almost all of its points in two or three z
+    layers, so z slabs cannot be balanced, while x or y slabs can).  Counts come from every sample_stride-th point --
+    ownership is by layer range, so the cut positions need not be exact, only identical on every rank (they are: the
+    sampled histograms are all-reduced for row chunks and identical for replicated input)."""
+    import torch.distributed as dist
+    from . import device as dev
+    best = None
+    for ax in ((0, 1, 2) if axis == "auto" else (int(axis),)):
+        n_layers = dev.grid_layers(bbox, sampleDl, ax)
+        if n_layers > MAX_LAYERS:
+            if axis == "auto":
+                continue
+            raise ValueError("grid has %d layers along axis %d (limit %d): sampleDl too small for this extent"
+                             % (n_layers, ax, MAX_LAYERS))
+        hist = dev.grid_layer_hist(points, sampleDl, ax, bbox, sample_stride)
+        if not replicated:
+            dist.all_reduce(hist, group=group)
+        h = hist.cpu().numpy()
+        bounds = balanced_slabs(h, world)
+        load = max(int(h[bounds[r]:bounds[r + 1]].sum()) for r in range(world))
+        if best is None or load < best[0]:  # ties keep the lower axis: deterministic
+            best = (load, ax, bounds)
+    if best is None:
+        raise ValueError("no axis of the grid has at most %d layers: sampleDl too small for this extent" % MAX_LAYERS)
+    return best[1], best[2]
+
+
 def grid_subsample_sharded(points, features=None, classes=None, sampleDl=0.1, *, replicated=False, group=None,
-                           axis=2, return_keys=False):
+                           axis=2, return_keys=False, return_axis=False):
     """Subsample ONE cloud with all ranks of `group`; returns this rank's slab of the result as cuda tensors.
 
     replicated=False: `points` (and features / classes) are this rank's contiguous row chunk of the cloud, chunks in
     rank order.  bbox and layer histogram are all-reduced (a few KB), then every point travels to its slab owner in
     one all-to-all that keeps input order.  replicated=True: every rank holds the whole cloud; no exchange.
-    Rows of all ranks concatenated in rank order == `device.grid_subsample` of the whole cloud (axis=2)."""
+    Every voxel has exactly one owner that sees its points in input order, so every row carries the bits of the
+    single-GPU run.  axis=2 (default): the ranks' rows concatenated in rank order ARE `device.grid_subsample` of the
+    whole cloud (keys are z-major).  axis="auto" picks the best balanced slab axis (see choose_slabs); the union of the
+    ranks' rows is then the same set of rows, in rank-major instead of key order (return_keys gives the keys)."""
     import torch
     import torch.distributed as dist
     from . import device as dev
@@ -302,23 +339,18 @@ def grid_subsample_sharded(points, features=None, classes=None, sampleDl=0.1, *,
         dist.all_reduce(hi, op=dist.ReduceOp.MAX, group=group)
         box = torch.cat([lo, hi])
     bbox = [float(v) for v in box.cpu()]
-    # 2. balanced slabs from the layer histogram (counted by the library; summed over the ranks for row chunks)
-    n_layers = dev.grid_layers(bbox, sampleDl, axis)
-    if n_layers > MAX_LAYERS:
-        raise ValueError("grid has %d layers along axis %d (limit %d): sampleDl too small for this extent"
-                         % (n_layers, axis, MAX_LAYERS))
-    hist = dev.grid_layer_hist(points, sampleDl, axis, bbox)
-    if not replicated:
-        dist.all_reduce(hist, group=group)
-    bounds = balanced_slabs(hist.cpu().numpy(), world)
+    # 2. balanced slabs from the (sampled) layer histogram, counted by the library
+    axis, bounds = choose_slabs(points, sampleDl, bbox, world, axis, replicated, group=group)
+    tail = (axis,) if return_axis else ()
     if replicated:
         slab = (axis, int(bounds[rank]), int(bounds[rank + 1]))
-        return dev.grid_subsample(points, features, classes, sampleDl, bbox=bbox, slab=slab, return_keys=return_keys)
+        return dev.grid_subsample(points, features, classes, sampleDl, bbox=bbox, slab=slab,
+                                  return_keys=return_keys) + tail
     # 3. route every point to its slab owner
     p, f, c = slab_exchange(points, features, classes, sampleDl, axis, bbox, bounds, group=group)
     if p.shape[0] == 0:
         e = lambda t, dt: None if t is None else torch.empty((0, t.shape[1]), dtype=dt, device=points.device)
         res = (torch.empty((0, 3), dtype=torch.float32, device=points.device), e(features, torch.float32),
                e(classes, torch.int32))
-        return res + (np.empty(0, np.uint64), np.empty(0, np.int32)) if return_keys else res
-    return dev.grid_subsample(p, f, c, sampleDl, bbox=bbox, slab=None, return_keys=return_keys)
+        return (res + (np.empty(0, np.uint64), np.empty(0, np.int32)) if return_keys else res) + tail
+    return dev.grid_subsample(p, f, c, sampleDl, bbox=bbox, slab=None, return_keys=return_keys) + tail

@@ -63,7 +63,35 @@ def attempt(tag, world, warm, delay):
         g.destroy()
 
 
+def attempt_deferred(tag, world):
+    """All ranks enqueue first (SSDR_PEER_DEFER_CHECK=1), meet at a host barrier, then wait for their streams."""
+    os.environ["SSDR_PEER_DEFER_CHECK"] = "1"
+    groups = SD.PeerGroup.local(world)
+    gate = threading.Barrier(world)
+
+    def work(r):
+        t1 = time.perf_counter()
+        try:
+            with torch.cuda.stream(torch.cuda.Stream()):
+                D.fps(F, 5, 11)
+                torch.cuda.current_stream().synchronize()
+                gate.wait()
+                t1 = time.perf_counter()
+                o = SD.fps_sharded(F, 50, 11, groups[r], max_ctas=sms // world)
+                gate.wait()
+                groups[r].check()
+                print("%s rank %d ok after %.3f s equal=%s" % (tag, r, time.perf_counter() - t1, bool(torch.equal(o, want))), flush=True)
+        except Exception as e:  # noqa: BLE001
+            print("%s rank %d FAILED after %.3f s: %s" % (tag, r, time.perf_counter() - t1, e), flush=True)
+
+    ts = [threading.Thread(target=work, args=(r,)) for r in range(world)]
+    [t.start() for t in ts]
+    [t.join() for t in ts]
+    for g in groups:
+        g.destroy()
+    os.environ.pop("SSDR_PEER_DEFER_CHECK", None)
+
+
+attempt_deferred("deferred2", 2)
+attempt_deferred("deferred4", 4)
 attempt("cold", 2, False, 0.0)
-attempt("warm", 2, True, 0.0)
-attempt("warm+late", 2, True, 0.3)
-attempt("warm4", 4, True, 0.0)
