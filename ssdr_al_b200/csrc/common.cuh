@@ -41,6 +41,10 @@ struct DevBuf {
     T* as() const { return reinterpret_cast<T*>(p); }
 };
 
+// bumped whenever a workspace of the calling thread is re-allocated: anything that cached raw workspace pointers (a
+// captured CUDA graph) compares generations before it trusts them
+unsigned long long ws_generation();
+
 enum { WS_SLOTS = 24 };
 
 // One per calling thread and device.

@@ -251,6 +251,7 @@ __global__ void bbox_fill_kernel(float* partials, float a0, float a1, float a2, 
 constexpr int PA_THREADS = 1024;
 constexpr int PA_WARPS = PA_THREADS / 32;
 constexpr int BINS = 256;
+constexpr int SC_ITEMS = 4;  // elements per thread and scatter round
 
 struct SortParams {
     const float* pts;
@@ -268,11 +269,9 @@ struct SortParams {
     unsigned long long* pmax;   // [G] largest key per CTA
     unsigned* cta_count;        // [G] slab members, later segment heads, per CTA
     unsigned* starts;           // [N + 1] voxel start offsets
-    unsigned* headmask;         // [N / 32 + 1] bit t of word c: sorted record 32c + t starts a voxel
-    unsigned* first_vid;        // [N / 32 + 1] voxel id of the first head inside chunk c (NO_HEAD if none)
     unsigned* barrier;          // monotonic arrival counter, zero at launch
 };
-constexpr unsigned NO_HEAD = 0xFFFFFFFFu;
+
 
 __device__ __forceinline__ unsigned long long gtimer_ns() {
     unsigned long long t;
@@ -681,29 +680,38 @@ __global__ void __launch_bounds__(PA_THREADS, 1) sort_kernel(const SortParams p)
             __syncthreads();
         }
         // stable scatter of the chunk, PA_THREADS consecutive elements per round
-        unsigned long long key_n = 0;  // the next round's pair is loaded while the current one is ranked
-        unsigned val_n = 0;
-        if (sb + t < se) {
-            key_n = __ldcg(kin + sb + t);
-            val_n = implicit_idx ? (unsigned)(sb + t) : __ldcg(vin + sb + t);
-        }
-        for (unsigned long long b = sb; b < se; b += PA_THREADS) {
+        // stable scatter of the chunk: rounds of SC_ITEMS * PA_THREADS consecutive elements, warp w owning the
+        // 32 * SC_ITEMS consecutive elements [w * 32 * SC_ITEMS, ...) of the round as SC_ITEMS rows of 32 (so both the
+        // loads and the element order inside a warp are coalesced / sequential).  Ranking: match_any inside a row, a
+        // per-warp running count per digit across the rows, one prefix over the warps per round.
+        for (unsigned long long b = sb; b < se; b += (unsigned long long)SC_ITEMS * PA_THREADS) {
             for (unsigned i = t; i < PA_WARPS * BINS; i += PA_THREADS) (&s_cnt[0][0])[i] = 0;
-            const bool in = b + t < se;
-            const unsigned long long key = key_n;
-            const unsigned val = val_n;
-            const unsigned digit = in ? (unsigned)(key >> shift) & (BINS - 1) : BINS;
-            {
-                const unsigned long long i2 = b + PA_THREADS + t;
-                if (i2 < se) {
-                    key_n = __ldcg(kin + i2);
-                    val_n = implicit_idx ? (unsigned)i2 : __ldcg(vin + i2);
+            unsigned long long key[SC_ITEMS];
+            unsigned val[SC_ITEMS], rank[SC_ITEMS];
+#pragma unroll
+            for (int k = 0; k < SC_ITEMS; ++k) {
+                const unsigned long long i = b + (unsigned long long)warp * (32 * SC_ITEMS) + (unsigned)k * 32u + lane;
+                key[k] = 0;
+                val[k] = 0;
+                if (i < se) {
+                    key[k] = __ldcg(kin + i);
+                    val[k] = implicit_idx ? (unsigned)i : __ldcg(vin + i);
                 }
             }
             __syncthreads();
-            const unsigned peers = __match_any_sync(0xffffffffu, digit);
-            const unsigned rank_in_warp = __popc(peers & ((1u << lane) - 1u));
-            if (in && rank_in_warp == 0) s_cnt[warp][digit] = __popc(peers);
+#pragma unroll
+            for (int k = 0; k < SC_ITEMS; ++k) {
+                const unsigned long long i = b + (unsigned long long)warp * (32 * SC_ITEMS) + (unsigned)k * 32u + lane;
+                const bool in = i < se;
+                const unsigned digit = in ? (unsigned)(key[k] >> shift) & (BINS - 1) : BINS;
+                const unsigned peers = __match_any_sync(0xffffffffu, digit);
+                const unsigned r = __popc(peers & ((1u << lane) - 1u));
+                const unsigned before = in ? s_cnt[warp][digit] : 0u;  // same digit in the earlier rows of this warp
+                rank[k] = before + r;
+                __syncwarp();
+                if (in && r == 0) s_cnt[warp][digit] = before + __popc(peers);
+                __syncwarp();
+            }
             __syncthreads();
             if (t < BINS) {
                 unsigned run = s_base[t];
@@ -716,10 +724,14 @@ __global__ void __launch_bounds__(PA_THREADS, 1) sort_kernel(const SortParams p)
                 s_base[t] = run;
             }
             __syncthreads();
-            if (in) {
-                const unsigned pos = s_cnt[warp][digit] + rank_in_warp;
-                kout[pos] = key;
-                vout[pos] = val;
+#pragma unroll
+            for (int k = 0; k < SC_ITEMS; ++k) {
+                const unsigned long long i = b + (unsigned long long)warp * (32 * SC_ITEMS) + (unsigned)k * 32u + lane;
+                if (i < se) {
+                    const unsigned pos = s_cnt[warp][(unsigned)(key[k] >> shift) & (BINS - 1)] + rank[k];
+                    kout[pos] = key[k];
+                    vout[pos] = val[k];
+                }
             }
             __syncthreads();
         }
@@ -778,13 +790,6 @@ __global__ void __launch_bounds__(PA_THREADS, 1) sort_kernel(const SortParams p)
         unsigned tt;
         const unsigned rank = block_excl_scan(head ? 1u : 0u, s_w, &tt);
         if (head) p.starts[vbase + rank] = (unsigned)i;
-        // a warp covers one aligned 32-record chunk: its head bitmap and the voxel id of its first head
-        const unsigned hb = __ballot_sync(0xffffffffu, head);
-        const unsigned fv = (unsigned)vbase + __shfl_sync(0xffffffffu, rank, hb ? __ffs((int)hb) - 1 : 0);
-        if (lane == 0 && i < se) {
-            p.headmask[i >> 5] = hb;
-            p.first_vid[i >> 5] = hb ? fv : NO_HEAD;
-        }
         vbase += tt;
     }
     if (c == 0 && t == 0) {
@@ -1029,164 +1034,6 @@ __global__ void __launch_bounds__(RB_THREADS) reduce_kernel(const ReduceParams p
     if (threadIdx.x == 0) atomicMax(&p.meta->tmark[14], gtimer_ns());
 }
 
-// ---- fast reduce (3 + fdim + ldim <= 32 columns, ldim <= 1): segmented sequential sums over the sorted order ----------
-// Eight lanes per 32-record chunk of the sorted (key, index) array, lane = column (x, y, z, feature j, label).  A group
-// owns the voxels whose FIRST record lies in its chunk and follows the last of them into the next chunks until the next
-// head bit.  Every lane gathers ITS column of eight consecutive records at a time (index -> value, the next eight already
-// in flight while the current eight are added), and adds them IN ORDER -- the per-voxel sequential sums of
-// SampledData::update_* (grid_subsampling.h:42-79) -- closing a voxel at every head bit.  All groups walk the same number
-// of records per chunk, so the warp does not serialise on voxel sizes; a heavy voxel costs its owner one add per record.
-// The label column counts in a per-group table that keeps first-occurrence order.
-constexpr int SS_THREADS = 256;
-constexpr int SS_GROUPS = SS_THREADS / 8;
-struct SegParams {
-    const float* pts;
-    const void* feats;
-    const void* cls;
-    int feat_u8, cls_u8;
-    int RS, fdim, ldim;
-    const unsigned long long* keys[2];
-    const unsigned* idx[2];
-    Meta* meta;
-    const unsigned* headmask;
-    const unsigned* first_vid;
-    float* out_p;
-    float* out_f;
-    int* out_c;
-    unsigned long long* out_k;
-    int* out_n;
-};
-
-// value of column `col` of input row `row` as 32 bits (labels travel as int bits)
-__device__ __forceinline__ float seg_load(const SegParams& p, unsigned long long row, int col) {
-    if (col < 3) return __ldg(p.pts + 3ull * row + col);
-    if (col < 3 + p.fdim) {
-        const unsigned long long o = row * (unsigned long long)p.fdim + (col - 3);
-        return p.feat_u8 ? (float)__ldg(reinterpret_cast<const unsigned char*>(p.feats) + o)
-                         : __ldg(reinterpret_cast<const float*>(p.feats) + o);
-    }
-    const unsigned long long o = row * (unsigned long long)p.ldim + (col - 3 - p.fdim);
-    return __int_as_float(p.cls_u8 ? (int)__ldg(reinterpret_cast<const unsigned char*>(p.cls) + o)
-                                   : __ldg(reinterpret_cast<const int*>(p.cls) + o));
-}
-
-// closes voxel `vid` = sorted records [seg_start, seg_start + cnt) for one column
-__device__ __noinline__ void seg_emit(const SegParams& p, const unsigned long long* keys, int col, unsigned vid, float acc,
-                                      unsigned cnt, unsigned long long seg_start, const int* labs, const int* cnts, int nl) {
-    if (col < 3 + p.fdim) {
-        // grid_subsampling.cpp:87: double reciprocal narrowed to float for the barycentre; :90-95 true division for features
-        if (col < 3) p.out_p[3ull * vid + col] = __fmul_rn(acc, (float)(1.0 / (double)cnt));
-        else p.out_f[(unsigned long long)vid * p.fdim + (col - 3)] = __fdiv_rn(acc, (float)cnt);
-        if (col == 0) {
-            p.out_k[vid] = keys[seg_start];
-            p.out_n[vid] = (int)cnt;
-        }
-    } else {
-        int best = -1, nbest = 0, arg = 0;
-        for (int q = 0; q < nl; ++q) {
-            if (cnts[q] > best) {
-                best = cnts[q];
-                nbest = 1;
-                arg = q;
-            } else if (cnts[q] == best)
-                ++nbest;
-        }
-        p.out_c[vid] = nbest == 1 ? labs[arg] : label_first_in_iteration_order(labs, cnts, nl, best);
-    }
-}
-
-__global__ void __launch_bounds__(SS_THREADS, 3) segsum_kernel(const SegParams p) {
-    __shared__ int s_labs[SS_GROUPS][LABEL_CAP], s_cnts[SS_GROUPS][LABEL_CAP];
-    const unsigned long long n = p.meta->n_sel;
-    const unsigned long long nchunks = (n + 31) / 32;
-    const int cur = p.meta->cur;
-    const unsigned long long* keys = p.keys[cur];
-    const unsigned* idx = p.idx[cur];
-    const int tid = threadIdx.x, g = tid >> 3, l = tid & 7;
-    int* labs = s_labs[g];
-    int* cnts = s_cnts[g];
-    const int nsum = 3 + p.fdim;
-    bool overflow = false;
-    if (blockIdx.x == 0 && tid == 0) p.meta->tmark[13] = gtimer_ns();
-    const unsigned long long ngroups = (unsigned long long)gridDim.x * SS_GROUPS;
-    for (unsigned long long chunk = (unsigned long long)blockIdx.x * SS_GROUPS + g; chunk < nchunks; chunk += ngroups) {
-        const unsigned fv = p.first_vid[chunk];
-        if (fv == NO_HEAD) continue;  // the whole chunk continues a voxel that began earlier
-        for (int col = l; col < p.RS; col += 8) {
-            const bool is_label = col >= nsum;
-            unsigned long long blk = chunk * 32ull;
-            unsigned hm = p.headmask[chunk];
-            unsigned vid = fv - 1u;
-            bool open = false, done = false;
-            float acc = 0.f;
-            int nl = 0, last = 0;
-            unsigned long long seg_start = 0;
-            float cur8[8], nxt8[8];
-#pragma unroll
-            for (int tt = 0; tt < 8; ++tt) cur8[tt] = blk + tt < n ? seg_load(p, idx[blk + tt], col) : 0.f;
-            while (!done) {
-#pragma unroll
-                for (int tt = 0; tt < 8; ++tt) nxt8[tt] = blk + 8 + tt < n ? seg_load(p, idx[blk + 8 + tt], col) : 0.f;
-                const unsigned hm8 = (hm >> (unsigned)(blk & 31ull)) & 0xFFu;
-#pragma unroll
-                for (int tt = 0; tt < 8; ++tt) {
-                    if (!done) {
-                        const unsigned long long i = blk + tt;
-                        const bool beyond = i >= n;
-                        const bool head = !beyond && ((hm8 >> tt) & 1u);
-                        if (head || beyond) {
-                            if (open) {
-                                seg_emit(p, keys, col, vid, acc, (unsigned)(i - seg_start), seg_start, labs, cnts, nl);
-                                open = false;
-                            }
-                            if (beyond || (i >> 5) != chunk) {
-                                done = true;  // heads of later chunks belong to their own groups; or the data ended
-                            } else {
-                                open = true;
-                                acc = 0.f;
-                                nl = 0;
-                                seg_start = i;
-                                ++vid;
-                            }
-                        }
-                        if (open && !done) {
-                            if (!is_label) {
-                                acc = __fadd_rn(acc, cur8[tt]);
-                            } else {
-                                const int lab = __float_as_int(cur8[tt]);
-                                if (nl > 0 && labs[last] == lab) {
-                                    cnts[last] += 1;
-                                } else {
-                                    int q = 0;
-                                    while (q < nl && labs[q] != lab) ++q;
-                                    if (q == nl) {
-                                        if (nl < LABEL_CAP) {
-                                            labs[nl] = lab;
-                                            cnts[nl] = 0;
-                                            ++nl;
-                                        } else {
-                                            overflow = true;
-                                            q = 0;
-                                        }
-                                    }
-                                    cnts[q] += 1;
-                                    last = q;
-                                }
-                            }
-                        }
-                    }
-                }
-                blk += 8;
-#pragma unroll
-                for (int tt = 0; tt < 8; ++tt) cur8[tt] = nxt8[tt];
-                if (!done && (blk & 31ull) == 0) hm = blk < n ? p.headmask[blk >> 5] : 0u;
-            }
-        }
-    }
-    if (overflow) p.meta->error = 2;
-    if (tid == 0) atomicMax(&p.meta->tmark[14], gtimer_ns());
-}
-
 // ---- 7. reference row order: libstdc++ unordered_map<size_t,...> iteration order, epoch by epoch ----------------
 // The map is rehashed through a fixed prime sequence; within one bucket count ("epoch") the list is the sequence of
 // bucket runs in REVERSE order of bucket creation, each run in REVERSE insertion order, where the epoch's insertion
@@ -1392,7 +1239,6 @@ static int run_core(Ctx* c, cudaStream_t s, const Inputs& in, size_t N, size_t f
     SSDR_TRY(c->ws[WS_IDX].reserve(N * sizeof(unsigned)));
     SSDR_TRY(c->ws[WS_IDX2].reserve(N * sizeof(unsigned)));
     SSDR_TRY(c->ws[WS_STARTS].reserve((N + 1) * sizeof(unsigned)));
-    SSDR_TRY(c->ws[WS_HEADS].reserve(2 * (N / 32 + 2) * sizeof(unsigned)));
     // control block: barrier counter | per-CTA partials, largest keys, counts | histogram matrix
     const size_t ctl_bytes = 256 + (size_t)G * (6 * sizeof(float) + sizeof(KeyT) + sizeof(unsigned)) + 256 +
                              (size_t)G * BINS * sizeof(unsigned);
@@ -1420,46 +1266,12 @@ static int run_core(Ctx* c, cudaStream_t s, const Inputs& in, size_t N, size_t f
     sp.cta_count = reinterpret_cast<unsigned*>(ctl + 256 + (size_t)G * (sizeof(KeyT) + 6 * sizeof(float)));
     sp.hist = reinterpret_cast<unsigned*>(ctl + (256 + (size_t)G * (6 * sizeof(float) + sizeof(KeyT) + sizeof(unsigned)) + 255) / 256 * 256);
     sp.starts = c->ws[WS_STARTS].as<unsigned>();
-    sp.headmask = c->ws[WS_HEADS].as<unsigned>();
-    sp.first_vid = sp.headmask + (N / 32 + 2);
     SSDR_CHECK_CUDA(cudaMemsetAsync(sp.barrier, 0, 256, s));
     {
         void* args[] = {(void*)&sp};
         SSDR_CHECK_CUDA(cudaLaunchCooperativeKernel((void*)sort_kernel, dim3(G), dim3(PA_THREADS), args, 0, s));
     }
-    const size_t RS = 3 + fdim + ldim;
-    // SSDR_GRID_REDUCE=1 selects the chunk-driven segmented-sum kernel (A/B measurements); the voxel-driven reduce is
-    // the default: measured faster on B200 for both the room (66 vs 194 us at 1 M points) and the scan shapes
-    const char* rsel = getenv("SSDR_GRID_REDUCE");
-    const bool use_segsum = rsel && rsel[0] == '1';
-    if (use_segsum && ldim <= 1 && RS <= 32) {
-        // fast reduce: segmented sequential sums straight over the sorted order
-        SegParams qp;
-        qp.pts = in.p;
-        qp.feats = fdim ? in.f : nullptr;
-        qp.cls = ldim ? in.c : nullptr;
-        qp.feat_u8 = in.f_u8 ? 1 : 0;
-        qp.cls_u8 = in.c_u8 ? 1 : 0;
-        qp.RS = (int)RS;
-        qp.fdim = (int)fdim;
-        qp.ldim = (int)ldim;
-        qp.keys[0] = sp.keys[0];
-        qp.keys[1] = sp.keys[1];
-        qp.idx[0] = sp.idx[0];
-        qp.idx[1] = sp.idx[1];
-        qp.meta = meta;
-        qp.headmask = sp.headmask;
-        qp.first_vid = sp.first_vid;
-        qp.out_p = out.p;
-        qp.out_f = out.f;
-        qp.out_c = out.c;
-        qp.out_k = out.k;
-        qp.out_n = out.n;
-        const size_t cap = (size_t)c->sm_count * 16;
-        const size_t chunks = (N + 31) / 32;
-        const size_t sb = (chunks + SS_GROUPS - 1) / SS_GROUPS;
-        segsum_kernel<<<(unsigned)(sb < cap ? sb : cap), SS_THREADS, 0, s>>>(qp);
-    } else {
+    {
         ReduceParams rp;
         rp.pts = in.p;
         rp.feats = fdim ? in.f : nullptr;

@@ -17,8 +17,12 @@ int set_error(int status, const char* fmt, ...) {
     return status;
 }
 
+static thread_local unsigned long long g_ws_generation = 0;
+unsigned long long ws_generation() { return g_ws_generation; }
+
 int DevBuf::reserve(size_t bytes) {
     if (bytes <= cap) return SSDR_OK;
+    ++g_ws_generation;
     if (p) cudaFree(p);
     p = nullptr;
     cap = 0;

@@ -1121,8 +1121,8 @@ static int configure(Ctx* c, Launch<T>& L, const T* dF, size_t N, size_t D) {
         groups = (int)(3072 / (4 * row_bytes));
         groups = groups < 1 ? 1 : (groups > 8 ? 8 : groups);
     }
-    if (bulk) {  // measured (tools/sweep_select.py): D = 256 FPS streams best with 8 warps x 2 stages (90 vs 103 us/pick)
-        if (D == 256 && MODE == MODE_FPS) nw = 8;
+    if (bulk) {  // measured (tools/sweep_select.py, N = 500k): 16 warps x 2 stages is best or equal for every fixed D
+                 // (D = 256 FPS 78 us/pick, 8 warps 85; D = 64: 26.9 vs 43; deeper rings add nothing)
         nst = 2;
         if (tn.warps > 0) nw = tn.warps > WARPS ? WARPS : tn.warps;
         if (tn.stages > 0) nst = tn.stages > MAX_STAGES ? MAX_STAGES : (tn.stages < 2 ? 2 : tn.stages);

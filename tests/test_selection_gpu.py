@@ -107,23 +107,42 @@ def test_kcenter_vs_oracle(S, oracle, N, D, dt):
 
 
 # ---- row-sharded selection with the pick exchange fused into the persistent kernel (peer mailboxes) -----------------
-def _virtual_ranks(world, fn):
+def _virtual_ranks(world, fn, warm=None):
     """Run fn(rank, group) on `world` threads: the virtual ranks of a peer group that lives in this one process and on
     this one GPU (each rank launches its persistent kernel with sm_count // world CTAs on its own stream, so all of
-    them are resident together and talk through the same mailbox protocol real ranks use over NVLink)."""
+    them are resident together and talk through the same mailbox protocol real ranks use over NVLink).
+
+    Ranks of ONE device must not allocate while a peer's kernel already spins for them (cudaMalloc, cudaFree and the
+    lazy load of a kernel image may wait for the device, i.e. for the very kernel that waits for this rank): every
+    thread first runs `warm(rank)` -- a single-GPU call of the same shape, which creates the thread's context and sizes
+    its workspaces -- then all ranks meet at a host barrier, enqueue with the time-out check deferred
+    (SSDR_PEER_DEFER_CHECK=1), meet again and only then wait for their streams.  Real ranks own a GPU each and need
+    none of this."""
+    import os
     import threading
     import torch
     from ssdr_al_b200 import dist as SD
     groups = SD.PeerGroup.local(world)
     res, err = [None] * world, []
+    gate = threading.Barrier(world, timeout=120)
+    before = os.environ.get("SSDR_PEER_DEFER_CHECK")
+    os.environ["SSDR_PEER_DEFER_CHECK"] = "1"
 
     def work(r):
         try:
             torch.cuda.set_device(0)
             with torch.cuda.stream(torch.cuda.Stream()):
-                res[r] = fn(r, groups[r])
+                if warm is not None:
+                    warm(r)
                 torch.cuda.current_stream().synchronize()
+                gate.wait()
+                out = fn(r, groups[r])
+                gate.wait()
+                groups[r].check()
+                torch.cuda.current_stream().synchronize()
+                res[r] = out.cpu().numpy()
         except Exception as e:  # noqa: BLE001
+            gate.abort()
             err.append((r, repr(e)))
 
     ts = [threading.Thread(target=work, args=(r,)) for r in range(world)]
@@ -133,6 +152,10 @@ def _virtual_ranks(world, fn):
         t.join()
     for g in groups:
         g.destroy()
+    if before is None:
+        os.environ.pop("SSDR_PEER_DEFER_CHECK", None)
+    else:
+        os.environ["SSDR_PEER_DEFER_CHECK"] = before
     assert not err, err
     return res
 
@@ -153,7 +176,8 @@ def test_sharded_fps_virtual_ranks_equal_single_gpu(S, oracle, monkeypatch, worl
     assert np.array_equal(want, oracle.fps(Fh, picks, 11))
     sms = torch.cuda.get_device_properties(0).multi_processor_count
     for rep in range(2):  # the second call continues the tag sequence of the first (no mailbox is ever cleared)
-        got = _virtual_ranks(world, lambda r, g: SD.fps_sharded(F, picks, 11, g, max_ctas=sms // world).cpu().numpy())
+        got = _virtual_ranks(world, lambda r, g: SD.fps_sharded(F, picks, 11, g, max_ctas=sms // world),
+                             warm=lambda r: dev.fps(F, picks, 11))
         for r in range(world):
             assert np.array_equal(got[r], want), (rep, r)
 
@@ -170,7 +194,8 @@ def test_sharded_kcenter_virtual_ranks_equal_single_gpu(S, oracle, monkeypatch, 
     want = dev.kcenter(X, sel, 90).cpu().numpy()
     assert np.array_equal(want, oracle.kcenter(Xh, np.arange(N - 40, N), 90))
     sms = torch.cuda.get_device_properties(0).multi_processor_count
-    got = _virtual_ranks(2, lambda r, g: SD.kcenter_sharded(X, sel, 90, g, max_ctas=sms // 2).cpu().numpy())
+    got = _virtual_ranks(2, lambda r, g: SD.kcenter_sharded(X, sel, 90, g, max_ctas=sms // 2),
+                         warm=lambda r: dev.kcenter(X, sel, 90))
     assert np.array_equal(got[0], want) and np.array_equal(got[1], want)
 
 
