@@ -633,6 +633,316 @@ __global__ void __launch_bounds__(128) query_kernel(const float4* __restrict__ s
     if ((threadIdx.x & 31) == 0 && my_evals) atomicAdd(evals, (unsigned long long)my_evals);
 }
 
+// ---- B2: main query kernel for 8 < K <= 16: batched selection --------------------------------------------------
+// Still one thread per query and warp-synchronous, but no per-candidate list insertion any more.  A candidate under
+// the lane's threshold is appended to the lane's column of a shared-memory queue (one store); when some lane has 16
+// queued, ALL lanes sort their batch with a 60-comparator network and fold it into their sorted 16-entry list with a
+// bitonic merge -- straight-line code that every lane executes together, so no issue slot is lost to divergence
+// (the one-deep deferred insertion above fires ~90 times per warp for ~10 lanes each; here a warp runs 5 merges).
+// The list holds the 16 nearest; `m17` tracks the smallest distance among everything else that was seen, i.e. the
+// 17th smallest: it is the queue's admission threshold, the row pruning bound, the termination bound and the
+// boundary-tie detector, exactly what dist[16] is in query_kernel<17>.
+// The candidates of a lane are a FLAT stream: the (start, length) pairs of up to Q16_DESC cell rows are computed by the
+// whole warp together (all cell-start loads of the chunk in flight at once, every row's lines prefetched into L1) and
+// parked in shared memory, then every lane walks its own pairs, four candidates per step, so that a lane with a short
+// or pruned row does not idle until the longest row of the warp is done.
+constexpr int Q16_L = 16;      // list entries kept sorted = batch size of a merge
+constexpr int Q16_STEP = 4;    // candidates per lane and scan step
+constexpr int Q16_CAP = Q16_L + Q16_STEP;  // queue rows: a step may overshoot a full batch by STEP - 1 entries
+constexpr int Q16_DESC = 8;    // row descriptors per lane and chunk
+constexpr int Q16_THREADS = 128;
+
+#define SSDR_CE(a, b)                                   \
+    {                                                   \
+        const float x_ = d[a], y_ = d[b];               \
+        const bool p_ = y_ < x_;                        \
+        const unsigned ia_ = i[a], ib_ = i[b];          \
+        d[a] = fminf(x_, y_);                           \
+        d[b] = fmaxf(x_, y_);                           \
+        i[a] = p_ ? ib_ : ia_;                          \
+        i[b] = p_ ? ia_ : ib_;                          \
+    }
+// 60 compare-exchanges, 10 layers (the smallest known 16-input network; 0-1 principle checked exhaustively)
+__device__ __forceinline__ void sort16(float (&d)[16], unsigned (&i)[16]) {
+    SSDR_CE(0, 13) SSDR_CE(1, 12) SSDR_CE(2, 15) SSDR_CE(3, 14) SSDR_CE(4, 8) SSDR_CE(5, 6) SSDR_CE(7, 11) SSDR_CE(9, 10)
+    SSDR_CE(0, 5) SSDR_CE(1, 7) SSDR_CE(2, 9) SSDR_CE(3, 4) SSDR_CE(6, 13) SSDR_CE(8, 14) SSDR_CE(10, 15) SSDR_CE(11, 12)
+    SSDR_CE(0, 1) SSDR_CE(2, 3) SSDR_CE(4, 5) SSDR_CE(6, 8) SSDR_CE(7, 9) SSDR_CE(10, 11) SSDR_CE(12, 13) SSDR_CE(14, 15)
+    SSDR_CE(0, 2) SSDR_CE(1, 3) SSDR_CE(4, 10) SSDR_CE(5, 11) SSDR_CE(6, 7) SSDR_CE(8, 9) SSDR_CE(12, 14) SSDR_CE(13, 15)
+    SSDR_CE(1, 2) SSDR_CE(3, 12) SSDR_CE(4, 6) SSDR_CE(5, 7) SSDR_CE(8, 10) SSDR_CE(9, 11) SSDR_CE(13, 14)
+    SSDR_CE(1, 4) SSDR_CE(2, 6) SSDR_CE(5, 8) SSDR_CE(7, 10) SSDR_CE(9, 13) SSDR_CE(11, 14)
+    SSDR_CE(2, 4) SSDR_CE(3, 6) SSDR_CE(9, 12) SSDR_CE(11, 13)
+    SSDR_CE(3, 5) SSDR_CE(6, 8) SSDR_CE(7, 9) SSDR_CE(10, 12)
+    SSDR_CE(3, 4) SSDR_CE(5, 6) SSDR_CE(7, 8) SSDR_CE(9, 10) SSDR_CE(11, 12)
+    SSDR_CE(6, 7) SSDR_CE(8, 9)
+}
+// ascending order of a bitonic 16-sequence: 4 layers of 8
+__device__ __forceinline__ void bitonic_merge16(float (&d)[16], unsigned (&i)[16]) {
+#pragma unroll
+    for (int st = 8; st > 0; st >>= 1)
+#pragma unroll
+        for (int a = 0; a < 16; ++a)
+            if ((a & st) == 0) SSDR_CE(a, a + st)
+}
+#undef SSDR_CE
+
+// Conservative distance from a coordinate to the slab [u0, u0 + h) of a cell row, all measured from the lower face of
+// the coordinate's own cell: max(u0 - f0, f0 - u0 - h, 0) - eps, never negative.  na = -f0 - eps and nb = f0 - h - eps
+// are per query and axis, so a row costs two adds and one three-input max.
+__device__ __forceinline__ float slab_gap_rel(float u0, float na, float nb) {
+    return fmaxf(fmaxf(u0 + na, nb - u0), 0.f);
+}
+__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+// p = *src where `on`, else p keeps whatever it held (an inactive slot is never looked at, so it needs no value)
+__device__ __forceinline__ void ldg_if(float4& p, const float4* src, bool on) {
+    asm volatile(
+        "{\n\t.reg .pred pp;\n\tsetp.ne.b32 pp, %4, 0;\n\t@pp ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%5];\n\t}"
+        : "+f"(p.x), "+f"(p.y), "+f"(p.z), "+f"(p.w)
+        : "r"((int)on), "l"(src));
+}
+
+template <typename OutT>
+__global__ void __launch_bounds__(Q16_THREADS, 5) query16_kernel(const float4* __restrict__ spts,
+                                                                 const float4* __restrict__ sq,
+                                                                 const unsigned* __restrict__ cell_start,
+                                                                 const ItemMeta* __restrict__ items, unsigned N, unsigned Q,
+                                                                 unsigned q_begin, unsigned q_end, int K,
+                                                                 OutT* __restrict__ out, unsigned* __restrict__ flag_count,
+                                                                 unsigned* __restrict__ flag_list,
+                                                                 unsigned long long* __restrict__ evals) {
+    constexpr unsigned FULL = 0xffffffffu;
+    __shared__ uint2 s_queue[Q16_CAP][Q16_THREADS];  // (distance bits, index); a lane only ever touches its own column
+    __shared__ uint2 s_list[Q16_L][Q16_THREADS];     // the lane's sorted list, parked here between merges
+    __shared__ uint2 s_desc[Q16_DESC][Q16_THREADS];  // (first position, length) of the lane's rows of the current chunk
+    const unsigned tid = threadIdx.x;
+    const unsigned t = q_begin + blockIdx.x * blockDim.x + tid;
+    const bool valid = t < q_end;
+    const unsigned tq = valid ? t : q_end - 1;
+    unsigned my_evals = 0;
+    const unsigned b = tq / Q;
+    const ItemMeta m = items[b];
+    const float4 q = __ldg(sq + tq);
+    const unsigned qid = (unsigned)__float_as_int(q.w);
+    const int gx = m.g[0], gy = m.g[1], gz = m.g[2];
+    const int cx = cell_coord(q.x, m.lo[0], m.inv_h, gx);
+    const int cy = cell_coord(q.y, m.lo[1], m.inv_h, gy);
+    const int cz = cell_coord(q.z, m.lo[2], m.inv_h, gz);
+    const float h = m.h;
+    // offsets of the query above the lower faces of its own cell, folded with the slack (see slab_gap_rel)
+    const float fx0 = q.x - (m.lo[0] + (float)cx * h), fy0 = q.y - (m.lo[1] + (float)cy * h),
+                fz0 = q.z - (m.lo[2] + (float)cz * h);
+    const float nax = -fx0 - m.eps_abs, nbx = fx0 - h - m.eps_abs;
+    const float nay = -fy0 - m.eps_abs, nby = fy0 - h - m.eps_abs;
+    const float naz = -fz0 - m.eps_abs, nbz = fz0 - h - m.eps_abs;
+    const unsigned* cs = cell_start + m.cell_base;
+#pragma unroll
+    for (int j = 0; j < Q16_L; ++j) s_list[j][tid] = make_uint2(0x7F800000u, 0xFFFFFFFFu);
+    float m17 = INFINITY;
+    unsigned cnt = 0;
+    bool done = !valid;
+    float4 p[Q16_STEP];
+#pragma unroll
+    for (int u = 0; u < Q16_STEP; ++u) p[u] = q;
+
+    int r = 1, nseg = 9;            // shell radius and its row segments (warp-uniform)
+    int base = 0;                   // segments of this shell already scanned
+    int it_dz = 0, it_dy = 0, it_lim = 0, it_ph = 0;  // row iterator of shells r >= 2: phase 0 = every row of the
+                                                      // (2r+1)^2 block (whole on the shell's faces, else its left end),
+                                                      // phase 1 = right ends of the interior rows
+    for (;;) {
+        // ---- descriptors of segments [base, base + nk) of shell r.  The two cell-start loads of a segment are used one
+        // iteration later, so a load is in flight while the next segment's geometry is worked out.
+        const int nk = min(Q16_DESC, nseg - base);
+        unsigned pa = 0, pb = 0;  // loads of the previous segment (0, 0 = empty)
+        for (int j = 0; j <= nk; ++j) {
+            unsigned na_ = 0, nb_ = 0;
+            if (j < nk) {
+                int dz, dy, dxa, dxb;  // row offsets; cell offsets of the segment's ends
+                if (r == 1) {
+                    dz = (int)((0x2402049u >> (3 * (base + j))) & 7u) - 1;  // nearest rows first, see query_kernel
+                    dy = (int)((0x2081281u >> (3 * (base + j))) & 7u) - 1;
+                    dxa = -1;
+                    dxb = 1;
+                } else {
+                    dz = it_dz;
+                    dy = it_dy;
+                    const bool whole = it_ph == 0 && (dz == -r || dz == r || dy == -r || dy == r);
+                    dxa = it_ph ? r : -r;
+                    dxb = whole ? r : dxa;
+                    if (++it_dy > it_lim) {
+                        it_dy = -it_lim;
+                        if (++it_dz > it_lim) {
+                            it_ph = 1;
+                            it_lim = r - 1;
+                            it_dz = it_dy = -it_lim;
+                        }
+                    }
+                }
+                const int z = cz + dz, y = cy + dy;
+                const int xa = max(cx + dxa, 0), xb = min(cx + dxb, gx - 1);
+                if (!done && (unsigned)z < (unsigned)gz && (unsigned)y < (unsigned)gy && xa <= xb) {
+                    const float gy_ = slab_gap_rel((float)dy * h, nay, nby);
+                    const float gz_ = slab_gap_rel((float)dz * h, naz, nbz);
+                    // a segment that spans the query's own cell column has no gap along x
+                    const float gx_ = dxa != dxb ? 0.f : slab_gap_rel((float)dxa * h, nax, nbx);
+                    const float lower = (gx_ * gx_ + gy_ * gy_ + gz_ * gz_) * 0.99999f;
+                    if (lower < m17) {
+                        const unsigned row = (unsigned)((z * gy + y) * gx);
+                        na_ = __ldg(cs + row + (unsigned)xa);
+                        nb_ = __ldg(cs + row + (unsigned)xb + 1u);
+                    }
+                }
+            }
+            if (j > 0) {
+                const unsigned len = pb - pa;
+                my_evals += len;
+                s_desc[j - 1][tid] = make_uint2(pa, len);
+                for (unsigned e = 0; e < len; e += 8) prefetch_l1(spts + pa + e);  // 8 records = one 128-byte line
+                if (len) prefetch_l1(spts + pa + len - 1);
+            }
+            pa = na_;
+            pb = nb_;
+        }
+        // ---- flat scan of the chunk; a merge runs whenever some lane has a full batch, and at the end of the shell
+        const bool last_chunk = base + nk >= nseg;
+        int k = 0;
+        unsigned rem = 0, ptr = 0;
+        for (;;) {
+            bool exhausted;
+            for (;;) {
+                while (rem == 0 && k < nk) {
+                    const uint2 dsc = s_desc[k][tid];
+                    ++k;
+                    ptr = dsc.x;
+                    rem = dsc.y;
+                }
+                exhausted = !__any_sync(FULL, rem != 0);
+                if (exhausted) break;
+                const unsigned n = rem < (unsigned)Q16_STEP ? rem : (unsigned)Q16_STEP;
+#pragma unroll
+                for (int u = 0; u < Q16_STEP; ++u) ldg_if(p[u], spts + ptr + u, (unsigned)u < n);
+#pragma unroll
+                for (int u = 0; u < Q16_STEP; ++u) {
+                    const float dx = __fsub_rn(q.x, p[u].x), dy_ = __fsub_rn(q.y, p[u].y), dz_ = __fsub_rn(q.z, p[u].z);
+                    const float d = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy_, dy_)), __fmul_rn(dz_, dz_));
+                    if ((unsigned)u < n && d < m17) {
+                        s_queue[cnt][tid] = make_uint2(__float_as_uint(d), __float_as_uint(p[u].w));
+                        ++cnt;
+                    }
+                }
+                ptr += n;
+                rem -= n;
+                if (__any_sync(FULL, cnt >= (unsigned)Q16_L)) break;
+            }
+            const bool tail = exhausted && last_chunk && __any_sync(FULL, cnt != 0);
+            if (!exhausted || tail) {
+                // ---- merge: sort the batch, keep the 16 smallest of list + batch, fold the rest into m17
+                float d[Q16_L];
+                unsigned i[Q16_L];
+#pragma unroll
+                for (int j = 0; j < Q16_L; ++j) {
+                    const uint2 e = s_queue[j][tid];
+                    d[j] = (unsigned)j < cnt ? __uint_as_float(e.x) : INFINITY;
+                    i[j] = e.y;
+                }
+#pragma unroll
+                for (int u = 0; u < Q16_STEP - 1; ++u)  // entries beyond the batch move to the front of the queue
+                    if ((unsigned)(Q16_L + u) < cnt) s_queue[u][tid] = s_queue[Q16_L + u][tid];
+                cnt = cnt > (unsigned)Q16_L ? cnt - (unsigned)Q16_L : 0u;
+                sort16(d, i);
+                // list ascending against batch descending: the minima are the 16 smallest (a bitonic sequence, here in
+                // the batch's registers, i.e. reversed -- still bitonic), the maxima only matter through their minimum
+                float hmin = INFINITY;
+#pragma unroll
+                for (int j = 0; j < Q16_L; ++j) {
+                    const uint2 e = s_list[j][tid];
+                    const float a = __uint_as_float(e.x), c2 = d[Q16_L - 1 - j];
+                    const bool pa_ = a < c2;
+                    d[Q16_L - 1 - j] = fminf(a, c2);
+                    hmin = fminf(hmin, fmaxf(a, c2));
+                    i[Q16_L - 1 - j] = pa_ ? e.y : i[Q16_L - 1 - j];
+                }
+                m17 = fminf(m17, hmin);
+                bitonic_merge16(d, i);
+#pragma unroll
+                for (int j = 0; j < Q16_L; ++j) s_list[j][tid] = make_uint2(__float_as_uint(d[j]), i[j]);
+            }
+            if (exhausted && !(tail && __any_sync(FULL, cnt != 0))) break;  // (left-overs of a full batch: once more)
+        }
+        if (!last_chunk) {  // next chunk of the same shell
+            base += nk;
+            continue;
+        }
+        // ---- the shell is complete: test termination per lane (the queues are empty)
+        if (!done) {
+            const int x0 = max(cx - r, 0), x1 = min(cx + r, gx - 1);
+            const int y0 = max(cy - r, 0), y1 = min(cy + r, gy - 1);
+            const int z0 = max(cz - r, 0), z1 = min(cz + r, gz - 1);
+            if (x0 == 0 && x1 == gx - 1 && y0 == 0 && y1 == gy - 1 && z0 == 0 && z1 == gz - 1) {
+                done = true;
+            } else {
+                float R = INFINITY;
+                if (cx - r >= 0) R = fminf(R, q.x - (m.lo[0] + (float)(cx - r) * m.h));
+                if (cx + r <= gx - 1) R = fminf(R, (m.lo[0] + (float)(cx + r + 1) * m.h) - q.x);
+                if (cy - r >= 0) R = fminf(R, q.y - (m.lo[1] + (float)(cy - r) * m.h));
+                if (cy + r <= gy - 1) R = fminf(R, (m.lo[1] + (float)(cy + r + 1) * m.h) - q.y);
+                if (cz - r >= 0) R = fminf(R, q.z - (m.lo[2] + (float)(cz - r) * m.h));
+                if (cz + r <= gz - 1) R = fminf(R, (m.lo[2] + (float)(cz + r + 1) * m.h) - q.z);
+                R -= m.eps_abs;
+                // the 17th smallest distance must be strictly inside the guaranteed radius
+                if (R > 0.f && m17 < R * R * 0.99999f) done = true;
+            }
+        }
+        if (!__any_sync(FULL, !done)) break;
+        ++r;
+        const int w = 2 * r + 1;
+        nseg = w * w + (w - 2) * (w - 2);
+        base = 0;
+        it_dz = it_dy = -r;
+        it_lim = r;
+        it_ph = 0;
+    }
+
+    // ---- emit + tie flags (dist[16] of the 17-slot kernel is m17 here)
+    if (valid) {
+        const int nvalid = (unsigned)K < N ? K : (int)N;
+        OutT* o = out + ((size_t)b * Q + qid) * (size_t)K;
+        float Ld[Q16_L];
+        unsigned Li[Q16_L];
+#pragma unroll
+        for (int j = 0; j < Q16_L; ++j) {
+            const uint2 e = s_list[j][tid];
+            Ld[j] = __uint_as_float(e.x);
+            Li[j] = e.y;
+        }
+        bool flag = false;
+        if (K == Q16_L && nvalid == Q16_L && (reinterpret_cast<size_t>(o) & 15) == 0) {  // full, aligned rows: 16-byte stores
+            if (sizeof(OutT) == 8) {
+#pragma unroll
+                for (int j = 0; j < Q16_L; j += 2)
+                    *reinterpret_cast<longlong2*>(o + j) = make_longlong2((long long)Li[j], (long long)Li[j + 1]);
+            } else {
+#pragma unroll
+                for (int j = 0; j < Q16_L; j += 4)
+                    *reinterpret_cast<int4*>(o + j) = make_int4((int)Li[j], (int)Li[j + 1], (int)Li[j + 2], (int)Li[j + 3]);
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < Q16_L; ++j)
+                if (j < nvalid) o[j] = (OutT)Li[j];
+        }
+#pragma unroll
+        for (int j = 0; j < Q16_L; ++j) {
+            const float nxt = j + 1 < Q16_L ? Ld[(j + 1) & (Q16_L - 1)] : m17;
+            if (j + 1 < nvalid && Ld[j] == nxt) flag = true;
+            if (j + 1 == K && N > (unsigned)K && nxt <= Ld[j] * 1.00001f) flag = true;
+        }
+        if (flag) flag_list[atomicAdd(flag_count, 1u)] = b * Q + qid;
+    }
+#pragma unroll
+    for (int mm = 16; mm > 0; mm >>= 1) my_evals += __shfl_xor_sync(FULL, my_evals, mm);
+    if ((tid & 31) == 0 && my_evals) atomicAdd(evals, (unsigned long long)my_evals);
+}
+
 struct DevStats {
     unsigned flag_count;
     unsigned pad;
@@ -641,6 +951,7 @@ struct DevStats {
 
 static float g_occupancy_scale = 0.3f;  // points per cell ~= scale * K (tunable: SSDR_KNN_OCCUPANCY)
 static bool g_probe_on = true;
+static bool g_query_v2 = true;  // SSDR_KNN_QUERY=1 selects the insertion kernel for 8 < K <= 16 (A/B runs)
 
 // Rows the tie path rewrote, compacted for a small second read-back (the bulk read-back of all rows runs on the copy
 // stream while the tie path works; the host then overwrites these rows).
@@ -770,6 +1081,8 @@ static int run_dev(Ctx* c, cudaStream_t s, const float* d_pts, size_t B, size_t 
         if (e && atof(e) > 0) g_occupancy_scale = (float)atof(e);
         const char* pr = getenv("SSDR_KNN_PROBE");  // SSDR_KNN_PROBE=0 switches the occupancy probe off (A/B runs)
         g_probe_on = !(pr && pr[0] == '0');
+        const char* qk = getenv("SSDR_KNN_QUERY");  // SSDR_KNN_QUERY=1: per-candidate insertion kernel for 8 < K <= 16
+        g_query_v2 = !(qk && qk[0] == '1');
     });
     float occupancy = g_occupancy_scale * (float)K;
     occupancy = occupancy < 0.6f ? 0.6f : (occupancy > 24.f ? 24.f : occupancy);
@@ -922,6 +1235,10 @@ static int run_dev(Ctx* c, cudaStream_t s, const float* d_pts, size_t B, size_t 
         if (K == 1) SSDR_QUERY(2);
         else if (K <= 4) SSDR_QUERY(5);
         else if (K <= 8) SSDR_QUERY(9);
+        else if (K <= 16 && g_query_v2)
+            query16_kernel<OutT><<<qblocks, Q16_THREADS, 0, s>>>(sort_p, sort_q, start_p, items, (unsigned)N, (unsigned)Q, qb,
+                                                                 qe, (int)K, d_out, &dstats->flag_count, flag_list,
+                                                                 &dstats->evals);
         else if (K <= 16) SSDR_QUERY(17);
         else if (K <= 32) SSDR_QUERY(33);
         else SSDR_QUERY(65);

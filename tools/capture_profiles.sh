@@ -20,7 +20,7 @@ $NCU_FULL -k regex:select32_kernel -s 1 -c 1 -o $O/${R}_ncu_fps32 python tools/p
 $NCU_FULL -k regex:select32_kernel -s 1 -c 1 -o $O/${R}_ncu_kc32 python tools/prof_select.py kc32 30 > /dev/null 2>&1
 $NCU_FULL -k regex:select_kernel -s 1 -c 1 -o $O/${R}_ncu_fps256 python tools/prof_select.py fps256 30 > /dev/null 2>&1
 $NCU_FULL -k regex:sort_kernel -s 2 -c 1 -o $O/${R}_ncu_grid_sort python tools/prof_select.py grid > /dev/null 2>&1
-$NCU_FULL -k regex:segsum_kernel -s 2 -c 1 -o $O/${R}_ncu_grid_segsum python tools/prof_select.py grid > /dev/null 2>&1
+$NCU_FULL -k regex:reduce_kernel -s 2 -c 1 -o $O/${R}_ncu_grid_reduce python tools/prof_select.py grid > /dev/null 2>&1
 # text summaries next to the reports; gpurun copies back at most 64 MiB, so only a few reports travel
 for f in $O/${R}_ncu_*.ncu-rep; do python tools/ncu_summary.py rep $f > ${f%.ncu-rep}.txt 2>&1; done
 for f in $O/${R}_launches_*.csv; do python tools/ncu_summary.py launches $f > ${f%.csv}.txt 2>&1; done
@@ -29,6 +29,7 @@ python tools/ncu_summary.py traffic $O/${R}_ncu_fps32.ncu-rep fps_d32 $O/${R}_tr
 python tools/ncu_summary.py traffic $O/${R}_ncu_fps256.ncu-rep fps_d256 $O/${R}_traffic.json 29
 python tools/ncu_summary.py traffic $O/${R}_ncu_kc32.ncu-rep kcenter_d32 $O/${R}_traffic.json 45
 python tools/ncu_summary.py traffic $O/${R}_ncu_grid_sort.ncu-rep grid_sort_1m $O/${R}_traffic.json 1000000
-python tools/ncu_summary.py traffic $O/${R}_ncu_grid_segsum.ncu-rep grid_segsum_1m $O/${R}_traffic.json 1000000
-rm -f $O/${R}_ncu_fps256.ncu-rep $O/${R}_ncu_kc32.ncu-rep $O/${R}_ncu_knn_build.ncu-rep $O/${R}_ncu_grid_segsum.ncu-rep
+python tools/ncu_summary.py traffic $O/${R}_ncu_grid_reduce.ncu-rep grid_reduce_1m $O/${R}_traffic.json 1000000
+rm -f $O/${R}_ncu_fps256.ncu-rep $O/${R}_ncu_kc32.ncu-rep $O/${R}_ncu_knn_build.ncu-rep $O/${R}_ncu_grid_reduce.ncu-rep
+for n in 160 640 2560 10240 40960; do python tools/prof_tree.py 6 $n; done > $O/${R}_tree_phases.txt 2>&1
 ls -la $O | tail -30
