@@ -64,7 +64,15 @@ struct Ctx {
     cudaEvent_t ev_async = nullptr;
     cudaStream_t async_stream = nullptr;
     bool async_pending = false;
-    DevBuf ws[WS_SLOTS];            // workspaces, addressed by the owning module
+    DevBuf ws0[WS_SLOTS];           // workspaces, addressed by the owning module
+    DevBuf* ws = ws0;               // the ACTIVE bank: every module says c->ws[slot]
+    // Branches of one call that run side by side on their own streams (the levels of the KNN pyramid) each work in a
+    // bank of their own; bank 0 is ws0.  Banks, streams and events are created on first use and live as long as the Ctx.
+    enum { MAX_BRANCH = 17 };
+    DevBuf* bank[MAX_BRANCH] = {};
+    cudaStream_t branch_stream[MAX_BRANCH] = {};
+    cudaEvent_t ev_branch[MAX_BRANCH] = {};
+    cudaEvent_t ev_fork = nullptr;
     // A calling thread that exits gives its streams, events and workspaces back (loader thread pools come and go).
     ~Ctx();
 };
@@ -77,6 +85,10 @@ int get_ctx(Ctx** out);
 int ctx_order(Ctx* c, cudaStream_t s);
 // Marks `s` as carrying an asynchronous call that ends here.
 int ctx_mark_async(Ctx* c, cudaStream_t s);
+// Branch k of a forked call: makes bank k the active workspace bank and returns its stream (k = 0: bank 0, no stream of
+// its own -- the caller's).  ctx_use_bank(c, 0) restores the default before the entry point returns.
+int ctx_branch(Ctx* c, int k, cudaStream_t* stream);
+void ctx_use_bank(Ctx* c, int k);
 
 // Host -> device copy of `bytes` from an arbitrary host pointer on stream s (pinned sources are truly asynchronous;
 // pageable ones are staged by the driver and return once the source may be reused).

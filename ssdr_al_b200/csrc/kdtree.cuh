@@ -1498,7 +1498,12 @@ static int launch_build(Ctx* c, cudaStream_t s, const float* d_pts, const Tree& 
     const float* pts = d_pts;
     Tree tt = t;
     void* args[] = {(void*)&pts, (void*)&tt};
-    SSDR_CHECK_CUDA(cudaLaunchCooperativeKernel((void*)build_kernel, dim3(c->sm_count), dim3(BT), args, smem, s));
+    // one CTA per 2048 points, at least one per item: a small cloud's build keeps to a few SMs (its barriers are
+    // cheaper, and the branches of a pyramid that run beside it keep the others)
+    size_t grid = ((size_t)t.B * t.N + 2047) / 2048;
+    grid = grid < t.B ? t.B : grid;
+    grid = grid > (size_t)c->sm_count ? (size_t)c->sm_count : grid;
+    SSDR_CHECK_CUDA(cudaLaunchCooperativeKernel((void*)build_kernel, dim3((unsigned)grid), dim3(BT), args, smem, s));
     return SSDR_OK;
 }
 

@@ -1429,15 +1429,55 @@ static int pyramid_dev(Ctx* c, cudaStream_t s, const float* d_points, size_t B, 
         level[l + 1] = w;
         w += B * n[l + 1] * 3;
     }
-    AsyncCtx ac;
-    SSDR_TRY(async_status_word(c, s, &ac.status));
+    unsigned* status = nullptr;
+    SSDR_TRY(async_status_word(c, s, &status));
     g_last_launches = 0;
-    for (size_t l = 0; l < n_levels; ++l) {
-        ac.reuse = l > 0;  // the trees of this level's cloud belong to the previous level's up-sampling query
-        SSDR_TRY((run_dev<long long>(c, s, level[l], B, n[l], level[l], n[l], K, d_neigh[l], nullptr, nullptr, &ac)));
-        ac.reuse = false;
-        SSDR_TRY((run_dev<long long>(c, s, level[l + 1], B, n[l + 1], level[l], n[l], 1, d_up[l], nullptr, nullptr, &ac)));
+    static const bool branches_on = [] {
+        const char* e = getenv("SSDR_KNN_BRANCHES");  // SSDR_KNN_BRANCHES=0: every call behind the previous one (A/B runs)
+        return !(e && e[0] == '0');
+    }();
+    if (!branches_on) {
+        AsyncCtx ac;
+        ac.status = status;
+        for (size_t l = 0; l < n_levels; ++l) {
+            ac.reuse = l > 0;  // the trees of this level's cloud belong to the previous level's up-sampling query
+            SSDR_TRY((run_dev<long long>(c, s, level[l], B, n[l], level[l], n[l], K, d_neigh[l], nullptr, nullptr, &ac)));
+            ac.reuse = false;
+            SSDR_TRY((run_dev<long long>(c, s, level[l + 1], B, n[l + 1], level[l], n[l], 1, d_up[l], nullptr, nullptr, &ac)));
+        }
+        return mark_async ? ctx_mark_async(c, s) : SSDR_OK;
     }
+    // The calls only depend on each other through the trees of a shared support cloud (the 1-NN query onto level j and
+    // the k-NN query of level j itself), so the pyramid is n_levels + 1 independent BRANCHES, one per support cloud:
+    // branch j = [1-NN of level j-1 onto level j] -> [k-NN of level j].  Branch 0 stays on the caller's stream, the
+    // others run on streams of their own, each in its own workspace bank, forked behind the packing copies and joined
+    // before the call returns: the small levels' latency-bound kernels fill the SMs the big level leaves idle.
+    struct Restore {
+        Ctx* c;
+        ~Restore() { ctx_use_bank(c, 0); }
+    } restore{c};
+    SSDR_TRY(ctx_branch(c, 0, nullptr));
+    SSDR_CHECK_CUDA(cudaEventRecord(c->ev_fork, s));
+    for (size_t j = 0; j <= n_levels; ++j) {
+        cudaStream_t bs = s;
+        if (j > 0) {
+            SSDR_TRY(ctx_branch(c, (int)j, &bs));
+            SSDR_CHECK_CUDA(cudaStreamWaitEvent(bs, c->ev_fork, 0));
+        }
+        AsyncCtx ac;
+        ac.status = status;
+        ac.reuse = false;
+        if (j > 0)
+            SSDR_TRY((run_dev<long long>(c, bs, level[j], B, n[j], level[j - 1], n[j - 1], 1, d_up[j - 1], nullptr, nullptr,
+                                         &ac)));
+        if (j < n_levels) {
+            ac.reuse = j > 0;  // the trees of this cloud belong to the up-sampling query just enqueued
+            SSDR_TRY((run_dev<long long>(c, bs, level[j], B, n[j], level[j], n[j], K, d_neigh[j], nullptr, nullptr, &ac)));
+        }
+        if (j > 0) SSDR_CHECK_CUDA(cudaEventRecord(c->ev_branch[j], bs));
+    }
+    for (size_t j = 1; j <= n_levels; ++j) SSDR_CHECK_CUDA(cudaStreamWaitEvent(s, c->ev_branch[j], 0));
+    ctx_use_bank(c, 0);
     // the call returns with its work in flight: later calls are ordered behind it (a capture records no event)
     return mark_async ? ctx_mark_async(c, s) : SSDR_OK;
 }

@@ -55,7 +55,21 @@ Ctx::~Ctx() {
     }
     if (stream) cudaStreamSynchronize(stream);
     if (copy_stream) cudaStreamSynchronize(copy_stream);
-    for (int i = 0; i < WS_SLOTS; ++i) ws[i].release();
+    for (int k = 1; k < MAX_BRANCH; ++k) {
+        if (branch_stream[k]) cudaStreamSynchronize(branch_stream[k]);
+        if (bank[k]) {
+            for (int i = 0; i < WS_SLOTS; ++i) bank[k][i].release();
+            delete[] bank[k];
+        }
+        if (ev_branch[k]) cudaEventDestroy(ev_branch[k]);
+        if (branch_stream[k]) cudaStreamDestroy(branch_stream[k]);
+        bank[k] = nullptr;
+        ev_branch[k] = nullptr;
+        branch_stream[k] = nullptr;
+    }
+    if (ev_fork) cudaEventDestroy(ev_fork);
+    for (int i = 0; i < WS_SLOTS; ++i) ws0[i].release();
+    ws = ws0;
     if (ev) cudaEventDestroy(ev);
     if (ev_main) cudaEventDestroy(ev_main);
     if (ev_async) cudaEventDestroy(ev_async);
@@ -133,6 +147,21 @@ int ctx_mark_async(Ctx* c, cudaStream_t s) {
     c->async_pending = true;
     return SSDR_OK;
 }
+
+int ctx_branch(Ctx* c, int k, cudaStream_t* stream) {
+    if (k < 0 || k >= Ctx::MAX_BRANCH) return set_error(SSDR_ERR_INVALID, "branch %d out of range", k);
+    if (!c->ev_fork) SSDR_CHECK_CUDA(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+    if (k > 0) {
+        if (!c->bank[k]) c->bank[k] = new DevBuf[WS_SLOTS];
+        if (!c->branch_stream[k]) SSDR_CHECK_CUDA(cudaStreamCreateWithFlags(&c->branch_stream[k], cudaStreamNonBlocking));
+        if (!c->ev_branch[k]) SSDR_CHECK_CUDA(cudaEventCreateWithFlags(&c->ev_branch[k], cudaEventDisableTiming));
+    }
+    ctx_use_bank(c, k);
+    if (stream) *stream = k > 0 ? c->branch_stream[k] : nullptr;
+    return SSDR_OK;
+}
+
+void ctx_use_bank(Ctx* c, int k) { c->ws = (k > 0 && c->bank[k]) ? c->bank[k] : c->ws0; }
 
 int h2d(Ctx* c, void* dst, const void* src, size_t bytes, cudaStream_t s) {
     (void)c;
