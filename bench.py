@@ -223,9 +223,10 @@ def run_ours(args):
         # counted inside the library where the launches happen (memsets and torch's slicing copies not included)
         return sum(int(st["kernel_launches"]) for _, _, st in stats)
 
-    def gpu_pyramid_fused():
-        # the same ten queries through ONE C-ABI call (ssdr_knn_pyramid_dev): no host round trip between the levels
-        D.knn_pyramid(xyz0, RATIOS, K, neigh=outs16, up=outs1)
+    def gpu_pyramid_fused(xyz=None):
+        # the same ten queries through ONE C-ABI call (ssdr_knn_pyramid_dev): no host round trip between the levels,
+        # the support clouds searched side by side
+        D.knn_pyramid(xyz0 if xyz is None else xyz, RATIOS, K, neigh=outs16, up=outs1)
 
     headline = gpu_pyramid if args.per_call else gpu_pyramid_fused
     for _ in range(max(args.warmup, 3)):
@@ -316,12 +317,39 @@ def run_ours(args):
 
     e2e_val, h2d_b, d2h_b, e2e_steps = time_api(host_clouds)
     e2e_pinned, _, _, _ = time_api(pinned)
+
+    # the same pyramid through the ONE-call host entry (nearest_neighbors.knn_pyramid = the loop of
+    # s3dis_dataset.py:164-177 as a single C-ABI call): one upload, rows copied back under the other levels' kernels
+    def api_pyramid_one_call(xyz):
+        neigh, up = NN.knn_pyramid(xyz, RATIOS, K)
+        return xyz.nbytes, sum(a.nbytes for a in neigh) + sum(a.nbytes for a in up)
+
+    def time_one_call(src):
+        for _ in range(2):
+            hb, db = api_pyramid_one_call(src)
+        steps = max(3, min(args.steps, 10))
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            api_pyramid_one_call(src)
+        dt = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([dt], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        return K16_QUERIES * world * steps / dt, hb, db
+
+    one_val, one_h2d, one_d2h = time_one_call(host_clouds)
+    got_n, got_u = NN.knn_pyramid(host_clouds, RATIOS, K)
+    one_equal = all(np.array_equal(a, b_.cpu().numpy()) for a, b_ in zip(got_n + got_u, want16 + want1))
+    del got_n, got_u
     clocks = sampler.stop() if rank == 0 else None
 
     # ---- secondary numbers of the same hot path (rank 0, short): grid subsampling, config-1 KNN, FPS / k-center
     extra = {}
     if rank == 0 and not args.no_extra:
-        extra = secondary_metrics(torch, D, dev, flush, gpu_pyramid)
+        extra = secondary_metrics(torch, D, dev, flush, gpu_pyramid, gpu_pyramid_fused)
     # ---- sharded paths: all ranks take part (at N = 1 the same workloads run on the one GPU)
     mg_ok = True
     if not args.no_extra and not args.no_multi:
@@ -355,11 +383,16 @@ def run_ours(args):
         "e2e": {"value": e2e_val, "unit": "queries/s",
                 "h2d_bytes_per_step": int(h2d_b), "d2h_bytes_per_step": int(d2h_b), "steps": e2e_steps,
                 "input": "pageable numpy arrays (what the dataset loader passes)", "pinned_input_value": e2e_pinned,
-                "api": "ssdr_al_b200.nearest_neighbors.knn_batch (numpy in/out, int64 indices)"},
+                "api": "ssdr_al_b200.nearest_neighbors.knn_batch (numpy in/out, int64 indices), ten calls per pyramid "
+                       "exactly like the reference loop",
+                "one_call": {"value": one_val, "unit": "queries/s", "h2d_bytes_per_step": int(one_h2d),
+                             "d2h_bytes_per_step": int(one_d2h), "equals_ten_calls": bool(one_equal),
+                             "api": "ssdr_al_b200.nearest_neighbors.knn_pyramid (the same loop as ONE C-ABI call, "
+                                    "ssdr_knn_pyramid; pageable numpy in, int64 numpy out)"}},
         "gpu_launches": launches_per_step * args.steps,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": ncu_traffic("knn_query_kernel_level0"), "peak_source": peak_src,
-                     "kernel": "knn::query_kernel<17,int64> level 0 (6x40960)",
+                     "kernel": "knn::query16_kernel<int64> level 0 (6x40960)",
                      "kernel_ms": dom_ms_avg, "algorithmic_bytes": algo_bytes,
                      "note": "KNN is FP32/issue bound, not HBM bound (SURVEY.md 8d): the numbers that bound it are "
                              "dist_evals_per_s and `issue` (ncu capture of the same launch)",
@@ -367,7 +400,8 @@ def run_ours(args):
                      "issue": ncu_issue("knn_query_kernel_level0")},
         "clocks": clocks,
         "headline_call": ("ten ssdr_knn_batch_dev calls" if args.per_call else
-                          "one ssdr_knn_pyramid_dev call (all levels enqueued without a host round trip)"),
+                          "one ssdr_knn_pyramid_dev call (no host round trip; the support clouds run as concurrent branches, "
+                          "replayed as one CUDA graph)"),
         "pyramid_call_equals_per_call_results": bool(pyramid_equal),
         "knn_detail": {"tie_rows_per_step": int(tie_rows), "stage_ms": [
             {"call": kind, "level_points": LEVELS[li], "grid_build_ms": st["grid_build_ms"],
@@ -426,7 +460,7 @@ def _oracle():
         return None
 
 
-def secondary_metrics(torch, D, dev, flush, gpu_pyramid):
+def secondary_metrics(torch, D, dev, flush, gpu_pyramid, gpu_pyramid_fused):
     """Grid subsampling + KNN (config-1 shape), FPS / k-center (config-4 shape), the tie-heavy pyramid (8f-1), chamfer
     adjacency: device resident, CUDA-event timed, each with its end-to-end and CPU-reference figure beside it."""
     from tools import synth
@@ -511,8 +545,9 @@ def secondary_metrics(torch, D, dev, flush, gpu_pyramid):
             crops.append(room[rng.permutation(np.argpartition(dd, N0)[:N0])])
         crops = np.stack(crops)
         cx = torch.from_numpy(crops).to(dev)
-        gpu_pyramid(xyz=cx)
-        ms, _ = timed(lambda: gpu_pyramid(xyz=cx), 7)
+        for _ in range(3):
+            gpu_pyramid_fused(cx)
+        ms, _ = timed(lambda: gpu_pyramid_fused(cx), 7)
         out["pyramid_surface_crops"] = {"batch": B, "points": N0, "ms": ms, "k16_queries_per_s": K16_QUERIES / ms * 1e3}
         # duplicate-heavy input -- the loader's data_aug pads short crops by REPEATING points
         # (s3dis_dataset.py:147-150), so most rows of such a batch hold exact distance ties and take the tie path
@@ -524,7 +559,9 @@ def secondary_metrics(torch, D, dev, flush, gpu_pyramid):
         cd = torch.from_numpy(dup).to(dev)
         st = []
         gpu_pyramid(collect=st, xyz=cd)
-        ms, _ = timed(lambda: gpu_pyramid(xyz=cd), 5)
+        for _ in range(3):
+            gpu_pyramid_fused(cd)
+        ms, _ = timed(lambda: gpu_pyramid_fused(cd), 5)
         out["pyramid_duplicated_points"] = {
             "batch": B, "points": N0, "duplicated_fraction": 0.5, "ms": ms, "k16_queries_per_s": K16_QUERIES / ms * 1e3,
             "tie_rows_per_step": int(sum(s_[2]["tie_rows"] for s_ in st)),

@@ -109,6 +109,12 @@ int ssdr_knn_batch_dev_i32(const float* d_points, size_t batch_size, size_t npts
 int ssdr_knn_pyramid_dev(const float* d_points, size_t batch_size, size_t npts, const int32_t* ratios, size_t n_levels,
                          size_t K, int64_t* const* d_neigh, int64_t* const* d_up, void* stream);
 int ssdr_knn_status(void* stream);
+/* The same pyramid with HOST arrays in and out, synchronous: batch_xyz (B, npts, dim == 3) float32, neigh[l] (B, N_l, K)
+ * and up[l] (B, N_l, 1) int64 host arrays (pinned or pageable).  One upload of the points (the levels are prefixes),
+ * the support clouds run as concurrent branches on the device and every branch's rows are copied back on the branch's
+ * own stream while the others compute.  Requires K <= N_l for every level. */
+int ssdr_knn_pyramid(const float* batch_xyz, size_t batch_size, size_t npts, size_t dim, const int32_t* ratios,
+                     size_t n_levels, size_t K, int64_t* const* neigh, int64_t* const* up);
 unsigned long long ssdr_knn_pyramid_launches(void); /* kernels launched by the calling thread's last pyramid call */
 
 /* Diagnostic only: the nanoflann-identical tree built on the device for one cloud (node arrays: 3*npts+64 entries). */

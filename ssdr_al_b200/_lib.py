@@ -40,6 +40,7 @@ SIGNATURES = {
     "ssdr_knn_batch_dev": [vp, sz, sz, vp, sz, sz, vp, vp, C.POINTER(KnnStats)],
     "ssdr_knn_batch_dev_i32": [vp, sz, sz, vp, sz, sz, vp, vp, C.POINTER(KnnStats)],
     "ssdr_knn_pyramid_dev": [vp, sz, sz, vp, sz, sz, vp, vp, vp],
+    "ssdr_knn_pyramid": [vp, sz, sz, sz, vp, sz, sz, vp, vp],
     "ssdr_knn_status": [vp],
     "ssdr_knn_pyramid_launches": [],
     "ssdr_knn_debug_tree": [vp, sz, vp, vp, vp, vp, vp, vp, vp, vp, vp],

@@ -17,6 +17,7 @@
 #include <mutex>
 #include <vector>
 
+#include <time.h>
 #include "common.cuh"
 #include "kdtree.cuh"
 #include "primitives.cuh"
@@ -1402,7 +1403,8 @@ static int async_status_word(Ctx* c, cudaStream_t s, unsigned** out) {
 
 // The loop of s3dis_dataset.py:164-177 in one call, every level enqueued behind the previous one.
 static int pyramid_dev(Ctx* c, cudaStream_t s, const float* d_points, size_t B, size_t npts, const int32_t* ratios,
-                       size_t n_levels, size_t K, long long* const* d_neigh, long long* const* d_up, bool mark_async) {
+                       size_t n_levels, size_t K, long long* const* d_neigh, long long* const* d_up, bool mark_async,
+                       long long* const* h_neigh = nullptr, long long* const* h_up = nullptr) {
     SSDR_REQUIRE(d_points && ratios && d_neigh && d_up, SSDR_ERR_INVALID, "NULL pointer");
     SSDR_REQUIRE(n_levels >= 1 && n_levels <= 16, SSDR_ERR_INVALID, "n_levels must be in [1, 16]");
     SSDR_REQUIRE(npts >= 1 && K >= 1, SSDR_ERR_INVALID, "npts and K must be >= 1");
@@ -1444,6 +1446,11 @@ static int pyramid_dev(Ctx* c, cudaStream_t s, const float* d_points, size_t B, 
             SSDR_TRY((run_dev<long long>(c, s, level[l], B, n[l], level[l], n[l], K, d_neigh[l], nullptr, nullptr, &ac)));
             ac.reuse = false;
             SSDR_TRY((run_dev<long long>(c, s, level[l + 1], B, n[l + 1], level[l], n[l], 1, d_up[l], nullptr, nullptr, &ac)));
+            if (h_neigh)
+                SSDR_CHECK_CUDA(cudaMemcpyAsync(h_neigh[l], d_neigh[l], B * n[l] * K * sizeof(long long),
+                                                cudaMemcpyDeviceToHost, s));
+            if (h_up)
+                SSDR_CHECK_CUDA(cudaMemcpyAsync(h_up[l], d_up[l], B * n[l] * sizeof(long long), cudaMemcpyDeviceToHost, s));
         }
         return mark_async ? ctx_mark_async(c, s) : SSDR_OK;
     }
@@ -1458,11 +1465,17 @@ static int pyramid_dev(Ctx* c, cudaStream_t s, const float* d_points, size_t B, 
     } restore{c};
     SSDR_TRY(ctx_branch(c, 0, nullptr));
     SSDR_CHECK_CUDA(cudaEventRecord(c->ev_fork, s));
-    for (size_t j = 0; j <= n_levels; ++j) {
+    // host flavour: branch 0 goes LAST and through the synchronous host path of run_dev -- its 31 MB of rows leave in two
+    // chunks under the second query launch and the tie path, the few rewritten rows follow as a patch -- while the
+    // other branches, already enqueued, run beside it
+    for (size_t jj = 0; jj <= n_levels; ++jj) {
+        const size_t j = h_neigh ? (jj + 1) % (n_levels + 1) : jj;
         cudaStream_t bs = s;
         if (j > 0) {
             SSDR_TRY(ctx_branch(c, (int)j, &bs));
             SSDR_CHECK_CUDA(cudaStreamWaitEvent(bs, c->ev_fork, 0));
+        } else {
+            ctx_use_bank(c, 0);
         }
         AsyncCtx ac;
         ac.status = status;
@@ -1470,10 +1483,20 @@ static int pyramid_dev(Ctx* c, cudaStream_t s, const float* d_points, size_t B, 
         if (j > 0)
             SSDR_TRY((run_dev<long long>(c, bs, level[j], B, n[j], level[j - 1], n[j - 1], 1, d_up[j - 1], nullptr, nullptr,
                                          &ac)));
-        if (j < n_levels) {
+        if (j == 0 && h_neigh) {
+            kdtree::invalidate_tree_cache(c);  // (the synchronous path would first check the previous call's trees)
+            SSDR_TRY((run_dev<long long>(c, s, level[0], B, n[0], level[0], n[0], K, d_neigh[0], nullptr, h_neigh[0], nullptr)));
+        } else if (j < n_levels) {
             ac.reuse = j > 0;  // the trees of this cloud belong to the up-sampling query just enqueued
             SSDR_TRY((run_dev<long long>(c, bs, level[j], B, n[j], level[j], n[j], K, d_neigh[j], nullptr, nullptr, &ac)));
         }
+        // host flavour: a branch's rows start their way home on the branch's own stream, under the other branches' kernels
+        if (h_up && j > 0)
+            SSDR_CHECK_CUDA(cudaMemcpyAsync(h_up[j - 1], d_up[j - 1], B * n[j - 1] * sizeof(long long),
+                                            cudaMemcpyDeviceToHost, bs));
+        if (h_neigh && j > 0 && j < n_levels)
+            SSDR_CHECK_CUDA(cudaMemcpyAsync(h_neigh[j], d_neigh[j], B * n[j] * K * sizeof(long long),
+                                            cudaMemcpyDeviceToHost, bs));
         if (j > 0) SSDR_CHECK_CUDA(cudaEventRecord(c->ev_branch[j], bs));
     }
     for (size_t j = 1; j <= n_levels; ++j) SSDR_CHECK_CUDA(cudaStreamWaitEvent(s, c->ev_branch[j], 0));
@@ -1587,6 +1610,74 @@ int ssdr_knn_pyramid_dev(const float* d_points, size_t batch_size, size_t npts, 
     return knn::pyramid_dev(c, s, d_points, batch_size, npts, ratios, n_levels, K, neigh, up, true);
 }
 unsigned long long ssdr_knn_pyramid_launches(void) { return knn::g_last_launches; }
+int ssdr_knn_pyramid(const float* batch_xyz, size_t batch_size, size_t npts, size_t dim, const int32_t* ratios,
+                     size_t n_levels, size_t K, int64_t* const* neigh, int64_t* const* up) {
+    using namespace knn;
+    SSDR_REQUIRE(batch_xyz && ratios && neigh && up, SSDR_ERR_INVALID, "NULL pointer");
+    SSDR_REQUIRE(dim == 3, SSDR_ERR_UNSUPPORTED, "dim=%zu: only 3-D points are supported", dim);
+    SSDR_REQUIRE(n_levels >= 1 && n_levels <= 16, SSDR_ERR_INVALID, "n_levels must be in [1, 16]");
+    Ctx* c;
+    SSDR_TRY(get_ctx(&c));
+    if (batch_size == 0) return SSDR_OK;
+    const size_t B = batch_size;
+    size_t n = npts, rows = 0;
+    for (size_t l = 0; l < n_levels; ++l) {
+        SSDR_REQUIRE(ratios[l] >= 1 && n / (size_t)ratios[l] >= 1, SSDR_ERR_INVALID, "bad sub-sampling ratio at level %zu", l);
+        SSDR_REQUIRE(K <= n, SSDR_ERR_UNSUPPORTED, "K=%zu exceeds the %zu points of level %zu", K, n, l);
+        rows += B * n;
+        n /= (size_t)ratios[l];
+    }
+    cudaStream_t s = c->stream;
+    static const bool trace = getenv("SSDR_TRACE") != nullptr;
+    auto now = [] {
+        timespec ts;
+        clock_gettime(CLOCK_MONOTONIC, &ts);
+        return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
+    };
+    const double t0 = trace ? now() : 0.0;
+    SSDR_TRY(c->ws[WS_IN_P].reserve(B * npts * 3 * sizeof(float)));
+    SSDR_TRY(c->ws[WS_OUT].reserve(rows * (K + 1) * sizeof(long long)));
+    SSDR_TRY(h2d(c, c->ws[WS_IN_P].p, batch_xyz, B * npts * 3 * sizeof(float), s));
+    const double t1 = trace ? now() : 0.0;
+    long long* dn[16];
+    long long* du[16];
+    long long* w = c->ws[WS_OUT].as<long long>();
+    n = npts;
+    for (size_t l = 0; l < n_levels; ++l) {
+        dn[l] = w;
+        w += B * n * K;
+        du[l] = w;
+        w += B * n;
+        n /= (size_t)ratios[l];
+    }
+    // no return path may leave a copy into the caller's arrays in flight
+    struct Fence {
+        Ctx* c;
+        ~Fence() {
+            cudaStreamSynchronize(c->stream);
+            for (int k = 1; k < Ctx::MAX_BRANCH; ++k)
+                if (c->branch_stream[k]) cudaStreamSynchronize(c->branch_stream[k]);
+        }
+    };
+    int rc;
+    double t2 = 0.0;
+    {
+        Fence fence{c};
+        rc = pyramid_dev(c, s, c->ws[WS_IN_P].as<float>(), B, npts, ratios, n_levels, K, dn, du, false,
+                         reinterpret_cast<long long* const*>(neigh), reinterpret_cast<long long* const*>(up));
+        if (trace) t2 = now();
+    }
+    if (trace)
+        fprintf(stderr, "ssdr_knn_pyramid: upload %.3f ms, enqueue + branch 0 %.3f ms, other branches %.3f ms\n", t1 - t0,
+                t2 - t1, now() - t2);
+    SSDR_TRY(rc);
+    unsigned* word = nullptr;
+    SSDR_TRY(async_status_word(c, s, &word));
+    unsigned h = 0;
+    SSDR_TRY(d2h_sync(c, &h, word, sizeof(h), s));
+    if (h) SSDR_CHECK_CUDA(cudaMemsetAsync(word, 0, sizeof(unsigned), s));
+    return kdtree::tree_error_to_status(h);
+}
 int ssdr_knn_status(void* stream) {
     Ctx* c;
     SSDR_TRY(get_ctx(&c));

@@ -47,6 +47,32 @@ def knn_batch(pts, queries, K, omp=False):
     return indices
 
 
+def knn_pyramid(batch_xyz, ratios, K):
+    """RandLA-Net's input pyramid, the loop of s3dis_dataset.py:164-177 (tf_map) / helper_tool.py:173-183, in ONE call:
+
+        for i in range(num_layers):
+            neigh[i] = knn_batch(xyz, xyz, K);  sub = xyz[:, :N // ratios[i], :];  up[i] = knn_batch(sub, xyz, 1);  xyz = sub
+
+    batch_xyz (B, N, 3) -> (neigh, up): lists of int64 arrays, neigh[i] (B, N_i, K) and up[i] (B, N_i, 1), identical to
+    what the ten calls return.  The points travel to the device once, the support clouds are searched side by side
+    and every level's rows are copied back while the others still compute."""
+    import ctypes as C
+    xyz = np.ascontiguousarray(batch_xyz, dtype=np.float32)
+    _check_dim(xyz.shape[2])
+    B, n = xyz.shape[0], xyz.shape[1]
+    L = len(ratios)
+    neigh, up = [], []
+    for r in ratios:
+        neigh.append(_lib.pinned_empty((B, n, K), np.int64))
+        up.append(_lib.pinned_empty((B, n, 1), np.int64))
+        n //= int(r)
+    rat = (C.c_int32 * L)(*[int(r) for r in ratios])
+    pn = (C.c_void_p * L)(*[_lib.ptr(a) for a in neigh])
+    pu = (C.c_void_p * L)(*[_lib.ptr(a) for a in up])
+    _lib.check(_lib.lib().ssdr_knn_pyramid(_lib.ptr(xyz), B, xyz.shape[1], xyz.shape[2], rat, L, int(K), pn, pu))
+    return neigh, up
+
+
 def knn_batch_distance_pick(pts, nqueries, K, omp=False):
     """knn.pyx:111-149.  The reference seeds this with time(0) (knn_.cxx:143), so it is not reproducible, and no
     caller exists anywhere in SSDR-AL; it is exported only so that attribute lookups do not fail."""

@@ -203,6 +203,54 @@ def test_knn_pyramid_single_call_equals_reference(oracle, kind):
             cur = sub
 
 
+def test_knn_pyramid_host_call_equals_the_ten_calls(NN, oracle):
+    """nearest_neighbors.knn_pyramid (host arrays in and out, one C-ABI call) against the loop of
+    s3dis_dataset.py:164-177 run through the reference; three calls in a row so that the branches' workspaces, the
+    copies on the branch streams and the pinned result pool are all reused."""
+    ref = _ref_knn_batch(oracle)
+    ratios = (4, 4, 4, 4, 2)
+    for seed, (B, N) in ((11, (6, 40960)), (12, (2, 4096)), (13, (6, 40960))):
+        rng = np.random.default_rng(seed)
+        xyz = (rng.uniform(-1, 1, (B, N, 3)) * np.array([2.0, 2.0, 1.5])).astype(np.float32)
+        if seed == 13:  # duplicate-heavy: most rows take the tie path
+            for b in range(B):
+                xyz[b, N // 2:] = xyz[b, rng.integers(0, N // 2, N - N // 2)]
+        neigh, up = NN.knn_pyramid(xyz, ratios, 16)
+        cur = xyz
+        for l, ratio in enumerate(ratios):
+            assert neigh[l].dtype == np.int64 and neigh[l].shape == (B, cur.shape[1], 16)
+            assert np.array_equal(neigh[l], ref(cur, cur, 16)), (seed, l)
+            sub = np.ascontiguousarray(cur[:, : cur.shape[1] // ratio, :])
+            assert np.array_equal(up[l], ref(sub, cur, 1)), (seed, l)
+            cur = sub
+    with pytest.raises(RuntimeError):
+        NN.knn_pyramid(xyz[:, :32], (4, 4), 16)  # level 1 would hold 8 points, fewer than K
+
+
+def test_knn_pyramid_repeated_calls_replay_and_follow_new_data(oracle):
+    """The device pyramid replays a captured graph from the second identical call on; refilling the SAME device
+    buffer with new points (what a loader does) must give the new cloud's rows, with the branches running side by
+    side in the replay as well."""
+    import torch
+    from ssdr_al_b200 import device as dev
+    ref = _ref_knn_batch(oracle)
+    ratios = (4, 4, 4, 4, 2)
+    B, N = 6, 40960
+    buf = torch.empty((B, N, 3), dtype=torch.float32, device="cuda")
+    neigh = up = None
+    for seed in (21, 22, 23, 24):
+        rng = np.random.default_rng(seed)
+        xyz = (rng.uniform(-1, 1, (B, N, 3)) * np.array([2.0, 2.0, 1.5])).astype(np.float32)
+        buf.copy_(torch.from_numpy(xyz))
+        neigh, up = dev.knn_pyramid(buf, ratios, 16, neigh=neigh, up=up, check=True)
+    cur = xyz
+    for l, ratio in enumerate(ratios):
+        assert np.array_equal(neigh[l].cpu().numpy(), ref(cur, cur, 16)), l
+        sub = np.ascontiguousarray(cur[:, : cur.shape[1] // ratio, :])
+        assert np.array_equal(up[l].cpu().numpy(), ref(sub, cur, 1)), l
+        cur = sub
+
+
 def test_knn_config1_full_size_properties(NN):
     """Config-1-sized cloud (~107k barycentres): self is the first neighbour, rows ascend in distance, and a random
     sample of rows equals brute force."""
