@@ -13,8 +13,10 @@ python bench.py --impl reference --steps 3 --warmup 1 > $O/${R}_bench_reference.
 $LIST --log-file $O/${R}_launches_pyramid.csv python tools/prof_knn.py 3 fused > /dev/null 2>&1
 $LIST --log-file $O/${R}_launches_grid.csv python tools/prof_select.py grid > /dev/null 2>&1
 $LIST --log-file $O/${R}_launches_fps32.csv python tools/prof_select.py fps32 50 > /dev/null 2>&1
-# full captures.  query: level 0, k=16, 245760 queries = the first query_kernel launch of the 3rd pyramid (5 per pyramid)
-$NCU_FULL -k regex:^query_kernel -s 10 -c 1 -o $O/${R}_ncu_knn_query python tools/prof_knn.py 3 fused > /dev/null 2>&1
+# full captures.  query: level 0, k=16, 245760 queries = the first query16_kernel launch of the 3rd pyramid (3 per pyramid:
+# levels 0-2; the two lowest levels run the brute-force kernel)
+$NCU_FULL -k regex:^query16_kernel -s 6 -c 1 -o $O/${R}_ncu_knn_query python tools/prof_knn.py 3 calls > /dev/null 2>&1
+$NCU_FULL -k regex:^exact_query_kernel -s 0 -c 1 -o $O/${R}_ncu_knn_exact python tools/prof_knn.py 1 calls > /dev/null 2>&1
 $NCU_FULL -k regex:^build_kernel -s 2 -c 1 -o $O/${R}_ncu_knn_build python tools/prof_tree.py 6 40960 > /dev/null 2>&1
 $NCU_FULL -k regex:select32_kernel -s 1 -c 1 -o $O/${R}_ncu_fps32 python tools/prof_select.py fps32 30 > /dev/null 2>&1
 $NCU_FULL -k regex:select32_kernel -s 1 -c 1 -o $O/${R}_ncu_kc32 python tools/prof_select.py kc32 30 > /dev/null 2>&1
@@ -30,6 +32,8 @@ python tools/ncu_summary.py traffic $O/${R}_ncu_fps256.ncu-rep fps_d256 $O/${R}_
 python tools/ncu_summary.py traffic $O/${R}_ncu_kc32.ncu-rep kcenter_d32 $O/${R}_traffic.json 45
 python tools/ncu_summary.py traffic $O/${R}_ncu_grid_sort.ncu-rep grid_sort_1m $O/${R}_traffic.json 1000000
 python tools/ncu_summary.py traffic $O/${R}_ncu_grid_reduce.ncu-rep grid_reduce_1m $O/${R}_traffic.json 1000000
-rm -f $O/${R}_ncu_fps256.ncu-rep $O/${R}_ncu_kc32.ncu-rep $O/${R}_ncu_knn_build.ncu-rep $O/${R}_ncu_grid_reduce.ncu-rep
+rm -f $O/${R}_ncu_fps256.ncu-rep $O/${R}_ncu_kc32.ncu-rep $O/${R}_ncu_knn_build.ncu-rep $O/${R}_ncu_grid_reduce.ncu-rep $O/${R}_ncu_knn_exact.ncu-rep
+python tools/prof_pyramid_host.py > $O/${R}_pyramid_host_call.txt 2>&1
+python tools/prof_e2e.py > $O/${R}_e2e_per_call.txt 2>&1
 for n in 160 640 2560 10240 40960; do python tools/prof_tree.py 6 $n; done > $O/${R}_tree_phases.txt 2>&1
 ls -la $O | tail -30
