@@ -241,6 +241,23 @@ int ssdr_superpoint_fps(const double* points, const int64_t* offsets, size_t S, 
 int ssdr_chamfer_matrix_f64_dev(const double* d_points, const int64_t* d_offsets, const int64_t* h_offsets, size_t S,
                                 double* d_out, void* stream);
 
+/* ---- superpoint adjacency and feature propagation in front of the FPS loop ------------------------------ */
+/* fps_adj_all's matrix arithmetic (fps_gcn_cpu.py:60-117) on the device.  Room b holds the superpoints
+ * block_off[b] .. block_off[b+1]: ref[] = their rows in [0, N), centres (., 3) float64, and its chamfer block cd
+ * (n_b x n_b float64, the blocks concatenated in room order).  S = A_ed + A_cd (1e10 + 1e10 outside the blocks),
+ * adj = exp(-S) - I, column-scaled by 1 / rowsum (inf -> 0), + I.  The matrix stays on the device behind *handle;
+ * ssdr_gcn_fetch copies it into a (N, N) float64 host array, ssdr_gcn_free releases it. */
+int ssdr_gcn_adjacency_f64(size_t N, size_t n_blocks, const int64_t* block_off, const int64_t* ref, const double* centres,
+                           const double* cd, void** handle);
+int ssdr_gcn_fetch(void* handle, double* adj_out);
+int ssdr_gcn_free(void* handle);
+/* GCN_FPS_sampling's propagation (fps_gcn_cpu.py:153-167): optionally keep the gcn_top largest entries of every row of
+ * adj (ties at the threshold: highest columns), then out = V + adj V + adj (adj V) + ... (gcn_number products).
+ * The adjacency comes from `handle` (device resident) or, when handle is NULL, from the host array adj (N, N).
+ * V and out are (N, D) float64 host arrays. */
+int ssdr_gcn_propagate_f64(void* handle, const double* adj, size_t N, const double* V, size_t D, int gcn_number,
+                           int gcn_top, double* out);
+
 /* Row-sharded multi-GPU selection (one process per GPU).  Every rank holds the FULL matrix d_F (so the chosen
  * centre row is local) but scans only rows [row_begin,row_end); after each step the packed (distance, index)
  * candidates are combined across ranks by an 8-byte max all-reduce over NCCL.  `nccl_comm` is an ncclComm_t.

@@ -42,6 +42,10 @@ SIGNATURES = {
     "ssdr_knn_pyramid_dev": [vp, sz, sz, vp, sz, sz, vp, vp, vp],
     "ssdr_knn_pyramid": [vp, sz, sz, sz, vp, sz, sz, vp, vp],
     "ssdr_knn_status": [vp],
+    "ssdr_gcn_adjacency_f64": [sz, sz, vp, vp, vp, vp, C.POINTER(vp)],
+    "ssdr_gcn_fetch": [vp, vp],
+    "ssdr_gcn_free": [vp],
+    "ssdr_gcn_propagate_f64": [vp, vp, sz, vp, sz, C.c_int, C.c_int, vp],
     "ssdr_knn_pyramid_launches": [],
     "ssdr_knn_debug_tree": [vp, sz, vp, vp, vp, vp, vp, vp, vp, vp, vp],
     "ssdr_knn_debug_build_timing": [vp, sz, sz, vp],

@@ -12,7 +12,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libssdr_b200.so")
-SOURCES = ["runtime.cu", "selection.cu", "grid.cu", "knn.cu", "chamfer.cu", "nccl_shim.cu"]
+SOURCES = ["runtime.cu", "selection.cu", "grid.cu", "knn.cu", "chamfer.cu", "gcn.cu", "nccl_shim.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "--fmad=false",  # parity-critical arithmetic must never be contracted (the x86 reference has no FMA)
