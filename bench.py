@@ -604,6 +604,42 @@ def secondary_metrics(torch, D, dev, flush, gpu_pyramid, gpu_pyramid_fused):
                 sub, "reference KD trees" if have else "numpy restatement")
     except Exception as e:
         out["chamfer_adjacency"] = {"error": repr(e)}
+    try:  # adjacency + propagation in front of the FPS loop (fps_adj_all :95-116, GCN_FPS_sampling :153-167):
+        # 8192 superpoints in 256 rooms, 32 features, one product; host arrays in and out like the reference
+        import ssdr_al_b200 as S
+        rng = np.random.default_rng(9)
+        n_sp, per_room, d_feat = 8192, 32, 32
+        perm = rng.permutation(n_sp)
+        rooms = []
+        for r0 in range(0, n_sp, per_room):
+            cd = rng.random((per_room, per_room)) * 0.8
+            cd = cd + cd.T
+            np.fill_diagonal(cd, 0.0)
+            rooms.append((perm[r0:r0 + per_room].tolist(), rng.random((per_room, 3)) * 8.0, cd))
+        vfeat = rng.standard_normal((n_sp, d_feat))
+        G = S.fps_gcn
+
+        def gcn_once():
+            a = G.adjacency_from_rooms(n_sp, rooms)
+            r = G.propagate(a, vfeat, 1, 0)
+            a.close()
+            return r
+        got = gcn_once()
+        ms_g = float(np.median([_cpu_ms(gcn_once) for _ in range(3)]))
+        out["gcn_adjacency_propagation"] = {
+            "superpoints": n_sp, "rooms": len(rooms), "features": d_feat, "products": 1, "e2e_ms": ms_g,
+            "matrix_bytes": 8 * n_sp * n_sp,
+            "note": "host arrays in, host features out; the N x N matrix is assembled, normalised and multiplied on "
+                    "the device and never leaves it"}
+        if O is not None:
+            t_ref = _cpu_ms(lambda: O.gcn_propagate(O.gcn_adjacency(n_sp, rooms), vfeat, 1, 0))
+            want = O.gcn_propagate(O.gcn_adjacency(n_sp, rooms), vfeat, 1, 0)
+            out["gcn_adjacency_propagation"]["cpu_ms"] = t_ref
+            out["gcn_adjacency_propagation"]["cpu_kind"] = "numpy restatement of fps_gcn_cpu.py:63-116,153-167 (the "\
+                                                           "reference IS these numpy calls), host BLAS threads"
+            out["gcn_adjacency_propagation"]["max_rel_diff"] = float(np.max(np.abs(got - want) / (np.abs(want) + 1e-300)))
+    except Exception as e:
+        out["gcn_adjacency_propagation"] = {"error": repr(e)}
     for d_, picks in ((32, 2000), (256, 1000)):
         try:
             g = torch.Generator(device=dev)

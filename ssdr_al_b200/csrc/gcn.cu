@@ -16,6 +16,7 @@
 // Rows of an N x N float64 matrix stream once per product: the propagation is bound by HBM (8 N^2 bytes per product).
 #include <math.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include <vector>
 
@@ -292,6 +293,91 @@ __global__ void __launch_bounds__(MM_THREADS) matmul_kernel(const double* __rest
     }
 }
 
+// ---- the same product on the FP64 tensor cores (mma.sync m8n8k4, DMMA): the fast path for even N and D with 16-byte
+// aligned rows.  A CTA owns 32 rows x 32 columns, a warp 8 rows x 32 columns (four 8 x 8 accumulator tiles); the k loop
+// moves 64-wide chunks of adj and V into a double-buffered shared-memory ring with 16-byte cp.async (zero fill beyond
+// the edges), rows padded by four doubles so that the fragment loads of a half-warp hit 16 distinct bank pairs.
+constexpr int DM_ROWS = 32, DM_COLS = 32, DM_K = 64, DM_THREADS = 128;
+constexpr int DM_AS = DM_K + 4;     // row stride of the adj tile (doubles): 68 = 4 mod 16
+constexpr int DM_VS = DM_COLS + 4;  // row stride of the V tile: 36 = 4 mod 16
+constexpr size_t DM_SMEM = 2 * (size_t)(DM_ROWS * DM_AS + DM_K * DM_VS) * sizeof(double);
+
+__device__ __forceinline__ void cp_async16_zfill(void* smem, const void* gmem, bool valid) {
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+    const int bytes = valid ? 16 : 0;
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(sa), "l"(gmem), "r"(bytes));
+}
+
+__global__ void __launch_bounds__(DM_THREADS) matmul_dmma_kernel(const double* __restrict__ A, const double* __restrict__ V,
+                                                                 double* __restrict__ out, unsigned N, unsigned D) {
+    extern __shared__ __align__(16) unsigned char dm_smem[];
+    double* s_a[2];
+    double* s_v[2];
+    s_a[0] = reinterpret_cast<double*>(dm_smem);
+    s_a[1] = s_a[0] + DM_ROWS * DM_AS;
+    s_v[0] = s_a[1] + DM_ROWS * DM_AS;
+    s_v[1] = s_v[0] + DM_K * DM_VS;
+    const unsigned r0 = blockIdx.x * DM_ROWS, d0 = blockIdx.y * DM_COLS;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int fr = lane >> 2, fk = lane & 3;  // fragment coordinates: A[fr][fk], B[fk][fr], C[fr][2 fk .. 2 fk + 1]
+    double acc[4][2];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) acc[t][0] = acc[t][1] = 0.0;
+    const unsigned nchunk = (N + DM_K - 1) / DM_K;
+    auto issue = [&](unsigned ch, int buf) {
+        const unsigned k0 = ch * DM_K;
+        // adj tile: 32 rows x 32 pairs of doubles
+        for (int t = tid; t < DM_ROWS * (DM_K / 2); t += DM_THREADS) {
+            const int rr = t / (DM_K / 2), kp = t % (DM_K / 2);
+            const unsigned r = r0 + rr, kx = k0 + 2 * kp;
+            const bool ok = r < N && kx < N;
+            cp_async16_zfill(s_a[buf] + rr * DM_AS + 2 * kp, A + (ok ? (unsigned long long)r * N + kx : 0ull), ok);
+        }
+        // V tile: 64 rows x 16 pairs
+        for (int t = tid; t < DM_K * (DM_COLS / 2); t += DM_THREADS) {
+            const int kk = t / (DM_COLS / 2), cp = t % (DM_COLS / 2);
+            const unsigned kx = k0 + kk, dx = d0 + 2 * cp;
+            const bool ok = kx < N && dx < D;
+            cp_async16_zfill(s_v[buf] + kk * DM_VS + 2 * cp, V + (ok ? (unsigned long long)kx * D + dx : 0ull), ok);
+        }
+        asm volatile("cp.async.commit_group;");
+    };
+    issue(0, 0);
+    for (unsigned ch = 0; ch < nchunk; ++ch) {
+        const int buf = (int)(ch & 1u);
+        if (ch + 1 < nchunk) {
+            issue(ch + 1, buf ^ 1);
+            asm volatile("cp.async.wait_group 1;");
+        } else {
+            asm volatile("cp.async.wait_group 0;");
+        }
+        __syncthreads();
+        const double* a = s_a[buf] + (warp * 8 + fr) * DM_AS + fk;
+        const double* v = s_v[buf] + fk * DM_VS + fr;
+#pragma unroll 4
+        for (int kk = 0; kk < DM_K; kk += 4) {
+            const double af = a[kk];
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                const double bf = v[kk * DM_VS + 8 * t];
+                asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
+                             : "+d"(acc[t][0]), "+d"(acc[t][1])
+                             : "d"(af), "d"(bf));
+            }
+        }
+        __syncthreads();
+    }
+    const unsigned r = r0 + warp * 8 + fr;
+    if (r < N) {
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            const unsigned c = d0 + 8 * t + 2 * fk;
+            if (c < D) out[(unsigned long long)r * D + c] = acc[t][0];
+            if (c + 1 < D) out[(unsigned long long)r * D + c + 1] = acc[t][1];
+        }
+    }
+}
+
 __global__ void add_kernel(double* __restrict__ sum, const double* __restrict__ v, unsigned long long n) {
     for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
          i += (unsigned long long)gridDim.x * blockDim.x)
@@ -448,8 +534,20 @@ int ssdr_gcn_propagate_f64(void* handle, const double* adj_host, size_t N, const
     double* sum = c->ws[WS_SUM].as<double>();
     SSDR_TRY(h2d(c, va, V, vb, s));
     SSDR_CHECK_CUDA(cudaMemcpyAsync(sum, va, vb, cudaMemcpyDeviceToDevice, s));
+    // tensor-core path: 16-byte cp.async needs even N and D (all workspaces and the adjacency are 256-byte aligned)
+    static const bool dmma_on = [] {
+        const char* e = getenv("SSDR_GCN_DMMA");  // SSDR_GCN_DMMA=0: the plain fma kernel (A/B runs)
+        return !(e && e[0] == '0');
+    }();
+    const bool dmma = dmma_on && N % 2 == 0 && D % 2 == 0 && (reinterpret_cast<size_t>(adj) & 15) == 0;
+    if (dmma)
+        SSDR_CHECK_CUDA(cudaFuncSetAttribute(matmul_dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DM_SMEM));
     for (int g = 0; g < gcn_number; ++g) {
-        matmul_kernel<<<(unsigned)((N + MM_ROWS - 1) / MM_ROWS), MM_THREADS, 0, s>>>(adj, va, vbuf, (unsigned)N, (unsigned)D);
+        if (dmma)
+            matmul_dmma_kernel<<<dim3((unsigned)((N + DM_ROWS - 1) / DM_ROWS), (unsigned)((D + DM_COLS - 1) / DM_COLS)),
+                                 DM_THREADS, DM_SMEM, s>>>(adj, va, vbuf, (unsigned)N, (unsigned)D);
+        else
+            matmul_kernel<<<(unsigned)((N + MM_ROWS - 1) / MM_ROWS), MM_THREADS, 0, s>>>(adj, va, vbuf, (unsigned)N, (unsigned)D);
         add_kernel<<<blocks_for(c, (unsigned long long)N * D, 256), 256, 0, s>>>(sum, vbuf, (unsigned long long)N * D);
         double* t = va;
         va = vbuf;
