@@ -68,7 +68,7 @@ struct Ctx {
     DevBuf* ws = ws0;               // the ACTIVE bank: every module says c->ws[slot]
     // Branches of one call that run side by side on their own streams (the levels of the KNN pyramid) each work in a
     // bank of their own; bank 0 is ws0.  Banks, streams and events are created on first use and live as long as the Ctx.
-    enum { MAX_BRANCH = 17 };
+    enum { MAX_BRANCH = 52 };  // (16 levels + 1) support clouds x up to 3 item parts, + 1
     DevBuf* bank[MAX_BRANCH] = {};
     cudaStream_t branch_stream[MAX_BRANCH] = {};
     cudaEvent_t ev_branch[MAX_BRANCH] = {};

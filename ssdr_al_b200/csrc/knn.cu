@@ -1465,14 +1465,28 @@ static int pyramid_dev(Ctx* c, cudaStream_t s, const float* d_points, size_t B, 
     } restore{c};
     SSDR_TRY(ctx_branch(c, 0, nullptr));
     SSDR_CHECK_CUDA(cudaEventRecord(c->ev_fork, s));
-    // host flavour: branch 0 goes LAST and through the synchronous host path of run_dev -- its 31 MB of rows leave in two
-    // chunks under the second query launch and the tie path, the few rewritten rows follow as a patch -- while the
-    // other branches, already enqueued, run beside it
-    for (size_t jj = 0; jj <= n_levels; ++jj) {
-        const size_t j = h_neigh ? (jj + 1) % (n_levels + 1) : jj;
+    // A support cloud's branch is split once more by batch items (independent clouds): the parts of a level run side by
+    // side, so one part's tree build -- a latency-bound cooperative kernel on a few dozen SMs -- overlaps the other
+    // parts' query kernels.  SSDR_KNN_SPLIT = parts per level of 131072 points and more (default 3; 1 = no split).
+    static const int split_env = [] {
+        const char* e = getenv("SSDR_KNN_SPLIT");
+        const int v = e ? atoi(e) : 3;
+        return v < 1 ? 1 : (v > 3 ? 3 : v);
+    }();
+    const size_t S = (size_t)split_env < B ? (size_t)split_env : B;
+    // host flavour: part 0 of branch 0 goes LAST and through the synchronous host path of run_dev -- its rows leave in
+    // chunks under the next query launch and the tie path, the few rewritten rows follow as a patch -- while the other
+    // branches, already enqueued, run beside it
+    const size_t n_br = (n_levels + 1) * S;
+    for (size_t tt = 0; tt < n_br; ++tt) {
+        const size_t t = h_neigh ? (tt + 1) % n_br : tt;
+        const size_t j = t / S, part = t % S;
+        const size_t Sj = B * n[j] >= 131072 ? S : 1;  // small levels stay whole: a split only adds launches there
+        if (part >= Sj) continue;
+        const size_t b0 = B * part / Sj, b1 = B * (part + 1) / Sj, Bp = b1 - b0;
         cudaStream_t bs = s;
-        if (j > 0) {
-            SSDR_TRY(ctx_branch(c, (int)j, &bs));
+        if (t > 0) {
+            SSDR_TRY(ctx_branch(c, (int)t, &bs));
             SSDR_CHECK_CUDA(cudaStreamWaitEvent(bs, c->ev_fork, 0));
         } else {
             ctx_use_bank(c, 0);
@@ -1480,26 +1494,32 @@ static int pyramid_dev(Ctx* c, cudaStream_t s, const float* d_points, size_t B, 
         AsyncCtx ac;
         ac.status = status;
         ac.reuse = false;
+        const float* sup = level[j] + b0 * n[j] * 3;  // this part's items of the support cloud
         if (j > 0)
-            SSDR_TRY((run_dev<long long>(c, bs, level[j], B, n[j], level[j - 1], n[j - 1], 1, d_up[j - 1], nullptr, nullptr,
-                                         &ac)));
-        if (j == 0 && h_neigh) {
+            SSDR_TRY((run_dev<long long>(c, bs, sup, Bp, n[j], level[j - 1] + b0 * n[j - 1] * 3, n[j - 1], 1,
+                                         d_up[j - 1] + b0 * n[j - 1], nullptr, nullptr, &ac)));
+        if (t == 0 && h_neigh) {
             kdtree::invalidate_tree_cache(c);  // (the synchronous path would first check the previous call's trees)
-            SSDR_TRY((run_dev<long long>(c, s, level[0], B, n[0], level[0], n[0], K, d_neigh[0], nullptr, h_neigh[0], nullptr)));
+            SSDR_TRY((run_dev<long long>(c, s, sup, Bp, n[0], sup, n[0], K, d_neigh[0], nullptr, h_neigh[0], nullptr)));
         } else if (j < n_levels) {
             ac.reuse = j > 0;  // the trees of this cloud belong to the up-sampling query just enqueued
-            SSDR_TRY((run_dev<long long>(c, bs, level[j], B, n[j], level[j], n[j], K, d_neigh[j], nullptr, nullptr, &ac)));
+            SSDR_TRY((run_dev<long long>(c, bs, sup, Bp, n[j], sup, n[j], K, d_neigh[j] + b0 * n[j] * K, nullptr, nullptr,
+                                         &ac)));
         }
         // host flavour: a branch's rows start their way home on the branch's own stream, under the other branches' kernels
         if (h_up && j > 0)
-            SSDR_CHECK_CUDA(cudaMemcpyAsync(h_up[j - 1], d_up[j - 1], B * n[j - 1] * sizeof(long long),
-                                            cudaMemcpyDeviceToHost, bs));
-        if (h_neigh && j > 0 && j < n_levels)
-            SSDR_CHECK_CUDA(cudaMemcpyAsync(h_neigh[j], d_neigh[j], B * n[j] * K * sizeof(long long),
-                                            cudaMemcpyDeviceToHost, bs));
-        if (j > 0) SSDR_CHECK_CUDA(cudaEventRecord(c->ev_branch[j], bs));
+            SSDR_CHECK_CUDA(cudaMemcpyAsync(h_up[j - 1] + b0 * n[j - 1], d_up[j - 1] + b0 * n[j - 1],
+                                            Bp * n[j - 1] * sizeof(long long), cudaMemcpyDeviceToHost, bs));
+        if (h_neigh && t > 0 && j < n_levels)
+            SSDR_CHECK_CUDA(cudaMemcpyAsync(h_neigh[j] + b0 * n[j] * K, d_neigh[j] + b0 * n[j] * K,
+                                            Bp * n[j] * K * sizeof(long long), cudaMemcpyDeviceToHost, bs));
+        if (t > 0) SSDR_CHECK_CUDA(cudaEventRecord(c->ev_branch[t], bs));
     }
-    for (size_t j = 1; j <= n_levels; ++j) SSDR_CHECK_CUDA(cudaStreamWaitEvent(s, c->ev_branch[j], 0));
+    for (size_t t = 1; t < n_br; ++t) {
+        const size_t Sj = B * n[t / S] >= 131072 ? S : 1;
+        if (t % S >= Sj) continue;
+        SSDR_CHECK_CUDA(cudaStreamWaitEvent(s, c->ev_branch[t], 0));
+    }
     ctx_use_bank(c, 0);
     // the call returns with its work in flight: later calls are ordered behind it (a capture records no event)
     return mark_async ? ctx_mark_async(c, s) : SSDR_OK;
