@@ -43,7 +43,7 @@ struct Meta {
     unsigned long long n_sel;    // points taking part (all of them, or the ones inside the requested slab)
     unsigned long long M;
     int cur;                     // which ping-pong pair holds the sorted (key, index) arrays
-    int pad;
+    unsigned n_heavy;            // voxels deferred to reduce_heavy_kernel (zeroed with the rest by the sort kernel)
     // %globaltimer marks (ns) of CTA 0: [0] start, [1] geometry, [2] keys, [3..10] end of radix pass k, [11] heads
     // counted, [12] starts written, [13] reduce start (first CTA), [14] reduce end (last CTA)
     unsigned long long tmark[16];
@@ -168,7 +168,7 @@ __global__ void setup_kernel(const float* __restrict__ partials, int nparts, flo
         m.n_sel = 0;
         m.M = 0;
         m.cur = 0;
-        m.pad = 0;
+        m.n_heavy = 0;
         for (int k = 0; k < 16; ++k) m.tmark[k] = 0;
         *meta = m;
     }
@@ -613,7 +613,7 @@ __global__ void __launch_bounds__(PA_THREADS, 1) sort_kernel(const SortParams p)
         m.n_sel = n;
         m.M = 0;
         m.cur = 0;
-        m.pad = 0;
+        m.n_heavy = 0;
         for (int k = 0; k < 16; ++k) m.tmark[k] = s_mark[k];
         *p.meta = m;
     }
@@ -867,6 +867,11 @@ constexpr int RB_THREADS = 256;
 constexpr int RB_GROUPS = RB_THREADS / 8;
 constexpr int STAGE_STRIDE = 72;  // 8 points x (8 channels + 1 pad): stores (stride 9) and loads of the four groups of a warp are conflict free
 constexpr int MAX_CB = 4;         // channel blocks of 8 held in registers per walk over a voxel (32 channels)
+constexpr unsigned HEAVY_MIN = 1024;  // voxels with more points than this are reduced by a CTA each
+constexpr int RH_THREADS = 256;
+constexpr int RH_GATHER = RH_THREADS - 32;     // warps 1..7 gather, the first eight lanes of warp 0 add
+constexpr int RH_PER = 2;                      // points per gatherer thread and batch
+constexpr int RH_BATCH = RH_GATHER * RH_PER;   // 448 points in flight per batch
 
 struct ReduceParams {
     const float* pts;
@@ -883,6 +888,9 @@ struct ReduceParams {
     int* out_c;
     unsigned long long* out_k;
     int* out_n;
+    unsigned* heavy;        // voxels with more than heavy_min points, in no particular order (meta->n_heavy of them)
+    unsigned heavy_cap;
+    unsigned heavy_min;     // voxels with more points than this are deferred to reduce_heavy_kernel
 };
 
 __device__ __forceinline__ float load_feat(const ReduceParams& p, unsigned long long row, int j) {
@@ -943,6 +951,13 @@ __global__ void __launch_bounds__(RB_THREADS, 5) reduce_kernel(const ReduceParam
     for (unsigned long long v = (unsigned long long)blockIdx.x * RB_GROUPS + g; v < M; v += ngroups) {
         const unsigned long long s = p.starts[v], e = p.starts[v + 1];
         const unsigned cnt = (unsigned)(e - s);
+        if (cnt > p.heavy_min) {  // a whole CTA takes it (reduce_heavy_kernel): eight lanes would walk it for milliseconds
+            if (l == 0) {
+                const unsigned pos = atomicAdd(&p.meta->n_heavy, 1u);
+                if (pos < p.heavy_cap) p.heavy[pos] = (unsigned)v;
+            }
+            continue;
+        }
         const float a = (float)(1.0 / (double)cnt);  // grid_subsampling.cpp:87: double reciprocal narrowed to float
         const float cf = (float)cnt;
         // walks over the voxel: 32 channels per walk (one walk for every reference caller: xyz + rgb)
@@ -1028,6 +1043,141 @@ __global__ void __launch_bounds__(RB_THREADS, 5) reduce_kernel(const ReduceParam
         if (l == 0) {
             p.out_k[v] = keys[s];
             p.out_n[v] = (int)cnt;
+        }
+    }
+    if (overflow) p.meta->error = 2;
+    if (threadIdx.x == 0) atomicMax(&p.meta->tmark[14], gtimer_ns());
+}
+
+// Heavy voxels (a terrestrial scan puts tens of thousands of points into the voxels next to the scanner): the sums
+// must still be the reference's sequential += in input order, so the ADDS of a channel stay one dependent chain -- but
+// the gathers need not wait for them.  One CTA per voxel: warps 1..7 gather batch b+1 (sorted index -> xyz, features,
+// label; 448 points in flight) into one half of a double buffer while the first eight lanes of warp 0 -- one lane per
+// channel, exactly the group of reduce_kernel -- add batch b out of the other half and count its labels.  On one GPU
+// the reduce is bound by its gather throughput and this path changes little (80 M-point scan: 11.0 vs 11.4 ms); it
+// matters when the cloud is sharded: the slab next to the scanner holds few, huge voxels and its eight-lane chains
+// (17 600 points: 4.4 ms) were the critical path of the whole sharded call.
+__global__ void __launch_bounds__(RH_THREADS) reduce_heavy_kernel(const ReduceParams p) {
+    __shared__ float s_val[2][RH_BATCH * 9];
+    __shared__ int s_lab[2][RH_BATCH];
+    __shared__ int s_labs[LABEL_CAP], s_cnts[LABEL_CAP];
+    __shared__ int s_mixed[2];  // batch in buffer b holds a label other than the voxel's first one
+    const unsigned nheavy = min(p.meta->n_heavy, p.heavy_cap);
+    const int cur = p.meta->cur;
+    const unsigned long long* keys = p.keys[cur];
+    const unsigned* idx = p.idx[cur];
+    const int tid = threadIdx.x, l = tid & 7;
+    const unsigned gmask = 0xFFu;
+    const int CH = 3 + p.fdim;
+    bool overflow = false;
+    for (unsigned h = blockIdx.x; h < nheavy; h += gridDim.x) {
+        const unsigned long long v = p.heavy[h];
+        const unsigned long long s = p.starts[v], e = p.starts[v + 1];
+        const unsigned cnt = (unsigned)(e - s);
+        const unsigned nb = (cnt + RH_BATCH - 1) / RH_BATCH;
+        const float a = (float)(1.0 / (double)cnt);
+        const float cf = (float)cnt;
+        for (int ch0 = 0; ch0 < CH; ch0 += 8) {
+            const bool vote = ch0 == 0 && p.ldim >= 1;
+            float acc = 0.f;
+            int nl = 0;
+            // labels are piecewise constant in space: a batch whose labels all equal the voxel's first label is counted
+            // with ONE table update instead of one per eight points (the adder lanes are the bottleneck otherwise)
+            const int lab0 = vote ? load_label(p, (unsigned long long)idx[s], 0) : 0;
+            auto gather = [&](unsigned b, int buf) {
+#pragma unroll
+                for (int k = 0; k < RH_PER; ++k) {
+                    const unsigned il = (unsigned)k * RH_GATHER + (unsigned)(tid - 32);
+                    const unsigned long long i = (unsigned long long)b * RH_BATCH + il;
+                    if (i < cnt) {
+                        const unsigned long long row = idx[s + i];
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const int ch = ch0 + j;
+                            if (ch < CH) s_val[buf][il * 9 + j] = ch < 3 ? __ldg(p.pts + 3ull * row + ch) : load_feat(p, row, ch - 3);
+                        }
+                        if (vote) {
+                            const int lab = load_label(p, row, 0);
+                            s_lab[buf][il] = lab;
+                            if (lab != lab0) s_mixed[buf] = 1;
+                        }
+                    }
+                }
+            };
+            __syncthreads();  // the previous walk's / voxel's buffers are free
+            if (tid < 2) s_mixed[tid] = 0;
+            __syncthreads();
+            if (tid >= 32) gather(0, 0);
+            __syncthreads();
+            for (unsigned b = 0; b < nb; ++b) {
+                const int buf = (int)(b & 1u);
+                if (tid >= 32) {
+                    if (b + 1 < nb) gather(b + 1, buf ^ 1);
+                } else if (tid < 8) {
+                    const unsigned mt = min((unsigned)RH_BATCH, cnt - b * RH_BATCH);
+                    const bool mixed = vote && s_mixed[buf] != 0;
+                    if (vote && !mixed) overflow |= !table_add(s_labs, s_cnts, &nl, lab0, (int)mt, gmask, 0, l);
+                    for (unsigned c0 = 0; c0 < mt; c0 += 8) {
+                        const int m = (int)min(8u, mt - c0);
+                        if (ch0 + l < CH) {
+#pragma unroll
+                            for (int t = 0; t < 8; ++t)
+                                if (t < m) acc = __fadd_rn(acc, s_val[buf][(c0 + t) * 9 + l]);
+                        }
+                        if (mixed) {
+                            const int lab = l < m ? s_lab[buf][c0 + l] : 0;
+                            const int first = __shfl_sync(gmask, lab, 0);
+                            const bool same = l >= m || lab == first;
+                            if ((__ballot_sync(gmask, same) & 0xFFu) == 0xFFu) {
+                                overflow |= !table_add(s_labs, s_cnts, &nl, first, m, gmask, 0, l);
+                            } else {
+                                for (int t = 0; t < m; ++t)
+                                    overflow |= !table_add(s_labs, s_cnts, &nl, __shfl_sync(gmask, lab, t), 1, gmask, 0, l);
+                            }
+                        }
+                    }
+                    if (l == 0) s_mixed[buf] = 0;  // the buffer is refilled in the next iteration, behind the barrier
+                }
+                __syncthreads();
+            }
+            if (tid < 8) {
+                const int ch = ch0 + l;
+                if (ch < CH) {
+                    if (ch < 3) p.out_p[3ull * v + ch] = __fmul_rn(acc, a);
+                    else p.out_f[v * (unsigned long long)p.fdim + (ch - 3)] = __fdiv_rn(acc, cf);
+                }
+                if (vote) {
+                    for (int col = 0;;) {
+                        int best = -1;
+                        for (int q = l; q < nl; q += 8) best = max(best, s_cnts[q]);
+#pragma unroll
+                        for (int mm = 1; mm < 8; mm <<= 1) best = max(best, __shfl_xor_sync(gmask, best, mm));
+                        int nbest = 0, arg = -1;
+                        for (int q0 = 0; q0 < nl; q0 += 8) {
+                            const int q = q0 + l;
+                            const unsigned bb = __ballot_sync(gmask, q < nl && s_cnts[q] == best) & 0xFFu;
+                            if (bb && arg < 0) arg = q0 + __ffs((int)bb) - 1;
+                            nbest += __popc(bb);
+                        }
+                        if (l == 0)
+                            p.out_c[v * (unsigned long long)p.ldim + col] =
+                                nbest == 1 ? s_labs[arg] : label_first_in_iteration_order(s_labs, s_cnts, nl, best);
+                        __syncwarp(gmask);
+                        if (++col >= p.ldim) break;
+                        nl = 0;  // further label columns (no reference caller has any): straight from global memory
+                        for (unsigned c0 = 0; c0 < cnt; c0 += 8) {
+                            const int m = (int)min(8u, cnt - c0);
+                            const int lab = l < m ? load_label(p, (unsigned long long)idx[s + c0 + l], col) : 0;
+                            for (int t = 0; t < m; ++t)
+                                overflow |= !table_add(s_labs, s_cnts, &nl, __shfl_sync(gmask, lab, t), 1, gmask, 0, l);
+                        }
+                    }
+                }
+                if (l == 0 && ch0 == 0) {
+                    p.out_k[v] = keys[s];
+                    p.out_n[v] = (int)cnt;
+                }
+            }
         }
     }
     if (overflow) p.meta->error = 2;
@@ -1239,6 +1389,7 @@ static int run_core(Ctx* c, cudaStream_t s, const Inputs& in, size_t N, size_t f
     SSDR_TRY(c->ws[WS_IDX].reserve(N * sizeof(unsigned)));
     SSDR_TRY(c->ws[WS_IDX2].reserve(N * sizeof(unsigned)));
     SSDR_TRY(c->ws[WS_STARTS].reserve((N + 1) * sizeof(unsigned)));
+    SSDR_TRY(c->ws[WS_HEADS].reserve((N / HEAVY_MIN + 2) * sizeof(unsigned)));  // voxels left to reduce_heavy_kernel
     // control block: barrier counter | per-CTA partials, largest keys, counts | histogram matrix
     const size_t ctl_bytes = 256 + (size_t)G * (6 * sizeof(float) + sizeof(KeyT) + sizeof(unsigned)) + 256 +
                              (size_t)G * BINS * sizeof(unsigned);
@@ -1294,7 +1445,16 @@ static int run_core(Ctx* c, cudaStream_t s, const Inputs& in, size_t N, size_t f
         size_t want = (N + RB_GROUPS - 1) / RB_GROUPS;  // M <= N voxels, one group each at most
         const size_t cap = (size_t)c->sm_count * 8;
         const unsigned blocks = (unsigned)(want < cap ? (want ? want : 1) : cap);
+        rp.heavy = c->ws[WS_HEADS].as<unsigned>();
+        rp.heavy_cap = (unsigned)(N / HEAVY_MIN + 1);
+        static const bool heavy_on = [] {
+            const char* e = getenv("SSDR_GRID_HEAVY");  // SSDR_GRID_HEAVY=0: every voxel by its eight-lane group (A/B runs)
+            return !(e && e[0] == '0');
+        }();
+        rp.heavy_min = heavy_on ? HEAVY_MIN : 0xFFFFFFFFu;
         reduce_kernel<<<blocks, RB_THREADS, 0, s>>>(rp);
+        // the voxels the groups passed over (count on the device; none: the CTAs return at once)
+        if (heavy_on) reduce_heavy_kernel<<<(unsigned)c->sm_count * 4, RH_THREADS, 0, s>>>(rp);
     }
     SSDR_CHECK_CUDA(cudaGetLastError());
     // the ONE host round trip of the call: voxel count (the caller sizes its arrays with it) and the error flag

@@ -67,12 +67,24 @@ def ev_ms(fn):
 c2 = c[:, None].contiguous()
 for world in (2, 8):
     t_box, box = ev_ms(lambda: D.grid_bbox(x))
-    t_hist, hist = ev_ms(lambda: D.grid_layer_hist(x, 0.06, 2, box))
-    bounds = SD.balanced_slabs(hist.cpu().numpy(), world)
-    print("slab path world=%d: bbox %.3f ms, layer hist %.3f ms (%d layers), bounds %s" % (
-        world, t_box, t_hist, hist.numel(), bounds.tolist()), flush=True)
+    # the slab axis the sharded path would pick ("auto": lightest heaviest slab by sampled point counts)
+    best = None
+    t_hist_all = 0.0
+    for ax in (0, 1, 2):
+        if D.grid_layers(box, 0.06, ax) > SD.MAX_LAYERS:
+            continue
+        t_hist, hist = ev_ms(lambda: D.grid_layer_hist(x, 0.06, ax, box, 16))
+        t_hist_all += t_hist
+        h = hist.cpu().numpy()
+        bnd = SD.balanced_slabs(h, world)
+        load = max(int(h[bnd[r]:bnd[r + 1]].sum()) for r in range(world))
+        if best is None or load < best[0]:
+            best = (load, ax, bnd, hist.numel())
+    _, axis, bounds, nl = best
+    print("slab path world=%d: bbox %.3f ms, layer hists %.3f ms, axis %d (%d layers), bounds %s" % (
+        world, t_box, t_hist_all, axis, nl, bounds.tolist()), flush=True)
     for r in range(world):
-        slab = (2, int(bounds[r]), int(bounds[r + 1]))
+        slab = (axis, int(bounds[r]), int(bounds[r + 1]))
         D.grid_subsample(x, f, c2, 0.06, bbox=box, slab=slab)
         t, res = ev_ms(lambda: D.grid_subsample(x, f, c2, 0.06, bbox=box, slab=slab))
         m = (C.c_uint64 * 16)()
@@ -85,5 +97,5 @@ for world in (2, 8):
             if v:
                 parts.append("%s %.1f" % (name, (v - prev) / 1e3))
                 prev = v
-        print("  rank %d layers [%d,%d): rows %d  event %.3f ms | %s" % (r, slab[1], slab[2], res[0].shape[0], t,
-                                                                       " ".join(parts)), flush=True)
+        print("  rank %d layers [%d,%d): voxels %d  event %.3f ms | %s" % (r, slab[1], slab[2], res[0].shape[0], t,
+                                                                         " ".join(parts)), flush=True)
