@@ -2,7 +2,7 @@
 //
 // Replaces grid_subsampling() (utils/cpp_wrappers/cpp_subsampling/grid_subsampling/grid_subsampling.cpp:5-106),
 // a single-threaded unordered_map loop, by a sort + segmented sequential reduce that reproduces the reference
-// bit for bit.  TWO launches, no host round trip in between (the host reads the voxel count once, at the end):
+// bit for bit.  THREE launches, no host round trip in between (the host reads the voxel count once, at the end):
 //
 //   sort_kernel   (persistent, cooperative, one CTA per SM; phases separated by a grid barrier)
 //     P0  min/max corners (cloud.cpp:27-67) -> origin = floor(min * (1/dl)) * dl, nX, nY (grid_subsampling.cpp:27-31)
@@ -22,6 +22,7 @@
 //         (grid_subsampling.cpp:87-95); the label vote counts in a per-voxel shared-memory table that keeps
 //         first-occurrence order, ties resolved by libstdc++'s unordered_map iteration order
 //         (grid_subsampling.cpp:97-102)
+//   reduce_heavy_kernel: the voxels of more than 1024 points that reduce_kernel passed over, one CTA each
 //   optional (SSDR_GRID_ORDER_REFERENCE): rows permuted into the reference's libstdc++ hash-iteration order.
 // Rows come out in ascending voxel-key order by default (SSDR_GRID_ORDER_KEY).
 #include <stdlib.h>
