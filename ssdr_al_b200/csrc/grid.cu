@@ -268,12 +268,25 @@ struct SortParams {
     unsigned* hist;             // [G][BINS] CTA-major digit histograms of the current pass
     float* partials;            // [G][6]
     unsigned long long* pmax;   // [G] largest key per CTA
-    unsigned* cta_count;        // [G] slab members, later segment heads, per CTA
+    unsigned* cta_count;        // [G] segment heads per CTA
+    unsigned* wcount;           // [G][PA_WARPS] slab members staged by each warp
     unsigned* starts;           // [N + 1] voxel start offsets
     unsigned* barrier;          // monotonic arrival counter, zero at launch
 };
 
 
+constexpr int SLAB_STAGES = 3;  // quads of 128 points per warp in the slab pass's cp.async ring
+__device__ __forceinline__ void cp_async_16(void* smem, const void* gmem) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_4(void* smem, const void* gmem) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
+}
 __device__ __forceinline__ unsigned long long gtimer_ns() {
     unsigned long long t;
     asm volatile("mov.u64 %0, %%globaltimer;\n" : "=l"(t));
@@ -386,6 +399,9 @@ __global__ void __launch_bounds__(PA_THREADS, 1) sort_kernel(const SortParams p)
     __shared__ unsigned long long s_n, s_maxkey;
     __shared__ unsigned s_bar_target;
     __shared__ unsigned long long s_mark[16];
+    extern __shared__ __align__(16) unsigned char s_dyn[];  // one scatter round in digit order: keys, then values
+    unsigned long long* s_rkey = reinterpret_cast<unsigned long long*>(s_dyn);
+    unsigned* s_rval = reinterpret_cast<unsigned*>(s_dyn + (size_t)SC_ITEMS * PA_THREADS * sizeof(unsigned long long));
     const unsigned t = threadIdx.x, lane = t & 31, warp = t >> 5;
     const unsigned G = gridDim.x, c = blockIdx.x;
     if (t == 0) s_bar_target = 0;
@@ -466,32 +482,80 @@ __global__ void __launch_bounds__(PA_THREADS, 1) sort_kernel(const SortParams p)
     const bool slab = p.slab_axis >= 0;
     if (t == 0) s_mark[1] = gtimer_ns();
 
-    // ---- P1: keys (slab members compacted in input order), digit histogram of the first pass, largest key
-    unsigned long long member_base = cb;  // where this CTA's first (member) point goes
+    // ---- P1: keys, digit histogram of the first pass, largest key
+    unsigned long long kmax = 0;
     if (slab) {
-        unsigned mine = 0;
-        if (cb < ce) tl.prefetch(cb, (unsigned)min((unsigned long long)PA_THREADS, ce - cb));
-        for (unsigned long long b = cb; b < ce; b += PA_THREADS) {
-            const unsigned cnt = (unsigned)min((unsigned long long)PA_THREADS, ce - b);
-            const unsigned long long nb = b + PA_THREADS;
-            float x = 0.f, y = 0.f, z = 0.f;
-            tl.next(b, cnt, nb, nb < ce ? (unsigned)min((unsigned long long)PA_THREADS, ce - nb) : 0u, &x, &y, &z);
-            if (t < cnt) {
-                const unsigned long long layer = voxel_layer(geo, p.slab_axis == 0 ? x : (p.slab_axis == 1 ? y : z), p.slab_axis);
-                mine += (layer >= p.slab_lo && layer < p.slab_hi) ? 1u : 0u;
+        // Slab members are compacted IN INPUT ORDER with ONE read of the cloud and no block barrier per tile: every warp
+        // owns a contiguous run of this CTA's chunk, streams it as coalesced words through its own shared-memory tile
+        // (the next two tiles are already in registers), tests the slab layer (one division per point), computes the
+        // key of the members only and stages (key, index) at the head of its own run inside the SECOND sort buffers
+        // (a run never holds more members than points).  After the barrier every warp knows where its members start
+        // in the compacted array and copies them over.
+        const unsigned long long wlen = perN / PA_WARPS;  // a multiple of 32
+        const unsigned long long wb = min(cb + (unsigned long long)warp * wlen, ce), we = min(wb + wlen, ce);
+        // the warp's ring in dynamic shared memory: SLAB_STAGES quads of 128 points, filled by cp.async (16-byte
+        // chunks when the cloud is 16-byte aligned), so SLAB_STAGES - 1 quads are in flight while one is worked on
+        float* ring = reinterpret_cast<float*>(s_dyn) + (size_t)warp * (SLAB_STAGES * 384);
+        const unsigned long long wend = 3ull * we;
+        const unsigned nq = (unsigned)((we - wb + 127) / 128);
+        auto issue = [&](unsigned q) {
+            if (q < nq) {
+                const unsigned long long b0 = wb + 128ull * q;
+                float* dst = ring + (q % SLAB_STAGES) * 384;
+                if (aligned && b0 + 128 <= we) {
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) cp_async_16(dst + 4 * (lane + 32 * k), p.pts + 3ull * b0 + 4 * (lane + 32 * k));
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 12; ++k) {
+                        const unsigned long long wi = 3ull * b0 + lane + 32u * (unsigned)k;
+                        if (wi < wend) cp_async_4(dst + lane + 32 * k, p.pts + wi);
+                    }
+                }
             }
+            cp_async_commit();
+        };
+        unsigned run = 0;
+#pragma unroll
+        for (int q = 0; q < SLAB_STAGES - 1; ++q) issue((unsigned)q);
+        for (unsigned q = 0; q < nq; ++q) {
+            issue(q + SLAB_STAGES - 1);
+            cp_async_wait<SLAB_STAGES - 1>();
+            __syncwarp();
+            const float* tile = ring + (q % SLAB_STAGES) * 384;
+            const unsigned long long b = wb + 128ull * q;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const unsigned long long i = b + 32u * (unsigned)u + lane;
+                bool member = false;
+                unsigned long long key = 0;
+                if (i < we) {
+                    const float x = tile[96 * u + 3 * lane], y = tile[96 * u + 3 * lane + 1], z = tile[96 * u + 3 * lane + 2];
+                    const unsigned long long layer =
+                        voxel_layer(geo, p.slab_axis == 0 ? x : (p.slab_axis == 1 ? y : z), p.slab_axis);
+                    member = layer >= p.slab_lo && layer < p.slab_hi;
+                    if (member) key = voxel_key(geo, x, y, z);
+                }
+                const unsigned bal = __ballot_sync(0xffffffffu, member);
+                if (member) {
+                    const unsigned long long pos = wb + run + __popc(bal & ((1u << lane) - 1u));
+                    p.keys[1][pos] = key;
+                    p.idx[1][pos] = (unsigned)i;
+                    kmax = key > kmax ? key : kmax;
+                }
+                run += __popc(bal);
+            }
+            __syncwarp();  // the stage is refilled by the next iteration's issue
         }
-        unsigned tot;
-        block_excl_scan(mine, s_w, &tot);
-        if (t == 0) p.cta_count[c] = tot;
+        cp_async_wait<0>();
+        if (lane == 0) p.wcount[c * PA_WARPS + warp] = run;
         grid_barrier(p.barrier, G, &s_bar_target);
-        unsigned long long pre = 0, all = 0;
-        for (unsigned b = t; b < G; b += PA_THREADS) {
-            const unsigned v = __ldcg(p.cta_count + b);
+        unsigned long long pre = 0, all = 0;  // members of the CTAs before this one, of all CTAs
+        for (unsigned j = t; j < G * PA_WARPS; j += PA_THREADS) {
+            const unsigned v = __ldcg(p.wcount + j);
             all += v;
-            if (b < c) pre += v;
+            if (j < c * PA_WARPS) pre += v;
         }
-        // G <= PA_THREADS on any real device: one value per thread, reduce the two sums through shared memory
 #pragma unroll
         for (int m = 16; m > 0; m >>= 1) {
             pre += __shfl_xor_sync(0xffffffffu, pre, m);
@@ -506,7 +570,7 @@ __global__ void __launch_bounds__(PA_THREADS, 1) sort_kernel(const SortParams p)
             s_maxkey = v;  // borrowed: prefix
         }
         __syncthreads();
-        member_base = s_maxkey;
+        unsigned long long dst = s_maxkey;
         __syncthreads();
         if (lane == 0) s_red64[warp] = all;
         __syncthreads();
@@ -515,41 +579,52 @@ __global__ void __launch_bounds__(PA_THREADS, 1) sort_kernel(const SortParams p)
             for (int w = 0; w < PA_WARPS; ++w) v += s_red64[w];
             s_n = v;
         }
+        {   // members of the warps of this CTA before this one
+            const unsigned mine = __ldcg(p.wcount + c * PA_WARPS + lane);
+            unsigned inc = mine;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const unsigned nn = __shfl_up_sync(0xffffffffu, inc, o);
+                if (lane >= o) inc += nn;
+            }
+            dst += __shfl_sync(0xffffffffu, inc - mine, warp);
+        }
+        for (unsigned i0 = 0; i0 < run; i0 += 128) {  // four rows of 32 in flight
+            unsigned long long kk[4];
+            unsigned vv[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const unsigned i = i0 + 32u * (unsigned)u + lane;
+                if (i < run) {
+                    kk[u] = __ldcg(p.keys[1] + wb + i);
+                    vv[u] = __ldcg(p.idx[1] + wb + i);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const unsigned i = i0 + 32u * (unsigned)u + lane;
+                if (i < run) {
+                    p.keys[0][dst + i] = kk[u];
+                    p.idx[0][dst + i] = vv[u];
+                }
+            }
+        }
         __syncthreads();
-    } else if (t == 0) {
-        s_n = p.N;
-    }
-    for (unsigned i = t; i < BINS; i += PA_THREADS) s_tot[i] = 0;  // first-pass histogram of this CTA's members
-    __syncthreads();
-    unsigned long long kmax = 0;
-    {
-        unsigned long long run = member_base;
+    } else {
+        if (t == 0) s_n = p.N;
+        for (unsigned i = t; i < BINS; i += PA_THREADS) s_tot[i] = 0;  // first-pass histogram of this CTA's chunk
+        __syncthreads();
         if (cb < ce) tl.prefetch(cb, (unsigned)min((unsigned long long)PA_THREADS, ce - cb));
         for (unsigned long long b = cb; b < ce; b += PA_THREADS) {
             const unsigned cnt = (unsigned)min((unsigned long long)PA_THREADS, ce - b);
             const unsigned long long nb = b + PA_THREADS;
             float x = 0.f, y = 0.f, z = 0.f;
             tl.next(b, cnt, nb, nb < ce ? (unsigned)min((unsigned long long)PA_THREADS, ce - nb) : 0u, &x, &y, &z);
-            bool member = t < cnt;
+            const bool member = t < cnt;
             unsigned long long key = 0;
             if (member) {
                 key = voxel_key(geo, x, y, z);
-                if (slab) {
-                    const unsigned long long layer =
-                        voxel_layer(geo, p.slab_axis == 0 ? x : (p.slab_axis == 1 ? y : z), p.slab_axis);
-                    member = layer >= p.slab_lo && layer < p.slab_hi;
-                }
-            }
-            unsigned long long pos = b + t;
-            if (slab) {
-                unsigned tot;
-                const unsigned rank = block_excl_scan(member ? 1u : 0u, s_w, &tot);
-                pos = run + rank;
-                run += tot;
-            }
-            if (member) {
-                p.keys[0][pos] = key;
-                if (slab) p.idx[0][pos] = (unsigned)(b + t);
+                p.keys[0][b + t] = key;
                 kmax = key > kmax ? key : kmax;
             }
             // warp-aggregated histogram of the low digit
@@ -571,7 +646,8 @@ __global__ void __launch_bounds__(PA_THREADS, 1) sort_kernel(const SortParams p)
         for (int w = 0; w < PA_WARPS; ++w) v = s_red64[w] > v ? s_red64[w] : v;
         p.pmax[c] = v;
     }
-    for (unsigned i = t; i < BINS; i += PA_THREADS) p.hist[(size_t)c * BINS + i] = s_tot[i];
+    if (!slab)
+        for (unsigned i = t; i < BINS; i += PA_THREADS) p.hist[(size_t)c * BINS + i] = s_tot[i];
     grid_barrier(p.barrier, G, &s_bar_target);
     {
         unsigned long long v = 0;
@@ -714,24 +790,45 @@ __global__ void __launch_bounds__(PA_THREADS, 1) sort_kernel(const SortParams p)
                 __syncwarp();
             }
             __syncthreads();
+            // exclusive prefix of every digit over the warps, then of the round's digit totals over the digits: the
+            // round is first put in digit order in shared memory and written out from there, so that a warp's stores
+            // fall into a few contiguous runs instead of 32 different places
+            unsigned total = 0;
             if (t < BINS) {
-                unsigned run = s_base[t];
 #pragma unroll 8
                 for (int w = 0; w < PA_WARPS; ++w) {
                     const unsigned cnt = s_cnt[w][t];
-                    s_cnt[w][t] = run;
-                    run += cnt;
+                    s_cnt[w][t] = total;
+                    total += cnt;
                 }
-                s_base[t] = run;
+            }
+            unsigned round_n;
+            const unsigned ex = block_excl_scan(t < BINS ? total : 0u, s_w, &round_n);
+            if (t < BINS) {
+                s_pre[t] = ex;               // where the digit starts inside the round
+                s_tot[t] = s_base[t] - ex;   // global position = s_tot[digit] + position inside the round
+                s_base[t] += total;
             }
             __syncthreads();
 #pragma unroll
             for (int k = 0; k < SC_ITEMS; ++k) {
                 const unsigned long long i = b + (unsigned long long)warp * (32 * SC_ITEMS) + (unsigned)k * 32u + lane;
                 if (i < se) {
-                    const unsigned pos = s_cnt[warp][(unsigned)(key[k] >> shift) & (BINS - 1)] + rank[k];
-                    kout[pos] = key[k];
-                    vout[pos] = val[k];
+                    const unsigned d = (unsigned)(key[k] >> shift) & (BINS - 1);
+                    const unsigned local = s_pre[d] + s_cnt[warp][d] + rank[k];
+                    s_rkey[local] = key[k];
+                    s_rval[local] = val[k];
+                }
+            }
+            __syncthreads();
+#pragma unroll
+            for (int k = 0; k < SC_ITEMS; ++k) {
+                const unsigned j = (unsigned)k * PA_THREADS + t;
+                if (j < round_n) {
+                    const unsigned long long kk = s_rkey[j];
+                    const unsigned pos = s_tot[(unsigned)(kk >> shift) & (BINS - 1)] + j;
+                    kout[pos] = kk;
+                    vout[pos] = s_rval[j];
                 }
             }
             __syncthreads();
@@ -892,7 +989,80 @@ struct ReduceParams {
     unsigned* heavy;        // voxels with more than heavy_min points, in no particular order (meta->n_heavy of them)
     unsigned heavy_cap;
     unsigned heavy_min;     // voxels with more points than this are deferred to reduce_heavy_kernel
+    int direct;             // pts / feats / cls are rows in SORTED order (sorted_rows_kernel ran): row = sorted position
 };
+
+// Rows of the input arrays in sorted (voxel-major, input order inside a voxel) order, so that the reduce reads
+// consecutive records instead of chasing an index per point.  The gathers happen HERE, where every thread has
+// SR_ITEMS independent rows in flight and nothing waits on them; the features and labels keep their input type.
+constexpr int SR_THREADS = 256;
+constexpr int SR_ITEMS = 4;
+struct SortedRowsParams {
+    const float* pts;
+    const void* feats;
+    const void* cls;
+    int feat_bytes, cls_bytes;  // bytes per ROW (0: absent)
+    const unsigned* idx[2];
+    const Meta* meta;
+    float* out_p;
+    unsigned char* out_f;
+    unsigned char* out_c;
+};
+template <typename W>
+__device__ __forceinline__ void copy_row(const void* src, void* dst, unsigned long long from, unsigned long long to, int words) {
+    const W* a = reinterpret_cast<const W*>(src) + from * (unsigned long long)words;
+    W* b = reinterpret_cast<W*>(dst) + to * (unsigned long long)words;
+    for (int j = 0; j < words; ++j) b[j] = __ldg(a + j);
+}
+__global__ void __launch_bounds__(SR_THREADS) sorted_rows_kernel(const SortedRowsParams p) {
+    const unsigned long long n = p.meta->n_sel;
+    const unsigned* idx = p.meta->cur ? p.idx[1] : p.idx[0];
+    const unsigned long long tile = (unsigned long long)SR_THREADS * SR_ITEMS;
+    for (unsigned long long b = (unsigned long long)blockIdx.x * tile; b < n; b += (unsigned long long)gridDim.x * tile) {
+        unsigned long long row[SR_ITEMS];
+#pragma unroll
+        for (int u = 0; u < SR_ITEMS; ++u) {
+            const unsigned long long i = b + (unsigned)u * SR_THREADS + threadIdx.x;
+            row[u] = i < n ? (unsigned long long)__ldg(idx + i) : 0ull;
+        }
+        float x[SR_ITEMS], y[SR_ITEMS], z[SR_ITEMS];
+#pragma unroll
+        for (int u = 0; u < SR_ITEMS; ++u) {
+            x[u] = __ldg(p.pts + 3ull * row[u]);
+            y[u] = __ldg(p.pts + 3ull * row[u] + 1);
+            z[u] = __ldg(p.pts + 3ull * row[u] + 2);
+        }
+#pragma unroll
+        for (int u = 0; u < SR_ITEMS; ++u) {
+            const unsigned long long i = b + (unsigned)u * SR_THREADS + threadIdx.x;
+            if (i < n) {
+                p.out_p[3ull * i] = x[u];
+                p.out_p[3ull * i + 1] = y[u];
+                p.out_p[3ull * i + 2] = z[u];
+            }
+        }
+        if (p.feat_bytes) {
+#pragma unroll
+            for (int u = 0; u < SR_ITEMS; ++u) {
+                const unsigned long long i = b + (unsigned)u * SR_THREADS + threadIdx.x;
+                if (i < n) {
+                    if ((p.feat_bytes & 3) == 0) copy_row<unsigned>(p.feats, p.out_f, row[u], i, p.feat_bytes >> 2);
+                    else copy_row<unsigned char>(p.feats, p.out_f, row[u], i, p.feat_bytes);
+                }
+            }
+        }
+        if (p.cls_bytes) {
+#pragma unroll
+            for (int u = 0; u < SR_ITEMS; ++u) {
+                const unsigned long long i = b + (unsigned)u * SR_THREADS + threadIdx.x;
+                if (i < n) {
+                    if ((p.cls_bytes & 3) == 0) copy_row<unsigned>(p.cls, p.out_c, row[u], i, p.cls_bytes >> 2);
+                    else copy_row<unsigned char>(p.cls, p.out_c, row[u], i, p.cls_bytes);
+                }
+            }
+        }
+    }
+}
 
 __device__ __forceinline__ float load_feat(const ReduceParams& p, unsigned long long row, int j) {
     const unsigned long long o = row * (unsigned long long)p.fdim + j;
@@ -968,9 +1138,12 @@ __global__ void __launch_bounds__(RB_THREADS, 5) reduce_kernel(const ReduceParam
             for (int cb = 0; cb < MAX_CB; ++cb) acc[cb] = 0.f;
             int nl = 0;
             const bool vote = ch0 == 0 && p.ldim >= 1;
+            // the sorted index of the NEXT eight points is fetched while this step's rows are gathered and added
+            unsigned long long row_next = (unsigned)l < cnt ? (p.direct ? s + l : (unsigned long long)idx[s + l]) : 0ull;
             for (unsigned c0 = 0; c0 < cnt; c0 += 8) {
                 const int m = (int)min(8u, cnt - c0);
-                const unsigned long long row = l < m ? (unsigned long long)idx[s + c0 + l] : 0ull;
+                const unsigned long long row = row_next;
+                if (c0 + 8 + l < cnt) row_next = p.direct ? s + c0 + 8 + l : (unsigned long long)idx[s + c0 + 8 + l];
 #pragma unroll
                 for (int cb = 0; cb < MAX_CB; ++cb) {
                     const int cbase = ch0 + 8 * cb;
@@ -1034,7 +1207,7 @@ __global__ void __launch_bounds__(RB_THREADS, 5) reduce_kernel(const ReduceParam
                     nl = 0;
                     for (unsigned c0 = 0; c0 < cnt; c0 += 8) {
                         const int m = (int)min(8u, cnt - c0);
-                        const int lab = l < m ? load_label(p, (unsigned long long)idx[s + c0 + l], col) : 0;
+                        const int lab = l < m ? load_label(p, p.direct ? s + c0 + l : (unsigned long long)idx[s + c0 + l], col) : 0;
                         for (int t = 0; t < m; ++t)
                             overflow |= !table_add(labs, cnts, &nl, __shfl_sync(gmask, lab, gshift + t), 1, gmask, gshift, l);
                     }
@@ -1084,14 +1257,14 @@ __global__ void __launch_bounds__(RH_THREADS) reduce_heavy_kernel(const ReducePa
             int nl = 0;
             // labels are piecewise constant in space: a batch whose labels all equal the voxel's first label is counted
             // with ONE table update instead of one per eight points (the adder lanes are the bottleneck otherwise)
-            const int lab0 = vote ? load_label(p, (unsigned long long)idx[s], 0) : 0;
+            const int lab0 = vote ? load_label(p, p.direct ? s : (unsigned long long)idx[s], 0) : 0;
             auto gather = [&](unsigned b, int buf) {
 #pragma unroll
                 for (int k = 0; k < RH_PER; ++k) {
                     const unsigned il = (unsigned)k * RH_GATHER + (unsigned)(tid - 32);
                     const unsigned long long i = (unsigned long long)b * RH_BATCH + il;
                     if (i < cnt) {
-                        const unsigned long long row = idx[s + i];
+                        const unsigned long long row = p.direct ? s + i : (unsigned long long)idx[s + i];
 #pragma unroll
                         for (int j = 0; j < 8; ++j) {
                             const int ch = ch0 + j;
@@ -1168,7 +1341,7 @@ __global__ void __launch_bounds__(RH_THREADS) reduce_heavy_kernel(const ReducePa
                         nl = 0;  // further label columns (no reference caller has any): straight from global memory
                         for (unsigned c0 = 0; c0 < cnt; c0 += 8) {
                             const int m = (int)min(8u, cnt - c0);
-                            const int lab = l < m ? load_label(p, (unsigned long long)idx[s + c0 + l], col) : 0;
+                            const int lab = l < m ? load_label(p, p.direct ? s + c0 + l : (unsigned long long)idx[s + c0 + l], col) : 0;
                             for (int t = 0; t < m; ++t)
                                 overflow |= !table_add(s_labs, s_cnts, &nl, __shfl_sync(gmask, lab, t), 1, gmask, 0, l);
                         }
@@ -1393,7 +1566,7 @@ static int run_core(Ctx* c, cudaStream_t s, const Inputs& in, size_t N, size_t f
     SSDR_TRY(c->ws[WS_HEADS].reserve((N / HEAVY_MIN + 2) * sizeof(unsigned)));  // voxels left to reduce_heavy_kernel
     // control block: barrier counter | per-CTA partials, largest keys, counts | histogram matrix
     const size_t ctl_bytes = 256 + (size_t)G * (6 * sizeof(float) + sizeof(KeyT) + sizeof(unsigned)) + 256 +
-                             (size_t)G * BINS * sizeof(unsigned);
+                             (size_t)G * BINS * sizeof(unsigned) + (size_t)G * PA_WARPS * sizeof(unsigned);
     SSDR_TRY(c->ws[WS_CTL].reserve(ctl_bytes));
     char* ctl = c->ws[WS_CTL].as<char>();
     Meta* meta = c->ws[WS_META].as<Meta>();
@@ -1417,11 +1590,16 @@ static int run_core(Ctx* c, cudaStream_t s, const Inputs& in, size_t N, size_t f
     sp.partials = reinterpret_cast<float*>(ctl + 256 + (size_t)G * sizeof(KeyT));
     sp.cta_count = reinterpret_cast<unsigned*>(ctl + 256 + (size_t)G * (sizeof(KeyT) + 6 * sizeof(float)));
     sp.hist = reinterpret_cast<unsigned*>(ctl + (256 + (size_t)G * (6 * sizeof(float) + sizeof(KeyT) + sizeof(unsigned)) + 255) / 256 * 256);
+    sp.wcount = sp.hist + (size_t)G * BINS;
     sp.starts = c->ws[WS_STARTS].as<unsigned>();
     SSDR_CHECK_CUDA(cudaMemsetAsync(sp.barrier, 0, 256, s));
     {
         void* args[] = {(void*)&sp};
-        SSDR_CHECK_CUDA(cudaLaunchCooperativeKernel((void*)sort_kernel, dim3(G), dim3(PA_THREADS), args, 0, s));
+        size_t dyn = (size_t)SC_ITEMS * PA_THREADS * (sizeof(unsigned long long) + sizeof(unsigned));
+        const size_t ring = (size_t)PA_WARPS * SLAB_STAGES * 384 * sizeof(float);  // the slab pass's cp.async rings
+        if (slab.axis >= 0 && ring > dyn) dyn = ring;
+        SSDR_CHECK_CUDA(cudaFuncSetAttribute((void*)sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+        SSDR_CHECK_CUDA(cudaLaunchCooperativeKernel((void*)sort_kernel, dim3(G), dim3(PA_THREADS), args, dyn, s));
     }
     {
         ReduceParams rp;
@@ -1453,6 +1631,38 @@ static int run_core(Ctx* c, cudaStream_t s, const Inputs& in, size_t N, size_t f
             return !(e && e[0] == '0');
         }();
         rp.heavy_min = heavy_on ? HEAVY_MIN : 0xFFFFFFFFu;
+        static const bool sorted_rows_on = [] {
+            // =1: rows gathered into sorted order by a kernel of their own, sequential reduce (A/B runs: the gather pass
+            // costs more than the reduce saves, profiles/r02_grid_sorted_rows_ab.txt)
+            const char* e = getenv("SSDR_GRID_SORTED_ROWS");
+            return e && e[0] == '1';
+        }();
+        rp.direct = 0;
+        if (sorted_rows_on) {
+            const size_t fb = fdim ? fdim * (in.f_u8 ? 1 : 4) : 0, cb = ldim ? ldim * (in.c_u8 ? 1 : 4) : 0;
+            const size_t o_f = (N * 12 + 255) / 256 * 256, o_c = o_f + (N * fb + 255) / 256 * 256;
+            SSDR_TRY(c->ws[WS_REC].reserve(o_c + N * cb + 256));
+            unsigned char* rec = c->ws[WS_REC].as<unsigned char>();
+            SortedRowsParams q;
+            q.pts = in.p;
+            q.feats = rp.feats;
+            q.cls = rp.cls;
+            q.feat_bytes = (int)fb;
+            q.cls_bytes = (int)cb;
+            q.idx[0] = sp.idx[0];
+            q.idx[1] = sp.idx[1];
+            q.meta = meta;
+            q.out_p = reinterpret_cast<float*>(rec);
+            q.out_f = rec + o_f;
+            q.out_c = rec + o_c;
+            const size_t tiles = (N + (size_t)SR_THREADS * SR_ITEMS - 1) / ((size_t)SR_THREADS * SR_ITEMS);
+            const size_t capb = (size_t)c->sm_count * 16;
+            sorted_rows_kernel<<<(unsigned)(tiles < capb ? tiles : capb), SR_THREADS, 0, s>>>(q);
+            rp.pts = q.out_p;
+            if (fb) rp.feats = q.out_f;
+            if (cb) rp.cls = q.out_c;
+            rp.direct = 1;
+        }
         reduce_kernel<<<blocks, RB_THREADS, 0, s>>>(rp);
         // the voxels the groups passed over (count on the device; none: the CTAs return at once)
         if (heavy_on) reduce_heavy_kernel<<<(unsigned)c->sm_count * 4, RH_THREADS, 0, s>>>(rp);

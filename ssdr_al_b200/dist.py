@@ -204,7 +204,9 @@ def knn_sharded(pts, queries, K, group=None, gather=False, int32=False):
 
 def gather_rows(rows, group=None):
     """All-gather row blocks of different lengths (the slabs of a sharded subsampling) into the full array, rank
-    order == row order.  Returns (full (sum m_r, ...), (begin, end) of this rank's block)."""
+    order == row order.  Returns (full (sum m_r, ...), (begin, end) of this rank's block).  Over NCCL every block
+    travels once, straight into its place in the result (a group of broadcasts, no padding and no re-packing); other
+    backends (gloo in the CPU tests) and empty blocks take the padded all-gather."""
     import torch
     import torch.distributed as dist
     world, rank = dist.get_world_size(group), dist.get_rank(group)
@@ -212,14 +214,23 @@ def gather_rows(rows, group=None):
     sizes[rank] = rows.shape[0]
     dist.all_reduce(sizes, group=group)
     sizes = sizes.tolist()
+    begin = sum(sizes[:rank])
+    span = (begin, begin + sizes[rank])
+    if rows.is_cuda and min(sizes) > 0 and dist.get_backend(group) == "nccl":
+        full = torch.empty((sum(sizes),) + tuple(rows.shape[1:]), dtype=rows.dtype, device=rows.device)
+        at, parts = 0, []
+        for n in sizes:
+            parts.append(full[at:at + n])
+            at += n
+        dist.all_gather(parts, rows.contiguous(), group=group)
+        return full, span
     width = max(max(sizes), 1)
     padded = torch.zeros((width,) + tuple(rows.shape[1:]), dtype=rows.dtype, device=rows.device)
     padded[: rows.shape[0]] = rows
     every = torch.empty((world, width) + tuple(rows.shape[1:]), dtype=rows.dtype, device=rows.device)
     dist.all_gather_into_tensor(every, padded, group=group)
     full = torch.cat([every[r, : sizes[r]] for r in range(world)])
-    begin = sum(sizes[:rank])
-    return full, (begin, begin + sizes[rank])
+    return full, span
 
 
 def balanced_slabs(layer_counts, world):
@@ -285,11 +296,13 @@ def choose_slabs(points, sampleDl, bbox, world, axis, replicated, group=None, sa
     """(axis, bounds): balanced voxel-layer slabs.  axis = 0/1/2 keeps the caller's axis; "auto" takes the axis whose
     balanced cut has the lightest heaviest slab (a terrestrial scan has almost all of its points in two or three z
     layers, so z slabs cannot be balanced, while x or y slabs can).  Counts come from every sample_stride-th point --
-    ownership is by layer range, so the cut positions need not be exact, only identical on every rank (they are: the
-    sampled histograms are all-reduced for row chunks and identical for replicated input)."""
+    ownership is by layer range, so the cut positions need not be exact, only identical on every rank.  `points` is
+    this rank's row chunk (replicated=False: the histograms of all candidate axes are summed over the ranks in ONE
+    all-reduce and read back once) or the whole cloud (replicated=True: no collective)."""
+    import torch
     import torch.distributed as dist
     from . import device as dev
-    best = None
+    axes, hists = [], []
     for ax in ((0, 1, 2) if axis == "auto" else (int(axis),)):
         n_layers = dev.grid_layers(bbox, sampleDl, ax)
         if n_layers > MAX_LAYERS:
@@ -297,16 +310,22 @@ def choose_slabs(points, sampleDl, bbox, world, axis, replicated, group=None, sa
                 continue
             raise ValueError("grid has %d layers along axis %d (limit %d): sampleDl too small for this extent"
                              % (n_layers, ax, MAX_LAYERS))
-        hist = dev.grid_layer_hist(points, sampleDl, ax, bbox, sample_stride)
-        if not replicated:
-            dist.all_reduce(hist, group=group)
-        h = hist.cpu().numpy()
+        axes.append(ax)
+        hists.append(dev.grid_layer_hist(points, sampleDl, ax, bbox, sample_stride))
+    if not axes:
+        raise ValueError("no axis of the grid has at most %d layers: sampleDl too small for this extent" % MAX_LAYERS)
+    every = torch.cat(hists) if len(hists) > 1 else hists[0]
+    if not replicated:
+        dist.all_reduce(every, group=group)
+    every = every.cpu().numpy()
+    best, at = None, 0
+    for ax, hist in zip(axes, hists):
+        h = every[at:at + hist.numel()]
+        at += hist.numel()
         bounds = balanced_slabs(h, world)
         load = max(int(h[bounds[r]:bounds[r + 1]].sum()) for r in range(world))
         if best is None or load < best[0]:  # ties keep the lower axis: deterministic
             best = (load, ax, bounds)
-    if best is None:
-        raise ValueError("no axis of the grid has at most %d layers: sampleDl too small for this extent" % MAX_LAYERS)
     return best[1], best[2]
 
 
@@ -328,19 +347,23 @@ def grid_subsample_sharded(points, features=None, classes=None, sampleDl=0.1, *,
     n_local = points.shape[0]
     if classes is not None and classes.dim() == 1:
         classes = classes[:, None]
-    # 1. geometry of the whole cloud
-    if n_local:
-        box = torch.tensor(dev.grid_bbox(points), dtype=torch.float32, device=points.device)
+    # 1. geometry of the whole cloud.  A replicated cloud is scanned in row chunks too (every rank reads 1/world of it
+    # for the corners and for the layer histograms; the few KB of partial results are all-reduced).
+    mine = points
+    if replicated and world > 1:
+        b, e = shard_range(n_local, world, rank)
+        mine = points[b:e]
+    if mine.shape[0]:
+        box = torch.tensor(dev.grid_bbox(mine), dtype=torch.float32, device=points.device)
     else:
         box = torch.tensor([float("inf")] * 3 + [float("-inf")] * 3, dtype=torch.float32, device=points.device)
-    if not replicated:
-        lo, hi = box[:3].clone(), box[3:].clone()
-        dist.all_reduce(lo, op=dist.ReduceOp.MIN, group=group)
-        dist.all_reduce(hi, op=dist.ReduceOp.MAX, group=group)
-        box = torch.cat([lo, hi])
+    if world > 1:
+        box[3:] = -box[3:]  # one MIN all-reduce for both corners
+        dist.all_reduce(box, op=dist.ReduceOp.MIN, group=group)
+        box[3:] = -box[3:]
     bbox = [float(v) for v in box.cpu()]
     # 2. balanced slabs from the (sampled) layer histogram, counted by the library
-    axis, bounds = choose_slabs(points, sampleDl, bbox, world, axis, replicated, group=group)
+    axis, bounds = choose_slabs(mine, sampleDl, bbox, world, axis, world == 1, group=group)
     tail = (axis,) if return_axis else ()
     if replicated:
         slab = (axis, int(bounds[rank]), int(bounds[rank + 1]))
