@@ -275,6 +275,18 @@ struct SortParams {
 };
 
 
+// Lanes of the warp holding the same radix digit (0 .. BINS; BINS = "no element"): nine ballots and a few logic ops,
+// a fixed cost, where match.any takes one round per DISTINCT value -- 32 rounds on the random low digits of a key.
+__device__ __forceinline__ unsigned match_digit(unsigned digit) {
+    unsigned peers = 0xffffffffu;
+#pragma unroll
+    for (int b = 0; b < 9; ++b) {
+        const bool on = (digit >> b) & 1u;
+        const unsigned bal = __ballot_sync(0xffffffffu, on);
+        peers &= on ? bal : ~bal;
+    }
+    return peers;
+}
 constexpr int SLAB_STAGES = 3;  // quads of 128 points per warp in the slab pass's cp.async ring
 __device__ __forceinline__ void cp_async_16(void* smem, const void* gmem) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
@@ -629,7 +641,7 @@ __global__ void __launch_bounds__(PA_THREADS, 1) sort_kernel(const SortParams p)
             }
             // warp-aggregated histogram of the low digit
             const unsigned digit = member ? (unsigned)(key & (BINS - 1)) : BINS;
-            const unsigned peers = __match_any_sync(0xffffffffu, digit);
+            const unsigned peers = match_digit(digit);
             if (member && (peers & ((1u << lane) - 1u)) == 0) atomicAdd(&s_tot[digit], __popc(peers));
         }
     }
@@ -709,6 +721,16 @@ __global__ void __launch_bounds__(PA_THREADS, 1) sort_kernel(const SortParams p)
         unsigned* vout = p.idx[cur ^ 1];
         const bool implicit_idx = shift == 0 && !slab;  // the first pass of a whole cloud: value = position
         const bool chunk_matches = shift == 0 && !slab; // the P1 histogram was taken over [cb, ce), which is [sb, se)
+        // How many DISTINCT digits does a row of 32 keys hold in this pass?  match.any costs one round per distinct
+        // value (cheap on the top digits of a key, where a few values dominate), the ballot form a fixed nine: every
+        // warp samples one row of its chunk and picks for the whole pass (speed only -- the masks are the same).
+        bool few;
+        {
+            const unsigned long long i = sb + (unsigned long long)warp * 32u + lane;
+            const unsigned dg = i < se ? (unsigned)(__ldcg(kin + i) >> shift) & (BINS - 1) : BINS;
+            const unsigned pe = __match_any_sync(0xffffffffu, dg);
+            few = __popc(__ballot_sync(0xffffffffu, (pe & ((1u << lane) - 1u)) == 0)) <= 12;
+        }
         if (shift > 0 || !chunk_matches) {
             // (slab: P1 counted the members of this CTA's POINT chunk, the sort chunks partition the compacted array)
             for (unsigned i = t; i < BINS; i += PA_THREADS) s_tot[i] = 0;
@@ -724,7 +746,7 @@ __global__ void __launch_bounds__(PA_THREADS, 1) sort_kernel(const SortParams p)
                 for (int u = 0; u < 4; ++u) {
                     const bool in = b + (unsigned long long)u * PA_THREADS + t < se;
                     const unsigned digit = in ? (unsigned)(kk[u] >> shift) & (BINS - 1) : BINS;
-                    const unsigned peers = __match_any_sync(0xffffffffu, digit);
+                    const unsigned peers = few ? __match_any_sync(0xffffffffu, digit) : match_digit(digit);
                     if (in && (peers & ((1u << lane) - 1u)) == 0) atomicAdd(&s_tot[digit], __popc(peers));
                 }
             }
@@ -781,7 +803,7 @@ __global__ void __launch_bounds__(PA_THREADS, 1) sort_kernel(const SortParams p)
                 const unsigned long long i = b + (unsigned long long)warp * (32 * SC_ITEMS) + (unsigned)k * 32u + lane;
                 const bool in = i < se;
                 const unsigned digit = in ? (unsigned)(key[k] >> shift) & (BINS - 1) : BINS;
-                const unsigned peers = __match_any_sync(0xffffffffu, digit);
+                const unsigned peers = few ? __match_any_sync(0xffffffffu, digit) : match_digit(digit);
                 const unsigned r = __popc(peers & ((1u << lane) - 1u));
                 const unsigned before = in ? s_cnt[warp][digit] : 0u;  // same digit in the earlier rows of this warp
                 rank[k] = before + r;
@@ -838,23 +860,45 @@ __global__ void __launch_bounds__(PA_THREADS, 1) sort_kernel(const SortParams p)
         if (t == 0 && shift / 8 < 8) s_mark[3 + shift / 8] = gtimer_ns();
     }
 
-    // ---- P3: segment heads -> voxel starts
+    // ---- P3: segment heads -> voxel starts.  Every warp owns a contiguous run of the CTA's chunk: it counts its heads,
+    // the counts of all warps of the grid are prefixed after one barrier, and the warp writes its heads' positions
+    // with ballot ranks -- no block barrier per tile.
     const unsigned long long* ks = p.keys[cur];
-    unsigned heads = 0;
-    for (unsigned long long b = sb; b < se; b += PA_THREADS) {
-        const unsigned long long i = b + t;
-        if (i < se) heads += (i == 0 || __ldcg(ks + i) != __ldcg(ks + i - 1)) ? 1u : 0u;
-    }
-    unsigned tot;
-    block_excl_scan(heads, s_w, &tot);
-    if (t == 0) p.cta_count[c] = tot;
+    const unsigned long long hlen = per / PA_WARPS;  // a multiple of 32
+    const unsigned long long hb = min(sb + (unsigned long long)warp * hlen, se), he = min(hb + hlen, se);
+    auto walk_heads = [&](bool write, unsigned long long first_id) {
+        unsigned long long seen = 0;
+        for (unsigned long long b0 = hb; b0 < he; b0 += 128) {  // four rows of keys in flight
+            unsigned long long kk[4], prev0[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const unsigned long long i = b0 + 32u * (unsigned)u + lane;
+                kk[u] = i < he ? __ldcg(ks + i) : 0ull;
+                prev0[u] = (lane == 0 && i < he && i > 0) ? __ldcg(ks + i - 1) : 0ull;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const unsigned long long i = b0 + 32u * (unsigned)u + lane;
+                unsigned long long pk = __shfl_up_sync(0xffffffffu, kk[u], 1);
+                if (lane == 0) pk = prev0[u];
+                const bool head = i < he && (i == 0 || kk[u] != pk);
+                const unsigned bal = __ballot_sync(0xffffffffu, head);
+                if (write && head) p.starts[first_id + seen + __popc(bal & ((1u << lane) - 1u))] = (unsigned)i;
+                seen += __popc(bal);
+            }
+        }
+        return seen;
+    };
+    const unsigned long long my_heads = walk_heads(false, 0ull);
+    if (lane == 0) p.wcount[c * PA_WARPS + warp] = (unsigned)my_heads;
     grid_barrier(p.barrier, G, &s_bar_target);
+    unsigned long long vbase, M;
     {
-        unsigned long long pre = 0, all = 0;
-        for (unsigned b = t; b < G; b += PA_THREADS) {
-            const unsigned v = __ldcg(p.cta_count + b);
+        unsigned long long pre = 0, all = 0;  // heads of the CTAs before this one, of all CTAs
+        for (unsigned j = t; j < G * PA_WARPS; j += PA_THREADS) {
+            const unsigned v = __ldcg(p.wcount + j);
             all += v;
-            if (b < c) pre += v;
+            if (j < c * PA_WARPS) pre += v;
         }
 #pragma unroll
         for (int m = 16; m > 0; m >>= 1) {
@@ -870,6 +914,8 @@ __global__ void __launch_bounds__(PA_THREADS, 1) sort_kernel(const SortParams p)
             s_maxkey = v;  // borrowed: voxel id of this CTA's first head
         }
         __syncthreads();
+        vbase = s_maxkey;
+        __syncthreads();
         if (lane == 0) s_red64[warp] = all;
         __syncthreads();
         if (t == 0) {
@@ -878,18 +924,19 @@ __global__ void __launch_bounds__(PA_THREADS, 1) sort_kernel(const SortParams p)
             s_n = v;  // borrowed: M
         }
         __syncthreads();
+        M = s_n;
+        const unsigned mine = __ldcg(p.wcount + c * PA_WARPS + lane);  // heads of the earlier warps of this CTA
+        unsigned inc = mine;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned nn = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += nn;
+        }
+        vbase += __shfl_sync(0xffffffffu, inc - mine, warp);
     }
-    unsigned long long vbase = s_maxkey;
-    const unsigned long long M = s_n;
     if (t == 0) s_mark[11] = gtimer_ns();
-    for (unsigned long long b = sb; b < se; b += PA_THREADS) {
-        const unsigned long long i = b + t;
-        const bool head = i < se && (i == 0 || __ldcg(ks + i) != __ldcg(ks + i - 1));
-        unsigned tt;
-        const unsigned rank = block_excl_scan(head ? 1u : 0u, s_w, &tt);
-        if (head) p.starts[vbase + rank] = (unsigned)i;
-        vbase += tt;
-    }
+    walk_heads(true, vbase);
+    __syncthreads();
     if (c == 0 && t == 0) {
         p.starts[M] = (unsigned)n;
         p.meta->M = M;
@@ -990,7 +1037,64 @@ struct ReduceParams {
     unsigned heavy_cap;
     unsigned heavy_min;     // voxels with more points than this are deferred to reduce_heavy_kernel
     int direct;             // pts / feats / cls are rows in SORTED order (sorted_rows_kernel ran): row = sorted position
+    unsigned pts_stride, feat_stride, cls_stride;  // bytes from one row to the next
 };
+
+// Input rows packed into one record each -- xyz | features | labels, padded to a multiple of 16 bytes -- so that the
+// reduce's gather through the sorted index costs ONE or two 32-byte sectors per point instead of one or two per ARRAY
+// (12-byte rows straddle sector boundaries: 3.75 sectors per point for xyz + rgb + label).  Sequential reads and
+// writes, run before the sort when the cloud is larger than the L2 (on an L2-resident cloud the gathers are cheap).
+struct PackParams {
+    const float* pts;
+    const void* feats;
+    const void* cls;
+    unsigned feat_bytes, cls_bytes;  // per row
+    unsigned cls_off, rec_bytes;     // labels start here inside a record; record size
+    unsigned long long N;
+    unsigned char* rec;
+};
+constexpr int PK_THREADS = 256;
+__global__ void __launch_bounds__(PK_THREADS) pack_rows_kernel(const PackParams p) {
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    const bool fast = p.rec_bytes == 32 && p.feat_bytes == 12 && p.cls_bytes == 4 && p.cls_off == 24;
+    const bool fast16 = p.rec_bytes == 16 && p.feat_bytes == 3 && p.cls_bytes == 1 && p.cls_off == 15;
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < p.N; i += stride) {
+        const float x = __ldg(p.pts + 3ull * i), y = __ldg(p.pts + 3ull * i + 1), z = __ldg(p.pts + 3ull * i + 2);
+        unsigned char* r = p.rec + i * p.rec_bytes;
+        if (fast) {  // xyz + three float32 features + one int32 label: two 16-byte stores
+            const unsigned* f = reinterpret_cast<const unsigned*>(p.feats) + 3ull * i;
+            const unsigned f0 = __ldg(f), f1 = __ldg(f + 1), f2 = __ldg(f + 2);
+            const unsigned lab = __ldg(reinterpret_cast<const unsigned*>(p.cls) + i);
+            reinterpret_cast<uint4*>(r)[0] = make_uint4(__float_as_uint(x), __float_as_uint(y), __float_as_uint(z), f0);
+            reinterpret_cast<uint4*>(r)[1] = make_uint4(f1, f2, lab, 0u);
+            continue;
+        }
+        if (fast16) {  // xyz + three uint8 features + one uint8 label: one 16-byte store
+            const unsigned char* f = reinterpret_cast<const unsigned char*>(p.feats) + 3ull * i;
+            const unsigned w = (unsigned)__ldg(f) | ((unsigned)__ldg(f + 1) << 8) | ((unsigned)__ldg(f + 2) << 16) |
+                               ((unsigned)__ldg(reinterpret_cast<const unsigned char*>(p.cls) + i) << 24);
+            *reinterpret_cast<uint4*>(r) = make_uint4(__float_as_uint(x), __float_as_uint(y), __float_as_uint(z), w);
+            continue;
+        }
+        reinterpret_cast<float*>(r)[0] = x;
+        reinterpret_cast<float*>(r)[1] = y;
+        reinterpret_cast<float*>(r)[2] = z;
+        if (p.feat_bytes) {
+            const unsigned char* a = reinterpret_cast<const unsigned char*>(p.feats) + i * p.feat_bytes;
+            if ((p.feat_bytes & 3u) == 0)
+                for (unsigned j = 0; j < p.feat_bytes; j += 4) *reinterpret_cast<unsigned*>(r + 12 + j) = __ldg(reinterpret_cast<const unsigned*>(a + j));
+            else
+                for (unsigned j = 0; j < p.feat_bytes; ++j) r[12 + j] = __ldg(a + j);
+        }
+        if (p.cls_bytes) {
+            const unsigned char* a = reinterpret_cast<const unsigned char*>(p.cls) + i * p.cls_bytes;
+            if ((p.cls_bytes & 3u) == 0)
+                for (unsigned j = 0; j < p.cls_bytes; j += 4) *reinterpret_cast<unsigned*>(r + p.cls_off + j) = __ldg(reinterpret_cast<const unsigned*>(a + j));
+            else
+                for (unsigned j = 0; j < p.cls_bytes; ++j) r[p.cls_off + j] = __ldg(a + j);
+        }
+    }
+}
 
 // Rows of the input arrays in sorted (voxel-major, input order inside a voxel) order, so that the reduce reads
 // consecutive records instead of chasing an index per point.  The gathers happen HERE, where every thread has
@@ -1064,15 +1168,18 @@ __global__ void __launch_bounds__(SR_THREADS) sorted_rows_kernel(const SortedRow
     }
 }
 
+// Rows are addressed as base + row * stride (bytes): the caller's own arrays (strides 12, fdim * size, ldim * size) or
+// the packed records of pack_rows_kernel (one stride for all three, every row inside one or two 32-byte sectors).
+__device__ __forceinline__ float load_coord(const ReduceParams& p, unsigned long long row, int ch) {
+    return __ldg(reinterpret_cast<const float*>(reinterpret_cast<const unsigned char*>(p.pts) + row * p.pts_stride) + ch);
+}
 __device__ __forceinline__ float load_feat(const ReduceParams& p, unsigned long long row, int j) {
-    const unsigned long long o = row * (unsigned long long)p.fdim + j;
-    return p.feat_u8 ? (float)__ldg(reinterpret_cast<const unsigned char*>(p.feats) + o)
-                     : __ldg(reinterpret_cast<const float*>(p.feats) + o);
+    const unsigned char* r = reinterpret_cast<const unsigned char*>(p.feats) + row * p.feat_stride;
+    return p.feat_u8 ? (float)__ldg(r + j) : __ldg(reinterpret_cast<const float*>(r) + j);
 }
 __device__ __forceinline__ int load_label(const ReduceParams& p, unsigned long long row, int col) {
-    const unsigned long long o = row * (unsigned long long)p.ldim + col;
-    return p.cls_u8 ? (int)__ldg(reinterpret_cast<const unsigned char*>(p.cls) + o)
-                    : __ldg(reinterpret_cast<const int*>(p.cls) + o);
+    const unsigned char* r = reinterpret_cast<const unsigned char*>(p.cls) + row * p.cls_stride;
+    return p.cls_u8 ? (int)__ldg(r + col) : __ldg(reinterpret_cast<const int*>(r) + col);
 }
 
 // The label table of one voxel (first-occurrence order, like the reference's unordered_map insertions); every lane of
@@ -1152,7 +1259,7 @@ __global__ void __launch_bounds__(RB_THREADS, 5) reduce_kernel(const ReduceParam
 #pragma unroll
                             for (int j = 0; j < 8; ++j) {
                                 const int ch = cbase + j;
-                                if (ch < CH) stage[l * 9 + j] = ch < 3 ? __ldg(p.pts + 3ull * row + ch) : load_feat(p, row, ch - 3);
+                                if (ch < CH) stage[l * 9 + j] = ch < 3 ? load_coord(p, row, ch) : load_feat(p, row, ch - 3);
                             }
                         }
                         __syncwarp(gmask);
@@ -1223,6 +1330,112 @@ __global__ void __launch_bounds__(RB_THREADS, 5) reduce_kernel(const ReduceParam
     if (threadIdx.x == 0) atomicMax(&p.meta->tmark[14], gtimer_ns());
 }
 
+// The same reduce for the two layouts every reference caller has -- xyz + three colour channels + one label column --
+// read from PACKED records (pack_rows_kernel): REC = 32: float32 colours, int32 label (device callers); REC = 16: uint8
+// colours and label (the data-preparation scripts).  A point is ONE or two 16-byte loads, everything else is compile-time
+// constant: about a third of the generic kernel's instructions per voxel.
+template <int REC>
+__global__ void __launch_bounds__(RB_THREADS, 5) reduce_rec_kernel(const ReduceParams p) {
+    __shared__ __align__(16) float s_stage[RB_GROUPS][STAGE_STRIDE];  // 8 points x 8 words (+ 8 pad: the four groups of a warp read different banks)
+    __shared__ int s_labs[RB_GROUPS][LABEL_CAP], s_cnts[RB_GROUPS][LABEL_CAP];
+    const unsigned long long M = p.meta->M;
+    const int cur = p.meta->cur;
+    if (blockIdx.x == 0 && threadIdx.x == 0) p.meta->tmark[13] = gtimer_ns();
+    const unsigned long long* keys = p.keys[cur];
+    const unsigned* idx = p.idx[cur];
+    const unsigned char* rec = reinterpret_cast<const unsigned char*>(p.pts);
+    const int tid = threadIdx.x, g = tid >> 3, l = tid & 7, lane = tid & 31;
+    const int gshift = (lane >> 3) * 8;
+    const unsigned gmask = 0xFFu << gshift;
+    float* stage = s_stage[g];
+    int* labs = s_labs[g];
+    int* cnts = s_cnts[g];
+    bool overflow = false;
+    const unsigned long long ngroups = (unsigned long long)gridDim.x * RB_GROUPS;
+    for (unsigned long long v = (unsigned long long)blockIdx.x * RB_GROUPS + g; v < M; v += ngroups) {
+        const unsigned long long s = p.starts[v], e = p.starts[v + 1];
+        const unsigned cnt = (unsigned)(e - s);
+        if (cnt > p.heavy_min) {
+            if (l == 0) {
+                const unsigned pos = atomicAdd(&p.meta->n_heavy, 1u);
+                if (pos < p.heavy_cap) p.heavy[pos] = (unsigned)v;
+            }
+            continue;
+        }
+        const float a = (float)(1.0 / (double)cnt);  // grid_subsampling.cpp:87
+        const float cf = (float)cnt;
+        float acc = 0.f;
+        int nl = 0;
+        unsigned long long row_next = (unsigned)l < cnt ? (unsigned long long)idx[s + l] : 0ull;
+        for (unsigned c0 = 0; c0 < cnt; c0 += 8) {
+            const int m = (int)min(8u, cnt - c0);
+            const unsigned long long row = row_next;
+            if (c0 + 8 + l < cnt) row_next = (unsigned long long)idx[s + c0 + 8 + l];
+            int lab = 0;
+            if (l < m) {
+                const uint4 r0 = __ldg(reinterpret_cast<const uint4*>(rec + row * REC));
+                float4 lo, hi;
+                lo.x = __uint_as_float(r0.x);
+                lo.y = __uint_as_float(r0.y);
+                lo.z = __uint_as_float(r0.z);
+                if (REC == 32) {
+                    const uint4 r1 = __ldg(reinterpret_cast<const uint4*>(rec + row * REC) + 1);
+                    lo.w = __uint_as_float(r0.w);
+                    hi.x = __uint_as_float(r1.x);
+                    hi.y = __uint_as_float(r1.y);
+                    lab = (int)r1.z;
+                } else {
+                    lo.w = (float)(r0.w & 0xFFu);
+                    hi.x = (float)((r0.w >> 8) & 0xFFu);
+                    hi.y = (float)((r0.w >> 16) & 0xFFu);
+                    lab = (int)(r0.w >> 24);
+                }
+                hi.z = hi.w = 0.f;
+                reinterpret_cast<float4*>(stage + l * 8)[0] = lo;
+                reinterpret_cast<float4*>(stage + l * 8)[1] = hi;
+            }
+            __syncwarp(gmask);
+            if (l < 6) {  // this lane owns channel l: add the points in input order
+#pragma unroll
+                for (int t = 0; t < 8; ++t)
+                    if (t < m) acc = __fadd_rn(acc, stage[t * 8 + l]);
+            }
+            __syncwarp(gmask);
+            const int first = __shfl_sync(gmask, lab, gshift);
+            const bool same = l >= m || lab == first;
+            if (((__ballot_sync(gmask, same) >> gshift) & 0xFFu) == 0xFFu) {
+                overflow |= !table_add(labs, cnts, &nl, first, m, gmask, gshift, l);
+            } else {
+                for (int t = 0; t < m; ++t)
+                    overflow |= !table_add(labs, cnts, &nl, __shfl_sync(gmask, lab, gshift + t), 1, gmask, gshift, l);
+            }
+        }
+        if (l < 3) p.out_p[3ull * v + l] = __fmul_rn(acc, a);
+        else if (l < 6) p.out_f[3ull * v + (l - 3)] = __fdiv_rn(acc, cf);
+        {   // winner of the table: largest count, ties by the reference's hash-iteration order
+            int best = -1;
+            for (int q = l; q < nl; q += 8) best = max(best, cnts[q]);
+#pragma unroll
+            for (int mm = 1; mm < 8; mm <<= 1) best = max(best, __shfl_xor_sync(gmask, best, mm));
+            int nbest = 0, arg = -1;
+            for (int q0 = 0; q0 < nl; q0 += 8) {
+                const int q = q0 + l;
+                const unsigned b = (__ballot_sync(gmask, q < nl && cnts[q] == best) >> gshift) & 0xFFu;
+                if (b && arg < 0) arg = q0 + __ffs((int)b) - 1;
+                nbest += __popc(b);
+            }
+            if (l == 0) p.out_c[v] = nbest == 1 ? labs[arg] : label_first_in_iteration_order(labs, cnts, nl, best);
+            __syncwarp(gmask);
+        }
+        if (l == 0) {
+            p.out_k[v] = keys[s];
+            p.out_n[v] = (int)cnt;
+        }
+    }
+    if (overflow) p.meta->error = 2;
+    if (threadIdx.x == 0) atomicMax(&p.meta->tmark[14], gtimer_ns());
+}
+
 // Heavy voxels (a terrestrial scan puts tens of thousands of points into the voxels next to the scanner): the sums
 // must still be the reference's sequential += in input order, so the ADDS of a channel stay one dependent chain -- but
 // the gathers need not wait for them.  One CTA per voxel: warps 1..7 gather batch b+1 (sorted index -> xyz, features,
@@ -1268,7 +1481,7 @@ __global__ void __launch_bounds__(RH_THREADS) reduce_heavy_kernel(const ReducePa
 #pragma unroll
                         for (int j = 0; j < 8; ++j) {
                             const int ch = ch0 + j;
-                            if (ch < CH) s_val[buf][il * 9 + j] = ch < 3 ? __ldg(p.pts + 3ull * row + ch) : load_feat(p, row, ch - 3);
+                            if (ch < CH) s_val[buf][il * 9 + j] = ch < 3 ? load_coord(p, row, ch) : load_feat(p, row, ch - 3);
                         }
                         if (vote) {
                             const int lab = load_label(p, row, 0);
@@ -1631,6 +1844,36 @@ static int run_core(Ctx* c, cudaStream_t s, const Inputs& in, size_t N, size_t f
             return !(e && e[0] == '0');
         }();
         rp.heavy_min = heavy_on ? HEAVY_MIN : 0xFFFFFFFFu;
+        const size_t fbytes = fdim ? fdim * (in.f_u8 ? 1 : 4) : 0, cbytes = ldim ? ldim * (in.c_u8 ? 1 : 4) : 0;
+        rp.pts_stride = 12;
+        rp.feat_stride = (unsigned)fbytes;
+        rp.cls_stride = (unsigned)cbytes;
+        // SSDR_GRID_PACK=0 / 1 forces the packed records off / on (A/B runs); default: whole clouds beyond the L2
+        const char* pack_e = getenv("SSDR_GRID_PACK");  // read per call: the tests flip it inside one process
+        const int pack_env = pack_e && pack_e[0] ? (pack_e[0] == '0' ? 0 : 1) : -1;
+        const bool pack = slab.axis < 0 && (fbytes + cbytes) > 0 &&
+                          (pack_env >= 0 ? pack_env == 1
+                                         : (N * (12 + fbytes + cbytes) >= ((size_t)128 << 20) ||  // beyond the L2 ...
+                                            (fdim == 3 && ldim == 1 && in.f_u8 == in.c_u8)));     // ... or a layout with a reduce of its own
+        if (pack) {
+            PackParams q;
+            q.pts = in.p;
+            q.feats = rp.feats;
+            q.cls = rp.cls;
+            q.feat_bytes = (unsigned)fbytes;
+            q.cls_bytes = (unsigned)cbytes;
+            q.cls_off = (unsigned)((cbytes && !in.c_u8) ? (12 + fbytes + 3) / 4 * 4 : 12 + fbytes);
+            q.rec_bytes = (unsigned)((q.cls_off + cbytes + 15) / 16 * 16);
+            q.N = N;
+            SSDR_TRY(c->ws[WS_REC].reserve(N * (size_t)q.rec_bytes));
+            q.rec = c->ws[WS_REC].as<unsigned char>();
+            const size_t want_b = (N + PK_THREADS - 1) / PK_THREADS, cap_b = (size_t)c->sm_count * 32;
+            pack_rows_kernel<<<(unsigned)(want_b < cap_b ? want_b : cap_b), PK_THREADS, 0, s>>>(q);
+            rp.pts = reinterpret_cast<const float*>(q.rec);
+            if (fbytes) rp.feats = q.rec + 12;
+            if (cbytes) rp.cls = q.rec + q.cls_off;
+            rp.pts_stride = rp.feat_stride = rp.cls_stride = q.rec_bytes;
+        }
         static const bool sorted_rows_on = [] {
             // =1: rows gathered into sorted order by a kernel of their own, sequential reduce (A/B runs: the gather pass
             // costs more than the reduce saves, profiles/r02_grid_sorted_rows_ab.txt)
@@ -1638,8 +1881,8 @@ static int run_core(Ctx* c, cudaStream_t s, const Inputs& in, size_t N, size_t f
             return e && e[0] == '1';
         }();
         rp.direct = 0;
-        if (sorted_rows_on) {
-            const size_t fb = fdim ? fdim * (in.f_u8 ? 1 : 4) : 0, cb = ldim ? ldim * (in.c_u8 ? 1 : 4) : 0;
+        if (sorted_rows_on && !pack) {
+            const size_t fb = fbytes, cb = cbytes;
             const size_t o_f = (N * 12 + 255) / 256 * 256, o_c = o_f + (N * fb + 255) / 256 * 256;
             SSDR_TRY(c->ws[WS_REC].reserve(o_c + N * cb + 256));
             unsigned char* rec = c->ws[WS_REC].as<unsigned char>();
@@ -1663,7 +1906,12 @@ static int run_core(Ctx* c, cudaStream_t s, const Inputs& in, size_t N, size_t f
             if (cb) rp.cls = q.out_c;
             rp.direct = 1;
         }
-        reduce_kernel<<<blocks, RB_THREADS, 0, s>>>(rp);
+        // the two layouts of the reference callers (xyz + rgb + one label column) have a reduce of their own
+        const bool rec32 = pack && fdim == 3 && ldim == 1 && !in.f_u8 && !in.c_u8;
+        const bool rec16 = pack && fdim == 3 && ldim == 1 && in.f_u8 && in.c_u8;
+        if (rec32) reduce_rec_kernel<32><<<blocks, RB_THREADS, 0, s>>>(rp);
+        else if (rec16) reduce_rec_kernel<16><<<blocks, RB_THREADS, 0, s>>>(rp);
+        else reduce_kernel<<<blocks, RB_THREADS, 0, s>>>(rp);
         // the voxels the groups passed over (count on the device; none: the CTAs return at once)
         if (heavy_on) reduce_heavy_kernel<<<(unsigned)c->sm_count * 4, RH_THREADS, 0, s>>>(rp);
     }

@@ -69,6 +69,37 @@ def test_grid_vs_oracle(G, oracle, n, dl, fdim):
     assert p.tobytes() == wp.tobytes() and f.tobytes() == wf.tobytes() and np.array_equal(c, wc)
 
 
+@pytest.mark.parametrize("fdt,fdim,ldt,ldim", [("f4", 3, "i4", 1), ("u1", 3, "u1", 1), ("u1", 3, "i4", 1), ("f4", 5, "u1", 2),
+                                               ("u1", 6, None, 0), (None, 0, "i4", 1), ("f4", 1, "i4", 3)])
+def test_grid_packed_records_equal_plain_gather(G, oracle, monkeypatch, fdt, fdim, ldt, ldim):
+    """Clouds beyond the L2 are reduced from packed (xyz | features | labels) records; force that path on a small cloud
+    for every input layout (record sizes 16 .. 48 bytes, labels at aligned and unaligned offsets, a voxel heavy enough
+    for the one-CTA-per-voxel reduce) and compare with the oracle and with the plain gather bit for bit."""
+    rng = np.random.default_rng(fdim * 10 + ldim)
+    n = 60_000
+    pts = _room(rng, n)
+    pts[:3000] = pts[0] + (rng.random((3000, 3)) * 0.01).astype(np.float32)  # > 1024 points in one voxel
+    feats = None if fdt is None else (rng.integers(0, 256, (n, fdim)).astype(np.uint8) if fdt == "u1"
+                                      else rng.random((n, fdim), dtype=np.float32))
+    lab = None if ldt is None else rng.integers(0, 13, (n, ldim)).astype(np.uint8 if ldt == "u1" else np.int32)
+    want = oracle.grid_subsample(pts, feats, lab, 0.05, order="key", with_keys=True)
+    got = {}
+    for mode in ("1", "0"):
+        monkeypatch.setenv("SSDR_GRID_PACK", mode)
+        got[mode] = G.compute(pts, features=feats, classes=lab, sampleDl=0.05, return_keys=True)
+    for mode in ("1", "0"):
+        res, k, cnt = got[mode]
+        res = res if isinstance(res, tuple) else (res,)
+        assert np.array_equal(k, want[3]) and np.array_equal(cnt, want[4])
+        assert res[0].tobytes() == want[0].tobytes()
+        j = 1
+        if feats is not None:
+            assert res[j].tobytes() == want[1].tobytes()
+            j += 1
+        if lab is not None:
+            assert np.array_equal(res[j], want[2])
+
+
 def test_grid_heavy_voxel_and_many_labels(G, oracle):
     rng = np.random.default_rng(11)
     n = 40_000
