@@ -270,6 +270,12 @@ struct SortParams {
     unsigned long long* pmax;   // [G] largest key per CTA
     unsigned* cta_count;        // [G] segment heads per CTA
     unsigned* wcount;           // [G][PA_WARPS] slab members staged by each warp
+    // slab members packed into records at their compacted position (rec_bytes = 32: xyz | 3 x float32 | int32 label,
+    // 16: xyz | 3 x uint8 | uint8 label; 0: none -- the reduce then gathers from the caller's arrays by input index)
+    const void* feats;
+    const void* cls;
+    unsigned char* rec;
+    int rec_bytes;
     unsigned* starts;           // [N + 1] voxel start offsets
     unsigned* barrier;          // monotonic arrival counter, zero at launch
 };
@@ -612,12 +618,52 @@ __global__ void __launch_bounds__(PA_THREADS, 1) sort_kernel(const SortParams p)
                     vv[u] = __ldcg(p.idx[1] + wb + i);
                 }
             }
+            if (p.rec_bytes) {
+                // the member's row, gathered HERE (four independent rows per lane in flight, nothing waits on them) into
+                // one record at its compacted position; the sort then carries positions, like a whole cloud's
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const unsigned i = i0 + 32u * (unsigned)u + lane;
-                if (i < run) {
-                    p.keys[0][dst + i] = kk[u];
-                    p.idx[0][dst + i] = vv[u];
+                for (int h = 0; h < 4; h += 2) {  // two rows at a time (registers)
+                    uint4 lo[2], hi[2];
+#pragma unroll
+                    for (int w = 0; w < 2; ++w) {
+                        const int u = h + w;
+                        const unsigned i = i0 + 32u * (unsigned)u + lane;
+                        if (i < run) {
+                            const unsigned long long row = vv[u];
+                            lo[w].x = __float_as_uint(__ldg(p.pts + 3ull * row));
+                            lo[w].y = __float_as_uint(__ldg(p.pts + 3ull * row + 1));
+                            lo[w].z = __float_as_uint(__ldg(p.pts + 3ull * row + 2));
+                            if (p.rec_bytes == 32) {
+                                const unsigned* f = reinterpret_cast<const unsigned*>(p.feats) + 3ull * row;
+                                lo[w].w = __ldg(f);
+                                hi[w] = make_uint4(__ldg(f + 1), __ldg(f + 2), __ldg(reinterpret_cast<const unsigned*>(p.cls) + row), 0u);
+                            } else {
+                                const unsigned char* f = reinterpret_cast<const unsigned char*>(p.feats) + 3ull * row;
+                                lo[w].w = (unsigned)__ldg(f) | ((unsigned)__ldg(f + 1) << 8) | ((unsigned)__ldg(f + 2) << 16) |
+                                          ((unsigned)__ldg(reinterpret_cast<const unsigned char*>(p.cls) + row) << 24);
+                            }
+                        }
+                    }
+#pragma unroll
+                    for (int w = 0; w < 2; ++w) {
+                        const int u = h + w;
+                        const unsigned i = i0 + 32u * (unsigned)u + lane;
+                        if (i < run) {
+                            uint4* r = reinterpret_cast<uint4*>(p.rec + (dst + i) * (unsigned long long)p.rec_bytes);
+                            r[0] = lo[w];
+                            if (p.rec_bytes == 32) r[1] = hi[w];
+                            p.keys[0][dst + i] = kk[u];
+                        }
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const unsigned i = i0 + 32u * (unsigned)u + lane;
+                    if (i < run) {
+                        p.keys[0][dst + i] = kk[u];
+                        p.idx[0][dst + i] = vv[u];
+                    }
                 }
             }
         }
@@ -719,7 +765,7 @@ __global__ void __launch_bounds__(PA_THREADS, 1) sort_kernel(const SortParams p)
         const unsigned* vin = p.idx[cur];
         unsigned long long* kout = p.keys[cur ^ 1];
         unsigned* vout = p.idx[cur ^ 1];
-        const bool implicit_idx = shift == 0 && !slab;  // the first pass of a whole cloud: value = position
+        const bool implicit_idx = shift == 0 && (!slab || p.rec_bytes != 0);  // first pass of a whole cloud or of packed slab members: value = position
         const bool chunk_matches = shift == 0 && !slab; // the P1 histogram was taken over [cb, ce), which is [sb, se)
         // How many DISTINCT digits does a row of 32 keys hold in this pass?  match.any costs one round per distinct
         // value (cheap on the top digits of a key, where a few values dominate), the ballot form a fixed nine: every
@@ -1804,6 +1850,21 @@ static int run_core(Ctx* c, cudaStream_t s, const Inputs& in, size_t N, size_t f
     sp.cta_count = reinterpret_cast<unsigned*>(ctl + 256 + (size_t)G * (sizeof(KeyT) + 6 * sizeof(float)));
     sp.hist = reinterpret_cast<unsigned*>(ctl + (256 + (size_t)G * (6 * sizeof(float) + sizeof(KeyT) + sizeof(unsigned)) + 255) / 256 * 256);
     sp.wcount = sp.hist + (size_t)G * BINS;
+    // slab + one of the two reference layouts: the members are packed into records while they are compacted
+    // (SSDR_GRID_PACK=0 keeps the gather through the input index, for A/B runs)
+    const char* pack_e = getenv("SSDR_GRID_PACK");  // read per call: the tests flip it inside one process
+    const int pack_env = pack_e && pack_e[0] ? (pack_e[0] == '0' ? 0 : 1) : -1;
+    const bool layout32 = fdim == 3 && ldim == 1 && !in.f_u8 && !in.c_u8, layout16 = fdim == 3 && ldim == 1 && in.f_u8 && in.c_u8;
+    const bool slab_pack = slab.axis >= 0 && layout32 && pack_env != 0;  // (device callers pass float32 / int32 rows)
+    sp.feats = in.f;
+    sp.cls = in.c;
+    sp.rec = nullptr;
+    sp.rec_bytes = 0;
+    if (slab_pack) {
+        sp.rec_bytes = layout32 ? 32 : 16;
+        SSDR_TRY(c->ws[WS_REC].reserve(N * (size_t)sp.rec_bytes));
+        sp.rec = c->ws[WS_REC].as<unsigned char>();
+    }
     sp.starts = c->ws[WS_STARTS].as<unsigned>();
     SSDR_CHECK_CUDA(cudaMemsetAsync(sp.barrier, 0, 256, s));
     {
@@ -1849,8 +1910,6 @@ static int run_core(Ctx* c, cudaStream_t s, const Inputs& in, size_t N, size_t f
         rp.feat_stride = (unsigned)fbytes;
         rp.cls_stride = (unsigned)cbytes;
         // SSDR_GRID_PACK=0 / 1 forces the packed records off / on (A/B runs); default: whole clouds beyond the L2
-        const char* pack_e = getenv("SSDR_GRID_PACK");  // read per call: the tests flip it inside one process
-        const int pack_env = pack_e && pack_e[0] ? (pack_e[0] == '0' ? 0 : 1) : -1;
         const bool pack = slab.axis < 0 && (fbytes + cbytes) > 0 &&
                           (pack_env >= 0 ? pack_env == 1
                                          : (N * (12 + fbytes + cbytes) >= ((size_t)128 << 20) ||  // beyond the L2 ...
@@ -1907,8 +1966,14 @@ static int run_core(Ctx* c, cudaStream_t s, const Inputs& in, size_t N, size_t f
             rp.direct = 1;
         }
         // the two layouts of the reference callers (xyz + rgb + one label column) have a reduce of their own
-        const bool rec32 = pack && fdim == 3 && ldim == 1 && !in.f_u8 && !in.c_u8;
-        const bool rec16 = pack && fdim == 3 && ldim == 1 && in.f_u8 && in.c_u8;
+        const bool rec32 = (pack || slab_pack) && layout32;
+        const bool rec16 = (pack || slab_pack) && layout16;
+        if (slab_pack) {  // (the heavy-voxel reduce reads the same records through the strides)
+            rp.pts = reinterpret_cast<const float*>(sp.rec);
+            rp.feats = sp.rec + 12;
+            rp.cls = sp.rec + (layout32 ? 24 : 15);
+            rp.pts_stride = rp.feat_stride = rp.cls_stride = (unsigned)sp.rec_bytes;
+        }
         if (rec32) reduce_rec_kernel<32><<<blocks, RB_THREADS, 0, s>>>(rp);
         else if (rec16) reduce_rec_kernel<16><<<blocks, RB_THREADS, 0, s>>>(rp);
         else reduce_kernel<<<blocks, RB_THREADS, 0, s>>>(rp);

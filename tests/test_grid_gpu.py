@@ -187,6 +187,7 @@ def test_grid_reference_row_order_vs_oracle(G, oracle, n, dl):
 def _slab_cloud(rng, n):
     p = (rng.random((n, 3)) * np.array([40.0, 30.0, 6.0])).astype(np.float32)
     p[: n // 3, 2] = rng.normal(1.0, 0.01, n // 3).astype(np.float32)  # a dense floor: unbalanced layers
+    p[-2500:] = p[-1] + (rng.random((2500, 3)) * 0.02).astype(np.float32)  # one voxel heavy enough for the one-CTA reduce
     p += np.float32(-7.3)
     f = rng.random((n, 3)).astype(np.float32)
     c = rng.integers(0, 13, (n, 1)).astype(np.int32)
@@ -194,7 +195,7 @@ def _slab_cloud(rng, n):
 
 
 @pytest.mark.parametrize("world", [2, 3, 5])
-def test_grid_slabs_replicated_cloud_equal_single_run(G, world):
+def test_grid_slabs_replicated_cloud_equal_single_run(G, world, monkeypatch):
     """Every virtual rank sees the whole cloud and reduces only its layers: rows concatenated in rank order are the
     single-run result, bit for bit (points, features, labels, keys, counts)."""
     import torch
@@ -214,6 +215,12 @@ def test_grid_slabs_replicated_cloud_equal_single_run(G, world):
         assert torch.equal(torch.cat([x[j] for x in parts]), want[j])
     assert np.array_equal(np.concatenate([x[3] for x in parts]), want[3])
     assert np.array_equal(np.concatenate([x[4] for x in parts]), want[4])
+    # the slab members are reduced from packed records by default; the gather through the input index gives the same
+    monkeypatch.setenv("SSDR_GRID_PACK", "0")
+    for r in range(world):
+        x = dev.grid_subsample(tp, tf, tc, 0.11, slab=(2, int(bounds[r]), int(bounds[r + 1])), return_keys=True)
+        assert all(torch.equal(x[j], parts[r][j]) for j in range(3)) and np.array_equal(x[3], parts[r][3])
+    monkeypatch.delenv("SSDR_GRID_PACK")
     # an empty slab is a valid shard
     e = dev.grid_subsample(tp, tf, tc, 0.11, slab=(2, n_layers + 5, n_layers + 9), return_keys=True)
     assert e[0].shape == (0, 3) and e[1].shape == (0, 3) and len(e[3]) == 0
