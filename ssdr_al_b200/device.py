@@ -1,6 +1,7 @@
 """Device-resident entry points: the same C ABI, fed with CUDA tensors (torch is used only for device memory and
 streams).  Work is enqueued on torch's current stream."""
 import ctypes as C
+import threading
 
 import torch
 
@@ -75,11 +76,28 @@ def grid_subsample(points, features=None, classes=None, sampleDl=0.1, bbox=None,
     fdim = features.shape[1] if features is not None else 0
     ldim = (1 if classes.dim() == 1 else classes.shape[1]) if classes is not None else 0
     dev = points.device
-    out_p = torch.empty((N, 3), dtype=torch.float32, device=dev)
-    out_f = torch.empty((N, fdim), dtype=torch.float32, device=dev) if fdim else None
-    out_c = torch.empty((N, ldim), dtype=torch.int32, device=dev) if ldim else None
-    out_k = torch.empty(N, dtype=torch.int64, device=dev) if return_keys else None
-    out_n = torch.empty(N, dtype=torch.int32, device=dev) if return_keys else None
+    # Worst-case-sized outputs.  A large cloud's come from ONE arena per device that is kept between calls (the rows
+    # leave it as compact copies): a fresh 80 M-row allocation per call would make torch's caching allocator split
+    # and re-grow its big blocks around the caller's other tensors -- milliseconds of cudaMalloc per call.
+    row_bytes = 12 + 4 * fdim + 4 * ldim + (12 if return_keys else 0)
+    arena = compact is not False and N * row_bytes > (256 << 20)
+    if arena:
+        compact = True
+        buf = _arena(dev, N * row_bytes + 5 * 256)
+        at = [0]
+
+        def carve(shape, dtype):
+            n_bytes = _ITEMSIZE[dtype] * int(shape[0]) * (int(shape[1]) if len(shape) > 1 else 1)
+            t = buf[at[0]:at[0] + n_bytes].view(dtype).view(shape)
+            at[0] += (n_bytes + 255) // 256 * 256
+            return t
+    else:
+        carve = lambda shape, dtype: torch.empty(shape, dtype=dtype, device=dev)
+    out_k = carve((N,), torch.int64) if return_keys else None  # (8-byte rows first: every piece stays aligned)
+    out_p = carve((N, 3), torch.float32)
+    out_f = carve((N, fdim), torch.float32) if fdim else None
+    out_c = carve((N, ldim), torch.int32) if ldim else None
+    out_n = carve((N,), torch.int32) if return_keys else None
     box = (C.c_float * 6)(*[float(v) for v in bbox]) if bbox is not None else None
     axis, lo, hi = slab if slab is not None else (-1, 0, 0)
     M = C.c_size_t(0)
@@ -95,6 +113,27 @@ def grid_subsample(points, features=None, classes=None, sampleDl=0.1, bbox=None,
         import numpy as np
         return res + (out_k[:m].cpu().numpy().view(np.uint64), out_n[:m].cpu().numpy())
     return res
+
+
+_ITEMSIZE = {torch.float32: 4, torch.int32: 4, torch.int64: 8}
+_ARENA = threading.local()  # per calling thread, like the library's own workspaces
+
+
+def _arena(dev, n_bytes):
+    """Grow-only scratch of the calling thread on `dev` (uint8 tensor of at least n_bytes).  Calls that share it must
+    be ordered on one stream (they are when the thread keeps torch's current stream)."""
+    key = (dev.type, dev.index if dev.index is not None else torch.cuda.current_device())
+    pool = _ARENA.__dict__.setdefault("pool", {})
+    buf = pool.get(key)
+    if buf is None or buf.numel() < n_bytes:
+        pool[key] = None  # drop the old block before the larger one is allocated
+        buf = pool[key] = torch.empty(n_bytes, dtype=torch.uint8, device=dev)
+    return buf
+
+
+def release_scratch():
+    """Give the calling thread's output arenas of large grid_subsample calls back to torch's allocator."""
+    _ARENA.__dict__.pop("pool", None)
 
 
 def _grid_arg(t, dtype, name, width=None):

@@ -81,13 +81,20 @@ def test_grid_packed_records_equal_plain_gather(G, oracle, monkeypatch, fdt, fdi
     pts[:3000] = pts[0] + (rng.random((3000, 3)) * 0.01).astype(np.float32)  # > 1024 points in one voxel
     feats = None if fdt is None else (rng.integers(0, 256, (n, fdim)).astype(np.uint8) if fdt == "u1"
                                       else rng.random((n, fdim), dtype=np.float32))
-    lab = None if ldt is None else rng.integers(0, 13, (n, ldim)).astype(np.uint8 if ldt == "u1" else np.int32)
+    lab = None
+    if ldt is not None:  # piecewise-constant labels with 3 % noise: single-label voxels (one thread each) and votes
+        lab = np.repeat((3 * (pts[:, 0] > 3.5) + 5 * (pts[:, 1] > 2.0))[:, None], ldim, 1)
+        noisy = rng.random((n, ldim)) < 0.03
+        lab = np.where(noisy, rng.integers(0, 13, (n, ldim)), lab).astype(np.uint8 if ldt == "u1" else np.int32)
     want = oracle.grid_subsample(pts, feats, lab, 0.05, order="key", with_keys=True)
     got = {}
     for mode in ("1", "0"):
         monkeypatch.setenv("SSDR_GRID_PACK", mode)
         got[mode] = G.compute(pts, features=feats, classes=lab, sampleDl=0.05, return_keys=True)
-    for mode in ("1", "0"):
+    monkeypatch.setenv("SSDR_GRID_PACK", "1")
+    monkeypatch.setenv("SSDR_GRID_SMALL", "0")  # every voxel by the eight-lane groups (no thread-per-voxel pass)
+    got["groups"] = G.compute(pts, features=feats, classes=lab, sampleDl=0.05, return_keys=True)
+    for mode in ("1", "0", "groups"):
         res, k, cnt = got[mode]
         res = res if isinstance(res, tuple) else (res,)
         assert np.array_equal(k, want[3]) and np.array_equal(cnt, want[4])
