@@ -460,6 +460,12 @@ def _oracle():
         return None
 
 
+def _grid_traffic():
+    """DRAM bytes of one config-1 subsampling call: the ncu captures of its kernels (pack, sort, the two reduces)."""
+    parts = [ncu_traffic(k) for k in ("grid_pack_1m", "grid_sort_1m", "grid_reduce_1m", "grid_reduce_groups_1m")]
+    return None if any(v is None for v in parts) else float(sum(parts))
+
+
 def secondary_metrics(torch, D, dev, flush, gpu_pyramid, gpu_pyramid_fused):
     """Grid subsampling + KNN (config-1 shape), FPS / k-center (config-4 shape), the tie-heavy pyramid (8f-1), chamfer
     adjacency: device resident, CUDA-event timed, each with its end-to-end and CPU-reference figure beside it."""
@@ -482,7 +488,7 @@ def secondary_metrics(torch, D, dev, flush, gpu_pyramid, gpu_pyramid_fused):
         algo = n * 28 + m * 28
         g = {"points": n, "voxels": int(m), "ms": ms, "mpts_per_s": n / ms / 1e3,
              "algorithmic_gbs": algo / ms / 1e6, "frac_of_hbm_peak": algo / ms / 1e6 / peak,
-             "traffic_bytes": ncu_traffic("grid_subsample_1m")}
+             "traffic_bytes": _grid_traffic()}
         # the same call through the reference-facing API (uint8 colours / labels in, conversions + PCIe inside)
         S.grid_subsampling.compute(p, features=rgb_h, classes=lab_h, sampleDl=0.04)
         g["e2e_ms"] = float(np.median([_cpu_ms(lambda: S.grid_subsampling.compute(

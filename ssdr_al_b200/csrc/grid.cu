@@ -2,18 +2,22 @@
 //
 // Replaces grid_subsampling() (utils/cpp_wrappers/cpp_subsampling/grid_subsampling/grid_subsampling.cpp:5-106),
 // a single-threaded unordered_map loop, by a sort + segmented sequential reduce that reproduces the reference
-// bit for bit.  THREE launches, no host round trip in between (the host reads the voxel count once, at the end):
+// bit for bit.  FIVE launches, no host round trip in between (the host reads the voxel count once, at the end):
 //
+//   pack_rows_kernel  xyz | features | labels of every point packed into ONE record (32 or 16 bytes for the two layouts
+//                     of the reference callers), so that a gathered point costs one sector instead of one or two per array
 //   sort_kernel   (persistent, cooperative, one CTA per SM; phases separated by a grid barrier)
 //     P0  min/max corners (cloud.cpp:27-67) -> origin = floor(min * (1/dl)) * dl, nX, nY (grid_subsampling.cpp:27-31)
 //     P1  key = iX + nX*iY + nX*nY*iZ with i* = floor((p-origin)/dl) in IEEE fp32, true division
-//         (grid_subsampling.cpp:53-56); points stream through shared memory as float4; slab members (multi-GPU) are
-//         compacted in input order; the digit histogram of the first radix pass is taken on the fly
-//     P2  STABLE LSD radix sort of (key, input index), 8 bits per pass, over the significant key bits only -- the
-//         number of passes is decided ON THE DEVICE from the largest key.  Per pass: per-CTA digit histogram, barrier,
-//         every CTA derives its digit offsets from the CTA-major histogram matrix, stable scatter of its contiguous
-//         chunk (warp match_any ranking keeps equal keys in input order), barrier
-//     P3  segment heads -> voxel start offsets, M
+//         (grid_subsampling.cpp:53-56); points stream through shared memory as float4, the digit histogram of the
+//         first radix pass is taken on the fly.  Slab mode (multi-GPU): ONE read of the cloud through per-warp cp.async
+//         rings, members compacted in input order and packed into records at their compacted position
+//     P2  STABLE LSD radix sort of (key, position), 8 bits per pass, over the significant key bits only -- the number
+//         of passes is decided ON THE DEVICE from the largest key.  Per pass: per-CTA digit histogram, barrier, every
+//         CTA derives its digit offsets from the CTA-major histogram matrix, stable scatter of its contiguous chunk
+//         (same-digit lane masks keep equal keys in input order; every round is put in digit order in shared memory
+//         and written out from there), barrier
+//     P3  segment heads -> voxel start offsets, M (warp-contiguous runs, ballot ranks)
 //   reduce_kernel (M known only on the device: grid-stride over voxels)
 //         eight lanes per voxel: the lanes gather up to eight points of the voxel in parallel (index, xyz, features,
 //         label) into shared memory, then every lane owns ONE CHANNEL (x, y, z, feature j) and adds the staged values
@@ -22,7 +26,9 @@
 //         (grid_subsampling.cpp:87-95); the label vote counts in a per-voxel shared-memory table that keeps
 //         first-occurrence order, ties resolved by libstdc++'s unordered_map iteration order
 //         (grid_subsampling.cpp:97-102)
-//   reduce_heavy_kernel: the voxels of more than 1024 points that reduce_kernel passed over, one CTA each
+//   reduce_small_kernel / reduce_rec_kernel: the same arithmetic for the reference layouts read from packed records --
+//         one THREAD per small single-label voxel first, the eight-lane groups take what it marks
+//   reduce_heavy_kernel: the voxels of more than 1024 points that the groups passed over, one CTA each
 //   optional (SSDR_GRID_ORDER_REFERENCE): rows permuted into the reference's libstdc++ hash-iteration order.
 // Rows come out in ascending voxel-key order by default (SSDR_GRID_ORDER_KEY).
 #include <stdlib.h>
