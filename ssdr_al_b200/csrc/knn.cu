@@ -1096,8 +1096,23 @@ static int run_dev(Ctx* c, cudaStream_t s, const float* d_pts, size_t B, size_t 
     const unsigned pstride = (unsigned)((N + PROBE_SAMPLE - 1) / PROBE_SAMPLE);
     const unsigned r2 = probe_on ? probe_resolution((unsigned)((N + pstride - 1) / pstride)) : 0u;
     size_t cap = (size_t)(3.0 * (double)N / occupancy) + 64;
-    if (r2 && cap < 4 * N) cap = 4 * N;
-    if (cap > (1u << 24)) cap = (1u << 24);
+    {
+        // cells a probed cloud may use per point: 4, or 8 for one large cloud queried with its own points (the query
+        // job shares the point job's arrays then, so the larger grid costs one scan, not two).  Config 3's barycentres
+        // (profiles/r02_cfg3_knn_cells.txt): 7.6 ms at 4, 6.5 at 8, 6.4 at 16, 6.9 at 32 cells per point on one GPU;
+        // as one of eight query blocks 2.4 / 2.8 / 4.0 / 4.9 ms.  SSDR_KNN_CELLS_PER_POINT overrides (A/B runs).
+        static const size_t cpp_env = [] {
+            const char* e = getenv("SSDR_KNN_CELLS_PER_POINT");
+            const int v = e ? atoi(e) : 0;
+            return (size_t)(v < 0 ? 0 : (v > 64 ? 64 : v));
+        }();
+        const size_t cpp = cpp_env ? cpp_env : ((d_q == d_pts && Q == N && N >= ((size_t)1 << 20)) ? 8 : 4);
+        if (r2 && cap < cpp * N) cap = cpp * N;
+    }
+    // (a scan of surfaces inside a 200 m bbox wants far more cells than points: the old 2^24 bound put 90 barycentres
+    // into every occupied cell of config 3's cloud -- 772 distance evaluations per query instead of ~150)
+    if (cap > ((size_t)1 << 28)) cap = (size_t)1 << 28;
+    if (cap > ((size_t)0xFFFFFFF0u / B) - 2) cap = ((size_t)0xFFFFFFF0u / B) - 2;  // 32-bit cell indices over all items
     if (N <= SG_MAX_POINTS && cap > SG_MAX_CELLS - 1 && (size_t)(3.0 * (double)N / occupancy) + 64 <= SG_MAX_CELLS - 1)
         cap = SG_MAX_CELLS - 1;  // stay within the shared memory of the single-CTA build
     const unsigned cstride = (unsigned)cap + 1;
