@@ -51,6 +51,7 @@ struct Meta {
     unsigned long long M;
     int cur;                     // which ping-pong pair holds the sorted (key, index) arrays
     unsigned n_heavy;            // voxels deferred to reduce_heavy_kernel (zeroed with the rest by the sort kernel)
+    unsigned n_deferred;         // voxels reduce_small_kernel left to the eight-lane groups (same)
     // %globaltimer marks (ns) of CTA 0: [0] start, [1] geometry, [2] keys, [3..10] end of radix pass k, [11] heads
     // counted, [12] starts written, [13] reduce start (first CTA), [14] reduce end (last CTA)
     unsigned long long tmark[16];
@@ -176,6 +177,7 @@ __global__ void setup_kernel(const float* __restrict__ partials, int nparts, flo
         m.M = 0;
         m.cur = 0;
         m.n_heavy = 0;
+        m.n_deferred = 0;
         for (int k = 0; k < 16; ++k) m.tmark[k] = 0;
         *meta = m;
     }
@@ -755,6 +757,7 @@ __global__ void __launch_bounds__(PA_THREADS, 1) sort_kernel(const SortParams p)
         m.M = 0;
         m.cur = 0;
         m.n_heavy = 0;
+        m.n_deferred = 0;
         for (int k = 0; k < 16; ++k) m.tmark[k] = s_mark[k];
         *p.meta = m;
     }
@@ -1090,7 +1093,8 @@ struct ReduceParams {
     unsigned heavy_min;     // voxels with more points than this are deferred to reduce_heavy_kernel
     int direct;             // pts / feats / cls are rows in SORTED order (sorted_rows_kernel ran): row = sorted position
     unsigned pts_stride, feat_stride, cls_stride;  // bytes from one row to the next
-    int only_deferred;      // reduce_small_kernel ran: take only the voxels it marked with out_n[v] == -1
+    int only_deferred;      // reduce_small_kernel ran: take only the voxels of its list (meta->n_deferred of them)
+    unsigned* deferred;     // that list, in no particular order
     unsigned small_max;     // voxels of at most this many points are tried by reduce_small_kernel
 };
 
@@ -1409,8 +1413,9 @@ __global__ void __launch_bounds__(RB_THREADS, 5) reduce_rec_kernel(const ReduceP
     int* cnts = s_cnts[g];
     bool overflow = false;
     const unsigned long long ngroups = (unsigned long long)gridDim.x * RB_GROUPS;
-    for (unsigned long long v = (unsigned long long)blockIdx.x * RB_GROUPS + g; v < M; v += ngroups) {
-        if (p.only_deferred && __ldcg(p.out_n + v) != -1) continue;  // reduced by reduce_small_kernel
+    const unsigned long long n_work = p.only_deferred ? (unsigned long long)p.meta->n_deferred : M;
+    for (unsigned long long w = (unsigned long long)blockIdx.x * RB_GROUPS + g; w < n_work; w += ngroups) {
+        const unsigned long long v = p.only_deferred ? (unsigned long long)__ldcg(p.deferred + w) : w;
         const unsigned long long s = p.starts[v], e = p.starts[v + 1];
         const unsigned cnt = (unsigned)(e - s);
         if (cnt > p.heavy_min) {
@@ -1510,17 +1515,18 @@ __global__ void __launch_bounds__(RS_THREADS) reduce_small_kernel(const ReducePa
     const unsigned* idx = p.idx[cur];
     const unsigned char* rec = reinterpret_cast<const unsigned char*>(p.pts);
     const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
-    for (unsigned long long v = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; v < M; v += stride) {
-        const unsigned s = p.starts[v], e = p.starts[v + 1];
+    const unsigned lane = threadIdx.x & 31;
+    // (every lane of a warp makes the same number of trips, so the warp can append its deferred voxels together)
+    for (unsigned long long vb = (unsigned long long)blockIdx.x * blockDim.x + (threadIdx.x - lane); vb < M; vb += stride) {
+        const unsigned long long v = vb + lane;
+        const bool valid = v < M;
+        const unsigned s = valid ? p.starts[v] : 0u, e = valid ? p.starts[v + 1] : 0u;
         const unsigned cnt = e - s;
-        if (cnt > p.small_max) {
-            p.out_n[v] = -1;
-            continue;
-        }
+        const bool small = valid && cnt <= p.small_max;
         float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f, a4 = 0.f, a5 = 0.f;
         int lab0 = 0;
         bool same = true;
-        for (unsigned t0 = 0; t0 < cnt; t0 += 4) {
+        for (unsigned t0 = 0; small && t0 < cnt; t0 += 4) {
             uint4 lo[4], hi[4];
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
@@ -1557,10 +1563,16 @@ __global__ void __launch_bounds__(RS_THREADS) reduce_small_kernel(const ReducePa
                 }
             }
         }
-        if (!same) {  // a vote is needed: the groups take the voxel
-            p.out_n[v] = -1;
-            continue;
+        // larger voxels, and voxels that need a vote, go to the groups: one list append per warp
+        const bool defer = valid && (!small || !same);
+        const unsigned dbal = __ballot_sync(0xffffffffu, defer);
+        if (dbal) {
+            unsigned base = 0;
+            if (lane == (unsigned)(__ffs((int)dbal) - 1)) base = atomicAdd(&p.meta->n_deferred, (unsigned)__popc(dbal));
+            base = __shfl_sync(0xffffffffu, base, __ffs((int)dbal) - 1);
+            if (defer) p.deferred[base + __popc(dbal & ((1u << lane) - 1u))] = (unsigned)v;
         }
+        if (!valid || defer) continue;
         const float a = (float)(1.0 / (double)cnt);  // grid_subsampling.cpp:87
         const float cf = (float)cnt;
         p.out_p[3ull * v] = __fmul_rn(a0, a);
@@ -1915,7 +1927,7 @@ static int run_core(Ctx* c, cudaStream_t s, const Inputs& in, size_t N, size_t f
     SSDR_TRY(c->ws[WS_IDX].reserve(N * sizeof(unsigned)));
     SSDR_TRY(c->ws[WS_IDX2].reserve(N * sizeof(unsigned)));
     SSDR_TRY(c->ws[WS_STARTS].reserve((N + 1) * sizeof(unsigned)));
-    SSDR_TRY(c->ws[WS_HEADS].reserve((N / HEAVY_MIN + 2) * sizeof(unsigned)));  // voxels left to reduce_heavy_kernel
+    SSDR_TRY(c->ws[WS_HEADS].reserve((N / HEAVY_MIN + 2 + N) * sizeof(unsigned)));  // voxels left to reduce_heavy_kernel | to the groups
     // control block: barrier counter | per-CTA partials, largest keys, counts | histogram matrix
     const size_t ctl_bytes = 256 + (size_t)G * (6 * sizeof(float) + sizeof(KeyT) + sizeof(unsigned)) + 256 +
                              (size_t)G * BINS * sizeof(unsigned) + (size_t)G * PA_WARPS * sizeof(unsigned);
@@ -1993,6 +2005,7 @@ static int run_core(Ctx* c, cudaStream_t s, const Inputs& in, size_t N, size_t f
         const unsigned blocks = (unsigned)(want < cap ? (want ? want : 1) : cap);
         rp.heavy = c->ws[WS_HEADS].as<unsigned>();
         rp.heavy_cap = (unsigned)(N / HEAVY_MIN + 1);
+        rp.deferred = rp.heavy + (N / HEAVY_MIN + 2);
         static const bool heavy_on = [] {
             const char* e = getenv("SSDR_GRID_HEAVY");  // SSDR_GRID_HEAVY=0: every voxel by its eight-lane group (A/B runs)
             return !(e && e[0] == '0');
