@@ -1502,8 +1502,8 @@ __global__ void __launch_bounds__(RB_THREADS, 5) reduce_rec_kernel(const ReduceP
 // Most voxels are small and hold one label (6.5 points per voxel in a 0.06 m scan, 9 in a 0.04 m room): ONE THREAD takes
 // such a voxel -- its records are fetched four at a time (eight independent 16-byte loads in flight), the six sums
 // stay in registers and are added in input order, no shared memory, no shuffles, all 32 lanes of a warp busy with 32
-// voxels.  A voxel with more than SMALL_MAX points or a second label is marked (out_n[v] = -1) and left to the
-// eight-lane groups of reduce_rec_kernel, which then skips everything else.
+// voxels.  A voxel with more than SMALL_MAX points or a second label is appended to a list (one atomic per warp) and
+// left to the eight-lane groups of reduce_rec_kernel, which then walk that list instead of all voxels.
 constexpr unsigned SMALL_MAX = 24;
 constexpr int RS_THREADS = 128;
 template <int REC>
