@@ -227,9 +227,10 @@ def gather_rows(rows, group=None):
     width = max(max(sizes), 1)
     padded = torch.zeros((width,) + tuple(rows.shape[1:]), dtype=rows.dtype, device=rows.device)
     padded[: rows.shape[0]] = rows
-    every = torch.empty((world, width) + tuple(rows.shape[1:]), dtype=rows.dtype, device=rows.device)
+    # (output in the concatenated form: gloo accepts no other, NCCL accepts both)
+    every = torch.empty((world * width,) + tuple(rows.shape[1:]), dtype=rows.dtype, device=rows.device)
     dist.all_gather_into_tensor(every, padded, group=group)
-    full = torch.cat([every[r, : sizes[r]] for r in range(world)])
+    full = torch.cat([every[r * width: r * width + sizes[r]] for r in range(world)])
     return full, span
 
 

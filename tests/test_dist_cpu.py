@@ -139,3 +139,42 @@ def test_slab_route_keeps_global_row_order_per_owner():
     for r in range(2):
         mask = (layers >= bounds[r]) & (layers < bounds[r + 1])
         assert np.array_equal(got[r][1], rows[mask])
+
+
+def _gather_worker(rank, world, port, sizes, out_q):
+    import torch
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    got = []
+    for case in sizes:  # rows of rank r: r * 1000 + 0, 1, ... in column 0
+        n = case[rank]
+        rows = torch.stack([torch.arange(n, dtype=torch.float32) + 1000 * rank, torch.full((n,), float(rank))], 1)
+        full, span = D.gather_rows(rows)
+        got.append((full.numpy(), span))
+    out_q.put((rank, got))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_gather_rows_of_uneven_and_empty_slabs():
+    """The slabs of a sharded subsampling differ in length and may be empty: every rank gets all rows in rank order
+    and the span of its own block (gloo takes the padded all-gather; NCCL moves each block once, unpadded)."""
+    cases = [(5, 3), (0, 4), (7, 0), (1, 1)]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_gather_worker, args=(r, 2, port, cases, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = dict(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for i, (n0, n1) in enumerate(cases):
+        want = np.concatenate([np.stack([np.arange(n0, dtype=np.float32), np.zeros(n0, np.float32)], 1),
+                               np.stack([np.arange(n1, dtype=np.float32) + 1000, np.ones(n1, np.float32)], 1)])
+        for r in range(2):
+            full, span = got[r][i]
+            assert np.array_equal(full, want)
+            assert tuple(span) == ((0, n0) if r == 0 else (n0, n0 + n1))
